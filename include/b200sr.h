@@ -1,0 +1,177 @@
+/*
+ * b200sr — C ABI of the B200-native (sm_100a) UNet slice-interpolation hot path.
+ *
+ * The reference (DeivanaiThiyagarajan/Multi-Image-Super-Resolution-for-Medical-Images) is pure
+ * Python/PyTorch and has no FFI layer: the arithmetic of its hot path lives in torch.nn modules
+ * (src/unet_model.py:22-118, :148-191). Each entry point below names the reference call site it replaces.
+ * The Python host side (package `multi-image-super-resolution-for-medical-images_b200`, import name
+ * `b200sr`) binds these with ctypes; see INTEGRATION.md for the reference-side stub.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a B200SR_E* code otherwise; b200sr_last_error() gives the text
+ *     (thread local). There is NO CPU fallback: without a CUDA device every compute entry point fails.
+ *   - all pointers are DEVICE pointers owned by the caller; the library allocates nothing on the device and
+ *     never synchronises; work is enqueued on `stream` (a cudaStream_t passed as void*).
+ *   - activations are NHWC bf16. A tensor may be a channel slot of a wider buffer, described by
+ *     (ptr, pix_stride, c_off): element (b,h,w,c) lives at ptr[((b*H+h)*W+w)*pix_stride + c_off + c].
+ *     pix_stride and c_off must be multiples of 8 (16-byte TMA / vector alignment), ptr 16-byte aligned.
+ *   - H must be a multiple of 8 and W a multiple of 16 for the tensor-core entry points; channel counts on
+ *     the tensor-core path are multiples of 64.
+ */
+#ifndef B200SR_H_
+#define B200SR_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum {
+    B200SR_OK = 0,
+    B200SR_EINVAL = 1,   /* bad shape / alignment / null pointer */
+    B200SR_ECUDA = 2,    /* CUDA runtime or driver error (text in last_error) */
+    B200SR_ENODEV = 3    /* no sm_100 device */
+};
+
+int b200sr_version(void);
+const char* b200sr_last_error(void);
+/* 0 when a compute-capability 10.x device is current, B200SR_ENODEV otherwise. */
+int b200sr_device_ok(void);
+
+/* ---- tensor-core implicit GEMMs (tcgen05 / TMEM / TMA) ------------------------------------------------ */
+
+/* nn.Conv2d(Cin, Cout, 3, padding=1) forward — unet_model.py:27,30 (inside UNetBlock) — and, with the
+ * dgrad-packed weights, its data gradient. x: (B,H,W,Cin) slot; w_packed: [Cout][9*Cin] bf16 from
+ * b200sr_pack_jobs (PACK_CONV_FWD / PACK_CONV_DGRAD); out: (B,H,W,Cout) slot, raw conv result (no bias).
+ * Optional epilogue: v = v*col_scale[c] + col_shift[c] (either may be NULL), ReLU if relu != 0 (eval-mode
+ * folded BatchNorm, unet_model.py:28-29), and per-channel sum / sum-of-squares of the stored values added
+ * into stats[(tile % stats_replicas)][2][Cout] (train-mode BatchNorm statistics; NULL to skip). */
+int b200sr_conv3x3_fwd(const void* x, int x_pix_stride, int x_c_off, int Cin, const void* w_packed, int Cout,
+                       int B, int H, int W, void* out, int out_pix_stride, int out_c_off,
+                       const float* col_scale, const float* col_shift, int relu, float* stats,
+                       int stats_replicas, void* stream);
+
+/* Same kernel; dy: (B,H,W,Cout) slot, w_packed: [Cin][9*Cout] (PACK_CONV_DGRAD), dx: (B,H,W,Cin) slot.
+ * stats (optional) receives per-channel sums of dx (used for the ConvTranspose2d bias gradient). */
+int b200sr_conv3x3_dgrad(const void* dy, int dy_pix_stride, int dy_c_off, int Cout, const void* w_packed,
+                         int Cin, int B, int H, int W, void* dx, int dx_pix_stride, int dx_c_off, float* stats,
+                         int stats_replicas, void* stream);
+
+/* nn.ConvTranspose2d(Cin, Cout, 2, stride=2) forward — unet_model.py:67,70,73,76 — as a GEMM
+ * [B*H*W, Cin] x [Cin, 4*Cout] with a pixel-shuffle scatter epilogue that writes (+bias) straight into a
+ * channel slot of the decoder's concat buffer (this replaces torch.cat, unet_model.py:101,105,109,113).
+ * x: (B,H,W,Cin) slot; w_packed: [4*Cout][Cin] (PACK_CONVT_FWD); out: (B,2H,2W,Cout) slot. */
+int b200sr_convT2x2_fwd(const void* x, int x_pix_stride, int x_c_off, int Cin, const void* w_packed, int Cout,
+                        const float* bias, int B, int H, int W, void* out, int out_pix_stride, int out_c_off,
+                        void* stream);
+
+/* ConvTranspose2d data gradient: dup: (B,2H,2W,Cout) slot, w_packed: [Cin][4*Cout] (PACK_CONVT_DGRAD),
+ * dx: (B,H,W,Cin) slot. */
+int b200sr_convT2x2_dgrad(const void* dup, int dup_pix_stride, int dup_c_off, int Cout, const void* w_packed,
+                          int Cin, int B, int H, int W, void* dx, int dx_pix_stride, int dx_c_off, void* stream);
+
+/* Conv2d 3x3 weight gradient (split-K over pixels, MN-major UMMA operands). x: (B,H,W,Cin) slot,
+ * dz: (B,H,W,Cout) slot; G: fp32 [9][Cin][Cout], ADDED into (caller zeroes it). */
+int b200sr_conv3x3_wgrad(const void* x, int x_pix_stride, int x_c_off, int Cin, const void* dz,
+                         int dz_pix_stride, int dz_c_off, int Cout, int B, int H, int W, float* G, void* stream);
+
+/* ConvTranspose2d weight gradient. dup: (B,2H,2W,Cout) slot, x: (B,H,W,Cin) slot;
+ * G: fp32 [4][Cout][Cin], ADDED into. */
+int b200sr_convT2x2_wgrad(const void* dup, int dup_pix_stride, int dup_c_off, int Cout, const void* x,
+                          int x_pix_stride, int x_c_off, int Cin, int B, int H, int W, float* G, void* stream);
+
+/* ---- bandwidth-bound kernels --------------------------------------------------------------------------- */
+
+/* Table-driven weight packing / gradient unpacking: `jobs` is a DEVICE array of b200sr_pack_job. */
+typedef struct b200sr_pack_job {
+    const void* src;
+    void* dst;
+    int32_t kind; /* 0 conv fwd, 1 conv dgrad, 2 convT fwd, 3 convT dgrad, 4 conv wgrad unpack, 5 convT wgrad unpack */
+    int32_t cout;
+    int32_t cin;
+    int32_t pad;
+    int64_t count; /* elements of dst */
+} b200sr_pack_job;
+int b200sr_pack_jobs(const b200sr_pack_job* jobs, int njobs, void* stream);
+
+typedef struct b200sr_fold_job {
+    const float* gamma;
+    const float* beta;
+    const float* running_mean;
+    const float* running_var;
+    const float* conv_bias; /* nullable */
+    float* scale;
+    float* shift;
+    int32_t C;
+    int32_t pad;
+} b200sr_fold_job;
+/* eval-mode BatchNorm fold (running stats + conv bias -> scale/shift), unet_model.py:28,31 in eval(). */
+int b200sr_bn_fold_eval(const b200sr_fold_job* jobs, int njobs, float eps, void* stream);
+
+/* First layer Conv2d(2,64,3,p=1) read directly from the fp32 NCHW network input (unet_model.py:49 -> :27).
+ * x: (B,2,H,W) f32; w: (64,2,3,3) f32 (the parameter itself); out: (B,H,W,64) bf16 dense. */
+int b200sr_conv1_fwd(const float* x, const float* w, const float* col_scale, const float* col_shift, int relu,
+                     void* out, float* stats, int stats_replicas, int B, int H, int W, void* stream);
+/* dW (64,2,3,3) f32, ADDED into. */
+int b200sr_conv1_wgrad(const float* x, const void* dz, float* dw, int B, int H, int W, void* stream);
+
+/* Train-mode nn.BatchNorm2d statistics -> scale/shift (+ saved mean/invstd, running-stat update with
+ * momentum, unbiased variance; conv_bias re-added to running_mean). unet_model.py:28,31. */
+int b200sr_bn_finalize(const float* stats, int replicas, int C, double count, const float* gamma,
+                       const float* beta, const float* conv_bias, float eps, float momentum, float* scale,
+                       float* shift, float* save_mean, float* save_invstd, float* running_mean,
+                       float* running_var, void* stream);
+
+/* BatchNorm-apply + ReLU (unet_model.py:28-29,31-32), optionally fused with MaxPool2d(2,2) (:52-61) and
+ * writing the activation into a concat slot. z: (B,H,W,C) dense raw conv output. pooled may be NULL. */
+int b200sr_bnrelu_apply(const void* z, int C, const float* scale, const float* shift, void* act,
+                        int act_pix_stride, int act_c_off, void* pooled, int B, int H, int W, void* stream);
+
+/* nn.MaxPool2d(2,2) forward / backward (unet_model.py:52,55,58,61). Backward adds the skip-connection
+ * gradient (dskip may be NULL) and routes to the first maximum in row-major window order like ATen. */
+int b200sr_maxpool2x2_fwd(const void* in, int in_pix_stride, int in_c_off, int C, void* out, int B, int H,
+                          int W, void* stream);
+int b200sr_maxpool2x2_bwd(const void* act, int act_pix_stride, int act_c_off, const void* dpool,
+                          const void* dskip, int dskip_pix_stride, int dskip_c_off, int C, void* dy, int B,
+                          int H, int W, void* stream);
+
+/* BatchNorm+ReLU backward. reduce: sums[replicas][2][C] += (sum g, sum g*xhat); finalize: c1 = S1/N,
+ * c2 = S2/N, dgamma, dbeta; apply: dz = scale*(g - c1 - xhat*c2). */
+int b200sr_bn_bwd_reduce(const void* dy, int dy_pix_stride, int dy_c_off, const void* z, int C,
+                         const float* scale, const float* shift, const float* mean, const float* invstd,
+                         float* sums, int replicas, int64_t npix, void* stream);
+int b200sr_bn_bwd_finalize(const float* sums, int replicas, int C, double count, float* c1, float* c2,
+                           float* dgamma, float* dbeta, void* stream);
+int b200sr_bn_bwd_apply(const void* dy, int dy_pix_stride, int dy_c_off, const void* z, int C,
+                        const float* scale, const float* shift, const float* mean, const float* invstd,
+                        const float* c1, const float* c2, void* dz, int64_t npix, void* stream);
+
+/* final nn.Conv2d(64,1,1) (unet_model.py:80,117): fp32 (B,1,H,W) output; and its backward. */
+int b200sr_head_fwd(const void* act, const float* w, const float* b, float* out, int64_t npix, void* stream);
+int b200sr_head_bwd(const float* dout, const void* act, const float* w, void* dact, float* dw, float* db,
+                    int64_t npix, void* stream);
+
+/* Fused MSE + windowed SSIM loss with gradient (nn.MSELoss, unet_model.py:156,180; SSIM per SURVEY §8 a11).
+ * pred/target/grad: (B,1,H,W) f32 (grad may be NULL); sums: DEVICE double[2], ADDED into:
+ * sum((x-y)^2) and sum(SSIM map). win: HOST pointer to K (<= 11) separable window taps.
+ * grad = w_mse * dMSE/dpred + w_ssim * d(1 - mean SSIM)/dpred. */
+int b200sr_mse_ssim(const float* pred, const float* target, float* grad, double* sums, int B, int H, int W,
+                    const float* win, int K, float cov_norm, float C1, float C2, float w_mse, float w_ssim,
+                    void* stream);
+
+/* torch.optim.Adam step (unet_model.py:155,185) over flat fp32 buffers; grad is multiplied by grad_scale
+ * (1/world_size after a sum all-reduce). `step` is the 1-based step count. */
+int b200sr_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1,
+                     float beta2, float eps, int64_t step, float grad_scale, void* stream);
+
+/* layout casts at the boundary */
+int b200sr_nchw_f32_to_nhwc_bf16(const float* in, void* out, int B, int C, int H, int W, void* stream);
+int b200sr_nhwc_bf16_to_nchw_f32(const void* in, int in_pix_stride, int in_c_off, float* out, int B, int C,
+                                 int H, int W, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200SR_H_ */

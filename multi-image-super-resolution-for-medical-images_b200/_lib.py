@@ -1,0 +1,109 @@
+"""ctypes binding of libb200sr.so (C ABI declared in include/b200sr.h).
+
+The library is the product: there is no Python/torch fallback for any op. If the shared object is missing the
+import of this module still succeeds (so CPU-only host logic such as state_dict handling keeps working), but the
+first call of any op raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_char_p, c_double, c_float, c_int, c_int64, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libb200sr.so")
+
+_lib = None
+_load_error = None
+
+# name -> argtypes (restype is always int unless listed in _RESTYPES)
+_P = c_void_p
+_SIGNATURES = {
+    "b200sr_version": [],
+    "b200sr_last_error": [],
+    "b200sr_device_ok": [],
+    "b200sr_conv3x3_fwd": [_P, c_int, c_int, c_int, _P, c_int, c_int, c_int, c_int, _P, c_int, c_int, _P, _P, c_int,
+                           _P, c_int, _P],
+    "b200sr_conv3x3_dgrad": [_P, c_int, c_int, c_int, _P, c_int, c_int, c_int, c_int, _P, c_int, c_int, _P, c_int,
+                             _P],
+    "b200sr_convT2x2_fwd": [_P, c_int, c_int, c_int, _P, c_int, _P, c_int, c_int, c_int, _P, c_int, c_int, _P],
+    "b200sr_convT2x2_dgrad": [_P, c_int, c_int, c_int, _P, c_int, c_int, c_int, c_int, _P, c_int, c_int, _P],
+    "b200sr_conv3x3_wgrad": [_P, c_int, c_int, c_int, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P],
+    "b200sr_convT2x2_wgrad": [_P, c_int, c_int, c_int, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P],
+    "b200sr_pack_jobs": [_P, c_int, _P],
+    "b200sr_bn_fold_eval": [_P, c_int, c_float, _P],
+    "b200sr_conv1_fwd": [_P, _P, _P, _P, c_int, _P, _P, c_int, c_int, c_int, c_int, _P],
+    "b200sr_conv1_wgrad": [_P, _P, _P, c_int, c_int, c_int, _P],
+    "b200sr_bn_finalize": [_P, c_int, c_int, c_double, _P, _P, _P, c_float, c_float, _P, _P, _P, _P, _P, _P, _P],
+    "b200sr_bnrelu_apply": [_P, c_int, _P, _P, _P, c_int, c_int, _P, c_int, c_int, c_int, _P],
+    "b200sr_maxpool2x2_fwd": [_P, c_int, c_int, c_int, _P, c_int, c_int, c_int, _P],
+    "b200sr_maxpool2x2_bwd": [_P, c_int, c_int, _P, _P, c_int, c_int, c_int, _P, c_int, c_int, c_int, _P],
+    "b200sr_bn_bwd_reduce": [_P, c_int, c_int, _P, c_int, _P, _P, _P, _P, _P, c_int, c_int64, _P],
+    "b200sr_bn_bwd_finalize": [_P, c_int, c_int, c_double, _P, _P, _P, _P, _P],
+    "b200sr_bn_bwd_apply": [_P, c_int, c_int, _P, c_int, _P, _P, _P, _P, _P, _P, _P, c_int64, _P],
+    "b200sr_head_fwd": [_P, _P, _P, _P, c_int64, _P],
+    "b200sr_head_bwd": [_P, _P, _P, _P, _P, _P, c_int64, _P],
+    "b200sr_mse_ssim": [_P, _P, _P, _P, c_int, c_int, c_int, _P, c_int, c_float, c_float, c_float, c_float, c_float,
+                        _P],
+    "b200sr_adam_step": [_P, _P, _P, _P, c_int64, c_float, c_float, c_float, c_float, c_int64, c_float, _P],
+    "b200sr_nchw_f32_to_nhwc_bf16": [_P, _P, c_int, c_int, c_int, c_int, _P],
+    "b200sr_nhwc_bf16_to_nchw_f32": [_P, c_int, c_int, _P, c_int, c_int, c_int, c_int, _P],
+}
+_RESTYPES = {"b200sr_last_error": c_char_p}
+
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+
+class B200SRError(RuntimeError):
+    pass
+
+
+def load():
+    """Load the shared library (once). Raises B200SRError if it has not been built."""
+    global _lib, _load_error
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        _load_error = (f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                       "(nvcc, sm_100a). There is no CPU/torch fallback for the b200sr hot path.")
+        raise B200SRError(_load_error)
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, argtypes in _SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError here = header/library mismatch: fail loudly
+        fn.argtypes = argtypes
+        fn.restype = _RESTYPES.get(name, c_int)
+    _lib = lib
+    return lib
+
+
+def last_error() -> str:
+    msg = load().b200sr_last_error()
+    return msg.decode() if msg else ""
+
+
+def call(name: str, *args):
+    """Call an exported op; non-zero return codes become B200SRError(last_error)."""
+    fn = getattr(load(), name)
+    rc = fn(*args)
+    if rc != 0:
+        raise B200SRError(f"{name} failed (code {rc}): {last_error()}")
+
+
+def ptr(t, elem_offset: int = 0):
+    """Device pointer of a torch tensor (or None -> NULL), optionally advanced by elements."""
+    if t is None:
+        return None
+    return t.data_ptr() + elem_offset * t.element_size()
+
+
+def current_stream_ptr():
+    import torch
+    return torch.cuda.current_stream().cuda_stream
+
+
+def require_device():
+    """Raise unless the current CUDA device is a compute-capability 10.x part."""
+    import torch
+    if not torch.cuda.is_available():
+        raise B200SRError("b200sr needs a CUDA sm_100a device; no CUDA device is available and there is no CPU path")
+    call("b200sr_device_ok")

@@ -1,0 +1,577 @@
+// C ABI of the b200sr hot path (see include/b200sr.h). Host-side argument checks, TMA descriptor cache,
+// kernel launches. No device allocation, no synchronisation, no CPU fallback.
+#include "../../include/b200sr.h"
+
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <unordered_map>
+
+#include "elementwise.cuh"
+#include "igemm.cuh"
+#include "loss.cuh"
+#include "wgrad.cuh"
+
+using namespace b200sr;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const std::string& msg) {
+    g_last_error = msg;
+    return code;
+}
+
+#define B2_CHECK_ARG(cond)                                                                      \
+    do {                                                                                        \
+        if (!(cond)) return fail(B200SR_EINVAL, std::string(__func__) + ": requirement failed: " #cond); \
+    } while (0)
+
+int check_launch(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(B200SR_ECUDA, std::string(what) + ": " + cudaGetErrorString(e));
+    return B200SR_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// driver entry point for cuTensorMapEncodeTiled (no link-time dependency on libcuda)
+// ---------------------------------------------------------------------------------------------
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    });
+    return fn;
+}
+
+struct MapKey {
+    const void* ptr;
+    uint32_t rank;
+    uint64_t dims[5];
+    uint64_t strides[4];
+    uint32_t box[5];
+    bool operator==(const MapKey& o) const { return std::memcmp(this, &o, sizeof(MapKey)) == 0; }
+};
+struct MapKeyHash {
+    size_t operator()(const MapKey& k) const {
+        const unsigned char* p = reinterpret_cast<const unsigned char*>(&k);
+        uint64_t h = 1469598103934665603ull;
+        for (size_t i = 0; i < sizeof(MapKey); ++i) {
+            h ^= p[i];
+            h *= 1099511628211ull;
+        }
+        return static_cast<size_t>(h);
+    }
+};
+
+std::mutex g_map_mutex;
+std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_map_cache;
+
+// bf16 tiled map with the 128-byte swizzle; out-of-bounds elements read as zero.
+int make_map(CUtensorMap* out, const void* ptr, uint32_t rank, const uint64_t* dims, const uint64_t* strides_bytes,
+             const uint32_t* box) {
+    MapKey key;
+    std::memset(&key, 0, sizeof(key));
+    key.ptr = ptr;
+    key.rank = rank;
+    for (uint32_t i = 0; i < rank; ++i) {
+        key.dims[i] = dims[i];
+        key.box[i] = box[i];
+        if (i + 1 < rank) key.strides[i] = strides_bytes[i];
+    }
+    {
+        std::lock_guard<std::mutex> lock(g_map_mutex);
+        auto it = g_map_cache.find(key);
+        if (it != g_map_cache.end()) {
+            *out = it->second;
+            return B200SR_OK;
+        }
+    }
+    EncodeTiledFn enc = get_encode_fn();
+    if (enc == nullptr) return fail(B200SR_ECUDA, "cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
+    cuuint64_t gdims[5];
+    cuuint64_t gstrides[4];
+    cuuint32_t gbox[5];
+    cuuint32_t estr[5];
+    for (uint32_t i = 0; i < rank; ++i) {
+        gdims[i] = dims[i];
+        gbox[i] = box[i];
+        estr[i] = 1;
+        if (i + 1 < rank) gstrides[i] = strides_bytes[i];
+    }
+    CUtensorMap m;
+    CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(ptr), gdims, gstrides, gbox, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(B200SR_ECUDA, "cuTensorMapEncodeTiled failed, CUresult=" + std::to_string(r));
+    {
+        std::lock_guard<std::mutex> lock(g_map_mutex);
+        if (g_map_cache.size() > 4096) g_map_cache.clear();
+        g_map_cache[key] = m;
+    }
+    *out = m;
+    return B200SR_OK;
+}
+
+// (B,H,W,C) channel slot viewed as a 4-D tensor (c, w, h, b)
+int make_act_map(CUtensorMap* out, const void* base, int pix_stride, int c_off, int C, int B, int H, int W, int box_w,
+                 int box_h) {
+    const __nv_bfloat16* p = static_cast<const __nv_bfloat16*>(base) + c_off;
+    const uint64_t dims[4] = {static_cast<uint64_t>(C), static_cast<uint64_t>(W), static_cast<uint64_t>(H),
+                              static_cast<uint64_t>(B)};
+    const uint64_t s = static_cast<uint64_t>(pix_stride) * 2;
+    const uint64_t strides[3] = {s, s * W, s * W * H};
+    const uint32_t box[4] = {64, static_cast<uint32_t>(box_w), static_cast<uint32_t>(box_h), 1};
+    return make_map(out, p, 4, dims, strides, box);
+}
+
+// (B,2H,2W,C) channel slot viewed as the 5-D tensor (c, j, w, i, b*H + h): sub-pixel (i,j) gather
+int make_gather_map(CUtensorMap* out, const void* base, int pix_stride, int c_off, int C, int B, int H, int W,
+                    int box_w, int box_h) {
+    const __nv_bfloat16* p = static_cast<const __nv_bfloat16*>(base) + c_off;
+    const uint64_t dims[5] = {static_cast<uint64_t>(C), 2, static_cast<uint64_t>(W), 2,
+                              static_cast<uint64_t>(B) * static_cast<uint64_t>(H)};
+    const uint64_t s = static_cast<uint64_t>(pix_stride) * 2;
+    const uint64_t strides[4] = {s, 2 * s, 2 * static_cast<uint64_t>(W) * s, 4 * static_cast<uint64_t>(W) * s};
+    const uint32_t box[5] = {64, 1, static_cast<uint32_t>(box_w), 1, static_cast<uint32_t>(box_h)};
+    return make_map(out, p, 5, dims, strides, box);
+}
+
+int make_weight_map(CUtensorMap* out, const void* w, int K_total, int N_total, int block_n) {
+    const uint64_t dims[2] = {static_cast<uint64_t>(K_total), static_cast<uint64_t>(N_total)};
+    const uint64_t strides[1] = {static_cast<uint64_t>(K_total) * 2};
+    const uint32_t box[2] = {64, static_cast<uint32_t>(block_n)};
+    return make_map(out, w, 2, dims, strides, box);
+}
+
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+int grid_for(long long total, int block, int max_blocks = 148 * 16) {
+    long long g = (total + block - 1) / block;
+    if (g < 1) g = 1;
+    if (g > max_blocks) g = max_blocks;
+    return static_cast<int>(g);
+}
+
+// ---------------------------------------------------------------------------------------------
+// igemm launch
+// ---------------------------------------------------------------------------------------------
+template <int BLOCK_N, int STAGES>
+int launch_igemm_t(const CUtensorMap& ma, const CUtensorMap& mb, const IGemmArgs& args, int grid, cudaStream_t st) {
+    constexpr int smem = ig_smem_bytes<BLOCK_N, STAGES>();
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(igemm_kernel<BLOCK_N, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             smem);
+        if (e != cudaSuccess) return fail(B200SR_ECUDA, std::string("igemm smem attribute: ") + cudaGetErrorString(e));
+        configured = true;
+    }
+    igemm_kernel<BLOCK_N, STAGES><<<grid, IG_THREADS, smem, st>>>(ma, mb, args);
+    return check_launch("igemm_kernel");
+}
+
+int pick_block_n(int n_total) {
+    const char* env = getenv("B200SR_BLOCK_N");
+    if (env != nullptr) {
+        const int v = atoi(env);
+        if ((v == 64 || v == 128 || v == 256) && n_total % v == 0) return v;
+    }
+    if (n_total % 128 == 0) return 128;
+    return 64;
+}
+
+// a_mode 0: A is (B,H,W,Ca) slot with num_taps in {1,9}; a_mode 1: A is the (B,2H,2W,Ca) slot gathered per (i,j).
+int run_igemm(int a_mode, const void* a, int a_stride, int a_coff, int Ca, int num_taps, const void* w_packed,
+              int n_total, int B, int H, int W, int epi_mode, int cout_t, void* out, int out_stride, int out_coff,
+              const float* col_scale, const float* col_shift, int relu, float* stats, int stats_replicas,
+              cudaStream_t st) {
+    B2_CHECK_ARG(a != nullptr && w_packed != nullptr && out != nullptr);
+    B2_CHECK_ARG(B > 0 && H > 0 && W > 0 && H % IG_TILE_H == 0 && W % IG_TILE_W == 0);
+    B2_CHECK_ARG(Ca % 64 == 0 && n_total % 64 == 0);
+    B2_CHECK_ARG(a_stride % 8 == 0 && a_coff % 8 == 0 && out_stride % 8 == 0 && out_coff % 8 == 0);
+    B2_CHECK_ARG(aligned16(a) && aligned16(w_packed) && aligned16(out));
+    B2_CHECK_ARG(stats == nullptr || stats_replicas > 0);
+    if (epi_mode == 1) B2_CHECK_ARG(cout_t % 32 == 0 && n_total == 4 * cout_t);
+    const int block_n = pick_block_n(n_total);
+    CUtensorMap ma, mb;
+    int rc;
+    if (a_mode == 0)
+        rc = make_act_map(&ma, a, a_stride, a_coff, Ca, B, H, W, IG_TILE_W, IG_TILE_H);
+    else
+        rc = make_gather_map(&ma, a, a_stride, a_coff, Ca, B, H, W, IG_TILE_W, IG_TILE_H);
+    if (rc) return rc;
+    rc = make_weight_map(&mb, w_packed, num_taps * Ca, n_total, block_n);
+    if (rc) return rc;
+
+    IGemmArgs args;
+    args.H = H;
+    args.W = W;
+    args.tiles_w = W / IG_TILE_W;
+    args.tiles_hw = (H / IG_TILE_H) * (W / IG_TILE_W);
+    args.a_mode = a_mode;
+    args.num_taps = num_taps;
+    args.kc_per_tap = Ca / 64;
+    args.n_total = n_total;
+    args.n_tiles = n_total / block_n;
+    args.epi_mode = epi_mode;
+    args.cout_t = cout_t;
+    args.relu = relu;
+    args.out_pix_stride = out_stride;
+    args.out_c_off = out_coff;
+    args.stats_replicas = stats_replicas > 0 ? stats_replicas : 1;
+    args.out = static_cast<__nv_bfloat16*>(out);
+    args.col_scale = col_scale;
+    args.col_shift = col_shift;
+    args.stats = stats;
+    const long long grid = static_cast<long long>(B) * args.tiles_hw * args.n_tiles;
+    B2_CHECK_ARG(grid < (1ll << 31));
+    switch (block_n) {
+        case 64:
+            return launch_igemm_t<64, 4>(ma, mb, args, static_cast<int>(grid), st);
+        case 128:
+            return launch_igemm_t<128, 3>(ma, mb, args, static_cast<int>(grid), st);
+        default:
+            return launch_igemm_t<256, 4>(ma, mb, args, static_cast<int>(grid), st);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// wgrad launch
+// ---------------------------------------------------------------------------------------------
+template <int N_TILE, int STAGES>
+int launch_wgrad_t(const CUtensorMap& mt, const CUtensorMap& mp, WGradArgs& args, cudaStream_t st) {
+    constexpr int smem = wg_smem_bytes<N_TILE, STAGES>();
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e =
+            cudaFuncSetAttribute(wgrad_kernel<N_TILE, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return fail(B200SR_ECUDA, std::string("wgrad smem attribute: ") + cudaGetErrorString(e));
+        configured = true;
+    }
+    constexpr int AT = wg_atoms_per_cta<N_TILE>();
+    const int groups_x = (args.total_atoms + AT - 1) / AT;
+    const int groups_y = args.n_total / N_TILE;
+    const int groups = groups_x * groups_y;
+    int target = 296;  // two waves of 148 SMs
+    if (const char* env = getenv("B200SR_WGRAD_CTAS")) target = atoi(env) > 0 ? atoi(env) : target;
+    int splits = groups >= target ? 1 : (target + groups - 1) / groups;
+    if (splits > args.total_chunks) splits = args.total_chunks;
+    args.chunks_per_cta = (args.total_chunks + splits - 1) / splits;
+    splits = (args.total_chunks + args.chunks_per_cta - 1) / args.chunks_per_cta;
+    dim3 grid(groups_x, groups_y, splits);
+    wgrad_kernel<N_TILE, STAGES><<<grid, WG_THREADS, smem, st>>>(mt, mp, args);
+    return check_launch("wgrad_kernel");
+}
+
+// t_mode 0: T = (B,H,W,Ct) slot, taps in {1,9}; t_mode 1: T = (B,2H,2W,Ct) slot gathered (4 taps). P = (B,H,W,Cp).
+int run_wgrad(int t_mode, const void* t, int t_stride, int t_coff, int Ct, int num_taps, const void* p, int p_stride,
+              int p_coff, int Cp, int B, int H, int W, float* G, cudaStream_t st) {
+    B2_CHECK_ARG(t != nullptr && p != nullptr && G != nullptr);
+    B2_CHECK_ARG(B > 0 && H > 0 && W > 0 && H % 2 == 0 && W % 16 == 0);
+    B2_CHECK_ARG(Ct % 64 == 0 && Cp % 64 == 0);
+    B2_CHECK_ARG(t_stride % 8 == 0 && t_coff % 8 == 0 && p_stride % 8 == 0 && p_coff % 8 == 0);
+    B2_CHECK_ARG(aligned16(t) && aligned16(p) && aligned16(G));
+    CUtensorMap mt, mp;
+    int rc;
+    if (t_mode == 0)
+        rc = make_act_map(&mt, t, t_stride, t_coff, Ct, B, H, W, 16, 2);
+    else
+        rc = make_gather_map(&mt, t, t_stride, t_coff, Ct, B, H, W, 16, 2);
+    if (rc) return rc;
+    rc = make_act_map(&mp, p, p_stride, p_coff, Cp, B, H, W, 16, 2);
+    if (rc) return rc;
+    WGradArgs args;
+    args.H = H;
+    args.W = W;
+    args.chunks_w = W / 16;
+    args.chunks_hw = (H / 2) * (W / 16);
+    args.total_chunks = B * args.chunks_hw;
+    args.chunks_per_cta = args.total_chunks;
+    args.t_mode = t_mode;
+    args.num_taps = num_taps;
+    args.tchunks_per_tap = Ct / 64;
+    args.total_atoms = num_taps * (Ct / 64);
+    args.n_total = Cp;
+    args.out = G;
+    if (Cp % 256 == 0) return launch_wgrad_t<256, 6>(mt, mp, args, st);
+    if (Cp % 128 == 0) return launch_wgrad_t<128, 5>(mt, mp, args, st);
+    return launch_wgrad_t<64, 3>(mt, mp, args, st);
+}
+
+}  // namespace
+
+// =================================================================================================
+// exported C ABI
+// =================================================================================================
+extern "C" {
+
+int b200sr_version(void) { return 100; }
+
+const char* b200sr_last_error(void) { return g_last_error.c_str(); }
+
+int b200sr_device_ok(void) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(B200SR_ENODEV, "no CUDA device");
+    }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(B200SR_ENODEV, "cudaGetDeviceProperties failed");
+    }
+    if (prop.major != 10) return fail(B200SR_ENODEV, "device is not compute capability 10.x (sm_100a required)");
+    return B200SR_OK;
+}
+
+int b200sr_conv3x3_fwd(const void* x, int x_pix_stride, int x_c_off, int Cin, const void* w_packed, int Cout, int B,
+                       int H, int W, void* out, int out_pix_stride, int out_c_off, const float* col_scale,
+                       const float* col_shift, int relu, float* stats, int stats_replicas, void* stream) {
+    return run_igemm(0, x, x_pix_stride, x_c_off, Cin, 9, w_packed, Cout, B, H, W, 0, Cout, out, out_pix_stride,
+                     out_c_off, col_scale, col_shift, relu, stats, stats_replicas, static_cast<cudaStream_t>(stream));
+}
+
+int b200sr_conv3x3_dgrad(const void* dy, int dy_pix_stride, int dy_c_off, int Cout, const void* w_packed, int Cin,
+                         int B, int H, int W, void* dx, int dx_pix_stride, int dx_c_off, float* stats,
+                         int stats_replicas, void* stream) {
+    return run_igemm(0, dy, dy_pix_stride, dy_c_off, Cout, 9, w_packed, Cin, B, H, W, 0, Cin, dx, dx_pix_stride,
+                     dx_c_off, nullptr, nullptr, 0, stats, stats_replicas, static_cast<cudaStream_t>(stream));
+}
+
+int b200sr_convT2x2_fwd(const void* x, int x_pix_stride, int x_c_off, int Cin, const void* w_packed, int Cout,
+                        const float* bias, int B, int H, int W, void* out, int out_pix_stride, int out_c_off,
+                        void* stream) {
+    return run_igemm(0, x, x_pix_stride, x_c_off, Cin, 1, w_packed, 4 * Cout, B, H, W, 1, Cout, out, out_pix_stride,
+                     out_c_off, nullptr, bias, 0, nullptr, 0, static_cast<cudaStream_t>(stream));
+}
+
+int b200sr_convT2x2_dgrad(const void* dup, int dup_pix_stride, int dup_c_off, int Cout, const void* w_packed, int Cin,
+                          int B, int H, int W, void* dx, int dx_pix_stride, int dx_c_off, void* stream) {
+    return run_igemm(1, dup, dup_pix_stride, dup_c_off, Cout, 4, w_packed, Cin, B, H, W, 0, Cin, dx, dx_pix_stride,
+                     dx_c_off, nullptr, nullptr, 0, nullptr, 0, static_cast<cudaStream_t>(stream));
+}
+
+int b200sr_conv3x3_wgrad(const void* x, int x_pix_stride, int x_c_off, int Cin, const void* dz, int dz_pix_stride,
+                         int dz_c_off, int Cout, int B, int H, int W, float* G, void* stream) {
+    return run_wgrad(0, x, x_pix_stride, x_c_off, Cin, 9, dz, dz_pix_stride, dz_c_off, Cout, B, H, W, G,
+                     static_cast<cudaStream_t>(stream));
+}
+
+int b200sr_convT2x2_wgrad(const void* dup, int dup_pix_stride, int dup_c_off, int Cout, const void* x,
+                          int x_pix_stride, int x_c_off, int Cin, int B, int H, int W, float* G, void* stream) {
+    return run_wgrad(1, dup, dup_pix_stride, dup_c_off, Cout, 4, x, x_pix_stride, x_c_off, Cin, B, H, W, G,
+                     static_cast<cudaStream_t>(stream));
+}
+
+int b200sr_pack_jobs(const b200sr_pack_job* jobs, int njobs, void* stream) {
+    B2_CHECK_ARG(jobs != nullptr && njobs > 0);
+    static_assert(sizeof(b200sr_pack_job) == sizeof(PackJob), "PackJob ABI mismatch");
+    dim3 grid(296, njobs);
+    pack_jobs_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const PackJob*>(jobs));
+    return check_launch("pack_jobs_kernel");
+}
+
+int b200sr_bn_fold_eval(const b200sr_fold_job* jobs, int njobs, float eps, void* stream) {
+    B2_CHECK_ARG(jobs != nullptr && njobs > 0);
+    static_assert(sizeof(b200sr_fold_job) == sizeof(FoldJob), "FoldJob ABI mismatch");
+    dim3 grid(4, njobs);
+    bn_fold_eval_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const FoldJob*>(jobs),
+                                                                             eps);
+    return check_launch("bn_fold_eval_kernel");
+}
+
+int b200sr_conv1_fwd(const float* x, const float* w, const float* col_scale, const float* col_shift, int relu,
+                     void* out, float* stats, int stats_replicas, int B, int H, int W, void* stream) {
+    B2_CHECK_ARG(x != nullptr && w != nullptr && out != nullptr);
+    B2_CHECK_ARG(B > 0 && H % C1_TILE == 0 && W % C1_TILE == 0);
+    B2_CHECK_ARG((col_scale == nullptr) == (col_shift == nullptr));
+    B2_CHECK_ARG(stats == nullptr || stats_replicas > 0);
+    B2_CHECK_ARG(aligned16(out));
+    const int grid = B * (H / C1_TILE) * (W / C1_TILE);
+    conv1_direct_fwd_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        x, w, col_scale, col_shift, relu, static_cast<__nv_bfloat16*>(out), stats, stats_replicas > 0 ? stats_replicas : 1,
+        H, W);
+    return check_launch("conv1_direct_fwd_kernel");
+}
+
+int b200sr_conv1_wgrad(const float* x, const void* dz, float* dw, int B, int H, int W, void* stream) {
+    B2_CHECK_ARG(x != nullptr && dz != nullptr && dw != nullptr);
+    B2_CHECK_ARG(B > 0 && H % C1_TILE == 0 && W % C1_TILE == 0 && aligned16(dz));
+    const int tiles = B * (H / C1_TILE) * (W / C1_TILE);
+    const int grid = tiles < 148 * 4 ? tiles : 148 * 4;
+    conv1_direct_wgrad_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        x, static_cast<const __nv_bfloat16*>(dz), dw, H, W, tiles);
+    return check_launch("conv1_direct_wgrad_kernel");
+}
+
+int b200sr_bn_finalize(const float* stats, int replicas, int C, double count, const float* gamma, const float* beta,
+                       const float* conv_bias, float eps, float momentum, float* scale, float* shift, float* save_mean,
+                       float* save_invstd, float* running_mean, float* running_var, void* stream) {
+    B2_CHECK_ARG(stats && gamma && beta && scale && shift && save_mean && save_invstd);
+    B2_CHECK_ARG(replicas > 0 && C > 0 && count > 1.0);
+    B2_CHECK_ARG((running_mean == nullptr) == (running_var == nullptr));
+    bn_finalize_kernel<<<(C + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+        stats, replicas, C, static_cast<float>(count), gamma, beta, conv_bias, eps, momentum, scale, shift, save_mean,
+        save_invstd, running_mean, running_var);
+    return check_launch("bn_finalize_kernel");
+}
+
+int b200sr_bnrelu_apply(const void* z, int C, const float* scale, const float* shift, void* act, int act_pix_stride,
+                        int act_c_off, void* pooled, int B, int H, int W, void* stream) {
+    B2_CHECK_ARG(z && scale && shift && act);
+    B2_CHECK_ARG(C % 8 == 0 && act_pix_stride % 8 == 0 && act_c_off % 8 == 0 && H % 2 == 0 && W % 2 == 0);
+    B2_CHECK_ARG(aligned16(z) && aligned16(act) && (pooled == nullptr || aligned16(pooled)));
+    const long long total = static_cast<long long>(B) * (H / 2) * (W / 2) * (C / 8);
+    bnrelu_apply_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16*>(z), C, scale, shift, static_cast<__nv_bfloat16*>(act), act_pix_stride,
+        act_c_off, static_cast<__nv_bfloat16*>(pooled), H, W, total);
+    return check_launch("bnrelu_apply_kernel");
+}
+
+int b200sr_maxpool2x2_fwd(const void* in, int in_pix_stride, int in_c_off, int C, void* out, int B, int H, int W,
+                          void* stream) {
+    B2_CHECK_ARG(in && out && C % 8 == 0 && in_pix_stride % 8 == 0 && in_c_off % 8 == 0 && H % 2 == 0 && W % 2 == 0);
+    B2_CHECK_ARG(aligned16(in) && aligned16(out));
+    const long long total = static_cast<long long>(B) * (H / 2) * (W / 2) * (C / 8);
+    maxpool2x2_fwd_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16*>(in), in_pix_stride, in_c_off, C, static_cast<__nv_bfloat16*>(out), H, W,
+        total);
+    return check_launch("maxpool2x2_fwd_kernel");
+}
+
+int b200sr_maxpool2x2_bwd(const void* act, int act_pix_stride, int act_c_off, const void* dpool, const void* dskip,
+                          int dskip_pix_stride, int dskip_c_off, int C, void* dy, int B, int H, int W, void* stream) {
+    B2_CHECK_ARG(act && dpool && dy && C % 8 == 0 && act_pix_stride % 8 == 0 && act_c_off % 8 == 0);
+    B2_CHECK_ARG(dskip == nullptr || (dskip_pix_stride % 8 == 0 && dskip_c_off % 8 == 0 && aligned16(dskip)));
+    B2_CHECK_ARG(H % 2 == 0 && W % 2 == 0 && aligned16(act) && aligned16(dpool) && aligned16(dy));
+    const long long total = static_cast<long long>(B) * (H / 2) * (W / 2) * (C / 8);
+    maxpool2x2_bwd_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16*>(act), act_pix_stride, act_c_off, static_cast<const __nv_bfloat16*>(dpool),
+        static_cast<const __nv_bfloat16*>(dskip), dskip_pix_stride, dskip_c_off, C, static_cast<__nv_bfloat16*>(dy), H,
+        W, total);
+    return check_launch("maxpool2x2_bwd_kernel");
+}
+
+int b200sr_bn_bwd_reduce(const void* dy, int dy_pix_stride, int dy_c_off, const void* z, int C, const float* scale,
+                         const float* shift, const float* mean, const float* invstd, float* sums, int replicas,
+                         int64_t npix, void* stream) {
+    B2_CHECK_ARG(dy && z && scale && shift && mean && invstd && sums);
+    B2_CHECK_ARG(C % 64 == 0 && dy_pix_stride % 8 == 0 && dy_c_off % 8 == 0 && replicas > 0 && npix > 0);
+    B2_CHECK_ARG(aligned16(dy) && aligned16(z));
+    const int cg = C / 64;
+    long long slices = (npix + 32 * 8 - 1) / (32 * 8);  // >= 8 pixels per thread row
+    const long long max_slices = (148 * 8 + cg - 1) / cg;
+    if (slices > max_slices) slices = max_slices;
+    if (slices < 1) slices = 1;
+    bn_bwd_reduce_kernel<<<static_cast<int>(slices) * cg, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16*>(dy), dy_pix_stride, dy_c_off, static_cast<const __nv_bfloat16*>(z), C, scale,
+        shift, mean, invstd, sums, replicas, npix);
+    return check_launch("bn_bwd_reduce_kernel");
+}
+
+int b200sr_bn_bwd_finalize(const float* sums, int replicas, int C, double count, float* c1, float* c2, float* dgamma,
+                           float* dbeta, void* stream) {
+    B2_CHECK_ARG(sums && c1 && c2 && dgamma && dbeta && replicas > 0 && C > 0 && count > 0);
+    bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+        sums, replicas, C, static_cast<float>(count), c1, c2, dgamma, dbeta);
+    return check_launch("bn_bwd_finalize_kernel");
+}
+
+int b200sr_bn_bwd_apply(const void* dy, int dy_pix_stride, int dy_c_off, const void* z, int C, const float* scale,
+                        const float* shift, const float* mean, const float* invstd, const float* c1, const float* c2,
+                        void* dz, int64_t npix, void* stream) {
+    B2_CHECK_ARG(dy && z && scale && shift && mean && invstd && c1 && c2 && dz);
+    B2_CHECK_ARG(C % 8 == 0 && dy_pix_stride % 8 == 0 && dy_c_off % 8 == 0 && npix > 0);
+    B2_CHECK_ARG(aligned16(dy) && aligned16(z) && aligned16(dz));
+    const long long total = npix * (C / 8);
+    bn_bwd_apply_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16*>(dy), dy_pix_stride, dy_c_off, static_cast<const __nv_bfloat16*>(z), C, scale,
+        shift, mean, invstd, c1, c2, static_cast<__nv_bfloat16*>(dz), total);
+    return check_launch("bn_bwd_apply_kernel");
+}
+
+int b200sr_head_fwd(const void* act, const float* w, const float* b, float* out, int64_t npix, void* stream) {
+    B2_CHECK_ARG(act && w && b && out && npix > 0 && aligned16(act) && aligned16(w));
+    head_fwd_kernel<<<grid_for(npix * 8, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16*>(act), w, b, out, npix);
+    return check_launch("head_fwd_kernel");
+}
+
+int b200sr_head_bwd(const float* dout, const void* act, const float* w, void* dact, float* dw, float* db,
+                    int64_t npix, void* stream) {
+    B2_CHECK_ARG(dout && act && w && dact && dw && db && npix > 0 && aligned16(act) && aligned16(dact) && aligned16(w));
+    head_bwd_kernel<<<grid_for(npix * 8, 256, 148 * 4), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        dout, static_cast<const __nv_bfloat16*>(act), w, static_cast<__nv_bfloat16*>(dact), dw, db, npix);
+    return check_launch("head_bwd_kernel");
+}
+
+int b200sr_mse_ssim(const float* pred, const float* target, float* grad, double* sums, int B, int H, int W,
+                    const float* win, int K, float cov_norm, float C1, float C2, float w_mse, float w_ssim,
+                    void* stream) {
+    B2_CHECK_ARG(pred && target && sums && win);
+    B2_CHECK_ARG(B > 0 && K >= 1 && K <= LS_KMAX && H >= K && W >= K);
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(mse_ssim_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LS_SMEM_BYTES);
+        if (e != cudaSuccess) return fail(B200SR_ECUDA, std::string("mse_ssim smem attribute: ") + cudaGetErrorString(e));
+        configured = true;
+    }
+    LossArgs a;
+    a.pred = pred;
+    a.target = target;
+    a.grad = grad;
+    a.sums = sums;
+    a.H = H;
+    a.W = W;
+    a.K = K;
+    for (int i = 0; i < LS_KMAX; ++i) a.win[i] = i < K ? win[i] : 0.f;
+    a.cov_norm = cov_norm;
+    a.C1 = C1;
+    a.C2 = C2;
+    a.g_mse = static_cast<float>(static_cast<double>(w_mse) * 2.0 / (static_cast<double>(B) * H * W));
+    a.g_ssim = static_cast<float>(-static_cast<double>(w_ssim) /
+                                  (static_cast<double>(B) * (H - K + 1) * static_cast<double>(W - K + 1)));
+    const int grid = B * ((H + LS_T - 1) / LS_T) * ((W + LS_T - 1) / LS_T);
+    mse_ssim_kernel<<<grid, 256, LS_SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(a);
+    return check_launch("mse_ssim_kernel");
+}
+
+int b200sr_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
+                     float eps, int64_t step, float grad_scale, void* stream) {
+    B2_CHECK_ARG(p && g && m && v && n > 0 && step >= 1);
+    B2_CHECK_ARG(aligned16(p) && aligned16(g) && aligned16(m) && aligned16(v));
+    const double bc1 = 1.0 - pow(static_cast<double>(beta1), static_cast<double>(step));
+    const double bc2 = 1.0 - pow(static_cast<double>(beta2), static_cast<double>(step));
+    adam_flat_kernel<<<grid_for((n + 3) / 4, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        p, g, m, v, n, lr, beta1, beta2, eps, static_cast<float>(bc1), static_cast<float>(sqrt(bc2)), grad_scale);
+    return check_launch("adam_flat_kernel");
+}
+
+int b200sr_nchw_f32_to_nhwc_bf16(const float* in, void* out, int B, int C, int H, int W, void* stream) {
+    B2_CHECK_ARG(in && out && B > 0 && C > 0 && H > 0 && W > 0);
+    const long long total = static_cast<long long>(B) * C * H * W;
+    nchw_f32_to_nhwc_bf16_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        in, static_cast<__nv_bfloat16*>(out), C, H * W, total);
+    return check_launch("nchw_f32_to_nhwc_bf16_kernel");
+}
+
+int b200sr_nhwc_bf16_to_nchw_f32(const void* in, int in_pix_stride, int in_c_off, float* out, int B, int C, int H,
+                                 int W, void* stream) {
+    B2_CHECK_ARG(in && out && B > 0 && C > 0 && H > 0 && W > 0);
+    const long long total = static_cast<long long>(B) * C * H * W;
+    nhwc_bf16_to_nchw_f32_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16*>(in), in_pix_stride, in_c_off, out, C, H * W, total);
+    return check_launch("nhwc_bf16_to_nchw_f32_kernel");
+}
+
+}  // extern "C"

@@ -1,0 +1,699 @@
+// Bandwidth-bound kernels of the UNet hot path: everything that is not a tensor-core GEMM.
+// All activations are NHWC bf16; a tensor may live in a channel slot of a wider buffer, described by
+// (base pointer, pixel stride in elements, first channel). 16-byte vector accesses (8 bf16) throughout.
+#pragma once
+#include "ptx.cuh"
+
+namespace b200sr {
+
+// ------------------------------------------------------------------------------------------------
+// vector helpers
+// ------------------------------------------------------------------------------------------------
+struct F8 {
+    float v[8];
+};
+
+__device__ __forceinline__ F8 ld_bf16x8(const __nv_bfloat16* p) {
+    const uint4 u = *reinterpret_cast<const uint4*>(p);
+    F8 r;
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        r.v[2 * i] = __low2float(h[i]);
+        r.v[2 * i + 1] = __high2float(h[i]);
+    }
+    return r;
+}
+
+__device__ __forceinline__ void st_bf16x8(__nv_bfloat16* p, const F8& r) {
+    uint4 u;
+    u.x = pack_bf16x2(r.v[0], r.v[1]);
+    u.y = pack_bf16x2(r.v[2], r.v[3]);
+    u.z = pack_bf16x2(r.v[4], r.v[5]);
+    u.w = pack_bf16x2(r.v[6], r.v[7]);
+    *reinterpret_cast<uint4*>(p) = u;
+}
+
+__device__ __forceinline__ F8 ld_f32x8(const float* p) {
+    const float4 a = *reinterpret_cast<const float4*>(p);
+    const float4 b = *reinterpret_cast<const float4*>(p + 4);
+    F8 r;
+    r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
+    r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+    return r;
+}
+
+__device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+
+// ------------------------------------------------------------------------------------------------
+// weight packing / gradient unpacking (table driven: one launch for the whole network)
+// ------------------------------------------------------------------------------------------------
+enum PackKind : int {
+    PACK_CONV_FWD = 0,     // (Cout,Cin,3,3) f32 -> [Cout][tap*Cin + ci] bf16
+    PACK_CONV_DGRAD = 1,   // (Cout,Cin,3,3) f32 -> [Cin][tap'*Cout + co] bf16, tap' = rotated tap
+    PACK_CONVT_FWD = 2,    // (Cin,Cout,2,2) f32 -> [(i*2+j)*Cout + co][ci] bf16
+    PACK_CONVT_DGRAD = 3,  // (Cin,Cout,2,2) f32 -> [ci][(i*2+j)*Cout + co] bf16
+    UNPACK_CONV_WGRAD = 4,   // G[tap][ci][co] f32 -> (Cout,Cin,3,3) f32
+    UNPACK_CONVT_WGRAD = 5,  // G[(i,j)][co][ci] f32 -> (Cin,Cout,2,2) f32
+};
+
+struct PackJob {
+    const void* src;
+    void* dst;
+    int kind;
+    int cout;
+    int cin;
+    int pad;
+    long long count;  // elements of dst
+};
+
+__global__ void pack_jobs_kernel(const PackJob* __restrict__ jobs) {
+    const PackJob job = jobs[blockIdx.y];
+    const int Cout = job.cout, Cin = job.cin;
+    for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < job.count;
+         idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+        switch (job.kind) {
+            case PACK_CONV_FWD: {
+                const int ci = idx % Cin;
+                const int t = (idx / Cin) % 9;
+                const int co = idx / (9LL * Cin);
+                const float v = static_cast<const float*>(job.src)[(static_cast<long long>(co) * Cin + ci) * 9 + t];
+                static_cast<__nv_bfloat16*>(job.dst)[idx] = __float2bfloat16_rn(v);
+                break;
+            }
+            case PACK_CONV_DGRAD: {
+                const int co = idx % Cout;
+                const int t = (idx / Cout) % 9;
+                const int ci = idx / (9LL * Cout);
+                // tap' with offset (dh,dw) = (t/3-1, t%3-1) multiplies W[co][ci][1-dh][1-dw]
+                const int kh = 2 - t / 3, kw = 2 - t % 3;
+                const float v =
+                    static_cast<const float*>(job.src)[(static_cast<long long>(co) * Cin + ci) * 9 + kh * 3 + kw];
+                static_cast<__nv_bfloat16*>(job.dst)[idx] = __float2bfloat16_rn(v);
+                break;
+            }
+            case PACK_CONVT_FWD: {
+                const int ci = idx % Cin;
+                const int co = (idx / Cin) % Cout;
+                const int ij = idx / (static_cast<long long>(Cin) * Cout);
+                const float v = static_cast<const float*>(job.src)[(static_cast<long long>(ci) * Cout + co) * 4 + ij];
+                static_cast<__nv_bfloat16*>(job.dst)[idx] = __float2bfloat16_rn(v);
+                break;
+            }
+            case PACK_CONVT_DGRAD: {
+                const int co = idx % Cout;
+                const int ij = (idx / Cout) % 4;
+                const int ci = idx / (4LL * Cout);
+                const float v = static_cast<const float*>(job.src)[(static_cast<long long>(ci) * Cout + co) * 4 + ij];
+                static_cast<__nv_bfloat16*>(job.dst)[idx] = __float2bfloat16_rn(v);
+                break;
+            }
+            case UNPACK_CONV_WGRAD: {
+                const int t = idx % 9;
+                const int ci = (idx / 9) % Cin;
+                const int co = idx / (9LL * Cin);
+                static_cast<float*>(job.dst)[idx] =
+                    static_cast<const float*>(job.src)[(static_cast<long long>(t) * Cin + ci) * Cout + co];
+                break;
+            }
+            case UNPACK_CONVT_WGRAD: {
+                const int ij = idx % 4;
+                const int co = (idx / 4) % Cout;
+                const int ci = idx / (4LL * Cout);
+                static_cast<float*>(job.dst)[idx] =
+                    static_cast<const float*>(job.src)[(static_cast<long long>(ij) * Cout + co) * Cin + ci];
+                break;
+            }
+            default:
+                break;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// first layer: Conv2d(2 -> 64, 3x3, p1) straight from the fp32 NCHW network input (K = 18: memory bound,
+// CUDA cores). Reference: unet_model.py:27 as instantiated by UNet.enc1 (:49).
+// One thread = one pixel x 64 output channels; a 16x16 pixel tile per block with an 18x18x2 halo in smem.
+// ------------------------------------------------------------------------------------------------
+constexpr int C1_TILE = 16;
+constexpr int C1_COUT = 64;
+
+__global__ void __launch_bounds__(256) conv1_direct_fwd_kernel(const float* __restrict__ x,      // [B][2][H][W]
+                                                               const float* __restrict__ wgt,    // [64][2][3][3]
+                                                               const float* __restrict__ col_scale,
+                                                               const float* __restrict__ col_shift, int relu,
+                                                               __nv_bfloat16* __restrict__ out,  // [B][H][W][64]
+                                                               float* __restrict__ stats, int stats_replicas,
+                                                               int H, int W) {
+    __shared__ float s_x[2][C1_TILE + 2][C1_TILE + 2];
+    __shared__ float s_w[18][C1_COUT];  // [ci*9 + tap][co]
+    __shared__ float s_stats[2][C1_COUT];
+    const int tid = threadIdx.x;
+    const int tiles_w = W / C1_TILE;
+    const int tiles_hw = tiles_w * (H / C1_TILE);
+    const int img = blockIdx.x / tiles_hw;
+    const int t_in = blockIdx.x - img * tiles_hw;
+    const int h0 = (t_in / tiles_w) * C1_TILE, w0 = (t_in % tiles_w) * C1_TILE;
+
+    for (int i = tid; i < 18 * C1_COUT; i += 256) {
+        const int co = i % C1_COUT, k = i / C1_COUT;
+        s_w[k][co] = wgt[co * 18 + k];
+    }
+    if (tid < 2 * C1_COUT) (&s_stats[0][0])[tid] = 0.f;
+    for (int i = tid; i < 2 * (C1_TILE + 2) * (C1_TILE + 2); i += 256) {
+        const int ci = i / ((C1_TILE + 2) * (C1_TILE + 2));
+        const int r = i % ((C1_TILE + 2) * (C1_TILE + 2));
+        const int hh = h0 + r / (C1_TILE + 2) - 1, ww = w0 + r % (C1_TILE + 2) - 1;
+        float v = 0.f;
+        if (hh >= 0 && hh < H && ww >= 0 && ww < W) v = x[((static_cast<size_t>(img) * 2 + ci) * H + hh) * W + ww];
+        s_x[ci][r / (C1_TILE + 2)][r % (C1_TILE + 2)] = v;
+    }
+    __syncthreads();
+
+    const int ph = tid / C1_TILE, pw = tid % C1_TILE;
+    float in[18];
+#pragma unroll
+    for (int ci = 0; ci < 2; ++ci)
+#pragma unroll
+        for (int t = 0; t < 9; ++t) in[ci * 9 + t] = s_x[ci][ph + t / 3][pw + t % 3];
+
+    __nv_bfloat16* dst = out + ((static_cast<size_t>(img) * H + h0 + ph) * W + w0 + pw) * C1_COUT;
+    const uint32_t lane = tid & 31;
+#pragma unroll 1
+    for (int cb = 0; cb < C1_COUT; cb += 32) {
+        float acc[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc[j] = 0.f;
+#pragma unroll
+        for (int k = 0; k < 18; ++k) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) acc[j] = fmaf(in[k], s_w[k][cb + j], acc[j]);
+        }
+        if (col_scale != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) acc[j] = fmaf(acc[j], col_scale[cb + j], col_shift[cb + j]);
+        }
+        if (relu) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) acc[j] = fmaxf(acc[j], 0.f);
+        }
+        uint32_t packed[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) packed[j] = pack_bf16x2(acc[2 * j], acc[2 * j + 1]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            reinterpret_cast<uint4*>(dst + cb)[j] =
+                make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+        if (stats != nullptr) {
+            float s1[32], s2[32];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const __nv_bfloat162 hh = *reinterpret_cast<const __nv_bfloat162*>(&packed[j]);
+                const float a = __low2float(hh), b = __high2float(hh);
+                s1[2 * j] = a; s1[2 * j + 1] = b;
+                s2[2 * j] = a * a; s2[2 * j + 1] = b * b;
+            }
+            const float cs = warp_transpose_reduce32(s1, lane);
+            const float cq = warp_transpose_reduce32(s2, lane);
+            atomicAdd(&s_stats[0][cb + lane], cs);
+            atomicAdd(&s_stats[1][cb + lane], cq);
+        }
+    }
+    if (stats != nullptr) {
+        __syncthreads();
+        float* d = stats + static_cast<size_t>(blockIdx.x % stats_replicas) * 2 * C1_COUT;
+        if (tid < 2 * C1_COUT) atomicAdd(d + tid, (&s_stats[0][0])[tid]);
+    }
+}
+
+// wgrad of the first layer: dW[co][ci][kh][kw] = sum_q dZ[q][co] * x[q + (kh-1, kw-1)][ci]
+// Persistent blocks (grid-stride over 16x16 tiles), register accumulation, one atomic flush per block.
+__global__ void __launch_bounds__(256) conv1_direct_wgrad_kernel(const float* __restrict__ x,             // [B][2][H][W]
+                                                                 const __nv_bfloat16* __restrict__ dz,   // [B][H][W][64]
+                                                                 float* __restrict__ dw,                  // [64][2][3][3]
+                                                                 int H, int W, int num_tiles) {
+    __shared__ float s_x[2][C1_TILE + 2][C1_TILE + 2];
+    __shared__ __nv_bfloat16 s_dz[C1_TILE * C1_TILE][C1_COUT + 8];  // +8: rows 144 B apart
+    const int tid = threadIdx.x;
+    const int co = tid & 63;
+    const int sub = tid >> 6;  // 4 pixel subsets of 64 pixels
+    const int tiles_w = W / C1_TILE;
+    const int tiles_hw = tiles_w * (H / C1_TILE);
+    float acc[18];
+#pragma unroll
+    for (int k = 0; k < 18; ++k) acc[k] = 0.f;
+
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int img = tile / tiles_hw;
+        const int t_in = tile - img * tiles_hw;
+        const int h0 = (t_in / tiles_w) * C1_TILE, w0 = (t_in % tiles_w) * C1_TILE;
+        __syncthreads();
+        for (int i = tid; i < 2 * (C1_TILE + 2) * (C1_TILE + 2); i += 256) {
+            const int ci = i / ((C1_TILE + 2) * (C1_TILE + 2));
+            const int r = i % ((C1_TILE + 2) * (C1_TILE + 2));
+            const int hh = h0 + r / (C1_TILE + 2) - 1, ww = w0 + r % (C1_TILE + 2) - 1;
+            float v = 0.f;
+            if (hh >= 0 && hh < H && ww >= 0 && ww < W) v = x[((static_cast<size_t>(img) * 2 + ci) * H + hh) * W + ww];
+            s_x[ci][r / (C1_TILE + 2)][r % (C1_TILE + 2)] = v;
+        }
+        // 256 pixels x 64 ch bf16 = 2048 uint4
+        for (int i = tid; i < C1_TILE * C1_TILE * 8; i += 256) {
+            const int p = i >> 3, c8 = i & 7;
+            const int hh = h0 + p / C1_TILE, ww = w0 + p % C1_TILE;
+            const uint4 u =
+                *reinterpret_cast<const uint4*>(dz + ((static_cast<size_t>(img) * H + hh) * W + ww) * C1_COUT + c8 * 8);
+            *reinterpret_cast<uint4*>(&s_dz[p][c8 * 8]) = u;
+        }
+        __syncthreads();
+        for (int p = sub * 64; p < sub * 64 + 64; ++p) {
+            const float g = __bfloat162float(s_dz[p][co]);
+            const int ph = p / C1_TILE, pw = p % C1_TILE;
+#pragma unroll
+            for (int ci = 0; ci < 2; ++ci)
+#pragma unroll
+                for (int t = 0; t < 9; ++t) acc[ci * 9 + t] = fmaf(g, s_x[ci][ph + t / 3][pw + t % 3], acc[ci * 9 + t]);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 18; ++k) atomicAdd(dw + co * 18 + k, acc[k]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// BatchNorm (train): finalize statistics -> per-channel scale/shift, saved mean/invstd, running stats.
+// Reference semantics: nn.BatchNorm2d defaults (eps 1e-5, momentum 0.1, biased var to normalise,
+// unbiased var into running_var), unet_model.py:28,31. The conv bias is not added to the stored conv
+// output (BN cancels it), so it is added back here for running_mean only.
+// ------------------------------------------------------------------------------------------------
+__global__ void bn_finalize_kernel(const float* __restrict__ stats, int replicas, int C, float count,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta,
+                                   const float* __restrict__ conv_bias, float eps, float momentum,
+                                   float* __restrict__ scale, float* __restrict__ shift, float* __restrict__ mean_out,
+                                   float* __restrict__ invstd_out, float* __restrict__ running_mean,
+                                   float* __restrict__ running_var) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    double s = 0.0, q = 0.0;
+    for (int r = 0; r < replicas; ++r) {
+        s += stats[(static_cast<size_t>(r) * 2) * C + c];
+        q += stats[(static_cast<size_t>(r) * 2 + 1) * C + c];
+    }
+    const double mean = s / count;
+    double var = q / count - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float invstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+    const float sc = gamma[c] * invstd;
+    scale[c] = sc;
+    shift[c] = beta[c] - static_cast<float>(mean) * sc;
+    mean_out[c] = static_cast<float>(mean);
+    invstd_out[c] = invstd;
+    if (running_mean != nullptr) {
+        const float b = conv_bias ? conv_bias[c] : 0.f;
+        const float unbiased = static_cast<float>(var * (count / (count - 1.0)));
+        running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (static_cast<float>(mean) + b);
+        running_var[c] = (1.f - momentum) * running_var[c] + momentum * unbiased;
+    }
+}
+
+// Eval-mode fold: y = relu(scale*conv + shift) with scale = gamma/sqrt(rv+eps),
+// shift = beta + (bias - rm)*scale. Tiny; one launch per network via the job table.
+struct FoldJob {
+    const float* gamma;
+    const float* beta;
+    const float* rmean;
+    const float* rvar;
+    const float* conv_bias;
+    float* scale;
+    float* shift;
+    int C;
+    int pad;
+};
+__global__ void bn_fold_eval_kernel(const FoldJob* __restrict__ jobs, float eps) {
+    const FoldJob j = jobs[blockIdx.y];
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < j.C; c += gridDim.x * blockDim.x) {
+        const float sc = j.gamma[c] * rsqrtf(j.rvar[c] + eps);
+        j.scale[c] = sc;
+        j.shift[c] = j.beta[c] + ((j.conv_bias ? j.conv_bias[c] : 0.f) - j.rmean[c]) * sc;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// BN-apply + ReLU (+ 2x2 max-pool): reads the raw conv output once, writes the activation into its
+// (possibly concat-slot) destination and, for encoder blocks, the pooled tensor in the same pass.
+// One thread = 8 channels of a 2x2 pixel quad.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) bnrelu_apply_kernel(const __nv_bfloat16* __restrict__ z, int C,
+                                                           const float* __restrict__ scale,
+                                                           const float* __restrict__ shift,
+                                                           __nv_bfloat16* __restrict__ act, int act_stride,
+                                                           int act_coff, __nv_bfloat16* __restrict__ pooled, int H,
+                                                           int W, long long total /* B*(H/2)*(W/2)*(C/8) */) {
+    const int c8n = C >> 3;
+    const int W2 = W >> 1, H2 = H >> 1;
+    for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+         idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int c = static_cast<int>(idx % c8n) * 8;
+        long long r = idx / c8n;
+        const int w2 = static_cast<int>(r % W2);
+        r /= W2;
+        const int h2 = static_cast<int>(r % H2);
+        const int img = static_cast<int>(r / H2);
+        const F8 sc = ld_f32x8(scale + c), sh = ld_f32x8(shift + c);
+        F8 mx;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) mx.v[k] = 0.f;  // post-ReLU values are >= 0
+#pragma unroll
+        for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+            for (int dx = 0; dx < 2; ++dx) {
+                const size_t pix = (static_cast<size_t>(img) * H + 2 * h2 + dy) * W + 2 * w2 + dx;
+                F8 v = ld_bf16x8(z + pix * C + c);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    v.v[k] = fmaxf(fmaf(v.v[k], sc.v[k], sh.v[k]), 0.f);
+                    // pool over the values as stored (bf16), like MaxPool2d reading the activation tensor
+                    mx.v[k] = fmaxf(mx.v[k], bf16_round(v.v[k]));
+                }
+                st_bf16x8(act + pix * act_stride + act_coff + c, v);
+            }
+        if (pooled != nullptr) st_bf16x8(pooled + ((static_cast<size_t>(img) * H2 + h2) * W2 + w2) * C + c, mx);
+    }
+}
+
+// Plain MaxPool2d(2,2) forward (unet_model.py:52,55,58,61) on an NHWC slot -> dense NHWC.
+__global__ void __launch_bounds__(256) maxpool2x2_fwd_kernel(const __nv_bfloat16* __restrict__ in, int in_stride,
+                                                             int in_coff, int C, __nv_bfloat16* __restrict__ out,
+                                                             int H, int W, long long total) {
+    const int c8n = C >> 3;
+    const int W2 = W >> 1, H2 = H >> 1;
+    for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+         idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int c = static_cast<int>(idx % c8n) * 8;
+        long long r = idx / c8n;
+        const int w2 = static_cast<int>(r % W2);
+        r /= W2;
+        const int h2 = static_cast<int>(r % H2);
+        const int img = static_cast<int>(r / H2);
+        const size_t p00 = (static_cast<size_t>(img) * H + 2 * h2) * W + 2 * w2;
+        const F8 a = ld_bf16x8(in + p00 * in_stride + in_coff + c);
+        const F8 b = ld_bf16x8(in + (p00 + 1) * in_stride + in_coff + c);
+        const F8 d = ld_bf16x8(in + (p00 + W) * in_stride + in_coff + c);
+        const F8 e = ld_bf16x8(in + (p00 + W + 1) * in_stride + in_coff + c);
+        F8 m;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) m.v[k] = fmaxf(fmaxf(a.v[k], b.v[k]), fmaxf(d.v[k], e.v[k]));
+        st_bf16x8(out + ((static_cast<size_t>(img) * H2 + h2) * W2 + w2) * C + c, m);
+    }
+}
+
+// MaxPool2d(2,2) backward fused with the skip-connection gradient add:
+//   dY[q] = dskip[q] + (q is the FIRST max of its 2x2 window in row-major order ? dpool[window] : 0)
+// (ATen max_pool2d_with_indices tie-breaking). `act` is the forward activation the pool read.
+__global__ void __launch_bounds__(256) maxpool2x2_bwd_kernel(const __nv_bfloat16* __restrict__ act, int act_stride,
+                                                             int act_coff, const __nv_bfloat16* __restrict__ dpool,
+                                                             const __nv_bfloat16* __restrict__ dskip,
+                                                             int dskip_stride, int dskip_coff, int C,
+                                                             __nv_bfloat16* __restrict__ dy, int H, int W,
+                                                             long long total) {
+    const int c8n = C >> 3;
+    const int W2 = W >> 1, H2 = H >> 1;
+    for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+         idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int c = static_cast<int>(idx % c8n) * 8;
+        long long r = idx / c8n;
+        const int w2 = static_cast<int>(r % W2);
+        r /= W2;
+        const int h2 = static_cast<int>(r % H2);
+        const int img = static_cast<int>(r / H2);
+        const size_t p00 = (static_cast<size_t>(img) * H + 2 * h2) * W + 2 * w2;
+        const size_t pix[4] = {p00, p00 + 1, p00 + W, p00 + W + 1};
+        F8 a[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) a[k] = ld_bf16x8(act + pix[k] * act_stride + act_coff + c);
+        const F8 g = ld_bf16x8(dpool + ((static_cast<size_t>(img) * H2 + h2) * W2 + w2) * C + c);
+        int arg[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            int best = 0;
+            float bv = a[0].v[k];
+#pragma unroll
+            for (int j = 1; j < 4; ++j)
+                if (a[j].v[k] > bv) {
+                    bv = a[j].v[k];
+                    best = j;
+                }
+            arg[k] = best;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            F8 o;
+            if (dskip != nullptr) {
+                o = ld_bf16x8(dskip + pix[j] * dskip_stride + dskip_coff + c);
+            } else {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) o.v[k] = 0.f;
+            }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) o.v[k] += (arg[k] == j) ? g.v[k] : 0.f;
+            st_bf16x8(dy + pix[j] * C + c, o);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// BatchNorm + ReLU backward, two passes over (dY, z):
+//   m = [scale*z + shift > 0];  g = dY*m;  xhat = (z - mean)*invstd
+//   pass 1: S1[c] = sum g, S2[c] = sum g*xhat            (-> dbeta, dgamma)
+//   pass 2: dZ = gamma*invstd * (g - S1/N - xhat*S2/N)
+// Pass 1 layout: a block owns a channel group (8 channels per thread-column) and a slice of pixels.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, int dy_stride,
+                                                            int dy_coff, const __nv_bfloat16* __restrict__ z, int C,
+                                                            const float* __restrict__ scale,
+                                                            const float* __restrict__ shift,
+                                                            const float* __restrict__ mean,
+                                                            const float* __restrict__ invstd,
+                                                            float* __restrict__ sums /* [replicas][2][C] */,
+                                                            int replicas, long long npix) {
+    // thread layout: tx = channel-vector (8 ch) within a 64-channel group, ty = pixel lane
+    const int cg = C >> 6;                       // 64-channel groups
+    const int group = blockIdx.x % cg;           // which 64-channel group
+    const int slice = blockIdx.x / cg;           // which pixel slice
+    const int nslices = gridDim.x / cg;
+    const int tx = threadIdx.x & 7, ty = threadIdx.x >> 3;  // 8 x 32
+    const int c = group * 64 + tx * 8;
+    const F8 sc = ld_f32x8(scale + c), sh = ld_f32x8(shift + c), mu = ld_f32x8(mean + c), is = ld_f32x8(invstd + c);
+    float s1[8], s2[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s1[k] = s2[k] = 0.f;
+    for (long long p = static_cast<long long>(slice) * 32 + ty; p < npix; p += static_cast<long long>(nslices) * 32) {
+        const F8 g = ld_bf16x8(dy + p * dy_stride + dy_coff + c);
+        const F8 zz = ld_bf16x8(z + p * C + c);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const float y = fmaf(zz.v[k], sc.v[k], sh.v[k]);
+            const float gm = y > 0.f ? g.v[k] : 0.f;
+            s1[k] += gm;
+            s2[k] = fmaf(gm, (zz.v[k] - mu.v[k]) * is.v[k], s2[k]);
+        }
+    }
+    __shared__ float red[2][32][65];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        red[0][ty][tx * 8 + k] = s1[k];
+        red[1][ty][tx * 8 + k] = s2[k];
+    }
+    __syncthreads();
+    if (threadIdx.x < 128) {
+        const int which = threadIdx.x >> 6, ch = threadIdx.x & 63;
+        float acc = 0.f;
+#pragma unroll 8
+        for (int r = 0; r < 32; ++r) acc += red[which][r][ch];
+        atomicAdd(sums + (static_cast<size_t>(slice % replicas) * 2 + which) * C + group * 64 + ch, acc);
+    }
+}
+
+__global__ void bn_bwd_finalize_kernel(const float* __restrict__ sums, int replicas, int C, float count,
+                                       float* __restrict__ c1, float* __restrict__ c2, float* __restrict__ dgamma,
+                                       float* __restrict__ dbeta) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    float s1 = 0.f, s2 = 0.f;
+    for (int r = 0; r < replicas; ++r) {
+        s1 += sums[(static_cast<size_t>(r) * 2) * C + c];
+        s2 += sums[(static_cast<size_t>(r) * 2 + 1) * C + c];
+    }
+    c1[c] = s1 / count;
+    c2[c] = s2 / count;
+    dgamma[c] = s2;
+    dbeta[c] = s1;
+}
+
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, int dy_stride,
+                                                           int dy_coff, const __nv_bfloat16* __restrict__ z, int C,
+                                                           const float* __restrict__ scale,
+                                                           const float* __restrict__ shift,
+                                                           const float* __restrict__ mean,
+                                                           const float* __restrict__ invstd,
+                                                           const float* __restrict__ c1, const float* __restrict__ c2,
+                                                           __nv_bfloat16* __restrict__ dz, long long total) {
+    const int c8n = C >> 3;
+    for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+         idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int c = static_cast<int>(idx % c8n) * 8;
+        const long long p = idx / c8n;
+        const F8 sc = ld_f32x8(scale + c), sh = ld_f32x8(shift + c), mu = ld_f32x8(mean + c), is = ld_f32x8(invstd + c);
+        const F8 k1 = ld_f32x8(c1 + c), k2 = ld_f32x8(c2 + c);
+        const F8 g = ld_bf16x8(dy + p * dy_stride + dy_coff + c);
+        const F8 zz = ld_bf16x8(z + p * C + c);
+        F8 o;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const float y = fmaf(zz.v[k], sc.v[k], sh.v[k]);
+            const float gm = y > 0.f ? g.v[k] : 0.f;
+            const float xh = (zz.v[k] - mu.v[k]) * is.v[k];
+            o.v[k] = sc.v[k] * (gm - k1.v[k] - xh * k2.v[k]);  // scale = gamma*invstd
+        }
+        st_bf16x8(dz + p * C + c, o);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// 1x1 head: Conv2d(64 -> 1) + bias (unet_model.py:80,117). fp32 output in NCHW (C=1 => same as NHW).
+// 8 threads per pixel (one uint4 each), shuffle reduce.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) head_fwd_kernel(const __nv_bfloat16* __restrict__ act,  // [P][64]
+                                                       const float* __restrict__ w, const float* __restrict__ b,
+                                                       float* __restrict__ out, long long npix) {
+    const int sub = threadIdx.x & 7;
+    const F8 wv = ld_f32x8(w + sub * 8);
+    const float bias = b[0];
+    for (long long p = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 3; p < npix;
+         p += (static_cast<long long>(gridDim.x) * blockDim.x) >> 3) {
+        const F8 a = ld_bf16x8(act + p * 64 + sub * 8);
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s = fmaf(a.v[k], wv.v[k], s);
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        s += __shfl_xor_sync(0xffffffffu, s, 4);
+        if (sub == 0) out[p] = s + bias;
+    }
+}
+
+// head backward: dA[p][c] = dOut[p]*w[c];  dW[c] = sum_p dOut[p]*a[p][c];  db = sum_p dOut[p]
+__global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__ dout,
+                                                       const __nv_bfloat16* __restrict__ act,
+                                                       const float* __restrict__ w, __nv_bfloat16* __restrict__ dact,
+                                                       float* __restrict__ dw, float* __restrict__ db, long long npix) {
+    const int sub = threadIdx.x & 7;
+    const F8 wv = ld_f32x8(w + sub * 8);
+    float accw[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) accw[k] = 0.f;
+    float accb = 0.f;
+    for (long long p = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 3; p < npix;
+         p += (static_cast<long long>(gridDim.x) * blockDim.x) >> 3) {
+        const float g = dout[p];
+        const F8 a = ld_bf16x8(act + p * 64 + sub * 8);
+        F8 o;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            o.v[k] = g * wv.v[k];
+            accw[k] = fmaf(g, a.v[k], accw[k]);
+        }
+        st_bf16x8(dact + p * 64 + sub * 8, o);
+        if (sub == 0) accb += g;
+    }
+    __shared__ float s_w[64];
+    __shared__ float s_b;
+    if (threadIdx.x < 64) s_w[threadIdx.x] = 0.f;
+    if (threadIdx.x == 0) s_b = 0.f;
+    __syncthreads();
+    // reduce over the 4 pixels a warp handles concurrently (lanes with equal sub), then smem atomics
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        accw[k] += __shfl_xor_sync(0xffffffffu, accw[k], 8);
+        accw[k] += __shfl_xor_sync(0xffffffffu, accw[k], 16);
+    }
+    accb += __shfl_xor_sync(0xffffffffu, accb, 8);
+    accb += __shfl_xor_sync(0xffffffffu, accb, 16);
+    if ((threadIdx.x & 31) < 8) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) atomicAdd(&s_w[sub * 8 + k], accw[k]);
+        if (sub == 0) atomicAdd(&s_b, accb);
+    }
+    __syncthreads();
+    if (threadIdx.x < 64) atomicAdd(dw + threadIdx.x, s_w[threadIdx.x]);
+    if (threadIdx.x == 0) atomicAdd(db, s_b);
+}
+
+// ------------------------------------------------------------------------------------------------
+// layout casts at the boundary (used by the per-op tests and by users feeding intermediate tensors)
+// ------------------------------------------------------------------------------------------------
+__global__ void nchw_f32_to_nhwc_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, int C,
+                                             int HW, long long total) {
+    for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+         idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int c = idx % C;
+        const long long r = idx / C;
+        const int p = r % HW;
+        const long long n = r / HW;
+        out[idx] = __float2bfloat16_rn(in[(n * C + c) * HW + p]);
+    }
+}
+
+__global__ void nhwc_bf16_to_nchw_f32_kernel(const __nv_bfloat16* __restrict__ in, int in_stride, int in_coff,
+                                             float* __restrict__ out, int C, int HW, long long total) {
+    for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+         idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int p = idx % HW;
+        const long long r = idx / HW;
+        const int c = r % C;
+        const long long n = r / C;
+        out[idx] = __bfloat162float(in[(n * HW + p) * in_stride + in_coff + c]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Adam (torch.optim.Adam semantics, unet_model.py:155: lr 1e-4, betas (0.9,0.999), eps 1e-8, wd 0) over the
+// flat fp32 parameter / gradient / moment buffers. step-dependent scalars are computed on the host.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) adam_flat_kernel(float* __restrict__ p, const float* __restrict__ g,
+                                                        float* __restrict__ m, float* __restrict__ v, long long n,
+                                                        float lr, float beta1, float beta2, float eps,
+                                                        float bias_corr1, float bias_corr2_sqrt, float grad_scale) {
+    for (long long i = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) * 4; i < n;
+         i += static_cast<long long>(gridDim.x) * blockDim.x * 4) {
+        if (i + 4 <= n) {
+            float4 pp = *reinterpret_cast<float4*>(p + i);
+            const float4 gg = *reinterpret_cast<const float4*>(g + i);
+            float4 mm = *reinterpret_cast<float4*>(m + i);
+            float4 vv = *reinterpret_cast<float4*>(v + i);
+            float* pa = &pp.x;
+            const float* ga = &gg.x;
+            float* ma = &mm.x;
+            float* va = &vv.x;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float gk = ga[k] * grad_scale;
+                ma[k] = beta1 * ma[k] + (1.f - beta1) * gk;
+                va[k] = beta2 * va[k] + (1.f - beta2) * gk * gk;
+                const float denom = sqrtf(va[k]) / bias_corr2_sqrt + eps;
+                pa[k] -= (lr / bias_corr1) * (ma[k] / denom);
+            }
+            *reinterpret_cast<float4*>(p + i) = pp;
+            *reinterpret_cast<float4*>(m + i) = mm;
+            *reinterpret_cast<float4*>(v + i) = vv;
+        } else {
+            for (long long j = i; j < n; ++j) {
+                const float gk = g[j] * grad_scale;
+                m[j] = beta1 * m[j] + (1.f - beta1) * gk;
+                v[j] = beta2 * v[j] + (1.f - beta2) * gk * gk;
+                const float denom = sqrtf(v[j]) / bias_corr2_sqrt + eps;
+                p[j] -= (lr / bias_corr1) * (m[j] / denom);
+            }
+        }
+    }
+}
+
+}  // namespace b200sr

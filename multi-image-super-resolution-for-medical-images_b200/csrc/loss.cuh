@@ -1,0 +1,194 @@
+// Fused MSE + windowed-SSIM loss, forward value AND gradient w.r.t. the prediction in one pass (fp32).
+//
+//   loss = w_mse * mean((x-y)^2) + w_ssim * (1 - mean(SSIM_map(x, y)))
+//
+// Reference: nn.MSELoss (unet_model.py:156,180); the combined-loss notebook is missing from the reference
+// snapshot, so the SSIM definition is the one frozen in SURVEY.md §8(a11):
+//   mode G: 11-tap Gaussian (sigma 1.5) separable window, "valid" map, biased covariance
+//   mode U: 7-tap uniform window, "valid" map, sample covariance (x K^2/(K^2-1)) == skimage defaults used by
+//           the reference's evaluation code (VolumeVisualization.py:256)
+// The window taps and the covariance normalisation are kernel arguments, so both modes are the same code.
+//
+// With mu = w*x, m_xx = w*x^2, m_xy = w*x*y (valid correlations) and S(mu_x, mu_y, m_xx, m_yy, m_xy) the SSIM
+// map, the gradient is three "full" correlations of per-map-pixel coefficient maps with the same window:
+//   dS/dx(q) = sum_p w(q-p) [ Gm(p) + 2 x(q) Gxx(p) + y(q) Gxy(p) ]
+// Each block owns a 32x32 tile of prediction pixels, stages x,y with a 2(K-1) halo in shared memory, and runs
+// the separable filters out of shared memory; loss partial sums leave through two double atomics per block.
+#pragma once
+#include "ptx.cuh"
+
+namespace b200sr {
+
+constexpr int LS_T = 32;
+constexpr int LS_KMAX = 11;
+constexpr int LS_IT = LS_T + 2 * (LS_KMAX - 1);  // 52
+constexpr int LS_MT = LS_T + (LS_KMAX - 1);      // 42
+constexpr int LS_SMEM_FLOATS = 2 * LS_IT * LS_IT + 5 * LS_IT * LS_MT + 3 * LS_MT * LS_MT;
+constexpr int LS_SMEM_BYTES = LS_SMEM_FLOATS * 4;
+
+struct LossArgs {
+    const float* pred;    // [B][H][W]
+    const float* target;  // [B][H][W]
+    float* grad;          // [B][H][W] or null
+    double* sums;         // [2]: sum (x-y)^2, sum SSIM map
+    int H, W, K;
+    float win[LS_KMAX];
+    float cov_norm, C1, C2;
+    float g_mse;   // w_mse * 2 / (B*H*W)
+    float g_ssim;  // -w_ssim / (B * (H-K+1) * (W-K+1))
+};
+
+__global__ void __launch_bounds__(256) mse_ssim_kernel(const LossArgs a) {
+    extern __shared__ float ls_smem[];
+    const int K = a.K, R = K - 1;
+    const int IT = LS_T + 2 * R, MT = LS_T + R;
+    float* s_x = ls_smem;                       // [IT][IT]
+    float* s_y = s_x + LS_IT * LS_IT;           // [IT][IT]
+    float* s_h = s_y + LS_IT * LS_IT;           // 5 x [IT][MT]; later reused as 3 x [MT][T]
+    float* s_g = s_h + 5 * LS_IT * LS_MT;       // 3 x [MT][MT]
+    __shared__ float s_win[LS_KMAX];
+    __shared__ float s_red[2][8];
+
+    const int tid = threadIdx.x;
+    const int tiles_w = (a.W + LS_T - 1) / LS_T;
+    const int tiles_h = (a.H + LS_T - 1) / LS_T;
+    const int img = blockIdx.x / (tiles_w * tiles_h);
+    const int t_in = blockIdx.x % (tiles_w * tiles_h);
+    const int qh0 = (t_in / tiles_w) * LS_T, qw0 = (t_in % tiles_w) * LS_T;
+    const int ih0 = qh0 - R, iw0 = qw0 - R;
+    const float* px = a.pred + static_cast<size_t>(img) * a.H * a.W;
+    const float* py = a.target + static_cast<size_t>(img) * a.H * a.W;
+    const int MH = a.H - K + 1, MW = a.W - K + 1;  // valid map size
+
+    if (tid < K) s_win[tid] = a.win[tid];
+    for (int i = tid; i < IT * IT; i += 256) {
+        const int r = i / IT, c = i % IT;
+        const int hh = ih0 + r, ww = iw0 + c;
+        float vx = 0.f, vy = 0.f;
+        if (hh >= 0 && hh < a.H && ww >= 0 && ww < a.W) {
+            vx = px[hh * a.W + ww];
+            vy = py[hh * a.W + ww];
+        }
+        s_x[r * LS_IT + c] = vx;
+        s_y[r * LS_IT + c] = vy;
+    }
+    __syncthreads();
+
+    // horizontal pass of the 5 moment images
+    for (int i = tid; i < IT * MT; i += 256) {
+        const int r = i / MT, b = i % MT;
+        float hx = 0.f, hy = 0.f, hxx = 0.f, hyy = 0.f, hxy = 0.f;
+        for (int v = 0; v < K; ++v) {
+            const float wv = s_win[v];
+            const float x = s_x[r * LS_IT + b + v], y = s_y[r * LS_IT + b + v];
+            hx = fmaf(wv, x, hx);
+            hy = fmaf(wv, y, hy);
+            hxx = fmaf(wv, x * x, hxx);
+            hyy = fmaf(wv, y * y, hyy);
+            hxy = fmaf(wv, x * y, hxy);
+        }
+        float* d = s_h + r * LS_MT + b;
+        d[0 * LS_IT * LS_MT] = hx;
+        d[1 * LS_IT * LS_MT] = hy;
+        d[2 * LS_IT * LS_MT] = hxx;
+        d[3 * LS_IT * LS_MT] = hyy;
+        d[4 * LS_IT * LS_MT] = hxy;
+    }
+    __syncthreads();
+
+    // vertical pass -> SSIM map value + gradient coefficient maps
+    float ssim_part = 0.f;
+    for (int i = tid; i < MT * MT; i += 256) {
+        const int ar = i / MT, b = i % MT;
+        const int ph = qh0 - R + ar, pw = qw0 - R + b;
+        float gm = 0.f, gxx = 0.f, gxy = 0.f;
+        if (ph >= 0 && ph < MH && pw >= 0 && pw < MW) {
+            float mx = 0.f, my = 0.f, mxx = 0.f, myy = 0.f, mxy = 0.f;
+            for (int u = 0; u < K; ++u) {
+                const float wu = s_win[u];
+                const float* s = s_h + (ar + u) * LS_MT + b;
+                mx = fmaf(wu, s[0 * LS_IT * LS_MT], mx);
+                my = fmaf(wu, s[1 * LS_IT * LS_MT], my);
+                mxx = fmaf(wu, s[2 * LS_IT * LS_MT], mxx);
+                myy = fmaf(wu, s[3 * LS_IT * LS_MT], myy);
+                mxy = fmaf(wu, s[4 * LS_IT * LS_MT], mxy);
+            }
+            const float cn = a.cov_norm;
+            const float sxx = cn * (mxx - mx * mx), syy = cn * (myy - my * my), sxy = cn * (mxy - mx * my);
+            const float A1 = 2.f * mx * my + a.C1, A2 = 2.f * sxy + a.C2;
+            const float B1 = mx * mx + my * my + a.C1, B2 = sxx + syy + a.C2;
+            const float inv = 1.f / (B1 * B2);
+            const float S = A1 * A2 * inv;
+            // partial derivatives of S
+            const float dS_dsxy = 2.f * A1 * inv;
+            const float dS_dsxx = -S / B2;
+            gxx = cn * dS_dsxx;
+            gxy = cn * dS_dsxy;
+            gm = 2.f * my * A2 * inv - 2.f * mx * S / B1 - cn * my * dS_dsxy - 2.f * cn * mx * dS_dsxx;
+            if (ar >= R && b >= R) ssim_part += S;  // map pixels owned by this block
+        }
+        s_g[0 * LS_MT * LS_MT + ar * LS_MT + b] = gm;
+        s_g[1 * LS_MT * LS_MT + ar * LS_MT + b] = gxx;
+        s_g[2 * LS_MT * LS_MT + ar * LS_MT + b] = gxy;
+    }
+    __syncthreads();
+
+    // horizontal pass of the coefficient maps (full correlation): Hg[a][j] = sum_v w[v] G[a][j + R - v]
+    float* s_hg = s_h;  // 3 x [MT][T], the moment rows are dead
+    for (int i = tid; i < MT * LS_T; i += 256) {
+        const int ar = i / LS_T, j = i % LS_T;
+        float h0 = 0.f, h1 = 0.f, h2 = 0.f;
+        for (int v = 0; v < K; ++v) {
+            const float wv = s_win[v];
+            const int b = j + R - v;
+            h0 = fmaf(wv, s_g[0 * LS_MT * LS_MT + ar * LS_MT + b], h0);
+            h1 = fmaf(wv, s_g[1 * LS_MT * LS_MT + ar * LS_MT + b], h1);
+            h2 = fmaf(wv, s_g[2 * LS_MT * LS_MT + ar * LS_MT + b], h2);
+        }
+        s_hg[0 * LS_MT * LS_T + ar * LS_T + j] = h0;
+        s_hg[1 * LS_MT * LS_T + ar * LS_T + j] = h1;
+        s_hg[2 * LS_MT * LS_T + ar * LS_T + j] = h2;
+    }
+    __syncthreads();
+
+    // vertical pass + combine with the MSE term
+    float mse_part = 0.f;
+    for (int i = tid; i < LS_T * LS_T; i += 256) {
+        const int r = i / LS_T, j = i % LS_T;
+        const int qh = qh0 + r, qw = qw0 + j;
+        if (qh >= a.H || qw >= a.W) continue;
+        float v0 = 0.f, v1 = 0.f, v2 = 0.f;
+        for (int u = 0; u < K; ++u) {
+            const float wu = s_win[u];
+            const int ar = r + R - u;
+            v0 = fmaf(wu, s_hg[0 * LS_MT * LS_T + ar * LS_T + j], v0);
+            v1 = fmaf(wu, s_hg[1 * LS_MT * LS_T + ar * LS_T + j], v1);
+            v2 = fmaf(wu, s_hg[2 * LS_MT * LS_T + ar * LS_T + j], v2);
+        }
+        const float x = s_x[(r + R) * LS_IT + j + R], y = s_y[(r + R) * LS_IT + j + R];
+        const float d = x - y;
+        mse_part = fmaf(d, d, mse_part);
+        if (a.grad != nullptr)
+            a.grad[(static_cast<size_t>(img) * a.H + qh) * a.W + qw] =
+                a.g_mse * d + a.g_ssim * (v0 + 2.f * x * v1 + y * v2);
+    }
+
+    // block reduction of the two loss partials
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+        mse_part += __shfl_xor_sync(0xffffffffu, mse_part, o);
+        ssim_part += __shfl_xor_sync(0xffffffffu, ssim_part, o);
+    }
+    if ((tid & 31) == 0) {
+        s_red[0][tid >> 5] = mse_part;
+        s_red[1][tid >> 5] = ssim_part;
+    }
+    __syncthreads();
+    if (tid < 2) {
+        double acc = 0.0;
+        for (int w = 0; w < 8; ++w) acc += s_red[tid][w];
+        atomicAdd(a.sums + tid, acc);
+    }
+}
+
+}  // namespace b200sr

@@ -1,0 +1,528 @@
+"""Execution engine of the UNet hot path: owns the HBM layout and issues the C-ABI ops in order.
+
+Reference being replaced: UNet.forward + autograd backward (/root/reference/src/unet_model.py:82-118).
+
+HBM layout (all activations NHWC bf16, resident for the whole step):
+  * parameters: one flat fp32 buffer; every nn.Parameter is a view into it (state_dict layout unchanged);
+    gradients: one flat fp32 buffer with the same offsets (bucketable for the NCCL all-reduce).
+  * derived bf16 operand copies of the conv weights (forward and dgrad packings) in one flat buffer,
+    refreshed by ONE table-driven kernel launch; never part of the state_dict.
+  * per decoder level one concat buffer (B,H,W,2C): ConvTranspose writes channels [0,C), the encoder block's
+    BN+ReLU pass writes channels [C,2C) -> torch.cat never runs.
+  * per conv: raw output z (kept for backward), per BN: scale/shift/mean/invstd and statistics replicas.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import call, ptr
+
+STATS_REPLICAS = 16
+BN_EPS = 1e-5
+BN_MOMENTUM = 0.1
+
+PACK_CONV_FWD, PACK_CONV_DGRAD, PACK_CONVT_FWD, PACK_CONVT_DGRAD, UNPACK_CONV_WGRAD, UNPACK_CONVT_WGRAD = range(6)
+
+_PACK_JOB_DTYPE = np.dtype([("src", "<u8"), ("dst", "<u8"), ("kind", "<i4"), ("cout", "<i4"), ("cin", "<i4"),
+                            ("pad", "<i4"), ("count", "<i8")])
+_FOLD_JOB_DTYPE = np.dtype([("gamma", "<u8"), ("beta", "<u8"), ("rmean", "<u8"), ("rvar", "<u8"), ("cbias", "<u8"),
+                            ("scale", "<u8"), ("shift", "<u8"), ("C", "<i4"), ("pad", "<i4")])
+
+
+def _align(n: int, a: int = 64) -> int:
+    return (n + a - 1) // a * a
+
+
+def _jobs_to_device(arr: np.ndarray, device) -> torch.Tensor:
+    return torch.from_numpy(arr.view(np.uint8).copy()).to(device)
+
+
+class ConvSpec:
+    """One Conv3x3+BN+ReLU layer of a UNetBlock (unet_model.py:27-32)."""
+
+    def __init__(self, name, conv, bn, cin, cout, level):
+        self.name, self.conv, self.bn, self.cin, self.cout, self.level = name, conv, bn, cin, cout, level
+
+
+class UpSpec:
+    """One ConvTranspose2d(k2,s2) (unet_model.py:67-76)."""
+
+    def __init__(self, name, mod, cin, cout, level):
+        self.name, self.mod, self.cin, self.cout, self.level = name, mod, cin, cout, level
+
+
+class UNetEngine:
+    def __init__(self, model):
+        self.model = model
+        f = model.init_features
+        if model.in_channels != 2 or model.out_channels != 1 or f != 64:
+            raise NotImplementedError(
+                "b200sr UNet engine implements the reference configuration UNet(in_channels=2, out_channels=1, "
+                f"init_features=64); got ({model.in_channels}, {model.out_channels}, {f})")
+        m = model
+        chans = [f, 2 * f, 4 * f, 8 * f, 16 * f]
+        self.chans = chans
+        blocks = [("enc1", m.enc1, 2, chans[0], 0), ("enc2", m.enc2, chans[0], chans[1], 1),
+                  ("enc3", m.enc3, chans[1], chans[2], 2), ("enc4", m.enc4, chans[2], chans[3], 3),
+                  ("bottleneck", m.bottleneck, chans[3], chans[4], 4),
+                  ("dec4", m.dec4, chans[4], chans[3], 3), ("dec3", m.dec3, chans[3], chans[2], 2),
+                  ("dec2", m.dec2, chans[2], chans[1], 1), ("dec1", m.dec1, chans[1], chans[0], 0)]
+        self.blocks = {}
+        self.convs = []  # forward order
+        for name, blk, cin, cout, level in blocks:
+            c1 = ConvSpec(f"{name}.conv.0", blk.conv[0], blk.conv[1], cin, cout, level)
+            c2 = ConvSpec(f"{name}.conv.3", blk.conv[3], blk.conv[4], cout, cout, level)
+            self.blocks[name] = (c1, c2)
+            self.convs += [c1, c2]
+        self.ups = {4: UpSpec("upconv4", m.upconv4, chans[4], chans[3], 3),
+                    3: UpSpec("upconv3", m.upconv3, chans[3], chans[2], 2),
+                    2: UpSpec("upconv2", m.upconv2, chans[2], chans[1], 1),
+                    1: UpSpec("upconv1", m.upconv1, chans[1], chans[0], 0)}
+        self.device = None
+        self.flat_p = None
+        self._plans = {}
+        self._eval_version = None
+        self._saved = None  # (plan, x) of the last train-mode forward
+
+    # ------------------------------------------------------------------------------------------------
+    # parameter flattening and derived operand buffers
+    # ------------------------------------------------------------------------------------------------
+    def _params(self):
+        return list(self.model.parameters())
+
+    def _is_flat(self) -> bool:
+        if self.flat_p is None:
+            return False
+        base = self.flat_p.data_ptr()
+        for p, off in zip(self._params(), self.p_off):
+            if p.data.data_ptr() != base + 4 * off or p.device != self.flat_p.device:
+                return False
+        # raw buffer pointers are baked into the fold-job table
+        return self._fold_ptrs == [(cs.bn.running_mean.data_ptr(), cs.bn.running_var.data_ptr()) for cs in self.convs]
+
+    def ensure_ready(self, device):
+        """(Re)build flat parameter storage and derived buffers if parameters moved (model.to(), new tensors)."""
+        if self.device == device and self._is_flat():
+            return
+        _lib.require_device()
+        self.device = device
+        params = self._params()
+        for p in params:
+            if p.device != device or p.dtype != torch.float32:
+                raise _lib.B200SRError(f"all UNet parameters must be fp32 on {device} (got {p.dtype} on {p.device})")
+        offs, total = [], 0
+        for p in params:
+            offs.append(total)
+            total += _align(p.numel())
+        self.p_off, self.p_total = offs, total
+        self.flat_p = torch.zeros(total, dtype=torch.float32, device=device)
+        self.flat_g = torch.zeros(total, dtype=torch.float32, device=device)
+        self.flat_G = torch.zeros(total, dtype=torch.float32, device=device)  # wgrad workspace, kernel layouts
+        self.grad_views = []
+        for p, off in zip(params, offs):
+            view = self.flat_p[off:off + p.numel()].view(p.shape)
+            view.copy_(p.data)
+            p.data = view
+            self.grad_views.append(self.flat_g[off:off + p.numel()].view(p.shape))
+        self.off_of = {id(p): off for p, off in zip(params, offs)}
+
+        # derived bf16 operand copies: forward + dgrad packings of every tensor-core layer
+        wp_total = 0
+        self.wp_fwd, self.wp_dgrad = {}, {}
+        for cs in self.convs[1:]:
+            n = cs.cout * cs.cin * 9
+            self.wp_fwd[cs.name] = wp_total
+            wp_total += _align(n)
+            self.wp_dgrad[cs.name] = wp_total
+            wp_total += _align(n)
+        for us in self.ups.values():
+            n = us.cin * us.cout * 4
+            self.wp_fwd[us.name] = wp_total
+            wp_total += _align(n)
+            self.wp_dgrad[us.name] = wp_total
+            wp_total += _align(n)
+        self.flat_wp = torch.zeros(wp_total, dtype=torch.bfloat16, device=device)
+
+        pack = np.zeros(2 * (len(self.convs) - 1 + len(self.ups)), dtype=_PACK_JOB_DTYPE)
+        unpack = np.zeros(len(self.convs) - 1 + len(self.ups), dtype=_PACK_JOB_DTYPE)
+        i = j = 0
+        wp_base, g_base, G_base = self.flat_wp.data_ptr(), self.flat_g.data_ptr(), self.flat_G.data_ptr()
+        for cs in self.convs[1:]:
+            w = cs.conv.weight
+            n = w.numel()
+            pack[i] = (w.data_ptr(), wp_base + 2 * self.wp_fwd[cs.name], PACK_CONV_FWD, cs.cout, cs.cin, 0, n)
+            pack[i + 1] = (w.data_ptr(), wp_base + 2 * self.wp_dgrad[cs.name], PACK_CONV_DGRAD, cs.cout, cs.cin, 0, n)
+            i += 2
+            off = self.off_of[id(w)]
+            unpack[j] = (G_base + 4 * off, g_base + 4 * off, UNPACK_CONV_WGRAD, cs.cout, cs.cin, 0, n)
+            j += 1
+        for us in self.ups.values():
+            w = us.mod.weight
+            n = w.numel()
+            pack[i] = (w.data_ptr(), wp_base + 2 * self.wp_fwd[us.name], PACK_CONVT_FWD, us.cout, us.cin, 0, n)
+            pack[i + 1] = (w.data_ptr(), wp_base + 2 * self.wp_dgrad[us.name], PACK_CONVT_DGRAD, us.cout, us.cin, 0, n)
+            i += 2
+            off = self.off_of[id(w)]
+            unpack[j] = (G_base + 4 * off, g_base + 4 * off, UNPACK_CONVT_WGRAD, us.cout, us.cin, 0, n)
+            j += 1
+        self.pack_jobs = _jobs_to_device(pack, device)
+        self.n_pack = len(pack)
+        # unpack jobs sorted by flat offset so that suffix ranges (= gradient buckets) are contiguous job ranges
+        order = np.argsort(unpack["dst"])
+        self.unpack_np = unpack[order]
+        self.unpack_jobs = _jobs_to_device(self.unpack_np, device)
+        self.n_unpack = len(unpack)
+
+        # per-BN workspace: scale, shift, mean, invstd, c1, c2 ; statistics replicas (fwd) and sums (bwd)
+        ws_total, st_total = 0, 0
+        self.bn_ws_off, self.bn_st_off = {}, {}
+        for cs in self.convs:
+            self.bn_ws_off[cs.name] = ws_total
+            ws_total += 6 * cs.cout
+            self.bn_st_off[cs.name] = st_total
+            st_total += STATS_REPLICAS * 2 * cs.cout
+        self.bn_ws = torch.zeros(ws_total, dtype=torch.float32, device=device)
+        self.bn_stats = torch.zeros(st_total, dtype=torch.float32, device=device)
+        self.bn_sums = torch.zeros(st_total, dtype=torch.float32, device=device)
+        # column sums of the decoder concat gradients (ConvTranspose bias gradient)
+        self.up_st_off, up_total = {}, 0
+        for k, us in self.ups.items():
+            self.up_st_off[k] = up_total
+            up_total += STATS_REPLICAS * 2 * 2 * us.cout
+        self.up_stats = torch.zeros(up_total, dtype=torch.float32, device=device)
+
+        fold = np.zeros(len(self.convs), dtype=_FOLD_JOB_DTYPE)
+        for i, cs in enumerate(self.convs):
+            o = self.bn_ws_off[cs.name]
+            fold[i] = (cs.bn.weight.data_ptr(), cs.bn.bias.data_ptr(), cs.bn.running_mean.data_ptr(),
+                       cs.bn.running_var.data_ptr(), cs.conv.bias.data_ptr() if cs.conv.bias is not None else 0,
+                       self.bn_ws.data_ptr() + 4 * o, self.bn_ws.data_ptr() + 4 * (o + cs.cout), cs.cout, 0)
+        self._fold_np = fold
+        self.fold_jobs = _jobs_to_device(fold, device)
+        self._fold_ptrs = [(cs.bn.running_mean.data_ptr(), cs.bn.running_var.data_ptr()) for cs in self.convs]
+        self._plans = {}
+        self._eval_version = None
+
+    def _bn(self, cs, which):
+        """Pointer (int) into the BN workspace: which in scale, shift, mean, invstd, c1, c2."""
+        idx = ("scale", "shift", "mean", "invstd", "c1", "c2").index(which)
+        return self.bn_ws.data_ptr() + 4 * (self.bn_ws_off[cs.name] + idx * cs.cout)
+
+    def _wp(self, table, name):
+        return self.flat_wp.data_ptr() + 2 * table[name]
+
+    def _state_version(self):
+        v = 0
+        for t in list(self.model.parameters()) + list(self.model.buffers()):
+            v += t._version
+        return v
+
+    def mark_weights_dirty(self):
+        """Parameters were changed behind torch's back (raw-pointer kernels): drop eval-mode derived state."""
+        self._eval_version = None
+
+    def repack_weights(self):
+        call("b200sr_pack_jobs", self.pack_jobs.data_ptr(), self.n_pack, _lib.current_stream_ptr())
+
+    # ------------------------------------------------------------------------------------------------
+    # activation plans
+    # ------------------------------------------------------------------------------------------------
+    def _plan(self, B, H, W, train):
+        key = (B, H, W, train)
+        plan = self._plans.get(key)
+        if plan is not None:
+            return plan
+        if H % 128 != 0 or W % 256 != 0:
+            # deepest level (H/16, W/16) must still tile into 8x16 pixel GEMM tiles
+            raise _lib.B200SRError(f"b200sr UNet needs H % 128 == 0 and W % 256 == 0 (got {H}x{W})")
+        dev, bf = self.device, torch.bfloat16
+        ch = self.chans
+        plan = {"B": B, "H": H, "W": W}
+
+        def buf(h, w, c):
+            return torch.empty((B, h, w, c), dtype=bf, device=dev)
+
+        for lvl in range(5):
+            h, w, c = H >> lvl, W >> lvl, ch[lvl]
+            if lvl < 4:
+                plan[f"cat{lvl}"] = buf(h, w, 2 * c)   # [0,C) upconv output, [C,2C) encoder skip
+                plan[f"pool{lvl}"] = buf(h // 2, w // 2, c)
+                plan[f"enc_a1_{lvl}"] = buf(h, w, c)
+                plan[f"dec_a1_{lvl}"] = buf(h, w, c)
+                plan[f"dec_a2_{lvl}"] = buf(h, w, c)
+            else:
+                plan["bot_a1"] = buf(h, w, c)
+                plan["bot_a2"] = buf(h, w, c)
+        if train:
+            for cs in self.convs:
+                h, w = H >> cs.level, W >> cs.level
+                plan["z:" + cs.name] = buf(h, w, cs.cout)
+            for lvl in range(4):
+                h, w, c = H >> lvl, W >> lvl, ch[lvl]
+                plan[f"dcat{lvl}"] = buf(h, w, 2 * c)
+            big = B * H * W * ch[0]
+            plan["scratch"] = [torch.empty(big, dtype=bf, device=dev) for _ in range(3)]
+        self._plans[key] = plan
+        return plan
+
+    # ------------------------------------------------------------------------------------------------
+    # forward
+    # ------------------------------------------------------------------------------------------------
+    def _check_input(self, x):
+        if x.dim() != 4 or x.shape[1] != 2:
+            raise _lib.B200SRError(f"expected input (B,2,H,W), got {tuple(x.shape)}")
+        if not x.is_cuda:
+            raise _lib.B200SRError("b200sr UNet runs on CUDA sm_100a only; there is no CPU path")
+        return x.contiguous().float()
+
+    def forward_eval(self, x):
+        x = self._check_input(x)
+        self.ensure_ready(x.device)
+        B, _, H, W = x.shape
+        plan = self._plan(B, H, W, False)
+        st = _lib.current_stream_ptr()
+        ver = self._state_version()
+        if ver != self._eval_version:
+            self.repack_weights()
+            call("b200sr_bn_fold_eval", self.fold_jobs.data_ptr(), len(self.convs), BN_EPS, st)
+            self._eval_version = ver
+        ch = self.chans
+
+        def conv(cs, src, s_stride, s_off, dst, d_stride, d_off, h, w):
+            call("b200sr_conv3x3_fwd", ptr(src), s_stride, s_off, cs.cin, self._wp(self.wp_fwd, cs.name), cs.cout,
+                 B, h, w, ptr(dst), d_stride, d_off, self._bn(cs, "scale"), self._bn(cs, "shift"), 1, None, 0, st)
+
+        cur = None
+        for lvl, name in enumerate(["enc1", "enc2", "enc3", "enc4"]):
+            c1, c2 = self.blocks[name]
+            h, w, c = H >> lvl, W >> lvl, ch[lvl]
+            a1, cat, pool = plan[f"enc_a1_{lvl}"], plan[f"cat{lvl}"], plan[f"pool{lvl}"]
+            if lvl == 0:
+                call("b200sr_conv1_fwd", ptr(x), ptr(c1.conv.weight), self._bn(c1, "scale"), self._bn(c1, "shift"), 1,
+                     ptr(a1), None, 0, B, h, w, st)
+            else:
+                conv(c1, cur, c1.cin, 0, a1, c, 0, h, w)
+            conv(c2, a1, c, 0, cat, 2 * c, c, h, w)
+            call("b200sr_maxpool2x2_fwd", ptr(cat), 2 * c, c, c, ptr(pool), B, h, w, st)
+            cur = pool
+        c1, c2 = self.blocks["bottleneck"]
+        h, w, c = H >> 4, W >> 4, ch[4]
+        conv(c1, cur, c1.cin, 0, plan["bot_a1"], c, 0, h, w)
+        conv(c2, plan["bot_a1"], c, 0, plan["bot_a2"], c, 0, h, w)
+        cur = plan["bot_a2"]
+        for k in (4, 3, 2, 1):
+            us = self.ups[k]
+            lvl = us.level
+            h, w, c = H >> lvl, W >> lvl, ch[lvl]
+            cat = plan[f"cat{lvl}"]
+            call("b200sr_convT2x2_fwd", ptr(cur), us.cin, 0, us.cin, self._wp(self.wp_fwd, us.name), us.cout,
+                 ptr(us.mod.bias), B, h // 2, w // 2, ptr(cat), 2 * c, 0, st)
+            c1, c2 = self.blocks[f"dec{k}"]
+            conv(c1, cat, 2 * c, 0, plan[f"dec_a1_{lvl}"], c, 0, h, w)
+            conv(c2, plan[f"dec_a1_{lvl}"], c, 0, plan[f"dec_a2_{lvl}"], c, 0, h, w)
+            cur = plan[f"dec_a2_{lvl}"]
+        fc = self.model.final_conv
+        out = torch.empty((B, 1, H, W), dtype=torch.float32, device=x.device)
+        call("b200sr_head_fwd", ptr(cur), ptr(fc.weight), ptr(fc.bias), ptr(out), B * H * W, st)
+        return out
+
+    def _conv_bn_train(self, plan, cs, src, s_stride, s_off, h, w, act, a_stride, a_off, pooled, x_input=None):
+        """conv -> batch statistics -> finalize -> BN-apply+ReLU(+pool)."""
+        B = plan["B"]
+        st = _lib.current_stream_ptr()
+        z = plan["z:" + cs.name]
+        stats = self.bn_stats.data_ptr() + 4 * self.bn_st_off[cs.name]
+        if x_input is not None:
+            call("b200sr_conv1_fwd", ptr(x_input), ptr(cs.conv.weight), None, None, 0, ptr(z), stats, STATS_REPLICAS,
+                 B, h, w, st)
+        else:
+            call("b200sr_conv3x3_fwd", ptr(src), s_stride, s_off, cs.cin, self._wp(self.wp_fwd, cs.name), cs.cout,
+                 B, h, w, ptr(z), cs.cout, 0, None, None, 0, stats, STATS_REPLICAS, st)
+        bn = cs.bn
+        track = bn.track_running_stats and bn.running_mean is not None
+        call("b200sr_bn_finalize", stats, STATS_REPLICAS, cs.cout, float(B * h * w), ptr(bn.weight), ptr(bn.bias),
+             ptr(cs.conv.bias), BN_EPS, BN_MOMENTUM, self._bn(cs, "scale"), self._bn(cs, "shift"),
+             self._bn(cs, "mean"), self._bn(cs, "invstd"), ptr(bn.running_mean) if track else None,
+             ptr(bn.running_var) if track else None, st)
+        call("b200sr_bnrelu_apply", ptr(z), cs.cout, self._bn(cs, "scale"), self._bn(cs, "shift"), ptr(act), a_stride,
+             a_off, ptr(pooled), B, h, w, st)
+
+    def forward_train(self, x):
+        x = self._check_input(x)
+        self.ensure_ready(x.device)
+        B, _, H, W = x.shape
+        plan = self._plan(B, H, W, True)
+        st = _lib.current_stream_ptr()
+        self.repack_weights()
+        self.bn_stats.zero_()
+        ch = self.chans
+        cur = None
+        for lvl, name in enumerate(["enc1", "enc2", "enc3", "enc4"]):
+            c1, c2 = self.blocks[name]
+            h, w, c = H >> lvl, W >> lvl, ch[lvl]
+            a1, cat, pool = plan[f"enc_a1_{lvl}"], plan[f"cat{lvl}"], plan[f"pool{lvl}"]
+            if lvl == 0:
+                self._conv_bn_train(plan, c1, None, 0, 0, h, w, a1, c, 0, None, x_input=x)
+            else:
+                self._conv_bn_train(plan, c1, cur, c1.cin, 0, h, w, a1, c, 0, None)
+            self._conv_bn_train(plan, c2, a1, c, 0, h, w, cat, 2 * c, c, pool)
+            cur = pool
+        c1, c2 = self.blocks["bottleneck"]
+        h, w, c = H >> 4, W >> 4, ch[4]
+        self._conv_bn_train(plan, c1, cur, c1.cin, 0, h, w, plan["bot_a1"], c, 0, None)
+        self._conv_bn_train(plan, c2, plan["bot_a1"], c, 0, h, w, plan["bot_a2"], c, 0, None)
+        cur = plan["bot_a2"]
+        for k in (4, 3, 2, 1):
+            us = self.ups[k]
+            lvl = us.level
+            h, w, c = H >> lvl, W >> lvl, ch[lvl]
+            cat = plan[f"cat{lvl}"]
+            call("b200sr_convT2x2_fwd", ptr(cur), us.cin, 0, us.cin, self._wp(self.wp_fwd, us.name), us.cout,
+                 ptr(us.mod.bias), B, h // 2, w // 2, ptr(cat), 2 * c, 0, st)
+            c1, c2 = self.blocks[f"dec{k}"]
+            self._conv_bn_train(plan, c1, cat, 2 * c, 0, h, w, plan[f"dec_a1_{lvl}"], c, 0, None)
+            self._conv_bn_train(plan, c2, plan[f"dec_a1_{lvl}"], c, 0, h, w, plan[f"dec_a2_{lvl}"], c, 0, None)
+            cur = plan[f"dec_a2_{lvl}"]
+        fc = self.model.final_conv
+        out = torch.empty((B, 1, H, W), dtype=torch.float32, device=x.device)
+        call("b200sr_head_fwd", ptr(cur), ptr(fc.weight), ptr(fc.bias), ptr(out), B * H * W, st)
+        bufs = [cs.bn.num_batches_tracked for cs in self.convs if cs.bn.num_batches_tracked is not None]
+        if bufs:
+            torch._foreach_add_(bufs, 1)
+        self._saved = (plan, x)
+        return out
+
+    # ------------------------------------------------------------------------------------------------
+    # backward
+    # ------------------------------------------------------------------------------------------------
+    def _bn_bwd(self, plan, cs, dy, dy_stride, dy_off, h, w, dz):
+        """BatchNorm+ReLU backward of one layer: dy -> dz (dense), dgamma/dbeta into the flat gradient."""
+        B = plan["B"]
+        st = _lib.current_stream_ptr()
+        z = plan["z:" + cs.name]
+        sums = self.bn_sums.data_ptr() + 4 * self.bn_st_off[cs.name]
+        npix = B * h * w
+        sc, sh, mu, iv = (self._bn(cs, k) for k in ("scale", "shift", "mean", "invstd"))
+        call("b200sr_bn_bwd_reduce", dy, dy_stride, dy_off, ptr(z), cs.cout, sc, sh, mu, iv, sums, STATS_REPLICAS,
+             npix, st)
+        g = self.flat_g.data_ptr()
+        call("b200sr_bn_bwd_finalize", sums, STATS_REPLICAS, cs.cout, float(npix), self._bn(cs, "c1"),
+             self._bn(cs, "c2"), g + 4 * self.off_of[id(cs.bn.weight)], g + 4 * self.off_of[id(cs.bn.bias)], st)
+        call("b200sr_bn_bwd_apply", dy, dy_stride, dy_off, ptr(z), cs.cout, sc, sh, mu, iv, self._bn(cs, "c1"),
+             self._bn(cs, "c2"), dz, npix, st)
+
+    def _G(self, param):
+        return self.flat_G.data_ptr() + 4 * self.off_of[id(param)]
+
+    def backward(self, dout, bucket_hook=None):
+        """Full backward of the last train-mode forward. dout: (B,1,H,W) fp32.
+        Gradients land in self.flat_g (views: self.grad_views, in model.parameters() order).
+        bucket_hook(lo, hi), if given, is called as soon as flat_g[lo:hi] is final (reverse forward order)."""
+        if self._saved is None:
+            raise _lib.B200SRError("backward() without a preceding train-mode forward")
+        plan, x = self._saved
+        B, H, W = plan["B"], plan["H"], plan["W"]
+        st = _lib.current_stream_ptr()
+        ch = self.chans
+        dout = dout.contiguous().float()
+        self.flat_g.zero_()
+        self.flat_G.zero_()
+        self.bn_sums.zero_()
+        self.up_stats.zero_()
+        s0, s1, s2 = (t.data_ptr() for t in plan["scratch"])
+        g = self.flat_g.data_ptr()
+        fc = self.model.final_conv
+
+        def unpack_range(lo_param, hi_off):
+            """Unpack wgrad workspaces for all layers with flat offset in [off(lo_param), hi_off) and report."""
+            lo = self.off_of[id(lo_param)]
+            sel = [i for i in range(self.n_unpack)
+                   if lo <= (int(self.unpack_np["dst"][i]) - g) // 4 < hi_off]
+            if sel:
+                first, n = sel[0], len(sel)
+                call("b200sr_pack_jobs", self.unpack_jobs.data_ptr() + first * _PACK_JOB_DTYPE.itemsize, n, st)
+            if bucket_hook is not None:
+                bucket_hook(lo, hi_off)
+
+        # head
+        a_last = plan["dec_a2_0"]
+        call("b200sr_head_bwd", ptr(dout), ptr(a_last), ptr(fc.weight), s0, g + 4 * self.off_of[id(fc.weight)],
+             g + 4 * self.off_of[id(fc.bias)], B * H * W, st)
+        dy = s0  # gradient w.r.t. the current block's output activation (dense)
+
+        def block_bwd(name, lvl, in_buf, in_stride, in_c, dx_dst, dx_stride, dx_stats, dy_ptr, x_input=None):
+            """Backward through a UNetBlock: dy (dense, cout ch) -> dx into dx_dst (in_c channels)."""
+            c1, c2 = self.blocks[name]
+            h, w, c = H >> lvl, W >> lvl, c2.cout
+            # pick two scratch buffers different from dy
+            free = [p for p in (s0, s1, s2) if p != dy_ptr]
+            dz2, dy1 = free[0], free[1]
+            a1 = plan["bot_a1"] if name == "bottleneck" else plan[f"{name[:3]}_a1_{lvl}"]
+            self._bn_bwd(plan, c2, dy_ptr, c, 0, h, w, dz2)
+            call("b200sr_conv3x3_wgrad", ptr(a1), c, 0, c, dz2, c, 0, c, B, h, w, self._G(c2.conv.weight), st)
+            call("b200sr_conv3x3_dgrad", dz2, c, 0, c, self._wp(self.wp_dgrad, c2.name), c, B, h, w, dy1, c, 0, None,
+                 0, st)
+            dz1 = dy_ptr  # dy is dead now
+            self._bn_bwd(plan, c1, dy1, c, 0, h, w, dz1)
+            if x_input is not None:
+                call("b200sr_conv1_wgrad", ptr(x_input), dz1, g + 4 * self.off_of[id(c1.conv.weight)], B, h, w, st)
+                return None
+            call("b200sr_conv3x3_wgrad", ptr(in_buf), in_stride, 0, in_c, dz1, c, 0, c, B, h, w,
+                 self._G(c1.conv.weight), st)
+            call("b200sr_conv3x3_dgrad", dz1, c, 0, c, self._wp(self.wp_dgrad, c1.name), in_c, B, h, w, dx_dst,
+                 dx_stride, 0, dx_stats, STATS_REPLICAS if dx_stats else 0, st)
+            return dx_dst
+
+        hi = self.p_total
+        # decoder, shallow -> deep
+        for k in (1, 2, 3, 4):
+            us = self.ups[k]
+            lvl = us.level
+            h, w, c = H >> lvl, W >> lvl, ch[lvl]
+            dcat = plan[f"dcat{lvl}"]
+            up_stats = self.up_stats.data_ptr() + 4 * self.up_st_off[k]
+            block_bwd(f"dec{k}", lvl, plan[f"cat{lvl}"], 2 * c, 2 * c, ptr(dcat), 2 * c, up_stats, dy)
+            # ConvTranspose bias gradient = column sums of the upsampled half of dcat
+            sums = self.up_stats[self.up_st_off[k]:self.up_st_off[k] + STATS_REPLICAS * 4 * c]
+            torch.sum(sums.view(STATS_REPLICAS, 2, 2 * c)[:, 0, :c], dim=0,
+                      out=self.grad_views[self._params_index(us.mod.bias)])
+            x_up = plan["bot_a2"] if k == 4 else plan[f"dec_a2_{lvl + 1}"]
+            call("b200sr_convT2x2_wgrad", ptr(dcat), 2 * c, 0, c, ptr(x_up), us.cin, 0, us.cin, B, h // 2, w // 2,
+                 self._G(us.mod.weight), st)
+            dy = s0 if dy != s0 else s1
+            call("b200sr_convT2x2_dgrad", ptr(dcat), 2 * c, 0, c, self._wp(self.wp_dgrad, us.name), us.cin, B, h // 2,
+                 w // 2, dy, us.cin, 0, st)
+        unpack_range(self.ups[4].mod.weight, hi)
+        hi = self.off_of[id(self.ups[4].mod.weight)]
+
+        # bottleneck: dx = gradient w.r.t. pool3 (dense)
+        dpool = [p for p in (s0, s1, s2) if p != dy][0]
+        # block_bwd uses the two scratch buffers != dy for dz2/dy1 and reuses dy for dz1; dx must not alias dz1
+        # -> write dx into dz2's buffer (dead after the conv2 dgrad), which is `dpool` by construction.
+        block_bwd("bottleneck", 4, plan["pool3"], ch[3], ch[3], dpool, ch[3], None, dy)
+        unpack_range(self.blocks["bottleneck"][0].conv.weight, hi)
+        hi = self.off_of[id(self.blocks["bottleneck"][0].conv.weight)]
+
+        # encoder, deep -> shallow
+        for lvl in (3, 2, 1, 0):
+            name = f"enc{lvl + 1}"
+            h, w, c = H >> lvl, W >> lvl, ch[lvl]
+            cat, dcat = plan[f"cat{lvl}"], plan[f"dcat{lvl}"]
+            dy = [p for p in (s0, s1, s2) if p != dpool][0]
+            call("b200sr_maxpool2x2_bwd", ptr(cat), 2 * c, c, dpool, ptr(dcat), 2 * c, c, c, dy, B, h, w, st)
+            if lvl == 0:
+                block_bwd(name, lvl, None, 0, 2, None, 0, None, dy, x_input=x)
+            else:
+                nxt = [p for p in (s0, s1, s2) if p != dy][0]
+                block_bwd(name, lvl, plan[f"pool{lvl - 1}"], ch[lvl - 1], ch[lvl - 1], nxt, ch[lvl - 1], None, dy)
+                dpool = nxt
+        unpack_range(self.blocks["enc1"][0].conv.weight, hi)
+        self._saved = None
+        return self.grad_views
+
+    def _params_index(self, param):
+        if not hasattr(self, "_pindex"):
+            self._pindex = {id(p): i for i, p in enumerate(self._params())}
+        return self._pindex[id(param)]

@@ -1,0 +1,140 @@
+"""TEST INFRASTRUCTURE ONLY — pins the oracle against the UNMODIFIED reference and writes tests/golden/.
+
+Run in the build container (needs /root/reference):  python oracle/make_golden.py
+  1. imports UNet from /root/reference/src/ModelLoader.py and /root/reference/src/unet_model.py (matplotlib
+     stubbed; nothing is copied) and checks both give the state_dict the b200sr mirror gives under the same seed;
+  2. checks oracle/unet_oracle.py against the reference module: eval forward, train forward, every gradient,
+     updated running statistics, one Adam step (torch.optim.Adam on the reference module);
+  3. writes tests/golden/unet_golden.npz with the reference's outputs for the seeded cases in oracle/cases.py.
+"""
+from __future__ import annotations
+
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+REF_SRC = "/root/reference/src"
+
+from oracle import cases, ssim_oracle, unet_oracle  # noqa: E402
+
+
+def import_reference():
+    sys.path.insert(0, REF_SRC)
+    for name in ("matplotlib", "matplotlib.pyplot", "tqdm"):
+        if name not in sys.modules:
+            try:
+                __import__(name)
+            except Exception:
+                m = types.ModuleType(name)
+                if name == "tqdm":
+                    m.tqdm = lambda it, **kw: it
+                sys.modules[name] = m
+    import ModelLoader as ref_loader
+    import unet_model as ref_unet
+    return ref_loader, ref_unet
+
+
+def rel(a, b):
+    return float((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30))
+
+
+def main():
+    torch.set_num_threads(os.cpu_count() or 1)
+    ref_loader, ref_unet = import_reference()
+    import b200sr
+
+    sd_ref = cases.seeded_state_dict(ref_loader.UNet)
+    sd_ref2 = cases.seeded_state_dict(ref_unet.UNet)
+    sd_mine = cases.seeded_state_dict(b200sr.UNet)
+    assert list(sd_ref) == list(sd_mine) == list(sd_ref2), "state_dict key order differs from the reference"
+    for k in sd_ref:
+        assert sd_ref[k].shape == sd_mine[k].shape and sd_ref[k].dtype == sd_mine[k].dtype, k
+        assert torch.equal(sd_ref[k], sd_mine[k]) and torch.equal(sd_ref[k], sd_ref2[k]), k
+    print(f"state_dict: {len(sd_ref)} entries identical (reference ModelLoader.UNet, unet_model.UNet, b200sr.UNet)")
+
+    out = {}
+    # ---------------- train case: reference module, MSE (the reference criterion) ----------------
+    c = cases.TRAIN_CASE
+    x, y = cases.seeded_batch(c["B"], c["H"], c["W"], c["seed"])
+    model = ref_loader.UNet()
+    model.load_state_dict(sd_ref)
+    model.train()
+    opt = torch.optim.Adam(model.parameters(), lr=1e-4)
+    pred = model(x)
+    loss = torch.nn.MSELoss()(pred, y)
+    opt.zero_grad()
+    loss.backward()
+    grads_ref = {k: p.grad.detach().clone() for k, p in model.named_parameters()}
+    # oracle vs reference
+    o_loss, o_out, o_grads, o_stats = unet_oracle.loss_and_grads(sd_ref, x, y)
+    print(f"train fwd  oracle vs reference rel-L2 {rel(o_out, pred.detach()):.3e}; loss {float(o_loss):.8f} vs {loss.item():.8f}")
+    worst = max((rel(o_grads[k], grads_ref[k]), k) for k in grads_ref if grads_ref[k].norm() > 1e-6)
+    print(f"train grads oracle vs reference worst rel-L2 {worst[0]:.3e} ({worst[1]})")
+    assert rel(o_out, pred.detach()) < 1e-5 and worst[0] < 1e-3
+    sd_after = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    for k, v in o_stats.items():
+        assert rel(v, sd_after[k]) < 1e-5, k
+    opt.step()
+    sd_stepped = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    for k in grads_ref:
+        p, _, _ = unet_oracle.adam_update(sd_ref[k], grads_ref[k], torch.zeros_like(sd_ref[k]),
+                                          torch.zeros_like(sd_ref[k]), 1)
+        assert rel(p - sd_ref[k], sd_stepped[k] - sd_ref[k]) < 1e-4 or (sd_stepped[k] - sd_ref[k]).norm() < 1e-7, k
+    print("running stats and one Adam step: oracle == reference")
+
+    out["train_loss"] = np.float64(loss.item())
+    out["train_out"] = pred.detach().numpy()
+    names = list(grads_ref)
+    out["grad_names"] = np.array(names)
+    out["grad_norms"] = np.array([grads_ref[k].double().norm().item() for k in names])
+    out["grad_heads"] = np.stack([np.pad(grads_ref[k].flatten()[:cases.GRAD_HEAD].numpy(),
+                                         (0, max(0, cases.GRAD_HEAD - grads_ref[k].numel()))) for k in names])
+    stat_names = [k for k in sd_after if k.endswith("running_mean") or k.endswith("running_var")]
+    out["stat_names"] = np.array(stat_names)
+    out["stats_after"] = np.concatenate([sd_after[k].numpy().ravel() for k in stat_names])
+    out["adam_delta_norms"] = np.array([(sd_stepped[k] - sd_ref[k]).double().norm().item() for k in names])
+    out["param_sums"] = np.array([sd_ref[k].double().sum().item() for k in names])
+
+    # ---------------- combined loss on the same case (reference module + SSIM oracle; SSIM unpinned) -------
+    for mode in ("gaussian", "uniform"):
+        model.load_state_dict(sd_ref)
+        model.train()
+        model.zero_grad()
+        pred = model(x)
+        closs = ssim_oracle.combined_loss(pred, y, 1.0, 0.005, mode)
+        closs.backward()
+        out[f"combined_{mode}_loss"] = np.float64(closs.item())
+        out[f"combined_{mode}_grad_norms"] = np.array([p.grad.double().norm().item() for _, p in model.named_parameters()])
+
+    # ---------------- eval case: running stats after the train step above -------------------------------
+    c = cases.EVAL_CASE
+    xe, _ = cases.seeded_batch(c["B"], c["H"], c["W"], c["seed"])
+    model.load_state_dict(sd_after)
+    model.eval()
+    with torch.no_grad():
+        pe = model(xe)
+        oe = unet_oracle.unet_forward(sd_after, xe, training=False)
+    print(f"eval fwd   oracle vs reference rel-L2 {rel(oe, pe):.3e}")
+    assert rel(oe, pe) < 1e-5
+    out["eval_out"] = pe.numpy()
+
+    # ---------------- SSIM oracle vs scipy restatement of skimage (mode uniform) ------------------------
+    a, b = x[0, 0].double(), (0.7 * x[0, 0] + 0.3 * y[0, 0]).double()
+    s_t = float(ssim_oracle.ssim_map(a[None, None], b[None, None], "uniform").mean())
+    s_s = ssim_oracle.ssim_skimage_restatement(a.numpy(), b.numpy())
+    print(f"SSIM uniform: torch oracle {s_t:.12f} vs skimage restatement {s_s:.12f}")
+    assert abs(s_t - s_s) < 1e-10
+    out["ssim_uniform_pair"] = np.float64(s_s)
+
+    path = os.path.join(ROOT, "tests", "golden", "unet_golden.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path), "bytes")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,91 @@
+"""TEST INFRASTRUCTURE ONLY — functional CPU (fp32/fp64) restatement of the reference UNet and its train step.
+
+Follows, op by op, /root/reference/src/unet_model.py:
+  UNetBlock (:22-36)  conv3x3(p=1,bias) -> BatchNorm2d(eps 1e-5, momentum 0.1) -> ReLU, twice
+  UNet.forward (:82-118)  4 encoder blocks with MaxPool2d(2,2), bottleneck, 4 x (ConvTranspose2d(k2,s2) ->
+                          cat([up, skip], dim=1) -> block), Conv2d 1x1 head
+  UNetTrainer.train_epoch (:168-191)  forward, MSELoss, zero_grad, backward, Adam(lr 1e-4).step
+It works directly on a state_dict (names exactly as the reference registers them), so it can be checked against
+the reference modules (oracle/make_golden.py) and run on the GPU box where /root/reference does not exist.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn.functional as F
+
+BN_EPS = 1e-5
+BN_MOMENTUM = 0.1
+ENCODERS = ("enc1", "enc2", "enc3", "enc4")
+DECODERS = (("upconv4", "dec4"), ("upconv3", "dec3"), ("upconv2", "dec2"), ("upconv1", "dec1"))
+
+
+def _block(sd, prefix, x, training, new_stats):
+    for conv_i, bn_i in ((0, 1), (3, 4)):
+        x = F.conv2d(x, sd[f"{prefix}.conv.{conv_i}.weight"], sd[f"{prefix}.conv.{conv_i}.bias"], padding=1)
+        g, b = sd[f"{prefix}.conv.{bn_i}.weight"], sd[f"{prefix}.conv.{bn_i}.bias"]
+        rm, rv = sd[f"{prefix}.conv.{bn_i}.running_mean"], sd[f"{prefix}.conv.{bn_i}.running_var"]
+        if training:
+            # F.batch_norm updates the running statistics in place: give it copies and hand them back
+            rm_new, rv_new = rm.detach().clone(), rv.detach().clone()
+            x = F.batch_norm(x, rm_new, rv_new, g, b, training=True, momentum=BN_MOMENTUM, eps=BN_EPS)
+            if new_stats is not None:
+                new_stats[f"{prefix}.conv.{bn_i}.running_mean"] = rm_new
+                new_stats[f"{prefix}.conv.{bn_i}.running_var"] = rv_new
+        else:
+            x = F.batch_norm(x, rm, rv, g, b, training=False, momentum=BN_MOMENTUM, eps=BN_EPS)
+        x = torch.relu(x)
+    return x
+
+
+def unet_forward(sd, x, training=False, new_stats=None):
+    """sd: state_dict-like mapping; x: (B,2,H,W). Returns (B,1,H,W). If training, BatchNorm uses batch statistics
+    and `new_stats` (dict) receives the updated running statistics."""
+    skips = []
+    for name in ENCODERS:
+        x = _block(sd, name, x, training, new_stats)
+        skips.append(x)
+        x = F.max_pool2d(x, kernel_size=2, stride=2)
+    x = _block(sd, "bottleneck", x, training, new_stats)
+    for (up, dec), skip in zip(DECODERS, reversed(skips)):
+        x = F.conv_transpose2d(x, sd[f"{up}.weight"], sd[f"{up}.bias"], stride=2)
+        x = torch.cat([x, skip], dim=1)
+        x = _block(sd, dec, x, training, new_stats)
+    return F.conv2d(x, sd["final_conv.weight"], sd["final_conv.bias"])
+
+
+def param_names(sd):
+    return [k for k in sd if not (k.endswith("running_mean") or k.endswith("running_var")
+                                  or k.endswith("num_batches_tracked"))]
+
+
+def loss_and_grads(sd, x, y, loss_fn=None):
+    """Train-mode forward + backward. Returns (loss, output, {name: grad}, new running stats)."""
+    leaf = {k: (v.detach().clone().requires_grad_(True) if k in set(param_names(sd)) else v) for k, v in sd.items()}
+    new_stats = {}
+    out = unet_forward(leaf, x, training=True, new_stats=new_stats)
+    loss = F.mse_loss(out, y) if loss_fn is None else loss_fn(out, y)
+    names = param_names(sd)
+    grads = torch.autograd.grad(loss, [leaf[k] for k in names])
+    return loss.detach(), out.detach(), dict(zip(names, grads)), new_stats
+
+
+def adam_update(p, g, m, v, step, lr=1e-4, b1=0.9, b2=0.999, eps=1e-8):
+    """One torch.optim.Adam step (defaults of unet_model.py:155) on plain tensors; returns (p, m, v)."""
+    m = b1 * m + (1 - b1) * g
+    v = b2 * v + (1 - b2) * g * g
+    bc1, bc2 = 1 - b1 ** step, 1 - b2 ** step
+    denom = v.sqrt() / (bc2 ** 0.5) + eps
+    return p - (lr / bc1) * m / denom, m, v
+
+
+def train_step_cpu(sd, x, y, opt_state, step, lr=1e-4, loss_fn=None):
+    """Reference train step on a state_dict (used as the timed CPU baseline in bench.py)."""
+    loss, _, grads, new_stats = loss_and_grads(sd, x, y, loss_fn)
+    with torch.no_grad():
+        for k, g in grads.items():
+            m, v = opt_state.setdefault(k, (torch.zeros_like(g), torch.zeros_like(g)))
+            p, m, v = adam_update(sd[k], g, m, v, step, lr)
+            sd[k] = p
+            opt_state[k] = (m, v)
+        sd.update(new_stats)
+    return loss

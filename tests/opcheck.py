@@ -1,0 +1,373 @@
+"""Per-op parity checks of the C-ABI kernels against plain PyTorch fp32 ops on identical (bf16-rounded) inputs.
+
+Each check returns a dict of named relative-L2 errors; the pytest wrappers (test_gpu_ops.py) assert them against
+the north-star tolerance (rel-L2 <= 1e-2 for bf16 outputs; tighter for fp32 outputs). tools/run_checks.py runs the
+same functions one per subprocess for debugging on the GPU box.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+import b200sr  # noqa: F401
+from b200sr import _lib
+from b200sr._lib import call, ptr
+from b200sr.engine import _PACK_JOB_DTYPE, _jobs_to_device
+
+DEV = "cuda"
+R = 16  # statistics replicas
+
+
+def _setup():
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+
+
+def st():
+    return _lib.current_stream_ptr()
+
+
+def rel(a, b):
+    a, b = a.double(), b.double()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def nhwc(x):
+    """(B,C,H,W) fp32 -> (B,H,W,C) bf16 contiguous"""
+    return x.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)
+
+
+def nchw(x):
+    """(B,H,W,C) any -> (B,C,H,W) fp32"""
+    return x.float().permute(0, 3, 1, 2).contiguous()
+
+
+def rnd(*shape, seed=0, scale=1.0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(DEV)
+
+
+def bf(x):
+    return x.to(torch.bfloat16).float()
+
+
+def pack(src, kind, cout, cin, dst_dtype=torch.bfloat16):
+    dst = torch.zeros(src.numel(), dtype=dst_dtype, device=DEV)
+    job = np.zeros(1, dtype=_PACK_JOB_DTYPE)
+    job[0] = (src.data_ptr(), dst.data_ptr(), kind, cout, cin, 0, src.numel())
+    jobs = _jobs_to_device(job, DEV)
+    call("b200sr_pack_jobs", jobs.data_ptr(), 1, st())
+    torch.cuda.synchronize()
+    return dst
+
+
+def slot_buffer(B, H, W, C, total_c, c_off, fill=None):
+    """A (B,H,W,total_c) bf16 buffer and the view of channels [c_off, c_off+C)."""
+    buf = torch.full((B, H, W, total_c), 7.0, dtype=torch.bfloat16, device=DEV)
+    if fill is not None:
+        buf[..., c_off:c_off + C] = fill
+    return buf
+
+
+# ------------------------------------------------------------------------------------------------------
+def conv3x3_fwd(B=2, H=16, W=32, Cin=64, Cout=128, slot=False, affine=False, seed=1):
+    _setup()
+    x = bf(rnd(B, Cin, H, W, seed=seed))
+    w = bf(rnd(Cout, Cin, 3, 3, seed=seed + 1, scale=(9 * Cin) ** -0.5))
+    ref = F.conv2d(x, w, padding=1)
+    wp = pack(w, 0, Cout, Cin)
+    x_tot, x_off = (Cin + 64, 64) if slot else (Cin, 0)
+    o_tot, o_off = (Cout + 64, 64) if slot else (Cout, 0)
+    xb = slot_buffer(B, H, W, Cin, x_tot, x_off, nhwc(x))
+    ob = slot_buffer(B, H, W, Cout, o_tot, o_off)
+    stats = torch.zeros(R, 2, Cout, device=DEV)
+    scale = shift = None
+    if affine:
+        scale = 1.0 + 0.1 * rnd(Cout, seed=seed + 2)
+        shift = 0.1 * rnd(Cout, seed=seed + 3)
+        ref = torch.relu(ref * scale[None, :, None, None] + shift[None, :, None, None])
+    call("b200sr_conv3x3_fwd", ptr(xb), x_tot, x_off, Cin, ptr(wp), Cout, B, H, W, ptr(ob), o_tot, o_off,
+         ptr(scale), ptr(shift), 1 if affine else 0, ptr(stats), R, st())
+    torch.cuda.synchronize()
+    out = nchw(ob[..., o_off:o_off + Cout])
+    res = {"out": rel(out, ref)}
+    s = stats.sum(0)
+    res["stats_sum"] = rel(s[0], out.sum(dim=(0, 2, 3)))
+    res["stats_sq"] = rel(s[1], (out * out).sum(dim=(0, 2, 3)))
+    if slot:
+        res["slot_untouched"] = float((ob[..., :o_off].float() - 7.0).abs().max())
+    return res
+
+
+def conv3x3_dgrad(B=2, H=16, W=32, Cin=64, Cout=128, seed=2):
+    _setup()
+    dy = bf(rnd(B, Cout, H, W, seed=seed))
+    w = bf(rnd(Cout, Cin, 3, 3, seed=seed + 1, scale=(9 * Cout) ** -0.5))
+    ref = F.conv_transpose2d(dy, w, padding=1)  # data gradient of a stride-1 conv
+    wp = pack(w, 1, Cout, Cin)
+    dyb = nhwc(dy)
+    dxb = torch.zeros(B, H, W, Cin, dtype=torch.bfloat16, device=DEV)
+    stats = torch.zeros(R, 2, Cin, device=DEV)
+    call("b200sr_conv3x3_dgrad", ptr(dyb), Cout, 0, Cout, ptr(wp), Cin, B, H, W, ptr(dxb), Cin, 0, ptr(stats), R, st())
+    torch.cuda.synchronize()
+    out = nchw(dxb)
+    return {"dx": rel(out, ref), "colsum": rel(stats.sum(0)[0], out.sum(dim=(0, 2, 3)))}
+
+
+def conv3x3_wgrad(B=2, H=16, W=32, Cin=64, Cout=128, seed=3, slot=False):
+    _setup()
+    x = bf(rnd(B, Cin, H, W, seed=seed))
+    dz = bf(rnd(B, Cout, H, W, seed=seed + 1))
+    ref = torch.nn.grad.conv2d_weight(x, (Cout, Cin, 3, 3), dz, padding=1)
+    x_tot, x_off = (Cin + 64, 64) if slot else (Cin, 0)
+    xb = slot_buffer(B, H, W, Cin, x_tot, x_off, nhwc(x))
+    dzb = nhwc(dz)
+    G = torch.zeros(9 * Cin * Cout, device=DEV)
+    call("b200sr_conv3x3_wgrad", ptr(xb), x_tot, x_off, Cin, ptr(dzb), Cout, 0, Cout, B, H, W, ptr(G), st())
+    torch.cuda.synchronize()
+    dw = pack(G, 4, Cout, Cin, torch.float32).view(Cout, Cin, 3, 3)
+    return {"dw": rel(dw, ref)}
+
+
+def convT_fwd(B=2, H=8, W=16, Cin=128, Cout=64, seed=4):
+    _setup()
+    x = bf(rnd(B, Cin, H, W, seed=seed))
+    w = bf(rnd(Cin, Cout, 2, 2, seed=seed + 1, scale=Cin ** -0.5))
+    bias = rnd(Cout, seed=seed + 2, scale=0.1)
+    ref = F.conv_transpose2d(x, w, bias, stride=2)
+    wp = pack(w, 2, Cout, Cin)
+    xb = nhwc(x)
+    ob = slot_buffer(B, 2 * H, 2 * W, Cout, 2 * Cout, 0)
+    call("b200sr_convT2x2_fwd", ptr(xb), Cin, 0, Cin, ptr(wp), Cout, ptr(bias), B, H, W, ptr(ob), 2 * Cout, 0, st())
+    torch.cuda.synchronize()
+    return {"out": rel(nchw(ob[..., :Cout]), ref), "slot_untouched": float((ob[..., Cout:].float() - 7.0).abs().max())}
+
+
+def convT_dgrad(B=2, H=8, W=16, Cin=128, Cout=64, seed=5):
+    _setup()
+    dup = bf(rnd(B, Cout, 2 * H, 2 * W, seed=seed))
+    w = bf(rnd(Cin, Cout, 2, 2, seed=seed + 1, scale=(4 * Cout) ** -0.5))
+    ref = F.conv2d(dup, w, stride=2)  # data gradient of ConvTranspose2d(k2,s2): weight (Cin,Cout,2,2) as conv OIHW
+    wp = pack(w, 3, Cout, Cin)
+    db = slot_buffer(B, 2 * H, 2 * W, Cout, 2 * Cout, 0, nhwc(dup))
+    dxb = torch.zeros(B, H, W, Cin, dtype=torch.bfloat16, device=DEV)
+    call("b200sr_convT2x2_dgrad", ptr(db), 2 * Cout, 0, Cout, ptr(wp), Cin, B, H, W, ptr(dxb), Cin, 0, st())
+    torch.cuda.synchronize()
+    return {"dx": rel(nchw(dxb), ref)}
+
+
+def convT_wgrad(B=2, H=8, W=16, Cin=128, Cout=64, seed=6):
+    _setup()
+    x = bf(rnd(B, Cin, H, W, seed=seed)).requires_grad_(False)
+    dup = bf(rnd(B, Cout, 2 * H, 2 * W, seed=seed + 1))
+    w = torch.zeros(Cin, Cout, 2, 2, device=DEV, requires_grad=True)
+    (F.conv_transpose2d(x, w, stride=2) * dup).sum().backward()
+    ref = w.grad
+    db = slot_buffer(B, 2 * H, 2 * W, Cout, 2 * Cout, 0, nhwc(dup))
+    xb = nhwc(x)
+    G = torch.zeros(4 * Cin * Cout, device=DEV)
+    call("b200sr_convT2x2_wgrad", ptr(db), 2 * Cout, 0, Cout, ptr(xb), Cin, 0, Cin, B, H, W, ptr(G), st())
+    torch.cuda.synchronize()
+    dw = pack(G, 5, Cout, Cin, torch.float32).view(Cin, Cout, 2, 2)
+    return {"dw": rel(dw, ref)}
+
+
+def conv1(B=2, H=32, W=48, seed=7):
+    _setup()
+    x = rnd(B, 2, H, W, seed=seed)
+    w = rnd(64, 2, 3, 3, seed=seed + 1, scale=18 ** -0.5)
+    ref = F.conv2d(x, w, padding=1)
+    ob = torch.zeros(B, H, W, 64, dtype=torch.bfloat16, device=DEV)
+    stats = torch.zeros(R, 2, 64, device=DEV)
+    call("b200sr_conv1_fwd", ptr(x), ptr(w), None, None, 0, ptr(ob), ptr(stats), R, B, H, W, st())
+    torch.cuda.synchronize()
+    out = nchw(ob)
+    res = {"out": rel(out, ref), "stats_sum": rel(stats.sum(0)[0], out.sum(dim=(0, 2, 3))),
+           "stats_sq": rel(stats.sum(0)[1], (out * out).sum(dim=(0, 2, 3)))}
+    dz = bf(rnd(B, 64, H, W, seed=seed + 2))
+    refw = torch.nn.grad.conv2d_weight(x, (64, 2, 3, 3), dz, padding=1)
+    dw = torch.zeros(64, 2, 3, 3, device=DEV)
+    call("b200sr_conv1_wgrad", ptr(x), ptr(nhwc(dz)), ptr(dw), B, H, W, st())
+    torch.cuda.synchronize()
+    res["dw"] = rel(dw, refw)
+    return res
+
+
+def bn_train(B=2, H=16, W=32, C=128, pool=True, seed=8):
+    """bn_finalize + bnrelu_apply(+pool) against F.batch_norm + relu + max_pool2d."""
+    _setup()
+    z = bf(rnd(B, C, H, W, seed=seed) * 1.5 + 0.3)
+    gamma, beta = 1 + 0.1 * rnd(C, seed=seed + 1), 0.1 * rnd(C, seed=seed + 2)
+    cbias = 0.1 * rnd(C, seed=seed + 3)
+    rm, rv = 0.2 * rnd(C, seed=seed + 4), 1 + 0.1 * rnd(C, seed=seed + 5).abs()
+    rm_ref, rv_ref = rm.clone(), rv.clone()
+    ref = torch.relu(F.batch_norm(z + cbias[None, :, None, None], rm_ref, rv_ref, gamma, beta, True, 0.1, 1e-5))
+    stats = torch.zeros(R, 2, C, device=DEV)
+    stats[0, 0] = z.sum(dim=(0, 2, 3))
+    stats[0, 1] = (z * z).sum(dim=(0, 2, 3))
+    ws = torch.zeros(4, C, device=DEV)
+    call("b200sr_bn_finalize", ptr(stats), R, C, float(B * H * W), ptr(gamma), ptr(beta), ptr(cbias), 1e-5, 0.1,
+         ptr(ws[0]), ptr(ws[1]), ptr(ws[2]), ptr(ws[3]), ptr(rm), ptr(rv), st())
+    zb = nhwc(z)
+    act = slot_buffer(B, H, W, C, 2 * C, C)
+    pooled = torch.zeros(B, H // 2, W // 2, C, dtype=torch.bfloat16, device=DEV) if pool else None
+    call("b200sr_bnrelu_apply", ptr(zb), C, ptr(ws[0]), ptr(ws[1]), ptr(act), 2 * C, C, ptr(pooled), B, H, W, st())
+    torch.cuda.synchronize()
+    a = nchw(act[..., C:])
+    res = {"act": rel(a, ref), "running_mean": rel(rm, rm_ref), "running_var": rel(rv, rv_ref),
+           "slot_untouched": float((act[..., :C].float() - 7.0).abs().max())}
+    if pool:
+        res["pool_exact"] = float((nchw(pooled) - F.max_pool2d(a, 2)).abs().max())
+        p2 = torch.zeros_like(pooled)
+        call("b200sr_maxpool2x2_fwd", ptr(act), 2 * C, C, C, ptr(p2), B, H, W, st())
+        torch.cuda.synchronize()
+        res["maxpool_fwd_exact"] = float((p2.float() - pooled.float()).abs().max())
+    return res
+
+
+def maxpool_bwd(B=2, H=16, W=32, C=64, seed=9):
+    _setup()
+    # coarse values force ties: the first maximum in row-major order must get the gradient (ATen)
+    a = (rnd(B, C, H, W, seed=seed) * 2).round().clamp_min(0) / 2
+    a = bf(a).requires_grad_(True)
+    dpool = bf(rnd(B, C, H // 2, W // 2, seed=seed + 1))
+    dskip = bf(rnd(B, C, H, W, seed=seed + 2))
+    F.max_pool2d(a, 2).backward(dpool)
+    ref = bf(a.grad + dskip)
+    ab = slot_buffer(B, H, W, C, 2 * C, C, nhwc(a.detach()))
+    dsb = slot_buffer(B, H, W, C, 2 * C, C, nhwc(dskip))
+    dy = torch.zeros(B, H, W, C, dtype=torch.bfloat16, device=DEV)
+    call("b200sr_maxpool2x2_bwd", ptr(ab), 2 * C, C, ptr(nhwc(dpool)), ptr(dsb), 2 * C, C, C, ptr(dy), B, H, W, st())
+    torch.cuda.synchronize()
+    return {"dy_exact": float((nchw(dy) - ref).abs().max())}
+
+
+def bn_bwd(B=2, H=16, W=32, C=128, seed=10):
+    _setup()
+    z = bf(rnd(B, C, H, W, seed=seed) * 1.5 + 0.3).requires_grad_(True)
+    gamma = (1 + 0.1 * rnd(C, seed=seed + 1)).requires_grad_(True)
+    beta = (0.1 * rnd(C, seed=seed + 2)).requires_grad_(True)
+    dy = bf(rnd(B, C, H, W, seed=seed + 3))
+    y = torch.relu(F.batch_norm(z, None, None, gamma, beta, True, 0.1, 1e-5))
+    y.backward(dy)
+    N = B * H * W
+    zd = z.detach()
+    mean = zd.mean(dim=(0, 2, 3))
+    invstd = torch.rsqrt(zd.var(dim=(0, 2, 3), unbiased=False) + 1e-5)
+    scale = (gamma.detach() * invstd).contiguous()
+    shift = (beta.detach() - mean * scale).contiguous()
+    sums = torch.zeros(R, 2, C, device=DEV)
+    c12 = torch.zeros(2, C, device=DEV)
+    dgb = torch.zeros(2, C, device=DEV)
+    zb, dyb = nhwc(zd), nhwc(dy)
+    dz = torch.zeros(B, H, W, C, dtype=torch.bfloat16, device=DEV)
+    call("b200sr_bn_bwd_reduce", ptr(dyb), C, 0, ptr(zb), C, ptr(scale), ptr(shift), ptr(mean), ptr(invstd), ptr(sums),
+         R, N, st())
+    call("b200sr_bn_bwd_finalize", ptr(sums), R, C, float(N), ptr(c12[0]), ptr(c12[1]), ptr(dgb[0]), ptr(dgb[1]), st())
+    call("b200sr_bn_bwd_apply", ptr(dyb), C, 0, ptr(zb), C, ptr(scale), ptr(shift), ptr(mean), ptr(invstd), ptr(c12[0]),
+         ptr(c12[1]), ptr(dz), N, st())
+    torch.cuda.synchronize()
+    return {"dz": rel(nchw(dz), z.grad), "dgamma": rel(dgb[0], gamma.grad), "dbeta": rel(dgb[1], beta.grad)}
+
+
+def head(B=2, H=16, W=32, seed=11):
+    _setup()
+    a = bf(rnd(B, 64, H, W, seed=seed)).requires_grad_(True)
+    w = rnd(1, 64, 1, 1, seed=seed + 1, scale=0.125).requires_grad_(True)
+    b = rnd(1, seed=seed + 2).requires_grad_(True)
+    dout = rnd(B, 1, H, W, seed=seed + 3)
+    y = F.conv2d(a, w, b)
+    y.backward(dout)
+    ab = nhwc(a.detach())
+    out = torch.zeros(B, 1, H, W, device=DEV)
+    call("b200sr_head_fwd", ptr(ab), ptr(w), ptr(b), ptr(out), B * H * W, st())
+    dact = torch.zeros(B, H, W, 64, dtype=torch.bfloat16, device=DEV)
+    dw, db = torch.zeros(64, device=DEV), torch.zeros(1, device=DEV)
+    call("b200sr_head_bwd", ptr(dout), ptr(ab), ptr(w), ptr(dact), ptr(dw), ptr(db), B * H * W, st())
+    torch.cuda.synchronize()
+    return {"out": rel(out, y.detach()), "dact": rel(nchw(dact), a.grad), "dw": rel(dw, w.grad.flatten()),
+            "db": rel(db, b.grad)}
+
+
+def mse_ssim(B=2, H=96, W=80, mode="gaussian", w_ssim=0.5, seed=12):
+    _setup()
+    from oracle import ssim_oracle
+    y = rnd(B, 1, H, W, seed=seed)
+    x = (0.6 * y + 0.4 * rnd(B, 1, H, W, seed=seed + 1)).double().requires_grad_(True)
+    loss_ref = ssim_oracle.combined_loss(x, y.double(), 1.0, w_ssim, mode)
+    loss_ref.backward()
+    crit = b200sr.CombinedLoss(1.0, w_ssim, mode)
+    loss, grad = crit.value_and_grad(x.detach().float(), y)
+    torch.cuda.synchronize()
+    return {"loss": abs(float(loss) - float(loss_ref)) / abs(float(loss_ref)), "grad": rel(grad, x.grad)}
+
+
+def adam(n=100003, seed=13):
+    _setup()
+    from oracle import unet_oracle
+    n4 = (n + 3) // 4 * 4
+    p, g = rnd(n4, seed=seed), rnd(n4, seed=seed + 1, scale=1e-2)
+    m, v = torch.zeros_like(p), torch.zeros_like(p)
+    pr, mr, vr = p.clone().double(), m.clone().double(), v.clone().double()
+    for step in (1, 2, 3):
+        call("b200sr_adam_step", ptr(p), ptr(g), ptr(m), ptr(v), n, 1e-4, 0.9, 0.999, 1e-8, step, 0.5, st())
+        pr2, mr, vr = unet_oracle.adam_update(pr, 0.5 * g.double(), mr, vr, step)
+        pr = torch.cat([pr2[:n], pr[n:]])
+        mr[n:] = 0
+        vr[n:] = 0
+    torch.cuda.synchronize()
+    return {"delta": rel(p.double() - rnd(n4, seed=seed).double(), pr - rnd(n4, seed=seed).double()),
+            "m": rel(m, mr), "v": rel(v, vr)}
+
+
+def layout_casts(B=2, C=24, H=8, W=12, seed=14):
+    _setup()
+    x = rnd(B, C, H, W, seed=seed)
+    o = torch.zeros(B, H, W, C, dtype=torch.bfloat16, device=DEV)
+    call("b200sr_nchw_f32_to_nhwc_bf16", ptr(x), ptr(o), B, C, H, W, st())
+    back = torch.zeros(B, C, H, W, device=DEV)
+    call("b200sr_nhwc_bf16_to_nchw_f32", ptr(o), C, 0, ptr(back), B, C, H, W, st())
+    torch.cuda.synchronize()
+    return {"fwd_exact": float((nchw(o) - bf(x)).abs().max()), "back_exact": float((back - bf(x)).abs().max())}
+
+
+# name -> (function, kwargs, {metric: tolerance})
+BF16 = 1e-2
+CHECKS = {
+    "conv3x3_fwd_n128": (conv3x3_fwd, {}, {"out": BF16, "stats_sum": 1e-3, "stats_sq": 1e-3}),
+    "conv3x3_fwd_n64_slot": (conv3x3_fwd, dict(Cin=128, Cout=64, slot=True, affine=True, B=1, H=8, W=16),
+                             {"out": BF16, "slot_untouched": 0.0}),
+    "conv3x3_fwd_n256": (conv3x3_fwd, dict(Cin=256, Cout=256, B=3, H=8, W=16), {"out": BF16, "stats_sq": 1e-3}),
+    "conv3x3_fwd_deep": (conv3x3_fwd, dict(Cin=1024, Cout=512, B=1, H=16, W=16, affine=True), {"out": BF16}),
+    "conv3x3_dgrad": (conv3x3_dgrad, {}, {"dx": BF16, "colsum": 1e-3}),
+    "conv3x3_dgrad_wide": (conv3x3_dgrad, dict(Cin=256, Cout=64, B=1, H=24, W=16), {"dx": BF16}),
+    "conv3x3_wgrad_n128": (conv3x3_wgrad, {}, {"dw": BF16}),
+    "conv3x3_wgrad_n64_slot": (conv3x3_wgrad, dict(Cin=128, Cout=64, slot=True, H=8, W=48), {"dw": BF16}),
+    "conv3x3_wgrad_n256": (conv3x3_wgrad, dict(Cin=320, Cout=256, B=3, H=8, W=16), {"dw": BF16}),
+    "convT_fwd": (convT_fwd, {}, {"out": BF16, "slot_untouched": 0.0}),
+    "convT_fwd_big": (convT_fwd, dict(Cin=1024, Cout=512, B=1, H=8, W=16), {"out": BF16}),
+    "convT_dgrad": (convT_dgrad, {}, {"dx": BF16}),
+    "convT_wgrad": (convT_wgrad, {}, {"dw": BF16}),
+    "convT_wgrad_big": (convT_wgrad, dict(Cin=512, Cout=256, B=1, H=8, W=16), {"dw": BF16}),
+    "conv1": (conv1, {}, {"out": BF16, "stats_sum": 1e-3, "stats_sq": 1e-3, "dw": 1e-3}),
+    "bn_train_pool": (bn_train, {}, {"act": BF16, "running_mean": 1e-5, "running_var": 1e-4, "pool_exact": 0.0,
+                                     "maxpool_fwd_exact": 0.0, "slot_untouched": 0.0}),
+    "maxpool_bwd_ties": (maxpool_bwd, {}, {"dy_exact": 0.0}),
+    "bn_bwd": (bn_bwd, {}, {"dz": BF16, "dgamma": 1e-3, "dbeta": 1e-3}),
+    "head": (head, {}, {"out": 1e-5, "dact": BF16, "dw": 1e-4, "db": 1e-4}),
+    "mse_ssim_gaussian": (mse_ssim, {}, {"loss": 1e-5, "grad": 1e-4}),
+    "mse_ssim_uniform": (mse_ssim, dict(mode="uniform", H=64, W=100), {"loss": 1e-5, "grad": 1e-4}),
+    "mse_only": (mse_ssim, dict(w_ssim=0.0), {"loss": 1e-5, "grad": 1e-5}),
+    "adam": (adam, {}, {"delta": 1e-4, "m": 1e-5, "v": 1e-5}),
+    "layout_casts": (layout_casts, {}, {"fwd_exact": 0.0, "back_exact": 0.0}),
+}
+
+
+def run(name):
+    fn, kw, tol = CHECKS[name]
+    res = fn(**kw)
+    bad = {k: (res[k], t) for k, t in tol.items() if not (res[k] <= t)}
+    return res, bad
