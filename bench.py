@@ -1,0 +1,300 @@
+#!/usr/bin/env python
+"""Benchmark of the b200sr hot path: UNet 2->1 slice triplets/sec @256^2 (BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (one process per GPU)
+  python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on the host CPU cores
+
+Workload at every N: BASELINE.json configs[2] restricted to the hot path the north star names — UNet train step
+with the combined MSE + 0.005*(1-SSIM) loss and Adam(lr 1e-4), bf16 tensor-core compute, batch 32 per GPU at
+256x256, data-parallel by batch (weak scaling; gradient all-reduce over NCCL overlapped with backward). The VGG
+perceptual term of configs[2] is a "next" row and is not part of the timed step. Inference
+throughput (configs[0]: B=8 fp32 in/out, eval mode) is reported in the same JSON line under "inference".
+
+Prints ONE JSON line (rank 0). See DESIGN.md §Measurement for how every field is produced.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+TRAIN_GFLOP_PER_TRIPLET = 288.627   # fwd + dgrad + wgrad, 2*MACs
+FWD_GFLOP_PER_TRIPLET = 96.259
+METRIC = "unet_train_triplets_per_sec_256x256"
+UNIT = "triplets/s"
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"bf16_tflops": p["bf16_tflops"], "bf16_tflops_sustained": p.get("bf16_tflops_sustained"),
+                "hbm_gbs": p["hbm_gbs"], "source": "measured (MEASURED_PEAKS.json)"}
+    return {"bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "hbm_gbs": 6650.0,
+            "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu_index, self.proc = gpu_index, None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.gpu_index), "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out, _ = self.proc.communicate()
+        sm, mx, pw, reasons = [], [], [], set()
+        for line in out.splitlines():
+            f = [t.strip() for t in line.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "power_w_max": max(pw), "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------------------------------------
+# reference arm: the reference algorithm (oracle port; the reference is Python/PyTorch and cannot travel to the
+# GPU box) on the host CPU cores
+# ----------------------------------------------------------------------------------------------------------
+def cpu_train_sample(batch, steps, warmup, threads=None):
+    import torch
+    import b200sr
+    from oracle import cases, ssim_oracle, unet_oracle
+    threads = threads or os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    sd = cases.seeded_state_dict(b200sr.UNet)
+    x, y = cases.seeded_batch(batch, 256, 256, 1234)
+    loss_fn = lambda p, t: ssim_oracle.combined_loss(p, t, 1.0, 0.005, "gaussian")
+    opt_state = {}
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        unet_oracle.train_step_cpu(sd, x, y, opt_state, i + 1, loss_fn=loss_fn)
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    total = sum(times)
+    return {"value": batch * steps / total, "ms_per_step": 1e3 * total / steps, "cores": threads,
+            "sample": f"{steps} train steps (MSE+0.005*(1-SSIM), Adam) at batch {batch}, 256x256 fp32, "
+                      f"torch {torch.__version__} CPU, {warmup} warm-up"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    batch = 4
+    r = cpu_train_sample(batch, args.steps, max(args.warmup, 1))
+    line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "unet_train_combined_mse_ssim_b32_256x256 (configs[2] hot path; CPU sample at "
+                                   f"batch {batch} per step)", "global_batch": batch},
+            "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
+                             "sample": r["sample"]},
+            "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------------------------
+# this repo's arm
+# ----------------------------------------------------------------------------------------------------------
+def run_b200sr(args):
+    import torch
+    import torch.distributed as dist
+    import b200sr
+    from b200sr import _lib
+    from oracle import cases
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B, H, W = args.batch, 256, 256
+    peaks = load_peaks()
+
+    model = b200sr.UNet()
+    model.load_state_dict(cases.seeded_state_dict(b200sr.UNet))
+    trainer = b200sr.UNetTrainer(model, device=dev, loss="combined", ssim_weight=0.005, learning_rate=1e-4,
+                                 model_save_dir="/tmp/b200sr_bench", verbose=False)
+    gen = b200sr.SyntheticTripletGenerator(B, H, W, device=dev, seed=1234, rank=rank)
+    ring = [gen.next() for _ in range(4)]
+    host_ring = [(x.cpu().pin_memory(), y.cpu().pin_memory()) for x, y in ring]
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for i in range(warmup):
+            fn(i)
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(warmup + i)
+        e1.record()
+        sync_all()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    # ---- value: K train steps, inputs resident in HBM ------------------------------------------------------
+    def step_resident(i):
+        x, y = ring[i % len(ring)]
+        trainer.train_step(x, y)
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    _lib.LAUNCH_COUNTER["n"] = 0
+    total_ms = timed(step_resident, args.steps, args.warmup)
+    launches_total = _lib.LAUNCH_COUNTER["n"]
+    clocks = sampler.stop() if rank == 0 else None
+    ms_per_step = total_ms / args.steps
+    value = world * B * args.steps / (total_ms / 1e3)
+    launches_timed = launches_total * args.steps // (args.steps + args.warmup)
+
+    # ---- e2e: same step through the public trainer API from pinned host buffers, loss read back each step ---
+    loss_host = torch.zeros((), dtype=torch.float32).pin_memory()
+
+    def step_e2e(i):
+        hx, hy = host_ring[i % len(host_ring)]
+        x = hx.to(dev, non_blocking=True)
+        y = hy.to(dev, non_blocking=True)
+        loss = trainer.train_step(x, y)
+        loss_host.copy_(loss, non_blocking=False)
+
+    e2e_ms = timed(step_e2e, args.steps, 3)
+    e2e_value = world * B * args.steps / (e2e_ms / 1e3)
+    h2d = sum(t.numel() * t.element_size() for t in host_ring[0])
+
+    # ---- inference (configs[0] shape: B=8 fp32 in/out, eval mode; batch-sharded, no collective) --------------
+    model.eval()
+    xi = ring[0][0][:8].contiguous()
+    with torch.no_grad():
+        inf_ms = timed(lambda i: model(xi), 20, 5)
+        inf_value = world * 8 * 20 / (inf_ms / 1e3)
+        xb = ring[0][0]
+        inf_big_ms = timed(lambda i: model(xb), 10, 3)
+        inf_big_value = world * B * 10 / (inf_big_ms / 1e3)
+
+    # ---- roofline of the dominant kernel (tensor-core implicit GEMM), timed live with CUDA events ------------
+    roofline = None
+    if rank == 0:
+        model.train()
+        prof = _lib.enable_profiling(True)
+        for i in range(3):
+            step_resident(i)
+        torch.cuda.synchronize()
+        agg = _lib.collect_profile()
+        _lib.enable_profiling(False)
+        gemm = {k: v for k, v in agg.items() if k in _lib.GEMM_OPS}
+        g_ms = sum(v["ms"] for v in gemm.values())
+        g_flop = sum(v["flop"] for v in gemm.values())
+        g_n = sum(v["n"] for v in gemm.values())
+        all_ms = sum(v["ms"] for v in agg.values())
+        achieved = g_flop / (g_ms / 1e3) / 1e12
+        peak = peaks["bf16_tflops_sustained"] or peaks["bf16_tflops"]
+        roofline = {"bound": "tensor", "kernel": "igemm_kernel + wgrad_kernel (tcgen05 implicit GEMM: conv3x3 "
+                    "fwd/dgrad/wgrad, ConvT fwd/dgrad/wgrad)", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                    "frac": achieved / peak, "traffic": None,
+                    "peak_source": peaks["source"] + " sustained bf16 (kernels timed inside a long step); burst "
+                                   f"{peaks['bf16_tflops']}",
+                    "launches_per_step": g_n // 3, "avg_launch_ms": g_ms / max(g_n, 1),
+                    "gflop_per_launch": g_flop / max(g_n, 1) / 1e9, "share_of_step": g_ms / all_ms,
+                    "per_op": {k: {"ms_per_step": v["ms"] / 3, "tflops": (v["flop"] / (v["ms"] / 1e3) / 1e12)
+                                   if v["flop"] else None, "gbs": (v["bytes"] / (v["ms"] / 1e3) / 1e9)
+                                   if v["bytes"] else None, "launches": v["n"] // 3}
+                               for k, v in sorted(agg.items(), key=lambda kv: -kv[1]["ms"])},
+                    "step_tflops": TRAIN_GFLOP_PER_TRIPLET * B / ms_per_step,
+                    "step_frac_of_peak": TRAIN_GFLOP_PER_TRIPLET * B / ms_per_step / peak}
+
+    # ---- CPU baseline (bounded sample, rank 0, N=1 only) -------------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        r = cpu_train_sample(4, 3, 1)
+        cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": "unet_train_combined_mse_ssim_b32_256x256 (BASELINE configs[2] hot path: "
+                                       "UNet fwd+bwd, MSE+0.005*(1-SSIM), Adam; VGG term is a next row)",
+                           "global_batch": world * B, "per_gpu_batch": B, "parallelism": f"dp{world}",
+                           "l2": "per-step working set (activations + gradients, several GB) >> 126 MB L2; ring of 4 "
+                                 "distinct input batches"},
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                        "ms_per_step": e2e_ms / args.steps},
+                "gpu_launches": launches_timed, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+                "inference": {"value": inf_value, "unit": UNIT, "batch_per_gpu": 8, "ms_per_batch": inf_ms / 20,
+                              "workload": "BASELINE configs[0]: UNet eval forward (B=8,2,256,256)->(B,1,256,256), "
+                                          "fp32 in/out, bf16 tensor-core compute",
+                              "value_b32": inf_big_value, "frac_of_peak_b32":
+                                  FWD_GFLOP_PER_TRIPLET * inf_big_value / world / 1e3 / peaks["bf16_tflops"]}}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200sr", choices=["b200sr", "reference"])
+    ap.add_argument("--batch", type=int, default=32, help="per-GPU batch (BASELINE configs[2]: 32)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline sample")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200sr" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200sr(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -81,10 +81,84 @@ def last_error() -> str:
     return msg.decode() if msg else ""
 
 
+# ---- launch accounting and optional per-call CUDA-event timing (used by bench.py for the roofline) ------------
+LAUNCH_COUNTER = {"n": 0}
+GEMM_OPS = ("b200sr_conv3x3_fwd", "b200sr_conv3x3_dgrad", "b200sr_conv3x3_wgrad", "b200sr_convT2x2_fwd",
+            "b200sr_convT2x2_dgrad", "b200sr_convT2x2_wgrad")
+_profile = None  # list of (name, start_event, end_event, flop, bytes) while profiling is enabled
+
+
+def _cost(name, a):
+    """Algorithmic (flop, bytes) of one call, from its argument list (see include/b200sr.h for the order)."""
+    if name in ("b200sr_conv3x3_fwd", "b200sr_conv3x3_dgrad"):
+        return 2.0 * a[6] * a[7] * a[8] * a[3] * a[5] * 9, 0.0
+    if name in ("b200sr_convT2x2_dgrad",):
+        return 2.0 * a[6] * a[7] * a[8] * a[3] * a[5] * 4, 0.0
+    if name == "b200sr_convT2x2_fwd":
+        return 2.0 * a[7] * a[8] * a[9] * a[3] * a[5] * 4, 0.0
+    if name == "b200sr_conv3x3_wgrad":
+        return 2.0 * a[8] * a[9] * a[10] * a[3] * a[7] * 9, 0.0
+    if name == "b200sr_convT2x2_wgrad":
+        return 2.0 * a[8] * a[9] * a[10] * a[3] * a[7] * 4, 0.0
+    if name == "b200sr_bnrelu_apply":
+        n = a[8] * a[9] * a[10] * a[1] * 2.0
+        return 0.0, n * (2.25 if a[7] else 2.0)
+    if name == "b200sr_maxpool2x2_fwd":
+        return 0.0, a[5] * a[6] * a[7] * a[3] * 2.0 * 1.25
+    if name == "b200sr_maxpool2x2_bwd":
+        return 0.0, a[9] * a[10] * a[11] * a[7] * 2.0 * (3.25 if a[4] else 2.25)
+    if name == "b200sr_bn_bwd_reduce":
+        return 0.0, a[11] * a[4] * 2.0 * 2
+    if name == "b200sr_bn_bwd_apply":
+        return 0.0, a[12] * a[4] * 2.0 * 3
+    if name == "b200sr_head_fwd":
+        return 0.0, a[4] * (128.0 + 4)
+    if name == "b200sr_head_bwd":
+        return 0.0, a[6] * (4.0 + 128 + 128)
+    if name == "b200sr_mse_ssim":
+        return 0.0, a[4] * a[5] * a[6] * 4.0 * (3 if a[2] else 2)
+    if name == "b200sr_adam_step":
+        return 0.0, a[4] * 4.0 * 7
+    if name == "b200sr_conv1_fwd":
+        return 0.0, a[8] * a[9] * a[10] * (8.0 + 128)
+    if name == "b200sr_conv1_wgrad":
+        return 0.0, a[3] * a[4] * a[5] * (8.0 + 128)
+    return 0.0, 0.0
+
+
+def enable_profiling(on: bool):
+    global _profile
+    _profile = [] if on else None
+    return _profile
+
+
+def collect_profile():
+    """Aggregate the recorded calls: {op: {"ms", "n", "flop", "bytes"}} (synchronises)."""
+    import torch
+    torch.cuda.synchronize()
+    agg = {}
+    for name, e0, e1, flop, nbytes in _profile or []:
+        d = agg.setdefault(name, {"ms": 0.0, "n": 0, "flop": 0.0, "bytes": 0.0})
+        d["ms"] += e0.elapsed_time(e1)
+        d["n"] += 1
+        d["flop"] += flop
+        d["bytes"] += nbytes
+    return agg
+
+
 def call(name: str, *args):
     """Call an exported op; non-zero return codes become B200SRError(last_error)."""
     fn = getattr(load(), name)
-    rc = fn(*args)
+    if _profile is not None:
+        import torch
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = fn(*args)
+        e1.record()
+        _profile.append((name, e0, e1) + _cost(name, args))
+    else:
+        rc = fn(*args)
+    LAUNCH_COUNTER["n"] += 1
     if rc != 0:
         raise B200SRError(f"{name} failed (code {rc}): {last_error()}")
 

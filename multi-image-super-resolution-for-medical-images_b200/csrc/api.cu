@@ -233,6 +233,10 @@ int run_igemm(int a_mode, const void* a, int a_stride, int a_coff, int Ca, int n
     args.col_scale = col_scale;
     args.col_shift = col_shift;
     args.stats = stats;
+    {
+        const char* dbg = getenv("B200SR_DEBUG_STAGE");
+        args.debug_stage = dbg ? atoi(dbg) : 0;
+    }
     const long long grid = static_cast<long long>(B) * args.tiles_hw * args.n_tiles;
     B2_CHECK_ARG(grid < (1ll << 31));
     switch (block_n) {
@@ -313,7 +317,51 @@ int run_wgrad(int t_mode, const void* t, int t_stride, int t_coff, int Ct, int n
 // =================================================================================================
 // exported C ABI
 // =================================================================================================
+// bring-up aid: one 2-D TMA box load (no swizzle) of a [rows][64] bf16 tile, copied back to global memory
+__global__ void debug_tma_kernel(const __grid_constant__ CUtensorMap map, __nv_bfloat16* dst, int rows, int c0, int c1) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 64 * 128);
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        fence_barrier_init();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        mbar_arrive_expect_tx(bar, rows * 128);
+        tma_load_2d(&map, bar, smem, c0, c1);
+    }
+    mbar_wait(bar, 0);
+    const __nv_bfloat16* s = reinterpret_cast<const __nv_bfloat16*>(smem);
+    for (int i = threadIdx.x; i < rows * 64; i += blockDim.x) dst[i] = s[i];
+}
+
 extern "C" {
+
+// bring-up aids (not part of the public header)
+int b200sr_debug_encode(const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides, const uint32_t* box,
+                        int swizzle, void* out128) {
+    EncodeTiledFn enc = get_encode_fn();
+    if (enc == nullptr) return fail(B200SR_ECUDA, "no encode fn");
+    cuuint64_t gd[5], gs[4];
+    cuuint32_t gb[5], es[5];
+    for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; gb[i] = box[i]; es[i] = 1; if (i + 1 < rank) gs[i] = strides[i]; }
+    CUtensorMap m;
+    CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(ptr), gd, gs, gb, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(B200SR_ECUDA, "encode failed " + std::to_string(r));
+    std::memcpy(out128, &m, 128);
+    return 0;
+}
+
+int b200sr_debug_tma(const void* map128, void* dst, int rows, int c0, int c1, void* stream) {
+    CUtensorMap m;
+    std::memcpy(&m, map128, 128);
+    cudaFuncSetAttribute(debug_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768);
+    debug_tma_kernel<<<1, 128, 32768, static_cast<cudaStream_t>(stream)>>>(m, static_cast<__nv_bfloat16*>(dst), rows, c0, c1);
+    return check_launch("debug_tma_kernel");
+}
 
 int b200sr_version(void) { return 100; }
 

@@ -37,6 +37,7 @@ struct IGemmArgs {
     int out_pix_stride;  // elements between consecutive output pixels (total channels of the buffer)
     int out_c_off;       // first channel of the slot written
     int stats_replicas;
+    int debug_stage;     // 0 = normal; 1..4 = stop early (bring-up aid, B200SR_DEBUG_STAGE)
     __nv_bfloat16* out;
     const float* col_scale;  // nullable
     const float* col_shift;  // nullable
@@ -111,8 +112,12 @@ __global__ void __launch_bounds__(IG_THREADS) igemm_kernel(const __grid_constant
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
+    const int dbg = args.debug_stage & 15;
+    const bool dbg_cl = (args.debug_stage & 16) != 0;
 
-    if (warp == 0) {
+    if (dbg == 1) {
+        // setup only
+    } else if (warp == 0) {
         // ===================== TMA producer =====================
         if (elect_one()) {
             int stage = 0;
@@ -123,8 +128,13 @@ __global__ void __launch_bounds__(IG_THREADS) igemm_kernel(const __grid_constant
                 uint8_t* sb = sa + IG_A_BYTES;
                 const int tap = kb / args.kc_per_tap;
                 const int c0 = (kb - tap * args.kc_per_tap) * IG_BLOCK_K;
-                mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
-                if (args.a_mode == 0) {
+                mbar_arrive_expect_tx(&full_bar[stage], dbg == 5   ? STAGE_BYTES - IG_A_BYTES
+                                                        : dbg == 6 ? IG_A_BYTES
+                                                                   : STAGE_BYTES);
+                if (dbg == 5) {
+                } else if (dbg_cl) {
+                    tma_load_4d_cl(&map_a, &full_bar[stage], sa, c0, w0, h0, img);
+                } else if (args.a_mode == 0) {
                     int dh = 0, dw = 0;
                     if (args.num_taps == 9) {
                         dh = tap / 3 - 1;
@@ -135,7 +145,12 @@ __global__ void __launch_bounds__(IG_THREADS) igemm_kernel(const __grid_constant
                     // (c, j, w, i, img*H + h) view of the (2H x 2W) tensor; tap = i*2 + j
                     tma_load_5d(&map_a, &full_bar[stage], sa, c0, tap & 1, w0, tap >> 1, img * args.H + h0);
                 }
-                tma_load_2d(&map_b, &full_bar[stage], sb, kb * IG_BLOCK_K, n0);
+                if (dbg == 6) {
+                } else if (dbg_cl) {
+                    tma_load_2d_cl(&map_b, &full_bar[stage], sb, kb * IG_BLOCK_K, n0);
+                } else {
+                    tma_load_2d(&map_b, &full_bar[stage], sb, kb * IG_BLOCK_K, n0);
+                }
                 if (++stage == STAGES) {
                     stage = 0;
                     phase ^= 1;
@@ -155,18 +170,22 @@ __global__ void __launch_bounds__(IG_THREADS) igemm_kernel(const __grid_constant
                 const uint32_t sb = sa + IG_A_BYTES;
                 const uint64_t da = umma_smem_desc_sw128(sa, 0, 1024);
                 const uint64_t db = umma_smem_desc_sw128(sb, 0, 1024);
+                if (dbg == 2 || dbg == 5 || dbg == 6) {
+                    mbar_arrive(&empty_bar[stage]);  // TMA + barriers only
+                } else {
 #pragma unroll
-                for (int k = 0; k < IG_BLOCK_K / 16; ++k) {
-                    // +32 B per UMMA_K inside the 128 B swizzle span (encoded >> 4)
-                    umma_bf16(tmem_base, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                    for (int k = 0; k < IG_BLOCK_K / 16; ++k) {
+                        // +32 B per UMMA_K inside the 128 B swizzle span (encoded >> 4)
+                        umma_bf16(tmem_base, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                    }
+                    umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
                 }
-                umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
                 if (++stage == STAGES) {
                     stage = 0;
                     phase ^= 1;
                 }
             }
-            umma_commit(tmem_full_bar);  // accumulator complete
+            if (dbg == 2 || dbg == 5 || dbg == 6) mbar_arrive(tmem_full_bar); else umma_commit(tmem_full_bar);  // accumulator complete
         }
     } else if (warp >= 4) {
         // ===================== epilogue =====================
@@ -176,13 +195,14 @@ __global__ void __launch_bounds__(IG_THREADS) igemm_kernel(const __grid_constant
         const int w = w0 + row % IG_TILE_W;
         mbar_wait(tmem_full_bar, 0);
         tc_fence_after();
-        const bool do_stats = args.stats != nullptr;
+        const bool do_stats = args.stats != nullptr && dbg == 0;
 
 #pragma unroll 1
-        for (int chunk = 0; chunk < BLOCK_N / 32; ++chunk) {
+        for (int chunk = 0; chunk < (dbg == 2 || dbg == 3 || dbg == 5 || dbg == 6 ? 0 : BLOCK_N / 32); ++chunk) {
             uint32_t raw[32];
             tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + chunk * 32, raw);
             tmem_ld_wait();
+            if (dbg == 4) continue;
             const int col0 = n0 + chunk * 32;  // global GEMM column of raw[0]
             float v[32];
 #pragma unroll

@@ -63,7 +63,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     asm volatile(
         "{\n\t"
         ".reg .pred P;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 P, [%0], %1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
         "selp.u32 %0, 1, 0, P;\n\t"
         "}\n"
         : "=r"(ok)
@@ -78,8 +78,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
     const long long t0 = clock64();
     while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > 8000000000LL) {
-            printf("b200sr: mbarrier watchdog block=(%d,%d,%d) thread=%d parity=%u\n", blockIdx.x, blockIdx.y,
+        if (clock64() - t0 > 2000000000LL) {
+            if ((threadIdx.x & 31) == 0)
+                printf("b200sr: mbarrier watchdog block=(%d,%d,%d) thread=%d parity=%u\n", blockIdx.x, blockIdx.y,
                    blockIdx.z, threadIdx.x, parity);
             __trap();
         }
@@ -105,6 +106,25 @@ __device__ __forceinline__ void tma_load_4d(const CUtensorMap* m, uint64_t* bar,
                                             int c3) {
     asm volatile(
         "cp.async.bulk.tensor.4d.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], "
+        "[%2];"
+        :
+        : "r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2),
+          "r"(c3)
+        : "memory");
+}
+
+// .shared::cluster destination forms (bring-up comparison)
+__device__ __forceinline__ void tma_load_2d_cl(const CUtensorMap* m, uint64_t* bar, void* dst, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        :
+        : "r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_cl(const CUtensorMap* m, uint64_t* bar, void* dst, int c0, int c1, int c2,
+                                               int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], "
         "[%2];"
         :
         : "r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2),

@@ -34,7 +34,7 @@ def window_1d(mode):
 def ssim_map(x, y, mode="gaussian", data_range=1.0):
     """x, y: (B,1,H,W). Returns the valid SSIM map (B,1,H-K+1,W-K+1) in the dtype of x."""
     w1, cov_norm = window_1d(mode)
-    w1 = w1.to(x.dtype)
+    w1 = w1.to(device=x.device, dtype=x.dtype)
     k = w1.numel()
     w2 = (w1[:, None] * w1[None, :]).view(1, 1, k, k)
     filt = lambda t: F.conv2d(t, w2)
