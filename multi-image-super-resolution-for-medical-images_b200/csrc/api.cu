@@ -8,6 +8,7 @@
 #include <unordered_map>
 
 #include "elementwise.cuh"
+#include "conv3x3.cuh"
 #include "igemm.cuh"
 #include "loss.cuh"
 #include "wgrad.cuh"
@@ -250,6 +251,86 @@ int run_igemm(int a_mode, const void* a, int a_stride, int a_coff, int Ca, int n
 }
 
 // ---------------------------------------------------------------------------------------------
+// persistent conv3x3 launch (forward and data gradient)
+// ---------------------------------------------------------------------------------------------
+int num_sms() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    }
+    return n;
+}
+
+template <int BLOCK_N>
+int launch_conv3_t(const CUtensorMap& ma, const CUtensorMap& mb, const Conv3Args& args, int grid, cudaStream_t st) {
+    constexpr int smem = C3Cfg<BLOCK_N>::SMEM_BYTES;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(conv3x3_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return fail(B200SR_ECUDA, std::string("conv3x3 smem attribute: ") + cudaGetErrorString(e));
+        configured = true;
+    }
+    conv3x3_kernel<BLOCK_N><<<grid, C3_THREADS, smem, st>>>(ma, mb, args);
+    return check_launch("conv3x3_kernel");
+}
+
+int run_conv3(const void* a, int a_stride, int a_coff, int Ca, const void* w_packed, int n_total, int B, int H, int W,
+              void* out, int out_stride, int out_coff, const float* col_scale, const float* col_shift, int relu,
+              float* stats, int stats_replicas, cudaStream_t st) {
+    B2_CHECK_ARG(a != nullptr && w_packed != nullptr && out != nullptr);
+    B2_CHECK_ARG(B > 0 && H > 0 && W > 0 && H % C3_TILE_H == 0 && W % C3_TILE_W == 0);
+    B2_CHECK_ARG(Ca % 64 == 0 && n_total % 64 == 0);
+    B2_CHECK_ARG(a_stride % 8 == 0 && a_coff % 8 == 0 && out_stride % 8 == 0 && out_coff % 8 == 0);
+    B2_CHECK_ARG(aligned16(a) && aligned16(w_packed) && aligned16(out));
+    B2_CHECK_ARG(stats == nullptr || stats_replicas > 0);
+    int block_n = n_total % 256 == 0 ? 256 : (n_total % 128 == 0 ? 128 : 64);
+    if (const char* env = getenv("B200SR_CONV_BLOCK_N")) {
+        const int v = atoi(env);
+        if ((v == 64 || v == 128 || v == 256) && n_total % v == 0) block_n = v;
+    }
+    CUtensorMap ma, mb;
+    int rc = make_act_map(&ma, a, a_stride, a_coff, Ca, B, H, W, C3_TILE_W, C3_TILE_H + 2);
+    if (rc) return rc;
+    rc = make_weight_map(&mb, w_packed, 9 * Ca, n_total, block_n < 128 ? block_n : 128);
+    if (rc) return rc;
+    Conv3Args args;
+    args.H = H;
+    args.W = W;
+    args.tiles_w = W / C3_TILE_W;
+    args.tiles_hw = (H / C3_TILE_H) * (W / C3_TILE_W);
+    args.n_tiles = n_total / block_n;
+    const long long tiles = static_cast<long long>(B) * args.tiles_hw * args.n_tiles;
+    B2_CHECK_ARG(tiles < (1ll << 31));
+    args.num_tiles = static_cast<int>(tiles);
+    args.cin_chunks = Ca / 64;
+    args.C = Ca;
+    args.n_total = n_total;
+    args.relu = relu;
+    args.out_pix_stride = out_stride;
+    args.out_c_off = out_coff;
+    args.stats_replicas = stats_replicas > 0 ? stats_replicas : 1;
+    args.out = static_cast<__nv_bfloat16*>(out);
+    args.col_scale = col_scale;
+    args.col_shift = col_shift;
+    args.stats = stats;
+    // persistent grid: one CTA per SM, rounded down so that a CTA stays on one column block (register statistics)
+    int grid = num_sms();
+    grid -= grid % args.n_tiles;
+    if (grid < args.n_tiles) grid = args.n_tiles;
+    if (grid > args.num_tiles) grid = args.num_tiles;
+    switch (block_n) {
+        case 64:
+            return launch_conv3_t<64>(ma, mb, args, grid, st);
+        case 128:
+            return launch_conv3_t<128>(ma, mb, args, grid, st);
+        default:
+            return launch_conv3_t<256>(ma, mb, args, grid, st);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // wgrad launch
 // ---------------------------------------------------------------------------------------------
 template <int N_TILE, int STAGES>
@@ -385,6 +466,9 @@ int b200sr_device_ok(void) {
 int b200sr_conv3x3_fwd(const void* x, int x_pix_stride, int x_c_off, int Cin, const void* w_packed, int Cout, int B,
                        int H, int W, void* out, int out_pix_stride, int out_c_off, const float* col_scale,
                        const float* col_shift, int relu, float* stats, int stats_replicas, void* stream) {
+    if (getenv("B200SR_CONV_V1") == nullptr)
+        return run_conv3(x, x_pix_stride, x_c_off, Cin, w_packed, Cout, B, H, W, out, out_pix_stride, out_c_off,
+                         col_scale, col_shift, relu, stats, stats_replicas, static_cast<cudaStream_t>(stream));
     return run_igemm(0, x, x_pix_stride, x_c_off, Cin, 9, w_packed, Cout, B, H, W, 0, Cout, out, out_pix_stride,
                      out_c_off, col_scale, col_shift, relu, stats, stats_replicas, static_cast<cudaStream_t>(stream));
 }
@@ -392,6 +476,9 @@ int b200sr_conv3x3_fwd(const void* x, int x_pix_stride, int x_c_off, int Cin, co
 int b200sr_conv3x3_dgrad(const void* dy, int dy_pix_stride, int dy_c_off, int Cout, const void* w_packed, int Cin,
                          int B, int H, int W, void* dx, int dx_pix_stride, int dx_c_off, float* stats,
                          int stats_replicas, void* stream) {
+    if (getenv("B200SR_CONV_V1") == nullptr)
+        return run_conv3(dy, dy_pix_stride, dy_c_off, Cout, w_packed, Cin, B, H, W, dx, dx_pix_stride, dx_c_off,
+                         nullptr, nullptr, 0, stats, stats_replicas, static_cast<cudaStream_t>(stream));
     return run_igemm(0, dy, dy_pix_stride, dy_c_off, Cout, 9, w_packed, Cin, B, H, W, 0, Cin, dx, dx_pix_stride,
                      dx_c_off, nullptr, nullptr, 0, stats, stats_replicas, static_cast<cudaStream_t>(stream));
 }

@@ -1,0 +1,290 @@
+// Persistent implicit-GEMM kernel for Conv2d 3x3 (padding 1) forward and data-gradient on tcgen05/TMEM + TMA.
+// Reference ops: nn.Conv2d(k=3, p=1) inside UNetBlock, /root/reference/src/unet_model.py:27,30 (and its dgrad).
+//
+//   D[pixel, n] = sum_{dh,dw,c} A[pixel + (dh-1, dw-1), c] * Wp[n, (dh*3+dw)*C + c]
+//
+// What differs from the generic one-tile-per-CTA kernel (igemm.cuh):
+//   * persistent CTAs (one per SM) walk a static tile schedule; the accumulator is double-buffered in TMEM so the
+//     epilogue of tile i overlaps the main loop of tile i+1; barrier set-up / TMEM allocation happen once per CTA.
+//   * an output tile is 16 rows x 8 columns of pixels. For a fixed horizontal tap dw, ONE haloed TMA box
+//     {64 ch, 8 w, 18 h} serves the three vertical taps: in the K-major 128B-swizzled layout one pixel row of the
+//     tile is exactly one 1024-byte swizzle atom, so the operand for tap dh starts dh*1024 bytes into the box.
+//     Activation traffic from L2 drops from 9 to 3.4 tile loads per 64-channel chunk.
+//   * activations (A ring, 18 KB slots) and weights (B ring, <=16 KB slots) have independent rings; with
+//     BLOCK_N = 256 the two 128-column halves of the weight tile reuse the same activation box.
+//   * BatchNorm statistics are accumulated in registers across all tiles of the CTA (the schedule keeps the CTA on
+//     one column block) and leave through one vector of atomics per CTA.
+#pragma once
+#include "ptx.cuh"
+
+namespace b200sr {
+
+struct Conv3Args {
+    int H, W;
+    int tiles_w;       // W / 8
+    int tiles_hw;      // (H / 16) * (W / 8)
+    int n_tiles;       // N / BLOCK_N
+    int num_tiles;     // B * tiles_hw * n_tiles
+    int cin_chunks;    // C / 64
+    int C;             // channels of A (GEMM-K per tap)
+    int n_total;       // GEMM-N
+    int relu;
+    int out_pix_stride;
+    int out_c_off;
+    int stats_replicas;
+    __nv_bfloat16* out;
+    const float* col_scale;  // nullable, [n_total]
+    const float* col_shift;  // nullable, [n_total]
+    float* stats;            // nullable, [replicas][2][n_total]
+};
+
+constexpr int C3_THREADS = 256;
+constexpr int C3_TILE_H = 16;
+constexpr int C3_TILE_W = 8;
+constexpr int C3_A_SLOT = (C3_TILE_H + 2) * C3_TILE_W * 128;  // 18432 B: 18 pixel rows x 8 pixels x 64 ch bf16
+
+template <int BLOCK_N>
+struct C3Cfg {
+    static constexpr int BN_SLOT = BLOCK_N < 128 ? BLOCK_N : 128;  // columns per weight slot = UMMA N
+    static constexpr int NH = BLOCK_N / BN_SLOT;
+    static constexpr int B_SLOT = BN_SLOT * 128;
+    static constexpr int SA = BLOCK_N == 64 ? 4 : 3;
+    static constexpr int SB = BLOCK_N == 64 ? 16 : 10;
+    static constexpr int RING_BYTES = SA * C3_A_SLOT + SB * B_SLOT;
+    static constexpr int SMEM_BYTES = RING_BYTES + 1024 /* barriers */ + 1024 /* alignment slack */;
+};
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_kernel(const __grid_constant__ CUtensorMap map_a,
+                                                                const __grid_constant__ CUtensorMap map_b,
+                                                                const Conv3Args args) {
+    using Cfg = C3Cfg<BLOCK_N>;
+    constexpr int SA = Cfg::SA, SB = Cfg::SB, NH = Cfg::NH, BN_SLOT = Cfg::BN_SLOT;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* ring_a = smem;
+    uint8_t* ring_b = smem + SA * C3_A_SLOT;
+    uint64_t* a_full = reinterpret_cast<uint64_t*>(smem + Cfg::RING_BYTES);
+    uint64_t* a_empty = a_full + SA;
+    uint64_t* b_full = a_empty + SA;
+    uint64_t* b_empty = b_full + SB;
+    uint64_t* acc_full = b_empty + SB;
+    uint64_t* acc_empty = acc_full + 2;
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const uint32_t lane = lane_id();
+
+    if (warp == 0 && elect_one()) {
+        tma_prefetch_desc(&map_a);
+        tma_prefetch_desc(&map_b);
+    }
+    if (warp == 1 && elect_one()) {
+        for (int s = 0; s < SA; ++s) {
+            mbar_init(&a_full[s], 1);
+            mbar_init(&a_empty[s], 1);
+        }
+        for (int s = 0; s < SB; ++s) {
+            mbar_init(&b_full[s], 1);
+            mbar_init(&b_empty[s], 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&acc_full[s], 1);
+            mbar_init(&acc_empty[s], 128);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 2) {
+        tmem_alloc(tmem_ptr_smem, 2 * BLOCK_N);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    const int chunks = args.cin_chunks;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (elect_one()) {
+            int sa = 0, sb = 0;
+            uint32_t pa = 0, pb = 0;
+            for (int tile = blockIdx.x; tile < args.num_tiles; tile += gridDim.x) {
+                const int n_tile = tile % args.n_tiles;
+                const int m_tile = tile / args.n_tiles;
+                const int img = m_tile / args.tiles_hw;
+                const int t_in = m_tile - img * args.tiles_hw;
+                const int h0 = (t_in / args.tiles_w) * C3_TILE_H;
+                const int w0 = (t_in % args.tiles_w) * C3_TILE_W;
+                const int n0 = n_tile * BLOCK_N;
+                for (int c = 0; c < chunks; ++c) {
+                    for (int dw = 0; dw < 3; ++dw) {
+                        mbar_wait(&a_empty[sa], pa ^ 1);
+                        mbar_arrive_expect_tx(&a_full[sa], C3_A_SLOT);
+                        tma_load_4d(&map_a, &a_full[sa], ring_a + sa * C3_A_SLOT, c * 64, w0 + dw - 1, h0 - 1, img);
+                        if (++sa == SA) {
+                            sa = 0;
+                            pa ^= 1;
+                        }
+                        for (int dh = 0; dh < 3; ++dh) {
+                            const int kcol = (dh * 3 + dw) * args.C + c * 64;
+#pragma unroll
+                            for (int nh = 0; nh < NH; ++nh) {
+                                mbar_wait(&b_empty[sb], pb ^ 1);
+                                mbar_arrive_expect_tx(&b_full[sb], Cfg::B_SLOT);
+                                tma_load_2d(&map_b, &b_full[sb], ring_b + sb * Cfg::B_SLOT, kcol, n0 + nh * BN_SLOT);
+                                if (++sb == SB) {
+                                    sb = 0;
+                                    pb ^= 1;
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (elect_one()) {
+            constexpr uint32_t idesc = umma_idesc_bf16(128, BN_SLOT, 0, 0);
+            int sa = 0, sb = 0, as = 0;
+            uint32_t pa = 0, pb = 0, pacc = 0;
+            for (int tile = blockIdx.x; tile < args.num_tiles; tile += gridDim.x) {
+                mbar_wait(&acc_empty[as], pacc ^ 1);
+                tc_fence_after();
+                const uint32_t d_base = tmem_base + as * BLOCK_N;
+                for (int c = 0; c < chunks; ++c) {
+                    for (int dw = 0; dw < 3; ++dw) {
+                        mbar_wait(&a_full[sa], pa);
+                        const uint32_t a_addr = smem_u32(ring_a + sa * C3_A_SLOT);
+                        for (int dh = 0; dh < 3; ++dh) {
+                            const uint64_t da = umma_smem_desc_sw128(a_addr + dh * 1024, 0, 1024);
+#pragma unroll
+                            for (int nh = 0; nh < NH; ++nh) {
+                                mbar_wait(&b_full[sb], pb);
+                                tc_fence_after();
+                                const uint64_t db = umma_smem_desc_sw128(smem_u32(ring_b + sb * Cfg::B_SLOT), 0, 1024);
+                                const uint32_t first = (c | dw | dh) == 0 ? 0u : 1u;
+#pragma unroll
+                                for (int k = 0; k < 4; ++k)
+                                    umma_bf16(d_base + nh * BN_SLOT, da + 2 * k, db + 2 * k, idesc, first | k);
+                                umma_commit(&b_empty[sb]);
+                                if (++sb == SB) {
+                                    sb = 0;
+                                    pb ^= 1;
+                                }
+                            }
+                        }
+                        umma_commit(&a_empty[sa]);
+                        if (++sa == SA) {
+                            sa = 0;
+                            pa ^= 1;
+                        }
+                    }
+                }
+                umma_commit(&acc_full[as]);
+                if (++as == 2) {
+                    as = 0;
+                    pacc ^= 1;
+                }
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue =====================
+        const int q = warp & 3;
+        const int row = q * 32 + lane;  // pixel inside the tile: row = h_local * 8 + w_local
+        const bool do_stats = args.stats != nullptr;
+        const bool affine = args.col_scale != nullptr || args.col_shift != nullptr;
+        float st_sum[BLOCK_N / 32], st_sq[BLOCK_N / 32];
+#pragma unroll
+        for (int i = 0; i < BLOCK_N / 32; ++i) st_sum[i] = st_sq[i] = 0.f;
+        int as = 0;
+        uint32_t pacc = 0;
+        int n0_last = 0;
+        for (int tile = blockIdx.x; tile < args.num_tiles; tile += gridDim.x) {
+            const int n_tile = tile % args.n_tiles;
+            const int m_tile = tile / args.n_tiles;
+            const int img = m_tile / args.tiles_hw;
+            const int t_in = m_tile - img * args.tiles_hw;
+            const int h = (t_in / args.tiles_w) * C3_TILE_H + (row >> 3);
+            const int w = (t_in % args.tiles_w) * C3_TILE_W + (row & 7);
+            const int n0 = n_tile * BLOCK_N;
+            n0_last = n0;
+            __nv_bfloat16* dst_pix =
+                args.out + (static_cast<size_t>(img * args.H + h) * args.W + w) * args.out_pix_stride + args.out_c_off + n0;
+            mbar_wait(&acc_full[as], pacc);
+            tc_fence_after();
+            const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BLOCK_N;
+#pragma unroll
+            for (int chunk = 0; chunk < BLOCK_N / 32; ++chunk) {
+                uint32_t raw[32];
+                tmem_ld32(t_addr + chunk * 32, raw);
+                tmem_ld_wait();
+                float v[32];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
+                if (affine) {
+                    const int c0 = n0 + chunk * 32;
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        const float sc = args.col_scale ? __ldg(args.col_scale + c0 + i) : 1.f;
+                        const float sh = args.col_shift ? __ldg(args.col_shift + c0 + i) : 0.f;
+                        v[i] = fmaf(v[i], sc, sh);
+                    }
+                }
+                if (args.relu) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+                }
+                uint32_t packed[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) packed[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+                uint4* dst = reinterpret_cast<uint4*>(dst_pix + chunk * 32);
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    dst[i] = make_uint4(packed[4 * i], packed[4 * i + 1], packed[4 * i + 2], packed[4 * i + 3]);
+                if (do_stats) {
+                    // statistics of the tensor as stored (bf16-rounded), like BatchNorm reading the conv output
+                    float s1[32], s2[32];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const __nv_bfloat162 hh = *reinterpret_cast<const __nv_bfloat162*>(&packed[i]);
+                        const float a = __low2float(hh), b = __high2float(hh);
+                        s1[2 * i] = a;
+                        s1[2 * i + 1] = b;
+                        s2[2 * i] = a * a;
+                        s2[2 * i + 1] = b * b;
+                    }
+                    st_sum[chunk] += warp_transpose_reduce32(s1, lane);
+                    st_sq[chunk] += warp_transpose_reduce32(s2, lane);
+                }
+            }
+            // all TMEM reads of this thread have completed (tmem_ld_wait above): hand the accumulator back
+            tc_fence_before();
+            mbar_arrive(&acc_empty[as]);
+            if (++as == 2) {
+                as = 0;
+                pacc ^= 1;
+            }
+        }
+        if (do_stats && blockIdx.x < args.num_tiles) {
+            // the tile schedule keeps this CTA on one column block (gridDim.x % n_tiles == 0, or one tile per CTA)
+            float* dst = args.stats + static_cast<size_t>(blockIdx.x % args.stats_replicas) * 2 * args.n_total + n0_last;
+#pragma unroll
+            for (int chunk = 0; chunk < BLOCK_N / 32; ++chunk) {
+                atomicAdd(dst + chunk * 32 + lane, st_sum[chunk]);
+                atomicAdd(dst + args.n_total + chunk * 32 + lane, st_sq[chunk]);
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 2 * BLOCK_N);
+    }
+}
+
+}  // namespace b200sr

@@ -339,12 +339,19 @@ def layout_casts(B=2, C=24, H=8, W=12, seed=14):
 BF16 = 1e-2
 CHECKS = {
     "conv3x3_fwd_n128": (conv3x3_fwd, {}, {"out": BF16, "stats_sum": 1e-3, "stats_sq": 1e-3}),
-    "conv3x3_fwd_n64_slot": (conv3x3_fwd, dict(Cin=128, Cout=64, slot=True, affine=True, B=1, H=8, W=16),
+    "conv3x3_fwd_n64_slot": (conv3x3_fwd, dict(Cin=128, Cout=64, slot=True, affine=True, B=1, H=16, W=16),
                              {"out": BF16, "slot_untouched": 0.0}),
-    "conv3x3_fwd_n256": (conv3x3_fwd, dict(Cin=256, Cout=256, B=3, H=8, W=16), {"out": BF16, "stats_sq": 1e-3}),
+    "conv3x3_fwd_n256": (conv3x3_fwd, dict(Cin=256, Cout=256, B=3, H=16, W=16), {"out": BF16, "stats_sq": 1e-3}),
     "conv3x3_fwd_deep": (conv3x3_fwd, dict(Cin=1024, Cout=512, B=1, H=16, W=16, affine=True), {"out": BF16}),
     "conv3x3_dgrad": (conv3x3_dgrad, {}, {"dx": BF16, "colsum": 1e-3}),
-    "conv3x3_dgrad_wide": (conv3x3_dgrad, dict(Cin=256, Cout=64, B=1, H=24, W=16), {"dx": BF16}),
+    "conv3x3_dgrad_wide": (conv3x3_dgrad, dict(Cin=256, Cout=64, B=1, H=32, W=16), {"dx": BF16}),
+    # persistent schedule: more tiles than SMs, one and several column blocks per row block
+    "conv3x3_fwd_persistent_n64": (conv3x3_fwd, dict(Cin=64, Cout=64, B=6, H=64, W=64),
+                                   {"out": BF16, "stats_sum": 1e-3, "stats_sq": 1e-3}),
+    "conv3x3_fwd_persistent_n512": (conv3x3_fwd, dict(Cin=128, Cout=512, B=8, H=32, W=64),
+                                    {"out": BF16, "stats_sum": 1e-3, "stats_sq": 1e-3}),
+    "conv3x3_fwd_persistent_n384": (conv3x3_fwd, dict(Cin=64, Cout=384, B=5, H=32, W=64, affine=True),
+                                    {"out": BF16, "stats_sum": 1e-3, "stats_sq": 1e-3}),
     "conv3x3_wgrad_n128": (conv3x3_wgrad, {}, {"dw": BF16}),
     "conv3x3_wgrad_n64_slot": (conv3x3_wgrad, dict(Cin=128, Cout=64, slot=True, H=8, W=48), {"dw": BF16}),
     "conv3x3_wgrad_n256": (conv3x3_wgrad, dict(Cin=320, Cout=256, B=3, H=8, W=16), {"dw": BF16}),
