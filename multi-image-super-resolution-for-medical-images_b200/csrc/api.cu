@@ -12,6 +12,7 @@
 #include "igemm.cuh"
 #include "loss.cuh"
 #include "wgrad.cuh"
+#include "wgrad3x3.cuh"
 
 using namespace b200sr;
 
@@ -145,6 +146,20 @@ int make_gather_map(CUtensorMap* out, const void* base, int pix_stride, int c_of
     const uint64_t s = static_cast<uint64_t>(pix_stride) * 2;
     const uint64_t strides[4] = {s, 2 * s, 2 * static_cast<uint64_t>(W) * s, 4 * static_cast<uint64_t>(W) * s};
     const uint32_t box[5] = {64, 1, static_cast<uint32_t>(box_w), 1, static_cast<uint32_t>(box_h)};
+    return make_map(out, p, 5, dims, strides, box);
+}
+
+// (B,H,W,C) channel slot viewed as the 5-D tensor (c within a 64-channel chunk, w, h, chunk, b): one box can
+// carry several channel chunks, each landing as its own [h][w][64 ch] block in shared memory
+int make_chunk_map(CUtensorMap* out, const void* base, int pix_stride, int c_off, int C, int B, int H, int W,
+                   int box_w, int box_h, int box_chunks) {
+    const __nv_bfloat16* p = static_cast<const __nv_bfloat16*>(base) + c_off;
+    const uint64_t dims[5] = {64, static_cast<uint64_t>(W), static_cast<uint64_t>(H), static_cast<uint64_t>(C / 64),
+                              static_cast<uint64_t>(B)};
+    const uint64_t s = static_cast<uint64_t>(pix_stride) * 2;
+    const uint64_t strides[4] = {s, s * W, 128, s * W * H};
+    const uint32_t box[5] = {64, static_cast<uint32_t>(box_w), static_cast<uint32_t>(box_h),
+                             static_cast<uint32_t>(box_chunks), 1};
     return make_map(out, p, 5, dims, strides, box);
 }
 
@@ -393,6 +408,78 @@ int run_wgrad(int t_mode, const void* t, int t_stride, int t_coff, int Ct, int n
     return launch_wgrad_t<64, 3>(mt, mp, args, st);
 }
 
+// ---------------------------------------------------------------------------------------------
+// second-generation conv3x3 wgrad launch
+// ---------------------------------------------------------------------------------------------
+template <int N_TILE, int MODE_B>
+int launch_wgrad3_t(const CUtensorMap& mx, const CUtensorMap& mz, WG3Args& args, int jobs, cudaStream_t st) {
+    using Cfg = WG3Cfg<N_TILE, MODE_B>;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(wgrad3x3_kernel<N_TILE, MODE_B>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+        if (e != cudaSuccess) return fail(B200SR_ECUDA, std::string("wgrad3x3 smem attribute: ") + cudaGetErrorString(e));
+        configured = true;
+    }
+    // split-K factor: fill whole waves of SMs (one CTA per SM), prefer fewer splits (less reduction traffic)
+    const int sms = num_sms();
+    int best = 1;
+    double best_score = -1.0;
+    const int max_splits = args.total_chunks < 64 ? args.total_chunks : 64;
+    for (int s = 1; s <= max_splits; ++s) {
+        const int per = (args.total_chunks + s - 1) / s;
+        const int real = (args.total_chunks + per - 1) / per;
+        if (real != s) continue;
+        const long long ctas = static_cast<long long>(jobs) * s;
+        const long long waves = (ctas + sms - 1) / sms;
+        // time ~ waves * (per + fixed per-CTA cost of ~6 stages for prologue/epilogue)
+        const double t = static_cast<double>(waves) * (per + 6.0);
+        const double score = 1.0 / t;
+        if (score > best_score * 1.0001) {
+            best_score = score;
+            best = s;
+        }
+    }
+    if (const char* env = getenv("B200SR_WGRAD_SPLITS")) best = atoi(env) > 0 ? atoi(env) : best;
+    args.chunks_per_cta = (args.total_chunks + best - 1) / best;
+    const int splits = (args.total_chunks + args.chunks_per_cta - 1) / args.chunks_per_cta;
+    dim3 grid(jobs, splits, 1);
+    wgrad3x3_kernel<N_TILE, MODE_B><<<grid, WG3_THREADS, Cfg::SMEM_BYTES, st>>>(mx, mz, args);
+    return check_launch("wgrad3x3_kernel");
+}
+
+// returns -1 when the shape is not covered (caller falls back to the first-generation kernel)
+int run_wgrad3(const void* x, int x_stride, int x_coff, int Cin, const void* dz, int dz_stride, int dz_coff, int Cout,
+               int B, int H, int W, float* G, cudaStream_t st) {
+    if (H % 4 != 0 || W % 16 != 0) return -1;
+    const bool mode_b = Cin == 64;
+    if (!mode_b && Cin % 128 != 0) return -1;
+    if (Cout % 64 != 0) return -1;
+    const int n_tile = (!mode_b && Cout % 128 == 0) ? 128 : 64;
+    CUtensorMap mx, mz;
+    int rc = make_chunk_map(&mx, x, x_stride, x_coff, Cin, B, H, W, 16, 6, mode_b ? 1 : 2);
+    if (rc) return rc;
+    rc = make_chunk_map(&mz, dz, dz_stride, dz_coff, Cout, B, H, W, 16, 4, n_tile / 64);
+    if (rc) return rc;
+    WG3Args args;
+    args.H = H;
+    args.W = W;
+    args.chunks_w = W / 16;
+    args.chunks_hw = (H / 4) * (W / 16);
+    args.total_chunks = B * args.chunks_hw;
+    args.chunks_per_cta = args.total_chunks;
+    args.mode_b = mode_b ? 1 : 0;
+    args.jobs_ci = mode_b ? 1 : Cin / 128;
+    args.jobs_co = Cout / n_tile;
+    args.Cin = Cin;
+    args.Cout = Cout;
+    args.out = G;
+    const int jobs = (mode_b ? 1 : 3 * args.jobs_ci) * args.jobs_co;
+    if (mode_b) return launch_wgrad3_t<64, 1>(mx, mz, args, jobs, st);
+    if (n_tile == 128) return launch_wgrad3_t<128, 0>(mx, mz, args, jobs, st);
+    return launch_wgrad3_t<64, 0>(mx, mz, args, jobs, st);
+}
+
 }  // namespace
 
 // =================================================================================================
@@ -498,6 +585,13 @@ int b200sr_convT2x2_dgrad(const void* dup, int dup_pix_stride, int dup_c_off, in
 
 int b200sr_conv3x3_wgrad(const void* x, int x_pix_stride, int x_c_off, int Cin, const void* dz, int dz_pix_stride,
                          int dz_c_off, int Cout, int B, int H, int W, float* G, void* stream) {
+    if (getenv("B200SR_WGRAD_V1") == nullptr && x != nullptr && dz != nullptr && G != nullptr && B > 0 &&
+        x_pix_stride % 8 == 0 && x_c_off % 8 == 0 && dz_pix_stride % 8 == 0 && dz_c_off % 8 == 0 && aligned16(x) &&
+        aligned16(dz) && aligned16(G)) {
+        const int rc = run_wgrad3(x, x_pix_stride, x_c_off, Cin, dz, dz_pix_stride, dz_c_off, Cout, B, H, W, G,
+                                  static_cast<cudaStream_t>(stream));
+        if (rc >= 0) return rc;
+    }
     return run_wgrad(0, x, x_pix_stride, x_c_off, Cin, 9, dz, dz_pix_stride, dz_c_off, Cout, B, H, W, G,
                      static_cast<cudaStream_t>(stream));
 }

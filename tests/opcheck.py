@@ -355,6 +355,8 @@ CHECKS = {
     "conv3x3_wgrad_n128": (conv3x3_wgrad, {}, {"dw": BF16}),
     "conv3x3_wgrad_n64_slot": (conv3x3_wgrad, dict(Cin=128, Cout=64, slot=True, H=8, W=48), {"dw": BF16}),
     "conv3x3_wgrad_n256": (conv3x3_wgrad, dict(Cin=320, Cout=256, B=3, H=8, W=16), {"dw": BF16}),
+    "conv3x3_wgrad_modeA_n128": (conv3x3_wgrad, dict(Cin=256, Cout=256, B=3, H=16, W=32), {"dw": BF16}),
+    "conv3x3_wgrad_modeB_split": (conv3x3_wgrad, dict(Cin=64, Cout=64, B=4, H=64, W=64), {"dw": BF16}),
     "convT_fwd": (convT_fwd, {}, {"out": BF16, "slot_untouched": 0.0}),
     "convT_fwd_big": (convT_fwd, dict(Cin=1024, Cout=512, B=1, H=8, W=16), {"out": BF16}),
     "convT_dgrad": (convT_dgrad, {}, {"dx": BF16}),
