@@ -278,24 +278,41 @@ int num_sms() {
     return n;
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, int MODE>
 int launch_conv3_t(const CUtensorMap& ma, const CUtensorMap& mb, const Conv3Args& args, int grid, cudaStream_t st) {
     constexpr int smem = C3Cfg<BLOCK_N>::SMEM_BYTES;
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(conv3x3_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaError_t e =
+            cudaFuncSetAttribute(conv3x3_kernel<BLOCK_N, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return fail(B200SR_ECUDA, std::string("conv3x3 smem attribute: ") + cudaGetErrorString(e));
         configured = true;
     }
-    conv3x3_kernel<BLOCK_N><<<grid, C3_THREADS, smem, st>>>(ma, mb, args);
+    conv3x3_kernel<BLOCK_N, MODE><<<grid, C3_THREADS, smem, st>>>(ma, mb, args);
     return check_launch("conv3x3_kernel");
 }
 
-int run_conv3(const void* a, int a_stride, int a_coff, int Ca, const void* w_packed, int n_total, int B, int H, int W,
+template <int MODE>
+int dispatch_conv3(int block_n, const CUtensorMap& ma, const CUtensorMap& mb, const Conv3Args& args, int grid,
+                   cudaStream_t st) {
+    switch (block_n) {
+        case 64:
+            return launch_conv3_t<64, MODE>(ma, mb, args, grid, st);
+        case 128:
+            return launch_conv3_t<128, MODE>(ma, mb, args, grid, st);
+        default:
+            return launch_conv3_t<256, MODE>(ma, mb, args, grid, st);
+    }
+}
+
+// mode 0: conv 3x3 fwd/dgrad (a = (B,H,W,Ca) slot); mode 1: ConvT fwd (a = (B,H,W,Ca) slot, n_total = 4*cout_t,
+// out = (B,2H,2W,cout_t) slot); mode 2: ConvT dgrad (a = (B,2H,2W,Ca) slot gathered per sub-pixel, out (B,H,W,n_total))
+int run_conv3(int mode, const void* a, int a_stride, int a_coff, int Ca, const void* w_packed, int n_total, int B, int H, int W,
               void* out, int out_stride, int out_coff, const float* col_scale, const float* col_shift, int relu,
-              float* stats, int stats_replicas, cudaStream_t st) {
+              float* stats, int stats_replicas, int cout_t, cudaStream_t st) {
     B2_CHECK_ARG(a != nullptr && w_packed != nullptr && out != nullptr);
     B2_CHECK_ARG(B > 0 && H > 0 && W > 0 && H % C3_TILE_H == 0 && W % C3_TILE_W == 0);
+    if (mode == 1) B2_CHECK_ARG(cout_t % 32 == 0 && n_total == 4 * cout_t);
     B2_CHECK_ARG(Ca % 64 == 0 && n_total % 64 == 0);
     B2_CHECK_ARG(a_stride % 8 == 0 && a_coff % 8 == 0 && out_stride % 8 == 0 && out_coff % 8 == 0);
     B2_CHECK_ARG(aligned16(a) && aligned16(w_packed) && aligned16(out));
@@ -306,9 +323,16 @@ int run_conv3(const void* a, int a_stride, int a_coff, int Ca, const void* w_pac
         if ((v == 64 || v == 128 || v == 256) && n_total % v == 0) block_n = v;
     }
     CUtensorMap ma, mb;
-    int rc = make_act_map(&ma, a, a_stride, a_coff, Ca, B, H, W, C3_TILE_W, C3_TILE_H + 2);
+    int rc;
+    if (mode == 0)
+        rc = make_act_map(&ma, a, a_stride, a_coff, Ca, B, H, W, C3_TILE_W, C3_TILE_H + 2);
+    else if (mode == 1)
+        rc = make_act_map(&ma, a, a_stride, a_coff, Ca, B, H, W, C3_TILE_W, C3_TILE_H);
+    else
+        rc = make_gather_map(&ma, a, a_stride, a_coff, Ca, B, H, W, C3_TILE_W, C3_TILE_H);
     if (rc) return rc;
-    rc = make_weight_map(&mb, w_packed, 9 * Ca, n_total, block_n < 128 ? block_n : 128);
+    const int taps = mode == 0 ? 9 : (mode == 1 ? 1 : 4);
+    rc = make_weight_map(&mb, w_packed, taps * Ca, n_total, block_n < 128 ? block_n : 128);
     if (rc) return rc;
     Conv3Args args;
     args.H = H;
@@ -330,19 +354,15 @@ int run_conv3(const void* a, int a_stride, int a_coff, int Ca, const void* w_pac
     args.col_scale = col_scale;
     args.col_shift = col_shift;
     args.stats = stats;
+    args.cout_t = cout_t;
     // persistent grid: one CTA per SM, rounded down so that a CTA stays on one column block (register statistics)
     int grid = num_sms();
     grid -= grid % args.n_tiles;
     if (grid < args.n_tiles) grid = args.n_tiles;
     if (grid > args.num_tiles) grid = args.num_tiles;
-    switch (block_n) {
-        case 64:
-            return launch_conv3_t<64>(ma, mb, args, grid, st);
-        case 128:
-            return launch_conv3_t<128>(ma, mb, args, grid, st);
-        default:
-            return launch_conv3_t<256>(ma, mb, args, grid, st);
-    }
+    if (mode == 0) return dispatch_conv3<0>(block_n, ma, mb, args, grid, st);
+    if (mode == 1) return dispatch_conv3<1>(block_n, ma, mb, args, grid, st);
+    return dispatch_conv3<2>(block_n, ma, mb, args, grid, st);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -553,9 +573,10 @@ int b200sr_device_ok(void) {
 int b200sr_conv3x3_fwd(const void* x, int x_pix_stride, int x_c_off, int Cin, const void* w_packed, int Cout, int B,
                        int H, int W, void* out, int out_pix_stride, int out_c_off, const float* col_scale,
                        const float* col_shift, int relu, float* stats, int stats_replicas, void* stream) {
-    if (getenv("B200SR_CONV_V1") == nullptr)
-        return run_conv3(x, x_pix_stride, x_c_off, Cin, w_packed, Cout, B, H, W, out, out_pix_stride, out_c_off,
-                         col_scale, col_shift, relu, stats, stats_replicas, static_cast<cudaStream_t>(stream));
+    // persistent kernel needs 16x8 pixel tiles; other shapes (H % 8 == 0, W % 16 == 0) use the generic kernel
+    if (getenv("B200SR_CONV_V1") == nullptr && H % C3_TILE_H == 0 && W % C3_TILE_W == 0)
+        return run_conv3(0, x, x_pix_stride, x_c_off, Cin, w_packed, Cout, B, H, W, out, out_pix_stride, out_c_off,
+                         col_scale, col_shift, relu, stats, stats_replicas, Cout, static_cast<cudaStream_t>(stream));
     return run_igemm(0, x, x_pix_stride, x_c_off, Cin, 9, w_packed, Cout, B, H, W, 0, Cout, out, out_pix_stride,
                      out_c_off, col_scale, col_shift, relu, stats, stats_replicas, static_cast<cudaStream_t>(stream));
 }
@@ -563,9 +584,9 @@ int b200sr_conv3x3_fwd(const void* x, int x_pix_stride, int x_c_off, int Cin, co
 int b200sr_conv3x3_dgrad(const void* dy, int dy_pix_stride, int dy_c_off, int Cout, const void* w_packed, int Cin,
                          int B, int H, int W, void* dx, int dx_pix_stride, int dx_c_off, float* stats,
                          int stats_replicas, void* stream) {
-    if (getenv("B200SR_CONV_V1") == nullptr)
-        return run_conv3(dy, dy_pix_stride, dy_c_off, Cout, w_packed, Cin, B, H, W, dx, dx_pix_stride, dx_c_off,
-                         nullptr, nullptr, 0, stats, stats_replicas, static_cast<cudaStream_t>(stream));
+    if (getenv("B200SR_CONV_V1") == nullptr && H % C3_TILE_H == 0 && W % C3_TILE_W == 0)
+        return run_conv3(0, dy, dy_pix_stride, dy_c_off, Cout, w_packed, Cin, B, H, W, dx, dx_pix_stride, dx_c_off,
+                         nullptr, nullptr, 0, stats, stats_replicas, Cin, static_cast<cudaStream_t>(stream));
     return run_igemm(0, dy, dy_pix_stride, dy_c_off, Cout, 9, w_packed, Cin, B, H, W, 0, Cin, dx, dx_pix_stride,
                      dx_c_off, nullptr, nullptr, 0, stats, stats_replicas, static_cast<cudaStream_t>(stream));
 }
@@ -573,12 +594,18 @@ int b200sr_conv3x3_dgrad(const void* dy, int dy_pix_stride, int dy_c_off, int Co
 int b200sr_convT2x2_fwd(const void* x, int x_pix_stride, int x_c_off, int Cin, const void* w_packed, int Cout,
                         const float* bias, int B, int H, int W, void* out, int out_pix_stride, int out_c_off,
                         void* stream) {
+    if (getenv("B200SR_CONV_V1") == nullptr && H % C3_TILE_H == 0 && W % C3_TILE_W == 0)
+        return run_conv3(1, x, x_pix_stride, x_c_off, Cin, w_packed, 4 * Cout, B, H, W, out, out_pix_stride, out_c_off,
+                         nullptr, bias, 0, nullptr, 0, Cout, static_cast<cudaStream_t>(stream));
     return run_igemm(0, x, x_pix_stride, x_c_off, Cin, 1, w_packed, 4 * Cout, B, H, W, 1, Cout, out, out_pix_stride,
                      out_c_off, nullptr, bias, 0, nullptr, 0, static_cast<cudaStream_t>(stream));
 }
 
 int b200sr_convT2x2_dgrad(const void* dup, int dup_pix_stride, int dup_c_off, int Cout, const void* w_packed, int Cin,
                           int B, int H, int W, void* dx, int dx_pix_stride, int dx_c_off, void* stream) {
+    if (getenv("B200SR_CONV_V1") == nullptr && H % C3_TILE_H == 0 && W % C3_TILE_W == 0)
+        return run_conv3(2, dup, dup_pix_stride, dup_c_off, Cout, w_packed, Cin, B, H, W, dx, dx_pix_stride, dx_c_off,
+                         nullptr, nullptr, 0, nullptr, 0, Cin, static_cast<cudaStream_t>(stream));
     return run_igemm(1, dup, dup_pix_stride, dup_c_off, Cout, 4, w_packed, Cin, B, H, W, 0, Cin, dx, dx_pix_stride,
                      dx_c_off, nullptr, nullptr, 0, nullptr, 0, static_cast<cudaStream_t>(stream));
 }
@@ -697,6 +724,16 @@ int b200sr_bn_bwd_reduce(const void* dy, int dy_pix_stride, int dy_c_off, const 
     B2_CHECK_ARG(dy && z && scale && shift && mean && invstd && sums);
     B2_CHECK_ARG(C % 64 == 0 && dy_pix_stride % 8 == 0 && dy_c_off % 8 == 0 && replicas > 0 && npix > 0);
     B2_CHECK_ARG(aligned16(dy) && aligned16(z));
+    const int CV = C / 8;
+    if (CV <= 256 && 256 % CV == 0 && getenv("B200SR_BN_SLOW") == nullptr) {
+        const int PB = 256 / CV;
+        long long blocks = (npix + static_cast<long long>(PB) * BNB_UNROLL - 1) / (static_cast<long long>(PB) * BNB_UNROLL);
+        if (blocks > num_sms() * 8) blocks = num_sms() * 8;
+        bn_bwd_reduce_fast_kernel<<<static_cast<int>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+            static_cast<const __nv_bfloat16*>(dy), dy_pix_stride, dy_c_off, static_cast<const __nv_bfloat16*>(z), C,
+            scale, shift, mean, invstd, sums, replicas, npix);
+        return check_launch("bn_bwd_reduce_fast_kernel");
+    }
     const int cg = C / 64;
     long long slices = (npix + 32 * 8 - 1) / (32 * 8);  // >= 8 pixels per thread row
     const long long max_slices = (148 * 8 + cg - 1) / cg;
@@ -722,6 +759,16 @@ int b200sr_bn_bwd_apply(const void* dy, int dy_pix_stride, int dy_c_off, const v
     B2_CHECK_ARG(dy && z && scale && shift && mean && invstd && c1 && c2 && dz);
     B2_CHECK_ARG(C % 8 == 0 && dy_pix_stride % 8 == 0 && dy_c_off % 8 == 0 && npix > 0);
     B2_CHECK_ARG(aligned16(dy) && aligned16(z) && aligned16(dz));
+    const int CV = C / 8;
+    if (CV <= 256 && 256 % CV == 0 && getenv("B200SR_BN_SLOW") == nullptr) {
+        const int PB = 256 / CV;
+        long long blocks = (npix + static_cast<long long>(PB) * BNB_UNROLL - 1) / (static_cast<long long>(PB) * BNB_UNROLL);
+        if (blocks > num_sms() * 8) blocks = num_sms() * 8;
+        bn_bwd_apply_fast_kernel<<<static_cast<int>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+            static_cast<const __nv_bfloat16*>(dy), dy_pix_stride, dy_c_off, static_cast<const __nv_bfloat16*>(z), C,
+            scale, shift, mean, invstd, c1, c2, static_cast<__nv_bfloat16*>(dz), npix);
+        return check_launch("bn_bwd_apply_fast_kernel");
+    }
     const long long total = npix * (C / 8);
     bn_bwd_apply_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         static_cast<const __nv_bfloat16*>(dy), dy_pix_stride, dy_c_off, static_cast<const __nv_bfloat16*>(z), C, scale,

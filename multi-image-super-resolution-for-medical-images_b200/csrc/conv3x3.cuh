@@ -32,6 +32,7 @@ struct Conv3Args {
     int out_pix_stride;
     int out_c_off;
     int stats_replicas;
+    int cout_t;        // MODE 1: channels per (i,j) sub-pixel (n_total = 4 * cout_t); modulus of the affine vectors
     __nv_bfloat16* out;
     const float* col_scale;  // nullable, [n_total]
     const float* col_shift;  // nullable, [n_total]
@@ -54,12 +55,19 @@ struct C3Cfg {
     static constexpr int SMEM_BYTES = RING_BYTES + 1024 /* barriers */ + 1024 /* alignment slack */;
 };
 
-template <int BLOCK_N>
+// MODE 0: Conv2d 3x3 forward / dgrad (three haloed boxes per channel chunk, three vertical taps per box)
+// MODE 1: ConvTranspose2d k2 s2 forward as a 1-tap GEMM with N = 4*Cout and a pixel-shuffle scatter epilogue + bias
+//         (unet_model.py:67-76; writes straight into the concat slot, which replaces torch.cat at :101-113)
+// MODE 2: ConvTranspose2d k2 s2 dgrad: four taps (i,j), each gathered through the 5-D view (c, j, w, i, b*H+h)
+template <int BLOCK_N, int MODE>
 __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_kernel(const __grid_constant__ CUtensorMap map_a,
                                                                 const __grid_constant__ CUtensorMap map_b,
                                                                 const Conv3Args args) {
     using Cfg = C3Cfg<BLOCK_N>;
     constexpr int SA = Cfg::SA, SB = Cfg::SB, NH = Cfg::NH, BN_SLOT = Cfg::BN_SLOT;
+    constexpr int NG = MODE == 0 ? 3 : (MODE == 1 ? 1 : 4);  // activation boxes per 64-channel chunk
+    constexpr int NT = MODE == 0 ? 3 : 1;                    // taps served by one box
+    constexpr int A_BYTES = MODE == 0 ? C3_A_SLOT : C3_TILE_H * C3_TILE_W * 128;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* ring_a = smem;
@@ -119,16 +127,22 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_kernel(const __grid_con
                 const int w0 = (t_in % args.tiles_w) * C3_TILE_W;
                 const int n0 = n_tile * BLOCK_N;
                 for (int c = 0; c < chunks; ++c) {
-                    for (int dw = 0; dw < 3; ++dw) {
+                    for (int dw = 0; dw < NG; ++dw) {
                         mbar_wait(&a_empty[sa], pa ^ 1);
-                        mbar_arrive_expect_tx(&a_full[sa], C3_A_SLOT);
-                        tma_load_4d(&map_a, &a_full[sa], ring_a + sa * C3_A_SLOT, c * 64, w0 + dw - 1, h0 - 1, img);
+                        mbar_arrive_expect_tx(&a_full[sa], A_BYTES);
+                        if (MODE == 0)
+                            tma_load_4d(&map_a, &a_full[sa], ring_a + sa * C3_A_SLOT, c * 64, w0 + dw - 1, h0 - 1, img);
+                        else if (MODE == 1)
+                            tma_load_4d(&map_a, &a_full[sa], ring_a + sa * C3_A_SLOT, c * 64, w0, h0, img);
+                        else
+                            tma_load_5d(&map_a, &a_full[sa], ring_a + sa * C3_A_SLOT, c * 64, dw & 1, w0, dw >> 1,
+                                        img * args.H + h0);
                         if (++sa == SA) {
                             sa = 0;
                             pa ^= 1;
                         }
-                        for (int dh = 0; dh < 3; ++dh) {
-                            const int kcol = (dh * 3 + dw) * args.C + c * 64;
+                        for (int dh = 0; dh < NT; ++dh) {
+                            const int kcol = (MODE == 0 ? (dh * 3 + dw) : dw) * args.C + c * 64;
 #pragma unroll
                             for (int nh = 0; nh < NH; ++nh) {
                                 mbar_wait(&b_empty[sb], pb ^ 1);
@@ -155,10 +169,10 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_kernel(const __grid_con
                 tc_fence_after();
                 const uint32_t d_base = tmem_base + as * BLOCK_N;
                 for (int c = 0; c < chunks; ++c) {
-                    for (int dw = 0; dw < 3; ++dw) {
+                    for (int dw = 0; dw < NG; ++dw) {
                         mbar_wait(&a_full[sa], pa);
                         const uint32_t a_addr = smem_u32(ring_a + sa * C3_A_SLOT);
-                        for (int dh = 0; dh < 3; ++dh) {
+                        for (int dh = 0; dh < NT; ++dh) {
                             const uint64_t da = umma_smem_desc_sw128(a_addr + dh * 1024, 0, 1024);
 #pragma unroll
                             for (int nh = 0; nh < NH; ++nh) {
@@ -212,7 +226,9 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_kernel(const __grid_con
             const int n0 = n_tile * BLOCK_N;
             n0_last = n0;
             __nv_bfloat16* dst_pix =
-                args.out + (static_cast<size_t>(img * args.H + h) * args.W + w) * args.out_pix_stride + args.out_c_off + n0;
+                MODE == 1 ? args.out + args.out_c_off
+                          : args.out + (static_cast<size_t>(img * args.H + h) * args.W + w) * args.out_pix_stride +
+                                args.out_c_off + n0;
             mbar_wait(&acc_full[as], pacc);
             tc_fence_after();
             const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BLOCK_N;
@@ -225,7 +241,7 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_kernel(const __grid_con
 #pragma unroll
                 for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
                 if (affine) {
-                    const int c0 = n0 + chunk * 32;
+                    const int c0 = MODE == 1 ? (n0 + chunk * 32) % args.cout_t : n0 + chunk * 32;
 #pragma unroll
                     for (int i = 0; i < 32; ++i) {
                         const float sc = args.col_scale ? __ldg(args.col_scale + c0 + i) : 1.f;
@@ -240,7 +256,17 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_kernel(const __grid_con
                 uint32_t packed[16];
 #pragma unroll
                 for (int i = 0; i < 16; ++i) packed[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
-                uint4* dst = reinterpret_cast<uint4*>(dst_pix + chunk * 32);
+                uint4* dst;
+                if (MODE == 1) {
+                    const int col0 = n0 + chunk * 32;
+                    const int ij = col0 / args.cout_t;
+                    const int co = col0 - ij * args.cout_t;
+                    const int oh = 2 * h + (ij >> 1), ow = 2 * w + (ij & 1);
+                    dst = reinterpret_cast<uint4*>(
+                        dst_pix + (static_cast<size_t>(img * 2 * args.H + oh) * (2 * args.W) + ow) * args.out_pix_stride + co);
+                } else {
+                    dst = reinterpret_cast<uint4*>(dst_pix + chunk * 32);
+                }
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
                     dst[i] = make_uint4(packed[4 * i], packed[4 * i + 1], packed[4 * i + 2], packed[4 * i + 3]);

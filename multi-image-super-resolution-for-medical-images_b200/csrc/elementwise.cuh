@@ -512,6 +512,137 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const __nv_bfloat16*
     }
 }
 
+// Bandwidth-tuned variants for C in {64,...,2048} with 256 % (C/8) == 0: a thread owns 8 fixed channels (all
+// per-channel constants live in registers) and walks pixels with 4 independent 16-byte loads in flight per tensor.
+__device__ __forceinline__ uint4 ld_stream(const __nv_bfloat16* p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+__device__ __forceinline__ F8 unpack8(const uint4& u) {
+    F8 r;
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        r.v[2 * i] = __low2float(h[i]);
+        r.v[2 * i + 1] = __high2float(h[i]);
+    }
+    return r;
+}
+
+constexpr int BNB_UNROLL = 4;
+
+__global__ void __launch_bounds__(256) bn_bwd_reduce_fast_kernel(const __nv_bfloat16* __restrict__ dy, int dy_stride,
+                                                                 int dy_coff, const __nv_bfloat16* __restrict__ z,
+                                                                 int C, const float* __restrict__ scale,
+                                                                 const float* __restrict__ shift,
+                                                                 const float* __restrict__ mean,
+                                                                 const float* __restrict__ invstd,
+                                                                 float* __restrict__ sums, int replicas,
+                                                                 long long npix) {
+    const int CV = C >> 3;            // channel vectors per pixel
+    const int PB = 256 / CV;          // pixels per block iteration
+    const int cv = threadIdx.x % CV, pl = threadIdx.x / CV;
+    const int c = cv * 8;
+    const F8 sc = ld_f32x8(scale + c), sh = ld_f32x8(shift + c), mu = ld_f32x8(mean + c);
+    float s1[8], s2[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s1[k] = s2[k] = 0.f;
+    const long long step = static_cast<long long>(gridDim.x) * PB;
+    for (long long p0 = static_cast<long long>(blockIdx.x) * PB + pl; p0 < npix; p0 += step * BNB_UNROLL) {
+        uint4 g[BNB_UNROLL], zz[BNB_UNROLL];
+#pragma unroll
+        for (int u = 0; u < BNB_UNROLL; ++u) {
+            const long long p = p0 + u * step;
+            if (p < npix) {
+                g[u] = ld_stream(dy + p * dy_stride + dy_coff + c);
+                zz[u] = ld_stream(z + p * C + c);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < BNB_UNROLL; ++u) {
+            if (p0 + u * step < npix) {
+                const F8 gf = unpack8(g[u]), zf = unpack8(zz[u]);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const float gm = fmaf(zf.v[k], sc.v[k], sh.v[k]) > 0.f ? gf.v[k] : 0.f;
+                    s1[k] += gm;
+                    s2[k] = fmaf(gm, zf.v[k] - mu.v[k], s2[k]);
+                }
+            }
+        }
+    }
+    // reduce over the PB pixel lanes of the block that share a channel vector
+    __shared__ float red[2][256][9];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        red[0][threadIdx.x][k] = s1[k];
+        red[1][threadIdx.x][k] = s2[k];
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * C; i += 256) {
+        const int which = i / C, ch = i % C;
+        float acc = 0.f;
+        for (int r = 0; r < PB; ++r) acc += red[which][r * CV + (ch >> 3)][ch & 7];
+        if (which == 1) acc *= invstd[ch];
+        atomicAdd(sums + (static_cast<size_t>(blockIdx.x % replicas) * 2 + which) * C + ch, acc);
+    }
+}
+
+__global__ void __launch_bounds__(256) bn_bwd_apply_fast_kernel(const __nv_bfloat16* __restrict__ dy, int dy_stride,
+                                                                int dy_coff, const __nv_bfloat16* __restrict__ z, int C,
+                                                                const float* __restrict__ scale,
+                                                                const float* __restrict__ shift,
+                                                                const float* __restrict__ mean,
+                                                                const float* __restrict__ invstd,
+                                                                const float* __restrict__ c1,
+                                                                const float* __restrict__ c2,
+                                                                __nv_bfloat16* __restrict__ dz, long long npix) {
+    const int CV = C >> 3;
+    const int PB = 256 / CV;
+    const int cv = threadIdx.x % CV, pl = threadIdx.x / CV;
+    const int c = cv * 8;
+    const F8 sc = ld_f32x8(scale + c), sh = ld_f32x8(shift + c);
+    F8 ka, kb;  // dz = gm*scale + z*ka + kb
+    {
+        const F8 mu = ld_f32x8(mean + c), is = ld_f32x8(invstd + c), k1 = ld_f32x8(c1 + c), k2 = ld_f32x8(c2 + c);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const float t = is.v[k] * k2.v[k] * sc.v[k];
+            ka.v[k] = -t;
+            kb.v[k] = mu.v[k] * t - sc.v[k] * k1.v[k];
+        }
+    }
+    const long long step = static_cast<long long>(gridDim.x) * PB;
+    for (long long p0 = static_cast<long long>(blockIdx.x) * PB + pl; p0 < npix; p0 += step * BNB_UNROLL) {
+        uint4 g[BNB_UNROLL], zz[BNB_UNROLL];
+#pragma unroll
+        for (int u = 0; u < BNB_UNROLL; ++u) {
+            const long long p = p0 + u * step;
+            if (p < npix) {
+                g[u] = ld_stream(dy + p * dy_stride + dy_coff + c);
+                zz[u] = ld_stream(z + p * C + c);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < BNB_UNROLL; ++u) {
+            const long long p = p0 + u * step;
+            if (p < npix) {
+                const F8 gf = unpack8(g[u]), zf = unpack8(zz[u]);
+                F8 o;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const float gm = fmaf(zf.v[k], sc.v[k], sh.v[k]) > 0.f ? gf.v[k] : 0.f;
+                    o.v[k] = fmaf(gm, sc.v[k], fmaf(zf.v[k], ka.v[k], kb.v[k]));
+                }
+                st_bf16x8(dz + p * C + c, o);
+            }
+        }
+    }
+}
+
 __global__ void bn_bwd_finalize_kernel(const float* __restrict__ sums, int replicas, int C, float count,
                                        float* __restrict__ c1, float* __restrict__ c2, float* __restrict__ dgamma,
                                        float* __restrict__ dbeta) {

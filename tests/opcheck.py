@@ -360,6 +360,12 @@ CHECKS = {
     "convT_fwd": (convT_fwd, {}, {"out": BF16, "slot_untouched": 0.0}),
     "convT_fwd_big": (convT_fwd, dict(Cin=1024, Cout=512, B=1, H=8, W=16), {"out": BF16}),
     "convT_dgrad": (convT_dgrad, {}, {"dx": BF16}),
+    # 16x8-tileable shapes run on the persistent kernel (modes 1 and 2)
+    "convT_fwd_persistent": (convT_fwd, dict(Cin=128, Cout=64, B=3, H=16, W=24), {"out": BF16, "slot_untouched": 0.0}),
+    "convT_fwd_persistent_big": (convT_fwd, dict(Cin=1024, Cout=512, B=2, H=16, W=16), {"out": BF16}),
+    "convT_fwd_persistent_many": (convT_fwd, dict(Cin=128, Cout=64, B=4, H=64, W=64), {"out": BF16}),
+    "convT_dgrad_persistent": (convT_dgrad, dict(Cin=128, Cout=64, B=3, H=16, W=24), {"dx": BF16}),
+    "convT_dgrad_persistent_big": (convT_dgrad, dict(Cin=1024, Cout=512, B=2, H=16, W=16), {"dx": BF16}),
     "convT_wgrad": (convT_wgrad, {}, {"dw": BF16}),
     "convT_wgrad_big": (convT_wgrad, dict(Cin=512, Cout=256, B=1, H=8, W=16), {"dw": BF16}),
     "conv1": (conv1, {}, {"out": BF16, "stats_sum": 1e-3, "stats_sq": 1e-3, "dw": 1e-3}),
@@ -367,6 +373,9 @@ CHECKS = {
                                      "maxpool_fwd_exact": 0.0, "slot_untouched": 0.0}),
     "maxpool_bwd_ties": (maxpool_bwd, {}, {"dy_exact": 0.0}),
     "bn_bwd": (bn_bwd, {}, {"dz": BF16, "dgamma": 1e-3, "dbeta": 1e-3}),
+    "bn_bwd_c1024": (bn_bwd, dict(C=1024, B=3, H=8, W=8), {"dz": BF16, "dgamma": 1e-3, "dbeta": 1e-3}),
+    "bn_bwd_c64_large": (bn_bwd, dict(C=64, B=2, H=96, W=80), {"dz": BF16, "dgamma": 1e-3, "dbeta": 1e-3}),
+    "bn_bwd_c24_generic": (bn_bwd, dict(C=192, B=2, H=8, W=8), {"dz": BF16, "dgamma": 1e-3, "dbeta": 1e-3}),
     "head": (head, {}, {"out": 1e-5, "dact": BF16, "dw": 1e-4, "db": 1e-4}),
     "mse_ssim_gaussian": (mse_ssim, {}, {"loss": 1e-5, "grad": 1e-4}),
     "mse_ssim_uniform": (mse_ssim, dict(mode="uniform", H=64, W=100), {"loss": 1e-5, "grad": 1e-4}),
