@@ -222,13 +222,15 @@ def run_b200sr(args):
         inf_big_value = world * B * 10 / (inf_big_ms / 1e3)
 
     # ---- roofline of the dominant kernel (tensor-core implicit GEMM), timed live with CUDA events ------------
+    # every rank runs the 3 instrumented steps (the train step contains collectives); rank 0 records them
     roofline = None
+    model.train()
     if rank == 0:
-        model.train()
-        prof = _lib.enable_profiling(True)
-        for i in range(3):
-            step_resident(i)
-        torch.cuda.synchronize()
+        _lib.enable_profiling(True)
+    for i in range(3):
+        step_resident(i)
+    sync_all()
+    if rank == 0:
         agg = _lib.collect_profile()
         _lib.enable_profiling(False)
         gemm = {k: v for k, v in agg.items() if k in _lib.GEMM_OPS}

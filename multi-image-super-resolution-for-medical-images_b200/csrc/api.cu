@@ -279,7 +279,8 @@ int num_sms() {
 }
 
 template <int BLOCK_N, int MODE>
-int launch_conv3_t(const CUtensorMap& ma, const CUtensorMap& mb, const Conv3Args& args, int grid, cudaStream_t st) {
+int launch_conv3_t(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mo, const Conv3Args& args, int grid,
+                   cudaStream_t st) {
     constexpr int smem = C3Cfg<BLOCK_N>::SMEM_BYTES;
     static bool configured = false;
     if (!configured) {
@@ -288,20 +289,20 @@ int launch_conv3_t(const CUtensorMap& ma, const CUtensorMap& mb, const Conv3Args
         if (e != cudaSuccess) return fail(B200SR_ECUDA, std::string("conv3x3 smem attribute: ") + cudaGetErrorString(e));
         configured = true;
     }
-    conv3x3_kernel<BLOCK_N, MODE><<<grid, C3_THREADS, smem, st>>>(ma, mb, args);
+    conv3x3_kernel<BLOCK_N, MODE><<<grid, C3_THREADS, smem, st>>>(ma, mb, mo, args);
     return check_launch("conv3x3_kernel");
 }
 
 template <int MODE>
-int dispatch_conv3(int block_n, const CUtensorMap& ma, const CUtensorMap& mb, const Conv3Args& args, int grid,
-                   cudaStream_t st) {
+int dispatch_conv3(int block_n, const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mo,
+                   const Conv3Args& args, int grid, cudaStream_t st) {
     switch (block_n) {
         case 64:
-            return launch_conv3_t<64, MODE>(ma, mb, args, grid, st);
+            return launch_conv3_t<64, MODE>(ma, mb, mo, args, grid, st);
         case 128:
-            return launch_conv3_t<128, MODE>(ma, mb, args, grid, st);
+            return launch_conv3_t<128, MODE>(ma, mb, mo, args, grid, st);
         default:
-            return launch_conv3_t<256, MODE>(ma, mb, args, grid, st);
+            return launch_conv3_t<256, MODE>(ma, mb, mo, args, grid, st);
     }
 }
 
@@ -334,6 +335,14 @@ int run_conv3(int mode, const void* a, int a_stride, int a_coff, int Ca, const v
     const int taps = mode == 0 ? 9 : (mode == 1 ? 1 : 4);
     rc = make_weight_map(&mb, w_packed, taps * Ca, n_total, block_n < 128 ? block_n : 128);
     if (rc) return rc;
+    // output tile store: 128 pixels x 64 channels per TMA store; mode 1 scatters through the sub-pixel view
+    CUtensorMap mo;
+    if (mode == 1)
+        rc = make_gather_map(&mo, out, out_stride, out_coff, cout_t, B, H, W, C3_TILE_W, C3_TILE_H);
+    else
+        rc = make_act_map(&mo, out, out_stride, out_coff, n_total, B, H, W, C3_TILE_W, C3_TILE_H);
+    if (rc) return rc;
+    if (mode == 1) B2_CHECK_ARG(cout_t % 64 == 0);
     Conv3Args args;
     args.H = H;
     args.W = W;
@@ -360,9 +369,9 @@ int run_conv3(int mode, const void* a, int a_stride, int a_coff, int Ca, const v
     grid -= grid % args.n_tiles;
     if (grid < args.n_tiles) grid = args.n_tiles;
     if (grid > args.num_tiles) grid = args.num_tiles;
-    if (mode == 0) return dispatch_conv3<0>(block_n, ma, mb, args, grid, st);
-    if (mode == 1) return dispatch_conv3<1>(block_n, ma, mb, args, grid, st);
-    return dispatch_conv3<2>(block_n, ma, mb, args, grid, st);
+    if (mode == 0) return dispatch_conv3<0>(block_n, ma, mb, mo, args, grid, st);
+    if (mode == 1) return dispatch_conv3<1>(block_n, ma, mb, mo, args, grid, st);
+    return dispatch_conv3<2>(block_n, ma, mb, mo, args, grid, st);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -632,7 +641,7 @@ int b200sr_convT2x2_wgrad(const void* dup, int dup_pix_stride, int dup_c_off, in
 int b200sr_pack_jobs(const b200sr_pack_job* jobs, int njobs, void* stream) {
     B2_CHECK_ARG(jobs != nullptr && njobs > 0);
     static_assert(sizeof(b200sr_pack_job) == sizeof(PackJob), "PackJob ABI mismatch");
-    dim3 grid(296, njobs);
+    dim3 grid(1024, njobs);  // >= tiles of the largest layer; blocks beyond a job's tile count exit at once
     pack_jobs_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const PackJob*>(jobs));
     return check_launch("pack_jobs_kernel");
 }
@@ -653,10 +662,11 @@ int b200sr_conv1_fwd(const float* x, const float* w, const float* col_scale, con
     B2_CHECK_ARG((col_scale == nullptr) == (col_shift == nullptr));
     B2_CHECK_ARG(stats == nullptr || stats_replicas > 0);
     B2_CHECK_ARG(aligned16(out));
-    const int grid = B * (H / C1_TILE) * (W / C1_TILE);
+    const int tiles = B * (H / C1_TILE) * (W / C1_TILE);
+    const int grid = tiles < num_sms() * 6 ? tiles : num_sms() * 6;
     conv1_direct_fwd_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
         x, w, col_scale, col_shift, relu, static_cast<__nv_bfloat16*>(out), stats, stats_replicas > 0 ? stats_replicas : 1,
-        H, W);
+        H, W, tiles);
     return check_launch("conv1_direct_fwd_kernel");
 }
 

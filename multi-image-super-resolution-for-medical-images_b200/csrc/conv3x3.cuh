@@ -43,6 +43,7 @@ constexpr int C3_THREADS = 256;
 constexpr int C3_TILE_H = 16;
 constexpr int C3_TILE_W = 8;
 constexpr int C3_A_SLOT = (C3_TILE_H + 2) * C3_TILE_W * 128;  // 18432 B: 18 pixel rows x 8 pixels x 64 ch bf16
+constexpr int C3_OUT_STAGE = C3_TILE_H * C3_TILE_W * 128;     // 16384 B: 128 pixels x 64 ch bf16
 
 template <int BLOCK_N>
 struct C3Cfg {
@@ -50,9 +51,10 @@ struct C3Cfg {
     static constexpr int NH = BLOCK_N / BN_SLOT;
     static constexpr int B_SLOT = BN_SLOT * 128;
     static constexpr int SA = BLOCK_N == 64 ? 4 : 3;
-    static constexpr int SB = BLOCK_N == 64 ? 16 : 10;
+    static constexpr int SB = BLOCK_N == 64 ? 12 : 8;
+    static constexpr int STAGING = 2 * C3_OUT_STAGE;  // double-buffered output tile (128 pixels x 64 ch) for TMA stores
     static constexpr int RING_BYTES = SA * C3_A_SLOT + SB * B_SLOT;
-    static constexpr int SMEM_BYTES = RING_BYTES + 1024 /* barriers */ + 1024 /* alignment slack */;
+    static constexpr int SMEM_BYTES = RING_BYTES + STAGING + 1024 /* barriers */ + 1024 /* alignment slack */;
 };
 
 // MODE 0: Conv2d 3x3 forward / dgrad (three haloed boxes per channel chunk, three vertical taps per box)
@@ -62,6 +64,7 @@ struct C3Cfg {
 template <int BLOCK_N, int MODE>
 __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_kernel(const __grid_constant__ CUtensorMap map_a,
                                                                 const __grid_constant__ CUtensorMap map_b,
+                                                                const __grid_constant__ CUtensorMap map_out,
                                                                 const Conv3Args args) {
     using Cfg = C3Cfg<BLOCK_N>;
     constexpr int SA = Cfg::SA, SB = Cfg::SB, NH = Cfg::NH, BN_SLOT = Cfg::BN_SLOT;
@@ -72,7 +75,8 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_kernel(const __grid_con
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* ring_a = smem;
     uint8_t* ring_b = smem + SA * C3_A_SLOT;
-    uint64_t* a_full = reinterpret_cast<uint64_t*>(smem + Cfg::RING_BYTES);
+    uint8_t* out_stage = smem + Cfg::RING_BYTES;  // 1024-byte aligned (all slot sizes are multiples of 1024)
+    uint64_t* a_full = reinterpret_cast<uint64_t*>(smem + Cfg::RING_BYTES + Cfg::STAGING);
     uint64_t* a_empty = a_full + SA;
     uint64_t* b_full = a_empty + SA;
     uint64_t* b_empty = b_full + SB;
@@ -86,6 +90,7 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_kernel(const __grid_con
     if (warp == 0 && elect_one()) {
         tma_prefetch_desc(&map_a);
         tma_prefetch_desc(&map_b);
+        tma_prefetch_desc(&map_out);
     }
     if (warp == 1 && elect_one()) {
         for (int s = 0; s < SA; ++s) {
@@ -210,81 +215,97 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_kernel(const __grid_con
         const int row = q * 32 + lane;  // pixel inside the tile: row = h_local * 8 + w_local
         const bool do_stats = args.stats != nullptr;
         const bool affine = args.col_scale != nullptr || args.col_shift != nullptr;
+        const bool issuer = threadIdx.x == 128;  // issues the TMA stores
         float st_sum[BLOCK_N / 32], st_sq[BLOCK_N / 32];
 #pragma unroll
         for (int i = 0; i < BLOCK_N / 32; ++i) st_sum[i] = st_sq[i] = 0.f;
         int as = 0;
         uint32_t pacc = 0;
         int n0_last = 0;
+        uint32_t sbuf = 0;  // staging buffer used by the next 64-column group
+        // swizzled position of this thread's pixel row inside a staging buffer (128-byte rows, 16-byte chunk j is
+        // stored at chunk j ^ (row & 7)): the layout a SWIZZLE_128B TMA store expects, and conflict-free to write
+        const uint32_t row_off = static_cast<uint32_t>(row) * 128u;
+        const uint32_t row_xor = static_cast<uint32_t>(row & 7);
         for (int tile = blockIdx.x; tile < args.num_tiles; tile += gridDim.x) {
             const int n_tile = tile % args.n_tiles;
             const int m_tile = tile / args.n_tiles;
             const int img = m_tile / args.tiles_hw;
             const int t_in = m_tile - img * args.tiles_hw;
-            const int h = (t_in / args.tiles_w) * C3_TILE_H + (row >> 3);
-            const int w = (t_in % args.tiles_w) * C3_TILE_W + (row & 7);
+            const int h0 = (t_in / args.tiles_w) * C3_TILE_H;
+            const int w0 = (t_in % args.tiles_w) * C3_TILE_W;
             const int n0 = n_tile * BLOCK_N;
             n0_last = n0;
-            __nv_bfloat16* dst_pix =
-                MODE == 1 ? args.out + args.out_c_off
-                          : args.out + (static_cast<size_t>(img * args.H + h) * args.W + w) * args.out_pix_stride +
-                                args.out_c_off + n0;
             mbar_wait(&acc_full[as], pacc);
             tc_fence_after();
             const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BLOCK_N;
 #pragma unroll
-            for (int chunk = 0; chunk < BLOCK_N / 32; ++chunk) {
-                uint32_t raw[32];
-                tmem_ld32(t_addr + chunk * 32, raw);
-                tmem_ld_wait();
-                float v[32];
+            for (int grp = 0; grp < BLOCK_N / 64; ++grp) {
+                uint8_t* stage = out_stage + sbuf * C3_OUT_STAGE;
 #pragma unroll
-                for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
-                if (affine) {
-                    const int c0 = MODE == 1 ? (n0 + chunk * 32) % args.cout_t : n0 + chunk * 32;
+                for (int half = 0; half < 2; ++half) {
+                    const int chunk = grp * 2 + half;
+                    uint32_t raw[32];
+                    tmem_ld32(t_addr + chunk * 32, raw);
+                    tmem_ld_wait();
+                    float v[32];
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        const float sc = args.col_scale ? __ldg(args.col_scale + c0 + i) : 1.f;
-                        const float sh = args.col_shift ? __ldg(args.col_shift + c0 + i) : 0.f;
-                        v[i] = fmaf(v[i], sc, sh);
+                    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
+                    if (affine) {
+                        const int c0 = MODE == 1 ? (n0 + chunk * 32) % args.cout_t : n0 + chunk * 32;
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            const float sc = args.col_scale ? __ldg(args.col_scale + c0 + i) : 1.f;
+                            const float sh = args.col_shift ? __ldg(args.col_shift + c0 + i) : 0.f;
+                            v[i] = fmaf(v[i], sc, sh);
+                        }
+                    }
+                    if (args.relu) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+                    }
+                    uint32_t packed[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) packed[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const uint32_t j = static_cast<uint32_t>(half * 4 + i);
+                        *reinterpret_cast<uint4*>(stage + row_off + ((j ^ row_xor) << 4)) =
+                            make_uint4(packed[4 * i], packed[4 * i + 1], packed[4 * i + 2], packed[4 * i + 3]);
+                    }
+                    if (do_stats) {
+                        // statistics of the tensor as stored (bf16-rounded), like BatchNorm reading the conv output
+                        float s1[32], s2[32];
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            const __nv_bfloat162 hh = *reinterpret_cast<const __nv_bfloat162*>(&packed[i]);
+                            const float a = __low2float(hh), b = __high2float(hh);
+                            s1[2 * i] = a;
+                            s1[2 * i + 1] = b;
+                            s2[2 * i] = a * a;
+                            s2[2 * i + 1] = b * b;
+                        }
+                        st_sum[chunk] += warp_transpose_reduce32(s1, lane);
+                        st_sq[chunk] += warp_transpose_reduce32(s2, lane);
                     }
                 }
-                if (args.relu) {
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
-                }
-                uint32_t packed[16];
-#pragma unroll
-                for (int i = 0; i < 16; ++i) packed[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
-                uint4* dst;
-                if (MODE == 1) {
-                    const int col0 = n0 + chunk * 32;
-                    const int ij = col0 / args.cout_t;
-                    const int co = col0 - ij * args.cout_t;
-                    const int oh = 2 * h + (ij >> 1), ow = 2 * w + (ij & 1);
-                    dst = reinterpret_cast<uint4*>(
-                        dst_pix + (static_cast<size_t>(img * 2 * args.H + oh) * (2 * args.W) + ow) * args.out_pix_stride + co);
-                } else {
-                    dst = reinterpret_cast<uint4*>(dst_pix + chunk * 32);
-                }
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-                    dst[i] = make_uint4(packed[4 * i], packed[4 * i + 1], packed[4 * i + 2], packed[4 * i + 3]);
-                if (do_stats) {
-                    // statistics of the tensor as stored (bf16-rounded), like BatchNorm reading the conv output
-                    float s1[32], s2[32];
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        const __nv_bfloat162 hh = *reinterpret_cast<const __nv_bfloat162*>(&packed[i]);
-                        const float a = __low2float(hh), b = __high2float(hh);
-                        s1[2 * i] = a;
-                        s1[2 * i + 1] = b;
-                        s2[2 * i] = a * a;
-                        s2[2 * i + 1] = b * b;
+                // make the generic-proxy writes visible to the TMA engine, make sure the OTHER buffer's previous
+                // store has finished reading shared memory (it is the next one to be overwritten), then store
+                fence_proxy_async_smem();
+                if (issuer) tma_store_wait_read<0>();
+                named_bar_sync(1, 128);
+                if (issuer) {
+                    const int col0 = n0 + grp * 64;
+                    if (MODE == 1) {
+                        const int ij = col0 / args.cout_t;
+                        const int co = col0 - ij * args.cout_t;
+                        tma_store_5d(&map_out, stage, co, ij & 1, w0, ij >> 1, img * args.H + h0);
+                    } else {
+                        tma_store_4d(&map_out, stage, col0, w0, h0, img);
                     }
-                    st_sum[chunk] += warp_transpose_reduce32(s1, lane);
-                    st_sq[chunk] += warp_transpose_reduce32(s2, lane);
+                    tma_store_commit();
                 }
+                sbuf ^= 1;
             }
             // all TMEM reads of this thread have completed (tmem_ld_wait above): hand the accumulator back
             tc_fence_before();
@@ -294,6 +315,7 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_kernel(const __grid_con
                 pacc ^= 1;
             }
         }
+        if (issuer) tma_store_wait<0>();  // global writes complete before the CTA retires
         if (do_stats && blockIdx.x < args.num_tiles) {
             // the tile schedule keeps this CTA on one column block (gridDim.x % n_tiles == 0, or one tile per CTA)
             float* dst = args.stats + static_cast<size_t>(blockIdx.x % args.stats_replicas) * 2 * args.n_total + n0_last;

@@ -67,65 +67,86 @@ struct PackJob {
     long long count;  // elements of dst
 };
 
-__global__ void pack_jobs_kernel(const PackJob* __restrict__ jobs) {
+// One 32 x 32 x T tile (T = 9 conv taps or 4 sub-pixels) per block iteration, staged through shared memory so that
+// BOTH the global reads and the global writes are coalesced runs (the element-wise version read fp32 weights with a
+// 36-byte stride). "outer" is the leading parameter dimension (Cout for Conv2d, Cin for ConvTranspose2d).
+constexpr int PK_TILE = 32;
+
+__global__ void __launch_bounds__(256) pack_jobs_kernel(const PackJob* __restrict__ jobs) {
+    __shared__ float tile[PK_TILE][PK_TILE * 9 + 1];
     const PackJob job = jobs[blockIdx.y];
     const int Cout = job.cout, Cin = job.cin;
-    for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < job.count;
-         idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const bool conv = job.kind == PACK_CONV_FWD || job.kind == PACK_CONV_DGRAD || job.kind == UNPACK_CONV_WGRAD;
+    const int T = conv ? 9 : 4;
+    const int outer_total = conv ? Cout : Cin, inner_total = conv ? Cin : Cout;
+    const int tiles_in = inner_total / PK_TILE;
+    const int num_tiles = (outer_total / PK_TILE) * tiles_in;
+    const int row = PK_TILE * T;  // floats per outer index inside a tile
+    const int tid = threadIdx.x;
+    for (int tl = blockIdx.x; tl < num_tiles; tl += gridDim.x) {
+        const int o0 = (tl / tiles_in) * PK_TILE, i0 = (tl % tiles_in) * PK_TILE;
+        __syncthreads();
+        // ---- load ----
+        if (job.kind <= PACK_CONVT_DGRAD) {
+            const float* src = static_cast<const float*>(job.src);
+            for (int idx = tid; idx < PK_TILE * row; idx += 256) {
+                const int o = idx / row, r = idx - o * row;
+                tile[o][r] = src[(static_cast<long long>(o0 + o) * inner_total + i0) * T + r];
+            }
+        } else {
+            const float* src = static_cast<const float*>(job.src);  // G[t][inner][outer] (conv) / G[ij][inner][outer]
+            for (int idx = tid; idx < PK_TILE * row; idx += 256) {
+                const int o = idx % PK_TILE, i = (idx / PK_TILE) % PK_TILE, t = idx / (PK_TILE * PK_TILE);
+                tile[o][i * T + t] = src[(static_cast<long long>(t) * inner_total + i0 + i) * outer_total + o0 + o];
+            }
+        }
+        __syncthreads();
+        // ---- store ----
         switch (job.kind) {
-            case PACK_CONV_FWD: {
-                const int ci = idx % Cin;
-                const int t = (idx / Cin) % 9;
-                const int co = idx / (9LL * Cin);
-                const float v = static_cast<const float*>(job.src)[(static_cast<long long>(co) * Cin + ci) * 9 + t];
-                static_cast<__nv_bfloat16*>(job.dst)[idx] = __float2bfloat16_rn(v);
+            case PACK_CONV_FWD: {  // dst[co][t*Cin + ci]
+                __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(job.dst);
+                for (int idx = tid; idx < PK_TILE * row; idx += 256) {
+                    const int i = idx % PK_TILE, t = (idx / PK_TILE) % 9, o = idx / (PK_TILE * 9);
+                    dst[static_cast<long long>(o0 + o) * (9LL * Cin) + t * Cin + i0 + i] =
+                        __float2bfloat16_rn(tile[o][i * 9 + t]);
+                }
                 break;
             }
-            case PACK_CONV_DGRAD: {
-                const int co = idx % Cout;
-                const int t = (idx / Cout) % 9;
-                const int ci = idx / (9LL * Cout);
-                // tap' with offset (dh,dw) = (t/3-1, t%3-1) multiplies W[co][ci][1-dh][1-dw]
-                const int kh = 2 - t / 3, kw = 2 - t % 3;
-                const float v =
-                    static_cast<const float*>(job.src)[(static_cast<long long>(co) * Cin + ci) * 9 + kh * 3 + kw];
-                static_cast<__nv_bfloat16*>(job.dst)[idx] = __float2bfloat16_rn(v);
+            case PACK_CONV_DGRAD: {  // dst[ci][t*Cout + co] = W[co][ci][8 - t]  (taps rotated by 180 degrees)
+                __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(job.dst);
+                for (int idx = tid; idx < PK_TILE * row; idx += 256) {
+                    const int o = idx % PK_TILE, t = (idx / PK_TILE) % 9, i = idx / (PK_TILE * 9);
+                    dst[static_cast<long long>(i0 + i) * (9LL * Cout) + t * Cout + o0 + o] =
+                        __float2bfloat16_rn(tile[o][i * 9 + 8 - t]);
+                }
                 break;
             }
-            case PACK_CONVT_FWD: {
-                const int ci = idx % Cin;
-                const int co = (idx / Cin) % Cout;
-                const int ij = idx / (static_cast<long long>(Cin) * Cout);
-                const float v = static_cast<const float*>(job.src)[(static_cast<long long>(ci) * Cout + co) * 4 + ij];
-                static_cast<__nv_bfloat16*>(job.dst)[idx] = __float2bfloat16_rn(v);
+            case PACK_CONVT_FWD: {  // dst[ij*Cout + co][ci], outer = ci, inner = co
+                __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(job.dst);
+                for (int idx = tid; idx < PK_TILE * row; idx += 256) {
+                    const int o = idx % PK_TILE, t = (idx / PK_TILE) % 4, i = idx / (PK_TILE * 4);
+                    dst[(static_cast<long long>(t) * Cout + i0 + i) * Cin + o0 + o] =
+                        __float2bfloat16_rn(tile[o][i * 4 + t]);
+                }
                 break;
             }
-            case PACK_CONVT_DGRAD: {
-                const int co = idx % Cout;
-                const int ij = (idx / Cout) % 4;
-                const int ci = idx / (4LL * Cout);
-                const float v = static_cast<const float*>(job.src)[(static_cast<long long>(ci) * Cout + co) * 4 + ij];
-                static_cast<__nv_bfloat16*>(job.dst)[idx] = __float2bfloat16_rn(v);
+            case PACK_CONVT_DGRAD: {  // dst[ci][ij*Cout + co]
+                __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(job.dst);
+                for (int idx = tid; idx < PK_TILE * row; idx += 256) {
+                    const int i = idx % PK_TILE, t = (idx / PK_TILE) % 4, o = idx / (PK_TILE * 4);
+                    dst[static_cast<long long>(o0 + o) * (4LL * Cout) + t * Cout + i0 + i] =
+                        __float2bfloat16_rn(tile[o][i * 4 + t]);
+                }
                 break;
             }
-            case UNPACK_CONV_WGRAD: {
-                const int t = idx % 9;
-                const int ci = (idx / 9) % Cin;
-                const int co = idx / (9LL * Cin);
-                static_cast<float*>(job.dst)[idx] =
-                    static_cast<const float*>(job.src)[(static_cast<long long>(t) * Cin + ci) * Cout + co];
+            default: {  // UNPACK_*: parameter layout [outer][inner][T], fp32
+                float* dst = static_cast<float*>(job.dst);
+                for (int idx = tid; idx < PK_TILE * row; idx += 256) {
+                    const int o = idx / row, r = idx - o * row;
+                    dst[(static_cast<long long>(o0 + o) * inner_total + i0) * T + r] = tile[o][r];
+                }
                 break;
             }
-            case UNPACK_CONVT_WGRAD: {
-                const int ij = idx % 4;
-                const int co = (idx / 4) % Cout;
-                const int ci = idx / (4LL * Cout);
-                static_cast<float*>(job.dst)[idx] =
-                    static_cast<const float*>(job.src)[(static_cast<long long>(ij) * Cout + co) * Cin + ci];
-                break;
-            }
-            default:
-                break;
         }
     }
 }
@@ -144,79 +165,90 @@ __global__ void __launch_bounds__(256) conv1_direct_fwd_kernel(const float* __re
                                                                const float* __restrict__ col_shift, int relu,
                                                                __nv_bfloat16* __restrict__ out,  // [B][H][W][64]
                                                                float* __restrict__ stats, int stats_replicas,
-                                                               int H, int W) {
+                                                               int H, int W, int num_tiles) {
     __shared__ float s_x[2][C1_TILE + 2][C1_TILE + 2];
-    __shared__ float s_w[18][C1_COUT];  // [ci*9 + tap][co]
+    __shared__ __align__(16) float s_w[18][C1_COUT];  // [ci*9 + tap][co]
     __shared__ float s_stats[2][C1_COUT];
     const int tid = threadIdx.x;
     const int tiles_w = W / C1_TILE;
     const int tiles_hw = tiles_w * (H / C1_TILE);
-    const int img = blockIdx.x / tiles_hw;
-    const int t_in = blockIdx.x - img * tiles_hw;
-    const int h0 = (t_in / tiles_w) * C1_TILE, w0 = (t_in % tiles_w) * C1_TILE;
+    const uint32_t lane = tid & 31;
+    const int ph = tid / C1_TILE, pw = tid % C1_TILE;
 
     for (int i = tid; i < 18 * C1_COUT; i += 256) {
         const int co = i % C1_COUT, k = i / C1_COUT;
         s_w[k][co] = wgt[co * 18 + k];
     }
     if (tid < 2 * C1_COUT) (&s_stats[0][0])[tid] = 0.f;
-    for (int i = tid; i < 2 * (C1_TILE + 2) * (C1_TILE + 2); i += 256) {
-        const int ci = i / ((C1_TILE + 2) * (C1_TILE + 2));
-        const int r = i % ((C1_TILE + 2) * (C1_TILE + 2));
-        const int hh = h0 + r / (C1_TILE + 2) - 1, ww = w0 + r % (C1_TILE + 2) - 1;
-        float v = 0.f;
-        if (hh >= 0 && hh < H && ww >= 0 && ww < W) v = x[((static_cast<size_t>(img) * 2 + ci) * H + hh) * W + ww];
-        s_x[ci][r / (C1_TILE + 2)][r % (C1_TILE + 2)] = v;
-    }
-    __syncthreads();
 
-    const int ph = tid / C1_TILE, pw = tid % C1_TILE;
-    float in[18];
-#pragma unroll
-    for (int ci = 0; ci < 2; ++ci)
-#pragma unroll
-        for (int t = 0; t < 9; ++t) in[ci * 9 + t] = s_x[ci][ph + t / 3][pw + t % 3];
+    // persistent blocks: statistics accumulate in shared memory across tiles, one global flush per block
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int img = tile / tiles_hw;
+        const int t_in = tile - img * tiles_hw;
+        const int h0 = (t_in / tiles_w) * C1_TILE, w0 = (t_in % tiles_w) * C1_TILE;
+        __syncthreads();
+        for (int i = tid; i < 2 * (C1_TILE + 2) * (C1_TILE + 2); i += 256) {
+            const int ci = i / ((C1_TILE + 2) * (C1_TILE + 2));
+            const int r = i % ((C1_TILE + 2) * (C1_TILE + 2));
+            const int hh = h0 + r / (C1_TILE + 2) - 1, ww = w0 + r % (C1_TILE + 2) - 1;
+            float v = 0.f;
+            if (hh >= 0 && hh < H && ww >= 0 && ww < W) v = x[((static_cast<size_t>(img) * 2 + ci) * H + hh) * W + ww];
+            s_x[ci][r / (C1_TILE + 2)][r % (C1_TILE + 2)] = v;
+        }
+        __syncthreads();
 
-    __nv_bfloat16* dst = out + ((static_cast<size_t>(img) * H + h0 + ph) * W + w0 + pw) * C1_COUT;
-    const uint32_t lane = tid & 31;
+        float in[18];
+#pragma unroll
+        for (int ci = 0; ci < 2; ++ci)
+#pragma unroll
+            for (int t = 0; t < 9; ++t) in[ci * 9 + t] = s_x[ci][ph + t / 3][pw + t % 3];
+
+        __nv_bfloat16* dst = out + ((static_cast<size_t>(img) * H + h0 + ph) * W + w0 + pw) * C1_COUT;
 #pragma unroll 1
-    for (int cb = 0; cb < C1_COUT; cb += 32) {
-        float acc[32];
+        for (int cb = 0; cb < C1_COUT; cb += 32) {
+            float acc[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) acc[j] = 0.f;
+            for (int j = 0; j < 32; ++j) acc[j] = 0.f;
 #pragma unroll
-        for (int k = 0; k < 18; ++k) {
+            for (int k = 0; k < 18; ++k) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) acc[j] = fmaf(in[k], s_w[k][cb + j], acc[j]);
-        }
-        if (col_scale != nullptr) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) acc[j] = fmaf(acc[j], col_scale[cb + j], col_shift[cb + j]);
-        }
-        if (relu) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) acc[j] = fmaxf(acc[j], 0.f);
-        }
-        uint32_t packed[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) packed[j] = pack_bf16x2(acc[2 * j], acc[2 * j + 1]);
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-            reinterpret_cast<uint4*>(dst + cb)[j] =
-                make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
-        if (stats != nullptr) {
-            float s1[32], s2[32];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const __nv_bfloat162 hh = *reinterpret_cast<const __nv_bfloat162*>(&packed[j]);
-                const float a = __low2float(hh), b = __high2float(hh);
-                s1[2 * j] = a; s1[2 * j + 1] = b;
-                s2[2 * j] = a * a; s2[2 * j + 1] = b * b;
+                for (int j = 0; j < 32; j += 4) {
+                    const float4 w4 = *reinterpret_cast<const float4*>(&s_w[k][cb + j]);  // one LDS.128 per 4 FMAs
+                    acc[j] = fmaf(in[k], w4.x, acc[j]);
+                    acc[j + 1] = fmaf(in[k], w4.y, acc[j + 1]);
+                    acc[j + 2] = fmaf(in[k], w4.z, acc[j + 2]);
+                    acc[j + 3] = fmaf(in[k], w4.w, acc[j + 3]);
+                }
             }
-            const float cs = warp_transpose_reduce32(s1, lane);
-            const float cq = warp_transpose_reduce32(s2, lane);
-            atomicAdd(&s_stats[0][cb + lane], cs);
-            atomicAdd(&s_stats[1][cb + lane], cq);
+            if (col_scale != nullptr) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) acc[j] = fmaf(acc[j], col_scale[cb + j], col_shift[cb + j]);
+            }
+            if (relu) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) acc[j] = fmaxf(acc[j], 0.f);
+            }
+            uint32_t packed[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) packed[j] = pack_bf16x2(acc[2 * j], acc[2 * j + 1]);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                reinterpret_cast<uint4*>(dst + cb)[j] =
+                    make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+            if (stats != nullptr) {
+                float s1[32], s2[32];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const __nv_bfloat162 hh = *reinterpret_cast<const __nv_bfloat162*>(&packed[j]);
+                    const float a = __low2float(hh), b = __high2float(hh);
+                    s1[2 * j] = a; s1[2 * j + 1] = b;
+                    s2[2 * j] = a * a; s2[2 * j + 1] = b * b;
+                }
+                const float cs = warp_transpose_reduce32(s1, lane);
+                const float cq = warp_transpose_reduce32(s2, lane);
+                atomicAdd(&s_stats[0][cb + lane], cs);
+                atomicAdd(&s_stats[1][cb + lane], cq);
+            }
         }
     }
     if (stats != nullptr) {
@@ -227,21 +259,24 @@ __global__ void __launch_bounds__(256) conv1_direct_fwd_kernel(const float* __re
 }
 
 // wgrad of the first layer: dW[co][ci][kh][kw] = sum_q dZ[q][co] * x[q + (kh-1, kw-1)][ci]
-// Persistent blocks (grid-stride over 16x16 tiles), register accumulation, one atomic flush per block.
+// Persistent blocks (grid-stride over 16x16 tiles). Thread = (group of 4 output channels, pixel lane); it keeps a
+// 4 x 18 register tile, so one shared-memory read of dZ (8 B) and 18 broadcast reads of x feed 72 FMAs.
 __global__ void __launch_bounds__(256) conv1_direct_wgrad_kernel(const float* __restrict__ x,             // [B][2][H][W]
                                                                  const __nv_bfloat16* __restrict__ dz,   // [B][H][W][64]
                                                                  float* __restrict__ dw,                  // [64][2][3][3]
                                                                  int H, int W, int num_tiles) {
     __shared__ float s_x[2][C1_TILE + 2][C1_TILE + 2];
-    __shared__ __nv_bfloat16 s_dz[C1_TILE * C1_TILE][C1_COUT + 8];  // +8: rows 144 B apart
+    __shared__ __align__(16) __nv_bfloat16 s_dz[C1_TILE * C1_TILE][C1_COUT + 8];  // +8: rows 144 B apart
     const int tid = threadIdx.x;
-    const int co = tid & 63;
-    const int sub = tid >> 6;  // 4 pixel subsets of 64 pixels
+    const int cg = tid & 15;   // channels 4*cg .. 4*cg+3
+    const int pl = tid >> 4;   // pixel lane: pixels pl, pl+16, ...
     const int tiles_w = W / C1_TILE;
     const int tiles_hw = tiles_w * (H / C1_TILE);
-    float acc[18];
+    float acc[4][18];
 #pragma unroll
-    for (int k = 0; k < 18; ++k) acc[k] = 0.f;
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int k = 0; k < 18; ++k) acc[j][k] = 0.f;
 
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int img = tile / tiles_hw;
@@ -265,17 +300,37 @@ __global__ void __launch_bounds__(256) conv1_direct_wgrad_kernel(const float* __
             *reinterpret_cast<uint4*>(&s_dz[p][c8 * 8]) = u;
         }
         __syncthreads();
-        for (int p = sub * 64; p < sub * 64 + 64; ++p) {
-            const float g = __bfloat162float(s_dz[p][co]);
+#pragma unroll 2
+        for (int p = pl; p < C1_TILE * C1_TILE; p += 16) {
+            const uint2 gu = *reinterpret_cast<const uint2*>(&s_dz[p][cg * 4]);
+            const __nv_bfloat162 g01 = *reinterpret_cast<const __nv_bfloat162*>(&gu.x);
+            const __nv_bfloat162 g23 = *reinterpret_cast<const __nv_bfloat162*>(&gu.y);
+            const float g[4] = {__low2float(g01), __high2float(g01), __low2float(g23), __high2float(g23)};
             const int ph = p / C1_TILE, pw = p % C1_TILE;
 #pragma unroll
             for (int ci = 0; ci < 2; ++ci)
 #pragma unroll
-                for (int t = 0; t < 9; ++t) acc[ci * 9 + t] = fmaf(g, s_x[ci][ph + t / 3][pw + t % 3], acc[ci * 9 + t]);
+                for (int t = 0; t < 9; ++t) {
+                    const float xv = s_x[ci][ph + t / 3][pw + t % 3];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) acc[j][ci * 9 + t] = fmaf(g[j], xv, acc[j][ci * 9 + t]);
+                }
         }
     }
+    // reduce over the 16 pixel lanes: lanes of a warp hold pl in {2w, 2w+1} -> shuffle once, then shared atomics
+    __shared__ float s_acc[C1_COUT * 18];
+    for (int i = tid; i < C1_COUT * 18; i += 256) s_acc[i] = 0.f;
+    __syncthreads();
 #pragma unroll
-    for (int k = 0; k < 18; ++k) atomicAdd(dw + co * 18 + k, acc[k]);
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int k = 0; k < 18; ++k) {
+            float v = acc[j][k];
+            v += __shfl_xor_sync(0xffffffffu, v, 16);
+            if ((tid & 16) == 0) atomicAdd(&s_acc[(cg * 4 + j) * 18 + k], v);
+        }
+    __syncthreads();
+    for (int i = tid; i < C1_COUT * 18; i += 256) atomicAdd(dw + i, s_acc[i]);
 }
 
 // ------------------------------------------------------------------------------------------------
