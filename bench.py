@@ -21,6 +21,10 @@ import subprocess
 import sys
 import time
 
+# keep stdout to the single JSON line: NCCL prints a version banner there when NCCL_DEBUG=VERSION/INFO is inherited
+if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", ""):
+    os.environ["NCCL_DEBUG"] = "WARN"
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)

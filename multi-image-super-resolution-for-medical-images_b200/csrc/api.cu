@@ -364,6 +364,13 @@ int run_conv3(int mode, const void* a, int a_stride, int a_coff, int Ca, const v
     args.col_shift = col_shift;
     args.stats = stats;
     args.cout_t = cout_t;
+    args.epi_debug = getenv("B200SR_EPI_DEBUG") ? atoi(getenv("B200SR_EPI_DEBUG")) : 0;
+    {
+        const int nh = block_n / (block_n < 128 ? block_n : 128);
+        const int slots = taps * args.cin_chunks * nh;
+        const int sb = block_n == 64 ? C3Cfg<64>::SB : C3Cfg<128>::SB;
+        args.b_resident = (slots <= sb && getenv("B200SR_NO_BRESIDENT") == nullptr) ? 1 : 0;
+    }
     // persistent grid: one CTA per SM, rounded down so that a CTA stays on one column block (register statistics)
     int grid = num_sms();
     grid -= grid % args.n_tiles;

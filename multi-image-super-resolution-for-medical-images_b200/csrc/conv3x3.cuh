@@ -33,6 +33,8 @@ struct Conv3Args {
     int out_c_off;
     int stats_replicas;
     int cout_t;        // MODE 1: channels per (i,j) sub-pixel (n_total = 4 * cout_t); modulus of the affine vectors
+    int epi_debug;     // bring-up/perf experiments (B200SR_EPI_DEBUG bit mask); 0 in production
+    int b_resident;    // the CTA's whole weight block fits the B ring: load it once, keep it for all tiles
     __nv_bfloat16* out;
     const float* col_scale;  // nullable, [n_total]
     const float* col_shift;  // nullable, [n_total]
@@ -50,11 +52,13 @@ struct C3Cfg {
     static constexpr int BN_SLOT = BLOCK_N < 128 ? BLOCK_N : 128;  // columns per weight slot = UMMA N
     static constexpr int NH = BLOCK_N / BN_SLOT;
     static constexpr int B_SLOT = BN_SLOT * 128;
-    static constexpr int SA = BLOCK_N == 64 ? 4 : 3;
-    static constexpr int SB = BLOCK_N == 64 ? 12 : 8;
-    static constexpr int STAGING = 2 * C3_OUT_STAGE;  // double-buffered output tile (128 pixels x 64 ch) for TMA stores
+    static constexpr int SA = 3;
+    static constexpr int SB = BLOCK_N == 64 ? 18 : 8;   // 18 x 8 KB holds every weight of a Cout=64 layer (K <= 1152)
+    static constexpr int NBUF = BLOCK_N == 64 ? 1 : 2;  // output staging buffers (128 pixels x 64 ch) for TMA stores
+    static constexpr int STAGING = NBUF * C3_OUT_STAGE;
     static constexpr int RING_BYTES = SA * C3_A_SLOT + SB * B_SLOT;
-    static constexpr int SMEM_BYTES = RING_BYTES + STAGING + 1024 /* barriers */ + 1024 /* alignment slack */;
+    static constexpr int SMEM_BYTES =
+        RING_BYTES + STAGING + 1024 /* barriers */ + 2048 /* affine vectors */ + 1024 /* alignment slack */;
 };
 
 // MODE 0: Conv2d 3x3 forward / dgrad (three haloed boxes per channel chunk, three vertical taps per box)
@@ -83,6 +87,9 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_kernel(const __grid_con
     uint64_t* acc_full = b_empty + SB;
     uint64_t* acc_empty = acc_full + 2;
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(acc_empty + 2);
+    // per-column affine (eval-mode folded BatchNorm scale/shift, ConvT bias) of this CTA's column block, staged once
+    float* s_scale = reinterpret_cast<float*>(smem + Cfg::RING_BYTES + Cfg::STAGING + 1024);
+    float* s_shift = s_scale + 256;
 
     const int warp = threadIdx.x >> 5;
     const uint32_t lane = lane_id();
@@ -110,6 +117,15 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_kernel(const __grid_con
     if (warp == 2) {
         tmem_alloc(tmem_ptr_smem, 2 * BLOCK_N);
         tmem_relinquish();
+    }
+    if (warp >= 4 && blockIdx.x < args.num_tiles) {
+        // the tile schedule keeps a CTA on one column block, so its affine vectors can be staged once
+        const int n0 = (static_cast<int>(blockIdx.x) % args.n_tiles) * BLOCK_N;
+        for (int i = threadIdx.x - 128; i < BLOCK_N; i += 128) {
+            const int c = MODE == 1 ? (n0 + i) % args.cout_t : n0 + i;
+            s_scale[i] = args.col_scale ? __ldg(args.col_scale + c) : 1.f;
+            s_shift[i] = args.col_shift ? __ldg(args.col_shift + c) : 0.f;
+        }
     }
     tc_fence_before();
     __syncthreads();
@@ -150,6 +166,16 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_kernel(const __grid_con
                             const int kcol = (MODE == 0 ? (dh * 3 + dw) : dw) * args.C + c * 64;
 #pragma unroll
                             for (int nh = 0; nh < NH; ++nh) {
+                                if (args.b_resident) {
+                                    // slot = position in the (fixed) per-tile consumption order; loaded once
+                                    if (tile == static_cast<int>(blockIdx.x)) {
+                                        mbar_arrive_expect_tx(&b_full[sb], Cfg::B_SLOT);
+                                        tma_load_2d(&map_b, &b_full[sb], ring_b + sb * Cfg::B_SLOT, kcol,
+                                                    n0 + nh * BN_SLOT);
+                                        ++sb;
+                                    }
+                                    continue;
+                                }
                                 mbar_wait(&b_empty[sb], pb ^ 1);
                                 mbar_arrive_expect_tx(&b_full[sb], Cfg::B_SLOT);
                                 tma_load_2d(&map_b, &b_full[sb], ring_b + sb * Cfg::B_SLOT, kcol, n0 + nh * BN_SLOT);
@@ -173,6 +199,8 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_kernel(const __grid_con
                 mbar_wait(&acc_empty[as], pacc ^ 1);
                 tc_fence_after();
                 const uint32_t d_base = tmem_base + as * BLOCK_N;
+                const bool first_tile = tile == static_cast<int>(blockIdx.x);
+                if (args.b_resident) sb = 0;
                 for (int c = 0; c < chunks; ++c) {
                     for (int dw = 0; dw < NG; ++dw) {
                         mbar_wait(&a_full[sa], pa);
@@ -181,17 +209,21 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_kernel(const __grid_con
                             const uint64_t da = umma_smem_desc_sw128(a_addr + dh * 1024, 0, 1024);
 #pragma unroll
                             for (int nh = 0; nh < NH; ++nh) {
-                                mbar_wait(&b_full[sb], pb);
+                                if (!args.b_resident || first_tile) mbar_wait(&b_full[sb], pb);
                                 tc_fence_after();
                                 const uint64_t db = umma_smem_desc_sw128(smem_u32(ring_b + sb * Cfg::B_SLOT), 0, 1024);
                                 const uint32_t first = (c | dw | dh) == 0 ? 0u : 1u;
 #pragma unroll
                                 for (int k = 0; k < 4; ++k)
                                     umma_bf16(d_base + nh * BN_SLOT, da + 2 * k, db + 2 * k, idesc, first | k);
-                                umma_commit(&b_empty[sb]);
-                                if (++sb == SB) {
-                                    sb = 0;
-                                    pb ^= 1;
+                                if (args.b_resident) {
+                                    ++sb;
+                                } else {
+                                    umma_commit(&b_empty[sb]);
+                                    if (++sb == SB) {
+                                        sb = 0;
+                                        pb ^= 1;
+                                    }
                                 }
                             }
                         }
@@ -242,22 +274,34 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_kernel(const __grid_con
 #pragma unroll
             for (int grp = 0; grp < BLOCK_N / 64; ++grp) {
                 uint8_t* stage = out_stage + sbuf * C3_OUT_STAGE;
+                if (Cfg::NBUF == 1) {
+                    // single staging buffer: the previous store must have finished reading it before it is rewritten
+                    if (issuer) tma_store_wait_read<0>();
+                    named_bar_sync(2, 128);
+                }
 #pragma unroll
                 for (int half = 0; half < 2; ++half) {
                     const int chunk = grp * 2 + half;
                     uint32_t raw[32];
-                    tmem_ld32(t_addr + chunk * 32, raw);
-                    tmem_ld_wait();
+                    if (args.epi_debug & 64) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) raw[i] = i + lane;
+                    } else {
+                        tmem_ld32(t_addr + chunk * 32, raw);
+                        tmem_ld_wait();
+                    }
                     float v[32];
 #pragma unroll
                     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
-                    if (affine) {
-                        const int c0 = MODE == 1 ? (n0 + chunk * 32) % args.cout_t : n0 + chunk * 32;
+                    if (affine && !(args.epi_debug & 16)) {
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) {
-                            const float sc = args.col_scale ? __ldg(args.col_scale + c0 + i) : 1.f;
-                            const float sh = args.col_shift ? __ldg(args.col_shift + c0 + i) : 0.f;
-                            v[i] = fmaf(v[i], sc, sh);
+                        for (int i = 0; i < 32; i += 4) {
+                            const float4 sc = *reinterpret_cast<const float4*>(s_scale + chunk * 32 + i);
+                            const float4 sh = *reinterpret_cast<const float4*>(s_shift + chunk * 32 + i);
+                            v[i] = fmaf(v[i], sc.x, sh.x);
+                            v[i + 1] = fmaf(v[i + 1], sc.y, sh.y);
+                            v[i + 2] = fmaf(v[i + 2], sc.z, sh.z);
+                            v[i + 3] = fmaf(v[i + 3], sc.w, sh.w);
                         }
                     }
                     if (args.relu) {
@@ -270,6 +314,7 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_kernel(const __grid_con
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         const uint32_t j = static_cast<uint32_t>(half * 4 + i);
+                        if (args.epi_debug & 32) continue;
                         *reinterpret_cast<uint4*>(stage + row_off + ((j ^ row_xor) << 4)) =
                             make_uint4(packed[4 * i], packed[4 * i + 1], packed[4 * i + 2], packed[4 * i + 3]);
                     }
@@ -291,10 +336,10 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_kernel(const __grid_con
                 }
                 // make the generic-proxy writes visible to the TMA engine, make sure the OTHER buffer's previous
                 // store has finished reading shared memory (it is the next one to be overwritten), then store
-                fence_proxy_async_smem();
-                if (issuer) tma_store_wait_read<0>();
-                named_bar_sync(1, 128);
-                if (issuer) {
+                if (!(args.epi_debug & 1)) fence_proxy_async_smem();
+                if (Cfg::NBUF == 2 && issuer && !(args.epi_debug & 4)) tma_store_wait_read<0>();
+                if (!(args.epi_debug & 8)) named_bar_sync(1, 128);
+                if (issuer && !(args.epi_debug & 2)) {
                     const int col0 = n0 + grp * 64;
                     if (MODE == 1) {
                         const int ij = col0 / args.cout_t;
@@ -305,7 +350,7 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_kernel(const __grid_con
                     }
                     tma_store_commit();
                 }
-                sbuf ^= 1;
+                if (Cfg::NBUF == 2) sbuf ^= 1;
             }
             // all TMEM reads of this thread have completed (tmem_ld_wait above): hand the accumulator back
             tc_fence_before();

@@ -589,7 +589,7 @@ __device__ __forceinline__ F8 unpack8(const uint4& u) {
 
 constexpr int BNB_UNROLL = 4;
 
-__global__ void __launch_bounds__(256) bn_bwd_reduce_fast_kernel(const __nv_bfloat16* __restrict__ dy, int dy_stride,
+__global__ void __launch_bounds__(256, 3) bn_bwd_reduce_fast_kernel(const __nv_bfloat16* __restrict__ dy, int dy_stride,
                                                                  int dy_coff, const __nv_bfloat16* __restrict__ z,
                                                                  int C, const float* __restrict__ scale,
                                                                  const float* __restrict__ shift,
@@ -646,7 +646,7 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_fast_kernel(const __nv_bflo
     }
 }
 
-__global__ void __launch_bounds__(256) bn_bwd_apply_fast_kernel(const __nv_bfloat16* __restrict__ dy, int dy_stride,
+__global__ void __launch_bounds__(256, 3) bn_bwd_apply_fast_kernel(const __nv_bfloat16* __restrict__ dy, int dy_stride,
                                                                 int dy_coff, const __nv_bfloat16* __restrict__ z, int C,
                                                                 const float* __restrict__ scale,
                                                                 const float* __restrict__ shift,

@@ -335,6 +335,32 @@ def layout_casts(B=2, C=24, H=8, W=12, seed=14):
     return {"fwd_exact": float((nchw(o) - bf(x)).abs().max()), "back_exact": float((back - bf(x)).abs().max())}
 
 
+def conv_determinism(B=6, H=64, W=64, Cin=128, Cout=256, seed=21):
+    """The persistent kernels have no data-dependent scheduling in their outputs: two runs must agree bit for bit
+    (forward / dgrad outputs) — a race in the smem rings or the TMEM double buffer would show up here."""
+    _setup()
+    x = nhwc(bf(rnd(B, Cin, H, W, seed=seed)))
+    w = bf(rnd(Cout, Cin, 3, 3, seed=seed + 1, scale=(9 * Cin) ** -0.5))
+    wp = pack(w, 0, Cout, Cin)
+    outs = []
+    for _ in range(3):
+        ob = torch.zeros(B, H, W, Cout, dtype=torch.bfloat16, device=DEV)
+        call("b200sr_conv3x3_fwd", ptr(x), Cin, 0, Cin, ptr(wp), Cout, B, H, W, ptr(ob), Cout, 0, None, None, 0, None, 0,
+             st())
+        torch.cuda.synchronize()
+        outs.append(ob)
+    up = bf(rnd(Cout, Cin // 2, 2, 2, seed=seed + 2, scale=Cout ** -0.5))   # ConvT(Cout -> Cin/2)
+    wpt = pack(up, 2, Cin // 2, Cout)
+    touts = []
+    for _ in range(2):
+        tb = torch.zeros(B, 2 * H, 2 * W, Cin // 2, dtype=torch.bfloat16, device=DEV)
+        call("b200sr_convT2x2_fwd", ptr(outs[0]), Cout, 0, Cout, ptr(wpt), Cin // 2, None, B, H, W, ptr(tb), Cin // 2, 0, st())
+        torch.cuda.synchronize()
+        touts.append(tb)
+    return {"conv_bitwise": float((outs[0].float() - outs[1].float()).abs().max() + (outs[0].float() - outs[2].float()).abs().max()),
+            "convT_bitwise": float((touts[0].float() - touts[1].float()).abs().max())}
+
+
 # name -> (function, kwargs, {metric: tolerance})
 BF16 = 1e-2
 CHECKS = {
@@ -343,6 +369,7 @@ CHECKS = {
                              {"out": BF16, "slot_untouched": 0.0}),
     "conv3x3_fwd_n256": (conv3x3_fwd, dict(Cin=256, Cout=256, B=3, H=16, W=16), {"out": BF16, "stats_sq": 1e-3}),
     "conv3x3_fwd_deep": (conv3x3_fwd, dict(Cin=1024, Cout=512, B=1, H=16, W=16, affine=True), {"out": BF16}),
+    "conv_determinism": (conv_determinism, {}, {"conv_bitwise": 0.0, "convT_bitwise": 0.0}),
     "conv3x3_dgrad": (conv3x3_dgrad, {}, {"dx": BF16, "colsum": 1e-3}),
     "conv3x3_dgrad_wide": (conv3x3_dgrad, dict(Cin=256, Cout=64, B=1, H=32, W=16), {"dx": BF16}),
     # persistent schedule: more tiles than SMs, one and several column blocks per row block
