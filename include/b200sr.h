@@ -129,6 +129,22 @@ int b200sr_bn_finalize(const float* stats, int replicas, int C, double count, co
 int b200sr_bnrelu_apply(const void* z, int C, const float* scale, const float* shift, void* act,
                         int act_pix_stride, int act_c_off, void* pooled, int B, int H, int W, void* stream);
 
+/* b200sr_bn_finalize + b200sr_bnrelu_apply in ONE launch (train-mode nn.BatchNorm2d + ReLU (+ MaxPool2d), unet_model.py:
+ * 28-32,52-61): every thread derives the scale/shift of its channels from the statistic replicas; scale/shift/
+ * save_mean/save_invstd are published for the backward pass and the running statistics are updated. C/8 must
+ * divide 256 or be a multiple of 256. */
+int b200sr_bn_train_apply(const void* z, int C, const float* stats, int replicas, double count, const float* gamma,
+                          const float* beta, const float* conv_bias, float eps, float momentum, float* scale,
+                          float* shift, float* save_mean, float* save_invstd, float* running_mean, float* running_var,
+                          void* act, int act_pix_stride, int act_c_off, void* pooled, int B, int H, int W,
+                          void* stream);
+
+/* b200sr_bn_bwd_finalize + b200sr_bn_bwd_apply in ONE launch (C/8 must divide 256). */
+int b200sr_bn_bwd_apply_fused(const void* dy, int dy_pix_stride, int dy_c_off, const void* z, int C,
+                              const float* scale, const float* shift, const float* mean, const float* invstd,
+                              const float* sums, int replicas, double count, float* dgamma, float* dbeta, void* dz,
+                              int64_t npix, void* stream);
+
 /* nn.MaxPool2d(2,2) forward / backward (unet_model.py:52,55,58,61). Backward adds the skip-connection
  * gradient (dskip may be NULL) and routes to the first maximum in row-major window order like ATen. */
 int b200sr_maxpool2x2_fwd(const void* in, int in_pix_stride, int in_c_off, int C, void* out, int B, int H,

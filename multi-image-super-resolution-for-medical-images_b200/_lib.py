@@ -36,6 +36,10 @@ _SIGNATURES = {
     "b200sr_conv1_wgrad": [_P, _P, _P, c_int, c_int, c_int, _P],
     "b200sr_bn_finalize": [_P, c_int, c_int, c_double, _P, _P, _P, c_float, c_float, _P, _P, _P, _P, _P, _P, _P],
     "b200sr_bnrelu_apply": [_P, c_int, _P, _P, _P, c_int, c_int, _P, c_int, c_int, c_int, _P],
+    "b200sr_bn_train_apply": [_P, c_int, _P, c_int, c_double, _P, _P, _P, c_float, c_float, _P, _P, _P, _P, _P, _P, _P,
+                              c_int, c_int, _P, c_int, c_int, c_int, _P],
+    "b200sr_bn_bwd_apply_fused": [_P, c_int, c_int, _P, c_int, _P, _P, _P, _P, _P, c_int, c_double, _P, _P, _P, c_int64,
+                                  _P],
     "b200sr_maxpool2x2_fwd": [_P, c_int, c_int, c_int, _P, c_int, c_int, c_int, _P],
     "b200sr_maxpool2x2_bwd": [_P, c_int, c_int, _P, _P, c_int, c_int, c_int, _P, c_int, c_int, c_int, _P],
     "b200sr_bn_bwd_reduce": [_P, c_int, c_int, _P, c_int, _P, _P, _P, _P, _P, c_int, c_int64, _P],
@@ -103,6 +107,11 @@ def _cost(name, a):
     if name == "b200sr_bnrelu_apply":
         n = a[8] * a[9] * a[10] * a[1] * 2.0
         return 0.0, n * (2.25 if a[7] else 2.0)
+    if name == "b200sr_bn_train_apply":
+        n = a[20] * a[21] * a[22] * a[1] * 2.0
+        return 0.0, n * (2.25 if a[19] else 2.0)
+    if name == "b200sr_bn_bwd_apply_fused":
+        return 0.0, a[15] * a[4] * 2.0 * 3
     if name == "b200sr_maxpool2x2_fwd":
         return 0.0, a[5] * a[6] * a[7] * a[3] * 2.0 * 1.25
     if name == "b200sr_maxpool2x2_bwd":

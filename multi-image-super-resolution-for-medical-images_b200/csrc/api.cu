@@ -711,6 +711,51 @@ int b200sr_bnrelu_apply(const void* z, int C, const float* scale, const float* s
     return check_launch("bnrelu_apply_kernel");
 }
 
+int b200sr_bn_train_apply(const void* z, int C, const float* stats, int replicas, double count, const float* gamma,
+                           const float* beta, const float* conv_bias, float eps, float momentum, float* scale,
+                           float* shift, float* save_mean, float* save_invstd, float* running_mean, float* running_var,
+                           void* act, int act_pix_stride, int act_c_off, void* pooled, int B, int H, int W,
+                           void* stream) {
+    B2_CHECK_ARG(z && stats && gamma && beta && scale && shift && save_mean && save_invstd && act);
+    B2_CHECK_ARG(replicas > 0 && count > 1.0 && (running_mean == nullptr) == (running_var == nullptr));
+    B2_CHECK_ARG(C % 8 == 0 && act_pix_stride % 8 == 0 && act_c_off % 8 == 0 && H % 2 == 0 && W % 2 == 0);
+    B2_CHECK_ARG(aligned16(z) && aligned16(act) && (pooled == nullptr || aligned16(pooled)) && aligned16(stats));
+    const int c8n = C / 8;
+    const long long total = static_cast<long long>(B) * (H / 2) * (W / 2) * c8n;
+    // a thread must stay on the same 8 channels across its grid-stride loop: grid * 256 % c8n == 0, and the first c8n
+    // threads of the grid publish the per-channel results, so the grid must hold at least c8n threads
+    B2_CHECK_ARG(c8n <= 256 ? 256 % c8n == 0 : c8n % 256 == 0);
+    int grid = grid_for(total, 256);
+    if (c8n > 256) {
+        const int m = c8n / 256;
+        grid = (grid + m - 1) / m * m;
+    }
+    bn_train_apply_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16*>(z), C, stats, replicas, static_cast<float>(count), gamma, beta, conv_bias, eps,
+        momentum, scale, shift, save_mean, save_invstd, running_mean, running_var, static_cast<__nv_bfloat16*>(act),
+        act_pix_stride, act_c_off, static_cast<__nv_bfloat16*>(pooled), H, W, total);
+    return check_launch("bn_train_apply_kernel");
+}
+
+int b200sr_bn_bwd_apply_fused(const void* dy, int dy_pix_stride, int dy_c_off, const void* z, int C, const float* scale,
+                              const float* shift, const float* mean, const float* invstd, const float* sums,
+                              int replicas, double count, float* dgamma, float* dbeta, void* dz, int64_t npix,
+                              void* stream) {
+    B2_CHECK_ARG(dy && z && scale && shift && mean && invstd && sums && dgamma && dbeta && dz);
+    B2_CHECK_ARG(C % 8 == 0 && dy_pix_stride % 8 == 0 && dy_c_off % 8 == 0 && npix > 0 && replicas > 0 && count > 0);
+    B2_CHECK_ARG(aligned16(dy) && aligned16(z) && aligned16(dz) && aligned16(sums));
+    const int CV = C / 8;
+    B2_CHECK_ARG(CV <= 256 && 256 % CV == 0);
+    const int PB = 256 / CV;
+    long long blocks = (npix + static_cast<long long>(PB) * BNB_UNROLL - 1) / (static_cast<long long>(PB) * BNB_UNROLL);
+    if (blocks > num_sms() * 8) blocks = num_sms() * 8;
+    bn_bwd_apply_fused_kernel<<<static_cast<int>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16*>(dy), dy_pix_stride, dy_c_off, static_cast<const __nv_bfloat16*>(z), C, scale,
+        shift, mean, invstd, sums, replicas, static_cast<float>(count), dgamma, dbeta, static_cast<__nv_bfloat16*>(dz),
+        npix);
+    return check_launch("bn_bwd_apply_fused_kernel");
+}
+
 int b200sr_maxpool2x2_fwd(const void* in, int in_pix_stride, int in_c_off, int C, void* out, int B, int H, int W,
                           void* stream) {
     B2_CHECK_ARG(in && out && C % 8 == 0 && in_pix_stride % 8 == 0 && in_c_off % 8 == 0 && H % 2 == 0 && W % 2 == 0);
@@ -835,6 +880,23 @@ int b200sr_mse_ssim(const float* pred, const float* target, float* grad, double*
     a.g_ssim = static_cast<float>(-static_cast<double>(w_ssim) /
                                   (static_cast<double>(B) * (H - K + 1) * static_cast<double>(W - K + 1)));
     const int grid = B * ((H + LS_T - 1) / LS_T) * ((W + LS_T - 1) / LS_T);
+    if ((K == 11 || K == 7) && getenv("B200SR_SSIM_GENERIC") == nullptr) {
+        static bool configured_fast = false;
+        if (!configured_fast) {
+            cudaError_t e1 = cudaFuncSetAttribute(mse_ssim_fast_kernel<11>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                  LsFast<11>::SMEM_BYTES);
+            cudaError_t e2 = cudaFuncSetAttribute(mse_ssim_fast_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                  LsFast<7>::SMEM_BYTES);
+            if (e1 != cudaSuccess || e2 != cudaSuccess)
+                return fail(B200SR_ECUDA, "mse_ssim_fast smem attribute failed");
+            configured_fast = true;
+        }
+        if (K == 11)
+            mse_ssim_fast_kernel<11><<<grid, 256, LsFast<11>::SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(a);
+        else
+            mse_ssim_fast_kernel<7><<<grid, 256, LsFast<7>::SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(a);
+        return check_launch("mse_ssim_fast_kernel");
+    }
     mse_ssim_kernel<<<grid, 256, LS_SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(a);
     return check_launch("mse_ssim_kernel");
 }

@@ -352,10 +352,11 @@ __global__ void bn_finalize_kernel(const float* __restrict__ stats, int replicas
         s += stats[(static_cast<size_t>(r) * 2) * C + c];
         q += stats[(static_cast<size_t>(r) * 2 + 1) * C + c];
     }
-    const double mean = s / count;
-    double var = q / count - mean * mean;
+    const double inv_count = 1.0 / static_cast<double>(count);
+    const double mean = s * inv_count;
+    double var = q * inv_count - mean * mean;
     if (var < 0.0) var = 0.0;
-    const float invstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+    const float invstd = 1.0f / sqrtf(static_cast<float>(var) + eps);
     const float sc = gamma[c] * invstd;
     scale[c] = sc;
     shift[c] = beta[c] - static_cast<float>(mean) * sc;
@@ -426,6 +427,89 @@ __global__ void __launch_bounds__(256) bnrelu_apply_kernel(const __nv_bfloat16* 
                 for (int k = 0; k < 8; ++k) {
                     v.v[k] = fmaxf(fmaf(v.v[k], sc.v[k], sh.v[k]), 0.f);
                     // pool over the values as stored (bf16), like MaxPool2d reading the activation tensor
+                    mx.v[k] = fmaxf(mx.v[k], bf16_round(v.v[k]));
+                }
+                st_bf16x8(act + pix * act_stride + act_coff + c, v);
+            }
+        if (pooled != nullptr) st_bf16x8(pooled + ((static_cast<size_t>(img) * H2 + h2) * W2 + w2) * C + c, mx);
+    }
+}
+
+// Train-mode BatchNorm finalize fused into the apply pass (saves one tiny launch per layer on the critical path):
+// every thread derives scale/shift of its own 8 channels from the statistic replicas (double precision for
+// E[x^2]-E[x]^2, exactly like bn_finalize_kernel); block 0 additionally publishes scale/shift/mean/invstd for the
+// backward pass and updates the running statistics (unbiased variance, conv bias re-added to the mean).
+__global__ void __launch_bounds__(256, 4) bn_train_apply_kernel(
+    const __nv_bfloat16* __restrict__ z, int C, const float* __restrict__ stats, int replicas, float count,
+    const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ conv_bias, float eps,
+    float momentum, float* __restrict__ scale_out, float* __restrict__ shift_out, float* __restrict__ mean_out,
+    float* __restrict__ invstd_out, float* __restrict__ running_mean, float* __restrict__ running_var,
+    __nv_bfloat16* __restrict__ act, int act_stride, int act_coff, __nv_bfloat16* __restrict__ pooled, int H, int W,
+    long long total /* B*(H/2)*(W/2)*(C/8) */) {
+    const int c8n = C >> 3;
+    const int W2 = W >> 1, H2 = H >> 1;
+    const long long first = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    // grid-stride by a multiple of c8n keeps a thread on the same 8 channels (host guarantees stride % c8n == 0)
+    const int c = static_cast<int>(first % c8n) * 8;
+    F8 sc, sh;
+    {
+        double s[8], q[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s[k] = q[k] = 0.0;
+        for (int r = 0; r < replicas; ++r) {
+            const F8 a = ld_f32x8(stats + (static_cast<size_t>(r) * 2) * C + c);
+            const F8 b = ld_f32x8(stats + (static_cast<size_t>(r) * 2 + 1) * C + c);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                s[k] += a.v[k];
+                q[k] += b.v[k];
+            }
+        }
+        const F8 ga = ld_f32x8(gamma + c), be = ld_f32x8(beta + c);
+        const bool publish = first < c8n;  // the first c8n threads of the grid cover every channel once
+        const double inv_count = 1.0 / static_cast<double>(count);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            // E[x^2] - E[x]^2 in double (cancellation), the rest in fp32: same formula as bn_finalize_kernel
+            const double mean = s[k] * inv_count;
+            double var = q[k] * inv_count - mean * mean;
+            if (var < 0.0) var = 0.0;
+            const float invstd = 1.0f / sqrtf(static_cast<float>(var) + eps);
+            sc.v[k] = ga.v[k] * invstd;
+            sh.v[k] = be.v[k] - static_cast<float>(mean) * sc.v[k];
+            if (publish) {
+                scale_out[c + k] = sc.v[k];
+                shift_out[c + k] = sh.v[k];
+                mean_out[c + k] = static_cast<float>(mean);
+                invstd_out[c + k] = invstd;
+                if (running_mean != nullptr) {
+                    const float b = conv_bias ? conv_bias[c + k] : 0.f;
+                    const float unbiased = static_cast<float>(var * (count / (count - 1.0)));
+                    running_mean[c + k] = (1.f - momentum) * running_mean[c + k] + momentum * (static_cast<float>(mean) + b);
+                    running_var[c + k] = (1.f - momentum) * running_var[c + k] + momentum * unbiased;
+                }
+            }
+        }
+    }
+    for (long long idx = first; idx < total; idx += stride) {
+        long long r = idx / c8n;
+        const int w2 = static_cast<int>(r % W2);
+        r /= W2;
+        const int h2 = static_cast<int>(r % H2);
+        const int img = static_cast<int>(r / H2);
+        F8 mx;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) mx.v[k] = 0.f;  // post-ReLU values are >= 0
+#pragma unroll
+        for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+            for (int dx = 0; dx < 2; ++dx) {
+                const size_t pix = (static_cast<size_t>(img) * H + 2 * h2 + dy) * W + 2 * w2 + dx;
+                F8 v = ld_bf16x8(z + pix * C + c);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    v.v[k] = fmaxf(fmaf(v.v[k], sc.v[k], sh.v[k]), 0.f);
                     mx.v[k] = fmaxf(mx.v[k], bf16_round(v.v[k]));
                 }
                 st_bf16x8(act + pix * act_stride + act_coff + c, v);
@@ -668,6 +752,76 @@ __global__ void __launch_bounds__(256, 3) bn_bwd_apply_fast_kernel(const __nv_bf
             const float t = is.v[k] * k2.v[k] * sc.v[k];
             ka.v[k] = -t;
             kb.v[k] = mu.v[k] * t - sc.v[k] * k1.v[k];
+        }
+    }
+    const long long step = static_cast<long long>(gridDim.x) * PB;
+    for (long long p0 = static_cast<long long>(blockIdx.x) * PB + pl; p0 < npix; p0 += step * BNB_UNROLL) {
+        uint4 g[BNB_UNROLL], zz[BNB_UNROLL];
+#pragma unroll
+        for (int u = 0; u < BNB_UNROLL; ++u) {
+            const long long p = p0 + u * step;
+            if (p < npix) {
+                g[u] = ld_stream(dy + p * dy_stride + dy_coff + c);
+                zz[u] = ld_stream(z + p * C + c);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < BNB_UNROLL; ++u) {
+            const long long p = p0 + u * step;
+            if (p < npix) {
+                const F8 gf = unpack8(g[u]), zf = unpack8(zz[u]);
+                F8 o;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const float gm = fmaf(zf.v[k], sc.v[k], sh.v[k]) > 0.f ? gf.v[k] : 0.f;
+                    o.v[k] = fmaf(gm, sc.v[k], fmaf(zf.v[k], ka.v[k], kb.v[k]));
+                }
+                st_bf16x8(dz + p * C + c, o);
+            }
+        }
+    }
+}
+
+// BatchNorm backward apply with the finalize step folded in: a thread derives c1 = S1/N, c2 = S2/N of its own 8
+// channels from the replicas of the reduce pass; the first pixel lane of block 0 publishes dgamma / dbeta.
+__global__ void __launch_bounds__(256, 3) bn_bwd_apply_fused_kernel(
+    const __nv_bfloat16* __restrict__ dy, int dy_stride, int dy_coff, const __nv_bfloat16* __restrict__ z, int C,
+    const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ mean,
+    const float* __restrict__ invstd, const float* __restrict__ sums, int replicas, float count,
+    float* __restrict__ dgamma, float* __restrict__ dbeta, __nv_bfloat16* __restrict__ dz, long long npix) {
+    const int CV = C >> 3;
+    const int PB = 256 / CV;
+    const int cv = threadIdx.x % CV, pl = threadIdx.x / CV;
+    const int c = cv * 8;
+    const F8 sc = ld_f32x8(scale + c), sh = ld_f32x8(shift + c);
+    F8 ka, kb;  // dz = gm*scale + z*ka + kb
+    {
+        F8 s1, s2;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s1.v[k] = s2.v[k] = 0.f;
+        for (int r = 0; r < replicas; ++r) {
+            const F8 a = ld_f32x8(sums + (static_cast<size_t>(r) * 2) * C + c);
+            const F8 b = ld_f32x8(sums + (static_cast<size_t>(r) * 2 + 1) * C + c);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                s1.v[k] += a.v[k];
+                s2.v[k] += b.v[k];
+            }
+        }
+        if (blockIdx.x == 0 && pl == 0) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                dgamma[c + k] = s2.v[k];
+                dbeta[c + k] = s1.v[k];
+            }
+        }
+        const F8 mu = ld_f32x8(mean + c), is = ld_f32x8(invstd + c);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const float k1 = s1.v[k] / count, k2 = s2.v[k] / count;
+            const float t = is.v[k] * k2 * sc.v[k];
+            ka.v[k] = -t;
+            kb.v[k] = mu.v[k] * t - sc.v[k] * k1;
         }
     }
     const long long step = static_cast<long long>(gridDim.x) * PB;

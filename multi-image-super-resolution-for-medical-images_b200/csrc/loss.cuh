@@ -191,4 +191,222 @@ __global__ void __launch_bounds__(256) mse_ssim_kernel(const LossArgs a) {
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Register-blocked version for the two frozen window sizes (K = 11 Gaussian, K = 7 uniform). Same algorithm and
+// tile as above; every separable pass gives a thread a strip of consecutive outputs along the filter direction,
+// so each shared-memory value is loaded once per strip instead of once per tap (LDS per pixel 218 -> ~50; the
+// generic kernel was LDS-bound at ~180 GB/s algorithmic). Odd row pitches keep column-parallel accesses
+// conflict-free. After this the kernel is FMA-bound (~290 FMA per pixel incl. halo), not HBM-bound.
+// ------------------------------------------------------------------------------------------------
+template <int K>
+struct LsFast {
+    static constexpr int R = K - 1;
+    static constexpr int IT = LS_T + 2 * R;  // input tile edge
+    static constexpr int MT = LS_T + R;      // SSIM-map tile edge
+    static constexpr int PX = IT | 1;        // odd pitches
+    static constexpr int PM = MT | 1;
+    static constexpr int PT = LS_T + 1;
+    static constexpr int SMEM_FLOATS = 2 * IT * PX + 5 * IT * PM + 3 * MT * PM;
+    static constexpr int SMEM_BYTES = SMEM_FLOATS * 4;
+};
+
+template <int K>
+__global__ void __launch_bounds__(256, 2) mse_ssim_fast_kernel(const LossArgs a) {
+    using L = LsFast<K>;
+    constexpr int R = L::R, IT = L::IT, MT = L::MT, PX = L::PX, PM = L::PM, PT = L::PT;
+    extern __shared__ float ls_smem[];
+    float* s_x = ls_smem;             // [IT][PX]
+    float* s_y = s_x + IT * PX;       // [IT][PX]
+    float* s_h = s_y + IT * PX;       // 5 x [IT][PM]; later reused as 3 x [MT][PT]
+    float* s_g = s_h + 5 * IT * PM;   // 3 x [MT][PM]
+    float* s_hg = s_h;
+    __shared__ float s_red[2][8];
+
+    const int tid = threadIdx.x;
+    const int tiles_w = (a.W + LS_T - 1) / LS_T;
+    const int tiles_h = (a.H + LS_T - 1) / LS_T;
+    const int img = blockIdx.x / (tiles_w * tiles_h);
+    const int t_in = blockIdx.x % (tiles_w * tiles_h);
+    const int qh0 = (t_in / tiles_w) * LS_T, qw0 = (t_in % tiles_w) * LS_T;
+    const int ih0 = qh0 - R, iw0 = qw0 - R;
+    const float* px = a.pred + static_cast<size_t>(img) * a.H * a.W;
+    const float* py = a.target + static_cast<size_t>(img) * a.H * a.W;
+    const int MH = a.H - K + 1, MW = a.W - K + 1;  // valid map size
+    float w[K];
+#pragma unroll
+    for (int i = 0; i < K; ++i) w[i] = a.win[i];
+
+    for (int i = tid; i < IT * IT; i += 256) {
+        const int r = i / IT, c = i % IT;
+        const int hh = ih0 + r, ww = iw0 + c;
+        float vx = 0.f, vy = 0.f;
+        if (hh >= 0 && hh < a.H && ww >= 0 && ww < a.W) {
+            vx = __ldg(px + hh * a.W + ww);
+            vy = __ldg(py + hh * a.W + ww);
+        }
+        s_x[r * PX + c] = vx;
+        s_y[r * PX + c] = vy;
+    }
+    __syncthreads();
+
+    // ---- pass H: 5 moment images, strips of 6 outputs along a row; consecutive threads take consecutive rows ----
+    {
+        constexpr int SW = 6, NS = (MT + SW - 1) / SW;
+        for (int item = tid; item < IT * NS; item += 256) {
+            const int r = item % IT, b0 = (item / IT) * SW;
+            float xi[SW + R], yi[SW + R];
+#pragma unroll
+            for (int i = 0; i < SW + R; ++i) {
+                const int c = min(b0 + i, IT - 1);
+                xi[i] = s_x[r * PX + c];
+                yi[i] = s_y[r * PX + c];
+            }
+#pragma unroll
+            for (int o = 0; o < SW; ++o) {
+                float hx = 0.f, hy = 0.f, hxx = 0.f, hyy = 0.f, hxy = 0.f;
+#pragma unroll
+                for (int v = 0; v < K; ++v) {
+                    const float x = xi[o + v], y = yi[o + v], wx = w[v] * x, wy = w[v] * y;
+                    hx += wx;
+                    hy += wy;
+                    hxx = fmaf(wx, x, hxx);
+                    hyy = fmaf(wy, y, hyy);
+                    hxy = fmaf(wx, y, hxy);
+                }
+                if (b0 + o < MT) {
+                    float* d = s_h + r * PM + b0 + o;
+                    d[0 * IT * PM] = hx;
+                    d[1 * IT * PM] = hy;
+                    d[2 * IT * PM] = hxx;
+                    d[3 * IT * PM] = hyy;
+                    d[4 * IT * PM] = hxy;
+                }
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- pass V: vertical filter -> SSIM value + gradient coefficient maps; strips of 6 rows per column ----
+    float ssim_part = 0.f;
+    {
+        constexpr int SV = 6, NS = (MT + SV - 1) / SV;
+        for (int item = tid; item < MT * NS; item += 256) {
+            const int b = item % MT, ar0 = (item / MT) * SV;
+            float m[5][SV];
+#pragma unroll
+            for (int q = 0; q < 5; ++q) {
+                float val[SV + R];
+#pragma unroll
+                for (int i = 0; i < SV + R; ++i) val[i] = s_h[q * IT * PM + min(ar0 + i, IT - 1) * PM + b];
+#pragma unroll
+                for (int o = 0; o < SV; ++o) {
+                    float acc = 0.f;
+#pragma unroll
+                    for (int u = 0; u < K; ++u) acc = fmaf(w[u], val[o + u], acc);
+                    m[q][o] = acc;
+                }
+            }
+#pragma unroll
+            for (int o = 0; o < SV; ++o) {
+                const int ar = ar0 + o;
+                if (ar >= MT) break;
+                const int ph = qh0 - R + ar, pw = qw0 - R + b;
+                float gm = 0.f, gxx = 0.f, gxy = 0.f;
+                if (ph >= 0 && ph < MH && pw >= 0 && pw < MW) {
+                    const float mx = m[0][o], my = m[1][o], mxx = m[2][o], myy = m[3][o], mxy = m[4][o];
+                    const float cn = a.cov_norm;
+                    const float sxx = cn * (mxx - mx * mx), syy = cn * (myy - my * my), sxy = cn * (mxy - mx * my);
+                    const float A1 = 2.f * mx * my + a.C1, A2 = 2.f * sxy + a.C2;
+                    const float B1 = mx * mx + my * my + a.C1, B2 = sxx + syy + a.C2;
+                    const float inv = 1.f / (B1 * B2);
+                    const float S = A1 * A2 * inv;
+                    const float dS_dsxy = 2.f * A1 * inv;
+                    const float dS_dsxx = -S / B2;
+                    gxx = cn * dS_dsxx;
+                    gxy = cn * dS_dsxy;
+                    gm = 2.f * my * A2 * inv - 2.f * mx * S / B1 - cn * my * dS_dsxy - 2.f * cn * mx * dS_dsxx;
+                    if (ar >= R && b >= R) ssim_part += S;  // map pixels owned by this block
+                }
+                s_g[0 * MT * PM + ar * PM + b] = gm;
+                s_g[1 * MT * PM + ar * PM + b] = gxx;
+                s_g[2 * MT * PM + ar * PM + b] = gxy;
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- pass H2: full correlation of the coefficient maps along rows, strips of 8 outputs ----
+    {
+        constexpr int SW = 8, NS = LS_T / SW;
+        for (int item = tid; item < MT * NS; item += 256) {
+            const int ar = item % MT, j0 = (item / MT) * SW;
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+                float val[SW + R];
+#pragma unroll
+                for (int i = 0; i < SW + R; ++i) val[i] = s_g[q * MT * PM + ar * PM + j0 + i];
+#pragma unroll
+                for (int o = 0; o < SW; ++o) {
+                    float acc = 0.f;
+#pragma unroll
+                    for (int t = 0; t <= R; ++t) acc = fmaf(w[R - t], val[o + t], acc);
+                    s_hg[q * MT * PT + ar * PT + j0 + o] = acc;
+                }
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- pass V2: along columns, strips of 8 rows, then combine with the MSE term ----
+    float mse_part = 0.f;
+    {
+        constexpr int SV = 8, NS = LS_T / SV;
+        for (int item = tid; item < LS_T * NS; item += 256) {
+            const int j = item % LS_T, r0 = (item / LS_T) * SV;
+            float v3[3][SV];
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+                float val[SV + R];
+#pragma unroll
+                for (int i = 0; i < SV + R; ++i) val[i] = s_hg[q * MT * PT + (r0 + i) * PT + j];
+#pragma unroll
+                for (int o = 0; o < SV; ++o) {
+                    float acc = 0.f;
+#pragma unroll
+                    for (int t = 0; t <= R; ++t) acc = fmaf(w[R - t], val[o + t], acc);
+                    v3[q][o] = acc;
+                }
+            }
+#pragma unroll
+            for (int o = 0; o < SV; ++o) {
+                const int r = r0 + o;
+                const int qh = qh0 + r, qw = qw0 + j;
+                if (qh >= a.H || qw >= a.W) continue;
+                const float x = s_x[(r + R) * PX + j + R], y = s_y[(r + R) * PX + j + R];
+                const float d = x - y;
+                mse_part = fmaf(d, d, mse_part);
+                if (a.grad != nullptr)
+                    a.grad[(static_cast<size_t>(img) * a.H + qh) * a.W + qw] =
+                        a.g_mse * d + a.g_ssim * (v3[0][o] + 2.f * x * v3[1][o] + y * v3[2][o]);
+            }
+        }
+    }
+
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+        mse_part += __shfl_xor_sync(0xffffffffu, mse_part, o);
+        ssim_part += __shfl_xor_sync(0xffffffffu, ssim_part, o);
+    }
+    if ((tid & 31) == 0) {
+        s_red[0][tid >> 5] = mse_part;
+        s_red[1][tid >> 5] = ssim_part;
+    }
+    __syncthreads();
+    if (tid < 2) {
+        double acc = 0.0;
+        for (int wi = 0; wi < 8; ++wi) acc += s_red[tid][wi];
+        atomicAdd(a.sums + tid, acc);
+    }
+}
+
 }  // namespace b200sr

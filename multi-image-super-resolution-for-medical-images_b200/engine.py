@@ -19,7 +19,7 @@ import torch
 from . import _lib
 from ._lib import call, ptr
 
-STATS_REPLICAS = 16
+STATS_REPLICAS = 4   # statistics are pre-reduced per CTA in registers, so few replicas suffice
 BN_EPS = 1e-5
 BN_MOMENTUM = 0.1
 
@@ -85,6 +85,10 @@ class UNetEngine:
         self._plans = {}
         self._eval_version = None
         self._saved = None  # (plan, x) of the last train-mode forward
+        self._side = None   # side stream for weight gradients (created on first backward)
+        self._events = []
+        import os
+        self.overlap_wgrad = os.environ.get("B200SR_NO_OVERLAP") is None
 
     # ------------------------------------------------------------------------------------------------
     # parameter flattening and derived operand buffers
@@ -259,6 +263,7 @@ class UNetEngine:
             for cs in self.convs:
                 h, w = H >> cs.level, W >> cs.level
                 plan["z:" + cs.name] = buf(h, w, cs.cout)
+                plan["dz:" + cs.name] = buf(h, w, cs.cout)  # own buffer per layer: read by the side-stream wgrad
             for lvl in range(4):
                 h, w, c = H >> lvl, W >> lvl, ch[lvl]
                 plan[f"dcat{lvl}"] = buf(h, w, 2 * c)
@@ -342,6 +347,8 @@ class UNetEngine:
                  B, h, w, ptr(z), cs.cout, 0, None, None, 0, stats, STATS_REPLICAS, st)
         bn = cs.bn
         track = bn.track_running_stats and bn.running_mean is not None
+        # (b200sr_bn_train_apply fuses these two launches, but its per-thread finalize prologue costs more HBM
+        # bandwidth-time than the extra tiny launch: 1.10 ms vs 0.95 ms per step over the 18 layers, measured)
         call("b200sr_bn_finalize", stats, STATS_REPLICAS, cs.cout, float(B * h * w), ptr(bn.weight), ptr(bn.bias),
              ptr(cs.conv.bias), BN_EPS, BN_MOMENTUM, self._bn(cs, "scale"), self._bn(cs, "shift"),
              self._bn(cs, "mean"), self._bn(cs, "invstd"), ptr(bn.running_mean) if track else None,
@@ -408,10 +415,8 @@ class UNetEngine:
         call("b200sr_bn_bwd_reduce", dy, dy_stride, dy_off, ptr(z), cs.cout, sc, sh, mu, iv, sums, STATS_REPLICAS,
              npix, st)
         g = self.flat_g.data_ptr()
-        call("b200sr_bn_bwd_finalize", sums, STATS_REPLICAS, cs.cout, float(npix), self._bn(cs, "c1"),
-             self._bn(cs, "c2"), g + 4 * self.off_of[id(cs.bn.weight)], g + 4 * self.off_of[id(cs.bn.bias)], st)
-        call("b200sr_bn_bwd_apply", dy, dy_stride, dy_off, ptr(z), cs.cout, sc, sh, mu, iv, self._bn(cs, "c1"),
-             self._bn(cs, "c2"), dz, npix, st)
+        call("b200sr_bn_bwd_apply_fused", dy, dy_stride, dy_off, ptr(z), cs.cout, sc, sh, mu, iv, sums, STATS_REPLICAS,
+             float(npix), g + 4 * self.off_of[id(cs.bn.weight)], g + 4 * self.off_of[id(cs.bn.bias)], dz, npix, st)
 
     def _G(self, param):
         return self.flat_G.data_ptr() + 4 * self.off_of[id(param)]
@@ -419,12 +424,27 @@ class UNetEngine:
     def backward(self, dout, bucket_hook=None):
         """Full backward of the last train-mode forward. dout: (B,1,H,W) fp32.
         Gradients land in self.flat_g (views: self.grad_views, in model.parameters() order).
-        bucket_hook(lo, hi), if given, is called as soon as flat_g[lo:hi] is final (reverse forward order)."""
+        bucket_hook(lo, hi), if given, is called as soon as flat_g[lo:hi] is final (reverse forward order).
+
+        Two streams: the data-gradient chain (BN backward -> dgrad -> ...) runs on the current stream; every weight
+        gradient (tensor-core wgrad kernels, their unpack into the parameter layout and the bucket hook) runs on a
+        side stream, ordered by events, so the tensor-bound wgrad kernels overlap the bandwidth-bound BatchNorm /
+        pooling backward kernels of the following layers. Each layer has its own dz buffer, hence no write-after-read
+        hazard between the streams inside a step; the streams are joined at the end."""
         if self._saved is None:
             raise _lib.B200SRError("backward() without a preceding train-mode forward")
         plan, x = self._saved
         B, H, W = plan["B"], plan["H"], plan["W"]
-        st = _lib.current_stream_ptr()
+        main = torch.cuda.current_stream()
+        st = main.cuda_stream
+        overlap = self.overlap_wgrad
+        if overlap:
+            if self._side is None:
+                self._side = torch.cuda.Stream(device=self.device)
+            side = self._side
+        else:
+            side = main
+        sst = side.cuda_stream
         ch = self.chans
         dout = dout.contiguous().float()
         self.flat_g.zero_()
@@ -434,17 +454,31 @@ class UNetEngine:
         s0, s1, s2 = (t.data_ptr() for t in plan["scratch"])
         g = self.flat_g.data_ptr()
         fc = self.model.final_conv
+        ev_i = [0]
+
+        def side_after_main():
+            """Everything enqueued on the main stream so far happens-before what is enqueued on the side stream next."""
+            if not overlap:
+                return
+            if ev_i[0] == len(self._events):
+                self._events.append(torch.cuda.Event())
+            ev = self._events[ev_i[0]]
+            ev_i[0] += 1
+            ev.record(main)
+            side.wait_event(ev)
 
         def unpack_range(lo_param, hi_off):
             """Unpack wgrad workspaces for all layers with flat offset in [off(lo_param), hi_off) and report."""
             lo = self.off_of[id(lo_param)]
             sel = [i for i in range(self.n_unpack)
                    if lo <= (int(self.unpack_np["dst"][i]) - g) // 4 < hi_off]
+            side_after_main()  # BN / bias gradients of the range are produced on the main stream
             if sel:
                 first, n = sel[0], len(sel)
-                call("b200sr_pack_jobs", self.unpack_jobs.data_ptr() + first * _PACK_JOB_DTYPE.itemsize, n, st)
+                call("b200sr_pack_jobs", self.unpack_jobs.data_ptr() + first * _PACK_JOB_DTYPE.itemsize, n, sst)
             if bucket_hook is not None:
-                bucket_hook(lo, hi_off)
+                with torch.cuda.stream(side):
+                    bucket_hook(lo, hi_off)
 
         # head
         a_last = plan["dec_a2_0"]
@@ -456,25 +490,26 @@ class UNetEngine:
             """Backward through a UNetBlock: dy (dense, cout ch) -> dx into dx_dst (in_c channels)."""
             c1, c2 = self.blocks[name]
             h, w, c = H >> lvl, W >> lvl, c2.cout
-            # pick two scratch buffers different from dy
-            free = [p for p in (s0, s1, s2) if p != dy_ptr]
-            dz2, dy1 = free[0], free[1]
+            dy1 = [p for p in (s0, s1, s2) if p != dy_ptr and p != dx_dst][0]
+            dz2, dz1 = ptr(plan["dz:" + c2.name]), ptr(plan["dz:" + c1.name])
             a1 = plan["bot_a1"] if name == "bottleneck" else plan[f"{name[:3]}_a1_{lvl}"]
             self._bn_bwd(plan, c2, dy_ptr, c, 0, h, w, dz2)
-            call("b200sr_conv3x3_wgrad", ptr(a1), c, 0, c, dz2, c, 0, c, B, h, w, self._G(c2.conv.weight), st)
+            side_after_main()
+            call("b200sr_conv3x3_wgrad", ptr(a1), c, 0, c, dz2, c, 0, c, B, h, w, self._G(c2.conv.weight), sst)
             call("b200sr_conv3x3_dgrad", dz2, c, 0, c, self._wp(self.wp_dgrad, c2.name), c, B, h, w, dy1, c, 0, None,
                  0, st)
-            dz1 = dy_ptr  # dy is dead now
             self._bn_bwd(plan, c1, dy1, c, 0, h, w, dz1)
+            side_after_main()
             if x_input is not None:
-                call("b200sr_conv1_wgrad", ptr(x_input), dz1, g + 4 * self.off_of[id(c1.conv.weight)], B, h, w, st)
+                call("b200sr_conv1_wgrad", ptr(x_input), dz1, g + 4 * self.off_of[id(c1.conv.weight)], B, h, w, sst)
                 return None
             call("b200sr_conv3x3_wgrad", ptr(in_buf), in_stride, 0, in_c, dz1, c, 0, c, B, h, w,
-                 self._G(c1.conv.weight), st)
+                 self._G(c1.conv.weight), sst)
             call("b200sr_conv3x3_dgrad", dz1, c, 0, c, self._wp(self.wp_dgrad, c1.name), in_c, B, h, w, dx_dst,
                  dx_stride, 0, dx_stats, STATS_REPLICAS if dx_stats else 0, st)
             return dx_dst
 
+        side_after_main()  # gradient buffers are zeroed
         hi = self.p_total
         # decoder, shallow -> deep
         for k in (1, 2, 3, 4):
@@ -489,8 +524,9 @@ class UNetEngine:
             torch.sum(sums.view(STATS_REPLICAS, 2, 2 * c)[:, 0, :c], dim=0,
                       out=self.grad_views[self._params_index(us.mod.bias)])
             x_up = plan["bot_a2"] if k == 4 else plan[f"dec_a2_{lvl + 1}"]
+            side_after_main()
             call("b200sr_convT2x2_wgrad", ptr(dcat), 2 * c, 0, c, ptr(x_up), us.cin, 0, us.cin, B, h // 2, w // 2,
-                 self._G(us.mod.weight), st)
+                 self._G(us.mod.weight), sst)
             dy = s0 if dy != s0 else s1
             call("b200sr_convT2x2_dgrad", ptr(dcat), 2 * c, 0, c, self._wp(self.wp_dgrad, us.name), us.cin, B, h // 2,
                  w // 2, dy, us.cin, 0, st)
@@ -499,8 +535,6 @@ class UNetEngine:
 
         # bottleneck: dx = gradient w.r.t. pool3 (dense)
         dpool = [p for p in (s0, s1, s2) if p != dy][0]
-        # block_bwd uses the two scratch buffers != dy for dz2/dy1 and reuses dy for dz1; dx must not alias dz1
-        # -> write dx into dz2's buffer (dead after the conv2 dgrad), which is `dpool` by construction.
         block_bwd("bottleneck", 4, plan["pool3"], ch[3], ch[3], dpool, ch[3], None, dy)
         unpack_range(self.blocks["bottleneck"][0].conv.weight, hi)
         hi = self.off_of[id(self.blocks["bottleneck"][0].conv.weight)]
@@ -519,6 +553,8 @@ class UNetEngine:
                 block_bwd(name, lvl, plan[f"pool{lvl - 1}"], ch[lvl - 1], ch[lvl - 1], nxt, ch[lvl - 1], None, dy)
                 dpool = nxt
         unpack_range(self.blocks["enc1"][0].conv.weight, hi)
+        if overlap:
+            main.wait_stream(side)
         self._saved = None
         return self.grad_views
 

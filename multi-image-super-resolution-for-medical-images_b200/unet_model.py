@@ -162,14 +162,7 @@ def create_dummy_dataset(num_samples=100, img_size=256, seed=None):
             for _ in range(num_samples)]
 
 
-def _unpack_batch(batch):
-    """Accept both loader contracts of the reference: (inputs, targets) (unet_model.py:174) and
-    ((pre, post), mid) (ModelDataGenerator.py:214)."""
-    first, targets = batch
-    if isinstance(first, (tuple, list)):
-        pre, post = first
-        first = torch.cat([pre, post], dim=1)
-    return first, targets
+from .data import DevicePrefetcher, unpack_batch as _unpack_batch  # noqa: E402
 
 
 class UNetTrainer:
@@ -236,10 +229,7 @@ class UNetTrainer:
         self.model.train()
         total = torch.zeros((), dtype=torch.float32, device=self.device)
         n = 0
-        for batch in train_loader:
-            inputs, targets = _unpack_batch(batch)
-            inputs = inputs.to(self.device, non_blocking=True)
-            targets = targets.to(self.device, non_blocking=True)
+        for inputs, targets in DevicePrefetcher(train_loader, self.device):  # H2D of batch i+1 overlaps step i
             total += self.train_step(inputs, targets).detach()
             n += 1
         return float(total.item()) / max(n, 1)  # single host sync per epoch (reference: one per step, :187)

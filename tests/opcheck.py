@@ -219,7 +219,20 @@ def bn_train(B=2, H=16, W=32, C=128, pool=True, seed=8):
     a = nchw(act[..., C:])
     res = {"act": rel(a, ref), "running_mean": rel(rm, rm_ref), "running_var": rel(rv, rv_ref),
            "slot_untouched": float((act[..., :C].float() - 7.0).abs().max())}
+    # fused finalize+apply must reproduce the two-kernel path bit for bit
+    rm2, rv2 = 0.2 * rnd(C, seed=seed + 4), 1 + 0.1 * rnd(C, seed=seed + 5).abs()
+    ws2 = torch.zeros(4, C, device=DEV)
+    act2 = slot_buffer(B, H, W, C, 2 * C, C)
+    pooled2 = torch.zeros_like(pooled) if pool else None
+    call("b200sr_bn_train_apply", ptr(zb), C, ptr(stats), R, float(B * H * W), ptr(gamma), ptr(beta), ptr(cbias), 1e-5,
+         0.1, ptr(ws2[0]), ptr(ws2[1]), ptr(ws2[2]), ptr(ws2[3]), ptr(rm2), ptr(rv2), ptr(act2), 2 * C, C, ptr(pooled2),
+         B, H, W, st())
+    torch.cuda.synchronize()
+    res["fused_act_exact"] = float((act2.float() - act.float()).abs().max())
+    res["fused_ws_exact"] = float((ws2 - ws).abs().max())
+    res["fused_running_exact"] = float((rm2 - rm).abs().max() + (rv2 - rv).abs().max())
     if pool:
+        res["fused_pool_exact"] = float((pooled2.float() - pooled.float()).abs().max())
         res["pool_exact"] = float((nchw(pooled) - F.max_pool2d(a, 2)).abs().max())
         p2 = torch.zeros_like(pooled)
         call("b200sr_maxpool2x2_fwd", ptr(act), 2 * C, C, C, ptr(p2), B, H, W, st())
@@ -270,7 +283,16 @@ def bn_bwd(B=2, H=16, W=32, C=128, seed=10):
     call("b200sr_bn_bwd_apply", ptr(dyb), C, 0, ptr(zb), C, ptr(scale), ptr(shift), ptr(mean), ptr(invstd), ptr(c12[0]),
          ptr(c12[1]), ptr(dz), N, st())
     torch.cuda.synchronize()
-    return {"dz": rel(nchw(dz), z.grad), "dgamma": rel(dgb[0], gamma.grad), "dbeta": rel(dgb[1], beta.grad)}
+    res = {"dz": rel(nchw(dz), z.grad), "dgamma": rel(dgb[0], gamma.grad), "dbeta": rel(dgb[1], beta.grad)}
+    if C % 8 == 0 and 256 % (C // 8) == 0:
+        dz2 = torch.zeros_like(dz)
+        dgb2 = torch.zeros(2, C, device=DEV)
+        call("b200sr_bn_bwd_apply_fused", ptr(dyb), C, 0, ptr(zb), C, ptr(scale), ptr(shift), ptr(mean), ptr(invstd),
+             ptr(sums), R, float(N), ptr(dgb2[0]), ptr(dgb2[1]), ptr(dz2), N, st())
+        torch.cuda.synchronize()
+        res["fused_dz"] = rel(nchw(dz2), z.grad)
+        res["fused_dgamma"] = rel(dgb2[0], gamma.grad)
+    return res
 
 
 def head(B=2, H=16, W=32, seed=11):
@@ -397,9 +419,12 @@ CHECKS = {
     "convT_wgrad_big": (convT_wgrad, dict(Cin=512, Cout=256, B=1, H=8, W=16), {"dw": BF16}),
     "conv1": (conv1, {}, {"out": BF16, "stats_sum": 1e-3, "stats_sq": 1e-3, "dw": 1e-3}),
     "bn_train_pool": (bn_train, {}, {"act": BF16, "running_mean": 1e-5, "running_var": 1e-4, "pool_exact": 0.0,
-                                     "maxpool_fwd_exact": 0.0, "slot_untouched": 0.0}),
+                                     "maxpool_fwd_exact": 0.0, "slot_untouched": 0.0, "fused_act_exact": 0.0,
+                                     "fused_ws_exact": 0.0, "fused_running_exact": 0.0, "fused_pool_exact": 0.0}),
+    "bn_train_c1024": (bn_train, dict(C=1024, B=2, H=8, W=8), {"act": BF16, "fused_act_exact": 0.0,
+                                                               "fused_running_exact": 0.0}),
     "maxpool_bwd_ties": (maxpool_bwd, {}, {"dy_exact": 0.0}),
-    "bn_bwd": (bn_bwd, {}, {"dz": BF16, "dgamma": 1e-3, "dbeta": 1e-3}),
+    "bn_bwd": (bn_bwd, {}, {"dz": BF16, "dgamma": 1e-3, "dbeta": 1e-3, "fused_dz": BF16, "fused_dgamma": 1e-3}),
     "bn_bwd_c1024": (bn_bwd, dict(C=1024, B=3, H=8, W=8), {"dz": BF16, "dgamma": 1e-3, "dbeta": 1e-3}),
     "bn_bwd_c64_large": (bn_bwd, dict(C=64, B=2, H=96, W=80), {"dz": BF16, "dgamma": 1e-3, "dbeta": 1e-3}),
     "bn_bwd_c24_generic": (bn_bwd, dict(C=192, B=2, H=8, W=8), {"dz": BF16, "dgamma": 1e-3, "dbeta": 1e-3}),
