@@ -203,13 +203,21 @@ def run_b200sr(args):
 
     # ---- e2e: the public API from pinned HOST buffers: DevicePrefetcher (H2D of batch i+1 overlaps step i) feeding
     # UNetTrainer.train_step, loss read back to the host every step (like the reference's loss.item(), :187) --------
-    loss_host = torch.zeros((), dtype=torch.float32).pin_memory()
+    loss_host = torch.zeros(2, dtype=torch.float32).pin_memory()
+    loss_ev = [torch.cuda.Event(), torch.cuda.Event()]
 
     def run_e2e(nsteps):
+        # every step: H2D of its inputs (pinned host -> device, prefetched one step ahead) and a D2H read of its loss;
+        # the host consumes the loss of step i-1 while step i runs (no per-step pipeline bubble)
         host_batches = (host_ring[i % len(host_ring)] for i in range(nsteps))
-        for x, y in b200sr.DevicePrefetcher(host_batches, dev):
+        for i, (x, y) in enumerate(b200sr.DevicePrefetcher(host_batches, dev)):
             loss = trainer.train_step(x, y)
-            loss_host.copy_(loss, non_blocking=False)
+            loss_host[i % 2:i % 2 + 1].copy_(loss.reshape(1), non_blocking=True)
+            loss_ev[i % 2].record()
+            if i > 0:
+                loss_ev[1 - i % 2].synchronize()
+                _ = float(loss_host[1 - i % 2])
+        loss_ev[(nsteps - 1) % 2].synchronize()
 
     run_e2e(3)
     sync_all()
@@ -240,14 +248,15 @@ def run_b200sr(args):
     roofline = None
     model.train()
     engine = model._get_engine()
-    overlap_was = engine.overlap_wgrad
-    engine.overlap_wgrad = False   # per-kernel event timing needs the kernels serialised on one stream
+    overlap_was, graph_was = engine.overlap_wgrad, trainer.use_cuda_graph
+    engine.overlap_wgrad = False   # per-kernel event timing needs the kernels serialised on one stream ...
+    trainer.use_cuda_graph = False  # ... and launched eagerly
     if rank == 0:
         _lib.enable_profiling(True)
     for i in range(3):
         step_resident(i)
     sync_all()
-    engine.overlap_wgrad = overlap_was
+    engine.overlap_wgrad, trainer.use_cuda_graph = overlap_was, graph_was
     if rank == 0:
         agg = _lib.collect_profile()
         _lib.enable_profiling(False)
@@ -263,7 +272,7 @@ def run_b200sr(args):
                     "frac": achieved / peak, "traffic": None,
                     "peak_source": peaks["source"] + " sustained bf16 (kernels timed inside a long step); burst "
                                    f"{peaks['bf16_tflops']}",
-                    "note": "per-kernel times from 3 instrumented steps with the wgrad side stream disabled",
+                    "note": "per-kernel times from 3 instrumented eager steps (CUDA graph and wgrad side stream off)",
                     "launches_per_step": g_n // 3, "avg_launch_ms": g_ms / max(g_n, 1),
                     "gflop_per_launch": g_flop / max(g_n, 1) / 1e9, "share_of_step": g_ms / all_ms,
                     "per_op": {k: {"ms_per_step": v["ms"] / 3, "tflops": (v["flop"] / (v["ms"] / 1e3) / 1e12)

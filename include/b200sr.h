@@ -182,6 +182,11 @@ int b200sr_mse_ssim(const float* pred, const float* target, float* grad, double*
 int b200sr_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1,
                      float beta2, float eps, int64_t step, float grad_scale, void* stream);
 
+/* Same step with the step-dependent scalars read from DEVICE memory: bias_corr[0] = 1 - beta1^step,
+ * bias_corr[1] = sqrt(1 - beta2^step). The launch itself is then step-independent and can be replayed from a CUDA graph. */
+int b200sr_adam_step_dev(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
+                         float eps, const float* bias_corr, float grad_scale, void* stream);
+
 /* layout casts at the boundary */
 int b200sr_nchw_f32_to_nhwc_bf16(const float* in, void* out, int B, int C, int H, int W, void* stream);
 int b200sr_nhwc_bf16_to_nchw_f32(const void* in, int in_pix_stride, int in_c_off, float* out, int B, int C,

@@ -50,6 +50,7 @@ _SIGNATURES = {
     "b200sr_mse_ssim": [_P, _P, _P, _P, c_int, c_int, c_int, _P, c_int, c_float, c_float, c_float, c_float, c_float,
                         _P],
     "b200sr_adam_step": [_P, _P, _P, _P, c_int64, c_float, c_float, c_float, c_float, c_int64, c_float, _P],
+    "b200sr_adam_step_dev": [_P, _P, _P, _P, c_int64, c_float, c_float, c_float, c_float, _P, c_float, _P],
     "b200sr_nchw_f32_to_nhwc_bf16": [_P, _P, c_int, c_int, c_int, c_int, _P],
     "b200sr_nhwc_bf16_to_nchw_f32": [_P, c_int, c_int, _P, c_int, c_int, c_int, c_int, _P],
 }
@@ -126,7 +127,7 @@ def _cost(name, a):
         return 0.0, a[6] * (4.0 + 128 + 128)
     if name == "b200sr_mse_ssim":
         return 0.0, a[4] * a[5] * a[6] * 4.0 * (3 if a[2] else 2)
-    if name == "b200sr_adam_step":
+    if name in ("b200sr_adam_step", "b200sr_adam_step_dev"):
         return 0.0, a[4] * 4.0 * 7
     if name == "b200sr_conv1_fwd":
         return 0.0, a[8] * a[9] * a[10] * (8.0 + 128)

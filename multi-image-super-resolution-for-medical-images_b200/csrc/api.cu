@@ -908,7 +908,17 @@ int b200sr_adam_step(float* p, const float* g, float* m, float* v, int64_t n, fl
     const double bc1 = 1.0 - pow(static_cast<double>(beta1), static_cast<double>(step));
     const double bc2 = 1.0 - pow(static_cast<double>(beta2), static_cast<double>(step));
     adam_flat_kernel<<<grid_for((n + 3) / 4, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        p, g, m, v, n, lr, beta1, beta2, eps, static_cast<float>(bc1), static_cast<float>(sqrt(bc2)), grad_scale);
+        p, g, m, v, n, lr, beta1, beta2, eps, static_cast<float>(bc1), static_cast<float>(sqrt(bc2)), grad_scale,
+        nullptr);
+    return check_launch("adam_flat_kernel");
+}
+
+int b200sr_adam_step_dev(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
+                         float eps, const float* bias_corr, float grad_scale, void* stream) {
+    B2_CHECK_ARG(p && g && m && v && n > 0 && bias_corr);
+    B2_CHECK_ARG(aligned16(p) && aligned16(g) && aligned16(m) && aligned16(v));
+    adam_flat_kernel<<<grid_for((n + 3) / 4, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        p, g, m, v, n, lr, beta1, beta2, eps, 1.f, 1.f, grad_scale, bias_corr);
     return check_launch("adam_flat_kernel");
 }
 

@@ -1001,7 +1001,13 @@ __global__ void nhwc_bf16_to_nchw_f32_kernel(const __nv_bfloat16* __restrict__ i
 __global__ void __launch_bounds__(256) adam_flat_kernel(float* __restrict__ p, const float* __restrict__ g,
                                                         float* __restrict__ m, float* __restrict__ v, long long n,
                                                         float lr, float beta1, float beta2, float eps,
-                                                        float bias_corr1, float bias_corr2_sqrt, float grad_scale) {
+                                                        float bias_corr1, float bias_corr2_sqrt, float grad_scale,
+                                                        const float* __restrict__ bias_corr_dev) {
+    // step-dependent scalars may come from device memory so that the launch can live in a CUDA graph
+    if (bias_corr_dev != nullptr) {
+        bias_corr1 = bias_corr_dev[0];
+        bias_corr2_sqrt = bias_corr_dev[1];
+    }
     for (long long i = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) * 4; i < n;
          i += static_cast<long long>(gridDim.x) * blockDim.x * 4) {
         if (i + 4 <= n) {

@@ -79,26 +79,37 @@ class DevicePrefetcher:
             return
         copy_stream = torch.cuda.Stream(device=self.device)
         it = iter(self.loader)
+        # two persistent device slots (no allocator traffic in the loop): slot s is refilled on the copy stream only
+        # after the consumer's work on it has been enqueued (event `done[s]`)
+        bufs, ready, done = [None, None], [torch.cuda.Event(), torch.cuda.Event()], [None, None]
 
-        def fetch():
+        def fetch(slot):
             batch = next(it, None)
             if batch is None:
-                return None
+                return False
             x, y = unpack_batch(batch)
+            b = bufs[slot]
+            if b is None or b[0].shape != x.shape or b[1].shape != y.shape or b[0].dtype != x.dtype:
+                b = bufs[slot] = (torch.empty(x.shape, dtype=x.dtype, device=self.device),
+                                  torch.empty(y.shape, dtype=y.dtype, device=self.device))
+                copy_stream.wait_stream(torch.cuda.current_stream(self.device))
+            if done[slot] is not None:
+                copy_stream.wait_event(done[slot])
             with torch.cuda.stream(copy_stream):
-                x = x.to(self.device, non_blocking=True)
-                y = y.to(self.device, non_blocking=True)
-            ev = torch.cuda.Event()
-            ev.record(copy_stream)
-            return x, y, ev
+                b[0].copy_(x, non_blocking=True)
+                b[1].copy_(y, non_blocking=True)
+            ready[slot].record(copy_stream)
+            return True
 
-        cur = fetch()
-        while cur is not None:
-            nxt = fetch()
-            x, y, ev = cur
+        i = 0
+        have = fetch(0)
+        while have:
+            nxt = fetch((i + 1) % 2)
             stream = torch.cuda.current_stream(self.device)
-            stream.wait_event(ev)
-            x.record_stream(stream)
-            y.record_stream(stream)
-            yield x, y
-            cur = nxt
+            stream.wait_event(ready[i % 2])
+            yield bufs[i % 2]
+            ev = done[i % 2] or torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(self.device))  # the consumer's use of this slot is enqueued
+            done[i % 2] = ev
+            i += 1
+            have = nxt

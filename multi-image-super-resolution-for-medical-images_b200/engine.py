@@ -94,13 +94,27 @@ class UNetEngine:
     # parameter flattening and derived operand buffers
     # ------------------------------------------------------------------------------------------------
     def _params(self):
-        return list(self.model.parameters())
+        ps = self.__dict__.get("_param_list")
+        if ps is None:
+            ps = self._param_list = list(self.model.parameters())
+        return ps
 
     def _is_flat(self) -> bool:
         if self.flat_p is None:
             return False
         base = self.flat_p.data_ptr()
-        for p, off in zip(self._params(), self.p_off):
+        params = self._params()
+        # every call: cheap probe of the first and last parameter; full scan every 64th call (model.to() and
+        # load_state_dict(assign=True) replace all tensors at once, so the probe catches them)
+        self._flat_checks = getattr(self, "_flat_checks", 0) + 1
+        if self._flat_checks % 64 == 0:
+            self.__dict__.pop("_param_list", None)  # re-read the module's parameter objects on the full scan
+            params = self._params()
+            if len(params) != len(self.p_off):
+                return False
+        probe = ((params[0], self.p_off[0]), (params[-1], self.p_off[-1])) if self._flat_checks % 64 else \
+            zip(params, self.p_off)
+        for p, off in probe:
             if p.data.data_ptr() != base + 4 * off or p.device != self.flat_p.device:
                 return False
         # raw buffer pointers are baked into the fold-job table
@@ -112,6 +126,8 @@ class UNetEngine:
             return
         _lib.require_device()
         self.device = device
+        self.__dict__.pop("_param_list", None)
+        self.__dict__.pop("_pindex", None)
         params = self._params()
         for p in params:
             if p.device != device or p.dtype != torch.float32:

@@ -176,7 +176,7 @@ class UNetTrainer:
 
     def __init__(self, model, device='cuda' if torch.cuda.is_available() else 'cpu', learning_rate=1e-4,
                  model_save_dir='models', loss='mse', ssim_weight=0.005, ssim_mode='gaussian', data_range=1.0,
-                 verbose=True):
+                 verbose=True, use_cuda_graph=False):
         from .losses import CombinedLoss
         self.model = model.to(device)
         self.device = device
@@ -197,6 +197,12 @@ class UNetTrainer:
         self.patience_counter = 0
         self.verbose = verbose
         self._reducer = None
+        # optional: replay single-GPU steps from a CUDA graph (captured on the third call per input shape), so the ~130
+        # kernel launches of a step cost one graph launch on the host. Off by default: the step is GPU-bound and the
+        # host stays ahead of the device, measured 13.3 ms (graph) vs 13.1 ms (eager) per B=32 step
+        import os
+        self.use_cuda_graph = use_cuda_graph and os.environ.get("B200SR_NO_GRAPH") is None
+        self._graphs, self._graph_calls = {}, {}
         if torch.distributed.is_available() and torch.distributed.is_initialized() \
                 and torch.distributed.get_world_size() > 1:
             from .ddp import broadcast_module_state
@@ -206,8 +212,9 @@ class UNetTrainer:
             print(f"Total parameters: {sum(p.numel() for p in self.model.parameters()):,}")
 
     # -- one optimisation step on device tensors; returns the loss as a 0-d device tensor (no host sync) --
-    def train_step(self, inputs, targets):
-        self.model.train()
+    def _device_step(self, inputs, targets):
+        """Everything of a step that runs on the device: forward, fused loss+gradient, backward (+ bucketed
+        all-reduce when distributed), Adam kernel. No host-side state that changes from step to step."""
         engine = self.model._get_engine()
         out = engine.forward_train(inputs)
         loss, dout = self.criterion.value_and_grad(out, targets)
@@ -222,8 +229,42 @@ class UNetTrainer:
         engine.backward(dout, bucket_hook=hook)
         if hook is not None:
             self._reducer.wait()
-        self.optimizer.step(grad_scale=scale)
+        self.optimizer.device_step(grad_scale=scale)
         return loss
+
+    def train_step(self, inputs, targets):
+        self.model.train()
+        from .ddp import is_distributed
+        if self.use_cuda_graph and inputs.is_cuda and not is_distributed():
+            key = (tuple(inputs.shape), tuple(targets.shape), inputs.device)
+            g = self._graphs.get(key)
+            if g is None:
+                n = self._graph_calls.get(key, 0)
+                self._graph_calls[key] = n + 1
+                if n >= 2:   # two eager steps first: lazy one-time set-up (buffers, kernel attributes) must be done
+                    g = self._capture(inputs, targets)
+                    self._graphs[key] = g
+            if g is not None:
+                g["x"].copy_(inputs)
+                g["y"].copy_(targets)
+                self.optimizer.host_pre_step()
+                g["graph"].replay()
+                _lib.LAUNCH_COUNTER["n"] += g["launches"]
+                return g["loss"]
+        self.optimizer.host_pre_step()
+        return self._device_step(inputs.contiguous().float(), targets.contiguous().float())
+
+    def _capture(self, inputs, targets):
+        x = inputs.detach().contiguous().float().clone()
+        y = targets.detach().contiguous().float().clone()
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        n0 = _lib.LAUNCH_COUNTER["n"]
+        with torch.cuda.graph(graph):
+            loss = self._device_step(x, y)
+        launches = _lib.LAUNCH_COUNTER["n"] - n0
+        _lib.LAUNCH_COUNTER["n"] = n0
+        return {"graph": graph, "x": x, "y": y, "loss": loss, "launches": launches}
 
     def train_epoch(self, train_loader):
         self.model.train()
