@@ -269,7 +269,10 @@ def run_b200sr(args):
         peak = peaks["bf16_tflops_sustained"] or peaks["bf16_tflops"]
         roofline = {"bound": "tensor", "kernel": "igemm_kernel + wgrad_kernel (tcgen05 implicit GEMM: conv3x3 "
                     "fwd/dgrad/wgrad, ConvT fwd/dgrad/wgrad)", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                    "frac": achieved / peak, "traffic": None,
+                    "frac": achieved / peak,
+                    # DRAM bytes per tensor-core launch (dram__bytes_read+write, mean of the 24 conv3x3/wgrad3x3
+                    # launches in profiles/r1_final_gemm_ncu_summary.txt, ncu --set full)
+                    "traffic": 101.8e6,
                     "peak_source": peaks["source"] + " sustained bf16 (kernels timed inside a long step); burst "
                                    f"{peaks['bf16_tflops']}",
                     "note": "per-kernel times from 3 instrumented eager steps (CUDA graph and wgrad side stream off)",
