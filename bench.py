@@ -21,9 +21,15 @@ import subprocess
 import sys
 import time
 
-# keep stdout to the single JSON line: NCCL prints a version banner there when NCCL_DEBUG=VERSION/INFO is inherited
-if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", ""):
-    os.environ["NCCL_DEBUG"] = "WARN"
+# stdout carries exactly ONE JSON line: libraries (e.g. NCCL's version banner) write to fd 1 behind Python's back, so
+# fd 1 is pointed at stderr for the whole run and the JSON line goes to the saved original descriptor
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line: dict):
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
@@ -131,7 +137,7 @@ def run_reference(args):
                              "sample": r["sample"]},
             "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    emit(line)
 
 
 # ----------------------------------------------------------------------------------------------------------
@@ -308,7 +314,7 @@ def run_b200sr(args):
                                           "fp32 in/out, bf16 tensor-core compute",
                               "value_b32": inf_big_value, "frac_of_peak_b32":
                                   FWD_GFLOP_PER_TRIPLET * inf_big_value / world / 1e3 / peaks["bf16_tflops"]}}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
