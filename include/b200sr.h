@@ -114,6 +114,9 @@ int b200sr_bn_fold_eval(const b200sr_fold_job* jobs, int njobs, float eps, void*
  * x: (B,2,H,W) f32; w: (64,2,3,3) f32 (the parameter itself); out: (B,H,W,64) bf16 dense. */
 int b200sr_conv1_fwd(const float* x, const float* w, const float* col_scale, const float* col_shift, int relu,
                      void* out, float* stats, int stats_replicas, int B, int H, int W, void* stream);
+/* Data gradient of the first layer: dx (B,2,H,W) f32 written (not added). Needed when the network input carries a
+ * gradient (Progressive UNet stages 2A/2B, ModelLoader.py:258-267). */
+int b200sr_conv1_dgrad(const void* dz, const float* w, float* dx, int B, int H, int W, void* stream);
 /* dW (64,2,3,3) f32, ADDED into. */
 int b200sr_conv1_wgrad(const float* x, const void* dz, float* dw, int B, int H, int W, void* stream);
 

@@ -2,8 +2,8 @@
 
 Same `load_model(model_name, device)` contract: known names, `ValueError` for unknown names,
 `FileNotFoundError` for a missing checkpoint, three accepted checkpoint layouts (`generator_state_dict`,
-`model_state_dict`, bare state_dict), result returned in eval mode. Only the models on the b200sr hot path
-('unet', 'unet_combined') are implemented natively; the other registry names are recognised but refuse to load
+`model_state_dict`, bare state_dict), result returned in eval mode. The models on the b200sr hot path
+('unet', 'unet_combined') and its first "next" row ('progressive_unet') are implemented natively; the other registry names are recognised but refuse to load
 (they are out of scope) instead of silently falling back to torch modules.
 """
 from __future__ import annotations
@@ -13,6 +13,7 @@ import os
 import torch
 
 from .unet_model import UNet, UNetBlock  # noqa: F401  (re-exported like the reference module does)
+from .progressive import ProgressiveUNet, ProgressiveUNetBlock, UNetStage  # noqa: F401
 
 _UNET_KW = {'in_channels': 2, 'out_channels': 1, 'init_features': 64}
 
@@ -21,7 +22,7 @@ CHECKPOINT_MAP = {
     'unet': ('unet_best.pt', UNet, _UNET_KW),
     'unet_combined': ('unet_combined_best.pt', UNet, _UNET_KW),
     'deepcnn': ('deepcnn_best.pt', None, {}),
-    'progressive_unet': ('progressive_unet_best.pt', None, {}),
+    'progressive_unet': ('progressive_unet_best.pt', ProgressiveUNet, {'base_features': 64}),
     'unet_gan': ('unet_gan_best.pt', None, {}),
     'fastddpm': ('fastddpm_advanced_best.pth', None, {}),
 }

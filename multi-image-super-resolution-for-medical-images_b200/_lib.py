@@ -33,6 +33,7 @@ _SIGNATURES = {
     "b200sr_pack_jobs": [_P, c_int, _P],
     "b200sr_bn_fold_eval": [_P, c_int, c_float, _P],
     "b200sr_conv1_fwd": [_P, _P, _P, _P, c_int, _P, _P, c_int, c_int, c_int, c_int, _P],
+    "b200sr_conv1_dgrad": [_P, _P, _P, c_int, c_int, c_int, _P],
     "b200sr_conv1_wgrad": [_P, _P, _P, c_int, c_int, c_int, _P],
     "b200sr_bn_finalize": [_P, c_int, c_int, c_double, _P, _P, _P, c_float, c_float, _P, _P, _P, _P, _P, _P, _P],
     "b200sr_bnrelu_apply": [_P, c_int, _P, _P, _P, c_int, c_int, _P, c_int, c_int, c_int, _P],
@@ -131,6 +132,8 @@ def _cost(name, a):
         return 0.0, a[4] * 4.0 * 7
     if name == "b200sr_conv1_fwd":
         return 0.0, a[8] * a[9] * a[10] * (8.0 + 128)
+    if name == "b200sr_conv1_dgrad":
+        return 0.0, a[3] * a[4] * a[5] * (8.0 + 128)
     if name == "b200sr_conv1_wgrad":
         return 0.0, a[3] * a[4] * a[5] * (8.0 + 128)
     return 0.0, 0.0

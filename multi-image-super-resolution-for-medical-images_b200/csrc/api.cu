@@ -687,6 +687,16 @@ int b200sr_conv1_wgrad(const float* x, const void* dz, float* dw, int B, int H, 
     return check_launch("conv1_direct_wgrad_kernel");
 }
 
+int b200sr_conv1_dgrad(const void* dz, const float* w, float* dx, int B, int H, int W, void* stream) {
+    B2_CHECK_ARG(dz != nullptr && w != nullptr && dx != nullptr);
+    B2_CHECK_ARG(B > 0 && H % C1_TILE == 0 && W % C1_TILE == 0 && aligned16(dz));
+    const int tiles = B * (H / C1_TILE) * (W / C1_TILE);
+    const int grid = tiles < num_sms() * 4 ? tiles : num_sms() * 4;
+    conv1_direct_dgrad_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16*>(dz), w, dx, H, W, tiles);
+    return check_launch("conv1_direct_dgrad_kernel");
+}
+
 int b200sr_bn_finalize(const float* stats, int replicas, int C, double count, const float* gamma, const float* beta,
                        const float* conv_bias, float eps, float momentum, float* scale, float* shift, float* save_mean,
                        float* save_invstd, float* running_mean, float* running_var, void* stream) {

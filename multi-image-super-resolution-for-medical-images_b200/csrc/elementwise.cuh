@@ -333,6 +333,64 @@ __global__ void __launch_bounds__(256) conv1_direct_wgrad_kernel(const float* __
     for (int i = tid; i < C1_COUT * 18; i += 256) atomicAdd(dw + i, s_acc[i]);
 }
 
+// Data gradient of the first layer (needed when the network input itself requires a gradient: stages 2A/2B of the
+// Progressive UNet feed stage 1's prediction into their first conv, reference src/ModelLoader.py:258-267).
+//   dx[b][ci][h][w] = sum_{kh,kw,co} dZ[b][h-(kh-1)][w-(kw-1)][co] * W[co][ci][kh][kw]        (fp32 NCHW output)
+// One thread = one pixel; the 18x18 dZ halo tile (bf16) and the weights live in shared memory.
+__global__ void __launch_bounds__(256) conv1_direct_dgrad_kernel(const __nv_bfloat16* __restrict__ dz,  // [B][H][W][64]
+                                                                 const float* __restrict__ wgt,          // [64][2][3][3]
+                                                                 float* __restrict__ dx,                 // [B][2][H][W]
+                                                                 int H, int W, int num_tiles) {
+    // rows of 66 bf16 = 33 words: the 32 pixels of a warp read the same channel pair from 32 different banks
+    __shared__ __align__(16) __nv_bfloat16 s_dz[(C1_TILE + 2) * (C1_TILE + 2)][C1_COUT + 2];
+    __shared__ float2 s_w[9][C1_COUT];  // [tap][co] -> (ci 0, ci 1)
+    const int tid = threadIdx.x;
+    const int tiles_w = W / C1_TILE;
+    const int tiles_hw = tiles_w * (H / C1_TILE);
+    for (int i = tid; i < 9 * C1_COUT; i += 256) {
+        const int co = i % C1_COUT, t = i / C1_COUT;
+        s_w[t][co] = make_float2(wgt[co * 18 + t], wgt[co * 18 + 9 + t]);
+    }
+    const int ph = tid / C1_TILE, pw = tid % C1_TILE;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int img = tile / tiles_hw;
+        const int t_in = tile - img * tiles_hw;
+        const int h0 = (t_in / tiles_w) * C1_TILE, w0 = (t_in % tiles_w) * C1_TILE;
+        __syncthreads();
+        for (int i = tid; i < (C1_TILE + 2) * (C1_TILE + 2) * 8; i += 256) {
+            const int p = i >> 3, c8 = i & 7;
+            const int hh = h0 + p / (C1_TILE + 2) - 1, ww = w0 + p % (C1_TILE + 2) - 1;
+            uint4 u = make_uint4(0, 0, 0, 0);
+            if (hh >= 0 && hh < H && ww >= 0 && ww < W)
+                u = *reinterpret_cast<const uint4*>(dz + ((static_cast<size_t>(img) * H + hh) * W + ww) * C1_COUT + c8 * 8);
+            uint32_t* d = reinterpret_cast<uint32_t*>(&s_dz[p][c8 * 8]);  // 4-byte aligned only (132-byte rows)
+            d[0] = u.x;
+            d[1] = u.y;
+            d[2] = u.z;
+            d[3] = u.w;
+        }
+        __syncthreads();
+        float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+            // tap (kh,kw) of the forward conv reads dZ at (h - (kh-1), w - (kw-1)): halo index (ph + 2 - kh, pw + 2 - kw)
+            const int kh = t / 3, kw = t % 3;
+            const __nv_bfloat16* row = s_dz[(ph + 2 - kh) * (C1_TILE + 2) + (pw + 2 - kw)];
+#pragma unroll 8
+            for (int co = 0; co < C1_COUT; co += 2) {
+                const __nv_bfloat162 g2 = *reinterpret_cast<const __nv_bfloat162*>(row + co);
+                const float g0 = __low2float(g2), g1 = __high2float(g2);
+                const float2 wa = s_w[t][co], wb = s_w[t][co + 1];
+                a0 = fmaf(g0, wa.x, fmaf(g1, wb.x, a0));
+                a1 = fmaf(g0, wa.y, fmaf(g1, wb.y, a1));
+            }
+        }
+        const size_t base = (static_cast<size_t>(img) * 2 * H + h0 + ph) * W + w0 + pw;
+        dx[base] = a0;
+        dx[base + static_cast<size_t>(H) * W] = a1;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // BatchNorm (train): finalize statistics -> per-channel scale/shift, saved mean/invstd, running stats.
 // Reference semantics: nn.BatchNorm2d defaults (eps 1e-5, momentum 0.1, biased var to normalise,

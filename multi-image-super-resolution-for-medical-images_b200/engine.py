@@ -62,6 +62,8 @@ class UNetEngine:
                 "b200sr UNet engine implements the reference configuration UNet(in_channels=2, out_channels=1, "
                 f"init_features=64); got ({model.in_channels}, {model.out_channels}, {f})")
         m = model
+        # the 1x1 head is `final_conv` in UNet (unet_model.py:80) and `final` in UNetStage (ModelLoader.py:186)
+        self.head = m.final_conv if hasattr(m, "final_conv") else m.final
         chans = [f, 2 * f, 4 * f, 8 * f, 16 * f]
         self.chans = chans
         blocks = [("enc1", m.enc1, 2, chans[0], 0), ("enc2", m.enc2, chans[0], chans[1], 1),
@@ -344,7 +346,7 @@ class UNetEngine:
             conv(c1, cat, 2 * c, 0, plan[f"dec_a1_{lvl}"], c, 0, h, w)
             conv(c2, plan[f"dec_a1_{lvl}"], c, 0, plan[f"dec_a2_{lvl}"], c, 0, h, w)
             cur = plan[f"dec_a2_{lvl}"]
-        fc = self.model.final_conv
+        fc = self.head
         out = torch.empty((B, 1, H, W), dtype=torch.float32, device=x.device)
         call("b200sr_head_fwd", ptr(cur), ptr(fc.weight), ptr(fc.bias), ptr(out), B * H * W, st)
         return out
@@ -408,7 +410,7 @@ class UNetEngine:
             self._conv_bn_train(plan, c1, cat, 2 * c, 0, h, w, plan[f"dec_a1_{lvl}"], c, 0, None)
             self._conv_bn_train(plan, c2, plan[f"dec_a1_{lvl}"], c, 0, h, w, plan[f"dec_a2_{lvl}"], c, 0, None)
             cur = plan[f"dec_a2_{lvl}"]
-        fc = self.model.final_conv
+        fc = self.head
         out = torch.empty((B, 1, H, W), dtype=torch.float32, device=x.device)
         call("b200sr_head_fwd", ptr(cur), ptr(fc.weight), ptr(fc.bias), ptr(out), B * H * W, st)
         bufs = [cs.bn.num_batches_tracked for cs in self.convs if cs.bn.num_batches_tracked is not None]
@@ -437,7 +439,7 @@ class UNetEngine:
     def _G(self, param):
         return self.flat_G.data_ptr() + 4 * self.off_of[id(param)]
 
-    def backward(self, dout, bucket_hook=None):
+    def backward(self, dout, bucket_hook=None, want_dx=False):
         """Full backward of the last train-mode forward. dout: (B,1,H,W) fp32.
         Gradients land in self.flat_g (views: self.grad_views, in model.parameters() order).
         bucket_hook(lo, hi), if given, is called as soon as flat_g[lo:hi] is final (reverse forward order).
@@ -451,6 +453,7 @@ class UNetEngine:
             raise _lib.B200SRError("backward() without a preceding train-mode forward")
         plan, x = self._saved
         B, H, W = plan["B"], plan["H"], plan["W"]
+        self.dx_input = None  # gradient w.r.t. the network input (B,2,H,W) fp32, filled when want_dx
         main = torch.cuda.current_stream()
         st = main.cuda_stream
         overlap = self.overlap_wgrad
@@ -469,7 +472,7 @@ class UNetEngine:
         self.up_stats.zero_()
         s0, s1, s2 = (t.data_ptr() for t in plan["scratch"])
         g = self.flat_g.data_ptr()
-        fc = self.model.final_conv
+        fc = self.head
         ev_i = [0]
 
         def side_after_main():
@@ -518,6 +521,9 @@ class UNetEngine:
             side_after_main()
             if x_input is not None:
                 call("b200sr_conv1_wgrad", ptr(x_input), dz1, g + 4 * self.off_of[id(c1.conv.weight)], B, h, w, sst)
+                if want_dx:
+                    self.dx_input = torch.empty((B, 2, h, w), dtype=torch.float32, device=x_input.device)
+                    call("b200sr_conv1_dgrad", dz1, ptr(c1.conv.weight), ptr(self.dx_input), B, h, w, st)
                 return None
             call("b200sr_conv3x3_wgrad", ptr(in_buf), in_stride, 0, in_c, dz1, c, 0, c, B, h, w,
                  self._G(c1.conv.weight), sst)

@@ -56,11 +56,11 @@ class _UNetFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dout):
         engine = ctx.model._get_engine()
-        engine.backward(dout)
+        engine.backward(dout, want_dx=ctx.needs_input_grad[1])
         # hand autograd an independent copy: the flat gradient buffer is reused by the next step
         flat = engine.flat_g.clone()
         grads = [flat[off:off + p.numel()].view(p.shape) for p, off in zip(engine._params(), engine.p_off)]
-        return (None, None, *grads)
+        return (None, engine.dx_input, *grads)
 
 
 class UNet(nn.Module):

@@ -33,3 +33,16 @@ def seeded_batch(B, H, W, seed=1234):
 TRAIN_CASE = dict(B=2, H=128, W=256, seed=1234)
 EVAL_CASE = dict(B=1, H=256, W=256, seed=4321)
 GRAD_HEAD = 32  # leading elements of every gradient stored verbatim in the golden file
+
+
+PROGRESSIVE_CASE = dict(B=1, H=128, W=256, seed=2468)
+
+
+def seeded_slices(B, H, W, seed):
+    """(B,5,H,W) correlated slices: a smooth drift over iid noise, each slice z-scored (ModelDataGenerator.py:73-75)."""
+    g = torch.Generator().manual_seed(seed)
+    base = torch.randn(B, 1, H, W, generator=g)
+    drift = torch.randn(B, 1, H, W, generator=g)
+    t = torch.linspace(-1.0, 1.0, 5).view(1, 5, 1, 1)
+    vol = base + 0.5 * t * drift + 0.2 * torch.randn(B, 5, H, W, generator=g)
+    return (vol - vol.mean(dim=(-2, -1), keepdim=True)) / (vol.std(dim=(-2, -1), keepdim=True) + 1e-6)

@@ -135,6 +135,41 @@ def main():
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes")
 
+    # ---------------- Progressive UNet (3-stage chain) ------------------------------------------
+    pout = {}
+    sd_p = cases.seeded_state_dict(ref_loader.ProgressiveUNet, seed=3)
+    sd_pm = cases.seeded_state_dict(b200sr.ProgressiveUNet, seed=3)
+    assert list(sd_p) == list(sd_pm) and all(torch.equal(sd_p[k], sd_pm[k]) for k in sd_p)
+    print(f"ProgressiveUNet state_dict: {len(sd_p)} entries identical (reference vs b200sr)")
+    c = cases.PROGRESSIVE_CASE
+    sl = cases.seeded_slices(c["B"], c["H"], c["W"], c["seed"])
+    pm = ref_loader.ProgressiveUNet()
+    pm.load_state_dict(sd_p)
+    pm.train()
+    p1, p2, p3 = pm(sl)
+    w = unet_oracle.PROGRESSIVE_LOSS_WEIGHTS
+    ploss = sum(wi * torch.nn.functional.mse_loss(p, sl[:, k:k + 1]) for wi, p, k in zip(w, (p1, p2, p3), (1, 2, 3)))
+    ploss.backward()
+    pg = {k: p.grad.detach().clone() for k, p in pm.named_parameters()}
+    o_l, o_p, o_g, _ = unet_oracle.progressive_loss_and_grads(sd_p, sl)
+    worst = max(rel(o_g[k], pg[k]) for k in pg if pg[k].norm() > 1e-7)
+    print(f"progressive: oracle vs reference outputs {max(rel(a, b.detach()) for a, b in zip(o_p, (p1, p2, p3))):.3e}, "
+          f"loss {float(o_l):.8f} vs {ploss.item():.8f}, worst grad rel-L2 {worst:.3e}")
+    assert worst < 1e-4 and abs(float(o_l) - ploss.item()) < 1e-6
+    pout["keys"] = np.array(list(sd_p))
+    pout["loss"] = np.float64(ploss.item())
+    pout["p1"], pout["p2"], pout["p3"] = p1.detach().numpy(), p2.detach().numpy(), p3.detach().numpy()
+    pnames = list(pg)
+    pout["grad_names"] = np.array(pnames)
+    pout["grad_norms"] = np.array([pg[k].double().norm().item() for k in pnames])
+    pm.eval()
+    with torch.no_grad():
+        e1, e2, e3 = pm(sl)
+    pout["eval_p1"], pout["eval_p2"], pout["eval_p3"] = e1.numpy(), e2.numpy(), e3.numpy()
+    ppath = os.path.join(ROOT, "tests", "golden", "progressive_golden.npz")
+    np.savez_compressed(ppath, **pout)
+    print("wrote", ppath, os.path.getsize(ppath), "bytes")
+
 
 if __name__ == "__main__":
     main()

@@ -21,7 +21,8 @@ DECODERS = (("upconv4", "dec4"), ("upconv3", "dec3"), ("upconv2", "dec2"), ("upc
 
 def _block(sd, prefix, x, training, new_stats):
     for conv_i, bn_i in ((0, 1), (3, 4)):
-        x = F.conv2d(x, sd[f"{prefix}.conv.{conv_i}.weight"], sd[f"{prefix}.conv.{conv_i}.bias"], padding=1)
+        # conv bias is present in UNetBlock (unet_model.py:27,30) and absent in ProgressiveUNetBlock (ModelLoader.py:38,41)
+        x = F.conv2d(x, sd[f"{prefix}.conv.{conv_i}.weight"], sd.get(f"{prefix}.conv.{conv_i}.bias"), padding=1)
         g, b = sd[f"{prefix}.conv.{bn_i}.weight"], sd[f"{prefix}.conv.{bn_i}.bias"]
         rm, rv = sd[f"{prefix}.conv.{bn_i}.running_mean"], sd[f"{prefix}.conv.{bn_i}.running_var"]
         if training:
@@ -37,20 +38,45 @@ def _block(sd, prefix, x, training, new_stats):
     return x
 
 
-def unet_forward(sd, x, training=False, new_stats=None):
+def unet_forward(sd, x, training=False, new_stats=None, prefix="", head="final_conv"):
     """sd: state_dict-like mapping; x: (B,2,H,W). Returns (B,1,H,W). If training, BatchNorm uses batch statistics
-    and `new_stats` (dict) receives the updated running statistics."""
+    and `new_stats` (dict) receives the updated running statistics. `prefix` / `head` select a UNetStage inside a
+    ProgressiveUNet state_dict (e.g. prefix="unet1.", head="final", ModelLoader.py:148-226)."""
     skips = []
     for name in ENCODERS:
-        x = _block(sd, name, x, training, new_stats)
+        x = _block(sd, prefix + name, x, training, new_stats)
         skips.append(x)
         x = F.max_pool2d(x, kernel_size=2, stride=2)
-    x = _block(sd, "bottleneck", x, training, new_stats)
+    x = _block(sd, prefix + "bottleneck", x, training, new_stats)
     for (up, dec), skip in zip(DECODERS, reversed(skips)):
-        x = F.conv_transpose2d(x, sd[f"{up}.weight"], sd[f"{up}.bias"], stride=2)
+        x = F.conv_transpose2d(x, sd[f"{prefix}{up}.weight"], sd[f"{prefix}{up}.bias"], stride=2)
         x = torch.cat([x, skip], dim=1)
-        x = _block(sd, dec, x, training, new_stats)
-    return F.conv2d(x, sd["final_conv.weight"], sd["final_conv.bias"])
+        x = _block(sd, prefix + dec, x, training, new_stats)
+    return F.conv2d(x, sd[f"{prefix}{head}.weight"], sd[f"{prefix}{head}.bias"])
+
+
+PROGRESSIVE_LOSS_WEIGHTS = (0.5, 1.0, 0.5)  # results/progressive_unet_history.json config.loss_weights
+
+
+def progressive_forward(sd, slices, training=False, new_stats=None):
+    """ProgressiveUNet.forward (ModelLoader.py:246-269): slices (B,5,H,W) -> (pred_i+1, pred_i+2, pred_i+3); the stage-1
+    prediction feeds stages 2A/2B without detach."""
+    i, i4 = slices[:, 0:1], slices[:, 4:5]
+    p2 = unet_forward(sd, torch.cat([i, i4], dim=1), training, new_stats, "unet1.", "final")
+    p1 = unet_forward(sd, torch.cat([i, p2], dim=1), training, new_stats, "unet2.", "final")
+    p3 = unet_forward(sd, torch.cat([p2, i4], dim=1), training, new_stats, "unet3.", "final")
+    return p1, p2, p3
+
+
+def progressive_loss_and_grads(sd, slices, weights=PROGRESSIVE_LOSS_WEIGHTS):
+    """Multi-scale MSE of the 3-stage chain and all parameter gradients (train mode)."""
+    names = param_names(sd)
+    leaf = {k: (v.detach().clone().requires_grad_(True) if k in set(names) else v) for k, v in sd.items()}
+    new_stats = {}
+    p1, p2, p3 = progressive_forward(leaf, slices, True, new_stats)
+    loss = sum(w * F.mse_loss(p, slices[:, k:k + 1]) for w, p, k in zip(weights, (p1, p2, p3), (1, 2, 3)))
+    grads = torch.autograd.grad(loss, [leaf[k] for k in names])
+    return loss.detach(), (p1.detach(), p2.detach(), p3.detach()), dict(zip(names, grads)), new_stats
 
 
 def param_names(sd):

@@ -196,6 +196,17 @@ def conv1(B=2, H=32, W=48, seed=7):
     return res
 
 
+def conv1_dgrad(B=2, H=32, W=48, seed=15):
+    _setup()
+    w = rnd(64, 2, 3, 3, seed=seed, scale=18 ** -0.5)
+    dz = bf(rnd(B, 64, H, W, seed=seed + 1))
+    ref = F.conv_transpose2d(dz, w, padding=1)  # data gradient of Conv2d(2,64,3,p=1)
+    dx = torch.zeros(B, 2, H, W, device=DEV)
+    call("b200sr_conv1_dgrad", ptr(nhwc(dz)), ptr(w), ptr(dx), B, H, W, st())
+    torch.cuda.synchronize()
+    return {"dx": rel(dx, ref)}
+
+
 def bn_train(B=2, H=16, W=32, C=128, pool=True, seed=8):
     """bn_finalize + bnrelu_apply(+pool) against F.batch_norm + relu + max_pool2d."""
     _setup()
@@ -418,6 +429,7 @@ CHECKS = {
     "convT_wgrad": (convT_wgrad, {}, {"dw": BF16}),
     "convT_wgrad_big": (convT_wgrad, dict(Cin=512, Cout=256, B=1, H=8, W=16), {"dw": BF16}),
     "conv1": (conv1, {}, {"out": BF16, "stats_sum": 1e-3, "stats_sq": 1e-3, "dw": 1e-3}),
+    "conv1_dgrad": (conv1_dgrad, {}, {"dx": 1e-5}),
     "bn_train_pool": (bn_train, {}, {"act": BF16, "running_mean": 1e-5, "running_var": 1e-4, "pool_exact": 0.0,
                                      "maxpool_fwd_exact": 0.0, "slot_untouched": 0.0, "fused_act_exact": 0.0,
                                      "fused_ws_exact": 0.0, "fused_running_exact": 0.0, "fused_pool_exact": 0.0}),
