@@ -167,6 +167,13 @@ int b200sr_bn_bwd_apply(const void* dy, int dy_pix_stride, int dy_c_off, const v
                         const float* scale, const float* shift, const float* mean, const float* invstd,
                         const float* c1, const float* c2, void* dz, int64_t npix, void* stream);
 
+/* ---- perceptual (VGG feature) loss helpers: README.md:82-86 "MSE + perceptual (VGG) + SSIM"; SURVEY §8(f) row 2 ---- */
+/* ReLU backward on bf16 tensors of n elements (n % 8 == 0): out = dy * [act > 0]. */
+int b200sr_relu_bwd(const void* dy, const void* act, void* out, int64_t n, void* stream);
+/* sums[0] (DEVICE double) += sum (fp-ft)^2 over n bf16 elements; grad (nullable) = gscale*(fp-ft)*[fp > 0]. */
+int b200sr_feat_mse_grad(const void* fp, const void* ft, void* grad, double* sums, float gscale, int64_t n,
+                         void* stream);
+
 /* final nn.Conv2d(64,1,1) (unet_model.py:80,117): fp32 (B,1,H,W) output; and its backward. */
 int b200sr_head_fwd(const void* act, const float* w, const float* b, float* out, int64_t npix, void* stream);
 int b200sr_head_bwd(const float* dout, const void* act, const float* w, void* dact, float* dw, float* db,

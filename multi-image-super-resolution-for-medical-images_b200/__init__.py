@@ -10,6 +10,7 @@ through the `b200sr` shim module at the repository root:  `import b200sr`.
 from ._lib import B200SRError, EXPORTED_SYMBOLS, LIB_PATH  # noqa: F401
 from .unet_model import UNet, UNetBlock, UNetTrainer, MRIDataset, create_dummy_dataset  # noqa: F401
 from .losses import CombinedLoss, ssim_window  # noqa: F401
+from .perceptual import PerceptualLoss, VGG16Features  # noqa: F401
 from .ModelLoader import load_model  # noqa: F401
 from .progressive import ProgressiveUNet, ProgressiveUNetBlock, ProgressiveUNetTrainer, UNetStage  # noqa: F401
 from .data import DevicePrefetcher, SyntheticTripletGenerator  # noqa: F401

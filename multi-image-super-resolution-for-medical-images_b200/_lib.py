@@ -46,6 +46,8 @@ _SIGNATURES = {
     "b200sr_bn_bwd_reduce": [_P, c_int, c_int, _P, c_int, _P, _P, _P, _P, _P, c_int, c_int64, _P],
     "b200sr_bn_bwd_finalize": [_P, c_int, c_int, c_double, _P, _P, _P, _P, _P],
     "b200sr_bn_bwd_apply": [_P, c_int, c_int, _P, c_int, _P, _P, _P, _P, _P, _P, _P, c_int64, _P],
+    "b200sr_relu_bwd": [_P, _P, _P, c_int64, _P],
+    "b200sr_feat_mse_grad": [_P, _P, _P, _P, c_float, c_int64, _P],
     "b200sr_head_fwd": [_P, _P, _P, _P, c_int64, _P],
     "b200sr_head_bwd": [_P, _P, _P, _P, _P, _P, c_int64, _P],
     "b200sr_mse_ssim": [_P, _P, _P, _P, c_int, c_int, c_int, _P, c_int, c_float, c_float, c_float, c_float, c_float,
@@ -122,6 +124,10 @@ def _cost(name, a):
         return 0.0, a[11] * a[4] * 2.0 * 2
     if name == "b200sr_bn_bwd_apply":
         return 0.0, a[12] * a[4] * 2.0 * 3
+    if name == "b200sr_relu_bwd":
+        return 0.0, a[3] * 2.0 * 3
+    if name == "b200sr_feat_mse_grad":
+        return 0.0, a[5] * 2.0 * (3 if a[2] else 2)
     if name == "b200sr_head_fwd":
         return 0.0, a[4] * (128.0 + 4)
     if name == "b200sr_head_bwd":

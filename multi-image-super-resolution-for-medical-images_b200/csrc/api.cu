@@ -848,6 +848,24 @@ int b200sr_bn_bwd_apply(const void* dy, int dy_pix_stride, int dy_c_off, const v
     return check_launch("bn_bwd_apply_kernel");
 }
 
+int b200sr_relu_bwd(const void* dy, const void* act, void* out, int64_t n, void* stream) {
+    B2_CHECK_ARG(dy && act && out && n > 0 && n % 8 == 0 && aligned16(dy) && aligned16(act) && aligned16(out));
+    relu_bwd_kernel<<<grid_for(n / 8, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(act), static_cast<__nv_bfloat16*>(out),
+        n / 8);
+    return check_launch("relu_bwd_kernel");
+}
+
+int b200sr_feat_mse_grad(const void* fp, const void* ft, void* grad, double* sums, float gscale, int64_t n,
+                         void* stream) {
+    B2_CHECK_ARG(fp && ft && sums && n > 0 && n % 8 == 0 && aligned16(fp) && aligned16(ft));
+    B2_CHECK_ARG(grad == nullptr || aligned16(grad));
+    feat_mse_grad_kernel<<<grid_for(n / 8, 256, 148 * 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16*>(fp), static_cast<const __nv_bfloat16*>(ft), static_cast<__nv_bfloat16*>(grad),
+        sums, gscale, n / 8);
+    return check_launch("feat_mse_grad_kernel");
+}
+
 int b200sr_head_fwd(const void* act, const float* w, const float* b, float* out, int64_t npix, void* stream) {
     B2_CHECK_ARG(act && w && b && out && npix > 0 && aligned16(act) && aligned16(w));
     head_fwd_kernel<<<grid_for(npix * 8, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(

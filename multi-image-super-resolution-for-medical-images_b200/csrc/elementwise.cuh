@@ -956,6 +956,54 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const __nv_bfloat16* 
 }
 
 // ------------------------------------------------------------------------------------------------
+// Perceptual (VGG feature) loss helpers — SURVEY §8(f) row 2. Frozen conv+bias+ReLU stacks have no BatchNorm, so
+// their backward only needs the ReLU mask of the stored activation:  out = dy * [act > 0]   (bf16, 8 per thread)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) relu_bwd_kernel(const __nv_bfloat16* __restrict__ dy,
+                                                       const __nv_bfloat16* __restrict__ act,
+                                                       __nv_bfloat16* __restrict__ out, long long n8) {
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n8;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const F8 g = unpack8(ld_stream(dy + i * 8)), a = unpack8(ld_stream(act + i * 8));
+        F8 o;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o.v[k] = a.v[k] > 0.f ? g.v[k] : 0.f;
+        st_bf16x8(out + i * 8, o);
+    }
+}
+
+// Feature-space MSE between two post-ReLU feature maps and its gradient w.r.t. the first one, already multiplied by
+// that layer's ReLU mask:  sums[0] += sum (fp - ft)^2 ;  g = gscale * (fp - ft) * [fp > 0]
+__global__ void __launch_bounds__(256) feat_mse_grad_kernel(const __nv_bfloat16* __restrict__ fp,
+                                                            const __nv_bfloat16* __restrict__ ft,
+                                                            __nv_bfloat16* __restrict__ g, double* __restrict__ sums,
+                                                            float gscale, long long n8) {
+    float part = 0.f;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n8;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const F8 a = unpack8(ld_stream(fp + i * 8)), b = unpack8(ld_stream(ft + i * 8));
+        F8 o;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const float d = a.v[k] - b.v[k];
+            part = fmaf(d, d, part);
+            o.v[k] = a.v[k] > 0.f ? gscale * d : 0.f;
+        }
+        if (g != nullptr) st_bf16x8(g + i * 8, o);
+    }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    __shared__ float s_red[8];
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = part;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double acc = 0.0;
+        for (int w = 0; w < 8; ++w) acc += s_red[w];
+        atomicAdd(sums, acc);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // 1x1 head: Conv2d(64 -> 1) + bias (unet_model.py:80,117). fp32 output in NCHW (C=1 => same as NHW).
 // 8 threads per pixel (one uint4 each), shuffle reduce.
 // ------------------------------------------------------------------------------------------------

@@ -176,10 +176,11 @@ class UNetTrainer:
 
     def __init__(self, model, device='cuda' if torch.cuda.is_available() else 'cpu', learning_rate=1e-4,
                  model_save_dir='models', loss='mse', ssim_weight=0.005, ssim_mode='gaussian', data_range=1.0,
-                 verbose=True, use_cuda_graph=False):
+                 verbose=True, use_cuda_graph=False, perceptual_weight=0.01, vgg_weights=None):
         from .losses import CombinedLoss
         self.model = model.to(device)
         self.device = device
+        self.perceptual = None
         from .optim import FlatAdam
         self.optimizer = FlatAdam(self.model, lr=learning_rate)
         if loss == 'mse':
@@ -187,8 +188,17 @@ class UNetTrainer:
         elif loss == 'combined':
             self.criterion = CombinedLoss(mse_weight=1.0, ssim_weight=ssim_weight, mode=ssim_mode,
                                           data_range=data_range)
+        elif loss == 'combined_perceptual':
+            # the full combined loss of README.md:82-86: MSE + perceptual (VGG16) + SSIM
+            from .perceptual import PerceptualLoss, VGG16Features
+            self.criterion = CombinedLoss(mse_weight=1.0, ssim_weight=ssim_weight, mode=ssim_mode,
+                                          data_range=data_range)
+            vgg = VGG16Features()
+            if vgg_weights is not None:
+                vgg.load_pretrained(vgg_weights)
+            self.perceptual = PerceptualLoss(weight=perceptual_weight, vgg=vgg)
         else:
-            raise ValueError(f"Unknown loss: {loss}. Choose from: ['mse', 'combined']")
+            raise ValueError(f"Unknown loss: {loss}. Choose from: ['mse', 'combined', 'combined_perceptual']")
         self.model_save_dir = Path(model_save_dir)
         self.model_save_dir.mkdir(parents=True, exist_ok=True)
         self.train_losses = []
@@ -218,6 +228,10 @@ class UNetTrainer:
         engine = self.model._get_engine()
         out = engine.forward_train(inputs)
         loss, dout = self.criterion.value_and_grad(out, targets)
+        if self.perceptual is not None:
+            lp, gp = self.perceptual.value_and_grad(out, targets)
+            loss = loss + lp
+            dout = dout + gp
         hook, scale = None, 1.0
         from .ddp import is_distributed
         if is_distributed():

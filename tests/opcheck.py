@@ -339,6 +339,23 @@ def mse_ssim(B=2, H=96, W=80, mode="gaussian", w_ssim=0.5, seed=12):
     return {"loss": abs(float(loss) - float(loss_ref)) / abs(float(loss_ref)), "grad": rel(grad.cpu(), xc.grad)}
 
 
+def perceptual(B=2, H=128, W=128, seed=31):
+    _setup()
+    from oracle import perceptual_oracle
+    y = rnd(B, 1, H, W, seed=seed)
+    x = 0.7 * y + 0.3 * rnd(B, 1, H, W, seed=seed + 1)
+    crit = b200sr.PerceptualLoss(weight=0.01)
+    loss, grad = crit.value_and_grad(x, y)
+    torch.cuda.synchronize()
+    sd = {k: v.detach().cpu().double() for k, v in crit.vgg.state_dict().items()}
+    xc = x.cpu().double().requires_grad_(True)
+    ref = perceptual_oracle.perceptual_loss(sd, xc, y.cpu().double(), 0.01)
+    ref.backward()
+    a, b = grad.cpu().double().flatten(), xc.grad.flatten()
+    return {"loss": abs(float(loss) - float(ref)) / abs(float(ref)), "grad": rel(grad.cpu(), xc.grad),
+            "grad_cos_defect": 1.0 - float((a @ b) / (a.norm() * b.norm()))}
+
+
 def adam(n=100003, seed=13):
     _setup()
     from oracle import unet_oracle
@@ -444,6 +461,10 @@ CHECKS = {
     "mse_ssim_gaussian": (mse_ssim, {}, {"loss": 1e-5, "grad": 1e-4}),
     "mse_ssim_uniform": (mse_ssim, dict(mode="uniform", H=64, W=100), {"loss": 1e-5, "grad": 1e-4}),
     "mse_only": (mse_ssim, dict(w_ssim=0.0), {"loss": 1e-5, "grad": 1e-5}),
+    # 7 stacked bf16 conv layers forward + 7 backward through a random-init VGG on noise: the loss is within 1e-2
+    # (measured 8e-4); the input gradient is ReLU-mask sensitive like the UNet's own deep gradients (measured
+    # rel-L2 8.6e-2, cosine 0.996 vs the fp64 oracle)
+    "perceptual_vgg": (perceptual, {}, {"loss": 1e-2, "grad": 0.15, "grad_cos_defect": 1e-2}),
     "adam": (adam, {}, {"delta": 1e-3,  # fp32 rounding of p (~1) against a 1e-4 update
               "m": 1e-5, "v": 1e-4}),
     "layout_casts": (layout_casts, {}, {"fwd_exact": 0.0, "back_exact": 0.0}),

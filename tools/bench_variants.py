@@ -1,0 +1,46 @@
+"""Train-step throughput of the workload variants beyond the headline (B=32/GPU, 256x256, one GPU):
+   combined_perceptual (MSE + VGG16 perceptual + SSIM: the full BASELINE configs[2]) and the Progressive UNet chain."""
+import os, sys, json
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+import b200sr
+from oracle import cases
+
+B = int(os.environ.get("B", "32"))
+dev = "cuda"
+
+
+def timed(fn, steps=10, warmup=3):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
+out = {}
+which = sys.argv[1:] or ["perceptual", "progressive"]
+if "perceptual" in which:
+    model = b200sr.UNet()
+    model.load_state_dict(cases.seeded_state_dict(b200sr.UNet))
+    tr = b200sr.UNetTrainer(model, device=dev, loss="combined_perceptual", model_save_dir="/tmp/b200sr_v", verbose=False)
+    gen = b200sr.SyntheticTripletGenerator(B, 256, 256, device=dev, seed=1)
+    x, y = gen.next()
+    ms = timed(lambda: tr.train_step(x, y))
+    out["unet_combined_perceptual"] = {"ms_per_step": ms, "triplets_per_s": B / ms * 1e3}
+    del tr, model
+    torch.cuda.empty_cache()
+if "progressive" in which:
+    pm = b200sr.ProgressiveUNet()
+    ptr_ = b200sr.ProgressiveUNetTrainer(pm, device=dev, model_save_dir="/tmp/b200sr_v", verbose=False)
+    sl = cases.seeded_slices(B, 256, 256, 5).to(dev)
+    ms = timed(lambda: ptr_.train_step(sl), steps=6, warmup=2)
+    out["progressive_unet_3stage"] = {"ms_per_step": ms, "windows_per_s": B / ms * 1e3,
+                                      "tflops": 3 * 288.627 * B / ms}
+print(json.dumps(out))
