@@ -91,6 +91,8 @@ class UNetEngine:
         self._events = []
         import os
         self.overlap_wgrad = os.environ.get("B200SR_NO_OVERLAP") is None
+        self.hp_chain = os.environ.get("B200SR_HP") is not None
+        self._hp = None
 
     # ------------------------------------------------------------------------------------------------
     # parameter flattening and derived operand buffers
@@ -189,6 +191,14 @@ class UNetEngine:
             off = self.off_of[id(w)]
             unpack[j] = (G_base + 4 * off, g_base + 4 * off, UNPACK_CONVT_WGRAD, us.cout, us.cin, 0, n)
             j += 1
+        # three contiguous groups so the train step can stage the packing: forward packings of enc1/enc2 (needed
+        # first, tiny), forward packings of everything else, then all dgrad packings (needed only in backward)
+        is_fwd = (pack["kind"] == PACK_CONV_FWD) | (pack["kind"] == PACK_CONVT_FWD)
+        early_dst = {wp_base + 2 * self.wp_fwd[cs.name] for cs in self.convs[1:4]}
+        early = np.array([int(d) in early_dst for d in pack["dst"]])
+        order = np.concatenate([np.nonzero(is_fwd & early)[0], np.nonzero(is_fwd & ~early)[0], np.nonzero(~is_fwd)[0]])
+        pack = pack[order]
+        self.pack_groups = (int((is_fwd & early).sum()), int((is_fwd & ~early).sum()), int((~is_fwd).sum()))
         self.pack_jobs = _jobs_to_device(pack, device)
         self.n_pack = len(pack)
         # unpack jobs sorted by flat offset so that suffix ranges (= gradient buckets) are contiguous job ranges
@@ -247,6 +257,29 @@ class UNetEngine:
 
     def repack_weights(self):
         call("b200sr_pack_jobs", self.pack_jobs.data_ptr(), self.n_pack, _lib.current_stream_ptr())
+
+    def _repack_staged(self):
+        """Train step: pack what enc1/enc2 need on the current stream, the rest on the side stream, overlapping
+        the first layers. Returns the event the forward must wait on before enc3; the dgrad packings are joined at
+        the start of backward (self._pack_done)."""
+        main = torch.cuda.current_stream()
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.device)
+        n0, n1, n2 = self.pack_groups
+        isz = _PACK_JOB_DTYPE.itemsize
+        base = self.pack_jobs.data_ptr()
+        fork = torch.cuda.Event()
+        fork.record(main)  # parameters are final (Adam of the previous step) at this point of the main stream
+        self._side.wait_event(fork)
+        call("b200sr_pack_jobs", base, n0, main.cuda_stream)
+        sst = self._side.cuda_stream
+        call("b200sr_pack_jobs", base + n0 * isz, n1, sst)
+        fwd_done = torch.cuda.Event()
+        fwd_done.record(self._side)
+        call("b200sr_pack_jobs", base + (n0 + n1) * isz, n2, sst)
+        self._pack_done = torch.cuda.Event()
+        self._pack_done.record(self._side)
+        return fwd_done
 
     # ------------------------------------------------------------------------------------------------
     # activation plans
@@ -380,7 +413,12 @@ class UNetEngine:
         B, _, H, W = x.shape
         plan = self._plan(B, H, W, True)
         st = _lib.current_stream_ptr()
-        self.repack_weights()
+        fwd_packed = None
+        if self.overlap_wgrad:
+            fwd_packed = self._repack_staged()
+        else:
+            self.repack_weights()
+            self._pack_done = None
         self.bn_stats.zero_()
         ch = self.chans
         cur = None
@@ -388,6 +426,8 @@ class UNetEngine:
             c1, c2 = self.blocks[name]
             h, w, c = H >> lvl, W >> lvl, ch[lvl]
             a1, cat, pool = plan[f"enc_a1_{lvl}"], plan[f"cat{lvl}"], plan[f"pool{lvl}"]
+            if lvl == 2 and fwd_packed is not None:
+                torch.cuda.current_stream().wait_event(fwd_packed)  # forward packings of enc3.. are ready
             if lvl == 0:
                 self._conv_bn_train(plan, c1, None, 0, 0, h, w, a1, c, 0, None, x_input=x)
             else:
@@ -440,6 +480,21 @@ class UNetEngine:
         return self.flat_G.data_ptr() + 4 * self.off_of[id(param)]
 
     def backward(self, dout, bucket_hook=None, want_dx=False):
+        """See _backward. With overlap enabled the data-gradient chain runs on a HIGH-priority stream and the weight
+        gradients on a default (lowest) priority stream: the chain is the critical path, the wgrad kernels only fill
+        the SMs it leaves idle (during the bandwidth-bound BatchNorm / pooling kernels)."""
+        if not (self.overlap_wgrad and self.hp_chain):
+            return self._backward(dout, bucket_hook, want_dx)
+        cur = torch.cuda.current_stream()
+        if self._hp is None:
+            self._hp = torch.cuda.Stream(device=self.device, priority=-1)
+        self._hp.wait_stream(cur)
+        with torch.cuda.stream(self._hp):
+            out = self._backward(dout, bucket_hook, want_dx)
+        cur.wait_stream(self._hp)
+        return out
+
+    def _backward(self, dout, bucket_hook=None, want_dx=False):
         """Full backward of the last train-mode forward. dout: (B,1,H,W) fp32.
         Gradients land in self.flat_g (views: self.grad_views, in model.parameters() order).
         bucket_hook(lo, hi), if given, is called as soon as flat_g[lo:hi] is final (reverse forward order).
@@ -455,6 +510,9 @@ class UNetEngine:
         B, H, W = plan["B"], plan["H"], plan["W"]
         self.dx_input = None  # gradient w.r.t. the network input (B,2,H,W) fp32, filled when want_dx
         main = torch.cuda.current_stream()
+        if getattr(self, "_pack_done", None) is not None:
+            main.wait_event(self._pack_done)  # dgrad packings were produced on the side stream during forward
+            self._pack_done = None
         st = main.cuda_stream
         overlap = self.overlap_wgrad
         if overlap:
