@@ -88,7 +88,8 @@ int b200sr_convT2x2_wgrad(const void* dup, int dup_pix_stride, int dup_c_off, in
 typedef struct b200sr_pack_job {
     const void* src;
     void* dst;
-    int32_t kind; /* 0 conv fwd, 1 conv dgrad, 2 convT fwd, 3 convT dgrad, 4 conv wgrad unpack, 5 convT wgrad unpack */
+    int32_t kind; /* 0 conv fwd, 1 conv dgrad, 2 convT fwd, 3 convT dgrad, 4 conv wgrad unpack, 5 convT wgrad unpack,
+                     6 conv1x1 fwd, 7 conv1x1 dgrad, 8 conv1x1 wgrad unpack */
     int32_t cout;
     int32_t cin;
     int32_t pad;
@@ -173,6 +174,37 @@ int b200sr_relu_bwd(const void* dy, const void* act, void* out, int64_t n, void*
 /* sums[0] (DEVICE double) += sum (fp-ft)^2 over n bf16 elements; grad (nullable) = gscale*(fp-ft)*[fp > 0]. */
 int b200sr_feat_mse_grad(const void* fp, const void* ft, void* grad, double* sums, float gscale, int64_t n,
                          void* stream);
+
+/* ---- DeepCNN residual baseline (reference src/ModelLoader.py:276-377; SURVEY §8(f) row 3, BASELINE configs[1]) ---- */
+/* Conv2d(2,64,7,padding=3,bias=False) (:324) from the fp32 NCHW input; out (B,H,W,64) bf16; optional BN statistics. */
+int b200sr_conv7_fwd(const float* x, const float* w, void* out, float* stats, int stats_replicas, int B, int H, int W,
+                     void* stream);
+/* dW (64,2,7,7) f32, ADDED into. */
+int b200sr_conv7_wgrad(const float* x, const void* dz, float* dw, int B, int H, int W, void* stream);
+/* nn.MaxPool2d(3, stride=1, padding=1) (:327) on dense NHWC bf16; backward routes to the first maximum (ATen). */
+int b200sr_maxpool3x3_fwd(const void* in, void* out, int C, int B, int H, int W, void* stream);
+int b200sr_maxpool3x3_bwd(const void* in, const void* dout, void* din, int C, int B, int H, int W, void* stream);
+/* ResidualBlock tail (:290-307): out = relu(scale2*z2+shift2 + identity); identity = x (scale_d NULL) or
+ * scale_d*z_d+shift_d (1x1 downsample + BatchNorm branch). Dense NHWC bf16, C/8 divides 256. */
+int b200sr_bn_add_relu(const void* z2, const float* scale2, const float* shift2, const void* identity,
+                       const float* scale_d, const float* shift_d, void* out, int C, int64_t npix, void* stream);
+/* BatchNorm backward (reduce + finalize + apply) where the ReLU mask comes from a stored activation (mask_src > 0)
+ * instead of scale*z+shift > 0: the ReLU of a residual block follows the skip addition. Dense tensors. */
+int b200sr_bn_bwd_masked(const void* dy, const void* z, const void* mask_src, int C, const float* scale,
+                         const float* shift, const float* mean, const float* invstd, float* sums, int replicas,
+                         double count, float* dgamma, float* dbeta, void* dz, int64_t npix, void* stream);
+/* out = a + b*[mask > 0] (mask NULL: a + b); n bf16 elements, n % 8 == 0. Gradient join of a residual block. */
+int b200sr_add_masked(const void* a, const void* b, const void* mask, void* out, int64_t n, void* stream);
+/* output_conv Conv2d(512,1,1)+bias (:336,375): fp32 (B,1,H,W) output, and its backward. C must be 512. */
+int b200sr_headw_fwd(const void* act, int C, const float* w, const float* b, float* out, int64_t npix, void* stream);
+int b200sr_headw_bwd(const float* dout, const void* act, int C, const float* w, void* dact, float* dw, float* db,
+                     int64_t npix, void* stream);
+/* Conv2d 1x1 (downsample branch, :347-351) forward and dgrad: D[pixel,n] = sum_c A[pixel,c]*Wp[n,c]; Wp from
+ * b200sr_pack_jobs kind 6 (forward) / 7 (dgrad); wgrad into G[ci][co] (unpack kind 8). */
+int b200sr_conv1x1(const void* a, int a_pix_stride, int a_c_off, int Ca, const void* w_packed, int N, int B, int H,
+                   int W, void* out, int out_pix_stride, int out_c_off, float* stats, int stats_replicas, void* stream);
+int b200sr_conv1x1_wgrad(const void* x, int x_pix_stride, int x_c_off, int Cin, const void* dz, int dz_pix_stride,
+                         int dz_c_off, int Cout, int B, int H, int W, float* G, void* stream);
 
 /* final nn.Conv2d(64,1,1) (unet_model.py:80,117): fp32 (B,1,H,W) output; and its backward. */
 int b200sr_head_fwd(const void* act, const float* w, const float* b, float* out, int64_t npix, void* stream);

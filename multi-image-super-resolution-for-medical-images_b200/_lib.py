@@ -48,6 +48,17 @@ _SIGNATURES = {
     "b200sr_bn_bwd_apply": [_P, c_int, c_int, _P, c_int, _P, _P, _P, _P, _P, _P, _P, c_int64, _P],
     "b200sr_relu_bwd": [_P, _P, _P, c_int64, _P],
     "b200sr_feat_mse_grad": [_P, _P, _P, _P, c_float, c_int64, _P],
+    "b200sr_conv7_fwd": [_P, _P, _P, _P, c_int, c_int, c_int, c_int, _P],
+    "b200sr_conv7_wgrad": [_P, _P, _P, c_int, c_int, c_int, _P],
+    "b200sr_maxpool3x3_fwd": [_P, _P, c_int, c_int, c_int, c_int, _P],
+    "b200sr_maxpool3x3_bwd": [_P, _P, _P, c_int, c_int, c_int, c_int, _P],
+    "b200sr_bn_add_relu": [_P, _P, _P, _P, _P, _P, _P, c_int, c_int64, _P],
+    "b200sr_bn_bwd_masked": [_P, _P, _P, c_int, _P, _P, _P, _P, _P, c_int, c_double, _P, _P, _P, c_int64, _P],
+    "b200sr_add_masked": [_P, _P, _P, _P, c_int64, _P],
+    "b200sr_headw_fwd": [_P, c_int, _P, _P, _P, c_int64, _P],
+    "b200sr_headw_bwd": [_P, _P, c_int, _P, _P, _P, _P, c_int64, _P],
+    "b200sr_conv1x1": [_P, c_int, c_int, c_int, _P, c_int, c_int, c_int, c_int, _P, c_int, c_int, _P, c_int, _P],
+    "b200sr_conv1x1_wgrad": [_P, c_int, c_int, c_int, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P],
     "b200sr_head_fwd": [_P, _P, _P, _P, c_int64, _P],
     "b200sr_head_bwd": [_P, _P, _P, _P, _P, _P, c_int64, _P],
     "b200sr_mse_ssim": [_P, _P, _P, _P, c_int, c_int, c_int, _P, c_int, c_float, c_float, c_float, c_float, c_float,
@@ -92,7 +103,7 @@ def last_error() -> str:
 # ---- launch accounting and optional per-call CUDA-event timing (used by bench.py for the roofline) ------------
 LAUNCH_COUNTER = {"n": 0}
 GEMM_OPS = ("b200sr_conv3x3_fwd", "b200sr_conv3x3_dgrad", "b200sr_conv3x3_wgrad", "b200sr_convT2x2_fwd",
-            "b200sr_convT2x2_dgrad", "b200sr_convT2x2_wgrad")
+            "b200sr_convT2x2_dgrad", "b200sr_convT2x2_wgrad", "b200sr_conv1x1", "b200sr_conv1x1_wgrad")
 _profile = None  # list of (name, start_event, end_event, flop, bytes) while profiling is enabled
 
 
@@ -108,6 +119,10 @@ def _cost(name, a):
         return 2.0 * a[8] * a[9] * a[10] * a[3] * a[7] * 9, 0.0
     if name == "b200sr_convT2x2_wgrad":
         return 2.0 * a[8] * a[9] * a[10] * a[3] * a[7] * 4, 0.0
+    if name == "b200sr_conv1x1":
+        return 2.0 * a[6] * a[7] * a[8] * a[3] * a[5], 0.0
+    if name == "b200sr_conv1x1_wgrad":
+        return 2.0 * a[8] * a[9] * a[10] * a[3] * a[7], 0.0
     if name == "b200sr_bnrelu_apply":
         n = a[8] * a[9] * a[10] * a[1] * 2.0
         return 0.0, n * (2.25 if a[7] else 2.0)

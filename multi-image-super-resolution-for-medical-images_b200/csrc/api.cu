@@ -9,6 +9,7 @@
 
 #include "elementwise.cuh"
 #include "conv3x3.cuh"
+#include "deepcnn.cuh"
 #include "igemm.cuh"
 #include "loss.cuh"
 #include "wgrad.cuh"
@@ -336,12 +337,12 @@ int run_conv3(int mode, const void* a, int a_stride, int a_coff, int Ca, const v
     int rc;
     if (mode == 0)
         rc = make_act_map(&ma, a, a_stride, a_coff, Ca, B, H, W, C3_TILE_W, C3_TILE_H + 2);
-    else if (mode == 1)
+    else if (mode == 1 || mode == 3)
         rc = make_act_map(&ma, a, a_stride, a_coff, Ca, B, H, W, C3_TILE_W, C3_TILE_H);
     else
         rc = make_gather_map(&ma, a, a_stride, a_coff, Ca, B, H, W, C3_TILE_W, C3_TILE_H);
     if (rc) return rc;
-    const int taps = mode == 0 ? 9 : (mode == 1 ? 1 : 4);
+    const int taps = mode == 0 ? 9 : (mode == 2 ? 4 : 1);
     rc = make_weight_map(&mb, w_packed, taps * Ca, n_total, block_n < 128 ? block_n : 128);
     if (rc) return rc;
     // output tile store: 128 pixels x 64 channels per TMA store; mode 1 scatters through the sub-pixel view
@@ -387,6 +388,7 @@ int run_conv3(int mode, const void* a, int a_stride, int a_coff, int Ca, const v
     if (grid > args.num_tiles) grid = args.num_tiles;
     if (mode == 0) return dispatch_conv3<0>(block_n, ma, mb, mo, args, grid, st);
     if (mode == 1) return dispatch_conv3<1>(block_n, ma, mb, mo, args, grid, st);
+    if (mode == 3) return dispatch_conv3<3>(block_n, ma, mb, mo, args, grid, st);
     return dispatch_conv3<2>(block_n, ma, mb, mo, args, grid, st);
 }
 
@@ -771,8 +773,121 @@ int b200sr_bn_bwd_apply_fused(const void* dy, int dy_pix_stride, int dy_c_off, c
     bn_bwd_apply_fused_kernel<<<static_cast<int>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         static_cast<const __nv_bfloat16*>(dy), dy_pix_stride, dy_c_off, static_cast<const __nv_bfloat16*>(z), C, scale,
         shift, mean, invstd, sums, replicas, static_cast<float>(count), dgamma, dbeta, static_cast<__nv_bfloat16*>(dz),
-        npix);
+        npix, nullptr);
     return check_launch("bn_bwd_apply_fused_kernel");
+}
+
+// ---- DeepCNN residual baseline -------------------------------------------------------------
+int b200sr_bn_bwd_masked(const void* dy, const void* z, const void* mask_src, int C, const float* scale,
+                         const float* shift, const float* mean, const float* invstd, float* sums, int replicas,
+                         double count, float* dgamma, float* dbeta, void* dz, int64_t npix, void* stream) {
+    B2_CHECK_ARG(dy && z && mask_src && scale && shift && mean && invstd && sums && dgamma && dbeta && dz);
+    B2_CHECK_ARG(C % 8 == 0 && npix > 0 && replicas > 0 && count > 0);
+    B2_CHECK_ARG(aligned16(dy) && aligned16(z) && aligned16(dz) && aligned16(mask_src) && aligned16(sums));
+    const int CV = C / 8;
+    B2_CHECK_ARG(CV <= 256 && 256 % CV == 0);
+    const int PB = 256 / CV;
+    long long blocks = (npix + static_cast<long long>(PB) * BNB_UNROLL - 1) / (static_cast<long long>(PB) * BNB_UNROLL);
+    if (blocks > num_sms() * 8) blocks = num_sms() * 8;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    bn_bwd_reduce_fast_kernel<<<static_cast<int>(blocks), 256, 0, st>>>(
+        static_cast<const __nv_bfloat16*>(dy), C, 0, static_cast<const __nv_bfloat16*>(z), C, scale, shift, mean, invstd,
+        sums, replicas, npix, static_cast<const __nv_bfloat16*>(mask_src));
+    bn_bwd_apply_fused_kernel<<<static_cast<int>(blocks), 256, 0, st>>>(
+        static_cast<const __nv_bfloat16*>(dy), C, 0, static_cast<const __nv_bfloat16*>(z), C, scale, shift, mean, invstd,
+        sums, replicas, static_cast<float>(count), dgamma, dbeta, static_cast<__nv_bfloat16*>(dz), npix,
+        static_cast<const __nv_bfloat16*>(mask_src));
+    return check_launch("bn_bwd_masked");
+}
+
+int b200sr_conv7_fwd(const float* x, const float* w, void* out, float* stats, int stats_replicas, int B, int H, int W,
+                     void* stream) {
+    B2_CHECK_ARG(x && w && out && B > 0 && H % C1_TILE == 0 && W % C1_TILE == 0 && aligned16(out));
+    B2_CHECK_ARG(stats == nullptr || stats_replicas > 0);
+    const int tiles = B * (H / C1_TILE) * (W / C1_TILE);
+    const int grid = tiles < num_sms() * 4 ? tiles : num_sms() * 4;
+    conv7_direct_fwd_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        x, w, static_cast<__nv_bfloat16*>(out), stats, stats_replicas > 0 ? stats_replicas : 1, H, W, tiles);
+    return check_launch("conv7_direct_fwd_kernel");
+}
+
+int b200sr_conv7_wgrad(const float* x, const void* dz, float* dw, int B, int H, int W, void* stream) {
+    B2_CHECK_ARG(x && dz && dw && B > 0 && H % C1_TILE == 0 && W % C1_TILE == 0 && aligned16(dz));
+    const int tiles = B * (H / C1_TILE) * (W / C1_TILE);
+    const int grid = tiles < num_sms() * 2 ? tiles : num_sms() * 2;
+    conv7_direct_wgrad_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        x, static_cast<const __nv_bfloat16*>(dz), dw, H, W, tiles);
+    return check_launch("conv7_direct_wgrad_kernel");
+}
+
+int b200sr_maxpool3x3_fwd(const void* in, void* out, int C, int B, int H, int W, void* stream) {
+    B2_CHECK_ARG(in && out && C % 8 == 0 && B > 0 && H > 0 && W > 0 && aligned16(in) && aligned16(out));
+    const long long total = static_cast<long long>(B) * H * W * (C / 8);
+    maxpool3x3_fwd_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16*>(in), static_cast<__nv_bfloat16*>(out), C, H, W, total);
+    return check_launch("maxpool3x3_fwd_kernel");
+}
+
+int b200sr_maxpool3x3_bwd(const void* in, const void* dout, void* din, int C, int B, int H, int W, void* stream) {
+    B2_CHECK_ARG(in && dout && din && C % 8 == 0 && B > 0 && H > 0 && W > 0);
+    const long long total = static_cast<long long>(B) * H * W * (C / 2);
+    maxpool3x3_bwd_kernel<<<grid_for(total, 256, 148 * 32), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16*>(in), static_cast<const __nv_bfloat16*>(dout), static_cast<__nv_bfloat16*>(din),
+        C, H, W, total);
+    return check_launch("maxpool3x3_bwd_kernel");
+}
+
+int b200sr_bn_add_relu(const void* z2, const float* scale2, const float* shift2, const void* identity,
+                       const float* scale_d, const float* shift_d, void* out, int C, int64_t npix, void* stream) {
+    B2_CHECK_ARG(z2 && scale2 && shift2 && identity && out && npix > 0 && (scale_d == nullptr) == (shift_d == nullptr));
+    B2_CHECK_ARG(C % 8 == 0 && C / 8 <= 256 && 256 % (C / 8) == 0);
+    B2_CHECK_ARG(aligned16(z2) && aligned16(identity) && aligned16(out));
+    const int PB = 256 / (C / 8);
+    long long blocks = (npix + PB - 1) / PB;
+    if (blocks > num_sms() * 16) blocks = num_sms() * 16;
+    bn_add_relu_kernel<<<static_cast<int>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16*>(z2), scale2, shift2, static_cast<const __nv_bfloat16*>(identity), scale_d,
+        shift_d, static_cast<__nv_bfloat16*>(out), C, npix);
+    return check_launch("bn_add_relu_kernel");
+}
+
+int b200sr_add_masked(const void* a, const void* b, const void* mask, void* out, int64_t n, void* stream) {
+    B2_CHECK_ARG(a && b && out && n > 0 && n % 8 == 0 && aligned16(a) && aligned16(b) && aligned16(out));
+    add_masked_kernel<<<grid_for(n / 8, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16*>(a), static_cast<const __nv_bfloat16*>(b),
+        static_cast<const __nv_bfloat16*>(mask), static_cast<__nv_bfloat16*>(out), n / 8);
+    return check_launch("add_masked_kernel");
+}
+
+int b200sr_headw_fwd(const void* act, int C, const float* w, const float* b, float* out, int64_t npix, void* stream) {
+    B2_CHECK_ARG(act && w && b && out && npix > 0 && aligned16(act) && C == 512);
+    headw_fwd_kernel<512><<<grid_for(npix * 32, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16*>(act), w, b, out, npix);
+    return check_launch("headw_fwd_kernel");
+}
+
+int b200sr_headw_bwd(const float* dout, const void* act, int C, const float* w, void* dact, float* dw, float* db,
+                     int64_t npix, void* stream) {
+    B2_CHECK_ARG(dout && act && w && dact && dw && db && npix > 0 && aligned16(act) && aligned16(dact) && C == 512);
+    headw_bwd_kernel<512><<<grid_for(npix * 32, 256, 148 * 4), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        dout, static_cast<const __nv_bfloat16*>(act), w, static_cast<__nv_bfloat16*>(dact), dw, db, npix);
+    return check_launch("headw_bwd_kernel");
+}
+
+/* Conv2d 1x1 forward / dgrad: D[pixel, n] = sum_c A[pixel, c] * Wp[n, c] (Wp: PACK_CONV1X1_FWD / _DGRAD) */
+int b200sr_conv1x1(const void* a, int a_pix_stride, int a_c_off, int Ca, const void* w_packed, int N, int B, int H,
+                   int W, void* out, int out_pix_stride, int out_c_off, float* stats, int stats_replicas, void* stream) {
+    if (H % C3_TILE_H == 0 && W % C3_TILE_W == 0)
+        return run_conv3(3, a, a_pix_stride, a_c_off, Ca, w_packed, N, B, H, W, out, out_pix_stride, out_c_off, nullptr,
+                         nullptr, 0, stats, stats_replicas, N, static_cast<cudaStream_t>(stream));
+    return run_igemm(0, a, a_pix_stride, a_c_off, Ca, 1, w_packed, N, B, H, W, 0, N, out, out_pix_stride, out_c_off,
+                     nullptr, nullptr, 0, stats, stats_replicas, static_cast<cudaStream_t>(stream));
+}
+
+int b200sr_conv1x1_wgrad(const void* x, int x_pix_stride, int x_c_off, int Cin, const void* dz, int dz_pix_stride,
+                         int dz_c_off, int Cout, int B, int H, int W, float* G, void* stream) {
+    return run_wgrad(0, x, x_pix_stride, x_c_off, Cin, 1, dz, dz_pix_stride, dz_c_off, Cout, B, H, W, G,
+                     static_cast<cudaStream_t>(stream));
 }
 
 int b200sr_maxpool2x2_fwd(const void* in, int in_pix_stride, int in_c_off, int C, void* out, int B, int H, int W,
@@ -812,7 +927,7 @@ int b200sr_bn_bwd_reduce(const void* dy, int dy_pix_stride, int dy_c_off, const 
         if (blocks > num_sms() * 8) blocks = num_sms() * 8;
         bn_bwd_reduce_fast_kernel<<<static_cast<int>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
             static_cast<const __nv_bfloat16*>(dy), dy_pix_stride, dy_c_off, static_cast<const __nv_bfloat16*>(z), C,
-            scale, shift, mean, invstd, sums, replicas, npix);
+            scale, shift, mean, invstd, sums, replicas, npix, nullptr);
         return check_launch("bn_bwd_reduce_fast_kernel");
     }
     const int cg = C / 64;

@@ -65,6 +65,7 @@ struct C3Cfg {
 // MODE 1: ConvTranspose2d k2 s2 forward as a 1-tap GEMM with N = 4*Cout and a pixel-shuffle scatter epilogue + bias
 //         (unet_model.py:67-76; writes straight into the concat slot, which replaces torch.cat at :101-113)
 // MODE 2: ConvTranspose2d k2 s2 dgrad: four taps (i,j), each gathered through the 5-D view (c, j, w, i, b*H+h)
+// MODE 3: Conv2d 1x1 forward / dgrad (DeepCNN downsample branch, ModelLoader.py:347-351): one tap, plain NHWC store
 template <int BLOCK_N, int MODE>
 __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_kernel(const __grid_constant__ CUtensorMap map_a,
                                                                 const __grid_constant__ CUtensorMap map_b,
@@ -72,7 +73,7 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_kernel(const __grid_con
                                                                 const Conv3Args args) {
     using Cfg = C3Cfg<BLOCK_N>;
     constexpr int SA = Cfg::SA, SB = Cfg::SB, NH = Cfg::NH, BN_SLOT = Cfg::BN_SLOT;
-    constexpr int NG = MODE == 0 ? 3 : (MODE == 1 ? 1 : 4);  // activation boxes per 64-channel chunk
+    constexpr int NG = MODE == 0 ? 3 : (MODE == 2 ? 4 : 1);  // activation boxes per 64-channel chunk
     constexpr int NT = MODE == 0 ? 3 : 1;                    // taps served by one box
     constexpr int A_BYTES = MODE == 0 ? C3_A_SLOT : C3_TILE_H * C3_TILE_W * 128;
     extern __shared__ uint8_t smem_raw[];
@@ -153,7 +154,7 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_kernel(const __grid_con
                         mbar_arrive_expect_tx(&a_full[sa], A_BYTES);
                         if (MODE == 0)
                             tma_load_4d(&map_a, &a_full[sa], ring_a + sa * C3_A_SLOT, c * 64, w0 + dw - 1, h0 - 1, img);
-                        else if (MODE == 1)
+                        else if (MODE == 1 || MODE == 3)
                             tma_load_4d(&map_a, &a_full[sa], ring_a + sa * C3_A_SLOT, c * 64, w0, h0, img);
                         else
                             tma_load_5d(&map_a, &a_full[sa], ring_a + sa * C3_A_SLOT, c * 64, dw & 1, w0, dw >> 1,

@@ -55,6 +55,9 @@ enum PackKind : int {
     PACK_CONVT_DGRAD = 3,  // (Cin,Cout,2,2) f32 -> [ci][(i*2+j)*Cout + co] bf16
     UNPACK_CONV_WGRAD = 4,   // G[tap][ci][co] f32 -> (Cout,Cin,3,3) f32
     UNPACK_CONVT_WGRAD = 5,  // G[(i,j)][co][ci] f32 -> (Cin,Cout,2,2) f32
+    PACK_CONV1X1_FWD = 6,    // (Cout,Cin,1,1) f32 -> [Cout][Cin] bf16
+    PACK_CONV1X1_DGRAD = 7,  // (Cout,Cin,1,1) f32 -> [Cin][Cout] bf16
+    UNPACK_CONV1X1_WGRAD = 8,  // G[ci][co] f32 -> (Cout,Cin,1,1) f32
 };
 
 struct PackJob {
@@ -76,8 +79,9 @@ __global__ void __launch_bounds__(256) pack_jobs_kernel(const PackJob* __restric
     __shared__ float tile[PK_TILE][PK_TILE * 9 + 1];
     const PackJob job = jobs[blockIdx.y];
     const int Cout = job.cout, Cin = job.cin;
-    const bool conv = job.kind == PACK_CONV_FWD || job.kind == PACK_CONV_DGRAD || job.kind == UNPACK_CONV_WGRAD;
-    const int T = conv ? 9 : 4;
+    const bool one = job.kind >= PACK_CONV1X1_FWD;
+    const bool conv = one || job.kind == PACK_CONV_FWD || job.kind == PACK_CONV_DGRAD || job.kind == UNPACK_CONV_WGRAD;
+    const int T = one ? 1 : (conv ? 9 : 4);
     const int outer_total = conv ? Cout : Cin, inner_total = conv ? Cin : Cout;
     const int tiles_in = inner_total / PK_TILE;
     const int num_tiles = (outer_total / PK_TILE) * tiles_in;
@@ -87,7 +91,7 @@ __global__ void __launch_bounds__(256) pack_jobs_kernel(const PackJob* __restric
         const int o0 = (tl / tiles_in) * PK_TILE, i0 = (tl % tiles_in) * PK_TILE;
         __syncthreads();
         // ---- load ----
-        if (job.kind <= PACK_CONVT_DGRAD) {
+        if (job.kind <= PACK_CONVT_DGRAD || job.kind == PACK_CONV1X1_FWD || job.kind == PACK_CONV1X1_DGRAD) {
             const float* src = static_cast<const float*>(job.src);
             for (int idx = tid; idx < PK_TILE * row; idx += 256) {
                 const int o = idx / row, r = idx - o * row;
@@ -118,6 +122,22 @@ __global__ void __launch_bounds__(256) pack_jobs_kernel(const PackJob* __restric
                     const int o = idx % PK_TILE, t = (idx / PK_TILE) % 9, i = idx / (PK_TILE * 9);
                     dst[static_cast<long long>(i0 + i) * (9LL * Cout) + t * Cout + o0 + o] =
                         __float2bfloat16_rn(tile[o][i * 9 + 8 - t]);
+                }
+                break;
+            }
+            case PACK_CONV1X1_FWD: {  // dst[co][ci]
+                __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(job.dst);
+                for (int idx = tid; idx < PK_TILE * PK_TILE; idx += 256) {
+                    const int i = idx % PK_TILE, o = idx / PK_TILE;
+                    dst[static_cast<long long>(o0 + o) * Cin + i0 + i] = __float2bfloat16_rn(tile[o][i]);
+                }
+                break;
+            }
+            case PACK_CONV1X1_DGRAD: {  // dst[ci][co]
+                __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(job.dst);
+                for (int idx = tid; idx < PK_TILE * PK_TILE; idx += 256) {
+                    const int o = idx % PK_TILE, i = idx / PK_TILE;
+                    dst[static_cast<long long>(i0 + i) * Cout + o0 + o] = __float2bfloat16_rn(tile[o][i]);
                 }
                 break;
             }
@@ -738,7 +758,10 @@ __global__ void __launch_bounds__(256, 3) bn_bwd_reduce_fast_kernel(const __nv_b
                                                                  const float* __restrict__ mean,
                                                                  const float* __restrict__ invstd,
                                                                  float* __restrict__ sums, int replicas,
-                                                                 long long npix) {
+                                                                 long long npix,
+                                                                 const __nv_bfloat16* __restrict__ mask_src) {
+    // mask_src (nullable, dense [npix][C]): ReLU mask taken from a stored activation (residual blocks, where the
+    // ReLU follows the skip addition) instead of from scale*z+shift > 0
     const int CV = C >> 3;            // channel vectors per pixel
     const int PB = 256 / CV;          // pixels per block iteration
     const int cv = threadIdx.x % CV, pl = threadIdx.x / CV;
@@ -749,22 +772,30 @@ __global__ void __launch_bounds__(256, 3) bn_bwd_reduce_fast_kernel(const __nv_b
     for (int k = 0; k < 8; ++k) s1[k] = s2[k] = 0.f;
     const long long step = static_cast<long long>(gridDim.x) * PB;
     for (long long p0 = static_cast<long long>(blockIdx.x) * PB + pl; p0 < npix; p0 += step * BNB_UNROLL) {
-        uint4 g[BNB_UNROLL], zz[BNB_UNROLL];
+        uint4 g[BNB_UNROLL], zz[BNB_UNROLL], mm[BNB_UNROLL];
 #pragma unroll
         for (int u = 0; u < BNB_UNROLL; ++u) {
             const long long p = p0 + u * step;
             if (p < npix) {
                 g[u] = ld_stream(dy + p * dy_stride + dy_coff + c);
                 zz[u] = ld_stream(z + p * C + c);
+                if (mask_src != nullptr) mm[u] = ld_stream(mask_src + p * C + c);
             }
         }
 #pragma unroll
         for (int u = 0; u < BNB_UNROLL; ++u) {
             if (p0 + u * step < npix) {
                 const F8 gf = unpack8(g[u]), zf = unpack8(zz[u]);
+                F8 mf;
+                if (mask_src != nullptr) {
+                    mf = unpack8(mm[u]);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) mf.v[k] = fmaf(zf.v[k], sc.v[k], sh.v[k]);
+                }
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
-                    const float gm = fmaf(zf.v[k], sc.v[k], sh.v[k]) > 0.f ? gf.v[k] : 0.f;
+                    const float gm = mf.v[k] > 0.f ? gf.v[k] : 0.f;
                     s1[k] += gm;
                     s2[k] = fmaf(gm, zf.v[k] - mu.v[k], s2[k]);
                 }
@@ -846,7 +877,8 @@ __global__ void __launch_bounds__(256, 3) bn_bwd_apply_fused_kernel(
     const __nv_bfloat16* __restrict__ dy, int dy_stride, int dy_coff, const __nv_bfloat16* __restrict__ z, int C,
     const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ mean,
     const float* __restrict__ invstd, const float* __restrict__ sums, int replicas, float count,
-    float* __restrict__ dgamma, float* __restrict__ dbeta, __nv_bfloat16* __restrict__ dz, long long npix) {
+    float* __restrict__ dgamma, float* __restrict__ dbeta, __nv_bfloat16* __restrict__ dz, long long npix,
+    const __nv_bfloat16* __restrict__ mask_src) {
     const int CV = C >> 3;
     const int PB = 256 / CV;
     const int cv = threadIdx.x % CV, pl = threadIdx.x / CV;
@@ -884,13 +916,14 @@ __global__ void __launch_bounds__(256, 3) bn_bwd_apply_fused_kernel(
     }
     const long long step = static_cast<long long>(gridDim.x) * PB;
     for (long long p0 = static_cast<long long>(blockIdx.x) * PB + pl; p0 < npix; p0 += step * BNB_UNROLL) {
-        uint4 g[BNB_UNROLL], zz[BNB_UNROLL];
+        uint4 g[BNB_UNROLL], zz[BNB_UNROLL], mm[BNB_UNROLL];
 #pragma unroll
         for (int u = 0; u < BNB_UNROLL; ++u) {
             const long long p = p0 + u * step;
             if (p < npix) {
                 g[u] = ld_stream(dy + p * dy_stride + dy_coff + c);
                 zz[u] = ld_stream(z + p * C + c);
+                if (mask_src != nullptr) mm[u] = ld_stream(mask_src + p * C + c);
             }
         }
 #pragma unroll
@@ -898,10 +931,17 @@ __global__ void __launch_bounds__(256, 3) bn_bwd_apply_fused_kernel(
             const long long p = p0 + u * step;
             if (p < npix) {
                 const F8 gf = unpack8(g[u]), zf = unpack8(zz[u]);
+                F8 mf;
+                if (mask_src != nullptr) {
+                    mf = unpack8(mm[u]);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) mf.v[k] = fmaf(zf.v[k], sc.v[k], sh.v[k]);
+                }
                 F8 o;
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
-                    const float gm = fmaf(zf.v[k], sc.v[k], sh.v[k]) > 0.f ? gf.v[k] : 0.f;
+                    const float gm = mf.v[k] > 0.f ? gf.v[k] : 0.f;
                     o.v[k] = fmaf(gm, sc.v[k], fmaf(zf.v[k], ka.v[k], kb.v[k]));
                 }
                 st_bf16x8(dz + p * C + c, o);

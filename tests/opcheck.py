@@ -207,6 +207,143 @@ def conv1_dgrad(B=2, H=32, W=48, seed=15):
     return {"dx": rel(dx, ref)}
 
 
+def conv7(B=2, H=32, W=48, seed=41):
+    _setup()
+    x = rnd(B, 2, H, W, seed=seed)
+    w = rnd(64, 2, 7, 7, seed=seed + 1, scale=98 ** -0.5)
+    ref = F.conv2d(x, w, padding=3)
+    ob = torch.zeros(B, H, W, 64, dtype=torch.bfloat16, device=DEV)
+    stats = torch.zeros(R, 2, 64, device=DEV)
+    call("b200sr_conv7_fwd", ptr(x), ptr(w), ptr(ob), ptr(stats), R, B, H, W, st())
+    torch.cuda.synchronize()
+    out = nchw(ob)
+    res = {"out": rel(out, ref), "stats_sum": rel(stats.sum(0)[0], out.sum(dim=(0, 2, 3))),
+           "stats_sq": rel(stats.sum(0)[1], (out * out).sum(dim=(0, 2, 3)))}
+    dz = bf(rnd(B, 64, H, W, seed=seed + 2))
+    refw = torch.nn.grad.conv2d_weight(x, (64, 2, 7, 7), dz, padding=3)
+    dw = torch.zeros(64, 2, 7, 7, device=DEV)
+    call("b200sr_conv7_wgrad", ptr(x), ptr(nhwc(dz)), ptr(dw), B, H, W, st())
+    torch.cuda.synchronize()
+    res["dw"] = rel(dw, refw)
+    return res
+
+
+def maxpool3(B=2, H=12, W=20, C=64, seed=42):
+    _setup()
+    # coarse non-negative values force ties inside windows
+    a = bf((rnd(B, C, H, W, seed=seed) * 2).round().clamp_min(0) / 2).requires_grad_(True)
+    g = bf(rnd(B, C, H, W, seed=seed + 1))
+    y = F.max_pool2d(a, 3, stride=1, padding=1)
+    y.backward(g)
+    ab = nhwc(a.detach())
+    ob = torch.zeros_like(ab)
+    call("b200sr_maxpool3x3_fwd", ptr(ab), ptr(ob), C, B, H, W, st())
+    db = torch.zeros_like(ab)
+    call("b200sr_maxpool3x3_bwd", ptr(ab), ptr(nhwc(g)), ptr(db), C, B, H, W, st())
+    torch.cuda.synchronize()
+    return {"fwd_exact": float((nchw(ob) - y.detach()).abs().max()), "bwd": rel(nchw(db), a.grad)}
+
+
+def residual_tail(B=2, H=16, W=16, C=128, down=True, seed=43):
+    """bn_add_relu forward and bn_bwd_masked / add_masked backward of a ResidualBlock tail vs autograd."""
+    _setup()
+    N = B * H * W
+    z2 = bf(rnd(B, C, H, W, seed=seed) * 1.5).requires_grad_(True)
+    g2 = (1 + 0.1 * rnd(C, seed=seed + 1)).requires_grad_(True)
+    b2 = (0.1 * rnd(C, seed=seed + 2)).requires_grad_(True)
+    idn = bf(rnd(B, C, H, W, seed=seed + 3)).requires_grad_(True)   # raw x, or z_d of the downsample branch
+    gd = (1 + 0.1 * rnd(C, seed=seed + 4)).requires_grad_(True)
+    bd = (0.1 * rnd(C, seed=seed + 5)).requires_grad_(True)
+    y2 = F.batch_norm(z2, None, None, g2, b2, True, 0.1, 1e-5)
+    yi = F.batch_norm(idn, None, None, gd, bd, True, 0.1, 1e-5) if down else idn
+    out = torch.relu(y2 + yi)
+    dout = bf(rnd(B, C, H, W, seed=seed + 6))
+    out.backward(dout)
+
+    def affine(z, gamma, beta):
+        zd = z.detach()
+        mean = zd.mean(dim=(0, 2, 3))
+        invstd = torch.rsqrt(zd.var(dim=(0, 2, 3), unbiased=False) + 1e-5)
+        sc = (gamma.detach() * invstd).contiguous()
+        return sc, (beta.detach() - mean * sc).contiguous(), mean.contiguous(), invstd.contiguous()
+
+    s2, h2, m2, i2 = affine(z2, g2, b2)
+    z2b, idb, doutb = nhwc(z2.detach()), nhwc(idn.detach()), nhwc(dout)
+    outb = torch.zeros_like(z2b)
+    if down:
+        sd, hd, md, idd = affine(idn, gd, bd)
+        call("b200sr_bn_add_relu", ptr(z2b), ptr(s2), ptr(h2), ptr(idb), ptr(sd), ptr(hd), ptr(outb), C, N, st())
+    else:
+        call("b200sr_bn_add_relu", ptr(z2b), ptr(s2), ptr(h2), ptr(idb), None, None, ptr(outb), C, N, st())
+    torch.cuda.synchronize()
+    res = {"out": rel(nchw(outb), out.detach())}
+    sums = torch.zeros(R, 2, C, device=DEV)
+    dgb = torch.zeros(2, C, device=DEV)
+    dz2 = torch.zeros_like(z2b)
+    call("b200sr_bn_bwd_masked", ptr(doutb), ptr(z2b), ptr(outb), C, ptr(s2), ptr(h2), ptr(m2), ptr(i2), ptr(sums), R,
+         float(N), ptr(dgb[0]), ptr(dgb[1]), ptr(dz2), N, st())
+    torch.cuda.synchronize()
+    res["dz2"] = rel(nchw(dz2), z2.grad)
+    res["dgamma2"] = rel(dgb[0], g2.grad)
+    if down:
+        sums.zero_()
+        dzd = torch.zeros_like(z2b)
+        call("b200sr_bn_bwd_masked", ptr(doutb), ptr(idb), ptr(outb), C, ptr(sd), ptr(hd), ptr(md), ptr(idd), ptr(sums),
+             R, float(N), ptr(dgb[0]), ptr(dgb[1]), ptr(dzd), N, st())
+        torch.cuda.synchronize()
+        res["dzd"] = rel(nchw(dzd), idn.grad)
+    else:
+        base = bf(rnd(B, C, H, W, seed=seed + 7))
+        ob = torch.zeros_like(z2b)
+        call("b200sr_add_masked", ptr(nhwc(base)), ptr(doutb), ptr(outb), ptr(ob), N * C, st())
+        torch.cuda.synchronize()
+        res["didentity"] = rel(nchw(ob), base + idn.grad)
+    return res
+
+
+def conv1x1(B=2, H=16, W=32, Cin=64, Cout=128, seed=44):
+    _setup()
+    x = bf(rnd(B, Cin, H, W, seed=seed))
+    w = bf(rnd(Cout, Cin, 1, 1, seed=seed + 1, scale=Cin ** -0.5))
+    dz = bf(rnd(B, Cout, H, W, seed=seed + 2))
+    ref = F.conv2d(x, w)
+    ref_dx = F.conv_transpose2d(dz, w)
+    ref_dw = torch.nn.grad.conv2d_weight(x, (Cout, Cin, 1, 1), dz)
+    wf, wd = pack(w, 6, Cout, Cin), pack(w, 7, Cout, Cin)
+    xb, dzb = nhwc(x), nhwc(dz)
+    ob = torch.zeros(B, H, W, Cout, dtype=torch.bfloat16, device=DEV)
+    stats = torch.zeros(R, 2, Cout, device=DEV)
+    call("b200sr_conv1x1", ptr(xb), Cin, 0, Cin, ptr(wf), Cout, B, H, W, ptr(ob), Cout, 0, ptr(stats), R, st())
+    dxb = torch.zeros(B, H, W, Cin, dtype=torch.bfloat16, device=DEV)
+    call("b200sr_conv1x1", ptr(dzb), Cout, 0, Cout, ptr(wd), Cin, B, H, W, ptr(dxb), Cin, 0, None, 0, st())
+    G = torch.zeros(Cin * Cout, device=DEV)
+    call("b200sr_conv1x1_wgrad", ptr(xb), Cin, 0, Cin, ptr(dzb), Cout, 0, Cout, B, H, W, ptr(G), st())
+    torch.cuda.synchronize()
+    dw = pack(G, 8, Cout, Cin, torch.float32).view(Cout, Cin, 1, 1)
+    out = nchw(ob)
+    return {"out": rel(out, ref), "dx": rel(nchw(dxb), ref_dx), "dw": rel(dw, ref_dw),
+            "stats_sum": rel(stats.sum(0)[0], out.sum(dim=(0, 2, 3)))}
+
+
+def headw(B=2, H=16, W=16, C=512, seed=45):
+    _setup()
+    a = bf(rnd(B, C, H, W, seed=seed)).requires_grad_(True)
+    w = rnd(1, C, 1, 1, seed=seed + 1, scale=C ** -0.5).requires_grad_(True)
+    b = rnd(1, seed=seed + 2).requires_grad_(True)
+    dout = rnd(B, 1, H, W, seed=seed + 3)
+    y = F.conv2d(a, w, b)
+    y.backward(dout)
+    ab = nhwc(a.detach())
+    out = torch.zeros(B, 1, H, W, device=DEV)
+    call("b200sr_headw_fwd", ptr(ab), C, ptr(w), ptr(b), ptr(out), B * H * W, st())
+    dact = torch.zeros(B, H, W, C, dtype=torch.bfloat16, device=DEV)
+    dw, db = torch.zeros(C, device=DEV), torch.zeros(1, device=DEV)
+    call("b200sr_headw_bwd", ptr(dout), ptr(ab), C, ptr(w), ptr(dact), ptr(dw), ptr(db), B * H * W, st())
+    torch.cuda.synchronize()
+    return {"out": rel(out, y.detach()), "dact": rel(nchw(dact), a.grad), "dw": rel(dw, w.grad.flatten()),
+            "db": rel(db, b.grad)}
+
+
 def bn_train(B=2, H=16, W=32, C=128, pool=True, seed=8):
     """bn_finalize + bnrelu_apply(+pool) against F.batch_norm + relu + max_pool2d."""
     _setup()
@@ -447,6 +584,14 @@ CHECKS = {
     "convT_wgrad_big": (convT_wgrad, dict(Cin=512, Cout=256, B=1, H=8, W=16), {"dw": BF16}),
     "conv1": (conv1, {}, {"out": BF16, "stats_sum": 1e-3, "stats_sq": 1e-3, "dw": 1e-3}),
     "conv1_dgrad": (conv1_dgrad, {}, {"dx": 1e-5}),
+    # DeepCNN-specific kernels
+    "conv7": (conv7, {}, {"out": BF16, "stats_sum": 1e-3, "stats_sq": 1e-3, "dw": 1e-3}),
+    "maxpool3x3_ties": (maxpool3, {}, {"fwd_exact": 0.0, "bwd": 4e-3}),
+    "residual_tail_downsample": (residual_tail, {}, {"out": BF16, "dz2": BF16, "dgamma2": 1e-3, "dzd": BF16}),
+    "residual_tail_identity": (residual_tail, dict(down=False, C=64), {"out": BF16, "dz2": BF16, "didentity": BF16}),
+    "conv1x1_persistent": (conv1x1, {}, {"out": BF16, "dx": BF16, "dw": BF16, "stats_sum": 1e-3}),
+    "conv1x1_generic": (conv1x1, dict(H=8, W=16, Cin=128, Cout=256), {"out": BF16, "dx": BF16, "dw": BF16}),
+    "headw_512": (headw, {}, {"out": 1e-5, "dact": BF16, "dw": 1e-4, "db": 1e-4}),
     "bn_train_pool": (bn_train, {}, {"act": BF16, "running_mean": 1e-5, "running_var": 1e-4, "pool_exact": 0.0,
                                      "maxpool_fwd_exact": 0.0, "slot_untouched": 0.0, "fused_act_exact": 0.0,
                                      "fused_ws_exact": 0.0, "fused_running_exact": 0.0, "fused_pool_exact": 0.0}),
