@@ -14,6 +14,7 @@ import torch
 
 from .unet_model import UNet, UNetBlock  # noqa: F401  (re-exported like the reference module does)
 from .progressive import ProgressiveUNet, ProgressiveUNetBlock, UNetStage  # noqa: F401
+from .deepcnn import DeepCNN, ResidualBlock  # noqa: F401
 
 _UNET_KW = {'in_channels': 2, 'out_channels': 1, 'init_features': 64}
 
@@ -21,7 +22,8 @@ _UNET_KW = {'in_channels': 2, 'out_channels': 1, 'init_features': 64}
 CHECKPOINT_MAP = {
     'unet': ('unet_best.pt', UNet, _UNET_KW),
     'unet_combined': ('unet_combined_best.pt', UNet, _UNET_KW),
-    'deepcnn': ('deepcnn_best.pt', None, {}),
+    'deepcnn': ('deepcnn_best.pt', DeepCNN, {'in_channels': 2, 'out_channels': 1, 'num_blocks': [2, 2, 2, 2],
+                                             'base_features': 64}),
     'progressive_unet': ('progressive_unet_best.pt', ProgressiveUNet, {'base_features': 64}),
     'unet_gan': ('unet_gan_best.pt', None, {}),
     'fastddpm': ('fastddpm_advanced_best.pth', None, {}),

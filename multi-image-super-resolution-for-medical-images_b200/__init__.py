@@ -12,6 +12,7 @@ from .unet_model import UNet, UNetBlock, UNetTrainer, MRIDataset, create_dummy_d
 from .losses import CombinedLoss, ssim_window  # noqa: F401
 from .perceptual import PerceptualLoss, VGG16Features  # noqa: F401
 from .ModelLoader import load_model  # noqa: F401
+from .deepcnn import DeepCNN, DeepCNNTrainer, ResidualBlock  # noqa: F401
 from .progressive import ProgressiveUNet, ProgressiveUNetBlock, ProgressiveUNetTrainer, UNetStage  # noqa: F401
 from .data import DevicePrefetcher, SyntheticTripletGenerator  # noqa: F401
 

@@ -15,7 +15,9 @@ def seeded_state_dict(model_ctor, seed=0, perturb_seed=7):
     sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
     g = torch.Generator().manual_seed(perturb_seed)
     for k in sd:
-        if ".conv.1." in k or ".conv.4." in k:
+        is_bn = ".conv.1." in k or ".conv.4." in k or ".bn1." in k or ".bn2." in k or k.startswith("bn1.") or \
+            ".downsample.1." in k
+        if is_bn and not k.endswith(("running_mean", "running_var", "num_batches_tracked")):
             if k.endswith(".weight"):
                 sd[k] = sd[k] + 0.1 * torch.randn(sd[k].shape, generator=g)
             elif k.endswith(".bias"):
@@ -46,3 +48,6 @@ def seeded_slices(B, H, W, seed):
     t = torch.linspace(-1.0, 1.0, 5).view(1, 5, 1, 1)
     vol = base + 0.5 * t * drift + 0.2 * torch.randn(B, 5, H, W, generator=g)
     return (vol - vol.mean(dim=(-2, -1), keepdim=True)) / (vol.std(dim=(-2, -1), keepdim=True) + 1e-6)
+
+
+DEEPCNN_CASE = dict(B=1, H=32, W=48, seed=1357)

@@ -170,6 +170,39 @@ def main():
     np.savez_compressed(ppath, **pout)
     print("wrote", ppath, os.path.getsize(ppath), "bytes")
 
+    # ---------------- DeepCNN residual baseline --------------------------------------------------
+    dout = {}
+    sd_d = cases.seeded_state_dict(ref_loader.DeepCNN, seed=5)
+    sd_dm = cases.seeded_state_dict(b200sr.DeepCNN, seed=5)
+    assert list(sd_d) == list(sd_dm) and all(torch.equal(sd_d[k], sd_dm[k]) for k in sd_d)
+    print(f"DeepCNN state_dict: {len(sd_d)} entries identical (reference vs b200sr)")
+    c = cases.DEEPCNN_CASE
+    xd, yd = cases.seeded_batch(c["B"], c["H"], c["W"], c["seed"])
+    dm = ref_loader.DeepCNN()
+    dm.load_state_dict(sd_d)
+    dm.train()
+    pd_ = dm(xd)
+    dloss = torch.nn.functional.mse_loss(pd_, yd)
+    dloss.backward()
+    dg = {k: p.grad.detach().clone() for k, p in dm.named_parameters()}
+    o_l, o_o, o_g, _ = unet_oracle.deepcnn_loss_and_grads(sd_d, xd, yd)
+    worst = max(rel(o_g[k], dg[k]) for k in dg if dg[k].norm() > 1e-9)
+    print(f"deepcnn: oracle vs reference out {rel(o_o, pd_.detach()):.3e}, loss {float(o_l):.8f} vs {dloss.item():.8f}, "
+          f"worst grad rel-L2 {worst:.3e}")
+    assert worst < 1e-4 and abs(float(o_l) - dloss.item()) < 1e-6
+    dout["keys"] = np.array(list(sd_d))
+    dout["loss"] = np.float64(dloss.item())
+    dout["train_out"] = pd_.detach().numpy()
+    dnames = list(dg)
+    dout["grad_names"] = np.array(dnames)
+    dout["grad_norms"] = np.array([dg[k].double().norm().item() for k in dnames])
+    dm.eval()
+    with torch.no_grad():
+        dout["eval_out"] = dm(xd).numpy()
+    dpath = os.path.join(ROOT, "tests", "golden", "deepcnn_golden.npz")
+    np.savez_compressed(dpath, **dout)
+    print("wrote", dpath, os.path.getsize(dpath), "bytes")
+
 
 if __name__ == "__main__":
     main()

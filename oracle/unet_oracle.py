@@ -95,6 +95,50 @@ def loss_and_grads(sd, x, y, loss_fn=None):
     return loss.detach(), out.detach(), dict(zip(names, grads)), new_stats
 
 
+def _bn(sd, name, x, training, new_stats):
+    rm, rv = sd[f"{name}.running_mean"], sd[f"{name}.running_var"]
+    if training:
+        rm_new, rv_new = rm.detach().clone(), rv.detach().clone()
+        x = F.batch_norm(x, rm_new, rv_new, sd[f"{name}.weight"], sd[f"{name}.bias"], training=True,
+                         momentum=BN_MOMENTUM, eps=BN_EPS)
+        if new_stats is not None:
+            new_stats[f"{name}.running_mean"], new_stats[f"{name}.running_var"] = rm_new, rv_new
+        return x
+    return F.batch_norm(x, rm, rv, sd[f"{name}.weight"], sd[f"{name}.bias"], training=False, momentum=BN_MOMENTUM,
+                        eps=BN_EPS)
+
+
+def deepcnn_forward(sd, x, training=False, new_stats=None, num_blocks=(2, 2, 2, 2)):
+    """DeepCNN.forward (ModelLoader.py:361-377) with ResidualBlock.forward (:290-307): 7x7 stem + BN + ReLU +
+    MaxPool(3,1,1), four layers of residual blocks (all stride 1; 1x1 conv + BN downsample branch when the channel
+    count changes), 1x1 output conv. The declared avgpool is not used by the reference forward."""
+    x = F.conv2d(x, sd["conv1.weight"], None, padding=3)
+    x = torch.relu(_bn(sd, "bn1", x, training, new_stats))
+    x = F.max_pool2d(x, kernel_size=3, stride=1, padding=1)
+    for li, nb in enumerate(num_blocks, start=1):
+        for bi in range(nb):
+            pre = f"layer{li}.{bi}"
+            idn = x
+            out = F.conv2d(x, sd[f"{pre}.conv1.weight"], None, padding=1)
+            out = torch.relu(_bn(sd, f"{pre}.bn1", out, training, new_stats))
+            out = F.conv2d(out, sd[f"{pre}.conv2.weight"], None, padding=1)
+            out = _bn(sd, f"{pre}.bn2", out, training, new_stats)
+            if f"{pre}.downsample.0.weight" in sd:
+                idn = _bn(sd, f"{pre}.downsample.1", F.conv2d(x, sd[f"{pre}.downsample.0.weight"]), training, new_stats)
+            x = torch.relu(out + idn)
+    return F.conv2d(x, sd["output_conv.weight"], sd["output_conv.bias"])
+
+
+def deepcnn_loss_and_grads(sd, x, y):
+    names = param_names(sd)
+    leaf = {k: (v.detach().clone().requires_grad_(True) if k in set(names) else v) for k, v in sd.items()}
+    new_stats = {}
+    out = deepcnn_forward(leaf, x, True, new_stats)
+    loss = F.mse_loss(out, y)
+    grads = torch.autograd.grad(loss, [leaf[k] for k in names])
+    return loss.detach(), out.detach(), dict(zip(names, grads)), new_stats
+
+
 def adam_update(p, g, m, v, step, lr=1e-4, b1=0.9, b2=0.999, eps=1e-8):
     """One torch.optim.Adam step (defaults of unet_model.py:155) on plain tensors; returns (p, m, v)."""
     m = b1 * m + (1 - b1) * g

@@ -96,9 +96,9 @@ def test_load_model_contract(tmp_path, capsys):
     m = b200sr.load_model("unet", device="cpu", root=str(tmp_path), verbose=False)
     assert torch.equal(m.state_dict()["final_conv.bias"], sd["final_conv.bias"])
     # registry names outside the hot path are recognised but refuse to load
-    torch.save(sd, tmp_path / "models" / "deepcnn_best.pt")
+    torch.save(sd, tmp_path / "models" / "unet_gan_best.pt")
     with pytest.raises(NotImplementedError):
-        b200sr.load_model("deepcnn", device="cpu", root=str(tmp_path))
+        b200sr.load_model("unet_gan", device="cpu", root=str(tmp_path))
 
 
 def test_trainer_surface():

@@ -1,0 +1,82 @@
+"""GPU parity of the DeepCNN residual baseline against the CPU oracle / golden fixtures.
+
+Tolerances: every kernel holds rel-L2 1e-2 per op (test_gpu_ops.py). End to end on this random-init case the REFERENCE
+under torch.autocast(bfloat16) deviates from its own fp32 run by 3.8e-2 on the output, 4.1e-3 on the loss and
+0.1-0.45 rel-L2 on gradients (cosine 0.90-0.99), so the gates are: output 6e-2, loss 1e-2, gradient cosines."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import b200sr
+from oracle import cases, unet_oracle
+
+pytestmark = pytest.mark.gpu
+GOLD = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "deepcnn_golden.npz"))
+
+
+def rel(a, b):
+    return float((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30))
+
+
+def cos(a, b):
+    a, b = a.double().flatten(), b.double().flatten()
+    return float((a @ b) / (a.norm() * b.norm()).clamp_min(1e-30))
+
+
+def _model(sd):
+    m = b200sr.DeepCNN()
+    m.load_state_dict(sd)
+    return m.cuda()
+
+
+def test_train_forward_backward_matches_oracle():
+    sd = cases.seeded_state_dict(b200sr.DeepCNN, seed=5)
+    c = cases.DEEPCNN_CASE
+    x, y = cases.seeded_batch(c["B"], c["H"], c["W"], c["seed"])
+    o_loss, o_out, o_grads, o_stats = unet_oracle.deepcnn_loss_and_grads(sd, x, y)
+    assert abs(float(o_loss) - float(GOLD["loss"])) / float(GOLD["loss"]) < 1e-6
+    m = _model(sd).train()
+    eng = m._get_engine()
+    out = eng.forward(x.cuda(), training=True)
+    crit = b200sr.CombinedLoss(1.0, 0.0)
+    loss, dout = crit.value_and_grad(out, y.cuda())
+    eng.backward(dout)
+    torch.cuda.synchronize()
+    assert rel(out.cpu(), o_out) < 6e-2
+    assert abs(float(loss) - float(o_loss)) / float(o_loss) < 1e-2
+    for (name, _), g in zip(m.named_parameters(), eng.grad_views):
+        ref = o_grads[name]
+        if ref.norm() < 1e-9:
+            continue
+        cs = cos(g.cpu(), ref)
+        assert cs > 0.5, (name, cs)
+        if name.startswith(("output_conv", "layer4.1.bn2", "layer4.1.conv2")):
+            assert cs > 0.95, (name, cs)
+    msd = m.state_dict()
+    assert max(rel(msd[k].cpu(), v) for k, v in o_stats.items()) < 1e-2
+
+
+def test_eval_forward_matches_golden():
+    sd = cases.seeded_state_dict(b200sr.DeepCNN, seed=5)
+    c = cases.DEEPCNN_CASE
+    x, y = cases.seeded_batch(c["B"], c["H"], c["W"], c["seed"])
+    _, _, _, stats = unet_oracle.deepcnn_loss_and_grads(sd, x, y)
+    sd.update(stats)
+    m = _model(sd).eval()
+    with torch.no_grad():
+        out = m(x.cuda())
+    assert rel(out.cpu(), torch.from_numpy(GOLD["eval_out"])) < 6e-2
+
+
+def test_trainer_learns(tmp_path):
+    torch.manual_seed(0)
+    m = b200sr.DeepCNN()
+    # reference hyper-parameters (results/deepcnn_history.json): Adam lr 1e-4; the un-normalised kaiming(fan_out) init
+    # starts at a loss of ~1e3, larger steps diverge (in the reference too)
+    tr = b200sr.DeepCNNTrainer(m, device="cuda", learning_rate=1e-4, model_save_dir=str(tmp_path), verbose=False)
+    gen = b200sr.SyntheticTripletGenerator(2, 64, 64, device="cuda", seed=3)
+    x, y = gen.next()
+    losses = [float(tr.train_step(x, y)) for _ in range(12)]
+    assert losses[-1] < 0.7 * losses[0], losses

@@ -25,7 +25,7 @@ def timed(fn, steps=10, warmup=3):
 
 
 out = {}
-which = sys.argv[1:] or ["perceptual", "progressive"]
+which = sys.argv[1:] or ["perceptual", "progressive", "deepcnn"]
 if "perceptual" in which:
     model = b200sr.UNet()
     model.load_state_dict(cases.seeded_state_dict(b200sr.UNet))
@@ -43,4 +43,16 @@ if "progressive" in which:
     ms = timed(lambda: ptr_.train_step(sl), steps=6, warmup=2)
     out["progressive_unet_3stage"] = {"ms_per_step": ms, "windows_per_s": B / ms * 1e3,
                                       "tflops": 3 * 288.627 * B / ms}
+if "deepcnn" in which:
+    dm = b200sr.DeepCNN()
+    dtr = b200sr.DeepCNNTrainer(dm, device=dev, model_save_dir="/tmp/b200sr_v", verbose=False)
+    gen = b200sr.SyntheticTripletGenerator(B, 256, 256, device=dev, seed=1)
+    x, y = gen.next()
+    ms = timed(lambda: dtr.train_step(x, y), steps=4, warmup=2)
+    # 1463 GFLOP forward per sample, x3 for the train step
+    out["deepcnn_train"] = {"ms_per_step": ms, "triplets_per_s": B / ms * 1e3, "tflops": 3 * 1463.0 * B / ms}
+    dm.eval()
+    with torch.no_grad():
+        ms = timed(lambda: dm(x), steps=4, warmup=2)
+    out["deepcnn_infer"] = {"ms_per_batch": ms, "triplets_per_s": B / ms * 1e3, "tflops": 1463.0 * B / ms}
 print(json.dumps(out))
