@@ -770,7 +770,7 @@ int b200sr_bn_bwd_apply_fused(const void* dy, int dy_pix_stride, int dy_c_off, c
     const int PB = 256 / CV;
     long long blocks = (npix + static_cast<long long>(PB) * BNB_UNROLL - 1) / (static_cast<long long>(PB) * BNB_UNROLL);
     if (blocks > num_sms() * 8) blocks = num_sms() * 8;
-    bn_bwd_apply_fused_kernel<<<static_cast<int>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+    bn_bwd_apply_fused_kernel<false><<<static_cast<int>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         static_cast<const __nv_bfloat16*>(dy), dy_pix_stride, dy_c_off, static_cast<const __nv_bfloat16*>(z), C, scale,
         shift, mean, invstd, sums, replicas, static_cast<float>(count), dgamma, dbeta, static_cast<__nv_bfloat16*>(dz),
         npix, nullptr);
@@ -790,10 +790,10 @@ int b200sr_bn_bwd_masked(const void* dy, const void* z, const void* mask_src, in
     long long blocks = (npix + static_cast<long long>(PB) * BNB_UNROLL - 1) / (static_cast<long long>(PB) * BNB_UNROLL);
     if (blocks > num_sms() * 8) blocks = num_sms() * 8;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    bn_bwd_reduce_fast_kernel<<<static_cast<int>(blocks), 256, 0, st>>>(
+    bn_bwd_reduce_fast_kernel<true><<<static_cast<int>(blocks), 256, 0, st>>>(
         static_cast<const __nv_bfloat16*>(dy), C, 0, static_cast<const __nv_bfloat16*>(z), C, scale, shift, mean, invstd,
         sums, replicas, npix, static_cast<const __nv_bfloat16*>(mask_src));
-    bn_bwd_apply_fused_kernel<<<static_cast<int>(blocks), 256, 0, st>>>(
+    bn_bwd_apply_fused_kernel<true><<<static_cast<int>(blocks), 256, 0, st>>>(
         static_cast<const __nv_bfloat16*>(dy), C, 0, static_cast<const __nv_bfloat16*>(z), C, scale, shift, mean, invstd,
         sums, replicas, static_cast<float>(count), dgamma, dbeta, static_cast<__nv_bfloat16*>(dz), npix,
         static_cast<const __nv_bfloat16*>(mask_src));
@@ -925,7 +925,7 @@ int b200sr_bn_bwd_reduce(const void* dy, int dy_pix_stride, int dy_c_off, const 
         const int PB = 256 / CV;
         long long blocks = (npix + static_cast<long long>(PB) * BNB_UNROLL - 1) / (static_cast<long long>(PB) * BNB_UNROLL);
         if (blocks > num_sms() * 8) blocks = num_sms() * 8;
-        bn_bwd_reduce_fast_kernel<<<static_cast<int>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        bn_bwd_reduce_fast_kernel<false><<<static_cast<int>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
             static_cast<const __nv_bfloat16*>(dy), dy_pix_stride, dy_c_off, static_cast<const __nv_bfloat16*>(z), C,
             scale, shift, mean, invstd, sums, replicas, npix, nullptr);
         return check_launch("bn_bwd_reduce_fast_kernel");

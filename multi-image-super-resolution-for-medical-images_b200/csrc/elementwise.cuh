@@ -751,6 +751,7 @@ __device__ __forceinline__ F8 unpack8(const uint4& u) {
 
 constexpr int BNB_UNROLL = 4;
 
+template <bool MASKED>
 __global__ void __launch_bounds__(256, 3) bn_bwd_reduce_fast_kernel(const __nv_bfloat16* __restrict__ dy, int dy_stride,
                                                                  int dy_coff, const __nv_bfloat16* __restrict__ z,
                                                                  int C, const float* __restrict__ scale,
@@ -772,14 +773,14 @@ __global__ void __launch_bounds__(256, 3) bn_bwd_reduce_fast_kernel(const __nv_b
     for (int k = 0; k < 8; ++k) s1[k] = s2[k] = 0.f;
     const long long step = static_cast<long long>(gridDim.x) * PB;
     for (long long p0 = static_cast<long long>(blockIdx.x) * PB + pl; p0 < npix; p0 += step * BNB_UNROLL) {
-        uint4 g[BNB_UNROLL], zz[BNB_UNROLL], mm[BNB_UNROLL];
+        uint4 g[BNB_UNROLL], zz[BNB_UNROLL], mm[MASKED ? BNB_UNROLL : 1];
 #pragma unroll
         for (int u = 0; u < BNB_UNROLL; ++u) {
             const long long p = p0 + u * step;
             if (p < npix) {
                 g[u] = ld_stream(dy + p * dy_stride + dy_coff + c);
                 zz[u] = ld_stream(z + p * C + c);
-                if (mask_src != nullptr) mm[u] = ld_stream(mask_src + p * C + c);
+                if (MASKED) mm[MASKED ? u : 0] = ld_stream(mask_src + p * C + c);
             }
         }
 #pragma unroll
@@ -787,8 +788,8 @@ __global__ void __launch_bounds__(256, 3) bn_bwd_reduce_fast_kernel(const __nv_b
             if (p0 + u * step < npix) {
                 const F8 gf = unpack8(g[u]), zf = unpack8(zz[u]);
                 F8 mf;
-                if (mask_src != nullptr) {
-                    mf = unpack8(mm[u]);
+                if (MASKED) {
+                    mf = unpack8(mm[MASKED ? u : 0]);
                 } else {
 #pragma unroll
                     for (int k = 0; k < 8; ++k) mf.v[k] = fmaf(zf.v[k], sc.v[k], sh.v[k]);
@@ -873,6 +874,7 @@ __global__ void __launch_bounds__(256, 3) bn_bwd_apply_fast_kernel(const __nv_bf
 
 // BatchNorm backward apply with the finalize step folded in: a thread derives c1 = S1/N, c2 = S2/N of its own 8
 // channels from the replicas of the reduce pass; the first pixel lane of block 0 publishes dgamma / dbeta.
+template <bool MASKED>
 __global__ void __launch_bounds__(256, 3) bn_bwd_apply_fused_kernel(
     const __nv_bfloat16* __restrict__ dy, int dy_stride, int dy_coff, const __nv_bfloat16* __restrict__ z, int C,
     const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ mean,
@@ -916,14 +918,14 @@ __global__ void __launch_bounds__(256, 3) bn_bwd_apply_fused_kernel(
     }
     const long long step = static_cast<long long>(gridDim.x) * PB;
     for (long long p0 = static_cast<long long>(blockIdx.x) * PB + pl; p0 < npix; p0 += step * BNB_UNROLL) {
-        uint4 g[BNB_UNROLL], zz[BNB_UNROLL], mm[BNB_UNROLL];
+        uint4 g[BNB_UNROLL], zz[BNB_UNROLL], mm[MASKED ? BNB_UNROLL : 1];
 #pragma unroll
         for (int u = 0; u < BNB_UNROLL; ++u) {
             const long long p = p0 + u * step;
             if (p < npix) {
                 g[u] = ld_stream(dy + p * dy_stride + dy_coff + c);
                 zz[u] = ld_stream(z + p * C + c);
-                if (mask_src != nullptr) mm[u] = ld_stream(mask_src + p * C + c);
+                if (MASKED) mm[MASKED ? u : 0] = ld_stream(mask_src + p * C + c);
             }
         }
 #pragma unroll
@@ -932,8 +934,8 @@ __global__ void __launch_bounds__(256, 3) bn_bwd_apply_fused_kernel(
             if (p < npix) {
                 const F8 gf = unpack8(g[u]), zf = unpack8(zz[u]);
                 F8 mf;
-                if (mask_src != nullptr) {
-                    mf = unpack8(mm[u]);
+                if (MASKED) {
+                    mf = unpack8(mm[MASKED ? u : 0]);
                 } else {
 #pragma unroll
                     for (int k = 0; k < 8; ++k) mf.v[k] = fmaf(zf.v[k], sc.v[k], sh.v[k]);
