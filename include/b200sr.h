@@ -206,6 +206,56 @@ int b200sr_conv1x1(const void* a, int a_pix_stride, int a_c_off, int Ca, const v
 int b200sr_conv1x1_wgrad(const void* x, int x_pix_stride, int x_c_off, int Cin, const void* dz, int dz_pix_stride,
                          int dz_c_off, int Cout, int B, int H, int W, float* G, void* stream);
 
+/* ---- Fast-DDPM denoiser (reference src/ModelLoader.py:471-636; SURVEY §8(f) row 4, BASELINE configs[4]) ---- */
+/* sinusoidal_timestep_embedding (:475-487) + time_mlp Linear/ReLU/Linear (:547-551, :563-564). t: int64 [B];
+ * w1,w2: (256,256) f32 row-major [out][in]; emb, hid (kept for backward) and e: [B][256] f32. */
+int b200sr_fd_time_mlp_fwd(const int64_t* t, const float* w1, const float* b1, const float* w2, const float* b2,
+                           float* emb, float* hid, float* e, int B, void* stream);
+/* Contribution of the spatially tiled time embedding (:565-568) to inc.block.0, as a per-sample bias for each of the 9
+ * border classes: tb[b][cls][co] = bias[co] + sum_{taps inside the image for cls} sum_c w[co][3+c][tap]*e[b][c].
+ * w: the (64,259,3,3) parameter itself; tb: [B][9][64] f32, cls = 3*rowclass + colclass (0 first, 1 interior, 2 last). */
+int b200sr_fd_time_bias(const float* e, const float* w, const float* bias, float* tb, int B, void* stream);
+/* inc.block.0 + ReLU (:521-527 as instantiated at :554): 3-channel direct conv + tb. Input channel 0 is
+ * coef[b].x*x0 + coef[b].y*noise (q_sample fused, :597-599) when noise != NULL, else x0 (sampling, :624); channels
+ * 1,2 = cond (B,2,H,W) f32. coef: DEVICE [B][2] f32. out: (B,H,W,64) bf16 dense, post-ReLU. */
+int b200sr_fd_convin_fwd(const float* x0, const float* noise, const float* coef, const float* cond, const float* w,
+                         const float* tb, void* out, int B, int H, int W, void* stream);
+/* Weight gradient of the 3 image channels, ADDED into dw (64,259,3,3) f32 at [co][0..2][tap]. */
+int b200sr_fd_convin_wgrad(const float* x0, const float* noise, const float* coef, const float* cond, const void* dz,
+                           float* dw, int B, int H, int W, void* stream);
+/* ReLU backward fused with the per-sample bias-gradient sums of a Conv+ReLU layer: dz = dy*[act > 0] (dense),
+ * ps[b][c] += sum over the sample's pixels of dz. dy / act may be channel slots. C/8 must divide 256. */
+int b200sr_fd_relu_bwd_bias(const void* dy, int dy_pix_stride, int dy_c_off, const void* act, int act_pix_stride,
+                            int act_c_off, void* dz, float* ps, int C, int B, int H, int W, void* stream);
+typedef struct b200sr_fd_bias_job {
+    const float* ps; /* [B][C] */
+    float* dst;      /* [C] bias gradient, ADDED into */
+    int32_t C;
+    int32_t pad;
+} b200sr_fd_bias_job;
+/* dst[c] += sum_b ps[b][c] for a DEVICE table of jobs (all conv biases of the network in one launch). */
+int b200sr_fd_bias_finish(const b200sr_fd_bias_job* jobs, int njobs, int B, void* stream);
+/* Backward of everything the time embedding touches: tap sums S[b][tap][co] of dz (B,H,W,64) from its border rows /
+ * columns and ps; dw_in (64,259,3,3)[co][3+c][tap] += sum_b e*S; de = W^T S; time_mlp weight / bias gradients
+ * (ADDED into). S [B][9][64], de and dh [B][256] are caller-provided scratch. */
+int b200sr_fd_time_bwd(const void* dz, const float* ps, const float* e, const float* emb, const float* hid,
+                       const float* w_in, const float* w2, float* S, float* de, float* dh, float* dw_in, float* dw1,
+                       float* db1, float* dw2, float* db2, int B, int H, int W, void* stream);
+/* F.interpolate(scale_factor=2) nearest (:579,582) written into a concat slot (replaces torch.cat :580,583), and its
+ * backward (2x2 block sum). in / din: (B,h,w,C) dense; out / dout: (B,2h,2w,C) slot. */
+int b200sr_fd_upsample2x_fwd(const void* in, int C, void* out, int out_pix_stride, int out_c_off, int B, int h, int w,
+                             void* stream);
+int b200sr_fd_upsample2x_bwd(const void* dout, int dout_pix_stride, int dout_c_off, int C, void* din, int B, int h, int w,
+                             void* stream);
+/* FastNoiseScheduler.q_sample (:515-518): out = coef[b].x*x0 + coef[b].y*noise over (B,1,H,W) f32. */
+int b200sr_fd_q_sample(const float* x0, const float* noise, const float* coef, float* out, int B, int H, int W,
+                       void* stream);
+/* One deterministic DDIM update of FastDDPM.sample (:626-633), in place on x; clamp(-1,1) when clamp != 0 (:635). */
+int b200sr_fd_ddim_update(float* x, const float* eps, float a_bar, float a_bar_prev, int clamp, int64_t n, void* stream);
+/* torch.nn.utils.clip_grad_norm_ over a flat gradient buffer: g *= min(1, max_norm/(pre_scale*||g|| + 1e-6)).
+ * sumsq: DEVICE double scratch (zeroed here). */
+int b200sr_grad_clip(float* g, int64_t n, double* sumsq, float max_norm, float pre_scale, void* stream);
+
 /* final nn.Conv2d(64,1,1) (unet_model.py:80,117): fp32 (B,1,H,W) output; and its backward. */
 int b200sr_head_fwd(const void* act, const float* w, const float* b, float* out, int64_t npix, void* stream);
 int b200sr_head_bwd(const float* dout, const void* act, const float* w, void* dact, float* dw, float* db,

@@ -2,9 +2,9 @@
 
 Same `load_model(model_name, device)` contract: known names, `ValueError` for unknown names,
 `FileNotFoundError` for a missing checkpoint, three accepted checkpoint layouts (`generator_state_dict`,
-`model_state_dict`, bare state_dict), result returned in eval mode. The models on the b200sr hot path
-('unet', 'unet_combined') and its first "next" row ('progressive_unet') are implemented natively; the other registry names are recognised but refuse to load
-(they are out of scope) instead of silently falling back to torch modules.
+`model_state_dict`, bare state_dict), result returned in eval mode. Every name of the reference registry is
+implemented natively on the b200sr kernels: 'unet' / 'unet_combined' (the hot path), 'progressive_unet', 'deepcnn',
+'unet_gan' (the generator; it is structurally a UNetStage) and 'fastddpm'. There is no fallback to torch modules.
 """
 from __future__ import annotations
 
@@ -13,8 +13,11 @@ import os
 import torch
 
 from .unet_model import UNet, UNetBlock  # noqa: F401  (re-exported like the reference module does)
-from .progressive import ProgressiveUNet, ProgressiveUNetBlock, UNetStage  # noqa: F401
+from .progressive import (GANUNetBlock, ProgressiveUNet, ProgressiveUNetBlock, UNetGenerator,  # noqa: F401
+                          UNetStage)
 from .deepcnn import DeepCNN, ResidualBlock  # noqa: F401
+from .fastddpm import (DoubleConv, FastDDPM, FastNoiseScheduler, UNet2D,  # noqa: F401
+                       sinusoidal_timestep_embedding)
 
 _UNET_KW = {'in_channels': 2, 'out_channels': 1, 'init_features': 64}
 
@@ -25,8 +28,8 @@ CHECKPOINT_MAP = {
     'deepcnn': ('deepcnn_best.pt', DeepCNN, {'in_channels': 2, 'out_channels': 1, 'num_blocks': [2, 2, 2, 2],
                                              'base_features': 64}),
     'progressive_unet': ('progressive_unet_best.pt', ProgressiveUNet, {'base_features': 64}),
-    'unet_gan': ('unet_gan_best.pt', None, {}),
-    'fastddpm': ('fastddpm_advanced_best.pth', None, {}),
+    'unet_gan': ('unet_gan_best.pt', UNetGenerator, {'in_channels': 2, 'out_channels': 1, 'base_features': 64}),
+    'fastddpm': ('fastddpm_advanced_best.pth', FastDDPM, {'T': 10}),
 }
 
 
@@ -55,6 +58,8 @@ def load_model(model_name, device='cuda', root=None, verbose=True):
         raise NotImplementedError(
             f"'{key}' is in the reference registry but outside the b200sr hot path (UNet only); "
             "load it with the reference ModelLoader")
+    if cls is FastDDPM:  # the reference passes the device into the constructor (:668)
+        kwargs = dict(kwargs, device=device)
     model = cls(**kwargs).to(device)
     checkpoint = torch.load(path, map_location=device)
     if isinstance(checkpoint, dict) and 'generator_state_dict' in checkpoint:

@@ -13,7 +13,10 @@ from .losses import CombinedLoss, ssim_window  # noqa: F401
 from .perceptual import PerceptualLoss, VGG16Features  # noqa: F401
 from .ModelLoader import load_model  # noqa: F401
 from .deepcnn import DeepCNN, DeepCNNTrainer, ResidualBlock  # noqa: F401
-from .progressive import ProgressiveUNet, ProgressiveUNetBlock, ProgressiveUNetTrainer, UNetStage  # noqa: F401
+from .progressive import (GANUNetBlock, ProgressiveUNet, ProgressiveUNetBlock, ProgressiveUNetTrainer,  # noqa: F401
+                          UNetGenerator, UNetStage)
+from .fastddpm import (DoubleConv, FastDDPM, FastDDPMTrainer, FastNoiseScheduler, UNet2D,  # noqa: F401
+                       sinusoidal_timestep_embedding)
 from .data import DevicePrefetcher, SyntheticTripletGenerator  # noqa: F401
 
 __version__ = "0.1.0"

@@ -59,6 +59,18 @@ _SIGNATURES = {
     "b200sr_headw_bwd": [_P, _P, c_int, _P, _P, _P, _P, c_int64, _P],
     "b200sr_conv1x1": [_P, c_int, c_int, c_int, _P, c_int, c_int, c_int, c_int, _P, c_int, c_int, _P, c_int, _P],
     "b200sr_conv1x1_wgrad": [_P, c_int, c_int, c_int, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P],
+    "b200sr_fd_time_mlp_fwd": [_P, _P, _P, _P, _P, _P, _P, _P, c_int, _P],
+    "b200sr_fd_time_bias": [_P, _P, _P, _P, c_int, _P],
+    "b200sr_fd_convin_fwd": [_P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, _P],
+    "b200sr_fd_convin_wgrad": [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, _P],
+    "b200sr_fd_relu_bwd_bias": [_P, c_int, c_int, _P, c_int, c_int, _P, _P, c_int, c_int, c_int, c_int, _P],
+    "b200sr_fd_bias_finish": [_P, c_int, c_int, _P],
+    "b200sr_fd_time_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, _P],
+    "b200sr_fd_upsample2x_fwd": [_P, c_int, _P, c_int, c_int, c_int, c_int, c_int, _P],
+    "b200sr_fd_upsample2x_bwd": [_P, c_int, c_int, c_int, _P, c_int, c_int, c_int, _P],
+    "b200sr_fd_q_sample": [_P, _P, _P, _P, c_int, c_int, c_int, _P],
+    "b200sr_fd_ddim_update": [_P, _P, c_float, c_float, c_int, c_int64, _P],
+    "b200sr_grad_clip": [_P, c_int64, _P, c_float, c_float, _P],
     "b200sr_head_fwd": [_P, _P, _P, _P, c_int64, _P],
     "b200sr_head_bwd": [_P, _P, _P, _P, _P, _P, c_int64, _P],
     "b200sr_mse_ssim": [_P, _P, _P, _P, c_int, c_int, c_int, _P, c_int, c_float, c_float, c_float, c_float, c_float,

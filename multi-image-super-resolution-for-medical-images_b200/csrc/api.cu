@@ -10,6 +10,7 @@
 #include "elementwise.cuh"
 #include "conv3x3.cuh"
 #include "deepcnn.cuh"
+#include "fastddpm.cuh"
 #include "igemm.cuh"
 #include "loss.cuh"
 #include "wgrad.cuh"
@@ -888,6 +889,138 @@ int b200sr_conv1x1_wgrad(const void* x, int x_pix_stride, int x_c_off, int Cin, 
                          int dz_c_off, int Cout, int B, int H, int W, float* G, void* stream) {
     return run_wgrad(0, x, x_pix_stride, x_c_off, Cin, 1, dz, dz_pix_stride, dz_c_off, Cout, B, H, W, G,
                      static_cast<cudaStream_t>(stream));
+}
+
+// ---- Fast-DDPM denoiser (reference src/ModelLoader.py:471-636) -------------------------------------------------
+int b200sr_fd_time_mlp_fwd(const int64_t* t, const float* w1, const float* b1, const float* w2, const float* b2,
+                           float* emb, float* hid, float* e, int B, void* stream) {
+    B2_CHECK_ARG(t && w1 && b1 && w2 && b2 && emb && hid && e && B > 0);
+    fd_time_mlp_fwd_kernel<<<B, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const long long*>(t), w1, b1, w2, b2, emb, hid, e);
+    return check_launch("fd_time_mlp_fwd_kernel");
+}
+
+int b200sr_fd_time_bias(const float* e, const float* w, const float* bias, float* tb, int B, void* stream) {
+    B2_CHECK_ARG(e && w && bias && tb && B > 0);
+    fd_time_bias_kernel<<<B, 576, 0, static_cast<cudaStream_t>(stream)>>>(e, w, bias, tb);
+    return check_launch("fd_time_bias_kernel");
+}
+
+int b200sr_fd_convin_fwd(const float* x0, const float* noise, const float* coef, const float* cond, const float* w,
+                         const float* tb, void* out, int B, int H, int W, void* stream) {
+    B2_CHECK_ARG(x0 && cond && w && tb && out && (noise == nullptr || coef != nullptr));
+    B2_CHECK_ARG(B > 0 && H % C1_TILE == 0 && W % C1_TILE == 0 && aligned16(out) && aligned16(tb));
+    const int tiles = B * (H / C1_TILE) * (W / C1_TILE);
+    const int grid = tiles < num_sms() * 6 ? tiles : num_sms() * 6;
+    fd_convin_fwd_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        x0, noise, reinterpret_cast<const float2*>(coef), cond, w, tb, static_cast<__nv_bfloat16*>(out), H, W, tiles);
+    return check_launch("fd_convin_fwd_kernel");
+}
+
+int b200sr_fd_convin_wgrad(const float* x0, const float* noise, const float* coef, const float* cond, const void* dz,
+                           float* dw, int B, int H, int W, void* stream) {
+    B2_CHECK_ARG(x0 && cond && dz && dw && (noise == nullptr || coef != nullptr));
+    B2_CHECK_ARG(B > 0 && H % C1_TILE == 0 && W % C1_TILE == 0 && aligned16(dz));
+    const int tiles = B * (H / C1_TILE) * (W / C1_TILE);
+    const int grid = tiles < num_sms() * 2 ? tiles : num_sms() * 2;
+    fd_convin_wgrad_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        x0, noise, reinterpret_cast<const float2*>(coef), cond, static_cast<const __nv_bfloat16*>(dz), dw, H, W, tiles);
+    return check_launch("fd_convin_wgrad_kernel");
+}
+
+int b200sr_fd_relu_bwd_bias(const void* dy, int dy_pix_stride, int dy_c_off, const void* act, int act_pix_stride,
+                            int act_c_off, void* dz, float* ps, int C, int B, int H, int W, void* stream) {
+    B2_CHECK_ARG(dy && act && dz && ps && B > 0 && H > 0 && W > 0);
+    B2_CHECK_ARG(C % 8 == 0 && C / 8 <= 256 && 256 % (C / 8) == 0);
+    B2_CHECK_ARG(dy_pix_stride % 8 == 0 && dy_c_off % 8 == 0 && act_pix_stride % 8 == 0 && act_c_off % 8 == 0);
+    B2_CHECK_ARG(aligned16(dy) && aligned16(act) && aligned16(dz));
+    const int HW = H * W;
+    const int rows = 256 / (C / 8);
+    int bx = (HW + rows * 8 - 1) / (rows * 8);  // >= 8 pixels per thread
+    const int cap = (num_sms() * 8 + B - 1) / B;
+    if (bx > cap) bx = cap;
+    if (bx < 1) bx = 1;
+    dim3 grid(bx, B);
+    fd_relu_bwd_bias_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16*>(dy), dy_pix_stride, dy_c_off, static_cast<const __nv_bfloat16*>(act),
+        act_pix_stride, act_c_off, static_cast<__nv_bfloat16*>(dz), ps, C, HW);
+    return check_launch("fd_relu_bwd_bias_kernel");
+}
+
+int b200sr_fd_bias_finish(const b200sr_fd_bias_job* jobs, int njobs, int B, void* stream) {
+    B2_CHECK_ARG(jobs && njobs > 0 && B > 0);
+    static_assert(sizeof(b200sr_fd_bias_job) == sizeof(FdBiasJob), "FdBiasJob ABI mismatch");
+    fd_bias_finish_kernel<<<njobs, 256, 0, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const FdBiasJob*>(jobs), B);
+    return check_launch("fd_bias_finish_kernel");
+}
+
+int b200sr_fd_time_bwd(const void* dz, const float* ps, const float* e, const float* emb, const float* hid,
+                       const float* w_in, const float* w2, float* S, float* de, float* dh, float* dw_in, float* dw1,
+                       float* db1, float* dw2, float* db2, int B, int H, int W, void* stream) {
+    B2_CHECK_ARG(dz && ps && e && emb && hid && w_in && w2 && S && de && dh && dw_in && dw1 && db1 && dw2 && db2);
+    B2_CHECK_ARG(B > 0 && H >= 2 && W >= 2 && aligned16(dz));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    fd_tap_sums_kernel<<<B, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(dz), ps, S, H, W);
+    fd_time_wgrad_kernel<<<C1_COUT, 256, 0, st>>>(e, S, dw_in, B);
+    fd_time_dgrad_kernel<<<B, 256, 0, st>>>(w_in, S, de);
+    fd_time_mlp_bwd_dh_kernel<<<B, 256, 0, st>>>(de, hid, w2, dh);
+    fd_time_mlp_bwd_w_kernel<<<dim3(FD_TDIM, 2), 256, 0, st>>>(de, dh, hid, emb, dw1, db1, dw2, db2, B);
+    return check_launch("fd_time_bwd kernels");
+}
+
+int b200sr_fd_upsample2x_fwd(const void* in, int C, void* out, int out_pix_stride, int out_c_off, int B, int h, int w,
+                             void* stream) {
+    B2_CHECK_ARG(in && out && C % 8 == 0 && out_pix_stride % 8 == 0 && out_c_off % 8 == 0 && B > 0 && h > 0 && w > 0);
+    B2_CHECK_ARG(aligned16(in) && aligned16(out));
+    const long long total = static_cast<long long>(B) * 4 * h * w * (C / 8);
+    const long long blocks = (total + 255) / 256;
+    const int grid = static_cast<int>(blocks < num_sms() * 16 ? blocks : num_sms() * 16);
+    fd_upsample2x_fwd_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16*>(in), C, static_cast<__nv_bfloat16*>(out), out_pix_stride, out_c_off, h, w, total);
+    return check_launch("fd_upsample2x_fwd_kernel");
+}
+
+int b200sr_fd_upsample2x_bwd(const void* dout, int dout_pix_stride, int dout_c_off, int C, void* din, int B, int h, int w,
+                             void* stream) {
+    B2_CHECK_ARG(dout && din && C % 8 == 0 && dout_pix_stride % 8 == 0 && dout_c_off % 8 == 0 && B > 0 && h > 0 && w > 0);
+    B2_CHECK_ARG(aligned16(dout) && aligned16(din));
+    const long long total = static_cast<long long>(B) * h * w * (C / 8);
+    const long long blocks = (total + 255) / 256;
+    const int grid = static_cast<int>(blocks < num_sms() * 16 ? blocks : num_sms() * 16);
+    fd_upsample2x_bwd_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16*>(dout), dout_pix_stride, dout_c_off, C, static_cast<__nv_bfloat16*>(din), h, w, total);
+    return check_launch("fd_upsample2x_bwd_kernel");
+}
+
+int b200sr_fd_q_sample(const float* x0, const float* noise, const float* coef, float* out, int B, int H, int W,
+                       void* stream) {
+    B2_CHECK_ARG(x0 && noise && coef && out && B > 0 && H > 0 && W > 0);
+    const long long total = static_cast<long long>(B) * H * W;
+    const long long blocks = (total + 255) / 256;
+    const int grid = static_cast<int>(blocks < num_sms() * 8 ? blocks : num_sms() * 8);
+    fd_q_sample_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(x0, noise, reinterpret_cast<const float2*>(coef),
+                                                                            out, H * W, total);
+    return check_launch("fd_q_sample_kernel");
+}
+
+int b200sr_fd_ddim_update(float* x, const float* eps, float a_bar, float a_bar_prev, int clamp, int64_t n, void* stream) {
+    B2_CHECK_ARG(x && eps && n > 0 && a_bar > 0.f && a_bar <= 1.f && a_bar_prev > 0.f && a_bar_prev <= 1.f);
+    const long long blocks = (n + 255) / 256;
+    const int grid = static_cast<int>(blocks < num_sms() * 8 ? blocks : num_sms() * 8);
+    fd_ddim_update_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        x, eps, sqrtf(1.f - a_bar), sqrtf(a_bar), sqrtf(a_bar_prev), sqrtf(1.f - a_bar_prev), clamp, n);
+    return check_launch("fd_ddim_update_kernel");
+}
+
+int b200sr_grad_clip(float* g, int64_t n, double* sumsq, float max_norm, float pre_scale, void* stream) {
+    B2_CHECK_ARG(g && sumsq && n > 0 && max_norm > 0.f && pre_scale > 0.f);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (cudaMemsetAsync(sumsq, 0, sizeof(double), st) != cudaSuccess) return check_launch("grad_clip memset");
+    const long long blocks = (n + 255) / 256;
+    const int grid = static_cast<int>(blocks < num_sms() * 4 ? blocks : num_sms() * 4);
+    fd_sumsq_kernel<<<grid, 256, 0, st>>>(g, n, sumsq);
+    fd_clip_scale_kernel<<<grid, 256, 0, st>>>(g, n, sumsq, max_norm, pre_scale);
+    return check_launch("grad_clip kernels");
 }
 
 int b200sr_maxpool2x2_fwd(const void* in, int in_pix_stride, int in_c_off, int C, void* out, int B, int H, int W,

@@ -160,10 +160,13 @@ __global__ void __launch_bounds__(256) pack_jobs_kernel(const PackJob* __restric
                 break;
             }
             default: {  // UNPACK_*: parameter layout [outer][inner][T], fp32
+                // job.pad > 0: the workspace covers a sub-range of the parameter's inner dimension (a conv whose
+                // input channels were split over two wgrad launches); pad = inner extent of the destination
                 float* dst = static_cast<float*>(job.dst);
+                const int inner_dst = job.pad > 0 ? job.pad : inner_total;
                 for (int idx = tid; idx < PK_TILE * row; idx += 256) {
                     const int o = idx / row, r = idx - o * row;
-                    dst[(static_cast<long long>(o0 + o) * inner_total + i0) * T + r] = tile[o][r];
+                    dst[(static_cast<long long>(o0 + o) * inner_dst + i0) * T + r] = tile[o][r];
                 }
                 break;
             }

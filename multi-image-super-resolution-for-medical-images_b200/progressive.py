@@ -91,6 +91,20 @@ class UNetStage(nn.Module):
         return engine.forward_eval(x)
 
 
+class GANUNetBlock(ProgressiveUNetBlock):
+    """Reference ModelLoader.py:49-63: the same (Conv3x3 bias=False -> BN -> ReLU) x 2 block under its GAN name."""
+
+
+class UNetGenerator(UNetStage):
+    """Generator of the UNet-GAN (reference ModelLoader.py:383-463): structurally a UNetStage (bias-free blocks, head
+    `final`, 118 state_dict entries), so it runs on the same UNetEngine. `load_model('unet_gan')` returns it for
+    inference; the adversarial training loop is out of scope (the discriminator's source is missing from the reference
+    snapshot), supervised fine-tuning works through UNetTrainer."""
+
+    def __init__(self, in_channels=2, out_channels=1, base_features=64):
+        super().__init__(in_channels, out_channels, base_features)
+
+
 class ProgressiveUNet(nn.Module):
     """Reference ModelLoader.py:229-269. Input (B,5,H,W) slices i..i+4; returns (pred_i+1, pred_i+2, pred_i+3)."""
 

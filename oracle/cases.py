@@ -51,3 +51,26 @@ def seeded_slices(B, H, W, seed):
 
 
 DEEPCNN_CASE = dict(B=1, H=32, W=48, seed=1357)
+
+
+FASTDDPM_CASE = dict(B=2, H=64, W=128, seed=9753, noise_seed=77, t=(3, 8), init_seed=11)
+
+
+def fastddpm_inputs(case=None):
+    """cond (B,2,H,W) = (pre, post), target (B,1,H,W), t (B,), noise (B,1,H,W) drawn the way the reference's
+    FastDDPM.forward / .sample draw it: first use of the global generator after torch.manual_seed(noise_seed)."""
+    c = case or FASTDDPM_CASE
+    sl = seeded_slices(c["B"], c["H"], c["W"], c["seed"])
+    cond = sl[:, [0, 2]].contiguous()
+    target = sl[:, 1:2].contiguous()
+    t = torch.tensor(c["t"], dtype=torch.long)
+    torch.manual_seed(c["noise_seed"])
+    noise = torch.randn_like(target)
+    return cond, target, t, noise
+
+
+def fastddpm_state_dict(ctor, case=None):
+    c = case or FASTDDPM_CASE
+    torch.manual_seed(c["init_seed"])
+    model = ctor(T=10, device="cpu")
+    return {k: v.detach().clone() for k, v in model.state_dict().items()}

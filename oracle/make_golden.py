@@ -20,7 +20,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 REF_SRC = "/root/reference/src"
 
-from oracle import cases, ssim_oracle, unet_oracle  # noqa: E402
+from oracle import cases, fastddpm_oracle, ssim_oracle, unet_oracle  # noqa: E402
 
 
 def import_reference():
@@ -202,6 +202,64 @@ def main():
     dpath = os.path.join(ROOT, "tests", "golden", "deepcnn_golden.npz")
     np.savez_compressed(dpath, **dout)
     print("wrote", dpath, os.path.getsize(dpath), "bytes")
+
+    # ---------------- UNet-GAN generator: structurally a UNetStage (ModelLoader.py:383-463) --------------------------
+    torch.manual_seed(21)
+    g_ref = ref_loader.UNetGenerator().state_dict()
+    torch.manual_seed(21)
+    g_mine = b200sr.UNetGenerator().state_dict()
+    assert list(g_ref) == list(g_mine) and all(torch.equal(g_ref[k], g_mine[k]) for k in g_ref)
+    print(f"UNetGenerator state_dict: {len(g_ref)} entries identical (reference vs b200sr)")
+
+    # ---------------- Fast-DDPM registry model ---------------------------------------------------
+    fout = {}
+    sd_f = cases.fastddpm_state_dict(ref_loader.FastDDPM)
+    sd_fm = cases.fastddpm_state_dict(b200sr.FastDDPM)
+    assert list(sd_f) == list(sd_fm) and all(torch.equal(sd_f[k], sd_fm[k]) for k in sd_f)
+    print(f"FastDDPM state_dict: {len(sd_f)} entries identical (reference vs b200sr)")
+    ab_o, idx_o = fastddpm_oracle.schedule(10)
+    ref_sched = ref_loader.FastNoiseScheduler(10, "cpu")
+    mine_sched = b200sr.FastNoiseScheduler(10, "cpu")
+    assert torch.equal(ab_o, ref_sched.alpha_bar) and torch.equal(mine_sched.alpha_bar, ref_sched.alpha_bar)
+    assert torch.equal(mine_sched.beta, ref_sched.beta) and torch.equal(mine_sched.alpha, ref_sched.alpha)
+    c = cases.FASTDDPM_CASE
+    cond, target, t, noise = cases.fastddpm_inputs()
+    fm = ref_loader.FastDDPM(T=10, device="cpu")
+    fm.load_state_dict(sd_f)
+    fm.train()
+    torch.manual_seed(c["noise_seed"])   # FastDDPM.forward draws torch.randn_like(target) first (:597)
+    floss = fm(cond, target, t)
+    floss.backward()
+    fg = {k: p.grad.detach().clone() for k, p in fm.named_parameters()}
+    with torch.no_grad():
+        x_t = ref_sched.q_sample(target, t, noise)
+        eps_ref = fm.unet(torch.cat([x_t, cond], dim=1), t)
+    o_l, o_eps, o_g = fastddpm_oracle.loss_and_grads(sd_f, cond, target, t, noise)
+    worst = max(rel(o_g[k], fg[k]) for k in fg if fg[k].norm() > 1e-9)
+    print(f"fastddpm: oracle vs reference eps {rel(o_eps, eps_ref):.3e}, loss {float(o_l):.8f} vs {floss.item():.8f}, "
+          f"worst grad rel-L2 {worst:.3e}")
+    assert worst < 1e-4 and abs(float(o_l) - floss.item()) < 1e-6 and rel(o_eps, eps_ref) < 1e-6
+    assert torch.equal(fastddpm_oracle.timestep_embedding(t), ref_loader.sinusoidal_timestep_embedding(t, 256))
+    torch.manual_seed(c["noise_seed"] + 1)  # FastDDPM.sample draws torch.randn(B,1,H,W) first (:616)
+    s_ref = fm.sample(cond, "cpu")
+    torch.manual_seed(c["noise_seed"] + 1)
+    x_T = torch.randn(c["B"], 1, c["H"], c["W"])
+    s_o = fastddpm_oracle.sample(sd_f, cond, x_T)
+    print(f"fastddpm: oracle vs reference 10-step sample {rel(s_o, s_ref):.3e}")
+    assert rel(s_o, s_ref) < 1e-5
+    fout["keys"] = np.array(list(sd_f))
+    fout["alpha_bar"] = ref_sched.alpha_bar.numpy()
+    fout["loss"] = np.float64(floss.item())
+    fout["eps"] = eps_ref.numpy()
+    fnames = list(fg)
+    fout["grad_names"] = np.array(fnames)
+    fout["grad_norms"] = np.array([fg[k].double().norm().item() for k in fnames])
+    for k in fnames:
+        fout["grad_head/" + k] = fg[k].reshape(-1)[:cases.GRAD_HEAD].numpy()
+    fout["sample"] = s_ref.numpy()
+    fpath = os.path.join(ROOT, "tests", "golden", "fastddpm_golden.npz")
+    np.savez_compressed(fpath, **fout)
+    print("wrote", fpath, os.path.getsize(fpath), "bytes")
 
 
 if __name__ == "__main__":

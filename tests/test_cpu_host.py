@@ -95,9 +95,9 @@ def test_load_model_contract(tmp_path, capsys):
     torch.save({"generator_state_dict": sd}, tmp_path / "models" / "unet_best.pt")
     m = b200sr.load_model("unet", device="cpu", root=str(tmp_path), verbose=False)
     assert torch.equal(m.state_dict()["final_conv.bias"], sd["final_conv.bias"])
-    # registry names outside the hot path are recognised but refuse to load
+    # a checkpoint of another architecture under a registry name fails loudly (strict load), no silent fallback
     torch.save(sd, tmp_path / "models" / "unet_gan_best.pt")
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(RuntimeError):
         b200sr.load_model("unet_gan", device="cpu", root=str(tmp_path))
 
 

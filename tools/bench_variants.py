@@ -25,7 +25,7 @@ def timed(fn, steps=10, warmup=3):
 
 
 out = {}
-which = sys.argv[1:] or ["perceptual", "progressive", "deepcnn"]
+which = sys.argv[1:] or ["perceptual", "progressive", "deepcnn", "fastddpm"]
 if "perceptual" in which:
     model = b200sr.UNet()
     model.load_state_dict(cases.seeded_state_dict(b200sr.UNet))
@@ -55,4 +55,30 @@ if "deepcnn" in which:
     with torch.no_grad():
         ms = timed(lambda: dm(x), steps=4, warmup=2)
     out["deepcnn_infer"] = {"ms_per_batch": ms, "triplets_per_s": B / ms * 1e3, "tflops": 1463.0 * B / ms}
+if "fastddpm" in which:
+    # BASELINE configs[4]: denoiser train step and T=10 DDIM sampling at 256x256. Algorithmic FLOPs are the
+    # reference's (77.83 GFLOP fwd/sample incl. the 259-channel first conv); the engine folds the tiled time channels
+    # into a bias table and issues 58.5 of them.
+    fm = b200sr.FastDDPM(T=10, device=dev)
+    ftr = b200sr.FastDDPMTrainer(fm, device=dev, model_save_dir="/tmp/b200sr_v", verbose=False)
+    gen = b200sr.SyntheticTripletGenerator(B, 256, 256, device=dev, seed=1)
+    x, y = gen.next()
+    ms = timed(lambda: ftr.train_step(x, y), steps=10, warmup=3)
+    out["fastddpm_train"] = {"ms_per_step": ms, "triplets_per_s": B / ms * 1e3, "tflops_algorithmic": 3 * 77.83 * B / ms,
+                             "tflops_issued": 3 * 58.5 * B / ms}
+    fm.eval()
+    ms = timed(lambda: fm.sample(x, dev), steps=4, warmup=2)
+    out["fastddpm_sample_T10"] = {"ms_per_batch": ms, "slices_per_s": B / ms * 1e3,
+                                  "denoiser_evals_per_s": 10 * B / ms * 1e3, "tflops_algorithmic": 10 * 77.83 * B / ms}
+    if os.environ.get("FD_PROFILE"):
+        from b200sr import _lib
+        _lib.enable_profiling(True)
+        fm.train()
+        for _ in range(3):
+            ftr.train_step(x, y)
+        agg = _lib.collect_profile()
+        _lib.enable_profiling(False)
+        out["fastddpm_train_per_op"] = {k: {"ms_per_step": v["ms"] / 3, "n": v["n"] // 3,
+                                            "tflops": v["flop"] / (v["ms"] / 1e3) / 1e12 if v["flop"] else None}
+                                        for k, v in sorted(agg.items(), key=lambda kv: -kv[1]["ms"])}
 print(json.dumps(out))
