@@ -972,11 +972,13 @@ int b200sr_fd_upsample2x_fwd(const void* in, int C, void* out, int out_pix_strid
                              void* stream) {
     B2_CHECK_ARG(in && out && C % 8 == 0 && out_pix_stride % 8 == 0 && out_c_off % 8 == 0 && B > 0 && h > 0 && w > 0);
     B2_CHECK_ARG(aligned16(in) && aligned16(out));
-    const long long total = static_cast<long long>(B) * 4 * h * w * (C / 8);
+    const long long total = static_cast<long long>(B) * h * w * (C / 8);
+    B2_CHECK_ARG(total < (1ll << 31));
     const long long blocks = (total + 255) / 256;
     const int grid = static_cast<int>(blocks < num_sms() * 16 ? blocks : num_sms() * 16);
     fd_upsample2x_fwd_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        static_cast<const __nv_bfloat16*>(in), C, static_cast<__nv_bfloat16*>(out), out_pix_stride, out_c_off, h, w, total);
+        static_cast<const __nv_bfloat16*>(in), C, static_cast<__nv_bfloat16*>(out), out_pix_stride, out_c_off, h, w,
+        static_cast<unsigned>(total));
     return check_launch("fd_upsample2x_fwd_kernel");
 }
 
@@ -985,10 +987,12 @@ int b200sr_fd_upsample2x_bwd(const void* dout, int dout_pix_stride, int dout_c_o
     B2_CHECK_ARG(dout && din && C % 8 == 0 && dout_pix_stride % 8 == 0 && dout_c_off % 8 == 0 && B > 0 && h > 0 && w > 0);
     B2_CHECK_ARG(aligned16(dout) && aligned16(din));
     const long long total = static_cast<long long>(B) * h * w * (C / 8);
+    B2_CHECK_ARG(total < (1ll << 31));
     const long long blocks = (total + 255) / 256;
     const int grid = static_cast<int>(blocks < num_sms() * 16 ? blocks : num_sms() * 16);
     fd_upsample2x_bwd_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        static_cast<const __nv_bfloat16*>(dout), dout_pix_stride, dout_c_off, C, static_cast<__nv_bfloat16*>(din), h, w, total);
+        static_cast<const __nv_bfloat16*>(dout), dout_pix_stride, dout_c_off, C, static_cast<__nv_bfloat16*>(din), h, w,
+        static_cast<unsigned>(total));
     return check_launch("fd_upsample2x_bwd_kernel");
 }
 

@@ -446,46 +446,49 @@ __global__ void __launch_bounds__(256) fd_time_mlp_bwd_w_kernel(const float* __r
 // F.interpolate(scale_factor=2), mode 'nearest' (:579,582): dense NHWC -> channel slot of the decoder's concat
 // buffer (replaces torch.cat, :580,583); backward = 2x2 block sum.
 // ------------------------------------------------------------------------------------------------
+// One thread = one input pixel x 8 channels: one 16-byte load, four 16-byte stores (32-bit index arithmetic).
 __global__ void __launch_bounds__(256) fd_upsample2x_fwd_kernel(const __nv_bfloat16* __restrict__ in, int C,
                                                                 __nv_bfloat16* __restrict__ out, int out_stride,
-                                                                int out_coff, int h, int w, long long total) {
-    const int c8n = C >> 3;
-    const int W2 = 2 * w, H2 = 2 * h;
-    for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
-         idx += static_cast<long long>(gridDim.x) * blockDim.x) {
-        const int c = static_cast<int>(idx % c8n) * 8;
-        long long r = idx / c8n;
-        const int ww = static_cast<int>(r % W2);
-        r /= W2;
-        const int hh = static_cast<int>(r % H2);
-        const int img = static_cast<int>(r / H2);
-        const uint4 v = *reinterpret_cast<const uint4*>(in + ((static_cast<size_t>(img) * h + (hh >> 1)) * w + (ww >> 1)) * C + c);
-        *reinterpret_cast<uint4*>(out + ((static_cast<size_t>(img) * H2 + hh) * W2 + ww) * out_stride + out_coff + c) = v;
+                                                                int out_coff, int h, int w, unsigned total) {
+    const unsigned c8n = C >> 3;
+    const unsigned W2 = 2 * w;
+    for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        const unsigned c = (idx % c8n) * 8;
+        unsigned r = idx / c8n;
+        const unsigned ww = r % w;
+        r /= w;
+        const unsigned hh = r % h;
+        const unsigned img = r / h;
+        const uint4 v = *reinterpret_cast<const uint4*>(in + static_cast<size_t>(idx) * 8);
+        __nv_bfloat16* o = out + ((static_cast<size_t>(img) * 2 * h + 2 * hh) * W2 + 2 * ww) * out_stride + out_coff + c;
+        *reinterpret_cast<uint4*>(o) = v;
+        *reinterpret_cast<uint4*>(o + out_stride) = v;
+        *reinterpret_cast<uint4*>(o + static_cast<size_t>(W2) * out_stride) = v;
+        *reinterpret_cast<uint4*>(o + static_cast<size_t>(W2 + 1) * out_stride) = v;
     }
 }
 
 __global__ void __launch_bounds__(256) fd_upsample2x_bwd_kernel(const __nv_bfloat16* __restrict__ dout, int dout_stride,
                                                                 int dout_coff, int C, __nv_bfloat16* __restrict__ din,
-                                                                int h, int w, long long total) {
-    const int c8n = C >> 3;
-    const int W2 = 2 * w, H2 = 2 * h;
-    for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
-         idx += static_cast<long long>(gridDim.x) * blockDim.x) {
-        const int c = static_cast<int>(idx % c8n) * 8;
-        long long r = idx / c8n;
-        const int ww = static_cast<int>(r % w);
+                                                                int h, int w, unsigned total) {
+    const unsigned c8n = C >> 3;
+    const unsigned W2 = 2 * w;
+    for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        const unsigned c = (idx % c8n) * 8;
+        unsigned r = idx / c8n;
+        const unsigned ww = r % w;
         r /= w;
-        const int hh = static_cast<int>(r % h);
-        const int img = static_cast<int>(r / h);
-        const size_t p00 = (static_cast<size_t>(img) * H2 + 2 * hh) * W2 + 2 * ww;
-        const F8 a = ld_bf16x8(dout + p00 * dout_stride + dout_coff + c);
-        const F8 b = ld_bf16x8(dout + (p00 + 1) * dout_stride + dout_coff + c);
-        const F8 d = ld_bf16x8(dout + (p00 + W2) * dout_stride + dout_coff + c);
-        const F8 e = ld_bf16x8(dout + (p00 + W2 + 1) * dout_stride + dout_coff + c);
+        const unsigned hh = r % h;
+        const unsigned img = r / h;
+        const __nv_bfloat16* p = dout + ((static_cast<size_t>(img) * 2 * h + 2 * hh) * W2 + 2 * ww) * dout_stride + dout_coff + c;
+        const F8 a = unpack8(ld_stream(p));
+        const F8 b = unpack8(ld_stream(p + dout_stride));
+        const F8 d = unpack8(ld_stream(p + static_cast<size_t>(W2) * dout_stride));
+        const F8 e = unpack8(ld_stream(p + static_cast<size_t>(W2 + 1) * dout_stride));
         F8 o;
 #pragma unroll
         for (int k = 0; k < 8; ++k) o.v[k] = (a.v[k] + b.v[k]) + (d.v[k] + e.v[k]);
-        st_bf16x8(din + ((static_cast<size_t>(img) * h + hh) * w + ww) * C + c, o);
+        st_bf16x8(din + static_cast<size_t>(idx) * 8, o);
     }
 }
 
