@@ -291,6 +291,28 @@ def run_b200sr(args):
                     "step_tflops": TRAIN_GFLOP_PER_TRIPLET * B / ms_per_step,
                     "step_frac_of_peak": TRAIN_GFLOP_PER_TRIPLET * B / ms_per_step / peak}
 
+    # ---- the other BASELINE.json configs built on the same kernels, N=1 only: each is a train step
+    # (or sampler run) at batch 32/GPU, 256x256, timed with CUDA events after warm-up. Reported next to the headline,
+    # never mixed into it. ------------------------------------------------------------------------------------------
+    variants = None
+    if world == 1 and not args.no_variants:
+        import gc
+        import importlib.util
+        del trainer, model, engine, ring, gen
+        gc.collect()
+        torch.cuda.empty_cache()
+        spec = importlib.util.spec_from_file_location("b200sr_bench_variants", os.path.join(ROOT, "tools", "bench_variants.py"))
+        bv = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(bv)
+        variants = {}
+        for name in ("perceptual", "progressive", "deepcnn", "fastddpm"):
+            try:
+                variants.update(bv.run((name,), B))
+            except Exception as exc:  # a variant must never take the headline line down with it
+                variants[name] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+            gc.collect()
+            torch.cuda.empty_cache()
+
     # ---- CPU baseline (bounded sample, rank 0, N=1 only) -------------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -309,6 +331,7 @@ def run_b200sr(args):
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                         "ms_per_step": e2e_ms / args.steps},
                 "gpu_launches": launches_timed, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+                "variants": variants,
                 "inference": {"value": inf_value, "unit": UNIT, "batch_per_gpu": 8, "ms_per_batch": inf_ms / 20,
                               "workload": "BASELINE configs[0]: UNet eval forward (B=8,2,256,256)->(B,1,256,256), "
                                           "fp32 in/out, bf16 tensor-core compute",
@@ -327,6 +350,7 @@ def main():
     ap.add_argument("--impl", default="b200sr", choices=["b200sr", "reference"])
     ap.add_argument("--batch", type=int, default=32, help="per-GPU batch (BASELINE configs[2]: 32)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline sample")
+    ap.add_argument("--no-variants", action="store_true", help="skip the other BASELINE configs (N=1 only)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200sr" else args.warmup
     if args.impl == "reference":
