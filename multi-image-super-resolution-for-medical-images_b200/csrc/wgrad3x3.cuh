@@ -40,12 +40,19 @@ constexpr int WG3_ROW_BYTES = 16 * 128;          // one pixel row of a box: 16 p
 constexpr int WG3_XBOX = 6 * WG3_ROW_BYTES;      // 12288: one (dw, channel chunk) halo box of 6 rows
 constexpr int WG3_ZBOX = 4 * WG3_ROW_BYTES;      // 8192: one 64-channel chunk of dZ, 4 rows
 
+#ifndef WG3_SMEM_BUDGET_KB
+#define WG3_SMEM_BUDGET_KB 225
+#endif
+
 template <int N_TILE, int MODE_B>
 struct WG3Cfg {
     static constexpr int X_BYTES = (MODE_B ? 3 : 2) * WG3_XBOX;
     static constexpr int Z_BYTES = (N_TILE / 64) * WG3_ZBOX;
     static constexpr int STAGE_BYTES = X_BYTES + Z_BYTES;
-    static constexpr int STAGES = (225 * 1024) / STAGE_BYTES > 6 ? 6 : (225 * 1024) / STAGE_BYTES;
+    // shared-memory budget. Measured (tools/bench_overlap.py): capping it at 180 KB so that BatchNorm-backward blocks
+    // can co-reside with a wgrad CTA costs nothing alone but does not buy stream overlap either — at 256^2 / 128^2 the
+    // wgrad kernels themselves stream 2.8-4 TB/s of operands, so they and the BatchNorm passes share the HBM roofline.
+    static constexpr int STAGES = (WG3_SMEM_BUDGET_KB * 1024) / STAGE_BYTES > 6 ? 6 : (WG3_SMEM_BUDGET_KB * 1024) / STAGE_BYTES;
     static constexpr int M_TILES = MODE_B ? 5 : 3;
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 256 + 1024;
     static_assert(M_TILES * N_TILE <= 512, "accumulators exceed TMEM");
