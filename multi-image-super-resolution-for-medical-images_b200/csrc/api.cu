@@ -474,7 +474,9 @@ int launch_wgrad3_t(const CUtensorMap& mx, const CUtensorMap& mz, WG3Args& args,
     const int sms = num_sms();
     int best = 1;
     double best_score = -1.0;
-    const int max_splits = args.total_chunks < 64 ? args.total_chunks : 64;
+    // up to two waves' worth of splits: a single-job layer (Cin = Cout = 64) must still be able to fill every SM
+    const int split_cap = 2 * sms > 64 ? 2 * sms : 64;
+    const int max_splits = args.total_chunks < split_cap ? args.total_chunks : split_cap;
     for (int s = 1; s <= max_splits; ++s) {
         const int per = (args.total_chunks + s - 1) / s;
         const int real = (args.total_chunks + per - 1) / per;
