@@ -227,6 +227,17 @@ int b200sr_fd_convin_wgrad(const float* x0, const float* noise, const float* coe
  * ps[b][c] += sum over the sample's pixels of dz. dy / act may be channel slots. C/8 must divide 256. */
 int b200sr_fd_relu_bwd_bias(const void* dy, int dy_pix_stride, int dy_c_off, const void* act, int act_pix_stride,
                             int act_c_off, void* dz, float* ps, int C, int B, int H, int W, void* stream);
+/* The same ReLU-mask + bias-sum fusion where the gradient is formed by a bandwidth-bound kernel (dz dense, ps ADDED into):
+ * nearest-upsample backward (2x2 block sum of the (B,2h,2w,C) slot `dout`, masked by act (B,h,w,C) > 0); the 1x1 head
+ * backward (outc, :558: dz = dout*w masked by act > 0, plus dw (64) and db (1) ADDED into); MaxPool2d(2,2) backward plus
+ * the skip-connection gradient, masked by the ReLU of the pooled layer (act is both arg-max source and mask). */
+int b200sr_fd_upsample2x_bwd_relu(const void* dout, int dout_pix_stride, int dout_c_off, const void* act, void* dz,
+                                  float* ps, int C, int B, int h, int w, void* stream);
+int b200sr_fd_head_bwd_relu(const float* dout, const void* act, const float* w, void* dz, float* dw, float* db, float* ps,
+                            int B, int H, int W, void* stream);
+int b200sr_fd_maxpool2x2_bwd_relu(const void* act, int act_pix_stride, int act_c_off, const void* dpool, const void* dskip,
+                                  int dskip_pix_stride, int dskip_c_off, int C, void* dz, float* ps, int B, int H, int W,
+                                  void* stream);
 typedef struct b200sr_fd_bias_job {
     const float* ps; /* [B][C] */
     float* dst;      /* [C] bias gradient, ADDED into */

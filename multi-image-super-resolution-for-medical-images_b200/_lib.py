@@ -64,6 +64,9 @@ _SIGNATURES = {
     "b200sr_fd_convin_fwd": [_P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, _P],
     "b200sr_fd_convin_wgrad": [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, _P],
     "b200sr_fd_relu_bwd_bias": [_P, c_int, c_int, _P, c_int, c_int, _P, _P, c_int, c_int, c_int, c_int, _P],
+    "b200sr_fd_upsample2x_bwd_relu": [_P, c_int, c_int, _P, _P, _P, c_int, c_int, c_int, c_int, _P],
+    "b200sr_fd_head_bwd_relu": [_P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, _P],
+    "b200sr_fd_maxpool2x2_bwd_relu": [_P, c_int, c_int, _P, _P, c_int, c_int, c_int, _P, _P, c_int, c_int, c_int, _P],
     "b200sr_fd_bias_finish": [_P, c_int, c_int, _P],
     "b200sr_fd_time_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, _P],
     "b200sr_fd_upsample2x_fwd": [_P, c_int, _P, c_int, c_int, c_int, c_int, c_int, _P],

@@ -979,6 +979,52 @@ int b200sr_fd_relu_bwd_bias(const void* dy, int dy_pix_stride, int dy_c_off, con
     return check_launch("fd_relu_bwd_bias_kernel");
 }
 
+namespace {
+int fd_grid_x(int work_items, int rows, int B) {
+    int bx = (work_items + rows * 8 - 1) / (rows * 8);
+    const int cap = (num_sms() * 8 + B - 1) / B;
+    if (bx > cap) bx = cap;
+    return bx < 1 ? 1 : bx;
+}
+}  // namespace
+
+int b200sr_fd_upsample2x_bwd_relu(const void* dout, int dout_pix_stride, int dout_c_off, const void* act, void* dz,
+                                  float* ps, int C, int B, int h, int w, void* stream) {
+    B2_CHECK_ARG(dout && act && dz && ps && B > 0 && h > 0 && w > 0);
+    B2_CHECK_ARG(C % 8 == 0 && C / 8 <= 256 && 256 % (C / 8) == 0 && dout_pix_stride % 8 == 0 && dout_c_off % 8 == 0);
+    B2_CHECK_ARG(aligned16(dout) && aligned16(act) && aligned16(dz));
+    dim3 grid(fd_grid_x(h * w, 256 / (C / 8), B), B);
+    fd_upsample2x_bwd_relu_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16*>(dout), dout_pix_stride, dout_c_off, static_cast<const __nv_bfloat16*>(act),
+        static_cast<__nv_bfloat16*>(dz), ps, C, h, w);
+    return check_launch("fd_upsample2x_bwd_relu_kernel");
+}
+
+int b200sr_fd_head_bwd_relu(const float* dout, const void* act, const float* w, void* dz, float* dw, float* db, float* ps,
+                            int B, int H, int W, void* stream) {
+    B2_CHECK_ARG(dout && act && w && dz && dw && db && ps && B > 0 && H > 0 && W > 0);
+    B2_CHECK_ARG(aligned16(act) && aligned16(dz) && aligned16(w));
+    dim3 grid(fd_grid_x(H * W, 32, B), B);
+    fd_head_bwd_relu_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        dout, static_cast<const __nv_bfloat16*>(act), w, static_cast<__nv_bfloat16*>(dz), dw, db, ps, H * W);
+    return check_launch("fd_head_bwd_relu_kernel");
+}
+
+int b200sr_fd_maxpool2x2_bwd_relu(const void* act, int act_pix_stride, int act_c_off, const void* dpool, const void* dskip,
+                                  int dskip_pix_stride, int dskip_c_off, int C, void* dz, float* ps, int B, int H, int W,
+                                  void* stream) {
+    B2_CHECK_ARG(act && dpool && dskip && dz && ps && B > 0 && H % 2 == 0 && W % 2 == 0);
+    B2_CHECK_ARG(C % 8 == 0 && C / 8 <= 256 && 256 % (C / 8) == 0);
+    B2_CHECK_ARG(act_pix_stride % 8 == 0 && act_c_off % 8 == 0 && dskip_pix_stride % 8 == 0 && dskip_c_off % 8 == 0);
+    B2_CHECK_ARG(aligned16(act) && aligned16(dpool) && aligned16(dskip) && aligned16(dz));
+    dim3 grid(fd_grid_x((H / 2) * (W / 2), 256 / (C / 8), B), B);
+    fd_maxpool2x2_bwd_relu_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16*>(act), act_pix_stride, act_c_off, static_cast<const __nv_bfloat16*>(dpool),
+        static_cast<const __nv_bfloat16*>(dskip), dskip_pix_stride, dskip_c_off, C, static_cast<__nv_bfloat16*>(dz), ps, H,
+        W);
+    return check_launch("fd_maxpool2x2_bwd_relu_kernel");
+}
+
 int b200sr_fd_bias_finish(const b200sr_fd_bias_job* jobs, int njobs, int B, void* stream) {
     B2_CHECK_ARG(jobs && njobs > 0 && B > 0);
     static_assert(sizeof(b200sr_fd_bias_job) == sizeof(FdBiasJob), "FdBiasJob ABI mismatch");

@@ -315,6 +315,155 @@ __global__ void __launch_bounds__(256) fd_relu_bwd_bias_kernel(const __nv_bfloat
     if (tid < C) atomicAdd(ps + static_cast<size_t>(b) * C + tid, s_c[tid]);
 }
 
+// The same fusion for gradients that are PRODUCED by a bandwidth-bound kernel: the ReLU mask and the bias sums are
+// applied where the gradient is formed, so it never makes a round trip through HBM unmasked.
+//   (1) nearest-upsample backward (2x2 block sum of a concat-slot gradient) -> dz of the layer below
+__global__ void __launch_bounds__(256) fd_upsample2x_bwd_relu_kernel(const __nv_bfloat16* __restrict__ dout, int dout_stride,
+                                                                     int dout_coff, const __nv_bfloat16* __restrict__ act,
+                                                                     __nv_bfloat16* __restrict__ dz, float* __restrict__ ps,
+                                                                     int C, int h, int w) {
+    __shared__ float s_c[256];
+    const int tid = threadIdx.x;
+    const int c8n = C >> 3;
+    const int rows = 256 / c8n;
+    const int cl = tid % c8n, pr = tid / c8n;
+    const int b = blockIdx.y;
+    const int HW = h * w, W2 = 2 * w;
+    if (tid < C) s_c[tid] = 0.f;
+    float acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+    for (int p = blockIdx.x * rows + pr; p < HW; p += gridDim.x * rows) {
+        const int hh = p / w, ww = p - hh * w;
+        const __nv_bfloat16* src =
+            dout + ((static_cast<size_t>(b) * 2 * h + 2 * hh) * W2 + 2 * ww) * dout_stride + dout_coff + cl * 8;
+        const F8 g0 = unpack8(ld_stream(src)), g1 = unpack8(ld_stream(src + dout_stride));
+        const F8 g2 = unpack8(ld_stream(src + static_cast<size_t>(W2) * dout_stride));
+        const F8 g3 = unpack8(ld_stream(src + static_cast<size_t>(W2 + 1) * dout_stride));
+        const size_t q = static_cast<size_t>(b) * HW + p;
+        const F8 a = ld_bf16x8(act + q * C + cl * 8);
+        F8 o;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            // the unfused path stores the 2x2 sum as bf16 before masking: round the same way
+            const float sum = bf16_round((g0.v[k] + g1.v[k]) + (g2.v[k] + g3.v[k]));
+            o.v[k] = a.v[k] > 0.f ? sum : 0.f;
+            acc[k] += o.v[k];
+        }
+        st_bf16x8(dz + q * C + cl * 8, o);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 8; ++k) atomicAdd(&s_c[cl * 8 + k], acc[k]);
+    __syncthreads();
+    if (tid < C) atomicAdd(ps + static_cast<size_t>(b) * C + tid, s_c[tid]);
+}
+
+//   (2) 1x1 head backward (outc, :558,585): d u1 = dOut * w masked by u1 > 0; dW, db of the head; bias sums of up1.2
+__global__ void __launch_bounds__(256) fd_head_bwd_relu_kernel(const float* __restrict__ dout,
+                                                               const __nv_bfloat16* __restrict__ act,  // [B][HW][64]
+                                                               const float* __restrict__ w, __nv_bfloat16* __restrict__ dz,
+                                                               float* __restrict__ dw, float* __restrict__ db,
+                                                               float* __restrict__ ps, int HW) {
+    __shared__ float s_w[64], s_p[64], s_b;
+    const int tid = threadIdx.x, sub = tid & 7, pl = tid >> 3;
+    const int b = blockIdx.y;
+    const F8 wv = ld_f32x8(w + sub * 8);
+    if (tid < 64) s_w[tid] = s_p[tid] = 0.f;
+    if (tid == 0) s_b = 0.f;
+    float accw[8], accp[8], accb = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) accw[k] = accp[k] = 0.f;
+    for (int p = blockIdx.x * 32 + pl; p < HW; p += gridDim.x * 32) {
+        const size_t q = static_cast<size_t>(b) * HW + p;
+        const float g = dout[q];
+        const F8 a = ld_bf16x8(act + q * 64 + sub * 8);
+        F8 o;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            o.v[k] = a.v[k] > 0.f ? bf16_round(g * wv.v[k]) : 0.f;
+            accw[k] = fmaf(g, a.v[k], accw[k]);
+            accp[k] += o.v[k];
+        }
+        st_bf16x8(dz + q * 64 + sub * 8, o);
+        if (sub == 0) accb += g;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        atomicAdd(&s_w[sub * 8 + k], accw[k]);
+        atomicAdd(&s_p[sub * 8 + k], accp[k]);
+    }
+    if (sub == 0) atomicAdd(&s_b, accb);
+    __syncthreads();
+    if (tid < 64) {
+        atomicAdd(dw + tid, s_w[tid]);
+        atomicAdd(ps + static_cast<size_t>(b) * 64 + tid, s_p[tid]);
+    }
+    if (tid == 0) atomicAdd(db, s_b);
+}
+
+//   (3) MaxPool2d(2,2) backward + skip-connection gradient (F.max_pool2d, :574-575; torch.cat skip, :580,583),
+//       masked by the ReLU of the layer that produced the pooled tensor (`act` is both the arg-max source and the mask)
+__global__ void __launch_bounds__(256) fd_maxpool2x2_bwd_relu_kernel(const __nv_bfloat16* __restrict__ act, int act_stride,
+                                                                     int act_coff, const __nv_bfloat16* __restrict__ dpool,
+                                                                     const __nv_bfloat16* __restrict__ dskip,
+                                                                     int dskip_stride, int dskip_coff, int C,
+                                                                     __nv_bfloat16* __restrict__ dz, float* __restrict__ ps,
+                                                                     int H, int W) {
+    __shared__ float s_c[256];
+    const int tid = threadIdx.x;
+    const int c8n = C >> 3;
+    const int rows = 256 / c8n;
+    const int cl = tid % c8n, pr = tid / c8n;
+    const int c = cl * 8;
+    const int b = blockIdx.y;
+    const int W2 = W >> 1, H2 = H >> 1;
+    if (tid < C) s_c[tid] = 0.f;
+    float acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+    for (int win = blockIdx.x * rows + pr; win < H2 * W2; win += gridDim.x * rows) {
+        const int h2 = win / W2, w2 = win - h2 * W2;
+        const size_t p00 = (static_cast<size_t>(b) * H + 2 * h2) * W + 2 * w2;
+        const size_t pix[4] = {p00, p00 + 1, p00 + W, p00 + W + 1};
+        F8 a[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) a[j] = ld_bf16x8(act + pix[j] * act_stride + act_coff + c);
+        const F8 g = unpack8(ld_stream(dpool + ((static_cast<size_t>(b) * H2 + h2) * W2 + w2) * C + c));
+        int arg[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            int best = 0;
+            float bv = a[0].v[k];
+#pragma unroll
+            for (int j = 1; j < 4; ++j)
+                if (a[j].v[k] > bv) {
+                    bv = a[j].v[k];
+                    best = j;
+                }
+            arg[k] = best;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const F8 sk = unpack8(ld_stream(dskip + pix[j] * dskip_stride + dskip_coff + c));
+            F8 o;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const float v = bf16_round(sk.v[k] + ((arg[k] == j) ? g.v[k] : 0.f));
+                o.v[k] = a[j].v[k] > 0.f ? v : 0.f;
+                acc[k] += o.v[k];
+            }
+            st_bf16x8(dz + pix[j] * C + c, o);
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 8; ++k) atomicAdd(&s_c[c + k], acc[k]);
+    __syncthreads();
+    if (tid < C) atomicAdd(ps + static_cast<size_t>(b) * C + tid, s_c[tid]);
+}
+
 struct FdBiasJob {
     const float* ps;  // [B][C]
     float* dst;       // [C] bias gradient, ADDED into

@@ -5,7 +5,11 @@
 // CUDA cores (the FFMA version sat at 27 % of the FP32 peak and 0.9 TB/s): m16n8k16 bf16 `mma.sync` with im2col
 // fragments built in registers from a haloed fp32 tile in shared memory. (tcgen05 would need the im2col tile
 // materialised in swizzled shared memory for 32 K-elements per pixel; at K=32 the legacy warp MMA is already far
-// from being the limiter.) Operands are rounded to bf16 like every other conv of the path; accumulation is fp32.
+// from being the limiter.) The forward pass keeps fp32 operand accuracy with the bf16x3 split (x = x_hi + x_lo,
+// w = w_hi + w_lo; x_hi*w_hi + x_lo*w_hi + x_hi*w_lo, the 2^-18 lo*lo term dropped): the network input is the one
+// tensor of the path that is NOT bf16 already, and rounding it measurably moves the end-to-end parity (Progressive
+// chain 2.4e-2 -> 2.6e-2); three MMAs instead of one are free in an HBM-bound kernel. The weight gradient uses single
+// bf16 operands like every other wgrad of the path (its other operand, dZ, is bf16 anyway). Accumulation is fp32.
 //
 //   forward : D[pixel][co]  = sum_k A[pixel][k] * W[co][k]        (M = 16 pixels of one tile row, N = 64, K = 32)
 //   wgrad   : G[k][co]     += sum_pixel A[pixel][k] * dZ[pixel][co] (M = 32 (k), N = 64, K = pixels)
@@ -93,12 +97,13 @@ __global__ void __launch_bounds__(256, 2) first_conv_mma_fwd_kernel(const FirstC
     __shared__ float s_x[CIN * FC_HT * FC_HT];
     __shared__ __align__(16) __nv_bfloat16 s_out[FC_TILE * FC_TILE * FC_PITCH];
     __shared__ float s_stats[2][FC_COUT];
+    __shared__ uint2 s_blo[2 * 8 * 32];  // low halves of the weight fragments, [ks][nb][lane] (each lane reads its own)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
     const int tiles_w = W / FC_TILE;
     const int tiles_hw = tiles_w * (H / FC_TILE);
 
-    // B fragments (weights), resident in registers: [ks][nb] -> (b0, b1)
+    // B fragments (weights): high halves resident in registers [ks][nb] -> (b0, b1), low halves in shared memory
     uint32_t bfrag[2][8][2];
 #pragma unroll
     for (int ks = 0; ks < 2; ++ks)
@@ -106,14 +111,16 @@ __global__ void __launch_bounds__(256, 2) first_conv_mma_fwd_kernel(const FirstC
         for (int nb = 0; nb < 8; ++nb) {
             const float* wr = wgt + static_cast<size_t>(nb * 8 + g) * w_stride;
             const int k0 = ks * 16 + 2 * t;
-            float v[4];
+            float v[4], lo[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const int k = k0 + (j & 1) + (j >> 1) * 8;
                 v[j] = k < CIN * 9 ? wr[k] : 0.f;
+                lo[j] = v[j] - bf16_round(v[j]);
             }
             bfrag[ks][nb][0] = pack_bf16x2(v[0], v[1]);
             bfrag[ks][nb][1] = pack_bf16x2(v[2], v[3]);
+            if (warp == 0) s_blo[(ks * 8 + nb) * 32 + lane] = make_uint2(pack_bf16x2(lo[0], lo[1]), pack_bf16x2(lo[2], lo[3]));
         }
     // im2col offsets of this thread's 8 K columns
     int koff[2][4];
@@ -153,13 +160,27 @@ __global__ void __launch_bounds__(256, 2) first_conv_mma_fwd_kernel(const FirstC
                     v[j][0] = o >= 0 ? base[o + g] : 0.f;
                     v[j][1] = o >= 0 ? base[o + g + 8] : 0.f;
                 }
-                uint32_t a[4];
+                uint32_t a[4], al[4];
                 a[0] = pack_bf16x2(v[0][0], v[1][0]);
                 a[1] = pack_bf16x2(v[0][1], v[1][1]);
                 a[2] = pack_bf16x2(v[2][0], v[3][0]);
                 a[3] = pack_bf16x2(v[2][1], v[3][1]);
 #pragma unroll
-                for (int nb = 0; nb < 8; ++nb) mma_bf16_16816(acc[nb], a, bfrag[ks][nb][0], bfrag[ks][nb][1]);
+                for (int j = 0; j < 4; ++j) {
+                    v[j][0] -= bf16_round(v[j][0]);
+                    v[j][1] -= bf16_round(v[j][1]);
+                }
+                al[0] = pack_bf16x2(v[0][0], v[1][0]);
+                al[1] = pack_bf16x2(v[0][1], v[1][1]);
+                al[2] = pack_bf16x2(v[2][0], v[3][0]);
+                al[3] = pack_bf16x2(v[2][1], v[3][1]);
+#pragma unroll
+                for (int nb = 0; nb < 8; ++nb) {
+                    const uint2 bl = s_blo[(ks * 8 + nb) * 32 + lane];
+                    mma_bf16_16816(acc[nb], al, bfrag[ks][nb][0], bfrag[ks][nb][1]);
+                    mma_bf16_16816(acc[nb], a, bl.x, bl.y);
+                    mma_bf16_16816(acc[nb], a, bfrag[ks][nb][0], bfrag[ks][nb][1]);
+                }
             }
             // epilogue -> staging tile
             const int h = h0 + row;

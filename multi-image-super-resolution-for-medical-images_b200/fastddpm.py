@@ -23,6 +23,7 @@ with no collective.
 from __future__ import annotations
 
 import math
+import os
 from pathlib import Path
 
 import numpy as np
@@ -179,6 +180,7 @@ class FastDDPMEngine:
         self._plans = {}
         self._packed_version = None
         self._saved = None
+        self.fuse_relu_bwd = os.environ.get("B200SR_FD_UNFUSED") is None
 
     # ---- flat parameter storage ---------------------------------------------------------------------------------
     def _params(self):
@@ -422,44 +424,69 @@ class FastDDPMEngine:
             call("b200sr_conv3x3_dgrad", dz, cv.cout, 0, cv.cout, self._wp(self.wp_dgrad, name), cv.cin, B, h, w, dx,
                  dx_stride, 0, None, 0, st)
 
-        call("b200sr_head_bwd", ptr(dout), ptr(plan["u1"]), ptr(m.outc.weight), g0, self._g(m.outc.weight),
-             self._g(m.outc.bias), B * H * W, st)
+        fused = self.fuse_relu_bwd  # ReLU mask + bias sums applied where a bandwidth-bound kernel forms the gradient
+
+        def ps_of(name):
+            return ps + 4 * plan["ps_off"][name]
+
+        if fused:
+            call("b200sr_fd_head_bwd_relu", ptr(dout), ptr(plan["u1"]), ptr(m.outc.weight), g0, self._g(m.outc.weight),
+                 self._g(m.outc.bias), ps_of("up1.2"), B, H, W, st)
+        else:
+            call("b200sr_head_bwd", ptr(dout), ptr(plan["u1"]), ptr(m.outc.weight), g0, self._g(m.outc.weight),
+                 self._g(m.outc.bias), B * H * W, st)
+            relu_bwd("up1.2", g0, 64, 0, plan["u1"], 64, 0, g0, H, W)
         # up1
-        relu_bwd("up1.2", g0, 64, 0, plan["u1"], 64, 0, g0, H, W)
         wgrad("up1.2", plan["a_u1"], 64, 0, g0, H, W)
         dgrad("up1.2", g0, g1, 64, H, W)
         relu_bwd("up1.0", g1, 64, 0, plan["a_u1"], 64, 0, g1, H, W)
         wgrad("up1.0", plan["cat1"], 192, 0, g1, H, W)
         dgrad("up1.0", g1, ptr(plan["d_cat1"]), 192, H, W)
-        call("b200sr_fd_upsample2x_bwd", ptr(plan["d_cat1"]), 192, 0, 128, g0, B, H1, W1, st)      # -> d u2
+        if fused:
+            call("b200sr_fd_upsample2x_bwd_relu", ptr(plan["d_cat1"]), 192, 0, ptr(plan["u2"]), g0, ps_of("up2.2"), 128,
+                 B, H1, W1, st)
+        else:
+            call("b200sr_fd_upsample2x_bwd", ptr(plan["d_cat1"]), 192, 0, 128, g0, B, H1, W1, st)  # -> d u2
+            relu_bwd("up2.2", g0, 128, 0, plan["u2"], 128, 0, g0, H1, W1)
         # up2
-        relu_bwd("up2.2", g0, 128, 0, plan["u2"], 128, 0, g0, H1, W1)
         wgrad("up2.2", plan["a_u2"], 128, 0, g0, H1, W1)
         dgrad("up2.2", g0, g1, 128, H1, W1)
         relu_bwd("up2.0", g1, 128, 0, plan["a_u2"], 128, 0, g1, H1, W1)
         wgrad("up2.0", plan["cat2"], 384, 0, g1, H1, W1)
         dgrad("up2.0", g1, ptr(plan["d_cat2"]), 384, H1, W1)
-        call("b200sr_fd_upsample2x_bwd", ptr(plan["d_cat2"]), 384, 0, 256, g0, B, H2, W2, st)      # -> d c3
+        if fused:
+            call("b200sr_fd_upsample2x_bwd_relu", ptr(plan["d_cat2"]), 384, 0, ptr(plan["c3"]), g0, ps_of("down2.2"), 256,
+                 B, H2, W2, st)
+        else:
+            call("b200sr_fd_upsample2x_bwd", ptr(plan["d_cat2"]), 384, 0, 256, g0, B, H2, W2, st)  # -> d c3
+            relu_bwd("down2.2", g0, 256, 0, plan["c3"], 256, 0, g0, H2, W2)
         # down2
-        relu_bwd("down2.2", g0, 256, 0, plan["c3"], 256, 0, g0, H2, W2)
         wgrad("down2.2", plan["a_d2"], 256, 0, g0, H2, W2)
         dgrad("down2.2", g0, g1, 256, H2, W2)
         relu_bwd("down2.0", g1, 256, 0, plan["a_d2"], 256, 0, g1, H2, W2)
         wgrad("down2.0", plan["p2"], 128, 0, g1, H2, W2)
         dgrad("down2.0", g1, g0, 128, H2, W2)                                                      # -> d p2
-        call("b200sr_maxpool2x2_bwd", ptr(plan["cat2"]), 384, 256, g0, ptr(plan["d_cat2"]), 384, 256, 128, g1, B, H1, W1,
-             st)                                                                                   # -> d c2 (+ skip)
+        if fused:
+            call("b200sr_fd_maxpool2x2_bwd_relu", ptr(plan["cat2"]), 384, 256, g0, ptr(plan["d_cat2"]), 384, 256, 128, g1,
+                 ps_of("down1.2"), B, H1, W1, st)
+        else:
+            call("b200sr_maxpool2x2_bwd", ptr(plan["cat2"]), 384, 256, g0, ptr(plan["d_cat2"]), 384, 256, 128, g1, B, H1,
+                 W1, st)                                                                           # -> d c2 (+ skip)
+            relu_bwd("down1.2", g1, 128, 0, plan["cat2"], 384, 256, g1, H1, W1)
         # down1
-        relu_bwd("down1.2", g1, 128, 0, plan["cat2"], 384, 256, g1, H1, W1)
         wgrad("down1.2", plan["a_d1"], 128, 0, g1, H1, W1)
         dgrad("down1.2", g1, g0, 128, H1, W1)
         relu_bwd("down1.0", g0, 128, 0, plan["a_d1"], 128, 0, g0, H1, W1)
         wgrad("down1.0", plan["p1"], 64, 0, g0, H1, W1)
         dgrad("down1.0", g0, g1, 64, H1, W1)                                                       # -> d p1
-        call("b200sr_maxpool2x2_bwd", ptr(plan["cat1"]), 192, 128, g1, ptr(plan["d_cat1"]), 192, 128, 64, g0, B, H, W,
-             st)                                                                                   # -> d c1 (+ skip)
+        if fused:
+            call("b200sr_fd_maxpool2x2_bwd_relu", ptr(plan["cat1"]), 192, 128, g1, ptr(plan["d_cat1"]), 192, 128, 64, g0,
+                 ps_of("inc.2"), B, H, W, st)
+        else:
+            call("b200sr_maxpool2x2_bwd", ptr(plan["cat1"]), 192, 128, g1, ptr(plan["d_cat1"]), 192, 128, 64, g0, B, H, W,
+                 st)                                                                               # -> d c1 (+ skip)
+            relu_bwd("inc.2", g0, 64, 0, plan["cat1"], 192, 128, g0, H, W)
         # inc
-        relu_bwd("inc.2", g0, 64, 0, plan["cat1"], 192, 128, g0, H, W)
         wgrad("inc.2", plan["a_inc"], 64, 0, g0, H, W)
         dgrad("inc.2", g0, g1, 64, H, W)
         relu_bwd("inc.0", g1, 64, 0, plan["a_inc"], 64, 0, g1, H, W)

@@ -193,10 +193,11 @@ def conv1(B=2, H=32, W=48, seed=7):
     call("b200sr_conv1_wgrad", ptr(x), ptr(nhwc(dz)), ptr(dw), B, H, W, st())
     torch.cuda.synchronize()
     res["dw"] = rel(dw, refw)
-    # the first-layer kernels feed bf16-rounded inputs / weights to the tensor cores (fp32 accumulation), like every
-    # other conv of the path: against a reference with the SAME operand rounding the result is exact to fp32 round-off
+    # the first-layer wgrad feeds the bf16-rounded input to the tensor cores (fp32 accumulation), like every other wgrad
+    # of the path: against a reference with the SAME operand rounding the result is exact to fp32 round-off; the
+    # forward keeps fp32 operand accuracy (bf16x3 split), so its only error is the bf16 rounding of the stored output
     res["dw_bf16_operands"] = rel(dw, torch.nn.grad.conv2d_weight(bf(x), (64, 2, 3, 3), dz, padding=1))
-    res["out_bf16_operands"] = rel(out, bf(F.conv2d(bf(x), bf(w), padding=1)))
+    res["out_vs_rounded_fp32"] = rel(out, bf(ref))
     return res
 
 
@@ -587,7 +588,7 @@ CHECKS = {
     "convT_wgrad": (convT_wgrad, {}, {"dw": BF16}),
     "convT_wgrad_big": (convT_wgrad, dict(Cin=512, Cout=256, B=1, H=8, W=16), {"dw": BF16}),
     "conv1": (conv1, {}, {"out": BF16, "stats_sum": 1e-3, "stats_sq": 1e-3, "dw": BF16, "dw_bf16_operands": 1e-4,
-                          "out_bf16_operands": 2e-3}),
+                          "out_vs_rounded_fp32": 1e-3}),
     "conv1_dgrad": (conv1_dgrad, {}, {"dx": 1e-5}),
     # DeepCNN-specific kernels
     "conv7": (conv7, {}, {"out": BF16, "stats_sum": 1e-3, "stats_sq": 1e-3, "dw": 1e-3}),

@@ -143,9 +143,12 @@ def test_grad_clip_and_trainer_step_match_oracle(tmp_path):
     # first Adam step moves every weight by ~lr*sign(g): compare the update direction where the gradient is not tiny
     for k, v in m.state_dict().items():
         upd, ref = v.cpu() - sd[k], new_sd[k] - sd[k]
-        big = o_grads[k].abs() > 1e-3 * o_grads[k].abs().max()
+        # Adam's first step is lr*sign(g): elements whose gradient is within bf16 noise of zero may flip, so the sign is
+        # compared where the gradient is at least 5 % of the tensor's largest, and the whole update by its cosine
+        big = o_grads[k].abs() > 5e-2 * o_grads[k].abs().max()
         agree = (torch.sign(upd[big]) == torch.sign(ref[big])).float().mean()
         assert agree > 0.97, (k, float(agree))
+        assert cos(upd, ref) > 0.9, (k, cos(upd, ref))
         assert float(upd.abs().max()) <= 2e-4 * 1.01
     # clip kernel on its own: fp32 exactness
     g = torch.randn(100_003, device="cuda") * 3
