@@ -428,8 +428,12 @@ __global__ void __launch_bounds__(256) fd_maxpool2x2_bwd_relu_kernel(const __nv_
         const size_t p00 = (static_cast<size_t>(b) * H + 2 * h2) * W + 2 * w2;
         const size_t pix[4] = {p00, p00 + 1, p00 + W, p00 + W + 1};
         F8 a[4];
+        uint4 skr[4];  // all loads of the window are issued before the first store
 #pragma unroll
-        for (int j = 0; j < 4; ++j) a[j] = ld_bf16x8(act + pix[j] * act_stride + act_coff + c);
+        for (int j = 0; j < 4; ++j) {
+            a[j] = ld_bf16x8(act + pix[j] * act_stride + act_coff + c);
+            skr[j] = ld_stream(dskip + pix[j] * dskip_stride + dskip_coff + c);
+        }
         const F8 g = unpack8(ld_stream(dpool + ((static_cast<size_t>(b) * H2 + h2) * W2 + w2) * C + c));
         int arg[8];
 #pragma unroll
@@ -446,7 +450,7 @@ __global__ void __launch_bounds__(256) fd_maxpool2x2_bwd_relu_kernel(const __nv_
         }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const F8 sk = unpack8(ld_stream(dskip + pix[j] * dskip_stride + dskip_coff + c));
+            const F8 sk = unpack8(skr[j]);
             F8 o;
 #pragma unroll
             for (int k = 0; k < 8; ++k) {

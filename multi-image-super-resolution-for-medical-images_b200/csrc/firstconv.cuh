@@ -71,6 +71,54 @@ __device__ __forceinline__ void fc_load_halo(float* s_x, const FirstConvSrc& src
     }
 }
 
+// register-staged variant: the global loads of the NEXT tile are issued before the MMAs of the current one and written
+// to the other shared-memory buffer afterwards, so their latency is hidden behind a whole tile of work
+template <int CIN>
+struct FcHaloRegs {
+    static constexpr int N = (CIN * FC_HT * FC_HT + 255) / 256;
+    float v[N];
+};
+
+template <int CIN>
+__device__ __forceinline__ void fc_fetch_halo(FcHaloRegs<CIN>& r, const FirstConvSrc& src, int img, int h0, int w0, int H,
+                                              int W, int tid) {
+    float ca = 1.f, cb = 0.f;
+    if (CIN == 3 && src.noise != nullptr) {
+        const float2 c = src.coef[img];
+        ca = c.x;
+        cb = c.y;
+    }
+#pragma unroll
+    for (int n = 0; n < FcHaloRegs<CIN>::N; ++n) {
+        const int i = tid + n * 256;
+        float v = 0.f;
+        if (i < CIN * FC_HT * FC_HT) {
+            const int ci = i / (FC_HT * FC_HT);
+            const int rr = i % (FC_HT * FC_HT);
+            const int hh = h0 + rr / FC_HT - 1, ww = w0 + rr % FC_HT - 1;
+            if (hh >= 0 && hh < H && ww >= 0 && ww < W) {
+                if (CIN == 3 && ci == 0) {
+                    const size_t q = (static_cast<size_t>(img) * H + hh) * W + ww;
+                    v = src.plane0[q];
+                    if (src.noise != nullptr) v = ca * v + cb * src.noise[q];
+                } else {
+                    v = src.planes[((static_cast<size_t>(img) * 2 + ci - (CIN - 2)) * H + hh) * W + ww];
+                }
+            }
+        }
+        r.v[n] = v;
+    }
+}
+
+template <int CIN>
+__device__ __forceinline__ void fc_store_halo(float* s_x, const FcHaloRegs<CIN>& r, int tid) {
+#pragma unroll
+    for (int n = 0; n < FcHaloRegs<CIN>::N; ++n) {
+        const int i = tid + n * 256;
+        if (i < CIN * FC_HT * FC_HT) s_x[i] = r.v[n];
+    }
+}
+
 // offset of im2col column k inside the halo tile (relative to the pixel's own halo position), or -1 beyond K
 template <int CIN>
 __device__ __forceinline__ int fc_koff(int k) {
@@ -94,9 +142,9 @@ __global__ void __launch_bounds__(256, 2) first_conv_mma_fwd_kernel(const FirstC
                                                                     __nv_bfloat16* __restrict__ out,
                                                                     float* __restrict__ stats, int stats_replicas, int H,
                                                                     int W, int num_tiles) {
-    __shared__ float s_x[CIN * FC_HT * FC_HT];
+    __shared__ float s_x2[2][CIN * FC_HT * FC_HT];
     __shared__ __align__(16) __nv_bfloat16 s_out[FC_TILE * FC_TILE * FC_PITCH];
-    __shared__ float s_stats[2][FC_COUT];
+    float (*s_stats)[FC_COUT] = reinterpret_cast<float (*)[FC_COUT]>(s_out);  // aliases the staging tile, used after the loop
     __shared__ uint2 s_blo[2 * 8 * 32];  // low halves of the weight fragments, [ks][nb][lane] (each lane reads its own)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
@@ -129,18 +177,28 @@ __global__ void __launch_bounds__(256, 2) first_conv_mma_fwd_kernel(const FirstC
 #pragma unroll
         for (int j = 0; j < 4; ++j) koff[ks][j] = fc_koff<CIN>(ks * 16 + 2 * t + (j & 1) + (j >> 1) * 8);
     // per-thread epilogue constants: this thread's 16 output channels are nb*8 + 2t + {0,1}
-    if (tid < 2 * FC_COUT) (&s_stats[0][0])[tid] = 0.f;
     float st1[8], st2[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) st1[k] = st2[k] = 0.f;
 
+    FcHaloRegs<CIN> pre;
+    int buf = 0;
+    if (static_cast<int>(blockIdx.x) < num_tiles) {
+        const int img = blockIdx.x / tiles_hw, t_in = blockIdx.x - img * tiles_hw;
+        fc_fetch_halo<CIN>(pre, src, img, (t_in / tiles_w) * FC_TILE, (t_in % tiles_w) * FC_TILE, H, W, tid);
+        fc_store_halo<CIN>(s_x2[0], pre, tid);
+    }
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int img = tile / tiles_hw;
         const int t_in = tile - img * tiles_hw;
         const int h0 = (t_in / tiles_w) * FC_TILE, w0 = (t_in % tiles_w) * FC_TILE;
-        __syncthreads();  // previous tile: s_x readers and s_out copy-out are done
-        fc_load_halo<CIN>(s_x, src, img, h0, w0, H, W, tid);
-        __syncthreads();
+        __syncthreads();  // s_x2[buf] is published; the previous tile's s_out copy-out is done
+        const int next = tile + gridDim.x;
+        if (next < num_tiles) {  // global loads of the next tile fly during this tile's MMAs
+            const int nimg = next / tiles_hw, nt = next - nimg * tiles_hw;
+            fc_fetch_halo<CIN>(pre, src, nimg, (nt / tiles_w) * FC_TILE, (nt % tiles_w) * FC_TILE, H, W, tid);
+        }
+        const float* s_x = s_x2[buf];
 
 #pragma unroll
         for (int mb = 0; mb < 2; ++mb) {
@@ -234,6 +292,8 @@ __global__ void __launch_bounds__(256, 2) first_conv_mma_fwd_kernel(const FirstC
                 }
             }
         }
+        if (next < num_tiles) fc_store_halo<CIN>(s_x2[buf ^ 1], pre, tid);
+        buf ^= 1;
     }
     if (stats != nullptr) {
         // lanes with equal (lane & 7) share channels: fold the 4 of a warp, then shared atomics, one global flush
@@ -244,6 +304,8 @@ __global__ void __launch_bounds__(256, 2) first_conv_mma_fwd_kernel(const FirstC
             st2[k] += __shfl_xor_sync(0xffffffffu, st2[k], 8);
             st2[k] += __shfl_xor_sync(0xffffffffu, st2[k], 16);
         }
+        __syncthreads();  // the last copy-out has finished reading the staging tile
+        if (tid < 2 * FC_COUT) (&s_stats[0][0])[tid] = 0.f;
         __syncthreads();
         if (lane < 8) {
 #pragma unroll
