@@ -33,6 +33,16 @@ int fail(int code, const std::string& msg) {
         if (!(cond)) return fail(B200SR_EINVAL, std::string(__func__) + ": requirement failed: " #cond); \
     } while (0)
 
+// resident-wave sizing of the grid-stride BatchNorm-backward kernels (3 blocks of 256 threads fit per SM)
+int bn_blocks_per_sm() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("B200SR_BN_BPS");
+        v = (e != nullptr && atoi(e) > 0) ? atoi(e) : 8;
+    }
+    return v;
+}
+
 int check_launch(const char* what) {
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(B200SR_ECUDA, std::string(what) + ": " + cudaGetErrorString(e));
@@ -382,6 +392,16 @@ int run_conv3(int mode, const void* a, int a_stride, int a_coff, int Ca, const v
         const int slots = taps * args.cin_chunks * nh;
         const int sb = block_n == 64 ? C3Cfg<64>::SB : C3Cfg<128>::SB;
         args.b_resident = (slots <= sb && getenv("B200SR_NO_BRESIDENT") == nullptr) ? 1 : 0;
+        // ring bytes that resident weights leave unused become extra activation stages
+        const int b_slot = (block_n < 128 ? block_n : 128) * 128;
+        const int ring = (block_n == 64 ? C3Cfg<64>::RING_BYTES : C3Cfg<128>::RING_BYTES);
+        int sa = C3Cfg<64>::SA;
+        if (args.b_resident && getenv("B200SR_FIXED_SA") == nullptr) {
+            sa = (ring - slots * b_slot) / C3_A_SLOT;
+            if (sa > C3_SA_MAX) sa = C3_SA_MAX;
+            if (sa < C3Cfg<64>::SA) sa = C3Cfg<64>::SA;
+        }
+        args.sa = sa;
     }
     // persistent grid: one CTA per SM, rounded down so that a CTA stays on one column block (register statistics)
     int grid = num_sms();
@@ -788,7 +808,7 @@ int b200sr_bn_bwd_apply_fused(const void* dy, int dy_pix_stride, int dy_c_off, c
     B2_CHECK_ARG(CV <= 256 && 256 % CV == 0);
     const int PB = 256 / CV;
     long long blocks = (npix + static_cast<long long>(PB) * BNB_UNROLL - 1) / (static_cast<long long>(PB) * BNB_UNROLL);
-    if (blocks > num_sms() * 8) blocks = num_sms() * 8;
+    if (blocks > num_sms() * bn_blocks_per_sm()) blocks = num_sms() * bn_blocks_per_sm();
     bn_bwd_apply_fused_kernel<false><<<static_cast<int>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         static_cast<const __nv_bfloat16*>(dy), dy_pix_stride, dy_c_off, static_cast<const __nv_bfloat16*>(z), C, scale,
         shift, mean, invstd, sums, replicas, static_cast<float>(count), dgamma, dbeta, static_cast<__nv_bfloat16*>(dz),
@@ -807,7 +827,7 @@ int b200sr_bn_bwd_masked(const void* dy, const void* z, const void* mask_src, in
     B2_CHECK_ARG(CV <= 256 && 256 % CV == 0);
     const int PB = 256 / CV;
     long long blocks = (npix + static_cast<long long>(PB) * BNB_UNROLL - 1) / (static_cast<long long>(PB) * BNB_UNROLL);
-    if (blocks > num_sms() * 8) blocks = num_sms() * 8;
+    if (blocks > num_sms() * bn_blocks_per_sm()) blocks = num_sms() * bn_blocks_per_sm();
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     bn_bwd_reduce_fast_kernel<true><<<static_cast<int>(blocks), 256, 0, st>>>(
         static_cast<const __nv_bfloat16*>(dy), C, 0, static_cast<const __nv_bfloat16*>(z), C, scale, shift, mean, invstd,
@@ -1139,7 +1159,7 @@ int b200sr_bn_bwd_reduce(const void* dy, int dy_pix_stride, int dy_c_off, const 
     if (CV <= 256 && 256 % CV == 0 && getenv("B200SR_BN_SLOW") == nullptr) {
         const int PB = 256 / CV;
         long long blocks = (npix + static_cast<long long>(PB) * BNB_UNROLL - 1) / (static_cast<long long>(PB) * BNB_UNROLL);
-        if (blocks > num_sms() * 8) blocks = num_sms() * 8;
+        if (blocks > num_sms() * bn_blocks_per_sm()) blocks = num_sms() * bn_blocks_per_sm();
         bn_bwd_reduce_fast_kernel<false><<<static_cast<int>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
             static_cast<const __nv_bfloat16*>(dy), dy_pix_stride, dy_c_off, static_cast<const __nv_bfloat16*>(z), C,
             scale, shift, mean, invstd, sums, replicas, npix, nullptr);
@@ -1174,7 +1194,7 @@ int b200sr_bn_bwd_apply(const void* dy, int dy_pix_stride, int dy_c_off, const v
     if (CV <= 256 && 256 % CV == 0 && getenv("B200SR_BN_SLOW") == nullptr) {
         const int PB = 256 / CV;
         long long blocks = (npix + static_cast<long long>(PB) * BNB_UNROLL - 1) / (static_cast<long long>(PB) * BNB_UNROLL);
-        if (blocks > num_sms() * 8) blocks = num_sms() * 8;
+        if (blocks > num_sms() * bn_blocks_per_sm()) blocks = num_sms() * bn_blocks_per_sm();
         bn_bwd_apply_fast_kernel<<<static_cast<int>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
             static_cast<const __nv_bfloat16*>(dy), dy_pix_stride, dy_c_off, static_cast<const __nv_bfloat16*>(z), C,
             scale, shift, mean, invstd, c1, c2, static_cast<__nv_bfloat16*>(dz), npix);

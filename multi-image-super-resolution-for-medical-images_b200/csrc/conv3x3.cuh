@@ -35,6 +35,8 @@ struct Conv3Args {
     int cout_t;        // MODE 1: channels per (i,j) sub-pixel (n_total = 4 * cout_t); modulus of the affine vectors
     int epi_debug;     // bring-up/perf experiments (B200SR_EPI_DEBUG bit mask); 0 in production
     int b_resident;    // the CTA's whole weight block fits the B ring: load it once, keep it for all tiles
+    int sa;            // activation ring depth (3 .. C3_SA_MAX): ring bytes the resident weights do not need go to A
+                       // stages — at 256^2 the kernel is bound by TMA latency x bytes in flight, not by the MMAs
     __nv_bfloat16* out;
     const float* col_scale;  // nullable, [n_total]
     const float* col_shift;  // nullable, [n_total]
@@ -42,6 +44,7 @@ struct Conv3Args {
 };
 
 constexpr int C3_THREADS = 256;
+constexpr int C3_SA_MAX = 8;
 constexpr int C3_TILE_H = 16;
 constexpr int C3_TILE_W = 8;
 constexpr int C3_A_SLOT = (C3_TILE_H + 2) * C3_TILE_W * 128;  // 18432 B: 18 pixel rows x 8 pixels x 64 ch bf16
@@ -72,7 +75,8 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_kernel(const __grid_con
                                                                 const __grid_constant__ CUtensorMap map_out,
                                                                 const Conv3Args args) {
     using Cfg = C3Cfg<BLOCK_N>;
-    constexpr int SA = Cfg::SA, SB = Cfg::SB, NH = Cfg::NH, BN_SLOT = Cfg::BN_SLOT;
+    constexpr int SB = Cfg::SB, NH = Cfg::NH, BN_SLOT = Cfg::BN_SLOT;
+    const int SA = args.sa;
     constexpr int NG = MODE == 0 ? 3 : (MODE == 2 ? 4 : 1);  // activation boxes per 64-channel chunk
     constexpr int NT = MODE == 0 ? 3 : 1;                    // taps served by one box
     constexpr int A_BYTES = MODE == 0 ? C3_A_SLOT : C3_TILE_H * C3_TILE_W * 128;
@@ -82,8 +86,8 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_kernel(const __grid_con
     uint8_t* ring_b = smem + SA * C3_A_SLOT;
     uint8_t* out_stage = smem + Cfg::RING_BYTES;  // 1024-byte aligned (all slot sizes are multiples of 1024)
     uint64_t* a_full = reinterpret_cast<uint64_t*>(smem + Cfg::RING_BYTES + Cfg::STAGING);
-    uint64_t* a_empty = a_full + SA;
-    uint64_t* b_full = a_empty + SA;
+    uint64_t* a_empty = a_full + C3_SA_MAX;
+    uint64_t* b_full = a_empty + C3_SA_MAX;
     uint64_t* b_empty = b_full + SB;
     uint64_t* acc_full = b_empty + SB;
     uint64_t* acc_empty = acc_full + 2;
