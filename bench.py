@@ -6,9 +6,10 @@
 
 Workload at every N: BASELINE.json configs[2] restricted to the hot path the north star names — UNet train step
 with the combined MSE + 0.005*(1-SSIM) loss and Adam(lr 1e-4), bf16 tensor-core compute, batch 32 per GPU at
-256x256, data-parallel by batch (weak scaling; gradient all-reduce over NCCL overlapped with backward). The VGG
-perceptual term of configs[2] is a "next" row and is not part of the timed step. Inference
-throughput (configs[0]: B=8 fp32 in/out, eval mode) is reported in the same JSON line under "inference".
+256x256, data-parallel by batch (weak scaling; gradient all-reduce over NCCL overlapped with backward). Inference
+throughput (configs[0]: B=8 fp32 in/out, eval mode) is reported in the same JSON line under "inference"; at N=1 the
+other BASELINE configs built on the same kernels (the step with the VGG16 perceptual term, the Progressive
+UNet chain, the DeepCNN baseline, Fast-DDPM training and 10-step sampling) are timed under "variants".
 
 Prints ONE JSON line (rank 0). See DESIGN.md §Measurement for how every field is produced.
 """
@@ -276,9 +277,10 @@ def run_b200sr(args):
         roofline = {"bound": "tensor", "kernel": "igemm_kernel + wgrad_kernel (tcgen05 implicit GEMM: conv3x3 "
                     "fwd/dgrad/wgrad, ConvT fwd/dgrad/wgrad)", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                     "frac": achieved / peak,
-                    # DRAM bytes per tensor-core launch (dram__bytes_read+write, mean of the 24 conv3x3/wgrad3x3
-                    # launches in profiles/r1_final_gemm_ncu_summary.txt, ncu --set full)
-                    "traffic": 101.8e6,
+                    # DRAM bytes per tensor-core launch (dram__bytes_read+write, ncu --set full): mean over the 48
+                    # conv3x3/wgrad3x3 launches of profiles/r1_final_gemm_ncu_summary.txt (mid-network layers, 101.8 MB)
+                    # and profiles/r1c_gemm_ncu_summary.txt (256^2/128^2 layers of the backward pass, 330.7 MB)
+                    "traffic": 216.3e6,
                     "peak_source": peaks["source"] + " sustained bf16 (kernels timed inside a long step); burst "
                                    f"{peaks['bf16_tflops']}",
                     "note": "per-kernel times from 3 instrumented eager steps (CUDA graph and wgrad side stream off)",
@@ -324,7 +326,8 @@ def run_b200sr(args):
                 "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
                 "config": {"workload": "unet_train_combined_mse_ssim_b32_256x256 (BASELINE configs[2] hot path: "
-                                       "UNet fwd+bwd, MSE+0.005*(1-SSIM), Adam; VGG term is a next row)",
+                                       "UNet fwd+bwd, MSE+0.005*(1-SSIM), Adam; the same step with the VGG16 perceptual term and the "
+                                       "other BASELINE configs are timed under 'variants')",
                            "global_batch": world * B, "per_gpu_batch": B, "parallelism": f"dp{world}",
                            "l2": "per-step working set (activations + gradients, several GB) >> 126 MB L2; ring of 4 "
                                  "distinct input batches"},
