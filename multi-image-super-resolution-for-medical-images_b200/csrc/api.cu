@@ -705,36 +705,23 @@ int b200sr_conv1_fwd(const float* x, const float* w, const float* col_scale, con
     B2_CHECK_ARG(stats == nullptr || stats_replicas > 0);
     B2_CHECK_ARG(aligned16(out));
     const int tiles = B * (H / C1_TILE) * (W / C1_TILE);
-    if (getenv("B200SR_FIRSTCONV_V1") == nullptr) {  // tensor-core (warp MMA) version, csrc/firstconv.cuh
-        FirstConvSrc src{nullptr, nullptr, nullptr, x};
-        const int grid = tiles < num_sms() * 2 ? tiles : num_sms() * 2;
-        first_conv_mma_fwd_kernel<2><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-            src, w, 18, nullptr, col_scale, col_shift, relu, static_cast<__nv_bfloat16*>(out), stats,
-            stats_replicas > 0 ? stats_replicas : 1, H, W, tiles);
-        return check_launch("first_conv_mma_fwd_kernel<2>");
-    }
-    const int grid = tiles < num_sms() * 6 ? tiles : num_sms() * 6;
-    conv1_direct_fwd_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        x, w, col_scale, col_shift, relu, static_cast<__nv_bfloat16*>(out), stats, stats_replicas > 0 ? stats_replicas : 1,
-        H, W, tiles);
-    return check_launch("conv1_direct_fwd_kernel");
+    FirstConvSrc src{nullptr, nullptr, nullptr, x};  // tensor-core (warp MMA) kernel, csrc/firstconv.cuh
+    const int grid = tiles < num_sms() * 2 ? tiles : num_sms() * 2;
+    first_conv_mma_fwd_kernel<2><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        src, w, 18, nullptr, col_scale, col_shift, relu, static_cast<__nv_bfloat16*>(out), stats,
+        stats_replicas > 0 ? stats_replicas : 1, H, W, tiles);
+    return check_launch("first_conv_mma_fwd_kernel<2>");
 }
 
 int b200sr_conv1_wgrad(const float* x, const void* dz, float* dw, int B, int H, int W, void* stream) {
     B2_CHECK_ARG(x != nullptr && dz != nullptr && dw != nullptr);
     B2_CHECK_ARG(B > 0 && H % C1_TILE == 0 && W % C1_TILE == 0 && aligned16(dz));
     const int tiles = B * (H / C1_TILE) * (W / C1_TILE);
-    if (getenv("B200SR_FIRSTCONV_V1") == nullptr) {
-        FirstConvSrc src{nullptr, nullptr, nullptr, x};
-        const int grid = tiles < num_sms() * 2 ? tiles : num_sms() * 2;
-        first_conv_mma_wgrad_kernel<2><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-            src, static_cast<const __nv_bfloat16*>(dz), dw, 18, H, W, tiles);
-        return check_launch("first_conv_mma_wgrad_kernel<2>");
-    }
-    const int grid = tiles < 148 * 4 ? tiles : 148 * 4;
-    conv1_direct_wgrad_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        x, static_cast<const __nv_bfloat16*>(dz), dw, H, W, tiles);
-    return check_launch("conv1_direct_wgrad_kernel");
+    FirstConvSrc src{nullptr, nullptr, nullptr, x};
+    const int grid = tiles < num_sms() * 2 ? tiles : num_sms() * 2;
+    first_conv_mma_wgrad_kernel<2><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        src, static_cast<const __nv_bfloat16*>(dz), dw, 18, H, W, tiles);
+    return check_launch("first_conv_mma_wgrad_kernel<2>");
 }
 
 int b200sr_conv1_dgrad(const void* dz, const float* w, float* dx, int B, int H, int W, void* stream) {
@@ -949,17 +936,11 @@ int b200sr_fd_convin_fwd(const float* x0, const float* noise, const float* coef,
     B2_CHECK_ARG(x0 && cond && w && tb && out && (noise == nullptr || coef != nullptr));
     B2_CHECK_ARG(B > 0 && H % C1_TILE == 0 && W % C1_TILE == 0 && aligned16(out) && aligned16(tb));
     const int tiles = B * (H / C1_TILE) * (W / C1_TILE);
-    if (getenv("B200SR_FIRSTCONV_V1") == nullptr) {
-        FirstConvSrc src{x0, noise, reinterpret_cast<const float2*>(coef), cond};
-        const int grid = tiles < num_sms() * 2 ? tiles : num_sms() * 2;
-        first_conv_mma_fwd_kernel<3><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-            src, w, FD_CIN0 * 9, tb, nullptr, nullptr, 1, static_cast<__nv_bfloat16*>(out), nullptr, 1, H, W, tiles);
-        return check_launch("first_conv_mma_fwd_kernel<3>");
-    }
-    const int grid = tiles < num_sms() * 6 ? tiles : num_sms() * 6;
-    fd_convin_fwd_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        x0, noise, reinterpret_cast<const float2*>(coef), cond, w, tb, static_cast<__nv_bfloat16*>(out), H, W, tiles);
-    return check_launch("fd_convin_fwd_kernel");
+    FirstConvSrc src{x0, noise, reinterpret_cast<const float2*>(coef), cond};
+    const int grid = tiles < num_sms() * 2 ? tiles : num_sms() * 2;
+    first_conv_mma_fwd_kernel<3><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        src, w, FD_CIN0 * 9, tb, nullptr, nullptr, 1, static_cast<__nv_bfloat16*>(out), nullptr, 1, H, W, tiles);
+    return check_launch("first_conv_mma_fwd_kernel<3>");
 }
 
 int b200sr_fd_convin_wgrad(const float* x0, const float* noise, const float* coef, const float* cond, const void* dz,
@@ -967,17 +948,11 @@ int b200sr_fd_convin_wgrad(const float* x0, const float* noise, const float* coe
     B2_CHECK_ARG(x0 && cond && dz && dw && (noise == nullptr || coef != nullptr));
     B2_CHECK_ARG(B > 0 && H % C1_TILE == 0 && W % C1_TILE == 0 && aligned16(dz));
     const int tiles = B * (H / C1_TILE) * (W / C1_TILE);
-    if (getenv("B200SR_FIRSTCONV_V1") == nullptr) {
-        FirstConvSrc src{x0, noise, reinterpret_cast<const float2*>(coef), cond};
-        const int grid = tiles < num_sms() * 2 ? tiles : num_sms() * 2;
-        first_conv_mma_wgrad_kernel<3><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-            src, static_cast<const __nv_bfloat16*>(dz), dw, FD_CIN0 * 9, H, W, tiles);
-        return check_launch("first_conv_mma_wgrad_kernel<3>");
-    }
+    FirstConvSrc src{x0, noise, reinterpret_cast<const float2*>(coef), cond};
     const int grid = tiles < num_sms() * 2 ? tiles : num_sms() * 2;
-    fd_convin_wgrad_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        x0, noise, reinterpret_cast<const float2*>(coef), cond, static_cast<const __nv_bfloat16*>(dz), dw, H, W, tiles);
-    return check_launch("fd_convin_wgrad_kernel");
+    first_conv_mma_wgrad_kernel<3><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        src, static_cast<const __nv_bfloat16*>(dz), dw, FD_CIN0 * 9, H, W, tiles);
+    return check_launch("first_conv_mma_wgrad_kernel<3>");
 }
 
 int b200sr_fd_relu_bwd_bias(const void* dy, int dy_pix_stride, int dy_c_off, const void* act, int act_pix_stride,

@@ -156,7 +156,10 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_kernel(const __grid_con
                     for (int dw = 0; dw < NG; ++dw) {
                         mbar_wait(&a_empty[sa], pa ^ 1);
                         mbar_arrive_expect_tx(&a_full[sa], A_BYTES);
-                        if (MODE == 0)
+                        if (MODE == 0 && (args.epi_debug & 128))
+                            tma_load_4d_hint(&map_a, &a_full[sa], ring_a + sa * C3_A_SLOT, c * 64, w0 + dw - 1, h0 - 1, img,
+                                             l2_policy_evict_last());
+                        else if (MODE == 0)
                             tma_load_4d(&map_a, &a_full[sa], ring_a + sa * C3_A_SLOT, c * 64, w0 + dw - 1, h0 - 1, img);
                         else if (MODE == 1 || MODE == 3)
                             tma_load_4d(&map_a, &a_full[sa], ring_a + sa * C3_A_SLOT, c * 64, w0, h0, img);
@@ -350,6 +353,8 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_kernel(const __grid_con
                         const int ij = col0 / args.cout_t;
                         const int co = col0 - ij * args.cout_t;
                         tma_store_5d(&map_out, stage, co, ij & 1, w0, ij >> 1, img * args.H + h0);
+                    } else if (args.epi_debug & 256) {
+                        tma_store_4d_hint(&map_out, stage, col0, w0, h0, img, l2_policy_evict_first());
                     } else {
                         tma_store_4d(&map_out, stage, col0, w0, h0, img);
                     }

@@ -175,186 +175,11 @@ __global__ void __launch_bounds__(256) pack_jobs_kernel(const PackJob* __restric
 }
 
 // ------------------------------------------------------------------------------------------------
-// first layer: Conv2d(2 -> 64, 3x3, p1) straight from the fp32 NCHW network input (K = 18: memory bound,
-// CUDA cores). Reference: unet_model.py:27 as instantiated by UNet.enc1 (:49).
-// One thread = one pixel x 64 output channels; a 16x16 pixel tile per block with an 18x18x2 halo in smem.
+// first layer Conv2d(2 -> 64, 3x3, p1): forward and weight gradient live in firstconv.cuh (tensor-core MMA straight
+// from the fp32 NCHW input); only the data gradient below stays on CUDA cores.
 // ------------------------------------------------------------------------------------------------
 constexpr int C1_TILE = 16;
 constexpr int C1_COUT = 64;
-
-__global__ void __launch_bounds__(256) conv1_direct_fwd_kernel(const float* __restrict__ x,      // [B][2][H][W]
-                                                               const float* __restrict__ wgt,    // [64][2][3][3]
-                                                               const float* __restrict__ col_scale,
-                                                               const float* __restrict__ col_shift, int relu,
-                                                               __nv_bfloat16* __restrict__ out,  // [B][H][W][64]
-                                                               float* __restrict__ stats, int stats_replicas,
-                                                               int H, int W, int num_tiles) {
-    __shared__ float s_x[2][C1_TILE + 2][C1_TILE + 2];
-    __shared__ __align__(16) float s_w[18][C1_COUT];  // [ci*9 + tap][co]
-    __shared__ float s_stats[2][C1_COUT];
-    const int tid = threadIdx.x;
-    const int tiles_w = W / C1_TILE;
-    const int tiles_hw = tiles_w * (H / C1_TILE);
-    const uint32_t lane = tid & 31;
-    const int ph = tid / C1_TILE, pw = tid % C1_TILE;
-
-    for (int i = tid; i < 18 * C1_COUT; i += 256) {
-        const int co = i % C1_COUT, k = i / C1_COUT;
-        s_w[k][co] = wgt[co * 18 + k];
-    }
-    if (tid < 2 * C1_COUT) (&s_stats[0][0])[tid] = 0.f;
-
-    // persistent blocks: statistics accumulate in shared memory across tiles, one global flush per block
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int img = tile / tiles_hw;
-        const int t_in = tile - img * tiles_hw;
-        const int h0 = (t_in / tiles_w) * C1_TILE, w0 = (t_in % tiles_w) * C1_TILE;
-        __syncthreads();
-        for (int i = tid; i < 2 * (C1_TILE + 2) * (C1_TILE + 2); i += 256) {
-            const int ci = i / ((C1_TILE + 2) * (C1_TILE + 2));
-            const int r = i % ((C1_TILE + 2) * (C1_TILE + 2));
-            const int hh = h0 + r / (C1_TILE + 2) - 1, ww = w0 + r % (C1_TILE + 2) - 1;
-            float v = 0.f;
-            if (hh >= 0 && hh < H && ww >= 0 && ww < W) v = x[((static_cast<size_t>(img) * 2 + ci) * H + hh) * W + ww];
-            s_x[ci][r / (C1_TILE + 2)][r % (C1_TILE + 2)] = v;
-        }
-        __syncthreads();
-
-        float in[18];
-#pragma unroll
-        for (int ci = 0; ci < 2; ++ci)
-#pragma unroll
-            for (int t = 0; t < 9; ++t) in[ci * 9 + t] = s_x[ci][ph + t / 3][pw + t % 3];
-
-        __nv_bfloat16* dst = out + ((static_cast<size_t>(img) * H + h0 + ph) * W + w0 + pw) * C1_COUT;
-#pragma unroll 1
-        for (int cb = 0; cb < C1_COUT; cb += 32) {
-            float acc[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) acc[j] = 0.f;
-#pragma unroll
-            for (int k = 0; k < 18; ++k) {
-#pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    const float4 w4 = *reinterpret_cast<const float4*>(&s_w[k][cb + j]);  // one LDS.128 per 4 FMAs
-                    acc[j] = fmaf(in[k], w4.x, acc[j]);
-                    acc[j + 1] = fmaf(in[k], w4.y, acc[j + 1]);
-                    acc[j + 2] = fmaf(in[k], w4.z, acc[j + 2]);
-                    acc[j + 3] = fmaf(in[k], w4.w, acc[j + 3]);
-                }
-            }
-            if (col_scale != nullptr) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) acc[j] = fmaf(acc[j], col_scale[cb + j], col_shift[cb + j]);
-            }
-            if (relu) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) acc[j] = fmaxf(acc[j], 0.f);
-            }
-            uint32_t packed[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) packed[j] = pack_bf16x2(acc[2 * j], acc[2 * j + 1]);
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-                reinterpret_cast<uint4*>(dst + cb)[j] =
-                    make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
-            if (stats != nullptr) {
-                float s1[32], s2[32];
-#pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const __nv_bfloat162 hh = *reinterpret_cast<const __nv_bfloat162*>(&packed[j]);
-                    const float a = __low2float(hh), b = __high2float(hh);
-                    s1[2 * j] = a; s1[2 * j + 1] = b;
-                    s2[2 * j] = a * a; s2[2 * j + 1] = b * b;
-                }
-                const float cs = warp_transpose_reduce32(s1, lane);
-                const float cq = warp_transpose_reduce32(s2, lane);
-                atomicAdd(&s_stats[0][cb + lane], cs);
-                atomicAdd(&s_stats[1][cb + lane], cq);
-            }
-        }
-    }
-    if (stats != nullptr) {
-        __syncthreads();
-        float* d = stats + static_cast<size_t>(blockIdx.x % stats_replicas) * 2 * C1_COUT;
-        if (tid < 2 * C1_COUT) atomicAdd(d + tid, (&s_stats[0][0])[tid]);
-    }
-}
-
-// wgrad of the first layer: dW[co][ci][kh][kw] = sum_q dZ[q][co] * x[q + (kh-1, kw-1)][ci]
-// Persistent blocks (grid-stride over 16x16 tiles). Thread = (group of 4 output channels, pixel lane); it keeps a
-// 4 x 18 register tile, so one shared-memory read of dZ (8 B) and 18 broadcast reads of x feed 72 FMAs.
-__global__ void __launch_bounds__(256) conv1_direct_wgrad_kernel(const float* __restrict__ x,             // [B][2][H][W]
-                                                                 const __nv_bfloat16* __restrict__ dz,   // [B][H][W][64]
-                                                                 float* __restrict__ dw,                  // [64][2][3][3]
-                                                                 int H, int W, int num_tiles) {
-    __shared__ float s_x[2][C1_TILE + 2][C1_TILE + 2];
-    __shared__ __align__(16) __nv_bfloat16 s_dz[C1_TILE * C1_TILE][C1_COUT + 8];  // +8: rows 144 B apart
-    const int tid = threadIdx.x;
-    const int cg = tid & 15;   // channels 4*cg .. 4*cg+3
-    const int pl = tid >> 4;   // pixel lane: pixels pl, pl+16, ...
-    const int tiles_w = W / C1_TILE;
-    const int tiles_hw = tiles_w * (H / C1_TILE);
-    float acc[4][18];
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-#pragma unroll
-        for (int k = 0; k < 18; ++k) acc[j][k] = 0.f;
-
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int img = tile / tiles_hw;
-        const int t_in = tile - img * tiles_hw;
-        const int h0 = (t_in / tiles_w) * C1_TILE, w0 = (t_in % tiles_w) * C1_TILE;
-        __syncthreads();
-        for (int i = tid; i < 2 * (C1_TILE + 2) * (C1_TILE + 2); i += 256) {
-            const int ci = i / ((C1_TILE + 2) * (C1_TILE + 2));
-            const int r = i % ((C1_TILE + 2) * (C1_TILE + 2));
-            const int hh = h0 + r / (C1_TILE + 2) - 1, ww = w0 + r % (C1_TILE + 2) - 1;
-            float v = 0.f;
-            if (hh >= 0 && hh < H && ww >= 0 && ww < W) v = x[((static_cast<size_t>(img) * 2 + ci) * H + hh) * W + ww];
-            s_x[ci][r / (C1_TILE + 2)][r % (C1_TILE + 2)] = v;
-        }
-        // 256 pixels x 64 ch bf16 = 2048 uint4
-        for (int i = tid; i < C1_TILE * C1_TILE * 8; i += 256) {
-            const int p = i >> 3, c8 = i & 7;
-            const int hh = h0 + p / C1_TILE, ww = w0 + p % C1_TILE;
-            const uint4 u =
-                *reinterpret_cast<const uint4*>(dz + ((static_cast<size_t>(img) * H + hh) * W + ww) * C1_COUT + c8 * 8);
-            *reinterpret_cast<uint4*>(&s_dz[p][c8 * 8]) = u;
-        }
-        __syncthreads();
-#pragma unroll 2
-        for (int p = pl; p < C1_TILE * C1_TILE; p += 16) {
-            const uint2 gu = *reinterpret_cast<const uint2*>(&s_dz[p][cg * 4]);
-            const __nv_bfloat162 g01 = *reinterpret_cast<const __nv_bfloat162*>(&gu.x);
-            const __nv_bfloat162 g23 = *reinterpret_cast<const __nv_bfloat162*>(&gu.y);
-            const float g[4] = {__low2float(g01), __high2float(g01), __low2float(g23), __high2float(g23)};
-            const int ph = p / C1_TILE, pw = p % C1_TILE;
-#pragma unroll
-            for (int ci = 0; ci < 2; ++ci)
-#pragma unroll
-                for (int t = 0; t < 9; ++t) {
-                    const float xv = s_x[ci][ph + t / 3][pw + t % 3];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) acc[j][ci * 9 + t] = fmaf(g[j], xv, acc[j][ci * 9 + t]);
-                }
-        }
-    }
-    // reduce over the 16 pixel lanes: lanes of a warp hold pl in {2w, 2w+1} -> shuffle once, then shared atomics
-    __shared__ float s_acc[C1_COUT * 18];
-    for (int i = tid; i < C1_COUT * 18; i += 256) s_acc[i] = 0.f;
-    __syncthreads();
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-#pragma unroll
-        for (int k = 0; k < 18; ++k) {
-            float v = acc[j][k];
-            v += __shfl_xor_sync(0xffffffffu, v, 16);
-            if ((tid & 16) == 0) atomicAdd(&s_acc[(cg * 4 + j) * 18 + k], v);
-        }
-    __syncthreads();
-    for (int i = tid; i < C1_COUT * 18; i += 256) atomicAdd(dw + i, s_acc[i]);
-}
 
 // Data gradient of the first layer (needed when the network input itself requires a gradient: stages 2A/2B of the
 // Progressive UNet feed stage 1's prediction into their first conv, reference src/ModelLoader.py:258-267).

@@ -104,177 +104,8 @@ __global__ void __launch_bounds__(576) fd_time_bias_kernel(const float* __restri
     }
 }
 
-// halo load of the 3 image channels of one 16x16 tile. Channel 0 is x_t = ca*x0 + cb*noise (q_sample, :515-518 /
-// :597-599) when noise != NULL, else x0 itself (sampling, :624); channels 1,2 are the conditioning slices.
-__device__ __forceinline__ void fd_load_halo(float (*s_x)[C1_TILE + 2][C1_TILE + 2], const float* __restrict__ x0,
-                                             const float* __restrict__ noise, const float2* __restrict__ coef,
-                                             const float* __restrict__ cond, int img, int h0, int w0, int H, int W,
-                                             int tid) {
-    constexpr int HT = C1_TILE + 2;
-    float ca = 1.f, cb = 0.f;
-    if (noise != nullptr) {
-        const float2 c = coef[img];
-        ca = c.x;
-        cb = c.y;
-    }
-    for (int i = tid; i < FD_CIMG * HT * HT; i += 256) {
-        const int ci = i / (HT * HT);
-        const int r = i % (HT * HT);
-        const int hh = h0 + r / HT - 1, ww = w0 + r % HT - 1;
-        float v = 0.f;
-        if (hh >= 0 && hh < H && ww >= 0 && ww < W) {
-            if (ci == 0) {
-                const size_t q = (static_cast<size_t>(img) * H + hh) * W + ww;
-                v = x0[q];
-                if (noise != nullptr) v = ca * v + cb * noise[q];
-            } else {
-                v = cond[((static_cast<size_t>(img) * 2 + ci - 1) * H + hh) * W + ww];
-            }
-        }
-        s_x[ci][r / HT][r % HT] = v;
-    }
-}
-
-// inc.block.0 forward: direct 3-channel conv + class bias + ReLU -> bf16 NHWC. One thread = one pixel x 64 channels.
-__global__ void __launch_bounds__(256) fd_convin_fwd_kernel(const float* __restrict__ x0, const float* __restrict__ noise,
-                                                            const float2* __restrict__ coef,
-                                                            const float* __restrict__ cond,  // [B][2][H][W]
-                                                            const float* __restrict__ wgt,   // [64][259][3][3]
-                                                            const float* __restrict__ tb,    // [B][9][64]
-                                                            __nv_bfloat16* __restrict__ out,  // [B][H][W][64]
-                                                            int H, int W, int num_tiles) {
-    __shared__ float s_x[FD_CIMG][C1_TILE + 2][C1_TILE + 2];
-    __shared__ __align__(16) float s_w[FD_K0][C1_COUT];  // [ci*9 + tap][co]
-    __shared__ __align__(16) float s_tb[9][C1_COUT];
-    const int tid = threadIdx.x;
-    const int tiles_w = W / C1_TILE;
-    const int tiles_hw = tiles_w * (H / C1_TILE);
-    const int ph = tid / C1_TILE, pw = tid % C1_TILE;
-    for (int i = tid; i < FD_K0 * C1_COUT; i += 256) {
-        const int co = i % C1_COUT, k = i / C1_COUT;
-        s_w[k][co] = wgt[static_cast<size_t>(co) * FD_CIN0 * 9 + k];
-    }
-    int img_loaded = -1;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int img = tile / tiles_hw;
-        const int t_in = tile - img * tiles_hw;
-        const int h0 = (t_in / tiles_w) * C1_TILE, w0 = (t_in % tiles_w) * C1_TILE;
-        __syncthreads();
-        fd_load_halo(s_x, x0, noise, coef, cond, img, h0, w0, H, W, tid);
-        if (img != img_loaded) {
-            for (int i = tid; i < 9 * C1_COUT; i += 256) (&s_tb[0][0])[i] = tb[static_cast<size_t>(img) * 9 * C1_COUT + i];
-            img_loaded = img;
-        }
-        __syncthreads();
-        float in[FD_K0];
-#pragma unroll
-        for (int ci = 0; ci < FD_CIMG; ++ci)
-#pragma unroll
-            for (int t = 0; t < 9; ++t) in[ci * 9 + t] = s_x[ci][ph + t / 3][pw + t % 3];
-        const int h = h0 + ph, w = w0 + pw;
-        const int cls = (h == 0 ? 0 : (h == H - 1 ? 2 : 1)) * 3 + (w == 0 ? 0 : (w == W - 1 ? 2 : 1));
-        __nv_bfloat16* dst = out + ((static_cast<size_t>(img) * H + h) * W + w) * C1_COUT;
-#pragma unroll 1
-        for (int cb = 0; cb < C1_COUT; cb += 32) {
-            float acc[32];
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-                const float4 t4 = *reinterpret_cast<const float4*>(&s_tb[cls][cb + j]);
-                acc[j] = t4.x;
-                acc[j + 1] = t4.y;
-                acc[j + 2] = t4.z;
-                acc[j + 3] = t4.w;
-            }
-#pragma unroll
-            for (int k = 0; k < FD_K0; ++k) {
-#pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    const float4 w4 = *reinterpret_cast<const float4*>(&s_w[k][cb + j]);
-                    acc[j] = fmaf(in[k], w4.x, acc[j]);
-                    acc[j + 1] = fmaf(in[k], w4.y, acc[j + 1]);
-                    acc[j + 2] = fmaf(in[k], w4.z, acc[j + 2]);
-                    acc[j + 3] = fmaf(in[k], w4.w, acc[j + 3]);
-                }
-            }
-            uint32_t packed[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) packed[j] = pack_bf16x2(fmaxf(acc[2 * j], 0.f), fmaxf(acc[2 * j + 1], 0.f));
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-                reinterpret_cast<uint4*>(dst + cb)[j] =
-                    make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
-        }
-    }
-}
-
-// inc.block.0 weight gradient of the 3 image channels: dW[co][ci][tap] += sum_q dZ[q][co] * xin[q + tap][ci],
-// written into the (64,259,3,3) parameter-gradient layout. Thread = (4 output channels, pixel lane), 4 x 27 register
-// tile; persistent blocks, one flush per block.
-__global__ void __launch_bounds__(256) fd_convin_wgrad_kernel(const float* __restrict__ x0, const float* __restrict__ noise,
-                                                              const float2* __restrict__ coef,
-                                                              const float* __restrict__ cond,
-                                                              const __nv_bfloat16* __restrict__ dz,  // [B][H][W][64]
-                                                              float* __restrict__ dw,                 // [64][259][3][3]
-                                                              int H, int W, int num_tiles) {
-    __shared__ float s_x[FD_CIMG][C1_TILE + 2][C1_TILE + 2];
-    __shared__ __align__(16) __nv_bfloat16 s_dz[C1_TILE * C1_TILE][C1_COUT + 8];
-    __shared__ float s_acc[C1_COUT * FD_K0];
-    const int tid = threadIdx.x;
-    const int cg = tid & 15;  // channels 4*cg .. 4*cg+3
-    const int pl = tid >> 4;  // pixel lane
-    const int tiles_w = W / C1_TILE;
-    const int tiles_hw = tiles_w * (H / C1_TILE);
-    float acc[4][FD_K0];
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-#pragma unroll
-        for (int k = 0; k < FD_K0; ++k) acc[j][k] = 0.f;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int img = tile / tiles_hw;
-        const int t_in = tile - img * tiles_hw;
-        const int h0 = (t_in / tiles_w) * C1_TILE, w0 = (t_in % tiles_w) * C1_TILE;
-        __syncthreads();
-        fd_load_halo(s_x, x0, noise, coef, cond, img, h0, w0, H, W, tid);
-        for (int i = tid; i < C1_TILE * C1_TILE * 8; i += 256) {
-            const int p = i >> 3, c8 = i & 7;
-            const int hh = h0 + p / C1_TILE, ww = w0 + p % C1_TILE;
-            *reinterpret_cast<uint4*>(&s_dz[p][c8 * 8]) =
-                *reinterpret_cast<const uint4*>(dz + ((static_cast<size_t>(img) * H + hh) * W + ww) * C1_COUT + c8 * 8);
-        }
-        __syncthreads();
-#pragma unroll 1
-        for (int p = pl; p < C1_TILE * C1_TILE; p += 16) {
-            const uint2 gu = *reinterpret_cast<const uint2*>(&s_dz[p][cg * 4]);
-            const __nv_bfloat162 g01 = *reinterpret_cast<const __nv_bfloat162*>(&gu.x);
-            const __nv_bfloat162 g23 = *reinterpret_cast<const __nv_bfloat162*>(&gu.y);
-            const float g[4] = {__low2float(g01), __high2float(g01), __low2float(g23), __high2float(g23)};
-            const int ph = p / C1_TILE, pw = p % C1_TILE;
-#pragma unroll
-            for (int ci = 0; ci < FD_CIMG; ++ci)
-#pragma unroll
-                for (int t = 0; t < 9; ++t) {
-                    const float xv = s_x[ci][ph + t / 3][pw + t % 3];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) acc[j][ci * 9 + t] = fmaf(g[j], xv, acc[j][ci * 9 + t]);
-                }
-        }
-    }
-    for (int i = tid; i < C1_COUT * FD_K0; i += 256) s_acc[i] = 0.f;
-    __syncthreads();
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-#pragma unroll
-        for (int k = 0; k < FD_K0; ++k) {
-            float v = acc[j][k];
-            v += __shfl_xor_sync(0xffffffffu, v, 16);
-            if ((tid & 16) == 0) atomicAdd(&s_acc[(cg * 4 + j) * FD_K0 + k], v);
-        }
-    __syncthreads();
-    for (int i = tid; i < C1_COUT * FD_K0; i += 256) {
-        const int co = i / FD_K0, k = i % FD_K0;
-        atomicAdd(dw + static_cast<size_t>(co) * FD_CIN0 * 9 + k, s_acc[i]);
-    }
-}
+// inc.block.0 itself (3-channel conv + tb + ReLU, with q_sample fused into the input load) and the weight gradient of its
+// image channels run on the tensor-core first-layer kernels in firstconv.cuh (first_conv_mma_{fwd,wgrad}<3>).
 
 // ------------------------------------------------------------------------------------------------
 // DoubleConv backward (Conv3x3 + bias -> ReLU, no BatchNorm, :521-533): dz = dy * [act > 0] fused with the bias

@@ -158,6 +158,36 @@ __device__ __forceinline__ void tma_store_5d(const CUtensorMap* m, const void* s
                  : "memory");
 }
 
+// L2 eviction-priority hints: outputs are streamed (evict_first), haloed activation boxes are re-read by the
+// neighbouring tiles (evict_last)
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void tma_store_4d_hint(const CUtensorMap* m, const void* src, int c0, int c1, int c2, int c3,
+                                                  uint64_t policy) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3, %4, %5}], [%1], %6;"
+                 :
+                 : "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "l"(policy)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_hint(const CUtensorMap* m, uint64_t* bar, void* dst, int c0, int c1, int c2,
+                                                 int c3, uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cta.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5, %6}], "
+        "[%2], %7;"
+        :
+        : "r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2),
+          "r"(c3), "l"(policy)
+        : "memory");
+}
+
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 
 template <int N>

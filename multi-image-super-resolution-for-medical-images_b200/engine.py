@@ -95,6 +95,7 @@ class UNetEngine:
         # experiment switch (off): order each layer's wgrad behind its dgrad so it overlaps the NEXT BatchNorm backward;
         # measured 13.20 vs 12.78 ms per step — the following dgrad then waits for the wgrad CTAs to retire
         self.wgrad_late = os.environ.get("B200SR_WGRAD_LATE") is not None
+        self.timing_skip_pack = os.environ.get("B200SR_TIMING_SKIP_PACK") is not None  # timing experiment only
         self._hp = None
 
     # ------------------------------------------------------------------------------------------------
@@ -417,8 +418,11 @@ class UNetEngine:
         plan = self._plan(B, H, W, True)
         st = _lib.current_stream_ptr()
         fwd_packed = None
-        if self.overlap_wgrad:
+        if self.timing_skip_pack and getattr(self, "_packed_once", False):
+            self._pack_done = None  # timing experiment only (stale bf16 weights): how much of the packing is exposed?
+        elif self.overlap_wgrad:
             fwd_packed = self._repack_staged()
+            self._packed_once = True
         else:
             self.repack_weights()
             self._pack_done = None

@@ -575,6 +575,9 @@ class FastDDPMTrainer:
         self.model_save_dir.mkdir(parents=True, exist_ok=True)
         self._reducer = None
         self._sumsq = None
+        from .ddp import broadcast_module_state, is_distributed
+        if is_distributed():
+            broadcast_module_state(self.model)  # every rank starts from rank 0's weights
         if verbose:
             print(f"Total parameters: {sum(p.numel() for p in self.model.parameters()):,}")
 
