@@ -59,6 +59,14 @@ int b200sr_conv3x3_dgrad(const void* dy, int dy_pix_stride, int dy_c_off, int Co
                          int Cin, int B, int H, int W, void* dx, int dx_pix_stride, int dx_c_off, float* stats,
                          int stats_replicas, void* stream);
 
+/* Data gradient fused with the ReLU backward of the layer it flows into (Conv+ReLU stacks without BatchNorm: the
+ * DoubleConv of ModelLoader.py:521-533, the VGG features of the perceptual loss): dx = dgrad(dy) * [act > 0], act the
+ * (B,H,W,Cin) activation slot of that layer. stats (optional) receives the per-channel sums of the stored dx, i.e. that
+ * layer's bias gradient. Needs H % 16 == 0 and W % 8 == 0 (persistent kernel only). */
+int b200sr_conv3x3_dgrad_relu(const void* dy, int dy_pix_stride, int dy_c_off, int Cout, const void* w_packed, int Cin,
+                              int B, int H, int W, void* dx, int dx_pix_stride, int dx_c_off, const void* act,
+                              int act_pix_stride, int act_c_off, float* stats, int stats_replicas, void* stream);
+
 /* nn.ConvTranspose2d(Cin, Cout, 2, stride=2) forward — unet_model.py:67,70,73,76 — as a GEMM
  * [B*H*W, Cin] x [Cin, 4*Cout] with a pixel-shuffle scatter epilogue that writes (+bias) straight into a
  * channel slot of the decoder's concat buffer (this replaces torch.cat, unet_model.py:101,105,109,113).
@@ -239,9 +247,11 @@ int b200sr_fd_maxpool2x2_bwd_relu(const void* act, int act_pix_stride, int act_c
                                   int dskip_pix_stride, int dskip_c_off, int C, void* dz, float* ps, int B, int H, int W,
                                   void* stream);
 typedef struct b200sr_fd_bias_job {
-    const float* ps; /* [B][C] */
+    const float* ps; /* [rows][stride] partial sums */
     float* dst;      /* [C] bias gradient, ADDED into */
     int32_t C;
+    int32_t rows;    /* 0: one row per sample (the B argument) */
+    int32_t stride;  /* floats between rows; 0: C */
     int32_t pad;
 } b200sr_fd_bias_job;
 /* dst[c] += sum_b ps[b][c] for a DEVICE table of jobs (all conv biases of the network in one launch). */

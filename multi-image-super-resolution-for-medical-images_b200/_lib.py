@@ -11,7 +11,7 @@ import os
 from ctypes import c_char_p, c_double, c_float, c_int, c_int64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb200sr.so")
+LIB_PATH = os.environ.get("B200SR_LIB") or os.path.join(_HERE, "libb200sr.so")  # B200SR_LIB: A/B builds of the library
 
 _lib = None
 _load_error = None
@@ -26,6 +26,8 @@ _SIGNATURES = {
                            _P, c_int, _P],
     "b200sr_conv3x3_dgrad": [_P, c_int, c_int, c_int, _P, c_int, c_int, c_int, c_int, _P, c_int, c_int, _P, c_int,
                              _P],
+    "b200sr_conv3x3_dgrad_relu": [_P, c_int, c_int, c_int, _P, c_int, c_int, c_int, c_int, _P, c_int, c_int, _P, c_int,
+                                  c_int, _P, c_int, _P],
     "b200sr_convT2x2_fwd": [_P, c_int, c_int, c_int, _P, c_int, _P, c_int, c_int, c_int, _P, c_int, c_int, _P],
     "b200sr_convT2x2_dgrad": [_P, c_int, c_int, c_int, _P, c_int, c_int, c_int, c_int, _P, c_int, c_int, _P],
     "b200sr_conv3x3_wgrad": [_P, c_int, c_int, c_int, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P],
@@ -117,14 +119,14 @@ def last_error() -> str:
 
 # ---- launch accounting and optional per-call CUDA-event timing (used by bench.py for the roofline) ------------
 LAUNCH_COUNTER = {"n": 0}
-GEMM_OPS = ("b200sr_conv3x3_fwd", "b200sr_conv3x3_dgrad", "b200sr_conv3x3_wgrad", "b200sr_convT2x2_fwd",
+GEMM_OPS = ("b200sr_conv3x3_fwd", "b200sr_conv3x3_dgrad", "b200sr_conv3x3_dgrad_relu", "b200sr_conv3x3_wgrad", "b200sr_convT2x2_fwd",
             "b200sr_convT2x2_dgrad", "b200sr_convT2x2_wgrad", "b200sr_conv1x1", "b200sr_conv1x1_wgrad")
 _profile = None  # list of (name, start_event, end_event, flop, bytes) while profiling is enabled
 
 
 def _cost(name, a):
     """Algorithmic (flop, bytes) of one call, from its argument list (see include/b200sr.h for the order)."""
-    if name in ("b200sr_conv3x3_fwd", "b200sr_conv3x3_dgrad"):
+    if name in ("b200sr_conv3x3_fwd", "b200sr_conv3x3_dgrad", "b200sr_conv3x3_dgrad_relu"):
         return 2.0 * a[6] * a[7] * a[8] * a[3] * a[5] * 9, 0.0
     if name in ("b200sr_convT2x2_dgrad",):
         return 2.0 * a[6] * a[7] * a[8] * a[3] * a[5] * 4, 0.0

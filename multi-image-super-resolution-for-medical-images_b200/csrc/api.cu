@@ -323,9 +323,11 @@ int dispatch_conv3(int block_n, const CUtensorMap& ma, const CUtensorMap& mb, co
 // out = (B,2H,2W,cout_t) slot); mode 2: ConvT dgrad (a = (B,2H,2W,Ca) slot gathered per sub-pixel, out (B,H,W,n_total))
 int run_conv3(int mode, const void* a, int a_stride, int a_coff, int Ca, const void* w_packed, int n_total, int B, int H, int W,
               void* out, int out_stride, int out_coff, const float* col_scale, const float* col_shift, int relu,
-              float* stats, int stats_replicas, int cout_t, cudaStream_t st) {
+              float* stats, int stats_replicas, int cout_t, cudaStream_t st, const void* mask = nullptr,
+              int mask_stride = 0, int mask_coff = 0) {
     B2_CHECK_ARG(a != nullptr && w_packed != nullptr && out != nullptr);
     B2_CHECK_ARG(B > 0 && H > 0 && W > 0 && H % C3_TILE_H == 0 && W % C3_TILE_W == 0);
+    B2_CHECK_ARG(mask == nullptr || (mode == 0 && mask_stride % 8 == 0 && mask_coff % 8 == 0 && aligned16(mask)));
     if (mode == 1) B2_CHECK_ARG(cout_t % 32 == 0 && n_total == 4 * cout_t);
     B2_CHECK_ARG(Ca % 64 == 0 && n_total % 64 == 0);
     B2_CHECK_ARG(a_stride % 8 == 0 && a_coff % 8 == 0 && out_stride % 8 == 0 && out_coff % 8 == 0);
@@ -386,6 +388,9 @@ int run_conv3(int mode, const void* a, int a_stride, int a_coff, int Ca, const v
     args.col_shift = col_shift;
     args.stats = stats;
     args.cout_t = cout_t;
+    args.mask = static_cast<const __nv_bfloat16*>(mask);
+    args.mask_pix_stride = mask_stride;
+    args.mask_c_off = mask_coff;
     args.epi_debug = getenv("B200SR_EPI_DEBUG") ? atoi(getenv("B200SR_EPI_DEBUG")) : 0;
     {
         const int nh = block_n / (block_n < 128 ? block_n : 128);
@@ -408,6 +413,7 @@ int run_conv3(int mode, const void* a, int a_stride, int a_coff, int Ca, const v
     grid -= grid % args.n_tiles;
     if (grid < args.n_tiles) grid = args.n_tiles;
     if (grid > args.num_tiles) grid = args.num_tiles;
+    if (mode == 0 && mask != nullptr) return dispatch_conv3<4>(block_n, ma, mb, mo, args, grid, st);
     if (mode == 0) return dispatch_conv3<0>(block_n, ma, mb, mo, args, grid, st);
     if (mode == 1) return dispatch_conv3<1>(block_n, ma, mb, mo, args, grid, st);
     if (mode == 3) return dispatch_conv3<3>(block_n, ma, mb, mo, args, grid, st);
@@ -640,6 +646,15 @@ int b200sr_conv3x3_dgrad(const void* dy, int dy_pix_stride, int dy_c_off, int Co
                          nullptr, nullptr, 0, stats, stats_replicas, Cin, static_cast<cudaStream_t>(stream));
     return run_igemm(0, dy, dy_pix_stride, dy_c_off, Cout, 9, w_packed, Cin, B, H, W, 0, Cin, dx, dx_pix_stride,
                      dx_c_off, nullptr, nullptr, 0, stats, stats_replicas, static_cast<cudaStream_t>(stream));
+}
+
+int b200sr_conv3x3_dgrad_relu(const void* dy, int dy_pix_stride, int dy_c_off, int Cout, const void* w_packed, int Cin,
+                              int B, int H, int W, void* dx, int dx_pix_stride, int dx_c_off, const void* act,
+                              int act_pix_stride, int act_c_off, float* stats, int stats_replicas, void* stream) {
+    B2_CHECK_ARG(act != nullptr && H % C3_TILE_H == 0 && W % C3_TILE_W == 0);
+    return run_conv3(0, dy, dy_pix_stride, dy_c_off, Cout, w_packed, Cin, B, H, W, dx, dx_pix_stride, dx_c_off, nullptr,
+                     nullptr, 0, stats, stats_replicas, Cin, static_cast<cudaStream_t>(stream), act, act_pix_stride,
+                     act_c_off);
 }
 
 int b200sr_convT2x2_fwd(const void* x, int x_pix_stride, int x_c_off, int Cin, const void* w_packed, int Cout,

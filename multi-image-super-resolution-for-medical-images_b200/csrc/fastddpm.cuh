@@ -300,16 +300,20 @@ __global__ void __launch_bounds__(256) fd_maxpool2x2_bwd_relu_kernel(const __nv_
 }
 
 struct FdBiasJob {
-    const float* ps;  // [B][C]
+    const float* ps;  // [rows][stride] partial sums (per sample, or the statistic replicas of a conv epilogue)
     float* dst;       // [C] bias gradient, ADDED into
     int C;
+    int rows;         // 0: one row per sample (B)
+    int stride;       // floats between rows; 0: C
     int pad;
 };
 __global__ void fd_bias_finish_kernel(const FdBiasJob* __restrict__ jobs, int B) {
     const FdBiasJob job = jobs[blockIdx.x];
+    const int rows = job.rows > 0 ? job.rows : B;
+    const int stride = job.stride > 0 ? job.stride : job.C;
     for (int c = threadIdx.x; c < job.C; c += blockDim.x) {
         float s = 0.f;
-        for (int b = 0; b < B; ++b) s += job.ps[static_cast<size_t>(b) * job.C + c];
+        for (int b = 0; b < rows; ++b) s += job.ps[static_cast<size_t>(b) * stride + c];
         job.dst[c] += s;
     }
 }

@@ -34,7 +34,11 @@ from . import _lib
 from ._lib import call, ptr
 from .engine import PACK_CONV_DGRAD, PACK_CONV_FWD, UNPACK_CONV_WGRAD, _PACK_JOB_DTYPE, _align, _jobs_to_device
 
-_BIAS_JOB_DTYPE = np.dtype([("ps", "<u8"), ("dst", "<u8"), ("C", "<i4"), ("pad", "<i4")])
+_BIAS_JOB_DTYPE = np.dtype([("ps", "<u8"), ("dst", "<u8"), ("C", "<i4"), ("rows", "<i4"), ("stride", "<i4"),
+                            ("pad", "<i4")])
+_EPI_STATS_REPLICAS = 4  # statistic replicas of a conv epilogue (bias sums of the layers masked inside a dgrad)
+# layers whose incoming gradient is produced by the dgrad of the conv above them: mask + bias sums in its epilogue
+_MASKED_IN_DGRAD = {"up1.0": "up1.2", "up2.0": "up2.2", "down2.0": "down2.2", "down1.0": "down1.2"}
 
 
 def sinusoidal_timestep_embedding(timesteps, dim):
@@ -317,9 +321,19 @@ class FastDDPMEngine:
             plan["ps_off"][c.name] = ps_total
             ps_total += B * c.cout
         plan["ps"] = torch.zeros(ps_total, dtype=f32, device=dev)
+        # bias sums of the layers masked inside a dgrad epilogue arrive as [replicas][2][C] statistics
+        st_total, plan["st_off"] = 0, {}
+        for name in _MASKED_IN_DGRAD:
+            plan["st_off"][name] = st_total
+            st_total += _EPI_STATS_REPLICAS * 2 * self.by_name[name].cout
+        plan["epi_stats"] = torch.zeros(st_total, dtype=f32, device=dev)
         jobs = np.zeros(len(self.convs), dtype=_BIAS_JOB_DTYPE)
         for i, c in enumerate(self.convs):
-            jobs[i] = (plan["ps"].data_ptr() + 4 * plan["ps_off"][c.name], self._g(c.mod.bias), c.cout, 0)
+            if self.fuse_relu_bwd and c.name in _MASKED_IN_DGRAD:
+                jobs[i] = (plan["epi_stats"].data_ptr() + 4 * plan["st_off"][c.name], self._g(c.mod.bias), c.cout,
+                           _EPI_STATS_REPLICAS, 2 * c.cout, 0)
+            else:
+                jobs[i] = (plan["ps"].data_ptr() + 4 * plan["ps_off"][c.name], self._g(c.mod.bias), c.cout, 0, 0, 0)
         plan["bias_jobs"] = _jobs_to_device(jobs, dev)
         plan["S"] = torch.empty(B, 9, 64, dtype=f32, device=dev)
         plan["de"] = torch.empty(B, 256, dtype=f32, device=dev)
@@ -399,6 +413,7 @@ class FastDDPMEngine:
         self.flat_g.zero_()
         self.flat_G.zero_()
         plan["ps"].zero_()
+        plan["epi_stats"].zero_()
         g0, g1 = plan["g0"].data_ptr(), plan["g1"].data_ptr()
         ps = plan["ps"].data_ptr()
 
@@ -424,6 +439,20 @@ class FastDDPMEngine:
             call("b200sr_conv3x3_dgrad", dz, cv.cout, 0, cv.cout, self._wp(self.wp_dgrad, name), cv.cin, B, h, w, dx,
                  dx_stride, 0, None, 0, st)
 
+        def dgrad_into(below, act, dz, dx, h, w):
+            """dgrad of the conv above `below`, producing dz of `below` directly: with the fusion on, the ReLU mask of
+            `below` (its stored activation) and its bias sums are applied in the dgrad epilogue; otherwise dgrad followed
+            by the separate ReLU-backward + bias pass (in place)."""
+            above = _MASKED_IN_DGRAD[below]
+            cv = c[above]
+            if self.fuse_relu_bwd:
+                call("b200sr_conv3x3_dgrad_relu", dz, cv.cout, 0, cv.cout, self._wp(self.wp_dgrad, above), cv.cin, B, h, w,
+                     dx, cv.cin, 0, ptr(act), cv.cin, 0, plan["epi_stats"].data_ptr() + 4 * plan["st_off"][below],
+                     _EPI_STATS_REPLICAS, st)
+            else:
+                dgrad(above, dz, dx, cv.cin, h, w)
+                relu_bwd(below, dx, cv.cin, 0, act, cv.cin, 0, dx, h, w)
+
         fused = self.fuse_relu_bwd  # ReLU mask + bias sums applied where a bandwidth-bound kernel forms the gradient
 
         def ps_of(name):
@@ -438,8 +467,7 @@ class FastDDPMEngine:
             relu_bwd("up1.2", g0, 64, 0, plan["u1"], 64, 0, g0, H, W)
         # up1
         wgrad("up1.2", plan["a_u1"], 64, 0, g0, H, W)
-        dgrad("up1.2", g0, g1, 64, H, W)
-        relu_bwd("up1.0", g1, 64, 0, plan["a_u1"], 64, 0, g1, H, W)
+        dgrad_into("up1.0", plan["a_u1"], g0, g1, H, W)
         wgrad("up1.0", plan["cat1"], 192, 0, g1, H, W)
         dgrad("up1.0", g1, ptr(plan["d_cat1"]), 192, H, W)
         if fused:
@@ -450,8 +478,7 @@ class FastDDPMEngine:
             relu_bwd("up2.2", g0, 128, 0, plan["u2"], 128, 0, g0, H1, W1)
         # up2
         wgrad("up2.2", plan["a_u2"], 128, 0, g0, H1, W1)
-        dgrad("up2.2", g0, g1, 128, H1, W1)
-        relu_bwd("up2.0", g1, 128, 0, plan["a_u2"], 128, 0, g1, H1, W1)
+        dgrad_into("up2.0", plan["a_u2"], g0, g1, H1, W1)
         wgrad("up2.0", plan["cat2"], 384, 0, g1, H1, W1)
         dgrad("up2.0", g1, ptr(plan["d_cat2"]), 384, H1, W1)
         if fused:
@@ -462,8 +489,7 @@ class FastDDPMEngine:
             relu_bwd("down2.2", g0, 256, 0, plan["c3"], 256, 0, g0, H2, W2)
         # down2
         wgrad("down2.2", plan["a_d2"], 256, 0, g0, H2, W2)
-        dgrad("down2.2", g0, g1, 256, H2, W2)
-        relu_bwd("down2.0", g1, 256, 0, plan["a_d2"], 256, 0, g1, H2, W2)
+        dgrad_into("down2.0", plan["a_d2"], g0, g1, H2, W2)
         wgrad("down2.0", plan["p2"], 128, 0, g1, H2, W2)
         dgrad("down2.0", g1, g0, 128, H2, W2)                                                      # -> d p2
         if fused:
@@ -475,8 +501,7 @@ class FastDDPMEngine:
             relu_bwd("down1.2", g1, 128, 0, plan["cat2"], 384, 256, g1, H1, W1)
         # down1
         wgrad("down1.2", plan["a_d1"], 128, 0, g1, H1, W1)
-        dgrad("down1.2", g1, g0, 128, H1, W1)
-        relu_bwd("down1.0", g0, 128, 0, plan["a_d1"], 128, 0, g0, H1, W1)
+        dgrad_into("down1.0", plan["a_d1"], g1, g0, H1, W1)
         wgrad("down1.0", plan["p1"], 64, 0, g0, H1, W1)
         dgrad("down1.0", g0, g1, 64, H1, W1)                                                       # -> d p1
         if fused:

@@ -178,21 +178,23 @@ class PerceptualLoss(nn.Module):
         def relu_bwd(dy, act, out, n):
             call("b200sr_relu_bwd", dy, ptr(act), out, n, st)
 
+        def dgrad_relu(k, dy, dx, act, h, w):
+            """dgrad of conv k with the ReLU mask of the layer below (its stored activation) applied in the epilogue"""
+            _, cin, cout = _CONVS[k]
+            call("b200sr_conv3x3_dgrad_relu", dy, cout, 0, cout, self.wp.data_ptr() + 2 * self.off_d[k], cin, B, h, w, dx,
+                 cin, 0, ptr(act), cin, 0, None, 0, st)
+
         h4, w4, h2, w2 = H // 4, W // 4, H // 2, W // 2
-        dgrad(6, g0, g1, h4, w4)                                  # -> d a6 (pre-mask)
-        relu_bwd(g1, a[6], g1, B * h4 * w4 * 256)
-        dgrad(5, g1, g0, h4, w4)
-        relu_bwd(g0, a[5], g0, B * h4 * w4 * 256)
+        dgrad_relu(6, g0, g1, a[6], h4, w4)                       # -> d z6 (masked by a6 > 0 in the epilogue)
+        dgrad_relu(5, g1, g0, a[5], h4, w4)
         dgrad(4, g0, g1, h4, w4)                                  # -> d p2
         call("b200sr_maxpool2x2_bwd", ptr(a[4]), 128, 0, g1, None, 0, 0, 128, g0, B, h2, w2, st)
         relu_bwd(g0, a[4], g0, B * h2 * w2 * 128)
-        dgrad(3, g0, g1, h2, w2)
-        relu_bwd(g1, a[3], g1, B * h2 * w2 * 128)
+        dgrad_relu(3, g0, g1, a[3], h2, w2)
         dgrad(2, g1, g0, h2, w2)                                  # -> d p1
         call("b200sr_maxpool2x2_bwd", ptr(a[2]), 64, 0, g0, None, 0, 0, 64, g1, B, H, W, st)
         relu_bwd(g1, a[2], g1, B * H * W * 64)
-        dgrad(1, g1, g0, H, W)
-        relu_bwd(g0, a[1], g0, B * H * W * 64)
+        dgrad_relu(1, g1, g0, a[1], H, W)
         call("b200sr_conv1_dgrad", g0, ptr(self.w1), ptr(b["dx2"]), B, H, W, st)
         return loss, b["dx2"][:, 0:1].contiguous()
 

@@ -117,6 +117,27 @@ def conv3x3_dgrad(B=2, H=16, W=32, Cin=64, Cout=128, seed=2):
     return {"dx": rel(out, ref), "colsum": rel(stats.sum(0)[0], out.sum(dim=(0, 2, 3)))}
 
 
+def conv3x3_dgrad_relu(B=2, H=16, W=32, Cin=64, Cout=128, seed=61, slot=False):
+    """dgrad fused with the ReLU mask of the layer below + its bias sums (Conv+ReLU stacks: Fast-DDPM, VGG)."""
+    _setup()
+    dy = bf(rnd(B, Cout, H, W, seed=seed))
+    w = bf(rnd(Cout, Cin, 3, 3, seed=seed + 1, scale=(9 * Cout) ** -0.5))
+    act = bf(torch.relu(rnd(B, Cin, H, W, seed=seed + 2)))  # stored post-ReLU activation: about half the entries are 0
+    ref = F.conv_transpose2d(dy, w, padding=1) * (act > 0)
+    wp = pack(w, 1, Cout, Cin)
+    dyb = nhwc(dy)
+    a_tot, a_off = (Cin + 64, 64) if slot else (Cin, 0)
+    actb = slot_buffer(B, H, W, Cin, a_tot, a_off, nhwc(act))
+    dxb = torch.zeros(B, H, W, Cin, dtype=torch.bfloat16, device=DEV)
+    stats = torch.zeros(R, 2, Cin, device=DEV)
+    call("b200sr_conv3x3_dgrad_relu", ptr(dyb), Cout, 0, Cout, ptr(wp), Cin, B, H, W, ptr(dxb), Cin, 0, ptr(actb), a_tot,
+         a_off, ptr(stats), R, st())
+    torch.cuda.synchronize()
+    out = nchw(dxb)
+    masked_out = float((out * (act <= 0)).abs().max())
+    return {"dx": rel(out, ref), "colsum": rel(stats.sum(0)[0], out.sum(dim=(0, 2, 3))), "masked_nonzero": masked_out}
+
+
 def conv3x3_wgrad(B=2, H=16, W=32, Cin=64, Cout=128, seed=3, slot=False):
     _setup()
     x = bf(rnd(B, Cin, H, W, seed=seed))
@@ -564,6 +585,9 @@ CHECKS = {
     "conv_determinism": (conv_determinism, {}, {"conv_bitwise": 0.0, "convT_bitwise": 0.0}),
     "conv3x3_dgrad": (conv3x3_dgrad, {}, {"dx": BF16, "colsum": 1e-3}),
     "conv3x3_dgrad_wide": (conv3x3_dgrad, dict(Cin=256, Cout=64, B=1, H=32, W=16), {"dx": BF16}),
+    "conv3x3_dgrad_relu": (conv3x3_dgrad_relu, {}, {"dx": BF16, "colsum": 1e-3, "masked_nonzero": 0.0}),
+    "conv3x3_dgrad_relu_n256_slot": (conv3x3_dgrad_relu, dict(Cin=256, Cout=128, B=1, H=32, W=16, slot=True),
+                                     {"dx": BF16, "colsum": 1e-3, "masked_nonzero": 0.0}),
     # persistent schedule: more tiles than SMs, one and several column blocks per row block
     "conv3x3_fwd_persistent_n64": (conv3x3_fwd, dict(Cin=64, Cout=64, B=6, H=64, W=64),
                                    {"out": BF16, "stats_sum": 1e-3, "stats_sq": 1e-3}),
