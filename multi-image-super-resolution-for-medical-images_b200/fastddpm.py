@@ -539,6 +539,8 @@ class FastDDPM(nn.Module):
         self.unet = UNet2D(in_ch=3, base_ch=64, time_dim=256).to(device)
         from .losses import CombinedLoss
         self.__dict__["_mse"] = CombinedLoss(mse_weight=1.0, ssim_weight=0.0)
+        self.__dict__["sample_graphs"] = os.environ.get("B200SR_NO_SAMPLE_GRAPH") is None
+        self.__dict__["_sample_graph_cache"], self.__dict__["_sample_graph_calls"] = {}, {}
 
     def _coef(self, t, dev):
         sch = self.scheduler
@@ -572,6 +574,37 @@ class FastDDPM(nn.Module):
         B, _, H, W = cond.shape
         x = (torch.randn(B, 1, H, W, device=dev) if noise is None else noise.to(dev).float().clone()).contiguous()
         engine = self.unet._get_engine()
+        if not self.sample_graphs or torch.cuda.is_current_stream_capturing():
+            return self._sample_loop(engine, x, cond)
+        # the whole T-step chain (T x ~22 launches + T DDIM updates) is replayed from one CUDA graph per input shape
+        key = (B, H, W, dev)
+        g = self._sample_graph_cache.get(key)
+        if g is not None and g[3] != engine.flat_p.data_ptr():
+            g = None  # parameters were re-flattened (model.to(), new tensors): the graph points into freed buffers
+        if g is None:
+            n = self._sample_graph_calls.get(key, 0)
+            self._sample_graph_calls[key] = n + 1
+            if n < 2:  # lazy set-up (plan buffers, TMA descriptors, packed weights) happens eagerly first
+                return self._sample_loop(engine, x, cond)
+            static_x, static_cond = x.clone(), cond.clone()
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                self._sample_loop(engine, static_x, static_cond)
+            g = (graph, static_x, static_cond, engine.flat_p.data_ptr())
+            self._sample_graph_cache[key] = g
+        graph, static_x, static_cond, _ = g
+        engine.ensure_ready(dev)
+        engine._repack_if_needed(_lib.current_stream_ptr())  # packed bf16 weights follow the parameters
+        static_x.copy_(x)
+        static_cond.copy_(cond)
+        graph.replay()
+        return static_x.clone()
+
+    def _sample_loop(self, engine, x, cond):
+        """T denoiser evaluations + DDIM updates, in place on x (which is also returned)."""
+        dev = x.device
+        B, _, H, W = x.shape
         T = self.scheduler.T
         ab = self.scheduler._alpha_bar_host
         n = B * H * W
