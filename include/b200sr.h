@@ -97,11 +97,12 @@ typedef struct b200sr_pack_job {
     const void* src;
     void* dst;
     int32_t kind; /* 0 conv fwd, 1 conv dgrad, 2 convT fwd, 3 convT dgrad, 4 conv wgrad unpack, 5 convT wgrad unpack,
-                     6 conv1x1 fwd, 7 conv1x1 dgrad, 8 conv1x1 wgrad unpack */
+                     6 conv1x1 fwd, 7 conv1x1 dgrad, 8 conv1x1 wgrad unpack, 9 conv fwd+dgrad (dst, count = second
+                     destination), 10 convT fwd+dgrad likewise */
     int32_t cout;
     int32_t cin;
     int32_t pad;
-    int64_t count; /* elements of dst */
+    int64_t count; /* elements of dst; kinds 9 / 10: the dgrad-packing destination pointer */
 } b200sr_pack_job;
 int b200sr_pack_jobs(const b200sr_pack_job* jobs, int njobs, void* stream);
 

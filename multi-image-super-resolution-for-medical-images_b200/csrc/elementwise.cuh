@@ -58,6 +58,8 @@ enum PackKind : int {
     PACK_CONV1X1_FWD = 6,    // (Cout,Cin,1,1) f32 -> [Cout][Cin] bf16
     PACK_CONV1X1_DGRAD = 7,  // (Cout,Cin,1,1) f32 -> [Cin][Cout] bf16
     UNPACK_CONV1X1_WGRAD = 8,  // G[ci][co] f32 -> (Cout,Cin,1,1) f32
+    PACK_CONV_BOTH = 9,    // kinds 0 and 1 from ONE read of the parameter tile: dst = forward, aux = dgrad packing
+    PACK_CONVT_BOTH = 10,  // kinds 2 and 3 likewise
 };
 
 struct PackJob {
@@ -67,7 +69,7 @@ struct PackJob {
     int cout;
     int cin;
     int pad;
-    long long count;  // elements of dst
+    long long count;  // elements of dst; kinds 9 / 10: the second destination pointer (dgrad packing)
 };
 
 // One 32 x 32 x T tile (T = 9 conv taps or 4 sub-pixels) per block iteration, staged through shared memory so that
@@ -79,8 +81,9 @@ __global__ void __launch_bounds__(256) pack_jobs_kernel(const PackJob* __restric
     __shared__ float tile[PK_TILE][PK_TILE * 9 + 1];
     const PackJob job = jobs[blockIdx.y];
     const int Cout = job.cout, Cin = job.cin;
-    const bool one = job.kind >= PACK_CONV1X1_FWD;
-    const bool conv = one || job.kind == PACK_CONV_FWD || job.kind == PACK_CONV_DGRAD || job.kind == UNPACK_CONV_WGRAD;
+    const bool one = job.kind >= PACK_CONV1X1_FWD && job.kind <= UNPACK_CONV1X1_WGRAD;
+    const bool conv = one || job.kind == PACK_CONV_FWD || job.kind == PACK_CONV_DGRAD || job.kind == UNPACK_CONV_WGRAD ||
+                      job.kind == PACK_CONV_BOTH;
     const int T = one ? 1 : (conv ? 9 : 4);
     const int outer_total = conv ? Cout : Cin, inner_total = conv ? Cin : Cout;
     const int tiles_in = inner_total / PK_TILE;
@@ -91,7 +94,8 @@ __global__ void __launch_bounds__(256) pack_jobs_kernel(const PackJob* __restric
         const int o0 = (tl / tiles_in) * PK_TILE, i0 = (tl % tiles_in) * PK_TILE;
         __syncthreads();
         // ---- load ----
-        if (job.kind <= PACK_CONVT_DGRAD || job.kind == PACK_CONV1X1_FWD || job.kind == PACK_CONV1X1_DGRAD) {
+        if (job.kind <= PACK_CONVT_DGRAD || job.kind == PACK_CONV1X1_FWD || job.kind == PACK_CONV1X1_DGRAD ||
+            job.kind >= PACK_CONV_BOTH) {
             const float* src = static_cast<const float*>(job.src);
             for (int idx = tid; idx < PK_TILE * row; idx += 256) {
                 const int o = idx / row, r = idx - o * row;
@@ -122,6 +126,36 @@ __global__ void __launch_bounds__(256) pack_jobs_kernel(const PackJob* __restric
                     const int o = idx % PK_TILE, t = (idx / PK_TILE) % 9, i = idx / (PK_TILE * 9);
                     dst[static_cast<long long>(i0 + i) * (9LL * Cout) + t * Cout + o0 + o] =
                         __float2bfloat16_rn(tile[o][i * 9 + 8 - t]);
+                }
+                break;
+            }
+            case PACK_CONV_BOTH: {  // both packings of a Conv2d weight from the tile already in shared memory
+                __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(job.dst);
+                __nv_bfloat16* aux = reinterpret_cast<__nv_bfloat16*>(job.count);
+                for (int idx = tid; idx < PK_TILE * row; idx += 256) {
+                    const int i = idx % PK_TILE, t = (idx / PK_TILE) % 9, o = idx / (PK_TILE * 9);
+                    dst[static_cast<long long>(o0 + o) * (9LL * Cin) + t * Cin + i0 + i] =
+                        __float2bfloat16_rn(tile[o][i * 9 + t]);
+                }
+                for (int idx = tid; idx < PK_TILE * row; idx += 256) {
+                    const int o = idx % PK_TILE, t = (idx / PK_TILE) % 9, i = idx / (PK_TILE * 9);
+                    aux[static_cast<long long>(i0 + i) * (9LL * Cout) + t * Cout + o0 + o] =
+                        __float2bfloat16_rn(tile[o][i * 9 + 8 - t]);
+                }
+                break;
+            }
+            case PACK_CONVT_BOTH: {  // both packings of a ConvTranspose2d weight (outer = ci, inner = co)
+                __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(job.dst);
+                __nv_bfloat16* aux = reinterpret_cast<__nv_bfloat16*>(job.count);
+                for (int idx = tid; idx < PK_TILE * row; idx += 256) {
+                    const int o = idx % PK_TILE, t = (idx / PK_TILE) % 4, i = idx / (PK_TILE * 4);
+                    dst[(static_cast<long long>(t) * Cout + i0 + i) * Cin + o0 + o] =
+                        __float2bfloat16_rn(tile[o][i * 4 + t]);
+                }
+                for (int idx = tid; idx < PK_TILE * row; idx += 256) {
+                    const int i = idx % PK_TILE, t = (idx / PK_TILE) % 4, o = idx / (PK_TILE * 4);
+                    aux[static_cast<long long>(o0 + o) * (4LL * Cout) + t * Cout + i0 + i] =
+                        __float2bfloat16_rn(tile[o][i * 4 + t]);
                 }
                 break;
             }

@@ -24,6 +24,7 @@ BN_EPS = 1e-5
 BN_MOMENTUM = 0.1
 
 PACK_CONV_FWD, PACK_CONV_DGRAD, PACK_CONVT_FWD, PACK_CONVT_DGRAD, UNPACK_CONV_WGRAD, UNPACK_CONVT_WGRAD = range(6)
+PACK_CONV_BOTH, PACK_CONVT_BOTH = 9, 10  # forward + dgrad packing from one read of the parameter
 
 _PACK_JOB_DTYPE = np.dtype([("src", "<u8"), ("dst", "<u8"), ("kind", "<i4"), ("cout", "<i4"), ("cin", "<i4"),
                             ("pad", "<i4"), ("count", "<i8")])
@@ -175,36 +176,36 @@ class UNetEngine:
             wp_total += _align(n)
         self.flat_wp = torch.zeros(wp_total, dtype=torch.bfloat16, device=device)
 
-        pack = np.zeros(2 * (len(self.convs) - 1 + len(self.ups)), dtype=_PACK_JOB_DTYPE)
+        # one job per layer writes BOTH packings (forward + dgrad) from a single read of the fp32 parameter
+        pack = np.zeros(len(self.convs) - 1 + len(self.ups), dtype=_PACK_JOB_DTYPE)
         unpack = np.zeros(len(self.convs) - 1 + len(self.ups), dtype=_PACK_JOB_DTYPE)
         i = j = 0
         wp_base, g_base, G_base = self.flat_wp.data_ptr(), self.flat_g.data_ptr(), self.flat_G.data_ptr()
         for cs in self.convs[1:]:
             w = cs.conv.weight
             n = w.numel()
-            pack[i] = (w.data_ptr(), wp_base + 2 * self.wp_fwd[cs.name], PACK_CONV_FWD, cs.cout, cs.cin, 0, n)
-            pack[i + 1] = (w.data_ptr(), wp_base + 2 * self.wp_dgrad[cs.name], PACK_CONV_DGRAD, cs.cout, cs.cin, 0, n)
-            i += 2
+            pack[i] = (w.data_ptr(), wp_base + 2 * self.wp_fwd[cs.name], PACK_CONV_BOTH, cs.cout, cs.cin, 0,
+                       wp_base + 2 * self.wp_dgrad[cs.name])
+            i += 1
             off = self.off_of[id(w)]
             unpack[j] = (G_base + 4 * off, g_base + 4 * off, UNPACK_CONV_WGRAD, cs.cout, cs.cin, 0, n)
             j += 1
         for us in self.ups.values():
             w = us.mod.weight
             n = w.numel()
-            pack[i] = (w.data_ptr(), wp_base + 2 * self.wp_fwd[us.name], PACK_CONVT_FWD, us.cout, us.cin, 0, n)
-            pack[i + 1] = (w.data_ptr(), wp_base + 2 * self.wp_dgrad[us.name], PACK_CONVT_DGRAD, us.cout, us.cin, 0, n)
-            i += 2
+            pack[i] = (w.data_ptr(), wp_base + 2 * self.wp_fwd[us.name], PACK_CONVT_BOTH, us.cout, us.cin, 0,
+                       wp_base + 2 * self.wp_dgrad[us.name])
+            i += 1
             off = self.off_of[id(w)]
             unpack[j] = (G_base + 4 * off, g_base + 4 * off, UNPACK_CONVT_WGRAD, us.cout, us.cin, 0, n)
             j += 1
-        # three contiguous groups so the train step can stage the packing: forward packings of enc1/enc2 (needed
-        # first, tiny), forward packings of everything else, then all dgrad packings (needed only in backward)
-        is_fwd = (pack["kind"] == PACK_CONV_FWD) | (pack["kind"] == PACK_CONVT_FWD)
+        # two contiguous groups so the train step can stage the packing: enc1/enc2 (needed first, tiny) on the main
+        # stream, everything else on the side stream while those layers run
         early_dst = {wp_base + 2 * self.wp_fwd[cs.name] for cs in self.convs[1:4]}
         early = np.array([int(d) in early_dst for d in pack["dst"]])
-        order = np.concatenate([np.nonzero(is_fwd & early)[0], np.nonzero(is_fwd & ~early)[0], np.nonzero(~is_fwd)[0]])
+        order = np.concatenate([np.nonzero(early)[0], np.nonzero(~early)[0]])
         pack = pack[order]
-        self.pack_groups = (int((is_fwd & early).sum()), int((is_fwd & ~early).sum()), int((~is_fwd).sum()))
+        self.pack_groups = (int(early.sum()), int((~early).sum()), 0)
         self.pack_jobs = _jobs_to_device(pack, device)
         self.n_pack = len(pack)
         # unpack jobs sorted by flat offset so that suffix ranges (= gradient buckets) are contiguous job ranges
@@ -283,9 +284,12 @@ class UNetEngine:
         call("b200sr_pack_jobs", base + n0 * isz, n1, sst)
         fwd_done = torch.cuda.Event()
         fwd_done.record(self._side)
-        call("b200sr_pack_jobs", base + (n0 + n1) * isz, n2, sst)
-        self._pack_done = torch.cuda.Event()
-        self._pack_done.record(self._side)
+        if n2 > 0:
+            call("b200sr_pack_jobs", base + (n0 + n1) * isz, n2, sst)
+            self._pack_done = torch.cuda.Event()
+            self._pack_done.record(self._side)
+        else:
+            self._pack_done = fwd_done  # the dgrad packings came with the forward ones
         return fwd_done
 
     # ------------------------------------------------------------------------------------------------
