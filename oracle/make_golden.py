@@ -222,6 +222,10 @@ def main():
     mine_sched = b200sr.FastNoiseScheduler(10, "cpu")
     assert torch.equal(ab_o, ref_sched.alpha_bar) and torch.equal(mine_sched.alpha_bar, ref_sched.alpha_bar)
     assert torch.equal(mine_sched.beta, ref_sched.beta) and torch.equal(mine_sched.alpha, ref_sched.alpha)
+    for T_ in (4, 5, 20, 50):  # the step selection for other chain lengths (40 % up to t=699, 60 % after)
+        r_, m_ = ref_loader.FastNoiseScheduler(T_, "cpu"), b200sr.FastNoiseScheduler(T_, "cpu")
+        assert torch.equal(r_.alpha_bar, m_.alpha_bar) and torch.equal(fastddpm_oracle.schedule(T_)[0], r_.alpha_bar), T_
+    fout["alpha_bar_T20"] = ref_loader.FastNoiseScheduler(20, "cpu").alpha_bar.numpy()
     c = cases.FASTDDPM_CASE
     cond, target, t, noise = cases.fastddpm_inputs()
     fm = ref_loader.FastDDPM(T=10, device="cpu")

@@ -43,6 +43,10 @@ def test_scheduler_matches_reference_steps():
     np.testing.assert_allclose(s.coef_table[:, 0].numpy() ** 2 + s.coef_table[:, 1].numpy() ** 2, 1.0, rtol=1e-6)
     t = torch.tensor([0, 5, 9])
     assert torch.equal(b200sr.sinusoidal_timestep_embedding(t, 256), fastddpm_oracle.timestep_embedding(t, 256))
+    # other chain lengths: mirror == oracle restatement == reference (golden vector for T=20)
+    for T in (4, 5, 20, 50):
+        assert torch.equal(b200sr.FastNoiseScheduler(T, "cpu").alpha_bar, fastddpm_oracle.schedule(T)[0])
+    np.testing.assert_array_equal(b200sr.FastNoiseScheduler(20, "cpu").alpha_bar.numpy(), GOLD["alpha_bar_T20"])
 
 
 def test_oracle_matches_golden():
