@@ -46,8 +46,12 @@ int b200sr_device_ok(void);
  * dgrad-packed weights, its data gradient. x: (B,H,W,Cin) slot; w_packed: [Cout][9*Cin] bf16 from
  * b200sr_pack_jobs (PACK_CONV_FWD / PACK_CONV_DGRAD); out: (B,H,W,Cout) slot, raw conv result (no bias).
  * Optional epilogue: v = v*col_scale[c] + col_shift[c] (either may be NULL), ReLU if relu != 0 (eval-mode
- * folded BatchNorm, unet_model.py:28-29), and per-channel sum / sum-of-squares of the stored values added
- * into stats[(tile % stats_replicas)][2][Cout] (train-mode BatchNorm statistics; NULL to skip). */
+ * folded BatchNorm, unet_model.py:28-29), and per-channel sum / sum-of-squares of the stored values
+ * (train-mode BatchNorm statistics; NULL to skip) into stats[stats_replicas][2][Cout]:
+ *   - stats_replicas >= number of SMs (148): DETERMINISTIC slot mode — every CTA stores its partial sums into its own
+ *     slot, the unused slots are zeroed by the kernel, nothing has to be pre-zeroed and no atomics touch the data;
+ *   - fewer replicas: legacy mode, partial sums are atomically ADDED into slot (CTA % stats_replicas) of a buffer the
+ *     caller zeroed. The same rule holds for every entry point that takes (stats, stats_replicas). */
 int b200sr_conv3x3_fwd(const void* x, int x_pix_stride, int x_c_off, int Cin, const void* w_packed, int Cout,
                        int B, int H, int W, void* out, int out_pix_stride, int out_c_off,
                        const float* col_scale, const float* col_shift, int relu, float* stats,
@@ -131,11 +135,12 @@ int b200sr_conv1_dgrad(const void* dz, const float* w, float* dx, int B, int H, 
 int b200sr_conv1_wgrad(const float* x, const void* dz, float* dw, int B, int H, int W, void* stream);
 
 /* Train-mode nn.BatchNorm2d statistics -> scale/shift (+ saved mean/invstd, running-stat update with
- * momentum, unbiased variance; conv_bias re-added to running_mean). unet_model.py:28,31. */
+ * momentum, unbiased variance; conv_bias re-added to running_mean; num_batches_tracked += 1 when not NULL).
+ * unet_model.py:28,31. The `replicas` statistic slots are summed in a fixed order (double precision). */
 int b200sr_bn_finalize(const float* stats, int replicas, int C, double count, const float* gamma,
                        const float* beta, const float* conv_bias, float eps, float momentum, float* scale,
                        float* shift, float* save_mean, float* save_invstd, float* running_mean,
-                       float* running_var, void* stream);
+                       float* running_var, int64_t* num_batches_tracked, void* stream);
 
 /* BatchNorm-apply + ReLU (unet_model.py:28-29,31-32), optionally fused with MaxPool2d(2,2) (:52-61) and
  * writing the activation into a concat slot. z: (B,H,W,C) dense raw conv output. pooled may be NULL. */
@@ -300,6 +305,55 @@ int b200sr_adam_step(float* p, const float* g, float* m, float* v, int64_t n, fl
  * bias_corr[1] = sqrt(1 - beta2^step). The launch itself is then step-independent and can be replayed from a CUDA graph. */
 int b200sr_adam_step_dev(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
                          float eps, const float* bias_corr, float grad_scale, void* stream);
+
+/* ---- deterministic (bit-reproducible) reductions -------------------------------------------------------
+ * Every cross-CTA reduction of the UNet train step has a variant that never orders floating-point additions by
+ * scheduling: each CTA / split-K slice STORES its partial result into its own slot of a caller-provided workspace
+ * `ws`, and a second stage (the last CTA to finish, chosen by a ticket counter, or a tiny follow-up kernel on the
+ * same stream) adds the slots in slot order. Outputs are WRITTEN, not added: nothing needs pre-zeroing.
+ * `counters`: DEVICE uint32, zero-initialised ONCE by the caller; the kernels reset them. A workspace / counter set
+ * must not be shared by calls that may run concurrently on different streams. */
+
+/* Conv2d 3x3 weight gradient (autograd of unet_model.py:27,30), split-K partials in ws, then reduced in split order and
+ * written in the PyTorch parameter layout: dW[co][cin_off + ci][3][3] of a (Cout, cin_total, 3, 3) f32 tensor
+ * (cin_total > Cin: a conv whose input channels are split over several launches). The split factor is capped by
+ * ws_floats / (9*Cin*Cout). */
+int b200sr_conv3x3_wgrad_det(const void* x, int x_pix_stride, int x_c_off, int Cin, const void* dz, int dz_pix_stride,
+                             int dz_c_off, int Cout, int B, int H, int W, float* dW, int cin_total, int cin_off,
+                             float* ws, int64_t ws_floats, void* stream);
+/* ConvTranspose2d k2 s2 weight gradient (unet_model.py:67-76), dW written as (Cin, Cout, 2, 2) f32. */
+int b200sr_convT2x2_wgrad_det(const void* dup, int dup_pix_stride, int dup_c_off, int Cout, const void* x,
+                              int x_pix_stride, int x_c_off, int Cin, int B, int H, int W, float* dW, float* ws,
+                              int64_t ws_floats, void* stream);
+/* Conv2d 1x1 weight gradient, dW written as (Cout, Cin, 1, 1) f32. */
+int b200sr_conv1x1_wgrad_det(const void* x, int x_pix_stride, int x_c_off, int Cin, const void* dz, int dz_pix_stride,
+                             int dz_c_off, int Cout, int B, int H, int W, float* dW, float* ws, int64_t ws_floats,
+                             void* stream);
+/* First-layer weight gradient, dw (64,2,3,3) f32 WRITTEN; ws >= 1152 floats per CTA (up to 2 CTAs per SM). */
+int b200sr_conv1_wgrad_det(const float* x, const void* dz, float* dw, int B, int H, int W, float* ws, int64_t ws_floats,
+                           void* stream);
+/* dst[i] = sum_s slots[s*slot_stride + i], s ascending, i < n. */
+int b200sr_sum_slots(const float* slots, int nslots, int64_t slot_stride, int n, float* dst, void* stream);
+/* BatchNorm+ReLU backward, pass 1: sums[0][c] = sum g, sums[1][c] = invstd[c] * sum g*(z-mean) WRITTEN (consume with
+ * b200sr_bn_bwd_apply_fused(..., sums, replicas = 1, ...)). mask_src (nullable, dense (npix,C)): ReLU mask from a
+ * stored activation instead of scale*z+shift > 0. ws: b200sr_bn_bwd_ws_floats(C) floats; counters: C/64 uint32. */
+int64_t b200sr_bn_bwd_ws_floats(int C);
+int b200sr_bn_bwd_reduce_det(const void* dy, int dy_pix_stride, int dy_c_off, const void* z, int C, const float* scale,
+                             const float* shift, const float* mean, const float* invstd, float* sums, float* ws,
+                             int64_t ws_floats, uint32_t* counters, const void* mask_src, int64_t npix, void* stream);
+/* 1x1 head backward with dw (64) / db (1) WRITTEN; ws: 72 floats per CTA (up to 4 CTAs per SM); counter: 1 uint32. */
+int b200sr_head_bwd_det(const float* dout, const void* act, const float* w, void* dact, float* dw, float* db,
+                        int64_t npix, float* ws, int64_t ws_floats, uint32_t* counter, void* stream);
+/* Fused MSE + SSIM loss: out3 = {loss, mse, mean SSIM} (DEVICE f32) WRITTEN by the last CTA; ws: 2 doubles per CTA
+ * (B * ceil(H/32) * ceil(W/32) CTAs); counter: 1 uint32. Nothing is left for the host to combine. */
+int b200sr_mse_ssim_det(const float* pred, const float* target, float* grad, float* out3, int B, int H, int W,
+                        const float* win, int K, float cov_norm, float C1, float C2, float w_mse, float w_ssim,
+                        double* ws, int64_t ws_doubles, uint32_t* counter, void* stream);
+/* Adam with the step count resident on the device: step_dev = {completed steps, 0} (DEVICE int32[2], zero-initialised
+ * or set to the resumed step count). The kernel derives the bias corrections of step step_dev[0]+1 itself and the last
+ * CTA increments step_dev[0]: graph-replayable, and immune to a host that runs several steps ahead of the device. */
+int b200sr_adam_step_auto(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
+                          float eps, int32_t* step_dev, float grad_scale, void* stream);
 
 /* layout casts at the boundary */
 int b200sr_nchw_f32_to_nhwc_bf16(const float* in, void* out, int B, int C, int H, int W, void* stream);

@@ -37,7 +37,7 @@ _SIGNATURES = {
     "b200sr_conv1_fwd": [_P, _P, _P, _P, c_int, _P, _P, c_int, c_int, c_int, c_int, _P],
     "b200sr_conv1_dgrad": [_P, _P, _P, c_int, c_int, c_int, _P],
     "b200sr_conv1_wgrad": [_P, _P, _P, c_int, c_int, c_int, _P],
-    "b200sr_bn_finalize": [_P, c_int, c_int, c_double, _P, _P, _P, c_float, c_float, _P, _P, _P, _P, _P, _P, _P],
+    "b200sr_bn_finalize": [_P, c_int, c_int, c_double, _P, _P, _P, c_float, c_float, _P, _P, _P, _P, _P, _P, _P, _P],
     "b200sr_bnrelu_apply": [_P, c_int, _P, _P, _P, c_int, c_int, _P, c_int, c_int, c_int, _P],
     "b200sr_bn_train_apply": [_P, c_int, _P, c_int, c_double, _P, _P, _P, c_float, c_float, _P, _P, _P, _P, _P, _P, _P,
                               c_int, c_int, _P, c_int, c_int, c_int, _P],
@@ -82,10 +82,26 @@ _SIGNATURES = {
                         _P],
     "b200sr_adam_step": [_P, _P, _P, _P, c_int64, c_float, c_float, c_float, c_float, c_int64, c_float, _P],
     "b200sr_adam_step_dev": [_P, _P, _P, _P, c_int64, c_float, c_float, c_float, c_float, _P, c_float, _P],
+    # deterministic (bit-reproducible) reductions
+    "b200sr_conv3x3_wgrad_det": [_P, c_int, c_int, c_int, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P, c_int, c_int,
+                                 _P, c_int64, _P],
+    "b200sr_convT2x2_wgrad_det": [_P, c_int, c_int, c_int, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P, c_int64,
+                                  _P],
+    "b200sr_conv1x1_wgrad_det": [_P, c_int, c_int, c_int, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P, c_int64,
+                                 _P],
+    "b200sr_conv1_wgrad_det": [_P, _P, _P, c_int, c_int, c_int, _P, c_int64, _P],
+    "b200sr_sum_slots": [_P, c_int, c_int64, c_int, _P, _P],
+    "b200sr_bn_bwd_ws_floats": [c_int],
+    "b200sr_bn_bwd_reduce_det": [_P, c_int, c_int, _P, c_int, _P, _P, _P, _P, _P, _P, c_int64, _P, _P, c_int64, _P],
+    "b200sr_head_bwd_det": [_P, _P, _P, _P, _P, _P, c_int64, _P, c_int64, _P, _P],
+    "b200sr_mse_ssim_det": [_P, _P, _P, _P, c_int, c_int, c_int, _P, c_int, c_float, c_float, c_float, c_float, c_float,
+                            _P, c_int64, _P, _P],
+    "b200sr_adam_step_auto": [_P, _P, _P, _P, c_int64, c_float, c_float, c_float, c_float, _P, c_float, _P],
     "b200sr_nchw_f32_to_nhwc_bf16": [_P, _P, c_int, c_int, c_int, c_int, _P],
     "b200sr_nhwc_bf16_to_nchw_f32": [_P, c_int, c_int, _P, c_int, c_int, c_int, c_int, _P],
 }
-_RESTYPES = {"b200sr_last_error": c_char_p}
+_RESTYPES = {"b200sr_last_error": c_char_p, "b200sr_bn_bwd_ws_floats": c_int64}
+_PLAIN_VALUE = ("b200sr_version", "b200sr_last_error", "b200sr_bn_bwd_ws_floats")  # return a value, not a status code
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 
@@ -119,8 +135,13 @@ def last_error() -> str:
 
 # ---- launch accounting and optional per-call CUDA-event timing (used by bench.py for the roofline) ------------
 LAUNCH_COUNTER = {"n": 0}
+# entry points that enqueue more than one kernel (split-K gradient + its fixed-order reduction, multi-kernel helpers)
+_KERNELS_PER_CALL = {"b200sr_conv3x3_wgrad_det": 2, "b200sr_convT2x2_wgrad_det": 2, "b200sr_conv1x1_wgrad_det": 2,
+                     "b200sr_conv1_wgrad_det": 2, "b200sr_bn_bwd_masked": 2, "b200sr_grad_clip": 2, "b200sr_fd_time_bwd": 5,
+                     "b200sr_bn_bwd_ws_floats": 0, "b200sr_version": 0, "b200sr_device_ok": 0}
 GEMM_OPS = ("b200sr_conv3x3_fwd", "b200sr_conv3x3_dgrad", "b200sr_conv3x3_dgrad_relu", "b200sr_conv3x3_wgrad", "b200sr_convT2x2_fwd",
-            "b200sr_convT2x2_dgrad", "b200sr_convT2x2_wgrad", "b200sr_conv1x1", "b200sr_conv1x1_wgrad")
+            "b200sr_convT2x2_dgrad", "b200sr_convT2x2_wgrad", "b200sr_conv1x1", "b200sr_conv1x1_wgrad",
+            "b200sr_conv3x3_wgrad_det", "b200sr_convT2x2_wgrad_det", "b200sr_conv1x1_wgrad_det")
 _profile = None  # list of (name, start_event, end_event, flop, bytes) while profiling is enabled
 
 
@@ -132,10 +153,22 @@ def _cost(name, a):
         return 2.0 * a[6] * a[7] * a[8] * a[3] * a[5] * 4, 0.0
     if name == "b200sr_convT2x2_fwd":
         return 2.0 * a[7] * a[8] * a[9] * a[3] * a[5] * 4, 0.0
-    if name == "b200sr_conv3x3_wgrad":
+    if name in ("b200sr_conv3x3_wgrad", "b200sr_conv3x3_wgrad_det"):
         return 2.0 * a[8] * a[9] * a[10] * a[3] * a[7] * 9, 0.0
-    if name == "b200sr_convT2x2_wgrad":
+    if name in ("b200sr_convT2x2_wgrad", "b200sr_convT2x2_wgrad_det"):
         return 2.0 * a[8] * a[9] * a[10] * a[3] * a[7] * 4, 0.0
+    if name == "b200sr_conv1x1_wgrad_det":
+        return 2.0 * a[8] * a[9] * a[10] * a[3] * a[7], 0.0
+    if name == "b200sr_bn_bwd_reduce_det":
+        return 0.0, a[14] * a[4] * 2.0 * 2
+    if name == "b200sr_head_bwd_det":
+        return 0.0, a[6] * (4.0 + 128 + 128)
+    if name == "b200sr_mse_ssim_det":
+        return 0.0, a[4] * a[5] * a[6] * 4.0 * (3 if a[2] else 2)
+    if name == "b200sr_adam_step_auto":
+        return 0.0, a[4] * 4.0 * 7
+    if name == "b200sr_conv1_wgrad_det":
+        return 0.0, a[3] * a[4] * a[5] * (8.0 + 128)
     if name == "b200sr_conv1x1":
         return 2.0 * a[6] * a[7] * a[8] * a[3] * a[5], 0.0
     if name == "b200sr_conv1x1_wgrad":
@@ -209,7 +242,9 @@ def call(name: str, *args):
         _profile.append((name, e0, e1) + _cost(name, args))
     else:
         rc = fn(*args)
-    LAUNCH_COUNTER["n"] += 1
+    LAUNCH_COUNTER["n"] += _KERNELS_PER_CALL.get(name, 1)
+    if name in _PLAIN_VALUE:
+        return rc
     if rc != 0:
         raise B200SRError(f"{name} failed (code {rc}): {last_error()}")
 

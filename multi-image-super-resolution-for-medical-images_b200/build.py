@@ -11,7 +11,9 @@ CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libb200sr.so")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared",
-              "-Xcompiler", "-fPIC",]
+              "-Xcompiler", "-fPIC",
+              # use the process's libcudart (torch loads it) instead of embedding a second, static runtime in the library
+              "-cudart", "shared"]
 
 
 def _sources():

@@ -262,12 +262,9 @@ int run_igemm(int a_mode, const void* a, int a_stride, int a_coff, int Ca, int n
     args.col_scale = col_scale;
     args.col_shift = col_shift;
     args.stats = stats;
-    {
-        const char* dbg = getenv("B200SR_DEBUG_STAGE");
-        args.debug_stage = dbg ? atoi(dbg) : 0;
-    }
     const long long grid = static_cast<long long>(B) * args.tiles_hw * args.n_tiles;
     B2_CHECK_ARG(grid < (1ll << 31));
+    args.stats_slots = (stats != nullptr && stats_replicas >= static_cast<long long>(B) * args.tiles_hw) ? 1 : 0;
     switch (block_n) {
         case 64:
             return launch_igemm_t<64, 4>(ma, mb, args, static_cast<int>(grid), st);
@@ -391,7 +388,6 @@ int run_conv3(int mode, const void* a, int a_stride, int a_coff, int Ca, const v
     args.mask = static_cast<const __nv_bfloat16*>(mask);
     args.mask_pix_stride = mask_stride;
     args.mask_c_off = mask_coff;
-    args.epi_debug = getenv("B200SR_EPI_DEBUG") ? atoi(getenv("B200SR_EPI_DEBUG")) : 0;
     {
         const int nh = block_n / (block_n < 128 ? block_n : 128);
         const int slots = taps * args.cin_chunks * nh;
@@ -413,6 +409,8 @@ int run_conv3(int mode, const void* a, int a_stride, int a_coff, int Ca, const v
     grid -= grid % args.n_tiles;
     if (grid < args.n_tiles) grid = args.n_tiles;
     if (grid > args.num_tiles) grid = args.num_tiles;
+    // deterministic statistics when the caller provides one slot per CTA of a column block (see Conv3Args::stats_slots)
+    args.stats_slots = (stats != nullptr && stats_replicas >= grid / args.n_tiles) ? 1 : 0;
     if (mode == 0 && mask != nullptr) return dispatch_conv3<4>(block_n, ma, mb, mo, args, grid, st);
     if (mode == 0) return dispatch_conv3<0>(block_n, ma, mb, mo, args, grid, st);
     if (mode == 1) return dispatch_conv3<1>(block_n, ma, mb, mo, args, grid, st);
@@ -423,8 +421,10 @@ int run_conv3(int mode, const void* a, int a_stride, int a_coff, int Ca, const v
 // ---------------------------------------------------------------------------------------------
 // wgrad launch
 // ---------------------------------------------------------------------------------------------
+// max_splits > 0: deterministic mode (partials of split s at args.out + s * args.split_stride), at most max_splits splits
 template <int N_TILE, int STAGES>
-int launch_wgrad_t(const CUtensorMap& mt, const CUtensorMap& mp, WGradArgs& args, cudaStream_t st) {
+int launch_wgrad_t(const CUtensorMap& mt, const CUtensorMap& mp, WGradArgs& args, cudaStream_t st, int max_splits = 0,
+                   int* splits_out = nullptr) {
     constexpr int smem = wg_smem_bytes<N_TILE, STAGES>();
     static bool configured = false;
     if (!configured) {
@@ -441,8 +441,10 @@ int launch_wgrad_t(const CUtensorMap& mt, const CUtensorMap& mp, WGradArgs& args
     if (const char* env = getenv("B200SR_WGRAD_CTAS")) target = atoi(env) > 0 ? atoi(env) : target;
     int splits = groups >= target ? 1 : (target + groups - 1) / groups;
     if (splits > args.total_chunks) splits = args.total_chunks;
+    if (max_splits > 0 && splits > max_splits) splits = max_splits;
     args.chunks_per_cta = (args.total_chunks + splits - 1) / splits;
     splits = (args.total_chunks + args.chunks_per_cta - 1) / args.chunks_per_cta;
+    if (splits_out != nullptr) *splits_out = splits;
     dim3 grid(groups_x, groups_y, splits);
     wgrad_kernel<N_TILE, STAGES><<<grid, WG_THREADS, smem, st>>>(mt, mp, args);
     return check_launch("wgrad_kernel");
@@ -450,7 +452,8 @@ int launch_wgrad_t(const CUtensorMap& mt, const CUtensorMap& mp, WGradArgs& args
 
 // t_mode 0: T = (B,H,W,Ct) slot, taps in {1,9}; t_mode 1: T = (B,2H,2W,Ct) slot gathered (4 taps). P = (B,H,W,Cp).
 int run_wgrad(int t_mode, const void* t, int t_stride, int t_coff, int Ct, int num_taps, const void* p, int p_stride,
-              int p_coff, int Cp, int B, int H, int W, float* G, cudaStream_t st) {
+              int p_coff, int Cp, int B, int H, int W, float* G, cudaStream_t st, long long ws_floats = 0,
+              int* splits_out = nullptr) {
     B2_CHECK_ARG(t != nullptr && p != nullptr && G != nullptr);
     B2_CHECK_ARG(B > 0 && H > 0 && W > 0 && H % 2 == 0 && W % 16 == 0);
     B2_CHECK_ARG(Ct % 64 == 0 && Cp % 64 == 0);
@@ -478,16 +481,24 @@ int run_wgrad(int t_mode, const void* t, int t_stride, int t_coff, int Ct, int n
     args.total_atoms = num_taps * (Ct / 64);
     args.n_total = Cp;
     args.out = G;
-    if (Cp % 256 == 0) return launch_wgrad_t<256, 6>(mt, mp, args, st);
-    if (Cp % 128 == 0) return launch_wgrad_t<128, 5>(mt, mp, args, st);
-    return launch_wgrad_t<64, 3>(mt, mp, args, st);
+    args.split_stride = 0;
+    int max_splits = 0;
+    if (ws_floats > 0) {  // deterministic mode: G is a workspace of per-split partials
+        args.split_stride = static_cast<long long>(num_taps) * Ct * Cp;
+        max_splits = static_cast<int>(ws_floats / args.split_stride < 4096 ? ws_floats / args.split_stride : 4096);
+        B2_CHECK_ARG(max_splits >= 1);
+    }
+    if (Cp % 256 == 0) return launch_wgrad_t<256, 6>(mt, mp, args, st, max_splits, splits_out);
+    if (Cp % 128 == 0) return launch_wgrad_t<128, 5>(mt, mp, args, st, max_splits, splits_out);
+    return launch_wgrad_t<64, 3>(mt, mp, args, st, max_splits, splits_out);
 }
 
 // ---------------------------------------------------------------------------------------------
 // second-generation conv3x3 wgrad launch
 // ---------------------------------------------------------------------------------------------
 template <int N_TILE, int MODE_B>
-int launch_wgrad3_t(const CUtensorMap& mx, const CUtensorMap& mz, WG3Args& args, int jobs, cudaStream_t st) {
+int launch_wgrad3_t(const CUtensorMap& mx, const CUtensorMap& mz, WG3Args& args, int jobs, cudaStream_t st,
+                    int ws_max_splits, int* splits_out) {
     using Cfg = WG3Cfg<N_TILE, MODE_B>;
     static bool configured = false;
     if (!configured) {
@@ -502,7 +513,8 @@ int launch_wgrad3_t(const CUtensorMap& mx, const CUtensorMap& mz, WG3Args& args,
     double best_score = -1.0;
     // up to two waves' worth of splits: a single-job layer (Cin = Cout = 64) must still be able to fill every SM
     const int split_cap = 2 * sms > 64 ? 2 * sms : 64;
-    const int max_splits = args.total_chunks < split_cap ? args.total_chunks : split_cap;
+    int max_splits = args.total_chunks < split_cap ? args.total_chunks : split_cap;
+    if (ws_max_splits > 0 && max_splits > ws_max_splits) max_splits = ws_max_splits;  // partial workspace capacity
     for (int s = 1; s <= max_splits; ++s) {
         const int per = (args.total_chunks + s - 1) / s;
         const int real = (args.total_chunks + per - 1) / per;
@@ -520,6 +532,8 @@ int launch_wgrad3_t(const CUtensorMap& mx, const CUtensorMap& mz, WG3Args& args,
     if (const char* env = getenv("B200SR_WGRAD_SPLITS")) best = atoi(env) > 0 ? atoi(env) : best;
     args.chunks_per_cta = (args.total_chunks + best - 1) / best;
     const int splits = (args.total_chunks + args.chunks_per_cta - 1) / args.chunks_per_cta;
+    if (ws_max_splits > 0 && splits > ws_max_splits) return fail(B200SR_EINVAL, "wgrad3x3: split workspace too small");
+    if (splits_out != nullptr) *splits_out = splits;
     dim3 grid(jobs, splits, 1);
     wgrad3x3_kernel<N_TILE, MODE_B><<<grid, WG3_THREADS, Cfg::SMEM_BYTES, st>>>(mx, mz, args);
     return check_launch("wgrad3x3_kernel");
@@ -527,7 +541,7 @@ int launch_wgrad3_t(const CUtensorMap& mx, const CUtensorMap& mz, WG3Args& args,
 
 // returns -1 when the shape is not covered (caller falls back to the first-generation kernel)
 int run_wgrad3(const void* x, int x_stride, int x_coff, int Cin, const void* dz, int dz_stride, int dz_coff, int Cout,
-               int B, int H, int W, float* G, cudaStream_t st) {
+               int B, int H, int W, float* G, cudaStream_t st, long long ws_floats = 0, int* splits_out = nullptr) {
     if (H % 4 != 0 || W % 16 != 0) return -1;
     const bool mode_b = Cin == 64;
     if (!mode_b && Cin % 128 != 0) return -1;
@@ -551,10 +565,18 @@ int run_wgrad3(const void* x, int x_stride, int x_coff, int Cin, const void* dz,
     args.Cin = Cin;
     args.Cout = Cout;
     args.out = G;
+    args.split_stride = 0;
+    int ws_max = 0;
+    if (ws_floats > 0) {  // deterministic mode: G is a workspace of per-split partials
+        args.split_stride = 9LL * Cin * Cout;
+        const long long m = ws_floats / args.split_stride;
+        if (m < 1) return fail(B200SR_EINVAL, "wgrad3x3: split workspace too small");
+        ws_max = static_cast<int>(m < 4096 ? m : 4096);
+    }
     const int jobs = (mode_b ? 1 : 3 * args.jobs_ci) * args.jobs_co;
-    if (mode_b) return launch_wgrad3_t<64, 1>(mx, mz, args, jobs, st);
-    if (n_tile == 128) return launch_wgrad3_t<128, 0>(mx, mz, args, jobs, st);
-    return launch_wgrad3_t<64, 0>(mx, mz, args, jobs, st);
+    if (mode_b) return launch_wgrad3_t<64, 1>(mx, mz, args, jobs, st, ws_max, splits_out);
+    if (n_tile == 128) return launch_wgrad3_t<128, 0>(mx, mz, args, jobs, st, ws_max, splits_out);
+    return launch_wgrad3_t<64, 0>(mx, mz, args, jobs, st, ws_max, splits_out);
 }
 
 }  // namespace
@@ -562,51 +584,7 @@ int run_wgrad3(const void* x, int x_stride, int x_coff, int Cin, const void* dz,
 // =================================================================================================
 // exported C ABI
 // =================================================================================================
-// bring-up aid: one 2-D TMA box load (no swizzle) of a [rows][64] bf16 tile, copied back to global memory
-__global__ void debug_tma_kernel(const __grid_constant__ CUtensorMap map, __nv_bfloat16* dst, int rows, int c0, int c1) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 64 * 128);
-    if (threadIdx.x == 0) {
-        mbar_init(bar, 1);
-        fence_barrier_init();
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        mbar_arrive_expect_tx(bar, rows * 128);
-        tma_load_2d(&map, bar, smem, c0, c1);
-    }
-    mbar_wait(bar, 0);
-    const __nv_bfloat16* s = reinterpret_cast<const __nv_bfloat16*>(smem);
-    for (int i = threadIdx.x; i < rows * 64; i += blockDim.x) dst[i] = s[i];
-}
-
 extern "C" {
-
-// bring-up aids (not part of the public header)
-int b200sr_debug_encode(const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides, const uint32_t* box,
-                        int swizzle, void* out128) {
-    EncodeTiledFn enc = get_encode_fn();
-    if (enc == nullptr) return fail(B200SR_ECUDA, "no encode fn");
-    cuuint64_t gd[5], gs[4];
-    cuuint32_t gb[5], es[5];
-    for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; gb[i] = box[i]; es[i] = 1; if (i + 1 < rank) gs[i] = strides[i]; }
-    CUtensorMap m;
-    CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(ptr), gd, gs, gb, es,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
-                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return fail(B200SR_ECUDA, "encode failed " + std::to_string(r));
-    std::memcpy(out128, &m, 128);
-    return 0;
-}
-
-int b200sr_debug_tma(const void* map128, void* dst, int rows, int c0, int c1, void* stream) {
-    CUtensorMap m;
-    std::memcpy(&m, map128, 128);
-    cudaFuncSetAttribute(debug_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768);
-    debug_tma_kernel<<<1, 128, 32768, static_cast<cudaStream_t>(stream)>>>(m, static_cast<__nv_bfloat16*>(dst), rows, c0, c1);
-    return check_launch("debug_tma_kernel");
-}
 
 int b200sr_version(void) { return 100; }
 
@@ -724,7 +702,7 @@ int b200sr_conv1_fwd(const float* x, const float* w, const float* col_scale, con
     const int grid = tiles < num_sms() * 2 ? tiles : num_sms() * 2;
     first_conv_mma_fwd_kernel<2><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
         src, w, 18, nullptr, col_scale, col_shift, relu, static_cast<__nv_bfloat16*>(out), stats,
-        stats_replicas > 0 ? stats_replicas : 1, H, W, tiles);
+        stats_replicas > 0 ? stats_replicas : 1, (stats != nullptr && stats_replicas >= grid) ? 1 : 0, H, W, tiles);
     return check_launch("first_conv_mma_fwd_kernel<2>");
 }
 
@@ -735,7 +713,7 @@ int b200sr_conv1_wgrad(const float* x, const void* dz, float* dw, int B, int H, 
     FirstConvSrc src{nullptr, nullptr, nullptr, x};
     const int grid = tiles < num_sms() * 2 ? tiles : num_sms() * 2;
     first_conv_mma_wgrad_kernel<2><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        src, static_cast<const __nv_bfloat16*>(dz), dw, 18, H, W, tiles);
+        src, static_cast<const __nv_bfloat16*>(dz), dw, 18, H, W, tiles, nullptr);
     return check_launch("first_conv_mma_wgrad_kernel<2>");
 }
 
@@ -751,13 +729,14 @@ int b200sr_conv1_dgrad(const void* dz, const float* w, float* dx, int B, int H, 
 
 int b200sr_bn_finalize(const float* stats, int replicas, int C, double count, const float* gamma, const float* beta,
                        const float* conv_bias, float eps, float momentum, float* scale, float* shift, float* save_mean,
-                       float* save_invstd, float* running_mean, float* running_var, void* stream) {
+                       float* save_invstd, float* running_mean, float* running_var, int64_t* num_batches_tracked,
+                       void* stream) {
     B2_CHECK_ARG(stats && gamma && beta && scale && shift && save_mean && save_invstd);
     B2_CHECK_ARG(replicas > 0 && C > 0 && count > 1.0);
     B2_CHECK_ARG((running_mean == nullptr) == (running_var == nullptr));
-    bn_finalize_kernel<<<(C + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+    bn_finalize_kernel<<<(C + 31) / 32, 256, 0, static_cast<cudaStream_t>(stream)>>>(
         stats, replicas, C, static_cast<float>(count), gamma, beta, conv_bias, eps, momentum, scale, shift, save_mean,
-        save_invstd, running_mean, running_var);
+        save_invstd, running_mean, running_var, reinterpret_cast<long long*>(num_batches_tracked));
     return check_launch("bn_finalize_kernel");
 }
 
@@ -816,6 +795,142 @@ int b200sr_bn_bwd_apply_fused(const void* dy, int dy_pix_stride, int dy_c_off, c
         shift, mean, invstd, sums, replicas, static_cast<float>(count), dgamma, dbeta, static_cast<__nv_bfloat16*>(dz),
         npix, nullptr);
     return check_launch("bn_bwd_apply_fused_kernel");
+}
+
+// ---- deterministic (bit-reproducible) variants: per-block / per-split partials + fixed-order second stage ----------
+namespace {
+int launch_reduce_unpack(const float* ws, int splits, long long split_stride, int T, int outer_total, int inner_total,
+                         int inner_dst, int inner_off, float* dst, cudaStream_t st) {
+    B2_CHECK_ARG(outer_total % PK_TILE == 0 && inner_total % PK_TILE == 0 && (T == 9 || T == 4 || T == 1));
+    int tiles = (outer_total / PK_TILE) * (inner_total / PK_TILE);
+    if (tiles > num_sms() * 8) tiles = num_sms() * 8;
+    wgrad_reduce_unpack_kernel<<<tiles, 256, 0, st>>>(ws, splits, split_stride, T, outer_total, inner_total, inner_dst,
+                                                      inner_off, dst);
+    return check_launch("wgrad_reduce_unpack_kernel");
+}
+}  // namespace
+
+int b200sr_conv3x3_wgrad_det(const void* x, int x_pix_stride, int x_c_off, int Cin, const void* dz, int dz_pix_stride,
+                             int dz_c_off, int Cout, int B, int H, int W, float* dW, int cin_total, int cin_off,
+                             float* ws, int64_t ws_floats, void* stream) {
+    B2_CHECK_ARG(x && dz && dW && ws && ws_floats > 0 && B > 0);
+    B2_CHECK_ARG(cin_total >= Cin && cin_off >= 0 && cin_off + Cin <= cin_total);
+    B2_CHECK_ARG(x_pix_stride % 8 == 0 && x_c_off % 8 == 0 && dz_pix_stride % 8 == 0 && dz_c_off % 8 == 0);
+    B2_CHECK_ARG(aligned16(x) && aligned16(dz) && aligned16(ws));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int splits = 0;
+    int rc = run_wgrad3(x, x_pix_stride, x_c_off, Cin, dz, dz_pix_stride, dz_c_off, Cout, B, H, W, ws, st, ws_floats,
+                        &splits);
+    if (rc < 0)
+        rc = run_wgrad(0, x, x_pix_stride, x_c_off, Cin, 9, dz, dz_pix_stride, dz_c_off, Cout, B, H, W, ws, st, ws_floats,
+                       &splits);
+    if (rc) return rc;
+    return launch_reduce_unpack(ws, splits, 9LL * Cin * Cout, 9, Cout, Cin, cin_total, cin_off, dW, st);
+}
+
+int b200sr_convT2x2_wgrad_det(const void* dup, int dup_pix_stride, int dup_c_off, int Cout, const void* x,
+                              int x_pix_stride, int x_c_off, int Cin, int B, int H, int W, float* dW, float* ws,
+                              int64_t ws_floats, void* stream) {
+    B2_CHECK_ARG(dW && ws && ws_floats > 0);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int splits = 0;
+    const int rc = run_wgrad(1, dup, dup_pix_stride, dup_c_off, Cout, 4, x, x_pix_stride, x_c_off, Cin, B, H, W, ws, st,
+                             ws_floats, &splits);
+    if (rc) return rc;
+    return launch_reduce_unpack(ws, splits, 4LL * Cout * Cin, 4, Cin, Cout, Cout, 0, dW, st);
+}
+
+int b200sr_conv1x1_wgrad_det(const void* x, int x_pix_stride, int x_c_off, int Cin, const void* dz, int dz_pix_stride,
+                             int dz_c_off, int Cout, int B, int H, int W, float* dW, float* ws, int64_t ws_floats,
+                             void* stream) {
+    B2_CHECK_ARG(dW && ws && ws_floats > 0);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int splits = 0;
+    const int rc = run_wgrad(0, x, x_pix_stride, x_c_off, Cin, 1, dz, dz_pix_stride, dz_c_off, Cout, B, H, W, ws, st,
+                             ws_floats, &splits);
+    if (rc) return rc;
+    return launch_reduce_unpack(ws, splits, 1LL * Cin * Cout, 1, Cout, Cin, Cin, 0, dW, st);
+}
+
+int b200sr_conv1_wgrad_det(const float* x, const void* dz, float* dw, int B, int H, int W, float* ws, int64_t ws_floats,
+                           void* stream) {
+    B2_CHECK_ARG(x != nullptr && dz != nullptr && dw != nullptr && ws != nullptr);
+    B2_CHECK_ARG(B > 0 && H % C1_TILE == 0 && W % C1_TILE == 0 && aligned16(dz));
+    const int tiles = B * (H / C1_TILE) * (W / C1_TILE);
+    FirstConvSrc src{nullptr, nullptr, nullptr, x};
+    int grid = tiles < num_sms() * 2 ? tiles : num_sms() * 2;
+    const long long cap = ws_floats / (18 * FC_COUT);
+    B2_CHECK_ARG(cap >= 1);
+    if (grid > cap) grid = static_cast<int>(cap);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    first_conv_mma_wgrad_kernel<2><<<grid, 256, 0, st>>>(src, static_cast<const __nv_bfloat16*>(dz), dw, 18, H, W, tiles,
+                                                         ws);
+    // partial [k][co] -> dw[co*18 + k]
+    reduce_partials_kernel<<<(18 * FC_COUT + 31) / 32, 256, 0, st>>>(ws, grid, 18LL * FC_COUT, 18 * FC_COUT, dw, FC_COUT,
+                                                                   18, 1, 1.f);
+    return check_launch("first_conv_mma_wgrad_kernel<2> (deterministic)");
+}
+
+/* out[i] = sum_s slots[s*slot_stride + i] (s ascending), i < n: finishes per-CTA column sums (ConvTranspose2d bias
+ * gradient from the dgrad epilogue statistics) in a fixed order. */
+int b200sr_sum_slots(const float* slots, int nslots, int64_t slot_stride, int n, float* dst, void* stream) {
+    B2_CHECK_ARG(slots && dst && nslots > 0 && n > 0 && slot_stride >= n);
+    reduce_partials_kernel<<<(n + 31) / 32, 256, 0, static_cast<cudaStream_t>(stream)>>>(slots, nslots, slot_stride, n, dst,
+                                                                                      n, 1, 0, 1.f);
+    return check_launch("reduce_partials_kernel");
+}
+
+int64_t b200sr_bn_bwd_ws_floats(int C) {
+    const int groups = C / 64 > 0 ? C / 64 : 1;
+    int slices = (num_sms() * 3) / groups;
+    if (slices < 1) slices = 1;
+    return static_cast<int64_t>(groups) * slices * 128;
+}
+
+int b200sr_bn_bwd_reduce_det(const void* dy, int dy_pix_stride, int dy_c_off, const void* z, int C, const float* scale,
+                             const float* shift, const float* mean, const float* invstd, float* sums, float* ws,
+                             int64_t ws_floats, uint32_t* counters, const void* mask_src, int64_t npix, void* stream) {
+    B2_CHECK_ARG(dy && z && scale && shift && mean && invstd && sums && ws && counters);
+    B2_CHECK_ARG(C % 64 == 0 && dy_pix_stride % 8 == 0 && dy_c_off % 8 == 0 && npix > 0);
+    B2_CHECK_ARG(aligned16(dy) && aligned16(z) && aligned16(ws) && (mask_src == nullptr || aligned16(mask_src)));
+    const int groups = C / 64;
+    long long slices = (num_sms() * 3) / groups;
+    const long long need = (npix + 32LL * BNB_UNROLL - 1) / (32LL * BNB_UNROLL);
+    if (slices > need) slices = need;
+    if (slices > ws_floats / (128LL * groups)) slices = ws_floats / (128LL * groups);
+    B2_CHECK_ARG(slices >= 1);
+    dim3 grid(static_cast<unsigned>(slices), static_cast<unsigned>(groups));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (mask_src != nullptr)
+        bn_bwd_reduce_det_kernel<true><<<grid, 256, 0, st>>>(
+            static_cast<const __nv_bfloat16*>(dy), dy_pix_stride, dy_c_off, static_cast<const __nv_bfloat16*>(z), C, scale,
+            shift, mean, invstd, sums, ws, counters, npix, static_cast<const __nv_bfloat16*>(mask_src));
+    else
+        bn_bwd_reduce_det_kernel<false><<<grid, 256, 0, st>>>(
+            static_cast<const __nv_bfloat16*>(dy), dy_pix_stride, dy_c_off, static_cast<const __nv_bfloat16*>(z), C, scale,
+            shift, mean, invstd, sums, ws, counters, npix, nullptr);
+    return check_launch("bn_bwd_reduce_det_kernel");
+}
+
+int b200sr_head_bwd_det(const float* dout, const void* act, const float* w, void* dact, float* dw, float* db,
+                        int64_t npix, float* ws, int64_t ws_floats, uint32_t* counter, void* stream) {
+    B2_CHECK_ARG(dout && act && w && dact && dw && db && ws && counter && npix > 0);
+    B2_CHECK_ARG(aligned16(act) && aligned16(dact) && aligned16(w));
+    int grid = grid_for(npix * 8, 256, num_sms() * 4);
+    if (grid > ws_floats / 72) grid = static_cast<int>(ws_floats / 72);
+    B2_CHECK_ARG(grid >= 1);
+    head_bwd_det_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        dout, static_cast<const __nv_bfloat16*>(act), w, static_cast<__nv_bfloat16*>(dact), dw, db, ws, counter, npix);
+    return check_launch("head_bwd_det_kernel");
+}
+
+int b200sr_adam_step_auto(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
+                          float eps, int32_t* step_dev, float grad_scale, void* stream) {
+    B2_CHECK_ARG(p && g && m && v && n > 0 && step_dev);
+    B2_CHECK_ARG(aligned16(p) && aligned16(g) && aligned16(m) && aligned16(v));
+    adam_flat_kernel<<<grid_for((n + 3) / 4, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        p, g, m, v, n, lr, beta1, beta2, eps, 1.f, 1.f, grad_scale, nullptr, step_dev);
+    return check_launch("adam_flat_kernel");
 }
 
 // ---- DeepCNN residual baseline -------------------------------------------------------------
@@ -954,7 +1069,7 @@ int b200sr_fd_convin_fwd(const float* x0, const float* noise, const float* coef,
     FirstConvSrc src{x0, noise, reinterpret_cast<const float2*>(coef), cond};
     const int grid = tiles < num_sms() * 2 ? tiles : num_sms() * 2;
     first_conv_mma_fwd_kernel<3><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        src, w, FD_CIN0 * 9, tb, nullptr, nullptr, 1, static_cast<__nv_bfloat16*>(out), nullptr, 1, H, W, tiles);
+        src, w, FD_CIN0 * 9, tb, nullptr, nullptr, 1, static_cast<__nv_bfloat16*>(out), nullptr, 1, 0, H, W, tiles);
     return check_launch("first_conv_mma_fwd_kernel<3>");
 }
 
@@ -966,7 +1081,7 @@ int b200sr_fd_convin_wgrad(const float* x0, const float* noise, const float* coe
     FirstConvSrc src{x0, noise, reinterpret_cast<const float2*>(coef), cond};
     const int grid = tiles < num_sms() * 2 ? tiles : num_sms() * 2;
     first_conv_mma_wgrad_kernel<3><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        src, static_cast<const __nv_bfloat16*>(dz), dw, FD_CIN0 * 9, H, W, tiles);
+        src, static_cast<const __nv_bfloat16*>(dz), dw, FD_CIN0 * 9, H, W, tiles, nullptr);
     return check_launch("first_conv_mma_wgrad_kernel<3>");
 }
 
@@ -1230,10 +1345,11 @@ int b200sr_head_bwd(const float* dout, const void* act, const float* w, void* da
     return check_launch("head_bwd_kernel");
 }
 
-int b200sr_mse_ssim(const float* pred, const float* target, float* grad, double* sums, int B, int H, int W,
-                    const float* win, int K, float cov_norm, float C1, float C2, float w_mse, float w_ssim,
-                    void* stream) {
-    B2_CHECK_ARG(pred && target && sums && win);
+namespace {
+int run_mse_ssim(const float* pred, const float* target, float* grad, double* sums, int B, int H, int W, const float* win,
+                 int K, float cov_norm, float C1, float C2, float w_mse, float w_ssim, double* partials, int64_t ws_doubles,
+                 uint32_t* counter, float* out, cudaStream_t st) {
+    B2_CHECK_ARG(pred && target && win && (sums != nullptr || partials != nullptr));
     B2_CHECK_ARG(B > 0 && K >= 1 && K <= LS_KMAX && H >= K && W >= K);
     static bool configured = false;
     if (!configured) {
@@ -1256,7 +1372,15 @@ int b200sr_mse_ssim(const float* pred, const float* target, float* grad, double*
     a.g_mse = static_cast<float>(static_cast<double>(w_mse) * 2.0 / (static_cast<double>(B) * H * W));
     a.g_ssim = static_cast<float>(-static_cast<double>(w_ssim) /
                                   (static_cast<double>(B) * (H - K + 1) * static_cast<double>(W - K + 1)));
+    a.partials = partials;
+    a.counter = counter;
+    a.out = out;
+    a.inv_n_mse = 1.0 / (static_cast<double>(B) * H * W);
+    a.inv_n_ssim = 1.0 / (static_cast<double>(B) * (H - K + 1) * static_cast<double>(W - K + 1));
+    a.w_mse = w_mse;
+    a.w_ssim = w_ssim;
     const int grid = B * ((H + LS_T - 1) / LS_T) * ((W + LS_T - 1) / LS_T);
+    if (partials != nullptr) B2_CHECK_ARG(counter != nullptr && out != nullptr && ws_doubles >= 2LL * grid);
     if ((K == 11 || K == 7) && getenv("B200SR_SSIM_GENERIC") == nullptr) {
         static bool configured_fast = false;
         if (!configured_fast) {
@@ -1269,13 +1393,29 @@ int b200sr_mse_ssim(const float* pred, const float* target, float* grad, double*
             configured_fast = true;
         }
         if (K == 11)
-            mse_ssim_fast_kernel<11><<<grid, 256, LsFast<11>::SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(a);
+            mse_ssim_fast_kernel<11><<<grid, 256, LsFast<11>::SMEM_BYTES, st>>>(a);
         else
-            mse_ssim_fast_kernel<7><<<grid, 256, LsFast<7>::SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(a);
+            mse_ssim_fast_kernel<7><<<grid, 256, LsFast<7>::SMEM_BYTES, st>>>(a);
         return check_launch("mse_ssim_fast_kernel");
     }
-    mse_ssim_kernel<<<grid, 256, LS_SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(a);
+    mse_ssim_kernel<<<grid, 256, LS_SMEM_BYTES, st>>>(a);
     return check_launch("mse_ssim_kernel");
+}
+}  // namespace
+
+int b200sr_mse_ssim(const float* pred, const float* target, float* grad, double* sums, int B, int H, int W,
+                    const float* win, int K, float cov_norm, float C1, float C2, float w_mse, float w_ssim,
+                    void* stream) {
+    return run_mse_ssim(pred, target, grad, sums, B, H, W, win, K, cov_norm, C1, C2, w_mse, w_ssim, nullptr, 0, nullptr,
+                        nullptr, static_cast<cudaStream_t>(stream));
+}
+
+int b200sr_mse_ssim_det(const float* pred, const float* target, float* grad, float* out3, int B, int H, int W,
+                        const float* win, int K, float cov_norm, float C1, float C2, float w_mse, float w_ssim,
+                        double* ws, int64_t ws_doubles, uint32_t* counter, void* stream) {
+    B2_CHECK_ARG(ws != nullptr && out3 != nullptr && counter != nullptr);
+    return run_mse_ssim(pred, target, grad, nullptr, B, H, W, win, K, cov_norm, C1, C2, w_mse, w_ssim, ws, ws_doubles,
+                        counter, out3, static_cast<cudaStream_t>(stream));
 }
 
 int b200sr_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
@@ -1286,7 +1426,7 @@ int b200sr_adam_step(float* p, const float* g, float* m, float* v, int64_t n, fl
     const double bc2 = 1.0 - pow(static_cast<double>(beta2), static_cast<double>(step));
     adam_flat_kernel<<<grid_for((n + 3) / 4, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         p, g, m, v, n, lr, beta1, beta2, eps, static_cast<float>(bc1), static_cast<float>(sqrt(bc2)), grad_scale,
-        nullptr);
+        nullptr, nullptr);
     return check_launch("adam_flat_kernel");
 }
 
@@ -1295,7 +1435,7 @@ int b200sr_adam_step_dev(float* p, const float* g, float* m, float* v, int64_t n
     B2_CHECK_ARG(p && g && m && v && n > 0 && bias_corr);
     B2_CHECK_ARG(aligned16(p) && aligned16(g) && aligned16(m) && aligned16(v));
     adam_flat_kernel<<<grid_for((n + 3) / 4, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        p, g, m, v, n, lr, beta1, beta2, eps, 1.f, 1.f, grad_scale, bias_corr);
+        p, g, m, v, n, lr, beta1, beta2, eps, 1.f, 1.f, grad_scale, bias_corr, nullptr);
     return check_launch("adam_flat_kernel");
 }
 

@@ -33,7 +33,9 @@ struct Conv3Args {
     int out_c_off;
     int stats_replicas;
     int cout_t;        // MODE 1: channels per (i,j) sub-pixel (n_total = 4 * cout_t); modulus of the affine vectors
-    int epi_debug;     // bring-up/perf experiments (B200SR_EPI_DEBUG bit mask); 0 in production
+    int stats_slots;   // > 0: deterministic statistics — CTA (blockIdx.x / n_tiles) STORES its partial sums into its own
+                       // slot of stats[stats_replicas][2][n_total] (no atomics, no pre-zeroing; unused slots are zeroed
+                       // here); 0: legacy mode, partial sums are atomically ADDED into slot blockIdx.x % stats_replicas
     int b_resident;    // the CTA's whole weight block fits the B ring: load it once, keep it for all tiles
     int sa;            // activation ring depth (3 .. C3_SA_MAX): ring bytes the resident weights do not need go to A
                        // stages — at 256^2 the kernel is bound by TMA latency x bytes in flight, not by the MMAs
@@ -168,10 +170,7 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_kernel(const __grid_con
                     for (int dw = 0; dw < NG; ++dw) {
                         mbar_wait(&a_empty[sa], pa ^ 1);
                         mbar_arrive_expect_tx(&a_full[sa], A_BYTES);
-                        if (MODE == 0 && (args.epi_debug & 128))
-                            tma_load_4d_hint(&map_a, &a_full[sa], ring_a + sa * C3_A_SLOT, c * 64, w0 + dw - 1, h0 - 1, img,
-                                             l2_policy_evict_last());
-                        else if (MODE == 0)
+                        if (MODE == 0)
                             tma_load_4d(&map_a, &a_full[sa], ring_a + sa * C3_A_SLOT, c * 64, w0 + dw - 1, h0 - 1, img);
                         else if (MODE == 1 || MODE == 3)
                             tma_load_4d(&map_a, &a_full[sa], ring_a + sa * C3_A_SLOT, c * 64, w0, h0, img);
@@ -312,17 +311,12 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_kernel(const __grid_con
                         for (int i = 0; i < 4; ++i) mraw[i] = __ldg(mp + i);
                     }
                     uint32_t raw[32];
-                    if (args.epi_debug & 64) {
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) raw[i] = i + lane;
-                    } else {
-                        tmem_ld32(t_addr + chunk * 32, raw);
-                        tmem_ld_wait();
-                    }
+                    tmem_ld32(t_addr + chunk * 32, raw);
+                    tmem_ld_wait();
                     float v[32];
 #pragma unroll
                     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
-                    if (affine && !(args.epi_debug & 16)) {
+                    if (affine) {
 #pragma unroll
                         for (int i = 0; i < 32; i += 4) {
                             const float4 sc = *reinterpret_cast<const float4*>(s_scale + chunk * 32 + i);
@@ -354,7 +348,6 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_kernel(const __grid_con
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         const uint32_t j = static_cast<uint32_t>(half * 4 + i);
-                        if (args.epi_debug & 32) continue;
                         *reinterpret_cast<uint4*>(stage + row_off + ((j ^ row_xor) << 4)) =
                             make_uint4(packed[4 * i], packed[4 * i + 1], packed[4 * i + 2], packed[4 * i + 3]);
                     }
@@ -376,17 +369,15 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_kernel(const __grid_con
                 }
                 // make the generic-proxy writes visible to the TMA engine, make sure the OTHER buffer's previous
                 // store has finished reading shared memory (it is the next one to be overwritten), then store
-                if (!(args.epi_debug & 1)) fence_proxy_async_smem();
-                if (Cfg::NBUF == 2 && issuer && !(args.epi_debug & 4)) tma_store_wait_read<0>();
-                if (!(args.epi_debug & 8)) named_bar_sync(1, 128);
-                if (issuer && !(args.epi_debug & 2)) {
+                fence_proxy_async_smem();
+                if (Cfg::NBUF == 2 && issuer) tma_store_wait_read<0>();
+                named_bar_sync(1, 128);
+                if (issuer) {
                     const int col0 = n0 + grp * 64;
                     if (MODE == 1) {
                         const int ij = col0 / args.cout_t;
                         const int co = col0 - ij * args.cout_t;
                         tma_store_5d(&map_out, stage, co, ij & 1, w0, ij >> 1, img * args.H + h0);
-                    } else if (args.epi_debug & 256) {
-                        tma_store_4d_hint(&map_out, stage, col0, w0, h0, img, l2_policy_evict_first());
                     } else {
                         tma_store_4d(&map_out, stage, col0, w0, h0, img);
                     }
@@ -405,11 +396,35 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_kernel(const __grid_con
         if (issuer) tma_store_wait<0>();  // global writes complete before the CTA retires
         if (do_stats && blockIdx.x < args.num_tiles) {
             // the tile schedule keeps this CTA on one column block (gridDim.x % n_tiles == 0, or one tile per CTA)
-            float* dst = args.stats + static_cast<size_t>(blockIdx.x % args.stats_replicas) * 2 * args.n_total + n0_last;
+            if (args.stats_slots > 0) {
+                // deterministic: this CTA owns slot (blockIdx.x / n_tiles) of its column block — plain stores; the slots no
+                // CTA owns are zeroed by the CTA that owns slot (s mod used), so bn_finalize can sum all of them in order
+                const int used = static_cast<int>(gridDim.x) / args.n_tiles;
+                const int mine = static_cast<int>(blockIdx.x) / args.n_tiles;
+                float* s_red = reinterpret_cast<float*>(out_stage);  // staging tile is dead (stores drained above)
+                named_bar_sync(1, 128);
 #pragma unroll
-            for (int chunk = 0; chunk < BLOCK_N / 32; ++chunk) {
-                atomicAdd(dst + chunk * 32 + lane, st_sum[chunk]);
-                atomicAdd(dst + args.n_total + chunk * 32 + lane, st_sq[chunk]);
+                for (int chunk = 0; chunk < BLOCK_N / 32; ++chunk) {
+                    s_red[(q * 2 + 0) * BLOCK_N + chunk * 32 + lane] = st_sum[chunk];
+                    s_red[(q * 2 + 1) * BLOCK_N + chunk * 32 + lane] = st_sq[chunk];
+                }
+                named_bar_sync(1, 128);
+                for (int i = threadIdx.x - 128; i < 2 * BLOCK_N; i += 128) {
+                    const int which = i / BLOCK_N, col = i - which * BLOCK_N;
+                    float acc = 0.f;
+#pragma unroll
+                    for (int w4 = 0; w4 < 4; ++w4) acc += s_red[(w4 * 2 + which) * BLOCK_N + col];
+                    args.stats[(static_cast<size_t>(mine) * 2 + which) * args.n_total + n0_last + col] = acc;
+                    for (int s2 = mine + used; s2 < args.stats_replicas; s2 += used)
+                        args.stats[(static_cast<size_t>(s2) * 2 + which) * args.n_total + n0_last + col] = 0.f;
+                }
+            } else {
+                float* dst = args.stats + static_cast<size_t>(blockIdx.x % args.stats_replicas) * 2 * args.n_total + n0_last;
+#pragma unroll
+                for (int chunk = 0; chunk < BLOCK_N / 32; ++chunk) {
+                    atomicAdd(dst + chunk * 32 + lane, st_sum[chunk]);
+                    atomicAdd(dst + args.n_total + chunk * 32 + lane, st_sq[chunk]);
+                }
             }
         }
     }

@@ -208,6 +208,100 @@ __global__ void __launch_bounds__(256) pack_jobs_kernel(const PackJob* __restric
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Deterministic cross-block reductions. Every block STORES its partial result into its own slot; the block that
+// draws the last ticket sums the slots in slot order. The summation order is a function of the launch geometry
+// only (never of the scheduling), so two runs give the same bits; the counter is reset by the last block, so the
+// same (zero-initialised) counter serves every later launch on the stream and CUDA-graph replays.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool last_block_ticket(unsigned* counter, unsigned total) {
+    __shared__ int s_last_flag;
+    __threadfence();  // this thread's partial stores are visible device-wide before the ticket is drawn
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned t = atomicAdd(counter, 1u);
+        s_last_flag = (t == total - 1u) ? 1 : 0;
+        if (s_last_flag) *counter = 0u;
+    }
+    __syncthreads();
+    const bool last = s_last_flag != 0;
+    if (last) __threadfence();
+    return last;
+}
+
+// out[map(i)] = sum_{p < nparts} partials[p * part_stride + i], p ascending, i < n.
+// map(i) = (i % inner) * stride_mod + (i / inner) * stride_div   (identity: inner = n, stride_mod = 1).
+// Block = 32 outputs x 8 part-lanes; lane l sums parts l, l+8, ... then the 8 lanes are combined in lane order.
+__global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __restrict__ partials, int nparts,
+                                                              long long part_stride, int n, float* __restrict__ out,
+                                                              int inner, long long stride_mod, long long stride_div,
+                                                              float scale) {
+    __shared__ float s_p[8][33];
+    const int col = threadIdx.x & 31, pl = threadIdx.x >> 5;
+    const int i = blockIdx.x * 32 + col;
+    float acc = 0.f;
+    if (i < n) {
+#pragma unroll 8
+        for (int p = pl; p < nparts; p += 8) acc += __ldcg(partials + static_cast<long long>(p) * part_stride + i);
+    }
+    s_p[pl][col] = acc;
+    __syncthreads();
+    if (pl == 0 && i < n) {
+        float t = 0.f;
+#pragma unroll
+        for (int l = 0; l < 8; ++l) t += s_p[l][col];
+        out[(i % inner) * stride_mod + (i / inner) * stride_div] = t * scale;
+    }
+}
+
+// Second stage of a split-K weight gradient: sums the per-split partials G_s[t][inner][outer] (s ascending) and writes
+// the PyTorch parameter layout dst[outer][inner_off + inner][t] (row length inner_dst) — the fixed-order replacement of
+// red.global.add + unpack. T = 9 (Conv2d 3x3: outer = Cout, inner = Cin), 4 (ConvTranspose2d: outer = Cin, inner = Cout)
+// or 1 (Conv2d 1x1). One 32 x 32 x T tile per block iteration; reads and writes are coalesced runs.
+__global__ void __launch_bounds__(256) wgrad_reduce_unpack_kernel(const float* __restrict__ parts, int nsplits,
+                                                                  long long split_stride, int T, int outer_total,
+                                                                  int inner_total, int inner_dst, int inner_off,
+                                                                  float* __restrict__ dst) {
+    __shared__ float tile[PK_TILE][PK_TILE * 9 + 1];
+    const int tiles_in = inner_total / PK_TILE;
+    const int num_tiles = (outer_total / PK_TILE) * tiles_in;
+    const int row = PK_TILE * T;
+    const int tid = threadIdx.x;
+    const int per_thread = (PK_TILE * row) / 256;  // 4 * T
+    for (int tl = blockIdx.x; tl < num_tiles; tl += gridDim.x) {
+        const int o0 = (tl / tiles_in) * PK_TILE, i0 = (tl % tiles_in) * PK_TILE;
+        float acc[36];
+#pragma unroll
+        for (int j = 0; j < 36; ++j) acc[j] = 0.f;
+        for (int sp = 0; sp < nsplits; ++sp) {
+            const float* src = parts + static_cast<long long>(sp) * split_stride;
+#pragma unroll
+            for (int j = 0; j < 36; ++j) {
+                if (j < per_thread) {
+                    const int idx = tid + 256 * j;
+                    const int o = idx % PK_TILE, i = (idx / PK_TILE) % PK_TILE, t = idx / (PK_TILE * PK_TILE);
+                    acc[j] += __ldcs(src + (static_cast<long long>(t) * inner_total + i0 + i) * outer_total + o0 + o);
+                }
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < 36; ++j) {
+            if (j < per_thread) {
+                const int idx = tid + 256 * j;
+                const int o = idx % PK_TILE, i = (idx / PK_TILE) % PK_TILE, t = idx / (PK_TILE * PK_TILE);
+                tile[o][i * T + t] = acc[j];
+            }
+        }
+        __syncthreads();
+        for (int idx = tid; idx < PK_TILE * row; idx += 256) {
+            const int o = idx / row, r = idx - o * row;
+            dst[(static_cast<long long>(o0 + o) * inner_dst + inner_off + i0) * T + r] = tile[o][r];
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // first layer Conv2d(2 -> 64, 3x3, p1): forward and weight gradient live in firstconv.cuh (tensor-core MMA straight
 // from the fp32 NCHW input); only the data gradient below stays on CUDA cores.
@@ -279,18 +373,38 @@ __global__ void __launch_bounds__(256) conv1_direct_dgrad_kernel(const __nv_bflo
 // unbiased var into running_var), unet_model.py:28,31. The conv bias is not added to the stored conv
 // output (BN cancels it), so it is added back here for running_mean only.
 // ------------------------------------------------------------------------------------------------
-__global__ void bn_finalize_kernel(const float* __restrict__ stats, int replicas, int C, float count,
-                                   const float* __restrict__ gamma, const float* __restrict__ beta,
-                                   const float* __restrict__ conv_bias, float eps, float momentum,
-                                   float* __restrict__ scale, float* __restrict__ shift, float* __restrict__ mean_out,
-                                   float* __restrict__ invstd_out, float* __restrict__ running_mean,
-                                   float* __restrict__ running_var) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C) return;
+__global__ void __launch_bounds__(256) bn_finalize_kernel(const float* __restrict__ stats, int replicas, int C,
+                                                          float count, const float* __restrict__ gamma,
+                                                          const float* __restrict__ beta,
+                                                          const float* __restrict__ conv_bias, float eps, float momentum,
+                                                          float* __restrict__ scale, float* __restrict__ shift,
+                                                          float* __restrict__ mean_out, float* __restrict__ invstd_out,
+                                                          float* __restrict__ running_mean,
+                                                          float* __restrict__ running_var,
+                                                          long long* __restrict__ num_batches_tracked) {
+    // block = 32 channels x 8 slot-lanes; lane l sums slots l, l+8, ... (double), lanes are combined in lane order:
+    // the result depends on the slot contents only, not on which CTA wrote them when
+    __shared__ double s_s[8][33], s_q[8][33];
+    const int col = threadIdx.x & 31, sl = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + col;
     double s = 0.0, q = 0.0;
-    for (int r = 0; r < replicas; ++r) {
-        s += stats[(static_cast<size_t>(r) * 2) * C + c];
-        q += stats[(static_cast<size_t>(r) * 2 + 1) * C + c];
+    if (c < C) {
+#pragma unroll 4
+        for (int r = sl; r < replicas; r += 8) {
+            s += stats[(static_cast<size_t>(r) * 2) * C + c];
+            q += stats[(static_cast<size_t>(r) * 2 + 1) * C + c];
+        }
+    }
+    s_s[sl][col] = s;
+    s_q[sl][col] = q;
+    __syncthreads();
+    if (blockIdx.x == 0 && threadIdx.x == 0 && num_batches_tracked != nullptr) *num_batches_tracked += 1;
+    if (sl != 0 || c >= C) return;
+    s = q = 0.0;
+#pragma unroll
+    for (int l = 0; l < 8; ++l) {
+        s += s_s[l][col];
+        q += s_q[l][col];
     }
     const double inv_count = 1.0 / static_cast<double>(count);
     const double mean = s * inv_count;
@@ -682,6 +796,99 @@ __global__ void __launch_bounds__(256, 3) bn_bwd_reduce_fast_kernel(const __nv_b
     }
 }
 
+// Deterministic BatchNorm+ReLU backward reduction (pass 1). grid = (slices, C/64): a block owns 64 channels (8 threads
+// x 8 channels per pixel) and every `slices`-th group of 32 pixels; its 128 partial sums go to its own slot of `ws`; the
+// last block of a channel group (ticket counter per group) sums that group's slots in slice order and writes the final
+//   sums[0][c] = sum g,  sums[1][c] = invstd[c] * sum g*(z - mean)        (g = dY * [scale*z + shift > 0], or the stored mask)
+// No atomics on data, no pre-zeroing: bit-reproducible. counters: C/64 zero-initialised unsigned, self-resetting.
+template <bool MASKED>
+__global__ void __launch_bounds__(256, 3) bn_bwd_reduce_det_kernel(
+    const __nv_bfloat16* __restrict__ dy, int dy_stride, int dy_coff, const __nv_bfloat16* __restrict__ z, int C,
+    const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ mean,
+    const float* __restrict__ invstd, float* __restrict__ sums /* [2][C] */, float* __restrict__ ws,
+    unsigned* __restrict__ counters, long long npix, const __nv_bfloat16* __restrict__ mask_src) {
+    const int slices = gridDim.x, slice = blockIdx.x, group = blockIdx.y;
+    const int tx = threadIdx.x & 7, ty = threadIdx.x >> 3;  // 8 channel vectors x 32 pixel lanes
+    const int c = group * 64 + tx * 8;
+    const F8 sc = ld_f32x8(scale + c), sh = ld_f32x8(shift + c), mu = ld_f32x8(mean + c);
+    float s1[8], s2[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s1[k] = s2[k] = 0.f;
+    const long long step = static_cast<long long>(slices) * 32;
+    for (long long p0 = static_cast<long long>(slice) * 32 + ty; p0 < npix; p0 += step * BNB_UNROLL) {
+        uint4 g[BNB_UNROLL], zz[BNB_UNROLL], mm[MASKED ? BNB_UNROLL : 1];
+#pragma unroll
+        for (int u = 0; u < BNB_UNROLL; ++u) {
+            const long long p = p0 + u * step;
+            if (p < npix) {
+                g[u] = ld_stream(dy + p * dy_stride + dy_coff + c);
+                zz[u] = ld_stream(z + p * C + c);
+                if (MASKED) mm[MASKED ? u : 0] = ld_stream(mask_src + p * C + c);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < BNB_UNROLL; ++u) {
+            if (p0 + u * step < npix) {
+                const F8 gf = unpack8(g[u]), zf = unpack8(zz[u]);
+                F8 mf;
+                if (MASKED) {
+                    mf = unpack8(mm[MASKED ? u : 0]);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) mf.v[k] = fmaf(zf.v[k], sc.v[k], sh.v[k]);
+                }
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const float gm = mf.v[k] > 0.f ? gf.v[k] : 0.f;
+                    s1[k] += gm;
+                    s2[k] = fmaf(gm, zf.v[k] - mu.v[k], s2[k]);
+                }
+            }
+        }
+    }
+    // in-block: pixel lanes combined in lane order
+    __shared__ float red[2][32][65];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        red[0][ty][tx * 8 + k] = s1[k];
+        red[1][ty][tx * 8 + k] = s2[k];
+    }
+    __syncthreads();
+    float* slot = ws + (static_cast<size_t>(group) * slices + slice) * 128;
+    if (threadIdx.x < 128) {
+        const int which = threadIdx.x >> 6, ch = threadIdx.x & 63;
+        float acc = 0.f;
+#pragma unroll 8
+        for (int r = 0; r < 32; ++r) acc += red[which][r][ch];
+        slot[threadIdx.x] = acc;
+    }
+    if (!last_block_ticket(counters + group, static_cast<unsigned>(slices))) return;
+    // last block of this channel group: 32 float4 columns x 8 slice-lanes, lanes combined in lane order
+    __shared__ float4 s_t[8][32];
+    const int col4 = threadIdx.x & 31, sl = threadIdx.x >> 5;
+    const float4* base = reinterpret_cast<const float4*>(ws + static_cast<size_t>(group) * slices * 128) + col4;
+    float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 8
+    for (int r = sl; r < slices; r += 8) {
+        const float4 v = __ldcg(base + static_cast<size_t>(r) * 32);
+        a4.x += v.x;
+        a4.y += v.y;
+        a4.z += v.z;
+        a4.w += v.w;
+    }
+    s_t[sl][col4] = a4;
+    __syncthreads();
+    if (threadIdx.x < 128) {
+        const int which = threadIdx.x >> 6, ch = threadIdx.x & 63;
+        float acc = 0.f;
+#pragma unroll
+        for (int l = 0; l < 8; ++l) acc += reinterpret_cast<const float*>(&s_t[l][0])[threadIdx.x];
+        if (which == 1) acc *= invstd[group * 64 + ch];
+        sums[static_cast<size_t>(which) * C + group * 64 + ch] = acc;
+    }
+}
+
+
 __global__ void __launch_bounds__(256, 3) bn_bwd_apply_fast_kernel(const __nv_bfloat16* __restrict__ dy, int dy_stride,
                                                                 int dy_coff, const __nv_bfloat16* __restrict__ z, int C,
                                                                 const float* __restrict__ scale,
@@ -977,6 +1184,74 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__
     if (threadIdx.x == 0) atomicAdd(db, s_b);
 }
 
+// Deterministic variant: block b STORES its 65 partials (dw[64], db) into ws[b][65+]; the last block (ticket) sums the
+// slots in block order and WRITES dw / db (no pre-zeroing, no atomics on data). counter: one zero-initialised unsigned.
+__global__ void __launch_bounds__(256) head_bwd_det_kernel(const float* __restrict__ dout,
+                                                           const __nv_bfloat16* __restrict__ act,
+                                                           const float* __restrict__ w, __nv_bfloat16* __restrict__ dact,
+                                                           float* __restrict__ dw, float* __restrict__ db,
+                                                           float* __restrict__ ws, unsigned* __restrict__ counter,
+                                                           long long npix) {
+    const int sub = threadIdx.x & 7;
+    const F8 wv = ld_f32x8(w + sub * 8);
+    float accw[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) accw[k] = 0.f;
+    float accb = 0.f;
+    for (long long p = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 3; p < npix;
+         p += (static_cast<long long>(gridDim.x) * blockDim.x) >> 3) {
+        const float g = dout[p];
+        const F8 a = ld_bf16x8(act + p * 64 + sub * 8);
+        F8 o;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            o.v[k] = g * wv.v[k];
+            accw[k] = fmaf(g, a.v[k], accw[k]);
+        }
+        st_bf16x8(dact + p * 64 + sub * 8, o);
+        if (sub == 0) accb += g;
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        accw[k] += __shfl_xor_sync(0xffffffffu, accw[k], 8);
+        accw[k] += __shfl_xor_sync(0xffffffffu, accw[k], 16);
+    }
+    accb += __shfl_xor_sync(0xffffffffu, accb, 8);
+    accb += __shfl_xor_sync(0xffffffffu, accb, 16);
+    __shared__ float s_w[8][66];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane < 8) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s_w[warp][sub * 8 + k] = accw[k];
+        if (sub == 0) s_w[warp][64] = accb;
+    }
+    __syncthreads();
+    float* slot = ws + static_cast<size_t>(blockIdx.x) * 72;
+    if (threadIdx.x < 65) {
+        float acc = 0.f;
+#pragma unroll
+        for (int w8 = 0; w8 < 8; ++w8) acc += s_w[w8][threadIdx.x];
+        slot[threadIdx.x] = acc;
+    }
+    if (!last_block_ticket(counter, gridDim.x)) return;
+    // 65 outputs x 3 slot-lanes (195 threads), combined in lane order
+    __shared__ float s_t[3][66];
+    const int o = threadIdx.x % 65, sl = threadIdx.x / 65;
+    if (sl < 3) {
+        float acc = 0.f;
+#pragma unroll 16
+        for (int r = sl; r < static_cast<int>(gridDim.x); r += 3) acc += __ldcg(ws + static_cast<size_t>(r) * 72 + o);
+        s_t[sl][o] = acc;
+    }
+    __syncthreads();
+    if (threadIdx.x < 65) {
+        const float t = s_t[0][threadIdx.x] + s_t[1][threadIdx.x] + s_t[2][threadIdx.x];
+        if (threadIdx.x < 64) dw[threadIdx.x] = t;
+        else *db = t;
+    }
+}
+
+
 // ------------------------------------------------------------------------------------------------
 // layout casts at the boundary (used by the per-op tests and by users feeding intermediate tensors)
 // ------------------------------------------------------------------------------------------------
@@ -1012,11 +1287,20 @@ __global__ void __launch_bounds__(256) adam_flat_kernel(float* __restrict__ p, c
                                                         float* __restrict__ m, float* __restrict__ v, long long n,
                                                         float lr, float beta1, float beta2, float eps,
                                                         float bias_corr1, float bias_corr2_sqrt, float grad_scale,
-                                                        const float* __restrict__ bias_corr_dev) {
+                                                        const float* __restrict__ bias_corr_dev,
+                                                        int* __restrict__ step_dev) {
     // step-dependent scalars may come from device memory so that the launch can live in a CUDA graph
     if (bias_corr_dev != nullptr) {
         bias_corr1 = bias_corr_dev[0];
         bias_corr2_sqrt = bias_corr_dev[1];
+    }
+    // step_dev = {completed steps, block ticket}: the step count lives on the device, the kernel derives the bias
+    // corrections of step t = completed + 1 itself and the last block to finish publishes t — the host never has to
+    // hand over per-step scalars, so an unsynchronised host running several steps ahead cannot skew them
+    if (step_dev != nullptr) {
+        const double t = static_cast<double>(step_dev[0] + 1);
+        bias_corr1 = static_cast<float>(1.0 - pow(static_cast<double>(beta1), t));
+        bias_corr2_sqrt = static_cast<float>(sqrt(1.0 - pow(static_cast<double>(beta2), t)));
     }
     for (long long i = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) * 4; i < n;
          i += static_cast<long long>(gridDim.x) * blockDim.x * 4) {
@@ -1047,6 +1331,17 @@ __global__ void __launch_bounds__(256) adam_flat_kernel(float* __restrict__ p, c
                 v[j] = beta2 * v[j] + (1.f - beta2) * gk * gk;
                 const float denom = sqrtf(v[j]) / bias_corr2_sqrt + eps;
                 p[j] -= (lr / bias_corr1) * (m[j] / denom);
+            }
+        }
+    }
+    if (step_dev != nullptr) {
+        __syncthreads();  // every thread of the block has read step_dev[0]
+        if (threadIdx.x == 0) {
+            const unsigned ticket = atomicAdd(reinterpret_cast<unsigned*>(step_dev + 1), 1u);
+            if (ticket == gridDim.x - 1) {  // all blocks have read the old count
+                step_dev[1] = 0;
+                __threadfence();
+                step_dev[0] += 1;
             }
         }
     }

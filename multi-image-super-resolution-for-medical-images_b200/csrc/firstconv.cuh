@@ -140,11 +140,10 @@ __global__ void __launch_bounds__(256, 2) first_conv_mma_fwd_kernel(const FirstC
                                                                     const float* __restrict__ col_scale,
                                                                     const float* __restrict__ col_shift, int relu,
                                                                     __nv_bfloat16* __restrict__ out,
-                                                                    float* __restrict__ stats, int stats_replicas, int H,
-                                                                    int W, int num_tiles) {
+                                                                    float* __restrict__ stats, int stats_replicas,
+                                                                    int stats_slots, int H, int W, int num_tiles) {
     __shared__ float s_x2[2][CIN * FC_HT * FC_HT];
     __shared__ __align__(16) __nv_bfloat16 s_out[FC_TILE * FC_TILE * FC_PITCH];
-    float (*s_stats)[FC_COUT] = reinterpret_cast<float (*)[FC_COUT]>(s_out);  // aliases the staging tile, used after the loop
     __shared__ uint2 s_blo[2 * 8 * 32];  // low halves of the weight fragments, [ks][nb][lane] (each lane reads its own)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
@@ -296,7 +295,8 @@ __global__ void __launch_bounds__(256, 2) first_conv_mma_fwd_kernel(const FirstC
         buf ^= 1;
     }
     if (stats != nullptr) {
-        // lanes with equal (lane & 7) share channels: fold the 4 of a warp, then shared atomics, one global flush
+        // lanes with equal (lane & 7) share channels: fold the 4 of a warp with shuffles, the 8 warps through shared
+        // memory in a fixed order (deterministic), one global flush per block
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
             st1[k] += __shfl_xor_sync(0xffffffffu, st1[k], 8);
@@ -305,31 +305,44 @@ __global__ void __launch_bounds__(256, 2) first_conv_mma_fwd_kernel(const FirstC
             st2[k] += __shfl_xor_sync(0xffffffffu, st2[k], 16);
         }
         __syncthreads();  // the last copy-out has finished reading the staging tile
-        if (tid < 2 * FC_COUT) (&s_stats[0][0])[tid] = 0.f;
-        __syncthreads();
+        float* s_w = reinterpret_cast<float*>(s_out);  // [8 warps][2][64]
         if (lane < 8) {
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
-                atomicAdd(&s_stats[0][lane * 8 + k], st1[k]);
-                atomicAdd(&s_stats[1][lane * 8 + k], st2[k]);
+                s_w[(warp * 2 + 0) * FC_COUT + lane * 8 + k] = st1[k];
+                s_w[(warp * 2 + 1) * FC_COUT + lane * 8 + k] = st2[k];
             }
         }
         __syncthreads();
-        float* d = stats + static_cast<size_t>(blockIdx.x % stats_replicas) * 2 * FC_COUT;
-        if (tid < 2 * FC_COUT) atomicAdd(d + tid, (&s_stats[0][0])[tid]);
+        if (tid < 2 * FC_COUT) {
+            const int which = tid / FC_COUT, c = tid % FC_COUT;
+            float acc = 0.f;
+#pragma unroll
+            for (int w8 = 0; w8 < 8; ++w8) acc += s_w[(w8 * 2 + which) * FC_COUT + c];
+            if (stats_slots > 0) {
+                // deterministic: block b STORES into its own slot; slots beyond the grid are zeroed (see conv3x3.cuh)
+                stats[static_cast<size_t>(blockIdx.x) * 2 * FC_COUT + tid] = acc;
+                for (int s2 = blockIdx.x + gridDim.x; s2 < stats_replicas; s2 += gridDim.x)
+                    stats[static_cast<size_t>(s2) * 2 * FC_COUT + tid] = 0.f;
+            } else {
+                atomicAdd(stats + static_cast<size_t>(blockIdx.x % stats_replicas) * 2 * FC_COUT + tid, acc);
+            }
+        }
     }
 }
 
 // ------------------------------------------------------------------------------------------------
 // weight gradient: dw[co*w_stride + k] += sum_pixels A[pixel][k] * dZ[pixel][co], k < 9*CIN.
 // Warp w accumulates the pixels of tile rows 2w, 2w+1 of every tile the block visits into a 32 x 64 fp32 fragment;
-// warps are combined through shared memory at the end, one global atomic per weight and block.
+// warps are combined through shared memory in a fixed order at the end. partial == nullptr: one global atomic per weight
+// and block into dw (legacy); otherwise block b STORES its [K][64] partial into partial[b] and a fixed-order second stage
+// (reduce_partials_kernel) produces dw — bit-reproducible.
 // ------------------------------------------------------------------------------------------------
 template <int CIN>
 __global__ void __launch_bounds__(256, 2) first_conv_mma_wgrad_kernel(const FirstConvSrc src,
                                                                       const __nv_bfloat16* __restrict__ dz,  // [B][H][W][64]
                                                                       float* __restrict__ dw, int w_stride, int H, int W,
-                                                                      int num_tiles) {
+                                                                      int num_tiles, float* __restrict__ partial) {
     __shared__ float s_x[CIN * FC_HT * FC_HT];
     __shared__ __align__(16) __nv_bfloat16 s_dz[FC_TILE * FC_TILE * FC_PITCH];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -391,22 +404,31 @@ __global__ void __launch_bounds__(256, 2) first_conv_mma_wgrad_kernel(const Firs
             }
         }
     }
-    // combine the 8 warps: s_acc[k][co] aliases the dz tile
+    // combine the 8 warps in warp order: s_acc[k][co] aliases the dz tile
     __syncthreads();
     float* s_acc = reinterpret_cast<float*>(s_dz);
     for (int i = tid; i < 32 * FC_COUT; i += 256) s_acc[i] = 0.f;
     __syncthreads();
+    for (int w8 = 0; w8 < 8; ++w8) {
+        if (warp == w8) {
 #pragma unroll
-    for (int mb = 0; mb < 2; ++mb)
+            for (int mb = 0; mb < 2; ++mb)
 #pragma unroll
-        for (int nb = 0; nb < 8; ++nb) {
-            const int c = nb * 8 + 2 * t;
-            atomicAdd(&s_acc[(mb * 16 + g) * FC_COUT + c], acc[mb][nb][0]);
-            atomicAdd(&s_acc[(mb * 16 + g) * FC_COUT + c + 1], acc[mb][nb][1]);
-            atomicAdd(&s_acc[(mb * 16 + g + 8) * FC_COUT + c], acc[mb][nb][2]);
-            atomicAdd(&s_acc[(mb * 16 + g + 8) * FC_COUT + c + 1], acc[mb][nb][3]);
+                for (int nb = 0; nb < 8; ++nb) {
+                    const int c = nb * 8 + 2 * t;
+                    s_acc[(mb * 16 + g) * FC_COUT + c] += acc[mb][nb][0];
+                    s_acc[(mb * 16 + g) * FC_COUT + c + 1] += acc[mb][nb][1];
+                    s_acc[(mb * 16 + g + 8) * FC_COUT + c] += acc[mb][nb][2];
+                    s_acc[(mb * 16 + g + 8) * FC_COUT + c + 1] += acc[mb][nb][3];
+                }
         }
-    __syncthreads();
+        __syncthreads();
+    }
+    if (partial != nullptr) {
+        float* dst = partial + static_cast<size_t>(blockIdx.x) * (CIN * 9 * FC_COUT);
+        for (int i = tid; i < CIN * 9 * FC_COUT; i += 256) dst[i] = s_acc[i];  // [k][co]
+        return;
+    }
     for (int i = tid; i < CIN * 9 * FC_COUT; i += 256) {
         const int k = i / FC_COUT, co = i % FC_COUT;
         atomicAdd(dw + static_cast<size_t>(co) * w_stride + k, s_acc[k * FC_COUT + co]);

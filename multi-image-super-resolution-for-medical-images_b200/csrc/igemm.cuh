@@ -37,7 +37,7 @@ struct IGemmArgs {
     int out_pix_stride;  // elements between consecutive output pixels (total channels of the buffer)
     int out_c_off;       // first channel of the slot written
     int stats_replicas;
-    int debug_stage;     // 0 = normal; 1..4 = stop early (bring-up aid, B200SR_DEBUG_STAGE)
+    int stats_slots;     // 1: deterministic — M tile t STORES into slot t (needs stats_replicas >= #M tiles), rest zeroed
     __nv_bfloat16* out;
     const float* col_scale;  // nullable
     const float* col_shift;  // nullable
@@ -58,7 +58,7 @@ __host__ __device__ constexpr int ig_stage_bytes() {
 template <int BLOCK_N, int STAGES>
 __host__ __device__ constexpr int ig_smem_bytes() {
     // operands + barriers/tmem ptr (256 B) + stats staging + 1 KB alignment slack
-    return STAGES * ig_stage_bytes<BLOCK_N>() + 256 + 2 * BLOCK_N * 4 + 1024;
+    return STAGES * ig_stage_bytes<BLOCK_N>() + 256 + 8 * BLOCK_N * 4 + 1024;
 }
 
 template <int BLOCK_N, int STAGES>
@@ -74,7 +74,7 @@ __global__ void __launch_bounds__(IG_THREADS) igemm_kernel(const __grid_constant
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* tmem_full_bar = empty_bar + STAGES;
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
-    float* s_stats = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 256);  // [2][BLOCK_N]
+    float* s_stats = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 256);  // [4 warps][2][BLOCK_N]
 
     const int warp = threadIdx.x >> 5;
     const uint32_t lane = lane_id();
@@ -106,18 +106,14 @@ __global__ void __launch_bounds__(IG_THREADS) igemm_kernel(const __grid_constant
         tmem_relinquish();
     }
     if (warp >= 4) {
-        for (int i = threadIdx.x - 128; i < 2 * BLOCK_N; i += 128) s_stats[i] = 0.f;
+        for (int i = threadIdx.x - 128; i < 8 * BLOCK_N; i += 128) s_stats[i] = 0.f;
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
-    const int dbg = args.debug_stage & 15;
-    const bool dbg_cl = (args.debug_stage & 16) != 0;
 
-    if (dbg == 1) {
-        // setup only
-    } else if (warp == 0) {
+    if (warp == 0) {
         // ===================== TMA producer =====================
         if (elect_one()) {
             int stage = 0;
@@ -128,13 +124,8 @@ __global__ void __launch_bounds__(IG_THREADS) igemm_kernel(const __grid_constant
                 uint8_t* sb = sa + IG_A_BYTES;
                 const int tap = kb / args.kc_per_tap;
                 const int c0 = (kb - tap * args.kc_per_tap) * IG_BLOCK_K;
-                mbar_arrive_expect_tx(&full_bar[stage], dbg == 5   ? STAGE_BYTES - IG_A_BYTES
-                                                        : dbg == 6 ? IG_A_BYTES
-                                                                   : STAGE_BYTES);
-                if (dbg == 5) {
-                } else if (dbg_cl) {
-                    tma_load_4d_cl(&map_a, &full_bar[stage], sa, c0, w0, h0, img);
-                } else if (args.a_mode == 0) {
+                mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
+                if (args.a_mode == 0) {
                     int dh = 0, dw = 0;
                     if (args.num_taps == 9) {
                         dh = tap / 3 - 1;
@@ -145,12 +136,7 @@ __global__ void __launch_bounds__(IG_THREADS) igemm_kernel(const __grid_constant
                     // (c, j, w, i, img*H + h) view of the (2H x 2W) tensor; tap = i*2 + j
                     tma_load_5d(&map_a, &full_bar[stage], sa, c0, tap & 1, w0, tap >> 1, img * args.H + h0);
                 }
-                if (dbg == 6) {
-                } else if (dbg_cl) {
-                    tma_load_2d_cl(&map_b, &full_bar[stage], sb, kb * IG_BLOCK_K, n0);
-                } else {
-                    tma_load_2d(&map_b, &full_bar[stage], sb, kb * IG_BLOCK_K, n0);
-                }
+                tma_load_2d(&map_b, &full_bar[stage], sb, kb * IG_BLOCK_K, n0);
                 if (++stage == STAGES) {
                     stage = 0;
                     phase ^= 1;
@@ -170,22 +156,18 @@ __global__ void __launch_bounds__(IG_THREADS) igemm_kernel(const __grid_constant
                 const uint32_t sb = sa + IG_A_BYTES;
                 const uint64_t da = umma_smem_desc_sw128(sa, 0, 1024);
                 const uint64_t db = umma_smem_desc_sw128(sb, 0, 1024);
-                if (dbg == 2 || dbg == 5 || dbg == 6) {
-                    mbar_arrive(&empty_bar[stage]);  // TMA + barriers only
-                } else {
 #pragma unroll
-                    for (int k = 0; k < IG_BLOCK_K / 16; ++k) {
-                        // +32 B per UMMA_K inside the 128 B swizzle span (encoded >> 4)
-                        umma_bf16(tmem_base, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
-                    }
-                    umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
+                for (int k = 0; k < IG_BLOCK_K / 16; ++k) {
+                    // +32 B per UMMA_K inside the 128 B swizzle span (encoded >> 4)
+                    umma_bf16(tmem_base, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
                 }
+                umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
                 if (++stage == STAGES) {
                     stage = 0;
                     phase ^= 1;
                 }
             }
-            if (dbg == 2 || dbg == 5 || dbg == 6) mbar_arrive(tmem_full_bar); else umma_commit(tmem_full_bar);  // accumulator complete
+            umma_commit(tmem_full_bar);  // accumulator complete
         }
     } else if (warp >= 4) {
         // ===================== epilogue =====================
@@ -195,14 +177,13 @@ __global__ void __launch_bounds__(IG_THREADS) igemm_kernel(const __grid_constant
         const int w = w0 + row % IG_TILE_W;
         mbar_wait(tmem_full_bar, 0);
         tc_fence_after();
-        const bool do_stats = args.stats != nullptr && dbg == 0;
+        const bool do_stats = args.stats != nullptr;
 
 #pragma unroll 1
-        for (int chunk = 0; chunk < (dbg == 2 || dbg == 3 || dbg == 5 || dbg == 6 ? 0 : BLOCK_N / 32); ++chunk) {
+        for (int chunk = 0; chunk < BLOCK_N / 32; ++chunk) {
             uint32_t raw[32];
             tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + chunk * 32, raw);
             tmem_ld_wait();
-            if (dbg == 4) continue;
             const int col0 = n0 + chunk * 32;  // global GEMM column of raw[0]
             float v[32];
 #pragma unroll
@@ -257,16 +238,26 @@ __global__ void __launch_bounds__(IG_THREADS) igemm_kernel(const __grid_constant
                 }
                 const float cs = warp_transpose_reduce32(s1, lane);
                 const float cq = warp_transpose_reduce32(s2, lane);
-                atomicAdd(&s_stats[chunk * 32 + lane], cs);
-                atomicAdd(&s_stats[BLOCK_N + chunk * 32 + lane], cq);
+                s_stats[(q * 2 + 0) * BLOCK_N + chunk * 32 + lane] = cs;  // own slot per warp: combined in warp order below
+                s_stats[(q * 2 + 1) * BLOCK_N + chunk * 32 + lane] = cq;
             }
         }
         if (do_stats) {
             named_bar_sync(1, 128);
-            float* dst = args.stats + static_cast<size_t>(m_tile % args.stats_replicas) * 2 * args.n_total;
-            for (int i = threadIdx.x - 128; i < BLOCK_N; i += 128) {
-                atomicAdd(dst + n0 + i, s_stats[i]);
-                atomicAdd(dst + args.n_total + n0 + i, s_stats[BLOCK_N + i]);
+            const int m_tiles = static_cast<int>(gridDim.x) / args.n_tiles;
+            for (int i = threadIdx.x - 128; i < 2 * BLOCK_N; i += 128) {
+                const int which = i / BLOCK_N, col = i - which * BLOCK_N;
+                float acc = 0.f;
+#pragma unroll
+                for (int w4 = 0; w4 < 4; ++w4) acc += s_stats[(w4 * 2 + which) * BLOCK_N + col];
+                if (args.stats_slots) {
+                    args.stats[(static_cast<size_t>(m_tile) * 2 + which) * args.n_total + n0 + col] = acc;
+                    for (int s2 = m_tile + m_tiles; s2 < args.stats_replicas; s2 += m_tiles)
+                        args.stats[(static_cast<size_t>(s2) * 2 + which) * args.n_total + n0 + col] = 0.f;
+                } else {
+                    atomicAdd(args.stats + (static_cast<size_t>(m_tile % args.stats_replicas) * 2 + which) * args.n_total + n0 + col,
+                              acc);
+                }
             }
         }
     }

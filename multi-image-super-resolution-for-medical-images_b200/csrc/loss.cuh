@@ -15,7 +15,7 @@
 // Each block owns a 32x32 tile of prediction pixels, stages x,y with a 2(K-1) halo in shared memory, and runs
 // the separable filters out of shared memory; loss partial sums leave through two double atomics per block.
 #pragma once
-#include "ptx.cuh"
+#include "elementwise.cuh"
 
 namespace b200sr {
 
@@ -36,7 +36,52 @@ struct LossArgs {
     float cov_norm, C1, C2;
     float g_mse;   // w_mse * 2 / (B*H*W)
     float g_ssim;  // -w_ssim / (B * (H-K+1) * (W-K+1))
+    // deterministic finish (partials != NULL): block b stores its two partial sums into partials[b][2]; the last block
+    // (ticket) adds them in block order and writes out = {loss, mse, mean SSIM} — no atomics, no host-side arithmetic
+    double* partials;
+    unsigned* counter;
+    float* out;
+    double inv_n_mse, inv_n_ssim;
+    float w_mse, w_ssim;
 };
+
+__device__ __forceinline__ void loss_finish(const LossArgs& a, const float (&s_red)[2][8], int tid) {
+    if (a.partials == nullptr) {
+        if (tid < 2) {
+            double acc = 0.0;
+            for (int w = 0; w < 8; ++w) acc += s_red[tid][w];
+            atomicAdd(a.sums + tid, acc);
+        }
+        return;
+    }
+    if (tid < 2) {
+        double acc = 0.0;
+        for (int w = 0; w < 8; ++w) acc += s_red[tid][w];
+        a.partials[static_cast<size_t>(blockIdx.x) * 2 + tid] = acc;
+    }
+    if (!last_block_ticket(a.counter, gridDim.x)) return;
+    __shared__ double s_t[2][128];
+    const int which = tid & 1, sl = tid >> 1;  // 2 sums x 128 block-lanes
+    double acc = 0.0;
+    for (unsigned b = sl; b < gridDim.x; b += 128) acc += __ldcg(a.partials + static_cast<size_t>(b) * 2 + which);
+    s_t[which][sl] = acc;
+    __syncthreads();
+    if (tid == 0) {
+        double m = 0.0, q = 0.0;
+        for (int l = 0; l < 128; ++l) {
+            m += s_t[0][l];
+            q += s_t[1][l];
+        }
+        const double mse = m * a.inv_n_mse, ssim = q * a.inv_n_ssim;
+        a.out[0] = static_cast<float>(a.w_mse * mse + a.w_ssim * (1.0 - ssim));
+        a.out[1] = static_cast<float>(mse);
+        a.out[2] = static_cast<float>(ssim);
+        if (a.sums != nullptr) {
+            a.sums[0] = m;
+            a.sums[1] = q;
+        }
+    }
+}
 
 __global__ void __launch_bounds__(256) mse_ssim_kernel(const LossArgs a) {
     extern __shared__ float ls_smem[];
@@ -184,11 +229,7 @@ __global__ void __launch_bounds__(256) mse_ssim_kernel(const LossArgs a) {
         s_red[1][tid >> 5] = ssim_part;
     }
     __syncthreads();
-    if (tid < 2) {
-        double acc = 0.0;
-        for (int w = 0; w < 8; ++w) acc += s_red[tid][w];
-        atomicAdd(a.sums + tid, acc);
-    }
+    loss_finish(a, s_red, tid);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -402,11 +443,7 @@ __global__ void __launch_bounds__(256, 2) mse_ssim_fast_kernel(const LossArgs a)
         s_red[1][tid >> 5] = ssim_part;
     }
     __syncthreads();
-    if (tid < 2) {
-        double acc = 0.0;
-        for (int wi = 0; wi < 8; ++wi) acc += s_red[tid][wi];
-        atomicAdd(a.sums + tid, acc);
-    }
+    loss_finish(a, s_red, tid);
 }
 
 }  // namespace b200sr

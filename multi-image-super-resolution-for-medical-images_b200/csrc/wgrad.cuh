@@ -31,7 +31,8 @@ struct WGradArgs {
     int tchunks_per_tap;  // channels of T / 64
     int total_atoms;      // num_taps * tchunks_per_tap
     int n_total;          // channels of P
-    float* out;           // [total_atoms*64][n_total] fp32, pre-zeroed
+    float* out;           // [total_atoms*64][n_total] fp32, pre-zeroed (split_stride == 0)
+    long long split_stride;  // > 0: split-K slice s STORES its partial into out + s * split_stride (deterministic mode)
 };
 
 constexpr int WG_THREADS = 256;
@@ -174,17 +175,26 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const __grid_const
         for (int mt = 0; mt < m_tiles; ++mt) {
             const int a = 2 * mt + (row >> 6);  // warp-uniform: a warp never straddles the two atoms
             if (a >= n_atoms) continue;
-            float* dst_row = args.out + (static_cast<size_t>(atom0 + a) * 64 + (row & 63)) * args.n_total + n0;
+            float* dst_row = args.out + static_cast<size_t>(blockIdx.z) * args.split_stride +
+                             (static_cast<size_t>(atom0 + a) * 64 + (row & 63)) * args.n_total + n0;
 #pragma unroll 1
             for (int chunk = 0; chunk < N_TILE / 32; ++chunk) {
                 uint32_t raw[32];
                 tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + mt * N_TILE + chunk * 32, raw);
                 tmem_ld_wait();
+                if (args.split_stride > 0) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i)
-                    red_add_v4_f32(dst_row + chunk * 32 + 4 * i, __uint_as_float(raw[4 * i]),
-                                   __uint_as_float(raw[4 * i + 1]), __uint_as_float(raw[4 * i + 2]),
-                                   __uint_as_float(raw[4 * i + 3]));
+                    for (int i = 0; i < 8; ++i)
+                        *reinterpret_cast<float4*>(dst_row + chunk * 32 + 4 * i) =
+                            make_float4(__uint_as_float(raw[4 * i]), __uint_as_float(raw[4 * i + 1]),
+                                        __uint_as_float(raw[4 * i + 2]), __uint_as_float(raw[4 * i + 3]));
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        red_add_v4_f32(dst_row + chunk * 32 + 4 * i, __uint_as_float(raw[4 * i]),
+                                       __uint_as_float(raw[4 * i + 1]), __uint_as_float(raw[4 * i + 2]),
+                                       __uint_as_float(raw[4 * i + 3]));
+                }
             }
         }
     }

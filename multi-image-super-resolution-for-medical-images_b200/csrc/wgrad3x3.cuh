@@ -32,7 +32,9 @@ struct WG3Args {
     int jobs_ci;         // mode A: Cin / 128
     int jobs_co;         // Cout / N_TILE
     int Cin, Cout;
-    float* out;          // [9][Cin][Cout] fp32, pre-zeroed, ADDED into
+    float* out;          // [9][Cin][Cout] fp32, pre-zeroed, ADDED into (split_stride == 0)
+    long long split_stride;  // > 0: deterministic mode — split-K slice s STORES its partial into out + s * split_stride
+                             // (floats); a fixed-order second stage (wgrad_reduce_unpack_kernel) sums the slices
 };
 
 constexpr int WG3_THREADS = 256;
@@ -205,17 +207,26 @@ __global__ void __launch_bounds__(WG3_THREADS, 1) wgrad3x3_kernel(const __grid_c
                 tap = t * 3 + dw_job;
                 ci = ci_group * 128 + half * 64;
             }
-            float* dst_row = args.out + (static_cast<size_t>(tap) * args.Cin + ci + (row & 63)) * args.Cout + n0;
+            float* dst_row = args.out + static_cast<size_t>(blockIdx.y) * args.split_stride +
+                             (static_cast<size_t>(tap) * args.Cin + ci + (row & 63)) * args.Cout + n0;
 #pragma unroll 1
             for (int chunk = 0; chunk < N_TILE / 32; ++chunk) {
                 uint32_t raw[32];
                 tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + t * N_TILE + chunk * 32, raw);
                 tmem_ld_wait();
+                if (args.split_stride > 0) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i)
-                    red_add_v4_f32(dst_row + chunk * 32 + 4 * i, __uint_as_float(raw[4 * i]),
-                                   __uint_as_float(raw[4 * i + 1]), __uint_as_float(raw[4 * i + 2]),
-                                   __uint_as_float(raw[4 * i + 3]));
+                    for (int i = 0; i < 8; ++i)
+                        *reinterpret_cast<float4*>(dst_row + chunk * 32 + 4 * i) =
+                            make_float4(__uint_as_float(raw[4 * i]), __uint_as_float(raw[4 * i + 1]),
+                                        __uint_as_float(raw[4 * i + 2]), __uint_as_float(raw[4 * i + 3]));
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        red_add_v4_f32(dst_row + chunk * 32 + 4 * i, __uint_as_float(raw[4 * i]),
+                                       __uint_as_float(raw[4 * i + 1]), __uint_as_float(raw[4 * i + 2]),
+                                       __uint_as_float(raw[4 * i + 3]));
+                }
             }
         }
     }

@@ -313,7 +313,7 @@ class DeepCNNEngine:
             call("b200sr_bn_finalize", stats_of(bn), STATS_REPLICAS, bn.C, float(npix), ptr(mod.weight), ptr(mod.bias),
                  None, BN_EPS, BN_MOMENTUM, self._ws(bn, "scale"), self._ws(bn, "shift"), self._ws(bn, "mean"),
                  self._ws(bn, "invstd"), ptr(mod.running_mean) if track else None,
-                 ptr(mod.running_var) if track else None, st)
+                 ptr(mod.running_var) if track else None, None, st)
 
         def conv3(w, src, cin, cout, dst, bn):
             call("b200sr_conv3x3_fwd", ptr(src), cin, 0, cin, self._wp(self.wp_fwd, w), cout, B, H, W, ptr(dst), cout, 0,

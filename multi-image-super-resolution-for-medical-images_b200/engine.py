@@ -19,7 +19,8 @@ import torch
 from . import _lib
 from ._lib import call, ptr
 
-STATS_REPLICAS = 4   # statistics are pre-reduced per CTA in registers, so few replicas suffice
+STATS_REPLICAS = 4   # legacy (atomic) statistic replicas, still used by the DeepCNN / Fast-DDPM engines
+WGRAD_WS_FLOATS = 24 * 1024 * 1024  # 96 MB of split-K partials (largest layer: 57 MB); caps the split factor
 BN_EPS = 1e-5
 BN_MOMENTUM = 0.1
 
@@ -111,23 +112,17 @@ class UNetEngine:
         return ps
 
     def _is_flat(self) -> bool:
+        """True while every parameter still is the view of the flat buffer handed out by ensure_ready() and the BatchNorm
+        buffers are where the job tables expect them. A complete scan: 66 data_ptr() reads per call (~20 us), so a
+        replaced p.data anywhere in the model is noticed at the next call, not up to 64 calls later."""
         if self.flat_p is None:
             return False
-        base = self.flat_p.data_ptr()
-        params = self._params()
-        # every call: cheap probe of the first and last parameter; full scan every 64th call (model.to() and
-        # load_state_dict(assign=True) replace all tensors at once, so the probe catches them)
-        self._flat_checks = getattr(self, "_flat_checks", 0) + 1
-        if self._flat_checks % 64 == 0:
-            self.__dict__.pop("_param_list", None)  # re-read the module's parameter objects on the full scan
-            params = self._params()
-            if len(params) != len(self.p_off):
-                return False
-        probe = ((params[0], self.p_off[0]), (params[-1], self.p_off[-1])) if self._flat_checks % 64 else \
-            zip(params, self.p_off)
-        for p, off in probe:
-            if p.data.data_ptr() != base + 4 * off or p.device != self.flat_p.device:
-                return False
+        params = list(self.model.parameters())
+        if len(params) != len(self.p_off) or params[0].device != self.flat_p.device:
+            return False
+        if tuple(p.data_ptr() for p in params) != self._flat_ptrs:
+            return False
+        self._param_list = params
         # raw buffer pointers are baked into the fold-job table
         return self._fold_ptrs == [(cs.bn.running_mean.data_ptr(), cs.bn.running_var.data_ptr()) for cs in self.convs]
 
@@ -150,7 +145,8 @@ class UNetEngine:
         self.p_off, self.p_total = offs, total
         self.flat_p = torch.zeros(total, dtype=torch.float32, device=device)
         self.flat_g = torch.zeros(total, dtype=torch.float32, device=device)
-        self.flat_G = torch.zeros(total, dtype=torch.float32, device=device)  # wgrad workspace, kernel layouts
+        # (flat_g is zeroed ONCE: every real gradient is WRITTEN by a deterministic kernel each step; the conv biases in front
+        # of a BatchNorm have an exactly-zero gradient and are never touched)
         self.grad_views = []
         for p, off in zip(params, offs):
             view = self.flat_p[off:off + p.numel()].view(p.shape)
@@ -158,6 +154,7 @@ class UNetEngine:
             p.data = view
             self.grad_views.append(self.flat_g[off:off + p.numel()].view(p.shape))
         self.off_of = {id(p): off for p, off in zip(params, offs)}
+        self._flat_ptrs = tuple(p.data_ptr() for p in params)
 
         # derived bf16 operand copies: forward + dgrad packings of every tensor-core layer
         wp_total = 0
@@ -178,27 +175,18 @@ class UNetEngine:
 
         # one job per layer writes BOTH packings (forward + dgrad) from a single read of the fp32 parameter
         pack = np.zeros(len(self.convs) - 1 + len(self.ups), dtype=_PACK_JOB_DTYPE)
-        unpack = np.zeros(len(self.convs) - 1 + len(self.ups), dtype=_PACK_JOB_DTYPE)
-        i = j = 0
-        wp_base, g_base, G_base = self.flat_wp.data_ptr(), self.flat_g.data_ptr(), self.flat_G.data_ptr()
+        i = 0
+        wp_base = self.flat_wp.data_ptr()
         for cs in self.convs[1:]:
             w = cs.conv.weight
-            n = w.numel()
             pack[i] = (w.data_ptr(), wp_base + 2 * self.wp_fwd[cs.name], PACK_CONV_BOTH, cs.cout, cs.cin, 0,
                        wp_base + 2 * self.wp_dgrad[cs.name])
             i += 1
-            off = self.off_of[id(w)]
-            unpack[j] = (G_base + 4 * off, g_base + 4 * off, UNPACK_CONV_WGRAD, cs.cout, cs.cin, 0, n)
-            j += 1
         for us in self.ups.values():
             w = us.mod.weight
-            n = w.numel()
             pack[i] = (w.data_ptr(), wp_base + 2 * self.wp_fwd[us.name], PACK_CONVT_BOTH, us.cout, us.cin, 0,
                        wp_base + 2 * self.wp_dgrad[us.name])
             i += 1
-            off = self.off_of[id(w)]
-            unpack[j] = (G_base + 4 * off, g_base + 4 * off, UNPACK_CONVT_WGRAD, us.cout, us.cin, 0, n)
-            j += 1
         # two contiguous groups so the train step can stage the packing: enc1/enc2 (needed first, tiny) on the main
         # stream, everything else on the side stream while those layers run
         early_dst = {wp_base + 2 * self.wp_fwd[cs.name] for cs in self.convs[1:4]}
@@ -208,36 +196,44 @@ class UNetEngine:
         self.pack_groups = (int(early.sum()), int((~early).sum()), 0)
         self.pack_jobs = _jobs_to_device(pack, device)
         self.n_pack = len(pack)
-        # unpack jobs sorted by flat offset so that suffix ranges (= gradient buckets) are contiguous job ranges
-        order = np.argsort(unpack["dst"])
-        self.unpack_np = unpack[order]
-        self.unpack_jobs = _jobs_to_device(self.unpack_np, device)
-        self.n_unpack = len(unpack)
 
-        # per-BN workspace: scale, shift, mean, invstd, c1, c2 ; statistics replicas (fwd) and sums (bwd)
-        ws_total, st_total = 0, 0
-        self.bn_ws_off, self.bn_st_off = {}, {}
-        for cs in self.convs:
+        # per-BN workspace: scale, shift, mean, invstd, eval scale, eval shift; forward statistic slots (one per CTA:
+        # deterministic, see include/b200sr.h) and the final backward sums [2][C]
+        sms = torch.cuda.get_device_properties(device).multi_processor_count
+        self.n_sms = sms
+        ws_total, st_total, sm_total = 0, 0, 0
+        self.bn_ws_off, self.bn_st_off, self.bn_sum_off, self.bn_slots = {}, {}, {}, {}
+        for li, cs in enumerate(self.convs):
             self.bn_ws_off[cs.name] = ws_total
             ws_total += 6 * cs.cout
+            self.bn_slots[cs.name] = 2 * sms if li == 0 else sms  # first conv: 2 CTAs per SM, persistent convs: 1
             self.bn_st_off[cs.name] = st_total
-            st_total += STATS_REPLICAS * 2 * cs.cout
+            st_total += self.bn_slots[cs.name] * 2 * cs.cout
+            self.bn_sum_off[cs.name] = sm_total
+            sm_total += 2 * cs.cout
         self.bn_ws = torch.zeros(ws_total, dtype=torch.float32, device=device)
         self.bn_stats = torch.zeros(st_total, dtype=torch.float32, device=device)
-        self.bn_sums = torch.zeros(st_total, dtype=torch.float32, device=device)
-        # column sums of the decoder concat gradients (ConvTranspose bias gradient)
+        self.bn_sums = torch.zeros(sm_total, dtype=torch.float32, device=device)
+        # column-sum slots of the decoder concat gradients (ConvTranspose bias gradient), one slot per dgrad CTA
         self.up_st_off, up_total = {}, 0
         for k, us in self.ups.items():
             self.up_st_off[k] = up_total
-            up_total += STATS_REPLICAS * 2 * 2 * us.cout
+            up_total += sms * 2 * 2 * us.cout
         self.up_stats = torch.zeros(up_total, dtype=torch.float32, device=device)
+        # workspaces of the deterministic reductions. Main-stream ops (BatchNorm backward, head) and side-stream ops
+        # (weight gradients) never share one; ticket counters are zeroed once and reset by the kernels themselves.
+        bn_ws_floats = max(int(call("b200sr_bn_bwd_ws_floats", cs.cout)) for cs in self.convs)
+        self.red_ws = torch.empty(max(bn_ws_floats, 4 * sms * 72), dtype=torch.float32, device=device)
+        self.red_counters = torch.zeros(64, dtype=torch.int32, device=device)
+        self.wg_ws = torch.empty(WGRAD_WS_FLOATS, dtype=torch.float32, device=device)
 
         fold = np.zeros(len(self.convs), dtype=_FOLD_JOB_DTYPE)
         for i, cs in enumerate(self.convs):
             o = self.bn_ws_off[cs.name]
             fold[i] = (cs.bn.weight.data_ptr(), cs.bn.bias.data_ptr(), cs.bn.running_mean.data_ptr(),
                        cs.bn.running_var.data_ptr(), cs.conv.bias.data_ptr() if cs.conv.bias is not None else 0,
-                       self.bn_ws.data_ptr() + 4 * o, self.bn_ws.data_ptr() + 4 * (o + cs.cout), cs.cout, 0)
+                       self.bn_ws.data_ptr() + 4 * (o + 4 * cs.cout), self.bn_ws.data_ptr() + 4 * (o + 5 * cs.cout),
+                       cs.cout, 0)
         self._fold_np = fold
         self.fold_jobs = _jobs_to_device(fold, device)
         self._fold_ptrs = [(cs.bn.running_mean.data_ptr(), cs.bn.running_var.data_ptr()) for cs in self.convs]
@@ -246,8 +242,10 @@ class UNetEngine:
         self._eval_version = None
 
     def _bn(self, cs, which):
-        """Pointer (int) into the BN workspace: which in scale, shift, mean, invstd, c1, c2."""
-        idx = ("scale", "shift", "mean", "invstd", "c1", "c2").index(which)
+        """Pointer (int) into the BN workspace: train-mode scale, shift, mean, invstd (kept for backward) and the
+        eval-mode folded scale / shift, which live in their own slots so that an eval forward between a train forward
+        and its backward leaves the saved train-mode values alone."""
+        idx = ("scale", "shift", "mean", "invstd", "escale", "eshift").index(which)
         return self.bn_ws.data_ptr() + 4 * (self.bn_ws_off[cs.name] + idx * cs.cout)
 
     def _wp(self, table, name):
@@ -303,6 +301,11 @@ class UNetEngine:
         if H % 128 != 0 or W % 256 != 0:
             # deepest level (H/16, W/16) must still tile into 8x16 pixel GEMM tiles
             raise _lib.B200SRError(f"b200sr UNet needs H % 128 == 0 and W % 256 == 0 (got {H}x{W})")
+        if (H >> 4) % 16 != 0 and B * ((H >> 4) // 8) * ((W >> 4) // 16) > self.n_sms:
+            # the bottleneck then runs on the generic one-tile-per-CTA kernel, whose deterministic statistics need one
+            # slot per tile
+            raise _lib.B200SRError(f"b200sr UNet: batch {B} at {H}x{W} exceeds the statistic slots of the bottleneck "
+                                   f"layer ({self.n_sms}); use H % 256 == 0 or a smaller batch")
         dev, bf = self.device, torch.bfloat16
         ch = self.chans
         plan = {"B": B, "H": H, "W": W}
@@ -388,7 +391,7 @@ class UNetEngine:
 
         def conv(cs, src, s_stride, s_off, dst, d_stride, d_off, h, w):
             call("b200sr_conv3x3_fwd", ptr(src), s_stride, s_off, cs.cin, self._wp(self.wp_fwd, cs.name), cs.cout,
-                 B, h, w, ptr(dst), d_stride, d_off, self._bn(cs, "scale"), self._bn(cs, "shift"), 1, None, 0, st)
+                 B, h, w, ptr(dst), d_stride, d_off, self._bn(cs, "escale"), self._bn(cs, "eshift"), 1, None, 0, st)
 
         cur = None
         for lvl, name in enumerate(["enc1", "enc2", "enc3", "enc4"]):
@@ -396,7 +399,7 @@ class UNetEngine:
             h, w, c = H >> lvl, W >> lvl, ch[lvl]
             a1, cat, pool = plan[f"enc_a1_{lvl}"], plan[f"cat{lvl}"], plan[f"pool{lvl}"]
             if lvl == 0:
-                call("b200sr_conv1_fwd", ptr(x), ptr(c1.conv.weight), self._bn(c1, "scale"), self._bn(c1, "shift"), 1,
+                call("b200sr_conv1_fwd", ptr(x), ptr(c1.conv.weight), self._bn(c1, "escale"), self._bn(c1, "eshift"), 1,
                      ptr(a1), None, 0, B, h, w, st)
             else:
                 conv(c1, cur, c1.cin, 0, a1, c, 0, h, w)
@@ -430,20 +433,20 @@ class UNetEngine:
         st = _lib.current_stream_ptr()
         z = plan["z:" + cs.name]
         stats = self.bn_stats.data_ptr() + 4 * self.bn_st_off[cs.name]
+        slots = self.bn_slots[cs.name]  # one statistic slot per CTA: stored, never accumulated -> no zeroing, bit-reproducible
         if x_input is not None:
-            call("b200sr_conv1_fwd", ptr(x_input), ptr(cs.conv.weight), None, None, 0, ptr(z), stats, STATS_REPLICAS,
-                 B, h, w, st)
+            call("b200sr_conv1_fwd", ptr(x_input), ptr(cs.conv.weight), None, None, 0, ptr(z), stats, slots, B, h, w, st)
         else:
             call("b200sr_conv3x3_fwd", ptr(src), s_stride, s_off, cs.cin, self._wp(self.wp_fwd, cs.name), cs.cout,
-                 B, h, w, ptr(z), cs.cout, 0, None, None, 0, stats, STATS_REPLICAS, st)
+                 B, h, w, ptr(z), cs.cout, 0, None, None, 0, stats, slots, st)
         bn = cs.bn
         track = bn.track_running_stats and bn.running_mean is not None
         # (b200sr_bn_train_apply fuses these two launches, but its per-thread finalize prologue costs more HBM
         # bandwidth-time than the extra tiny launch: 1.10 ms vs 0.95 ms per step over the 18 layers, measured)
-        call("b200sr_bn_finalize", stats, STATS_REPLICAS, cs.cout, float(B * h * w), ptr(bn.weight), ptr(bn.bias),
+        call("b200sr_bn_finalize", stats, slots, cs.cout, float(B * h * w), ptr(bn.weight), ptr(bn.bias),
              ptr(cs.conv.bias), BN_EPS, BN_MOMENTUM, self._bn(cs, "scale"), self._bn(cs, "shift"),
              self._bn(cs, "mean"), self._bn(cs, "invstd"), ptr(bn.running_mean) if track else None,
-             ptr(bn.running_var) if track else None, st)
+             ptr(bn.running_var) if track else None, ptr(bn.num_batches_tracked) if track else None, st)
         call("b200sr_bnrelu_apply", ptr(z), cs.cout, self._bn(cs, "scale"), self._bn(cs, "shift"), ptr(act), a_stride,
              a_off, ptr(pooled), B, h, w, st)
 
@@ -462,7 +465,6 @@ class UNetEngine:
         else:
             self.repack_weights()
             self._pack_done = None
-        self.bn_stats.zero_()
         ch = self.chans
         cur = None
         for lvl, name in enumerate(["enc1", "enc2", "enc3", "enc4"]):
@@ -496,9 +498,6 @@ class UNetEngine:
         fc = self.head
         out = torch.empty((B, 1, H, W), dtype=torch.float32, device=x.device)
         call("b200sr_head_fwd", ptr(cur), ptr(fc.weight), ptr(fc.bias), ptr(out), B * H * W, st)
-        bufs = [cs.bn.num_batches_tracked for cs in self.convs if cs.bn.num_batches_tracked is not None]
-        if bufs:
-            torch._foreach_add_(bufs, 1)
         self._saved = (plan, x)
         return out
 
@@ -510,17 +509,18 @@ class UNetEngine:
         B = plan["B"]
         st = _lib.current_stream_ptr()
         z = plan["z:" + cs.name]
-        sums = self.bn_sums.data_ptr() + 4 * self.bn_st_off[cs.name]
+        sums = self.bn_sums.data_ptr() + 4 * self.bn_sum_off[cs.name]
         npix = B * h * w
         sc, sh, mu, iv = (self._bn(cs, k) for k in ("scale", "shift", "mean", "invstd"))
-        call("b200sr_bn_bwd_reduce", dy, dy_stride, dy_off, ptr(z), cs.cout, sc, sh, mu, iv, sums, STATS_REPLICAS,
-             npix, st)
+        call("b200sr_bn_bwd_reduce_det", dy, dy_stride, dy_off, ptr(z), cs.cout, sc, sh, mu, iv, sums, ptr(self.red_ws),
+             self.red_ws.numel(), ptr(self.red_counters), None, npix, st)
         g = self.flat_g.data_ptr()
-        call("b200sr_bn_bwd_apply_fused", dy, dy_stride, dy_off, ptr(z), cs.cout, sc, sh, mu, iv, sums, STATS_REPLICAS,
+        call("b200sr_bn_bwd_apply_fused", dy, dy_stride, dy_off, ptr(z), cs.cout, sc, sh, mu, iv, sums, 1,
              float(npix), g + 4 * self.off_of[id(cs.bn.weight)], g + 4 * self.off_of[id(cs.bn.bias)], dz, npix, st)
 
-    def _G(self, param):
-        return self.flat_G.data_ptr() + 4 * self.off_of[id(param)]
+    def _g(self, param):
+        """Device address of a parameter's gradient inside the flat gradient buffer."""
+        return self.flat_g.data_ptr() + 4 * self.off_of[id(param)]
 
     def backward(self, dout, bucket_hook=None, want_dx=False):
         """See _backward. With overlap enabled the data-gradient chain runs on a HIGH-priority stream and the weight
@@ -540,13 +540,17 @@ class UNetEngine:
     def _backward(self, dout, bucket_hook=None, want_dx=False):
         """Full backward of the last train-mode forward. dout: (B,1,H,W) fp32.
         Gradients land in self.flat_g (views: self.grad_views, in model.parameters() order).
-        bucket_hook(lo, hi), if given, is called as soon as flat_g[lo:hi] is final (reverse forward order).
+        bucket_hook(lo, hi), if given, is called as soon as flat_g[lo:hi] is final (reverse forward order, one range
+        per block: final_conv+dec1+upconv1, dec2+upconv2, ..., bottleneck, enc4, ..., enc1).
 
         Two streams: the data-gradient chain (BN backward -> dgrad -> ...) runs on the current stream; every weight
-        gradient (tensor-core wgrad kernels, their unpack into the parameter layout and the bucket hook) runs on a
-        side stream, ordered by events, so the tensor-bound wgrad kernels overlap the bandwidth-bound BatchNorm /
+        gradient (tensor-core split-K kernels, their fixed-order reduction into the parameter layout and the bucket hook)
+        runs on a side stream, ordered by events, so the tensor-bound wgrad kernels overlap the bandwidth-bound BatchNorm /
         pooling backward kernels of the following layers. Each layer has its own dz buffer, hence no write-after-read
-        hazard between the streams inside a step; the streams are joined at the end."""
+        hazard between the streams inside a step; the streams are joined at the end.
+
+        Every reduction is deterministic (per-CTA / per-split partials, fixed-order second stage; include/b200sr.h):
+        the gradients are WRITTEN, nothing is zeroed per step, and two runs on the same inputs give the same bits."""
         if self._saved is None:
             raise _lib.B200SRError("backward() without a preceding train-mode forward")
         plan, x = self._saved
@@ -567,14 +571,11 @@ class UNetEngine:
         sst = side.cuda_stream
         ch = self.chans
         dout = dout.contiguous().float()
-        self.flat_g.zero_()
-        self.flat_G.zero_()
-        self.bn_sums.zero_()
-        self.up_stats.zero_()
         s0, s1, s2 = (t.data_ptr() for t in plan["scratch"])
-        g = self.flat_g.data_ptr()
         fc = self.head
         ev_i = [0]
+        wg_ws, wg_n = ptr(self.wg_ws), self.wg_ws.numel()
+        n_slots = self.n_sms
 
         def side_after_main():
             """Everything enqueued on the main stream so far happens-before what is enqueued on the side stream next."""
@@ -587,23 +588,23 @@ class UNetEngine:
             ev.record(main)
             side.wait_event(ev)
 
-        def unpack_range(lo_param, hi_off):
-            """Unpack wgrad workspaces for all layers with flat offset in [off(lo_param), hi_off) and report."""
+        def report(lo_param, hi_off):
+            """flat_g[off(lo_param) : hi_off] is final once everything enqueued so far (both streams) has run."""
             lo = self.off_of[id(lo_param)]
-            sel = [i for i in range(self.n_unpack)
-                   if lo <= (int(self.unpack_np["dst"][i]) - g) // 4 < hi_off]
-            side_after_main()  # BN / bias gradients of the range are produced on the main stream
-            if sel:
-                first, n = sel[0], len(sel)
-                call("b200sr_pack_jobs", self.unpack_jobs.data_ptr() + first * _PACK_JOB_DTYPE.itemsize, n, sst)
             if bucket_hook is not None:
+                side_after_main()  # BN / bias gradients of the range are produced on the main stream
                 with torch.cuda.stream(side):
                     bucket_hook(lo, hi_off)
+            return lo
+
+        def wgrad3(src, s_stride, cin, dz, cout, h, w, weight):
+            call("b200sr_conv3x3_wgrad_det", src, s_stride, 0, cin, dz, cout, 0, cout, B, h, w, self._g(weight), cin, 0,
+                 wg_ws, wg_n, sst)
 
         # head
         a_last = plan["dec_a2_0"]
-        call("b200sr_head_bwd", ptr(dout), ptr(a_last), ptr(fc.weight), s0, g + 4 * self.off_of[id(fc.weight)],
-             g + 4 * self.off_of[id(fc.bias)], B * H * W, st)
+        call("b200sr_head_bwd_det", ptr(dout), ptr(a_last), ptr(fc.weight), s0, self._g(fc.weight), self._g(fc.bias),
+             B * H * W, ptr(self.red_ws), self.red_ws.numel(), ptr(self.red_counters) + 4 * 63, st)
         dy = s0  # gradient w.r.t. the current block's output activation (dense)
 
         def block_bwd(name, lvl, in_buf, in_stride, in_c, dx_dst, dx_stride, dx_stats, dy_ptr, x_input=None):
@@ -619,33 +620,30 @@ class UNetEngine:
             self._bn_bwd(plan, c2, dy_ptr, c, 0, h, w, dz2)
             if not late:
                 side_after_main()
-                call("b200sr_conv3x3_wgrad", ptr(a1), c, 0, c, dz2, c, 0, c, B, h, w, self._G(c2.conv.weight), sst)
+                wgrad3(ptr(a1), c, c, dz2, c, h, w, c2.conv.weight)
             call("b200sr_conv3x3_dgrad", dz2, c, 0, c, self._wp(self.wp_dgrad, c2.name), c, B, h, w, dy1, c, 0, None,
                  0, st)
             if late:
                 side_after_main()
-                call("b200sr_conv3x3_wgrad", ptr(a1), c, 0, c, dz2, c, 0, c, B, h, w, self._G(c2.conv.weight), sst)
+                wgrad3(ptr(a1), c, c, dz2, c, h, w, c2.conv.weight)
             self._bn_bwd(plan, c1, dy1, c, 0, h, w, dz1)
             if x_input is not None:
                 side_after_main()
-                call("b200sr_conv1_wgrad", ptr(x_input), dz1, g + 4 * self.off_of[id(c1.conv.weight)], B, h, w, sst)
+                call("b200sr_conv1_wgrad_det", ptr(x_input), dz1, self._g(c1.conv.weight), B, h, w, wg_ws, wg_n, sst)
                 if want_dx:
                     self.dx_input = torch.empty((B, 2, h, w), dtype=torch.float32, device=x_input.device)
                     call("b200sr_conv1_dgrad", dz1, ptr(c1.conv.weight), ptr(self.dx_input), B, h, w, st)
                 return None
             if not late:
                 side_after_main()
-                call("b200sr_conv3x3_wgrad", ptr(in_buf), in_stride, 0, in_c, dz1, c, 0, c, B, h, w,
-                     self._G(c1.conv.weight), sst)
+                wgrad3(ptr(in_buf), in_stride, in_c, dz1, c, h, w, c1.conv.weight)
             call("b200sr_conv3x3_dgrad", dz1, c, 0, c, self._wp(self.wp_dgrad, c1.name), in_c, B, h, w, dx_dst,
-                 dx_stride, 0, dx_stats, STATS_REPLICAS if dx_stats else 0, st)
+                 dx_stride, 0, dx_stats, n_slots if dx_stats else 0, st)
             if late:
                 side_after_main()
-                call("b200sr_conv3x3_wgrad", ptr(in_buf), in_stride, 0, in_c, dz1, c, 0, c, B, h, w,
-                     self._G(c1.conv.weight), sst)
+                wgrad3(ptr(in_buf), in_stride, in_c, dz1, c, h, w, c1.conv.weight)
             return dx_dst
 
-        side_after_main()  # gradient buffers are zeroed
         hi = self.p_total
         # decoder, shallow -> deep
         for k in (1, 2, 3, 4):
@@ -655,30 +653,29 @@ class UNetEngine:
             dcat = plan[f"dcat{lvl}"]
             up_stats = self.up_stats.data_ptr() + 4 * self.up_st_off[k]
             block_bwd(f"dec{k}", lvl, plan[f"cat{lvl}"], 2 * c, 2 * c, ptr(dcat), 2 * c, up_stats, dy)
-            # ConvTranspose bias gradient = column sums of the upsampled half of dcat
-            sums = self.up_stats[self.up_st_off[k]:self.up_st_off[k] + STATS_REPLICAS * 4 * c]
-            torch.sum(sums.view(STATS_REPLICAS, 2, 2 * c)[:, 0, :c], dim=0,
-                      out=self.grad_views[self._params_index(us.mod.bias)])
+            # ConvTranspose bias gradient = column sums of the upsampled half of dcat: per-CTA slots [sum | sumsq][2c]
+            # from the dgrad epilogue, added in slot order
+            call("b200sr_sum_slots", up_stats, n_slots, 2 * 2 * c, c, self._g(us.mod.bias), st)
             x_up = plan["bot_a2"] if k == 4 else plan[f"dec_a2_{lvl + 1}"]
-            if not self.wgrad_late:
+
+            def up_wgrad():
                 side_after_main()
-                call("b200sr_convT2x2_wgrad", ptr(dcat), 2 * c, 0, c, ptr(x_up), us.cin, 0, us.cin, B, h // 2, w // 2,
-                     self._G(us.mod.weight), sst)
+                call("b200sr_convT2x2_wgrad_det", ptr(dcat), 2 * c, 0, c, ptr(x_up), us.cin, 0, us.cin, B, h // 2, w // 2,
+                     self._g(us.mod.weight), wg_ws, wg_n, sst)
+
+            if not self.wgrad_late:
+                up_wgrad()
             dy = s0 if dy != s0 else s1
             call("b200sr_convT2x2_dgrad", ptr(dcat), 2 * c, 0, c, self._wp(self.wp_dgrad, us.name), us.cin, B, h // 2,
                  w // 2, dy, us.cin, 0, st)
             if self.wgrad_late:
-                side_after_main()
-                call("b200sr_convT2x2_wgrad", ptr(dcat), 2 * c, 0, c, ptr(x_up), us.cin, 0, us.cin, B, h // 2, w // 2,
-                     self._G(us.mod.weight), sst)
-        unpack_range(self.ups[4].mod.weight, hi)
-        hi = self.off_of[id(self.ups[4].mod.weight)]
+                up_wgrad()
+            hi = report(us.mod.weight, hi)  # upconv_k is the lowest flat offset of {upconv_k, dec_k[, final_conv]}
 
         # bottleneck: dx = gradient w.r.t. pool3 (dense)
         dpool = [p for p in (s0, s1, s2) if p != dy][0]
         block_bwd("bottleneck", 4, plan["pool3"], ch[3], ch[3], dpool, ch[3], None, dy)
-        unpack_range(self.blocks["bottleneck"][0].conv.weight, hi)
-        hi = self.off_of[id(self.blocks["bottleneck"][0].conv.weight)]
+        hi = report(self.blocks["bottleneck"][0].conv.weight, hi)
 
         # encoder, deep -> shallow
         for lvl in (3, 2, 1, 0):
@@ -693,7 +690,7 @@ class UNetEngine:
                 nxt = [p for p in (s0, s1, s2) if p != dy][0]
                 block_bwd(name, lvl, plan[f"pool{lvl - 1}"], ch[lvl - 1], ch[lvl - 1], nxt, ch[lvl - 1], None, dy)
                 dpool = nxt
-        unpack_range(self.blocks["enc1"][0].conv.weight, hi)
+            hi = report(self.blocks[name][0].conv.weight, hi)
         if overlap:
             main.wait_stream(side)
         self._saved = None

@@ -561,6 +561,12 @@ class FastDDPM(nn.Module):
         return self._mse.value_and_grad(eps, noise, need_grad=need_grad)
 
     def forward(self, cond, target, t, noise=None):
+        """Noise-prediction MSE (reference ModelLoader.py:595-602). Like the reference's, the returned loss is
+        differentiable: `loss.backward()` runs the engine's hand-written backward and fills `p.grad` of the denoiser's
+        parameters (an autograd node around forward + backward). Under no_grad / frozen parameters it is a plain value."""
+        params = list(self.unet.parameters())
+        if torch.is_grad_enabled() and any(p.requires_grad for p in params):
+            return _FastDDPMLossFn.apply(self, cond, target, t, noise, *params)
         return self.loss_and_grad(cond, target, t, noise=noise, need_grad=False)[0]
 
     @torch.no_grad()
@@ -615,6 +621,26 @@ class FastDDPM(nn.Module):
             call("b200sr_fd_ddim_update", ptr(x), ptr(eps), ab[i], a_prev, 1 if i == 0 else 0, n,
                  _lib.current_stream_ptr())
         return x
+
+
+class _FastDDPMLossFn(torch.autograd.Function):
+    """Autograd node of FastDDPM.forward: engine forward + fused MSE in forward(), engine backward in backward()."""
+
+    @staticmethod
+    def forward(ctx, model, cond, target, t, noise, *params):
+        loss, dout = model.loss_and_grad(cond, target, t, noise=noise, need_grad=True)
+        ctx.model = model
+        ctx.save_for_backward(dout)
+        return loss
+
+    @staticmethod
+    def backward(ctx, gout):
+        (dout,) = ctx.saved_tensors
+        engine = ctx.model.unet._get_engine()
+        engine.backward(dout * gout)
+        flat = engine.flat_g.clone()  # independent copy: the flat gradient buffer is reused by the next step
+        grads = [flat[off:off + p.numel()].view(p.shape) for p, off in zip(engine._params(), engine.p_off)]
+        return (None, None, None, None, None, *grads)
 
 
 class FastDDPMTrainer:

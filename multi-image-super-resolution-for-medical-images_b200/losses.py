@@ -55,6 +55,7 @@ class CombinedLoss(nn.Module):
         self.C1, self.C2 = (0.01 * data_range) ** 2, (0.03 * data_range) ** 2
         self._win_c = (ctypes.c_float * len(self.win))(*self.win)
         self.last_components = None  # (mse, ssim) device scalars of the last call
+        self._ws = {}  # device -> (partial sums, ticket counter) of the deterministic in-kernel reduction
 
     def value_and_grad(self, pred, target, need_grad=True):
         """Returns (loss 0-d fp32 device tensor, dloss/dpred or None). No host synchronisation."""
@@ -66,16 +67,21 @@ class CombinedLoss(nn.Module):
         target = target.detach().contiguous().float()
         B, _, H, W = pred.shape
         K = len(self.win)
-        sums = torch.zeros(2, dtype=torch.float64, device=pred.device)
+        # deterministic finish inside the kernel: per-CTA partial sums in a persistent workspace, the last CTA adds them in
+        # CTA order and writes {loss, mse, mean SSIM}; no atomics, no host-side arithmetic, no extra launches
+        nblocks = B * ((H + 31) // 32) * ((W + 31) // 32)
+        ws = self._ws.get(pred.device)
+        if ws is None or ws[0].numel() < 2 * nblocks:
+            ws = (torch.empty(2 * nblocks, dtype=torch.float64, device=pred.device),
+                  torch.zeros(1, dtype=torch.int32, device=pred.device))
+            self._ws[pred.device] = ws
+        out3 = torch.empty(4, dtype=torch.float32, device=pred.device)  # fresh per call: the caller may keep the loss
         grad = torch.empty_like(pred) if need_grad else None
-        call("b200sr_mse_ssim", ptr(pred), ptr(target), ptr(grad), ptr(sums), B, H, W,
+        call("b200sr_mse_ssim_det", ptr(pred), ptr(target), ptr(grad), ptr(out3), B, H, W,
              ctypes.cast(self._win_c, ctypes.c_void_p), K, self.cov_norm, self.C1, self.C2, self.mse_weight,
-             self.ssim_weight, _lib.current_stream_ptr())
-        mse = sums[0] / float(B * H * W)
-        ssim = sums[1] / float(B * (H - K + 1) * (W - K + 1))
-        self.last_components = (mse, ssim)
-        loss = (self.mse_weight * mse + self.ssim_weight * (1.0 - ssim)).float()
-        return loss, grad
+             self.ssim_weight, ptr(ws[0]), ws[0].numel(), ptr(ws[1]), _lib.current_stream_ptr())
+        self.last_components = (out3[1], out3[2])
+        return out3[0], grad
 
     def forward(self, pred, target):
         if pred.requires_grad and torch.is_grad_enabled():

@@ -159,3 +159,54 @@ def train_step_cpu(sd, x, y, opt_state, step, lr=1e-4, loss_fn=None):
             opt_state[k] = (m, v)
         sd.update(new_stats)
     return loss
+
+
+def layer_taps(sd, x, y, loss_fn=None):
+    """Train-mode forward + backward that also returns, for every layer, the tensors a per-layer (teacher-forced) parity
+    test needs: the layer input, the raw conv output z (bias included, as nn.Conv2d produces it), the post-ReLU
+    activation, and the gradients of the loss w.r.t. z and the activation. Used by tests/test_gpu_layers.py.
+    Returns (loss, out, taps, grads) with taps[name] = dict(a_in, z, act, dz, dact) for the 18 Conv+BN+ReLU layers
+    ('enc1.conv.0' ...) and taps['upconvK'] = dict(a_in, out, dout) for the 4 ConvTranspose2d layers."""
+    names = param_names(sd)
+    leaf = {k: (v.detach().clone().requires_grad_(True) if k in set(names) else v) for k, v in sd.items()}
+    taps = {}
+
+    def block(prefix, t):
+        for conv_i, bn_i in ((0, 1), (3, 4)):
+            a_in = t
+            z = F.conv2d(t, leaf[f"{prefix}.conv.{conv_i}.weight"], leaf.get(f"{prefix}.conv.{conv_i}.bias"), padding=1)
+            rm = sd[f"{prefix}.conv.{bn_i}.running_mean"].detach().clone()
+            rv = sd[f"{prefix}.conv.{bn_i}.running_var"].detach().clone()
+            t = torch.relu(F.batch_norm(z, rm, rv, leaf[f"{prefix}.conv.{bn_i}.weight"], leaf[f"{prefix}.conv.{bn_i}.bias"],
+                                        training=True, momentum=BN_MOMENTUM, eps=BN_EPS))
+            taps[f"{prefix}.conv.{conv_i}"] = {"a_in": a_in, "z": z, "act": t}
+        return t
+
+    t = x
+    skips = []
+    for name in ENCODERS:
+        t = block(name, t)
+        skips.append(t)
+        t = F.max_pool2d(t, kernel_size=2, stride=2)
+    t = block("bottleneck", t)
+    for (up, dec), skip in zip(DECODERS, reversed(skips)):
+        u = F.conv_transpose2d(t, leaf[f"{up}.weight"], leaf[f"{up}.bias"], stride=2)
+        taps[up] = {"a_in": t, "out": u}
+        t = block(dec, torch.cat([u, skip], dim=1))
+    out = F.conv2d(t, leaf["final_conv.weight"], leaf["final_conv.bias"])
+    loss = F.mse_loss(out, y) if loss_fn is None else loss_fn(out, y)
+    wanted = []
+    for k, d in taps.items():
+        wanted += [d["z"], d["act"]] if "z" in d else [d["out"]]
+    gl = torch.autograd.grad(loss, wanted + [leaf[k] for k in names])
+    it = iter(gl)
+    for k, d in taps.items():
+        if "z" in d:
+            d["dz"], d["dact"] = next(it), next(it)
+        else:
+            d["dout"] = next(it)
+    grads = dict(zip(names, it))
+    for d in taps.values():
+        for k in list(d):
+            d[k] = d[k].detach()
+    return loss.detach(), out.detach(), taps, grads

@@ -383,8 +383,9 @@ def bn_train(B=2, H=16, W=32, C=128, pool=True, seed=8):
     stats[0, 0] = z.sum(dim=(0, 2, 3))
     stats[0, 1] = (z * z).sum(dim=(0, 2, 3))
     ws = torch.zeros(4, C, device=DEV)
+    nbt = torch.full((), 5, dtype=torch.int64, device=DEV)
     call("b200sr_bn_finalize", ptr(stats), R, C, float(B * H * W), ptr(gamma), ptr(beta), ptr(cbias), 1e-5, 0.1,
-         ptr(ws[0]), ptr(ws[1]), ptr(ws[2]), ptr(ws[3]), ptr(rm), ptr(rv), st())
+         ptr(ws[0]), ptr(ws[1]), ptr(ws[2]), ptr(ws[3]), ptr(rm), ptr(rv), ptr(nbt), st())
     zb = nhwc(z)
     act = slot_buffer(B, H, W, C, 2 * C, C)
     pooled = torch.zeros(B, H // 2, W // 2, C, dtype=torch.bfloat16, device=DEV) if pool else None
@@ -392,7 +393,7 @@ def bn_train(B=2, H=16, W=32, C=128, pool=True, seed=8):
     torch.cuda.synchronize()
     a = nchw(act[..., C:])
     res = {"act": rel(a, ref), "running_mean": rel(rm, rm_ref), "running_var": rel(rv, rv_ref),
-           "slot_untouched": float((act[..., :C].float() - 7.0).abs().max())}
+           "slot_untouched": float((act[..., :C].float() - 7.0).abs().max()), "nbt_exact": abs(int(nbt) - 6)}
     # fused finalize+apply must reproduce the two-kernel path bit for bit
     rm2, rv2 = 0.2 * rnd(C, seed=seed + 4), 1 + 0.1 * rnd(C, seed=seed + 5).abs()
     ws2 = torch.zeros(4, C, device=DEV)
@@ -574,6 +575,224 @@ def conv_determinism(B=6, H=64, W=64, Cin=128, Cout=256, seed=21):
             "convT_bitwise": float((touts[0].float() - touts[1].float()).abs().max())}
 
 
+# ------------------------------------------------------------------------------------------------------
+# deterministic (bit-reproducible) variants: every check runs the op TWICE from garbage-filled outputs / workspaces and
+# requires identical bits, plus parity against the same torch reference as the legacy op
+# ------------------------------------------------------------------------------------------------------
+SLOTS = 148  # one statistic slot per SM
+WS_FLOATS = 4 * 1024 * 1024
+
+
+def _garbage(*shape, dtype=torch.float32):
+    return torch.full(shape, 7.0, dtype=dtype, device=DEV)
+
+
+def conv3x3_fwd_slots(B=6, H=64, W=64, Cin=64, Cout=128, seed=71):
+    """conv3x3 forward with per-CTA statistic slots (no pre-zeroing, no atomics) + bn_finalize over all slots."""
+    _setup()
+    x = bf(rnd(B, Cin, H, W, seed=seed))
+    w = bf(rnd(Cout, Cin, 3, 3, seed=seed + 1, scale=(9 * Cin) ** -0.5))
+    ref = F.conv2d(x, w, padding=1)
+    wp = pack(w, 0, Cout, Cin)
+    xb = nhwc(x)
+    runs = []
+    for _ in range(2):
+        ob = torch.zeros(B, H, W, Cout, dtype=torch.bfloat16, device=DEV)
+        stats = _garbage(SLOTS, 2, Cout)
+        call("b200sr_conv3x3_fwd", ptr(xb), Cin, 0, Cin, ptr(wp), Cout, B, H, W, ptr(ob), Cout, 0, None, None, 0,
+             ptr(stats), SLOTS, st())
+        torch.cuda.synchronize()
+        runs.append((ob, stats))
+    out = nchw(runs[0][0])
+    s = runs[0][1].double().sum(0)
+    return {"out": rel(out, ref), "stats_sum": rel(s[0], out.double().sum(dim=(0, 2, 3))),
+            "stats_sq": rel(s[1], (out.double() ** 2).sum(dim=(0, 2, 3))),
+            "bitwise": float((runs[0][1] - runs[1][1]).abs().max())}
+
+
+def conv3x3_wgrad_det(B=2, H=16, W=32, Cin=64, Cout=128, seed=3, cin_total=None, cin_off=0):
+    _setup()
+    x = bf(rnd(B, Cin, H, W, seed=seed))
+    dz = bf(rnd(B, Cout, H, W, seed=seed + 1))
+    ref = torch.nn.grad.conv2d_weight(x, (Cout, Cin, 3, 3), dz, padding=1)
+    xb, dzb = nhwc(x), nhwc(dz)
+    ct = cin_total or Cin
+    outs = []
+    for _ in range(2):
+        dw = _garbage(Cout, ct, 3, 3)
+        ws = _garbage(WS_FLOATS)
+        call("b200sr_conv3x3_wgrad_det", ptr(xb), Cin, 0, Cin, ptr(dzb), Cout, 0, Cout, B, H, W, ptr(dw), ct, cin_off,
+             ptr(ws), WS_FLOATS, st())
+        torch.cuda.synchronize()
+        outs.append(dw)
+    part = outs[0][:, cin_off:cin_off + Cin]
+    res = {"dw": rel(part, ref), "bitwise": float((outs[0] - outs[1]).abs().max())}
+    if ct != Cin:
+        rest = torch.cat([outs[0][:, :cin_off], outs[0][:, cin_off + Cin:]], dim=1)
+        res["rest_untouched"] = float((rest - 7.0).abs().max())
+    return res
+
+
+def convT_wgrad_det(B=2, H=8, W=16, Cin=128, Cout=64, seed=6):
+    _setup()
+    x = bf(rnd(B, Cin, H, W, seed=seed))
+    dup = bf(rnd(B, Cout, 2 * H, 2 * W, seed=seed + 1))
+    w = torch.zeros(Cin, Cout, 2, 2, device=DEV, requires_grad=True)
+    (F.conv_transpose2d(x, w, stride=2) * dup).sum().backward()
+    db = slot_buffer(B, 2 * H, 2 * W, Cout, 2 * Cout, 0, nhwc(dup))
+    xb = nhwc(x)
+    outs = []
+    for _ in range(2):
+        dw = _garbage(Cin, Cout, 2, 2)
+        ws = _garbage(WS_FLOATS)
+        call("b200sr_convT2x2_wgrad_det", ptr(db), 2 * Cout, 0, Cout, ptr(xb), Cin, 0, Cin, B, H, W, ptr(dw), ptr(ws),
+             WS_FLOATS, st())
+        torch.cuda.synchronize()
+        outs.append(dw)
+    return {"dw": rel(outs[0], w.grad), "bitwise": float((outs[0] - outs[1]).abs().max())}
+
+
+def conv1x1_wgrad_det(B=2, H=16, W=32, Cin=64, Cout=128, seed=44):
+    _setup()
+    x = bf(rnd(B, Cin, H, W, seed=seed))
+    dz = bf(rnd(B, Cout, H, W, seed=seed + 1))
+    ref = torch.nn.grad.conv2d_weight(x, (Cout, Cin, 1, 1), dz)
+    outs = []
+    for _ in range(2):
+        dw = _garbage(Cout, Cin, 1, 1)
+        ws = _garbage(WS_FLOATS)
+        call("b200sr_conv1x1_wgrad_det", ptr(nhwc(x)), Cin, 0, Cin, ptr(nhwc(dz)), Cout, 0, Cout, B, H, W, ptr(dw),
+             ptr(ws), WS_FLOATS, st())
+        torch.cuda.synchronize()
+        outs.append(dw)
+    return {"dw": rel(outs[0], ref), "bitwise": float((outs[0] - outs[1]).abs().max())}
+
+
+def conv1_det(B=3, H=64, W=48, seed=7):
+    """first layer: forward statistics in per-CTA slots, weight gradient through per-CTA partials."""
+    _setup()
+    x = rnd(B, 2, H, W, seed=seed)
+    w = rnd(64, 2, 3, 3, seed=seed + 1, scale=18 ** -0.5)
+    dz = bf(rnd(B, 64, H, W, seed=seed + 2))
+    refw = torch.nn.grad.conv2d_weight(bf(x), (64, 2, 3, 3), dz, padding=1)
+    runs = []
+    for _ in range(2):
+        ob = torch.zeros(B, H, W, 64, dtype=torch.bfloat16, device=DEV)
+        stats = _garbage(2 * SLOTS, 2, 64)
+        call("b200sr_conv1_fwd", ptr(x), ptr(w), None, None, 0, ptr(ob), ptr(stats), 2 * SLOTS, B, H, W, st())
+        dw = _garbage(64, 2, 3, 3)
+        ws = _garbage(WS_FLOATS)
+        call("b200sr_conv1_wgrad_det", ptr(x), ptr(nhwc(dz)), ptr(dw), B, H, W, ptr(ws), WS_FLOATS, st())
+        torch.cuda.synchronize()
+        runs.append((ob, stats, dw))
+    out = nchw(runs[0][0])
+    s = runs[0][1].double().sum(0)
+    return {"stats_sum": rel(s[0], out.double().sum(dim=(0, 2, 3))),
+            "stats_sq": rel(s[1], (out.double() ** 2).sum(dim=(0, 2, 3))), "dw": rel(runs[0][2], refw),
+            "bitwise": float((runs[0][1] - runs[1][1]).abs().max() + (runs[0][2] - runs[1][2]).abs().max())}
+
+
+def bn_bwd_det(B=2, H=16, W=32, C=128, seed=10):
+    _setup()
+    z = bf(rnd(B, C, H, W, seed=seed) * 1.5 + 0.3).requires_grad_(True)
+    gamma = (1 + 0.1 * rnd(C, seed=seed + 1)).requires_grad_(True)
+    beta = (0.1 * rnd(C, seed=seed + 2)).requires_grad_(True)
+    dy = bf(rnd(B, C, H, W, seed=seed + 3))
+    y = torch.relu(F.batch_norm(z, None, None, gamma, beta, True, 0.1, 1e-5))
+    y.backward(dy)
+    N = B * H * W
+    zd = z.detach()
+    mean = zd.mean(dim=(0, 2, 3))
+    invstd = torch.rsqrt(zd.var(dim=(0, 2, 3), unbiased=False) + 1e-5)
+    scale = (gamma.detach() * invstd).contiguous()
+    shift = (beta.detach() - mean * scale).contiguous()
+    zb, dyb = nhwc(zd), nhwc(dy)
+    nws = int(call("b200sr_bn_bwd_ws_floats", C))
+    counters = torch.zeros(64, dtype=torch.int32, device=DEV)  # zeroed ONCE: the kernels reset their tickets
+    runs = []
+    for _ in range(2):
+        sums, ws = _garbage(2, C), _garbage(nws)
+        dgb = _garbage(2, C)
+        dz = torch.zeros(B, H, W, C, dtype=torch.bfloat16, device=DEV)
+        call("b200sr_bn_bwd_reduce_det", ptr(dyb), C, 0, ptr(zb), C, ptr(scale), ptr(shift), ptr(mean), ptr(invstd),
+             ptr(sums), ptr(ws), nws, ptr(counters), None, N, st())
+        call("b200sr_bn_bwd_apply_fused", ptr(dyb), C, 0, ptr(zb), C, ptr(scale), ptr(shift), ptr(mean), ptr(invstd),
+             ptr(sums), 1, float(N), ptr(dgb[0]), ptr(dgb[1]), ptr(dz), N, st())
+        torch.cuda.synchronize()
+        runs.append((dz, dgb))
+    return {"dz": rel(nchw(runs[0][0]), z.grad), "dgamma": rel(runs[0][1][0], gamma.grad),
+            "dbeta": rel(runs[0][1][1], beta.grad), "counters_reset": float(counters.abs().max()),
+            "bitwise": float((runs[0][0].float() - runs[1][0].float()).abs().max() + (runs[0][1] - runs[1][1]).abs().max())}
+
+
+def head_det(B=2, H=64, W=96, seed=11):
+    _setup()
+    a = bf(rnd(B, 64, H, W, seed=seed)).requires_grad_(True)
+    w = rnd(1, 64, 1, 1, seed=seed + 1, scale=0.125).requires_grad_(True)
+    b = rnd(1, seed=seed + 2).requires_grad_(True)
+    dout = rnd(B, 1, H, W, seed=seed + 3)
+    F.conv2d(a, w, b).backward(dout)
+    ab = nhwc(a.detach())
+    counter = torch.zeros(1, dtype=torch.int32, device=DEV)
+    runs = []
+    for _ in range(2):
+        dact = torch.zeros(B, H, W, 64, dtype=torch.bfloat16, device=DEV)
+        dwb = _garbage(65)
+        ws = _garbage(4 * SLOTS * 72)
+        call("b200sr_head_bwd_det", ptr(dout), ptr(ab), ptr(w), ptr(dact), ptr(dwb), ptr(dwb) + 4 * 64, B * H * W,
+             ptr(ws), ws.numel(), ptr(counter), st())
+        torch.cuda.synchronize()
+        runs.append((dact, dwb))
+    return {"dact": rel(nchw(runs[0][0]), a.grad), "dw": rel(runs[0][1][:64], w.grad.flatten()),
+            "db": rel(runs[0][1][64:], b.grad), "bitwise": float((runs[0][1] - runs[1][1]).abs().max())}
+
+
+def mse_ssim_det(B=3, H=96, W=80, seed=12):
+    """the loss module runs on the deterministic kernel: value, components and gradient identical over two calls."""
+    _setup()
+    y = rnd(B, 1, H, W, seed=seed)
+    x = (0.6 * y + 0.4 * rnd(B, 1, H, W, seed=seed + 1))
+    crit = b200sr.CombinedLoss(1.0, 0.5, "gaussian")
+    l1, g1 = crit.value_and_grad(x, y)
+    c1 = torch.stack(list(crit.last_components))
+    l2, g2 = crit.value_and_grad(x, y)
+    c2 = torch.stack(list(crit.last_components))
+    torch.cuda.synchronize()
+    mse_ref = float(((x - y) ** 2).double().mean())
+    return {"bitwise": float((l1 - l2).abs() + (g1 - g2).abs().max() + (c1 - c2).abs().max()),
+            "mse_component": abs(float(c1[0]) - mse_ref) / mse_ref,
+            "loss_consistent": abs(float(l1) - (float(c1[0]) + 0.5 * (1.0 - float(c1[1])))) / abs(float(l1))}
+
+
+def adam_auto(n=100003, seed=13):
+    """device-resident step counter: three launches with NO host-side per-step scalars == three torch Adam steps."""
+    _setup()
+    from oracle import unet_oracle
+    n4 = (n + 3) // 4 * 4
+    p, g = rnd(n4, seed=seed), rnd(n4, seed=seed + 1, scale=1e-2)
+    m, v = torch.zeros_like(p), torch.zeros_like(p)
+    pr, mr, vr = p.clone().double(), m.clone().double(), v.clone().double()
+    step_dev = torch.zeros(2, dtype=torch.int32, device=DEV)
+    for step in (1, 2, 3):
+        call("b200sr_adam_step_auto", ptr(p), ptr(g), ptr(m), ptr(v), n, 1e-4, 0.9, 0.999, 1e-8, ptr(step_dev), 0.5, st())
+        pr2, mr, vr = unet_oracle.adam_update(pr, 0.5 * g.double(), mr, vr, step)
+        pr = torch.cat([pr2[:n], pr[n:]])
+        mr[n:] = 0
+        vr[n:] = 0
+    torch.cuda.synchronize()
+    return {"delta": rel(p.double() - rnd(n4, seed=seed).double(), pr - rnd(n4, seed=seed).double()),
+            "m": rel(m, mr), "v": rel(v, vr), "step_count": abs(int(step_dev[0]) - 3) + abs(int(step_dev[1]))}
+
+
+def sum_slots(n=96, slots=SLOTS, stride=256, seed=91):
+    _setup()
+    a = rnd(slots, stride, seed=seed)
+    out = _garbage(n)
+    call("b200sr_sum_slots", ptr(a), slots, stride, n, ptr(out), st())
+    torch.cuda.synchronize()
+    return {"sum": rel(out, a[:, :n].double().sum(0))}
+
+
 # name -> (function, kwargs, {metric: tolerance})
 BF16 = 1e-2
 CHECKS = {
@@ -622,7 +841,7 @@ CHECKS = {
     "conv1x1_persistent": (conv1x1, {}, {"out": BF16, "dx": BF16, "dw": BF16, "stats_sum": 1e-3}),
     "conv1x1_generic": (conv1x1, dict(H=8, W=16, Cin=128, Cout=256), {"out": BF16, "dx": BF16, "dw": BF16}),
     "headw_512": (headw, {}, {"out": 1e-5, "dact": BF16, "dw": 1e-4, "db": 1e-4}),
-    "bn_train_pool": (bn_train, {}, {"act": BF16, "running_mean": 1e-5, "running_var": 1e-4, "pool_exact": 0.0,
+    "bn_train_pool": (bn_train, {}, {"act": BF16, "running_mean": 1e-5, "running_var": 1e-4, "pool_exact": 0.0, "nbt_exact": 0,
                                      "maxpool_fwd_exact": 0.0, "slot_untouched": 0.0, "fused_act_exact": 0.0,
                                      "fused_ws_exact": 0.0, "fused_running_exact": 0.0, "fused_pool_exact": 0.0}),
     "bn_train_c1024": (bn_train, dict(C=1024, B=2, H=8, W=8), {"act": BF16, "fused_act_exact": 0.0,
@@ -643,6 +862,33 @@ CHECKS = {
     "adam": (adam, {}, {"delta": 1e-3,  # fp32 rounding of p (~1) against a 1e-4 update
               "m": 1e-5, "v": 1e-4}),
     "layout_casts": (layout_casts, {}, {"fwd_exact": 0.0, "back_exact": 0.0}),
+    # deterministic reductions: parity + two runs bit-identical from garbage-filled outputs
+    "det_conv3x3_stats_slots": (conv3x3_fwd_slots, {}, {"out": BF16, "stats_sum": 1e-4, "stats_sq": 1e-4, "bitwise": 0.0}),
+    "det_conv3x3_stats_slots_n64": (conv3x3_fwd_slots, dict(Cin=128, Cout=64, B=4, H=128, W=64),
+                                    {"out": BF16, "stats_sum": 1e-4, "stats_sq": 1e-4, "bitwise": 0.0}),
+    "det_conv3x3_stats_slots_n512": (conv3x3_fwd_slots, dict(Cin=128, Cout=512, B=8, H=32, W=64),
+                                     {"out": BF16, "stats_sum": 1e-4, "stats_sq": 1e-4, "bitwise": 0.0}),
+    "det_conv3x3_stats_generic_kernel": (conv3x3_fwd_slots, dict(Cin=64, Cout=128, B=2, H=8, W=16),
+                                         {"out": BF16, "stats_sum": 1e-4, "stats_sq": 1e-4, "bitwise": 0.0}),
+    "det_conv3x3_wgrad_modeA": (conv3x3_wgrad_det, dict(Cin=256, Cout=256, B=3, H=16, W=32), {"dw": BF16, "bitwise": 0.0}),
+    "det_conv3x3_wgrad_modeB": (conv3x3_wgrad_det, dict(Cin=64, Cout=64, B=4, H=64, W=64), {"dw": BF16, "bitwise": 0.0}),
+    "det_conv3x3_wgrad_n64": (conv3x3_wgrad_det, dict(Cin=128, Cout=64, B=2, H=32, W=64), {"dw": BF16, "bitwise": 0.0}),
+    "det_conv3x3_wgrad_generic": (conv3x3_wgrad_det, dict(Cin=320, Cout=256, B=3, H=8, W=16), {"dw": BF16, "bitwise": 0.0}),
+    "det_conv3x3_wgrad_cin_slice": (conv3x3_wgrad_det, dict(Cin=64, Cout=64, B=2, H=32, W=32, cin_total=192, cin_off=128),
+                                    {"dw": BF16, "bitwise": 0.0, "rest_untouched": 0.0}),
+    "det_convT_wgrad": (convT_wgrad_det, {}, {"dw": BF16, "bitwise": 0.0}),
+    "det_convT_wgrad_big": (convT_wgrad_det, dict(Cin=512, Cout=256, B=2, H=16, W=16), {"dw": BF16, "bitwise": 0.0}),
+    "det_conv1x1_wgrad": (conv1x1_wgrad_det, {}, {"dw": BF16, "bitwise": 0.0}),
+    "det_conv1": (conv1_det, {}, {"stats_sum": 1e-4, "stats_sq": 1e-4, "dw": 1e-4, "bitwise": 0.0}),
+    "det_bn_bwd": (bn_bwd_det, {}, {"dz": BF16, "dgamma": 1e-3, "dbeta": 1e-3, "counters_reset": 0.0, "bitwise": 0.0}),
+    "det_bn_bwd_c1024": (bn_bwd_det, dict(C=1024, B=3, H=8, W=8),
+                         {"dz": BF16, "dgamma": 1e-3, "dbeta": 1e-3, "counters_reset": 0.0, "bitwise": 0.0}),
+    "det_bn_bwd_c64_large": (bn_bwd_det, dict(C=64, B=4, H=128, W=96),
+                             {"dz": BF16, "dgamma": 1e-3, "dbeta": 1e-3, "counters_reset": 0.0, "bitwise": 0.0}),
+    "det_head": (head_det, {}, {"dact": BF16, "dw": 1e-4, "db": 1e-4, "bitwise": 0.0}),
+    "det_mse_ssim": (mse_ssim_det, {}, {"bitwise": 0.0, "mse_component": 1e-5, "loss_consistent": 1e-6}),
+    "det_adam_auto": (adam_auto, {}, {"delta": 1e-3, "m": 1e-5, "v": 1e-4, "step_count": 0}),
+    "det_sum_slots": (sum_slots, {}, {"sum": 1e-6}),
 }
 
 

@@ -98,6 +98,26 @@ def test_train_forward_backward_matches_oracle():
     print("fastddpm worst gradient rel-L2", worst)
 
 
+def test_forward_loss_is_differentiable_like_the_reference():
+    """Reference FastDDPM.forward returns a differentiable F.mse_loss and its training loops call loss.backward()
+    (ModelLoader.py:595-602): the drop-in must fill p.grad the same way (autograd node around the engine)."""
+    sd = cases.fastddpm_state_dict(b200sr.FastDDPM)
+    cond, target, t, noise = cases.fastddpm_inputs()
+    o_loss, _, o_grads = fastddpm_oracle.loss_and_grads(sd, cond, target, t, noise)
+    m = _model(sd).train()
+    loss = m(cond.cuda(), target.cuda(), t.cuda(), noise=noise.cuda())
+    assert loss.requires_grad
+    loss.backward()
+    torch.cuda.synchronize()
+    assert abs(float(loss) - float(o_loss)) / float(o_loss) < 1e-3
+    for name, p in m.unet.named_parameters():
+        assert p.grad is not None, name
+        ref = o_grads["unet." + name]
+        assert cos(p.grad.cpu(), ref) > 0.999 and rel(p.grad.cpu(), ref) < 3e-2, name
+    with torch.no_grad():
+        assert not m(cond.cuda(), target.cuda(), t.cuda(), noise=noise.cuda()).requires_grad
+
+
 def test_unet2d_module_call_and_autograd():
     sd = cases.fastddpm_state_dict(b200sr.FastDDPM)
     cond, target, t, noise = cases.fastddpm_inputs()

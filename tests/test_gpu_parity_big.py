@@ -1,0 +1,181 @@
+"""End-to-end parity AT THE BENCHMARKED CONFIGURATIONS against the CPU oracle (pinned to the reference):
+
+  * BASELINE configs[2]: train step, B=32 @ 256x256, combined MSE + 0.005*(1-SSIM) loss, Adam(lr 1e-4)
+    (reference src/unet_model.py:168-191) — forward output, loss, every gradient, running statistics, and the
+    weights after one optimizer step;
+  * BASELINE configs[0]: eval forward, B=8 @ 256x256 (reference src/VolumeVisualization.py:884,932-964).
+
+Gates. loss <= 1e-3 relative and eval forward <= 1e-2 are the north-star numbers. The train-mode output and the
+gradients are gated PER TENSOR by the deviation of the unmodified reference's own bf16-autocast run from its fp32 run
+on the same seeded case (tests/golden/bf16_calibration.json, written by oracle/make_calibration.py):
+      rel-L2(cuda, oracle) <= max(1e-2, 1.5 * rel-L2(reference bf16, reference fp32))
+plus cosine >= 0.9 everywhere and >= 0.99 for the shallow tensors (final_conv, dec1) — relaxed only where the reference's
+own bf16 run is below that (then 1 - 1.5 * its cosine defect; worst tensor of the B=32 case: bottleneck.conv.1.bias,
+reference cosine 0.877) — so that a halo / tap-rotation bug in a deep layer (which scrambles a gradient: cosine near 0,
+rel-L2 near 1.4) cannot pass.
+"""
+import json
+import os
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def rel(a, b):
+    a, b = a.double(), b.double()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def cos(a, b):
+    a, b = a.double().flatten(), b.double().flatten()
+    return float((a @ b) / (a.norm() * b.norm()).clamp_min(1e-30))
+
+
+def _calibration(key):
+    with open(os.path.join(HERE, "golden", "bf16_calibration.json")) as f:
+        return json.load(f)[key]
+
+
+def _check_train_case(case_key, B, H, W, seed):
+    import b200sr
+    from oracle import cases, ssim_oracle, unet_oracle
+    cal = _calibration(case_key)
+    assert (cal["B"], cal["H"], cal["W"], cal["seed"]) == (B, H, W, seed)
+    sd = cases.seeded_state_dict(b200sr.UNet)
+    x, y = cases.seeded_batch(B, H, W, seed)
+    loss_fn = lambda p, t: ssim_oracle.combined_loss(p, t, 1.0, 0.005, "gaussian")
+    o_loss, o_out, o_grads, o_stats = unet_oracle.loss_and_grads(sd, x, y, loss_fn)
+    assert abs(float(o_loss) - cal["loss_fp32"]) / abs(cal["loss_fp32"]) < 1e-5  # same case as the calibration run
+
+    model = b200sr.UNet()
+    model.load_state_dict(sd)
+    trainer = b200sr.UNetTrainer(model, device="cuda", loss="combined", ssim_weight=0.005, learning_rate=1e-4,
+                                 model_save_dir="/tmp/b200sr_parity", verbose=False)
+    eng = model._get_engine()
+    names = unet_oracle.param_names(sd)
+    params = dict(model.named_parameters())
+    trainer.model.train()
+    trainer.optimizer.host_pre_step()
+    xs, ys = x.cuda(), y.cuda()
+    # the step, phase by phase (exactly what UNetTrainer._device_step issues), so that the gradients can be read
+    out = eng.forward_train(xs)
+    loss, dout = trainer.criterion.value_and_grad(out, ys)
+    eng.backward(dout)
+    torch.cuda.synchronize()
+    grads = {n: g.detach().float().cpu().clone() for n, g in zip(names, eng.grad_views)}
+    p_before = {n: params[n].detach().float().cpu().clone() for n in names}
+    trainer.optimizer.device_step()
+    torch.cuda.synchronize()
+
+    fails = []
+    r_loss = abs(float(loss) - float(o_loss)) / abs(float(o_loss))
+    if r_loss > 1e-3:
+        fails.append(("loss", r_loss))
+    r_out = rel(out.cpu(), o_out)
+    if r_out > max(1e-2, 1.5 * cal["out"]):
+        fails.append(("out", r_out, cal["out"]))
+    report = {"loss": r_loss, "out": (r_out, cal["out"])}
+    for n in names:
+        if n.endswith("conv.0.bias") or n.endswith("conv.3.bias"):
+            if float(grads[n].abs().max()) != 0.0:   # BatchNorm cancels these: exactly zero on this path
+                fails.append((n, "nonzero"))
+            continue
+        r, c = rel(grads[n], o_grads[n]), cos(grads[n], o_grads[n])
+        r_cal, c_cal = cal["grads"][n]
+        report[n] = (r, r_cal, c)
+        shallow = n.startswith(("final_conv", "dec1"))
+        c_min = min(0.99 if shallow else 0.9, 1.0 - 1.5 * (1.0 - c_cal))  # never looser than 1.5x the reference's own defect
+        if r > max(1e-2, 1.5 * r_cal) or c < c_min:
+            fails.append((n, r, r_cal, c, c_min))
+    msd = model.state_dict()
+    r_stats = max(rel(msd[k].cpu(), v) for k, v in o_stats.items())
+    if r_stats > 1e-2:
+        fails.append(("running_stats", r_stats))
+    if int(msd["enc1.conv.1.num_batches_tracked"]) != 1:
+        fails.append(("num_batches_tracked", int(msd["enc1.conv.1.num_batches_tracked"])))
+
+    # ---- weights after ONE Adam step (unet_model.py:185) ----
+    worst_plumb, worst_w, upd_cos = 0.0, 0.0, 1.0
+    for n in names:
+        p_after = params[n].detach().float().cpu()
+        # (a) the Adam kernel on the path's own gradient == torch Adam arithmetic
+        p_exp, _, _ = unet_oracle.adam_update(p_before[n].double(), grads[n].double(), 0.0, 0.0, 1)
+        worst_plumb = max(worst_plumb, float((p_after.double() - p_exp).abs().max()))
+        # (b) against the oracle's step (first Adam step = lr * g / (|g| + eps): the sign pattern of the gradient)
+        p_ora, _, _ = unet_oracle.adam_update(p_before[n].double(), o_grads[n].double(), 0.0, 0.0, 1)
+        worst_w = max(worst_w, rel(p_after, p_ora))
+        if not (n.endswith("conv.0.bias") or n.endswith("conv.3.bias")):
+            upd_cos = min(upd_cos, cos(p_after.double() - p_before[n].double(), p_ora - p_before[n].double()))
+    report["adam"] = (worst_plumb, worst_w, upd_cos)
+    if worst_plumb > 2e-7:
+        fails.append(("adam_kernel_vs_torch_formula", worst_plumb))
+    if worst_w > 1e-2:
+        fails.append(("post_adam_weights", worst_w))
+    if upd_cos < 0.6:
+        fails.append(("adam_update_alignment", upd_cos))
+    assert not fails, f"{fails}\nfull report: {report}"
+    return report
+
+
+def test_train_step_b32_256_matches_oracle():
+    """BASELINE configs[2] — the configuration bench.py quotes the headline number on."""
+    _check_train_case("train_b32_combined", 32, 256, 256, 1234)
+
+
+def test_train_step_small_calibrated():
+    """The golden-fixture case (B=2, 128x256) with the same calibrated per-tensor gates."""
+    from oracle import cases
+    c = cases.TRAIN_CASE
+    _check_train_case("train_small_combined", c["B"], c["H"], c["W"], c["seed"])
+
+
+def test_eval_forward_b8_256_matches_oracle():
+    """BASELINE configs[0]: eval-mode forward with non-trivial running statistics, bf16 tensor-core path: <= 1e-2."""
+    import b200sr
+    from oracle import cases, unet_oracle
+    sd = cases.seeded_state_dict(b200sr.UNet)
+    c = cases.TRAIN_CASE
+    x, y = cases.seeded_batch(c["B"], c["H"], c["W"], c["seed"])
+    _, _, _, new_stats = unet_oracle.loss_and_grads(sd, x, y)
+    sd.update(new_stats)
+    xe, _ = cases.seeded_batch(8, 256, 256, 4321)
+    with torch.no_grad():
+        ref = unet_oracle.unet_forward(sd, xe, training=False)
+    model = b200sr.UNet()
+    model.load_state_dict(sd)
+    model = model.cuda().eval()
+    with torch.no_grad():
+        outs = [model(xe.cuda()) for _ in range(4)]  # eager twice, then CUDA-graph replays
+    torch.cuda.synchronize()
+    assert all(torch.equal(outs[0], o) for o in outs[1:])
+    r = rel(outs[0].cpu(), ref)
+    assert r <= 1e-2, r
+    assert r <= max(1e-2, 1.5 * _calibration("eval_b8")["out"])
+
+
+def test_train_step_is_bit_reproducible():
+    """Two independent runs of a train step from the same state give identical bits: loss, every gradient, running
+    statistics and post-Adam weights (all cross-CTA reductions are fixed-order; nothing rides on atomics)."""
+    import b200sr
+    from oracle import cases
+    sd = cases.seeded_state_dict(b200sr.UNet)
+    x, y = cases.seeded_batch(4, 256, 256, 777)
+    runs = []
+    for _ in range(2):
+        model = b200sr.UNet()
+        model.load_state_dict(sd)
+        tr = b200sr.UNetTrainer(model, device="cuda", loss="combined", model_save_dir="/tmp/b200sr_parity", verbose=False)
+        losses = [tr.train_step(x.cuda(), y.cuda()).clone() for _ in range(3)]
+        torch.cuda.synchronize()
+        eng = model._get_engine()
+        runs.append((torch.stack(losses).cpu(), eng.flat_g.clone().cpu(), eng.flat_p.clone().cpu(),
+                     {k: v.clone().cpu() for k, v in model.state_dict().items()}))
+    assert torch.equal(runs[0][0], runs[1][0]), (runs[0][0], runs[1][0])
+    assert torch.equal(runs[0][1], runs[1][1])
+    assert torch.equal(runs[0][2], runs[1][2])
+    for k in runs[0][3]:
+        assert torch.equal(runs[0][3][k], runs[1][3][k]), k

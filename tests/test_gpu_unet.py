@@ -5,9 +5,10 @@ pipeline cannot meet 1e-2 on this random-init network fed iid noise: the REFEREN
 torch.autocast(bfloat16) deviates from its own fp32 run by 1.7e-2 on the forward output and by 0.2-0.45 rel-L2 on
 the deep-layer gradients (ReLU/max-pool decisions flip under bf16 rounding; measured with oracle/bf16_sensitivity.py,
 figures in DESIGN.md). The end-to-end gates are therefore: loss within 1e-3 relative (north star), forward output
-within 2.5e-2, every real gradient positively aligned with the oracle's (cosine > 0.5, shallow layers > 0.95) —
-a wiring or indexing bug gives a cosine near 0 — plus exact-semantics checks (running statistics, BN-cancelled
-bias gradients ~ 0, num_batches_tracked).
+within the reference's own bf16 deviation (x1.5), every gradient gated per tensor by that same calibration
+(tests/golden/bf16_calibration.json) — a wiring or indexing bug gives a cosine near 0 — plus exact-semantics checks
+(running statistics, BN-cancelled bias gradients exactly 0, num_batches_tracked). The benchmarked configurations
+(B=32 train, B=8 eval at 256x256) are covered by test_gpu_parity_big.py, the per-layer 1e-2 bound by test_gpu_layers.py.
 """
 import pytest
 import torch
@@ -20,27 +21,35 @@ pytestmark = pytest.mark.gpu
 def test_eval_forward_matches_oracle_and_golden():
     r = e2echeck.eval_case()
     assert r["oracle_vs_golden"] < 1e-5, r
-    assert r["out_vs_oracle"] < 2.5e-2, r
-    assert r["out_vs_golden"] < 2.5e-2, r
+    assert r["out_vs_oracle"] < 1e-2, r   # north-star bf16 bound (measured 2.5e-3)
+    assert r["out_vs_golden"] < 1e-2, r
 
 
 @pytest.mark.parametrize("loss", ["mse", "combined"])
 def test_train_step_matches_oracle(loss):
+    """Gradient gates are calibrated per tensor with the unmodified reference's own bf16-autocast deviation on this very
+    case (tests/golden/bf16_calibration.json, oracle/make_calibration.py): rel-L2 <= max(1e-2, 1.5 x reference), cosine
+    >= 0.9 (0.99 for final_conv / dec1) unless the reference itself is below that."""
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "bf16_calibration.json")) as f:
+        cal = json.load(f)[f"train_small_{loss}"]
     r = e2echeck.train_case(loss)
     if loss == "mse":
         assert r["oracle_vs_golden_out"] < 1e-5 and r["oracle_vs_golden_loss"] < 1e-6, r
     assert r["loss"] < 1e-3, r
-    assert r["out"] < 2.5e-2, r
+    assert r["out"] < max(1e-2, 1.5 * cal["out"]), (r["out"], cal["out"])
     assert r["running_stats"] < 1e-2, r
     assert r["num_batches_tracked"] == 1
     for name, v in r["grads"].items():
         if v[0] == "abs":
-            assert v[1] < 1e-3, (name, v)   # true gradient is 0 (BatchNorm cancels the conv bias)
+            assert v[1] == 0.0, (name, v)   # true gradient is 0 (BatchNorm cancels the conv bias); never written here
         else:
             _, rel, cos = v
-            assert cos > 0.5, (name, v)
-            if name.startswith(("final_conv", "dec1")):
-                assert cos > 0.95, (name, v)
+            r_cal, c_cal = cal["grads"][name]
+            shallow = name.startswith(("final_conv", "dec1"))
+            assert rel <= max(1e-2, 1.5 * r_cal), (name, v, r_cal)
+            assert cos >= min(0.99 if shallow else 0.9, 1.0 - 1.5 * (1.0 - c_cal)), (name, v, c_cal)
 
 
 def test_autograd_path_matches_engine_path():
@@ -65,16 +74,9 @@ def test_autograd_path_matches_engine_path():
     _, dout = crit.value_and_grad(out2, y.cuda())
     eng.backward(dout)
     torch.cuda.synchronize()
-    # the two runs are not bit-identical: BatchNorm statistics are accumulated with fp32 atomics (order varies),
-    # and one-ulp differences flip a few bf16 roundings that the deep backward pass amplifies
-    names = [n for n, _ in m.named_parameters()]
-    for n, a, b in zip(names, g_auto, eng.grad_views):
-        if n.endswith("conv.0.bias") or n.endswith("conv.3.bias"):
-            continue
-        cos = float((a.flatten().double() @ b.flatten().double()) / (a.double().norm() * b.double().norm()).clamp_min(1e-30))
-        assert cos > 0.90, (n, cos)   # measured run-to-run cosine down to 0.967 (enc3) on this tiny ill-conditioned case
-        if n.startswith(("final_conv", "dec1.conv.3", "dec1.conv.4")):
-            assert cos > 0.99, (n, cos)
+    # both paths issue the same deterministic kernels: identical bits
+    for n, a, b in zip([n for n, _ in m.named_parameters()], g_auto, eng.grad_views):
+        assert torch.equal(a, b), n
 
 
 def test_trainer_reduces_loss_and_checkpoint_roundtrip(tmp_path):
