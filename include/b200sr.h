@@ -102,7 +102,8 @@ typedef struct b200sr_pack_job {
     void* dst;
     int32_t kind; /* 0 conv fwd, 1 conv dgrad, 2 convT fwd, 3 convT dgrad, 4 conv wgrad unpack, 5 convT wgrad unpack,
                      6 conv1x1 fwd, 7 conv1x1 dgrad, 8 conv1x1 wgrad unpack, 9 conv fwd+dgrad (dst, count = second
-                     destination), 10 convT fwd+dgrad likewise */
+                     destination), 10 convT fwd+dgrad likewise, 11 conv fwd bf16x3 split [w_hi|w_hi|w_lo], 12 convT fwd
+                     bf16x3 split (fp32-accuracy eval mode) */
     int32_t cout;
     int32_t cin;
     int32_t pad;
@@ -354,6 +355,28 @@ int b200sr_mse_ssim_det(const float* pred, const float* target, float* grad, flo
  * CTA increments step_dev[0]: graph-replayable, and immune to a host that runs several steps ahead of the device. */
 int b200sr_adam_step_auto(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
                           float eps, int32_t* step_dev, float grad_scale, void* stream);
+
+/* ---- fp32-accuracy eval mode ---------------------------------------------------------------------------
+ * The reference's inference path is an fp32 forward (src/VolumeVisualization.py:932-964; BASELINE configs[0]) and the
+ * north star asks for rel-L2 <= 1e-4 in fp32/tf32. These entry points run the SAME tcgen05 bf16 main loop with
+ * bf16x3 operand splitting: an fp32 activation is stored as (B,H,W,3C) bf16 [hi | lo | hi] (hi = bf16(v),
+ * lo = bf16(v - hi)), a weight as [w_hi | w_hi | w_lo] along K (pack kinds 11 / 12), the accumulation is fp32 and
+ * the epilogue (fp32 affine + ReLU) splits the result again. part_stride = channel distance between the three parts
+ * of the OUTPUT slot (its logical channel count; 2C for a decoder concat buffer). Cin3 = 3 * logical Cin. */
+int b200sr_conv3x3_fwd_split(const void* x, int x_pix_stride, int x_c_off, int Cin3, const void* w_packed, int Cout,
+                             int B, int H, int W, void* out, int out_pix_stride, int out_c_off, int part_stride,
+                             const float* col_scale, const float* col_shift, int relu, void* stream);
+int b200sr_convT2x2_fwd_split(const void* x, int x_pix_stride, int x_c_off, int Cin3, const void* w_packed, int Cout,
+                              const float* bias, int B, int H, int W, void* out, int out_pix_stride, int out_c_off,
+                              int part_stride, void* stream);
+/* First layer in fp32 FMAs from the fp32 NCHW input; out: (B,H,W,192) split. */
+int b200sr_conv1_fwd_split(const float* x, const float* w, const float* col_scale, const float* col_shift, int relu,
+                           void* out, int B, int H, int W, void* stream);
+/* MaxPool2d(2,2) of a split channel slot (parts in_part_stride apart) -> dense split (B,H/2,W/2,3C). */
+int b200sr_maxpool2x2_fwd_split(const void* in, int in_pix_stride, int in_c_off, int in_part_stride, int C, void* out,
+                                int B, int H, int W, void* stream);
+/* final nn.Conv2d(64,1,1) on a split (B,H,W,192) activation, fp32 output. */
+int b200sr_head_fwd_split(const void* act, const float* w, const float* b, float* out, int64_t npix, void* stream);
 
 /* layout casts at the boundary */
 int b200sr_nchw_f32_to_nhwc_bf16(const float* in, void* out, int B, int C, int H, int W, void* stream);

@@ -97,6 +97,13 @@ _SIGNATURES = {
     "b200sr_mse_ssim_det": [_P, _P, _P, _P, c_int, c_int, c_int, _P, c_int, c_float, c_float, c_float, c_float, c_float,
                             _P, c_int64, _P, _P],
     "b200sr_adam_step_auto": [_P, _P, _P, _P, c_int64, c_float, c_float, c_float, c_float, _P, c_float, _P],
+    # fp32-accuracy eval mode (bf16x3 operand split)
+    "b200sr_conv3x3_fwd_split": [_P, c_int, c_int, c_int, _P, c_int, c_int, c_int, c_int, _P, c_int, c_int, c_int, _P, _P,
+                                 c_int, _P],
+    "b200sr_convT2x2_fwd_split": [_P, c_int, c_int, c_int, _P, c_int, _P, c_int, c_int, c_int, _P, c_int, c_int, c_int, _P],
+    "b200sr_conv1_fwd_split": [_P, _P, _P, _P, c_int, _P, c_int, c_int, c_int, _P],
+    "b200sr_maxpool2x2_fwd_split": [_P, c_int, c_int, c_int, c_int, _P, c_int, c_int, c_int, _P],
+    "b200sr_head_fwd_split": [_P, _P, _P, _P, c_int64, _P],
     "b200sr_nchw_f32_to_nhwc_bf16": [_P, _P, c_int, c_int, c_int, c_int, _P],
     "b200sr_nhwc_bf16_to_nchw_f32": [_P, c_int, c_int, _P, c_int, c_int, c_int, c_int, _P],
 }
@@ -136,7 +143,7 @@ def last_error() -> str:
 # ---- launch accounting and optional per-call CUDA-event timing (used by bench.py for the roofline) ------------
 LAUNCH_COUNTER = {"n": 0}
 # entry points that enqueue more than one kernel (split-K gradient + its fixed-order reduction, multi-kernel helpers)
-_KERNELS_PER_CALL = {"b200sr_conv3x3_wgrad_det": 2, "b200sr_convT2x2_wgrad_det": 2, "b200sr_conv1x1_wgrad_det": 2,
+_KERNELS_PER_CALL = {"b200sr_conv3x3_wgrad_det": 3, "b200sr_convT2x2_wgrad_det": 3, "b200sr_conv1x1_wgrad_det": 3,
                      "b200sr_conv1_wgrad_det": 2, "b200sr_bn_bwd_masked": 2, "b200sr_grad_clip": 2, "b200sr_fd_time_bwd": 5,
                      "b200sr_bn_bwd_ws_floats": 0, "b200sr_version": 0, "b200sr_device_ok": 0}
 GEMM_OPS = ("b200sr_conv3x3_fwd", "b200sr_conv3x3_dgrad", "b200sr_conv3x3_dgrad_relu", "b200sr_conv3x3_wgrad", "b200sr_convT2x2_fwd",
@@ -147,8 +154,8 @@ _profile = None  # list of (name, start_event, end_event, flop, bytes) while pro
 
 def _cost(name, a):
     """Algorithmic (flop, bytes) of one call, from its argument list (see include/b200sr.h for the order)."""
-    if name in ("b200sr_conv3x3_fwd", "b200sr_conv3x3_dgrad", "b200sr_conv3x3_dgrad_relu"):
-        return 2.0 * a[6] * a[7] * a[8] * a[3] * a[5] * 9, 0.0
+    if name in ("b200sr_conv3x3_fwd", "b200sr_conv3x3_dgrad", "b200sr_conv3x3_dgrad_relu", "b200sr_conv3x3_fwd_split"):
+        return 2.0 * a[6] * a[7] * a[8] * a[3] * a[5] * 9, 0.0   # (split: issued flops, 3x the algorithmic ones)
     if name in ("b200sr_convT2x2_dgrad",):
         return 2.0 * a[6] * a[7] * a[8] * a[3] * a[5] * 4, 0.0
     if name == "b200sr_convT2x2_fwd":

@@ -288,31 +288,31 @@ int num_sms() {
     return n;
 }
 
-template <int BLOCK_N, int MODE>
+template <int BLOCK_N, int MODE, bool SPLIT = false>
 int launch_conv3_t(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mo, const Conv3Args& args, int grid,
                    cudaStream_t st) {
-    constexpr int smem = C3Cfg<BLOCK_N>::SMEM_BYTES;
+    constexpr int smem = C3Cfg<BLOCK_N, SPLIT>::SMEM_BYTES;
     static bool configured = false;
     if (!configured) {
-        cudaError_t e =
-            cudaFuncSetAttribute(conv3x3_kernel<BLOCK_N, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaError_t e = cudaFuncSetAttribute(conv3x3_kernel<BLOCK_N, MODE, SPLIT>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return fail(B200SR_ECUDA, std::string("conv3x3 smem attribute: ") + cudaGetErrorString(e));
         configured = true;
     }
-    conv3x3_kernel<BLOCK_N, MODE><<<grid, C3_THREADS, smem, st>>>(ma, mb, mo, args);
+    conv3x3_kernel<BLOCK_N, MODE, SPLIT><<<grid, C3_THREADS, smem, st>>>(ma, mb, mo, args);
     return check_launch("conv3x3_kernel");
 }
 
-template <int MODE>
+template <int MODE, bool SPLIT = false>
 int dispatch_conv3(int block_n, const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mo,
                    const Conv3Args& args, int grid, cudaStream_t st) {
     switch (block_n) {
         case 64:
-            return launch_conv3_t<64, MODE>(ma, mb, mo, args, grid, st);
+            return launch_conv3_t<64, MODE, SPLIT>(ma, mb, mo, args, grid, st);
         case 128:
-            return launch_conv3_t<128, MODE>(ma, mb, mo, args, grid, st);
+            return launch_conv3_t<128, MODE, SPLIT>(ma, mb, mo, args, grid, st);
         default:
-            return launch_conv3_t<256, MODE>(ma, mb, mo, args, grid, st);
+            return launch_conv3_t<256, MODE, SPLIT>(ma, mb, mo, args, grid, st);
     }
 }
 
@@ -321,8 +321,11 @@ int dispatch_conv3(int block_n, const CUtensorMap& ma, const CUtensorMap& mb, co
 int run_conv3(int mode, const void* a, int a_stride, int a_coff, int Ca, const void* w_packed, int n_total, int B, int H, int W,
               void* out, int out_stride, int out_coff, const float* col_scale, const float* col_shift, int relu,
               float* stats, int stats_replicas, int cout_t, cudaStream_t st, const void* mask = nullptr,
-              int mask_stride = 0, int mask_coff = 0) {
+              int mask_stride = 0, int mask_coff = 0, int split_stride = 0) {
     B2_CHECK_ARG(a != nullptr && w_packed != nullptr && out != nullptr);
+    // split_stride > 0: fp32-accuracy eval epilogue ([hi | lo | hi] output parts, conv3x3.cuh), modes 0 and 1 only
+    B2_CHECK_ARG(split_stride == 0 || ((mode == 0 || mode == 1) && mask == nullptr && stats == nullptr &&
+                                       split_stride % 8 == 0 && split_stride >= (mode == 1 ? cout_t : n_total)));
     B2_CHECK_ARG(B > 0 && H > 0 && W > 0 && H % C3_TILE_H == 0 && W % C3_TILE_W == 0);
     B2_CHECK_ARG(mask == nullptr || (mode == 0 && mask_stride % 8 == 0 && mask_coff % 8 == 0 && aligned16(mask)));
     if (mode == 1) B2_CHECK_ARG(cout_t % 32 == 0 && n_total == 4 * cout_t);
@@ -359,9 +362,9 @@ int run_conv3(int mode, const void* a, int a_stride, int a_coff, int Ca, const v
     // output tile store: 128 pixels x 64 channels per TMA store; mode 1 scatters through the sub-pixel view
     CUtensorMap mo;
     if (mode == 1)
-        rc = make_gather_map(&mo, out, out_stride, out_coff, cout_t, B, H, W, C3_TILE_W, C3_TILE_H);
+        rc = make_gather_map(&mo, out, out_stride, out_coff, 2 * split_stride + cout_t, B, H, W, C3_TILE_W, C3_TILE_H);
     else
-        rc = make_act_map(&mo, out, out_stride, out_coff, n_total, B, H, W, C3_TILE_W, C3_TILE_H);
+        rc = make_act_map(&mo, out, out_stride, out_coff, 2 * split_stride + n_total, B, H, W, C3_TILE_W, C3_TILE_H);
     if (rc) return rc;
     if (mode == 1) B2_CHECK_ARG(cout_t % 64 == 0);
     Conv3Args args;
@@ -388,14 +391,16 @@ int run_conv3(int mode, const void* a, int a_stride, int a_coff, int Ca, const v
     args.mask = static_cast<const __nv_bfloat16*>(mask);
     args.mask_pix_stride = mask_stride;
     args.mask_c_off = mask_coff;
+    args.split_stride = split_stride;
     {
         const int nh = block_n / (block_n < 128 ? block_n : 128);
         const int slots = taps * args.cin_chunks * nh;
-        const int sb = block_n == 64 ? C3Cfg<64>::SB : C3Cfg<128>::SB;
+        const int sb = (block_n == 64 && split_stride == 0) ? C3Cfg<64>::SB : C3Cfg<128>::SB;
         args.b_resident = (slots <= sb && getenv("B200SR_NO_BRESIDENT") == nullptr) ? 1 : 0;
         // ring bytes that resident weights leave unused become extra activation stages
         const int b_slot = (block_n < 128 ? block_n : 128) * 128;
-        const int ring = (block_n == 64 ? C3Cfg<64>::RING_BYTES : C3Cfg<128>::RING_BYTES);
+        const int ring = block_n == 64 ? (split_stride ? C3Cfg<64, true>::RING_BYTES : C3Cfg<64>::RING_BYTES)
+                                       : C3Cfg<128>::RING_BYTES;
         int sa = C3Cfg<64>::SA;
         if (args.b_resident && getenv("B200SR_FIXED_SA") == nullptr) {
             sa = (ring - slots * b_slot) / C3_A_SLOT;
@@ -411,6 +416,9 @@ int run_conv3(int mode, const void* a, int a_stride, int a_coff, int Ca, const v
     if (grid > args.num_tiles) grid = args.num_tiles;
     // deterministic statistics when the caller provides one slot per CTA of a column block (see Conv3Args::stats_slots)
     args.stats_slots = (stats != nullptr && stats_replicas >= grid / args.n_tiles) ? 1 : 0;
+    if (split_stride > 0)
+        return mode == 0 ? dispatch_conv3<0, true>(block_n, ma, mb, mo, args, grid, st)
+                         : dispatch_conv3<1, true>(block_n, ma, mb, mo, args, grid, st);
     if (mode == 0 && mask != nullptr) return dispatch_conv3<4>(block_n, ma, mb, mo, args, grid, st);
     if (mode == 0) return dispatch_conv3<0>(block_n, ma, mb, mo, args, grid, st);
     if (mode == 1) return dispatch_conv3<1>(block_n, ma, mb, mo, args, grid, st);
@@ -799,12 +807,22 @@ int b200sr_bn_bwd_apply_fused(const void* dy, int dy_pix_stride, int dy_c_off, c
 
 // ---- deterministic (bit-reproducible) variants: per-block / per-split partials + fixed-order second stage ----------
 namespace {
-int launch_reduce_unpack(const float* ws, int splits, long long split_stride, int T, int outer_total, int inner_total,
+int launch_reduce_unpack(float* ws, int splits, long long split_stride, int T, int outer_total, int inner_total,
                          int inner_dst, int inner_off, float* dst, cudaStream_t st) {
     B2_CHECK_ARG(outer_total % PK_TILE == 0 && inner_total % PK_TILE == 0 && (T == 9 || T == 4 || T == 1));
+    if (splits > 1) {
+        // stage 2a: fold the split-K slices into slice 0 (element-parallel; part-lanes when there are many slices)
+        B2_CHECK_ARG(split_stride % 4 == 0);
+        const long long n4 = split_stride / 4;
+        const int lanes = splits >= 32 ? 8 : (splits >= 16 ? 4 : (splits >= 8 ? 2 : 1));
+        const long long blocks = (n4 + 256 / lanes - 1) / (256 / lanes);
+        reduce_splits_inplace_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(reinterpret_cast<float4*>(ws), splits,
+                                                                                   n4, n4, lanes);
+    }
+    // stage 2b: kernel layout [t][inner][outer] -> PyTorch parameter layout
     int tiles = (outer_total / PK_TILE) * (inner_total / PK_TILE);
     if (tiles > num_sms() * 8) tiles = num_sms() * 8;
-    wgrad_reduce_unpack_kernel<<<tiles, 256, 0, st>>>(ws, splits, split_stride, T, outer_total, inner_total, inner_dst,
+    wgrad_reduce_unpack_kernel<<<tiles, 256, 0, st>>>(ws, 1, split_stride, T, outer_total, inner_total, inner_dst,
                                                       inner_off, dst);
     return check_launch("wgrad_reduce_unpack_kernel");
 }
@@ -931,6 +949,51 @@ int b200sr_adam_step_auto(float* p, const float* g, float* m, float* v, int64_t 
     adam_flat_kernel<<<grid_for((n + 3) / 4, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         p, g, m, v, n, lr, beta1, beta2, eps, 1.f, 1.f, grad_scale, nullptr, step_dev);
     return check_launch("adam_flat_kernel");
+}
+
+// ---- fp32-accuracy eval mode (north star: fp32/tf32 tolerance 1e-4; BASELINE configs[0] is an fp32 forward) -------------
+int b200sr_conv3x3_fwd_split(const void* x, int x_pix_stride, int x_c_off, int Cin3, const void* w_packed, int Cout,
+                             int B, int H, int W, void* out, int out_pix_stride, int out_c_off, int part_stride,
+                             const float* col_scale, const float* col_shift, int relu, void* stream) {
+    B2_CHECK_ARG(Cin3 % 192 == 0 && part_stride >= Cout && H % C3_TILE_H == 0 && W % C3_TILE_W == 0);
+    return run_conv3(0, x, x_pix_stride, x_c_off, Cin3, w_packed, Cout, B, H, W, out, out_pix_stride, out_c_off,
+                     col_scale, col_shift, relu, nullptr, 0, Cout, static_cast<cudaStream_t>(stream), nullptr, 0, 0,
+                     part_stride);
+}
+
+int b200sr_convT2x2_fwd_split(const void* x, int x_pix_stride, int x_c_off, int Cin3, const void* w_packed, int Cout,
+                              const float* bias, int B, int H, int W, void* out, int out_pix_stride, int out_c_off,
+                              int part_stride, void* stream) {
+    B2_CHECK_ARG(Cin3 % 192 == 0 && part_stride >= Cout && H % C3_TILE_H == 0 && W % C3_TILE_W == 0);
+    return run_conv3(1, x, x_pix_stride, x_c_off, Cin3, w_packed, 4 * Cout, B, H, W, out, out_pix_stride, out_c_off,
+                     nullptr, bias, 0, nullptr, 0, Cout, static_cast<cudaStream_t>(stream), nullptr, 0, 0, part_stride);
+}
+
+int b200sr_conv1_fwd_split(const float* x, const float* w, const float* col_scale, const float* col_shift, int relu,
+                           void* out, int B, int H, int W, void* stream) {
+    B2_CHECK_ARG(x && w && col_scale && col_shift && out && B > 0 && H > 0 && W > 0 && aligned16(out));
+    const long long total = static_cast<long long>(B) * H * W * 8;
+    conv1_split_fwd_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        x, w, col_scale, col_shift, relu, static_cast<__nv_bfloat16*>(out), H, W, total);
+    return check_launch("conv1_split_fwd_kernel");
+}
+
+int b200sr_maxpool2x2_fwd_split(const void* in, int in_pix_stride, int in_c_off, int in_part_stride, int C, void* out,
+                                int B, int H, int W, void* stream) {
+    B2_CHECK_ARG(in && out && C % 8 == 0 && in_pix_stride % 8 == 0 && in_c_off % 8 == 0 && in_part_stride % 8 == 0);
+    B2_CHECK_ARG(H % 2 == 0 && W % 2 == 0 && aligned16(in) && aligned16(out));
+    const long long total = static_cast<long long>(B) * (H / 2) * (W / 2) * (C / 8);
+    maxpool2x2_split_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16*>(in), in_pix_stride, in_c_off, in_part_stride, C,
+        static_cast<__nv_bfloat16*>(out), H, W, total);
+    return check_launch("maxpool2x2_split_kernel");
+}
+
+int b200sr_head_fwd_split(const void* act, const float* w, const float* b, float* out, int64_t npix, void* stream) {
+    B2_CHECK_ARG(act && w && b && out && npix > 0 && aligned16(act) && aligned16(w));
+    head_split_fwd_kernel<<<grid_for(npix * 8, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16*>(act), w, b, out, npix);
+    return check_launch("head_split_fwd_kernel");
 }
 
 // ---- DeepCNN residual baseline -------------------------------------------------------------

@@ -48,6 +48,8 @@ struct Conv3Args {
     const __nv_bfloat16* mask;
     int mask_pix_stride;
     int mask_c_off;
+    // SPLIT epilogue (fp32-accuracy eval mode, see below): channel distance between the [hi | lo | hi] parts of the output
+    int split_stride;
 };
 
 #ifndef C3_HAS_MASK
@@ -60,14 +62,15 @@ constexpr int C3_TILE_W = 8;
 constexpr int C3_A_SLOT = (C3_TILE_H + 2) * C3_TILE_W * 128;  // 18432 B: 18 pixel rows x 8 pixels x 64 ch bf16
 constexpr int C3_OUT_STAGE = C3_TILE_H * C3_TILE_W * 128;     // 16384 B: 128 pixels x 64 ch bf16
 
-template <int BLOCK_N>
+template <int BLOCK_N, bool SPLIT = false>
 struct C3Cfg {
     static constexpr int BN_SLOT = BLOCK_N < 128 ? BLOCK_N : 128;  // columns per weight slot = UMMA N
     static constexpr int NH = BLOCK_N / BN_SLOT;
     static constexpr int B_SLOT = BN_SLOT * 128;
     static constexpr int SA = 3;
-    static constexpr int SB = BLOCK_N == 64 ? 18 : 8;   // 18 x 8 KB holds every weight of a Cout=64 layer (K <= 1152)
-    static constexpr int NBUF = BLOCK_N == 64 ? 1 : 2;  // output staging buffers (128 pixels x 64 ch) for TMA stores
+    // 18 x 8 KB holds every weight of a Cout=64 layer (K <= 1152); the SPLIT epilogue needs a second staging buffer instead
+    static constexpr int SB = (BLOCK_N == 64 && !SPLIT) ? 18 : 8;
+    static constexpr int NBUF = (BLOCK_N == 64 && !SPLIT) ? 1 : 2;  // output staging buffers (128 pixels x 64 ch)
     static constexpr int STAGING = NBUF * C3_OUT_STAGE;
     static constexpr int RING_BYTES = SA * C3_A_SLOT + SB * B_SLOT;
     static constexpr int SMEM_BYTES =
@@ -79,12 +82,20 @@ struct C3Cfg {
 //         (unet_model.py:67-76; writes straight into the concat slot, which replaces torch.cat at :101-113)
 // MODE 2: ConvTranspose2d k2 s2 dgrad: four taps (i,j), each gathered through the 5-D view (c, j, w, i, b*H+h)
 // MODE 3: Conv2d 1x1 forward / dgrad (DeepCNN downsample branch, ModelLoader.py:347-351): one tap, plain NHWC store
-template <int BLOCK_N, int MODE_T>
+//
+// SPLIT (MODE 0 / 1 only): fp32-accuracy inference on the bf16 tensor cores (BASELINE configs[0] is an fp32 forward,
+// tolerance 1e-4). An fp32 activation v is stored as THREE bf16 channel groups [hi | lo | hi], hi = bf16(v),
+// lo = bf16(v - hi); the weights are packed as [w_hi | w_hi | w_lo] along K (b200sr_pack_jobs kinds 11 / 12), so the
+// ordinary main loop over K' = 3*Cin accumulates a_hi*w_hi + a_lo*w_hi + a_hi*w_lo in fp32 (the dropped lo*lo term is
+// 2^-18 relative). Only the epilogue differs: the fp32 result (after the fp32 affine / ReLU) is split again and the
+// three parts are stored at channel offsets 0, split_stride, 2*split_stride of the output slot.
+template <int BLOCK_N, int MODE_T, bool SPLIT = false>
 __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_kernel(const __grid_constant__ CUtensorMap map_a,
                                                                 const __grid_constant__ CUtensorMap map_b,
                                                                 const __grid_constant__ CUtensorMap map_out,
                                                                 const Conv3Args args) {
-    using Cfg = C3Cfg<BLOCK_N>;
+    using Cfg = C3Cfg<BLOCK_N, SPLIT>;
+    static_assert(!SPLIT || MODE_T == 0 || MODE_T == 1, "SPLIT epilogue exists for conv3x3 forward and ConvT forward");
     constexpr int SB = Cfg::SB, NH = Cfg::NH, BN_SLOT = Cfg::BN_SLOT;
     const int SA = args.sa;
     // MODE 4 = MODE 0 (3x3 conv / dgrad) + the ReLU-mask epilogue: a separate instantiation, so the kernels of the UNet
@@ -292,6 +303,70 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_kernel(const __grid_con
             const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BLOCK_N;
 #pragma unroll
             for (int grp = 0; grp < BLOCK_N / 64; ++grp) {
+                if (SPLIT) {
+                    // both staging buffers per group: [0] = hi, [1] = lo; the previous group's stores must have been read
+                    if (issuer) tma_store_wait_read<0>();
+                    named_bar_sync(2, 128);
+#pragma unroll
+                    for (int half = 0; half < 2; ++half) {
+                        const int chunk = grp * 2 + half;
+                        uint32_t raw[32];
+                        tmem_ld32(t_addr + chunk * 32, raw);
+                        tmem_ld_wait();
+                        float v[32];
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
+                        if (affine) {
+#pragma unroll
+                            for (int i = 0; i < 32; i += 4) {
+                                const float4 sc = *reinterpret_cast<const float4*>(s_scale + chunk * 32 + i);
+                                const float4 sh = *reinterpret_cast<const float4*>(s_shift + chunk * 32 + i);
+                                v[i] = fmaf(v[i], sc.x, sh.x);
+                                v[i + 1] = fmaf(v[i + 1], sc.y, sh.y);
+                                v[i + 2] = fmaf(v[i + 2], sc.z, sh.z);
+                                v[i + 3] = fmaf(v[i + 3], sc.w, sh.w);
+                            }
+                        }
+                        if (args.relu) {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+                        }
+                        uint32_t phi[16], plo[16];
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            const __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+                            phi[i] = *reinterpret_cast<const uint32_t*>(&h2);
+                            plo[i] = pack_bf16x2(v[2 * i] - __low2float(h2), v[2 * i + 1] - __high2float(h2));
+                        }
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const uint32_t off = row_off + (((static_cast<uint32_t>(half * 4 + i)) ^ row_xor) << 4);
+                            *reinterpret_cast<uint4*>(out_stage + off) =
+                                make_uint4(phi[4 * i], phi[4 * i + 1], phi[4 * i + 2], phi[4 * i + 3]);
+                            *reinterpret_cast<uint4*>(out_stage + C3_OUT_STAGE + off) =
+                                make_uint4(plo[4 * i], plo[4 * i + 1], plo[4 * i + 2], plo[4 * i + 3]);
+                        }
+                    }
+                    fence_proxy_async_smem();
+                    named_bar_sync(1, 128);
+                    if (issuer) {
+                        const int col0 = n0 + grp * 64;
+                        const int S = args.split_stride;
+                        if (MODE == 1) {
+                            const int ij = col0 / args.cout_t;
+                            const int co = col0 - ij * args.cout_t;
+                            tma_store_5d(&map_out, out_stage, co, ij & 1, w0, ij >> 1, img * args.H + h0);
+                            tma_store_5d(&map_out, out_stage + C3_OUT_STAGE, co + S, ij & 1, w0, ij >> 1, img * args.H + h0);
+                            tma_store_5d(&map_out, out_stage, co + 2 * S, ij & 1, w0, ij >> 1, img * args.H + h0);
+                        } else {
+                            tma_store_4d(&map_out, out_stage, col0, w0, h0, img);
+                            tma_store_4d(&map_out, out_stage + C3_OUT_STAGE, col0 + S, w0, h0, img);
+                            tma_store_4d(&map_out, out_stage, col0 + 2 * S, w0, h0, img);
+                        }
+                        tma_store_commit();
+                    }
+                    continue;
+                }
                 uint8_t* stage = out_stage + sbuf * C3_OUT_STAGE;
                 if (Cfg::NBUF == 1) {
                     // single staging buffer: the previous store must have finished reading it before it is rewritten

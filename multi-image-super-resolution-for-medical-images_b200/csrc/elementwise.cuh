@@ -60,7 +60,15 @@ enum PackKind : int {
     UNPACK_CONV1X1_WGRAD = 8,  // G[ci][co] f32 -> (Cout,Cin,1,1) f32
     PACK_CONV_BOTH = 9,    // kinds 0 and 1 from ONE read of the parameter tile: dst = forward, aux = dgrad packing
     PACK_CONVT_BOTH = 10,  // kinds 2 and 3 likewise
+    // fp32-accuracy eval mode (conv3x3.cuh, SPLIT): each weight as [w_hi | w_hi | w_lo] along K, matching [a_hi | a_lo | a_hi]
+    PACK_CONV_FWD_SPLIT3 = 11,   // (Cout,Cin,3,3) f32 -> [Cout][tap*3Cin + part*Cin + ci] bf16
+    PACK_CONVT_FWD_SPLIT3 = 12,  // (Cin,Cout,2,2) f32 -> [(i*2+j)*Cout + co][part*Cin + ci] bf16
 };
+
+__device__ __forceinline__ __nv_bfloat16 split3_part(float w, int part) {
+    const __nv_bfloat16 hi = __float2bfloat16_rn(w);
+    return part == 2 ? __float2bfloat16_rn(w - __bfloat162float(hi)) : hi;
+}
 
 struct PackJob {
     const void* src;
@@ -83,7 +91,7 @@ __global__ void __launch_bounds__(256) pack_jobs_kernel(const PackJob* __restric
     const int Cout = job.cout, Cin = job.cin;
     const bool one = job.kind >= PACK_CONV1X1_FWD && job.kind <= UNPACK_CONV1X1_WGRAD;
     const bool conv = one || job.kind == PACK_CONV_FWD || job.kind == PACK_CONV_DGRAD || job.kind == UNPACK_CONV_WGRAD ||
-                      job.kind == PACK_CONV_BOTH;
+                      job.kind == PACK_CONV_BOTH || job.kind == PACK_CONV_FWD_SPLIT3;
     const int T = one ? 1 : (conv ? 9 : 4);
     const int outer_total = conv ? Cout : Cin, inner_total = conv ? Cin : Cout;
     const int tiles_in = inner_total / PK_TILE;
@@ -156,6 +164,30 @@ __global__ void __launch_bounds__(256) pack_jobs_kernel(const PackJob* __restric
                     const int i = idx % PK_TILE, t = (idx / PK_TILE) % 4, o = idx / (PK_TILE * 4);
                     aux[static_cast<long long>(o0 + o) * (4LL * Cout) + t * Cout + i0 + i] =
                         __float2bfloat16_rn(tile[o][i * 4 + t]);
+                }
+                break;
+            }
+            case PACK_CONV_FWD_SPLIT3: {  // dst[co][t*3Cin + part*Cin + ci]
+                __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(job.dst);
+                for (int idx = tid; idx < PK_TILE * row; idx += 256) {
+                    const int i = idx % PK_TILE, t = (idx / PK_TILE) % 9, o = idx / (PK_TILE * 9);
+                    const float w = tile[o][i * 9 + t];
+#pragma unroll
+                    for (int part = 0; part < 3; ++part)
+                        dst[static_cast<long long>(o0 + o) * (27LL * Cin) + (t * 3 + part) * Cin + i0 + i] =
+                            split3_part(w, part);
+                }
+                break;
+            }
+            case PACK_CONVT_FWD_SPLIT3: {  // dst[(t*Cout + co)][part*Cin + ci], outer = ci, inner = co
+                __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(job.dst);
+                for (int idx = tid; idx < PK_TILE * row; idx += 256) {
+                    const int o = idx % PK_TILE, t = (idx / PK_TILE) % 4, i = idx / (PK_TILE * 4);
+                    const float w = tile[o][i * 4 + t];
+#pragma unroll
+                    for (int part = 0; part < 3; ++part)
+                        dst[(static_cast<long long>(t) * Cout + i0 + i) * (3LL * Cin) + part * Cin + o0 + o] =
+                            split3_part(w, part);
                 }
                 break;
             }
@@ -252,6 +284,46 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __res
 #pragma unroll
         for (int l = 0; l < 8; ++l) t += s_p[l][col];
         out[(i % inner) * stride_mod + (i / inner) * stride_div] = t * scale;
+    }
+}
+
+// In-place first stage of a split-K reduction: parts[0][i] = sum_p parts[p][i] (p ascending) for float4 columns i < n4.
+// Fully parallel over the elements AND (for many parts) over `lanes` part-lanes (lane l sums parts l, l+lanes, ...; the
+// lanes are then combined in lane order): the summation order is fixed by (nparts, lanes) alone. A thread reads every part
+// of its own column before it overwrites part 0, so reducing in place is safe.
+__global__ void __launch_bounds__(256) reduce_splits_inplace_kernel(float4* __restrict__ parts, int nparts,
+                                                                    long long part_stride4, long long n4, int lanes) {
+    __shared__ float4 s_p[256];
+    const int cols = 256 / lanes;
+    const int col = threadIdx.x % cols, pl = threadIdx.x / cols;
+    const long long i = static_cast<long long>(blockIdx.x) * cols + col;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i < n4) {
+#pragma unroll 4
+        for (int p = pl; p < nparts; p += lanes) {
+            const float4 v = __ldcs(parts + static_cast<long long>(p) * part_stride4 + i);
+            acc.x += v.x;
+            acc.y += v.y;
+            acc.z += v.z;
+            acc.w += v.w;
+        }
+    }
+    if (lanes == 1) {
+        if (i < n4) parts[i] = acc;
+        return;
+    }
+    s_p[threadIdx.x] = acc;
+    __syncthreads();
+    if (pl == 0 && i < n4) {
+        float4 t = s_p[col];
+        for (int l = 1; l < lanes; ++l) {
+            const float4 v = s_p[l * cols + col];
+            t.x += v.x;
+            t.y += v.y;
+            t.z += v.z;
+            t.w += v.w;
+        }
+        parts[i] = t;
     }
 }
 
@@ -1251,6 +1323,120 @@ __global__ void __launch_bounds__(256) head_bwd_det_kernel(const float* __restri
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// fp32-accuracy eval mode: the bandwidth kernels around the SPLIT tensor-core convolutions (conv3x3.cuh). Activations
+// are (B,H,W,3C) bf16 [hi | lo | hi] with hi + lo the fp32 value to 2^-17 relative.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void st_split3(__nv_bfloat16* p, int part_stride, const F8& v) {
+    F8 hi, lo;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        hi.v[k] = bf16_round(v.v[k]);
+        lo.v[k] = v.v[k] - hi.v[k];
+    }
+    st_bf16x8(p, hi);
+    st_bf16x8(p + part_stride, lo);
+    st_bf16x8(p + 2 * part_stride, hi);
+}
+
+// First layer Conv2d(2,64,3,p=1) + folded BatchNorm + ReLU in plain fp32 FMAs (0.15 GFLOP per sample: CUDA cores are
+// plenty), input fp32 NCHW, output split (B,H,W,192). One thread = one pixel x 8 output channels.
+__global__ void __launch_bounds__(256) conv1_split_fwd_kernel(const float* __restrict__ x, const float* __restrict__ wgt,
+                                                              const float* __restrict__ scale,
+                                                              const float* __restrict__ shift, int relu,
+                                                              __nv_bfloat16* __restrict__ out, int H, int W,
+                                                              long long total /* B*H*W*8 */) {
+    __shared__ float s_w[18][64];
+    for (int i = threadIdx.x; i < 18 * 64; i += 256) s_w[i % 18][i / 18] = wgt[i];  // wgt[co][ci][3][3] -> [k][co]
+    __syncthreads();
+    for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+         idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int c8 = static_cast<int>(idx & 7);
+        long long p = idx >> 3;
+        const int w = static_cast<int>(p % W);
+        p /= W;
+        const int h = static_cast<int>(p % H);
+        const long long img = p / H;
+        float acc[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+#pragma unroll
+        for (int ci = 0; ci < 2; ++ci)
+#pragma unroll
+            for (int t = 0; t < 9; ++t) {
+                const int hh = h + t / 3 - 1, ww = w + t % 3 - 1;
+                const float v = (hh >= 0 && hh < H && ww >= 0 && ww < W) ? __ldg(x + ((img * 2 + ci) * H + hh) * W + ww) : 0.f;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) acc[k] = fmaf(v, s_w[ci * 9 + t][c8 * 8 + k], acc[k]);
+            }
+        F8 r;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            float v = fmaf(acc[k], scale[c8 * 8 + k], shift[c8 * 8 + k]);
+            r.v[k] = relu ? fmaxf(v, 0.f) : v;
+        }
+        st_split3(out + ((img * H + h) * W + w) * 192 + c8 * 8, 64, r);
+    }
+}
+
+// MaxPool2d(2,2) on a split slot: compares hi + lo, copies the winner's pair. in: channel slot of a (.., in_stride)
+// buffer whose parts are in_part apart; out: dense (B,H/2,W/2,3C).
+__global__ void __launch_bounds__(256) maxpool2x2_split_kernel(const __nv_bfloat16* __restrict__ in, int in_stride,
+                                                               int in_coff, int in_part, int C,
+                                                               __nv_bfloat16* __restrict__ out, int H, int W,
+                                                               long long total) {
+    const int c8n = C >> 3;
+    const int W2 = W >> 1, H2 = H >> 1;
+    for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+         idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int c = static_cast<int>(idx % c8n) * 8;
+        long long r = idx / c8n;
+        const int w2 = static_cast<int>(r % W2);
+        r /= W2;
+        const int h2 = static_cast<int>(r % H2);
+        const long long img = r / H2;
+        const long long p00 = (img * H + 2 * h2) * W + 2 * w2;
+        const long long pix[4] = {p00, p00 + 1, p00 + W, p00 + W + 1};
+        F8 bh, bl;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const __nv_bfloat16* q = in + pix[j] * in_stride + in_coff + c;
+            const F8 hi = ld_bf16x8(q), lo = ld_bf16x8(q + in_part);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                if (j == 0 || hi.v[k] + lo.v[k] > bh.v[k] + bl.v[k]) {
+                    bh.v[k] = hi.v[k];
+                    bl.v[k] = lo.v[k];
+                }
+            }
+        }
+        __nv_bfloat16* o = out + ((img * H2 + h2) * W2 + w2) * (3 * C) + c;
+        st_bf16x8(o, bh);
+        st_bf16x8(o + C, bl);
+        st_bf16x8(o + 2 * C, bh);
+    }
+}
+
+// 1x1 head on a split (B,H,W,192) activation: out = b + sum_c (hi + lo)[c] * w[c], fp32.
+__global__ void __launch_bounds__(256) head_split_fwd_kernel(const __nv_bfloat16* __restrict__ act,
+                                                             const float* __restrict__ w, const float* __restrict__ b,
+                                                             float* __restrict__ out, long long npix) {
+    const int sub = threadIdx.x & 7;
+    const F8 wv = ld_f32x8(w + sub * 8);
+    const float bias = b[0];
+    for (long long p = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 3; p < npix;
+         p += (static_cast<long long>(gridDim.x) * blockDim.x) >> 3) {
+        const F8 hi = ld_bf16x8(act + p * 192 + sub * 8), lo = ld_bf16x8(act + p * 192 + 64 + sub * 8);
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s = fmaf(hi.v[k] + lo.v[k], wv.v[k], s);
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        s += __shfl_xor_sync(0xffffffffu, s, 4);
+        if (sub == 0) out[p] = s + bias;
+    }
+}
 
 // ------------------------------------------------------------------------------------------------
 // layout casts at the boundary (used by the per-op tests and by users feeding intermediate tensors)

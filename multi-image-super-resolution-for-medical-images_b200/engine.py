@@ -26,6 +26,7 @@ BN_MOMENTUM = 0.1
 
 PACK_CONV_FWD, PACK_CONV_DGRAD, PACK_CONVT_FWD, PACK_CONVT_DGRAD, UNPACK_CONV_WGRAD, UNPACK_CONVT_WGRAD = range(6)
 PACK_CONV_BOTH, PACK_CONVT_BOTH = 9, 10  # forward + dgrad packing from one read of the parameter
+PACK_CONV_FWD_SPLIT3, PACK_CONVT_FWD_SPLIT3 = 11, 12  # bf16x3 operand split of the fp32-accuracy eval mode
 
 _PACK_JOB_DTYPE = np.dtype([("src", "<u8"), ("dst", "<u8"), ("kind", "<i4"), ("cout", "<i4"), ("cin", "<i4"),
                             ("pad", "<i4"), ("count", "<i8")])
@@ -347,27 +348,33 @@ class UNetEngine:
             raise _lib.B200SRError("b200sr UNet runs on CUDA sm_100a only; there is no CPU path")
         return x.contiguous().float()
 
-    def forward_eval(self, x):
-        """Eval-mode forward. From the third call with a given input shape the ~30 launches are replayed from a CUDA
-        graph (small inference batches are launch-latency bound between dependent kernels): the input is copied into
-        the graph's static buffer and the result is returned as a fresh tensor. B200SR_NO_EVAL_GRAPH=1 disables it."""
+    def forward_eval(self, x, precision="bf16"):
+        """Eval-mode forward. precision 'bf16' (default): bf16 operands / activations, fp32 accumulation. precision
+        'fp32': the reference's inference arithmetic (an fp32 forward, VolumeVisualization.py:932-964) to rel-L2 <= 1e-4 on
+        the same tensor-core kernels through bf16x3 operand splitting (csrc/conv3x3.cuh SPLIT; 3x the tensor work).
+        From the third call with a given input shape the ~30 launches are replayed from a CUDA graph (small inference
+        batches are launch-latency bound between dependent kernels): the input is copied into the graph's static buffer
+        and the result is returned as a fresh tensor. B200SR_NO_EVAL_GRAPH=1 disables it."""
+        if precision not in ("bf16", "fp32"):
+            raise ValueError(f"Unknown precision: {precision}. Choose from: ['bf16', 'fp32']")
         x = self._check_input(x)
         self.ensure_ready(x.device)
-        self._refresh_eval_weights()
+        self._refresh_eval_weights(precision)
+        launch = self._forward_eval_launch if precision == "bf16" else self._forward_eval_launch_fp32
         if not self.eval_graphs or torch.cuda.is_current_stream_capturing():
-            return self._forward_eval_launch(x)
-        key = (tuple(x.shape), x.device)
+            return launch(x)
+        key = (tuple(x.shape), x.device, precision)
         g = self._eval_graph_cache.get(key)
         if g is None:
             n = self._eval_graph_calls.get(key, 0)
             self._eval_graph_calls[key] = n + 1
             if n < 2:  # lazy one-time set-up (plan buffers, TMA descriptors, kernel attributes) happens eagerly
-                return self._forward_eval_launch(x)
+                return launch(x)
             static_x = x.clone()
             torch.cuda.synchronize()
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
-                static_out = self._forward_eval_launch(static_x)
+                static_out = launch(static_x)
             g = (graph, static_x, static_out)
             self._eval_graph_cache[key] = g
         graph, static_x, static_out = g
@@ -375,13 +382,109 @@ class UNetEngine:
         graph.replay()
         return static_out.clone()
 
-    def _refresh_eval_weights(self):
+    def _refresh_eval_weights(self, precision="bf16"):
         """Eval-mode derived state (packed bf16 weights, folded BatchNorm) follows the parameters / buffers."""
         ver = self._state_version()
         if ver != self._eval_version:
             self.repack_weights()
             call("b200sr_bn_fold_eval", self.fold_jobs.data_ptr(), len(self.convs), BN_EPS, _lib.current_stream_ptr())
             self._eval_version = ver
+        if precision == "fp32" and ver != getattr(self, "_eval_version_fp32", None):
+            self._pack_split_weights()
+            self._eval_version_fp32 = ver
+
+    def _pack_split_weights(self):
+        """[w_hi | w_hi | w_lo] packings of every tensor-core layer for the fp32-accuracy eval mode (built on first use)."""
+        if getattr(self, "_wp32_for", None) != self.flat_p.data_ptr():
+            total, self.wp32 = 0, {}
+            for cs in self.convs[1:]:
+                self.wp32[cs.name] = total
+                total += _align(3 * cs.cout * cs.cin * 9)
+            for us in self.ups.values():
+                self.wp32[us.name] = total
+                total += _align(3 * us.cin * us.cout * 4)
+            self.flat_wp32 = torch.zeros(total, dtype=torch.bfloat16, device=self.device)
+            jobs = np.zeros(len(self.convs) - 1 + len(self.ups), dtype=_PACK_JOB_DTYPE)
+            base = self.flat_wp32.data_ptr()
+            i = 0
+            for cs in self.convs[1:]:
+                w = cs.conv.weight
+                jobs[i] = (w.data_ptr(), base + 2 * self.wp32[cs.name], PACK_CONV_FWD_SPLIT3, cs.cout, cs.cin, 0, 3 * w.numel())
+                i += 1
+            for us in self.ups.values():
+                w = us.mod.weight
+                jobs[i] = (w.data_ptr(), base + 2 * self.wp32[us.name], PACK_CONVT_FWD_SPLIT3, us.cout, us.cin, 0,
+                           3 * w.numel())
+                i += 1
+            self.pack32_jobs, self.n_pack32 = _jobs_to_device(jobs, self.device), len(jobs)
+            self._wp32_for = self.flat_p.data_ptr()
+        call("b200sr_pack_jobs", self.pack32_jobs.data_ptr(), self.n_pack32, _lib.current_stream_ptr())
+
+    def _forward_eval_launch_fp32(self, x):
+        """The eval forward with every activation stored as (B,H,W,3C) bf16 [hi | lo | hi] and every weight as
+        [w_hi | w_hi | w_lo]: fp32 accuracy (2^-17 operands, fp32 accumulation, fp32 BatchNorm fold) on the bf16 tensor
+        cores. Decoder concat buffers hold 2C logical channels, i.e. parts 2C apart; ConvTranspose writes [0,C) of each
+        part, the encoder skip writes [C,2C)."""
+        B, _, H, W = x.shape
+        key = (B, H, W, "fp32")
+        plan = self._plans.get(key)
+        ch = self.chans
+        if plan is None:
+            if H % 256 != 0 or W % 128 != 0:
+                raise _lib.B200SRError(f"b200sr UNet fp32 eval mode needs H % 256 == 0 and W % 128 == 0 (got {H}x{W})")
+            bf, dev = torch.bfloat16, self.device
+            plan = {}
+            for lvl in range(5):
+                h, w, c = H >> lvl, W >> lvl, ch[lvl]
+                if lvl < 4:
+                    plan[f"cat{lvl}"] = torch.empty((B, h, w, 6 * c), dtype=bf, device=dev)
+                    plan[f"pool{lvl}"] = torch.empty((B, h // 2, w // 2, 3 * c), dtype=bf, device=dev)
+                    for k in ("enc_a1", "dec_a1", "dec_a2"):
+                        plan[f"{k}_{lvl}"] = torch.empty((B, h, w, 3 * c), dtype=bf, device=dev)
+                else:
+                    plan["bot_a1"] = torch.empty((B, h, w, 3 * c), dtype=bf, device=dev)
+                    plan["bot_a2"] = torch.empty((B, h, w, 3 * c), dtype=bf, device=dev)
+            self._plans[key] = plan
+        st = _lib.current_stream_ptr()
+        wbase = self.flat_wp32.data_ptr()
+
+        def conv(cs, src, s_stride, cin_logical, dst, d_stride, d_off, part, h, w):
+            call("b200sr_conv3x3_fwd_split", ptr(src), s_stride, 0, 3 * cin_logical, wbase + 2 * self.wp32[cs.name],
+                 cs.cout, B, h, w, ptr(dst), d_stride, d_off, part, self._bn(cs, "escale"), self._bn(cs, "eshift"), 1, st)
+
+        cur = None
+        for lvl, name in enumerate(["enc1", "enc2", "enc3", "enc4"]):
+            c1, c2 = self.blocks[name]
+            h, w, c = H >> lvl, W >> lvl, ch[lvl]
+            a1, cat, pool = plan[f"enc_a1_{lvl}"], plan[f"cat{lvl}"], plan[f"pool{lvl}"]
+            if lvl == 0:
+                call("b200sr_conv1_fwd_split", ptr(x), ptr(c1.conv.weight), self._bn(c1, "escale"), self._bn(c1, "eshift"),
+                     1, ptr(a1), B, h, w, st)
+            else:
+                conv(c1, cur, 3 * c1.cin, c1.cin, a1, 3 * c, 0, c, h, w)
+            conv(c2, a1, 3 * c, c, cat, 6 * c, c, 2 * c, h, w)
+            call("b200sr_maxpool2x2_fwd_split", ptr(cat), 6 * c, c, 2 * c, c, ptr(pool), B, h, w, st)
+            cur = pool
+        c1, c2 = self.blocks["bottleneck"]
+        h, w, c = H >> 4, W >> 4, ch[4]
+        conv(c1, cur, 3 * c1.cin, c1.cin, plan["bot_a1"], 3 * c, 0, c, h, w)
+        conv(c2, plan["bot_a1"], 3 * c, c, plan["bot_a2"], 3 * c, 0, c, h, w)
+        cur = plan["bot_a2"]
+        for k in (4, 3, 2, 1):
+            us = self.ups[k]
+            lvl = us.level
+            h, w, c = H >> lvl, W >> lvl, ch[lvl]
+            cat = plan[f"cat{lvl}"]
+            call("b200sr_convT2x2_fwd_split", ptr(cur), 3 * us.cin, 0, 3 * us.cin, wbase + 2 * self.wp32[us.name], us.cout,
+                 ptr(us.mod.bias), B, h // 2, w // 2, ptr(cat), 6 * c, 0, 2 * c, st)
+            c1, c2 = self.blocks[f"dec{k}"]
+            conv(c1, cat, 6 * c, 2 * c, plan[f"dec_a1_{lvl}"], 3 * c, 0, c, h, w)
+            conv(c2, plan[f"dec_a1_{lvl}"], 3 * c, c, plan[f"dec_a2_{lvl}"], 3 * c, 0, c, h, w)
+            cur = plan[f"dec_a2_{lvl}"]
+        fc = self.head
+        out = torch.empty((B, 1, H, W), dtype=torch.float32, device=x.device)
+        call("b200sr_head_fwd_split", ptr(cur), ptr(fc.weight), ptr(fc.bias), ptr(out), B * H * W, st)
+        return out
 
     def _forward_eval_launch(self, x):
         B, _, H, W = x.shape

@@ -9,6 +9,7 @@ through the C ABI in include/b200sr.h. There is no torch/cuDNN fallback on that 
 from __future__ import annotations
 
 import json
+import os
 from pathlib import Path
 
 import numpy as np
@@ -74,6 +75,10 @@ class UNet(nn.Module):
         super().__init__()
         features = init_features
         self.in_channels, self.out_channels, self.init_features = in_channels, out_channels, init_features
+        # arithmetic of the eval-mode forward: 'bf16' (bf16 operands, fp32 accumulation; rel-L2 ~3e-3 vs the fp32 reference)
+        # or 'fp32' (bf16x3 operand splitting on the same tensor-core kernels; rel-L2 <= 1e-4, ~3x the tensor work).
+        # Not a parameter / buffer: state_dict stays the reference's. Training always runs the bf16 path.
+        self.eval_precision = os.environ.get("B200SR_EVAL_PRECISION", "bf16")
 
         self.enc1 = UNetBlock(in_channels, features)
         self.pool1 = nn.MaxPool2d(kernel_size=2, stride=2)
@@ -135,7 +140,14 @@ class UNet(nn.Module):
             if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
                 return _UNetFunction.apply(self, x, *self.parameters())
             return engine.forward_train(x)
-        return engine.forward_eval(x)
+        return engine.forward_eval(x, precision=self.eval_precision)
+
+    def set_eval_precision(self, precision):
+        """'bf16' or 'fp32' (see __init__); returns self so it chains like .eval()."""
+        if precision not in ("bf16", "fp32"):
+            raise ValueError(f"Unknown precision: {precision}. Choose from: ['bf16', 'fp32']")
+        self.eval_precision = precision
+        return self
 
 
 class MRIDataset(Dataset):

@@ -77,13 +77,20 @@ def train_entry(ref_loader, sd, case, loss_name):
           f"grads {pin:.1e}")
     assert rel(o_out, o32) < 1e-5 and pin < 1e-3
     grads = {}
+    adam_w, adam_cos = 0.0, 1.0   # weights after ONE Adam step (lr 1e-4) from the bf16 gradients vs from the fp32 ones
     for k in g32:
         if g32[k].norm() <= 1e-6:   # conv bias in front of a BatchNorm: true gradient 0
             continue
         grads[k] = [rel(g16[k], g32[k]), cos(g16[k], g32[k])]
+        p0 = sd[k].double()
+        p32, _, _ = unet_oracle.adam_update(p0, g32[k].double(), 0.0, 0.0, 1)
+        p16, _, _ = unet_oracle.adam_update(p0, g16[k].double(), 0.0, 0.0, 1)
+        adam_w = max(adam_w, rel(p16, p32))
+        adam_cos = min(adam_cos, cos(p16 - p0, p32 - p0))
     return {"B": case["B"], "H": case["H"], "W": case["W"], "seed": case["seed"], "loss_fn": loss_name,
             "loss_fp32": l32, "loss": abs(l16 - l32) / abs(l32), "out": rel(o16, o32),
-            "running_stats": max(rel(s16[k], s32[k]) for k in s32), "grads": grads}
+            "running_stats": max(rel(s16[k], s32[k]) for k in s32), "grads": grads,
+            "post_adam_weights": adam_w, "adam_update_cos": adam_cos}
 
 
 def eval_entry(ref_loader, sd, case):

@@ -793,6 +793,105 @@ def sum_slots(n=96, slots=SLOTS, stride=256, seed=91):
     return {"sum": rel(out, a[:, :n].double().sum(0))}
 
 
+# ------------------------------------------------------------------------------------------------------
+# fp32-accuracy eval mode (bf16x3 operand split): fp32 inputs / weights, compared with fp32 torch ops (TF32 off) at 1e-4,
+# the north-star fp32/tf32 tolerance (measured ~1e-6)
+# ------------------------------------------------------------------------------------------------------
+def split3(x_nchw, total_c=None, c_off=0):
+    """(B,C,H,W) fp32 -> (B,H,W,3*T) bf16 [hi | lo | hi] with the C channels at offset c_off inside every T-channel part."""
+    x = x_nchw.permute(0, 2, 3, 1).contiguous()
+    B, H, W, C = x.shape
+    T = total_c or C
+    hi = x.to(torch.bfloat16)
+    lo = (x - hi.float()).to(torch.bfloat16)
+    buf = torch.full((B, H, W, 3 * T), 7.0, dtype=torch.bfloat16, device=DEV)
+    for p, part in enumerate((hi, lo, hi)):
+        buf[..., p * T + c_off:p * T + c_off + C] = part
+    return buf
+
+
+def unsplit3(buf, C, total_c=None, c_off=0):
+    T = total_c or C
+    hi = buf[..., c_off:c_off + C].float()
+    lo = buf[..., T + c_off:T + c_off + C].float()
+    hi2 = buf[..., 2 * T + c_off:2 * T + c_off + C].float()
+    return (hi + lo).permute(0, 3, 1, 2).contiguous(), float((hi - hi2).abs().max())
+
+
+def conv3x3_fwd_split(B=2, H=32, W=32, Cin=64, Cout=128, seed=81, slot=False):
+    _setup()
+    x = rnd(B, Cin, H, W, seed=seed)
+    w = rnd(Cout, Cin, 3, 3, seed=seed + 1, scale=(9 * Cin) ** -0.5)
+    scale, shift = 1.0 + 0.1 * rnd(Cout, seed=seed + 2), 0.1 * rnd(Cout, seed=seed + 3)
+    ref = torch.relu(F.conv2d(x, w, padding=1) * scale[None, :, None, None] + shift[None, :, None, None])
+    wp = torch.zeros(3 * w.numel(), dtype=torch.bfloat16, device=DEV)
+    job = np.zeros(1, dtype=_PACK_JOB_DTYPE)
+    job[0] = (w.data_ptr(), wp.data_ptr(), 11, Cout, Cin, 0, wp.numel())
+    call("b200sr_pack_jobs", _jobs_to_device(job, DEV).data_ptr(), 1, st())
+    xb = split3(x)
+    T, off = (2 * Cout, Cout) if slot else (Cout, 0)
+    ob = torch.full((B, H, W, 3 * T), 7.0, dtype=torch.bfloat16, device=DEV)
+    call("b200sr_conv3x3_fwd_split", ptr(xb), 3 * Cin, 0, 3 * Cin, ptr(wp), Cout, B, H, W, ptr(ob), 3 * T, off, T,
+         ptr(scale), ptr(shift), 1, st())
+    torch.cuda.synchronize()
+    out, hi_mismatch = unsplit3(ob, Cout, T, off)
+    res = {"out": rel(out, ref), "hi_copies_equal": hi_mismatch}
+    if slot:
+        res["slot_untouched"] = float((ob[..., :Cout].float() - 7.0).abs().max())
+    return res
+
+
+def convT_fwd_split(B=2, H=16, W=16, Cin=128, Cout=64, seed=82):
+    _setup()
+    x = rnd(B, Cin, H, W, seed=seed)
+    w = rnd(Cin, Cout, 2, 2, seed=seed + 1, scale=Cin ** -0.5)
+    bias = 0.1 * rnd(Cout, seed=seed + 2)
+    ref = F.conv_transpose2d(x, w, bias, stride=2)
+    wp = torch.zeros(3 * w.numel(), dtype=torch.bfloat16, device=DEV)
+    job = np.zeros(1, dtype=_PACK_JOB_DTYPE)
+    job[0] = (w.data_ptr(), wp.data_ptr(), 12, Cout, Cin, 0, wp.numel())
+    call("b200sr_pack_jobs", _jobs_to_device(job, DEV).data_ptr(), 1, st())
+    xb = split3(x)
+    T = 2 * Cout  # decoder concat buffer: the upsampled half goes to [0, Cout) of every part
+    ob = torch.full((B, 2 * H, 2 * W, 3 * T), 7.0, dtype=torch.bfloat16, device=DEV)
+    call("b200sr_convT2x2_fwd_split", ptr(xb), 3 * Cin, 0, 3 * Cin, ptr(wp), Cout, ptr(bias), B, H, W, ptr(ob), 3 * T, 0,
+         T, st())
+    torch.cuda.synchronize()
+    out, hi_mismatch = unsplit3(ob, Cout, T, 0)
+    return {"out": rel(out, ref), "hi_copies_equal": hi_mismatch,
+            "slot_untouched": float((ob[..., Cout:T].float() - 7.0).abs().max())}
+
+
+def split_small_ops(B=2, H=32, W=48, seed=83):
+    """first conv (fp32 FMAs), max-pool and 1x1 head of the fp32-accuracy eval mode."""
+    _setup()
+    x = rnd(B, 2, H, W, seed=seed)
+    w = rnd(64, 2, 3, 3, seed=seed + 1, scale=18 ** -0.5)
+    scale, shift = 1.0 + 0.1 * rnd(64, seed=seed + 2), 0.1 * rnd(64, seed=seed + 3)
+    ref = torch.relu(F.conv2d(x, w, padding=1) * scale[None, :, None, None] + shift[None, :, None, None])
+    ob = torch.zeros(B, H, W, 192, dtype=torch.bfloat16, device=DEV)
+    call("b200sr_conv1_fwd_split", ptr(x), ptr(w), ptr(scale), ptr(shift), 1, ptr(ob), B, H, W, st())
+    torch.cuda.synchronize()
+    a, _ = unsplit3(ob, 64)
+    res = {"conv1": rel(a, ref)}
+    # max-pool of the skip half of a concat buffer
+    v = rnd(B, 64, H, W, seed=seed + 4)
+    cat = split3(v, 128, 64)
+    pb = torch.zeros(B, H // 2, W // 2, 192, dtype=torch.bfloat16, device=DEV)
+    call("b200sr_maxpool2x2_fwd_split", ptr(cat), 3 * 128, 64, 128, 64, ptr(pb), B, H, W, st())
+    torch.cuda.synchronize()
+    pooled, _ = unsplit3(pb, 64)
+    vv, _ = unsplit3(cat, 64, 128, 64)  # the values as stored
+    res["maxpool_exact"] = float((pooled - F.max_pool2d(vv, 2, 2)).abs().max())
+    # head
+    hw, hb = rnd(1, 64, 1, 1, seed=seed + 5, scale=0.125), rnd(1, seed=seed + 6)
+    out = torch.zeros(B, 1, H, W, device=DEV)
+    call("b200sr_head_fwd_split", ptr(split3(v)), ptr(hw), ptr(hb), ptr(out), B * H * W, st())
+    torch.cuda.synchronize()
+    res["head"] = rel(out, F.conv2d(v, hw, hb))
+    return res
+
+
 # name -> (function, kwargs, {metric: tolerance})
 BF16 = 1e-2
 CHECKS = {
@@ -889,6 +988,15 @@ CHECKS = {
     "det_mse_ssim": (mse_ssim_det, {}, {"bitwise": 0.0, "mse_component": 1e-5, "loss_consistent": 1e-6}),
     "det_adam_auto": (adam_auto, {}, {"delta": 1e-3, "m": 1e-5, "v": 1e-4, "step_count": 0}),
     "det_sum_slots": (sum_slots, {}, {"sum": 1e-6}),
+    # fp32-accuracy eval mode (north-star fp32/tf32 tolerance 1e-4)
+    "fp32_conv3x3_split_n128": (conv3x3_fwd_split, {}, {"out": 1e-4, "hi_copies_equal": 0.0}),
+    "fp32_conv3x3_split_n64_slot": (conv3x3_fwd_split, dict(Cin=128, Cout=64, B=3, H=64, W=64, slot=True),
+                                    {"out": 1e-4, "hi_copies_equal": 0.0, "slot_untouched": 0.0}),
+    "fp32_conv3x3_split_deep": (conv3x3_fwd_split, dict(Cin=512, Cout=1024, B=2, H=16, W=16), {"out": 1e-4}),
+    "fp32_conv3x3_split_cat": (conv3x3_fwd_split, dict(Cin=128, Cout=64, B=2, H=32, W=64), {"out": 1e-4}),
+    "fp32_convT_split": (convT_fwd_split, {}, {"out": 1e-4, "hi_copies_equal": 0.0, "slot_untouched": 0.0}),
+    "fp32_convT_split_big": (convT_fwd_split, dict(Cin=1024, Cout=512, B=2, H=16, W=16), {"out": 1e-4}),
+    "fp32_small_ops": (split_small_ops, {}, {"conv1": 1e-5, "maxpool_exact": 0.0, "head": 1e-5}),
 }
 
 

@@ -105,18 +105,26 @@ def _check_train_case(case_key, B, H, W, seed):
         # (a) the Adam kernel on the path's own gradient == torch Adam arithmetic
         p_exp, _, _ = unet_oracle.adam_update(p_before[n].double(), grads[n].double(), 0.0, 0.0, 1)
         worst_plumb = max(worst_plumb, float((p_after.double() - p_exp).abs().max()))
+        if n.endswith("conv.0.bias") or n.endswith("conv.3.bias"):
+            # conv bias in front of a BatchNorm: the true gradient is 0, so the parameter must not move. (The fp32
+            # reference computes ~1e-8 of round-off there, which Adam's g/(|g|+eps) turns into a +-lr/2 random walk; that
+            # artefact is not reproduced.)
+            if not torch.equal(p_after, p_before[n]):
+                fails.append((n, "moved"))
+            continue
         # (b) against the oracle's step (first Adam step = lr * g / (|g| + eps): the sign pattern of the gradient)
         p_ora, _, _ = unet_oracle.adam_update(p_before[n].double(), o_grads[n].double(), 0.0, 0.0, 1)
         worst_w = max(worst_w, rel(p_after, p_ora))
-        if not (n.endswith("conv.0.bias") or n.endswith("conv.3.bias")):
-            upd_cos = min(upd_cos, cos(p_after.double() - p_before[n].double(), p_ora - p_before[n].double()))
+        upd_cos = min(upd_cos, cos(p_after.double() - p_before[n].double(), p_ora - p_before[n].double()))
     report["adam"] = (worst_plumb, worst_w, upd_cos)
     if worst_plumb > 2e-7:
         fails.append(("adam_kernel_vs_torch_formula", worst_plumb))
-    if worst_w > 1e-2:
-        fails.append(("post_adam_weights", worst_w))
-    if upd_cos < 0.6:
-        fails.append(("adam_update_alignment", upd_cos))
+    # the first Adam step is lr * g / (|g| + eps) = +-lr per element: it turns the gradient's sign noise into a weight
+    # difference (1.7 % of a bottleneck weight's rms per flipped sign), so this too is gated by the reference's own bf16 run
+    if worst_w > max(1e-3, 1.5 * cal["post_adam_weights"]):
+        fails.append(("post_adam_weights", worst_w, cal["post_adam_weights"]))
+    if upd_cos < 1.0 - 1.5 * (1.0 - cal["adam_update_cos"]):
+        fails.append(("adam_update_alignment", upd_cos, cal["adam_update_cos"]))
     assert not fails, f"{fails}\nfull report: {report}"
     return report
 
@@ -155,6 +163,33 @@ def test_eval_forward_b8_256_matches_oracle():
     r = rel(outs[0].cpu(), ref)
     assert r <= 1e-2, r
     assert r <= max(1e-2, 1.5 * _calibration("eval_b8")["out"])
+
+
+def test_eval_forward_b8_256_fp32_mode_matches_oracle():
+    """BASELINE configs[0] at the reference's own precision: fp32 forward, north-star tolerance rel-L2 <= 1e-4
+    (bf16x3 operand splitting on the tensor-core kernels, fp32 accumulation and fp32 BatchNorm fold)."""
+    import b200sr
+    from oracle import cases, unet_oracle
+    sd = cases.seeded_state_dict(b200sr.UNet)
+    c = cases.TRAIN_CASE
+    x, y = cases.seeded_batch(c["B"], c["H"], c["W"], c["seed"])
+    _, _, _, new_stats = unet_oracle.loss_and_grads(sd, x, y)
+    sd.update(new_stats)
+    xe, _ = cases.seeded_batch(8, 256, 256, 4321)
+    with torch.no_grad():
+        ref = unet_oracle.unet_forward(sd, xe, training=False)
+    model = b200sr.UNet()
+    model.load_state_dict(sd)
+    model = model.cuda().eval().set_eval_precision("fp32")
+    with torch.no_grad():
+        outs = [model(xe.cuda()) for _ in range(4)]  # eager twice, then CUDA-graph replays
+        model.set_eval_precision("bf16")
+        out_bf16 = model(xe.cuda())
+    torch.cuda.synchronize()
+    assert all(torch.equal(outs[0], o) for o in outs[1:])
+    r = rel(outs[0].cpu(), ref)
+    assert r <= 1e-4, r
+    assert rel(out_bf16.cpu(), ref) <= 1e-2   # switching back leaves the bf16 path intact
 
 
 def test_train_step_is_bit_reproducible():
