@@ -378,6 +378,16 @@ int b200sr_maxpool2x2_fwd_split(const void* in, int in_pix_stride, int in_c_off,
 /* final nn.Conv2d(64,1,1) on a split (B,H,W,192) activation, fp32 output. */
 int b200sr_head_fwd_split(const void* act, const float* w, const float* b, float* out, int64_t npix, void* stream);
 
+/* Evaluation metrics of the reference (compute_metrics, src/VolumeVisualization.py:237-269) on the device: min-max
+ * normalisation by the ORIGINAL volume's range (+1e-8), prediction clipped to [0,1], per-slice SSIM (7x7 uniform window,
+ * sample covariance: the skimage defaults the reference calls) and PSNR (data_range 1), MAE over the volume.
+ * original / predicted / orig_norm / pred_norm: (S,H,W) f32; per_slice: [S][2] = {SSIM, PSNR};
+ * out5 = {ssim_mean, ssim_std, psnr_mean, psnr_std, mae} (population std, like np.std).
+ * ws: 2048 + 4*S*ceil(H/32)*ceil(W/32) doubles; counters: 2 zero-initialised uint32. */
+int b200sr_volume_metrics(const float* original, const float* predicted, int S, int H, int W, float* orig_norm,
+                          float* pred_norm, float* out5, float* per_slice, double* ws, int64_t ws_doubles,
+                          uint32_t* counters, void* stream);
+
 /* layout casts at the boundary */
 int b200sr_nchw_f32_to_nhwc_bf16(const float* in, void* out, int B, int C, int H, int W, void* stream);
 int b200sr_nhwc_bf16_to_nchw_f32(const void* in, int in_pix_stride, int in_c_off, float* out, int B, int C,

@@ -18,5 +18,6 @@ from .progressive import (GANUNetBlock, ProgressiveUNet, ProgressiveUNetBlock, P
 from .fastddpm import (DoubleConv, FastDDPM, FastDDPMTrainer, FastNoiseScheduler, UNet2D,  # noqa: F401
                        sinusoidal_timestep_embedding)
 from .data import DevicePrefetcher, SyntheticTripletGenerator  # noqa: F401
+from .metrics import compute_metrics  # noqa: F401
 
 __version__ = "0.1.0"

@@ -104,6 +104,7 @@ _SIGNATURES = {
     "b200sr_conv1_fwd_split": [_P, _P, _P, _P, c_int, _P, c_int, c_int, c_int, _P],
     "b200sr_maxpool2x2_fwd_split": [_P, c_int, c_int, c_int, c_int, _P, c_int, c_int, c_int, _P],
     "b200sr_head_fwd_split": [_P, _P, _P, _P, c_int64, _P],
+    "b200sr_volume_metrics": [_P, _P, c_int, c_int, c_int, _P, _P, _P, _P, _P, c_int64, _P, _P],
     "b200sr_nchw_f32_to_nhwc_bf16": [_P, _P, c_int, c_int, c_int, c_int, _P],
     "b200sr_nhwc_bf16_to_nchw_f32": [_P, c_int, c_int, _P, c_int, c_int, c_int, c_int, _P],
 }
@@ -144,7 +145,7 @@ def last_error() -> str:
 LAUNCH_COUNTER = {"n": 0}
 # entry points that enqueue more than one kernel (split-K gradient + its fixed-order reduction, multi-kernel helpers)
 _KERNELS_PER_CALL = {"b200sr_conv3x3_wgrad_det": 3, "b200sr_convT2x2_wgrad_det": 3, "b200sr_conv1x1_wgrad_det": 3,
-                     "b200sr_conv1_wgrad_det": 2, "b200sr_bn_bwd_masked": 2, "b200sr_grad_clip": 2, "b200sr_fd_time_bwd": 5,
+                     "b200sr_conv1_wgrad_det": 2, "b200sr_bn_bwd_masked": 2, "b200sr_grad_clip": 2, "b200sr_volume_metrics": 3, "b200sr_fd_time_bwd": 5,
                      "b200sr_bn_bwd_ws_floats": 0, "b200sr_version": 0, "b200sr_device_ok": 0}
 GEMM_OPS = ("b200sr_conv3x3_fwd", "b200sr_conv3x3_dgrad", "b200sr_conv3x3_dgrad_relu", "b200sr_conv3x3_wgrad", "b200sr_convT2x2_fwd",
             "b200sr_convT2x2_dgrad", "b200sr_convT2x2_wgrad", "b200sr_conv1x1", "b200sr_conv1x1_wgrad",

@@ -996,6 +996,51 @@ int b200sr_head_fwd_split(const void* act, const float* w, const float* b, float
     return check_launch("head_split_fwd_kernel");
 }
 
+/* reference compute_metrics (src/VolumeVisualization.py:237-269) on the device: original / predicted (S,H,W) f32 ->
+ * orig_norm / pred_norm (S,H,W) f32, per_slice [S][2] = {SSIM, PSNR}, out5 = {ssim_mean, ssim_std, psnr_mean, psnr_std,
+ * mae}. ws: 2048 + 4 * S * ceil(H/32) * ceil(W/32) doubles; counters: 2 zero-initialised uint32. */
+int b200sr_volume_metrics(const float* original, const float* predicted, int S, int H, int W, float* orig_norm,
+                          float* pred_norm, float* out5, float* per_slice, double* ws, int64_t ws_doubles,
+                          uint32_t* counters, void* stream) {
+    B2_CHECK_ARG(original && predicted && orig_norm && pred_norm && out5 && per_slice && ws && counters);
+    B2_CHECK_ARG(S > 0 && H >= 7 && W >= 7);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const long long n = static_cast<long long>(S) * H * W;
+    const int grid_m = S * ((H + LS_T - 1) / LS_T) * ((W + LS_T - 1) / LS_T);
+    B2_CHECK_ARG(ws_doubles >= 2048 + 4LL * grid_m);
+    float* mm_part = reinterpret_cast<float*>(ws);  // [1024][2] floats = 1024 doubles
+    float* mm = mm_part + 2048;                     // 2 floats
+    const int g1 = grid_for(n, 256, 1024);
+    volume_minmax_kernel<<<g1, 256, 0, st>>>(original, n, mm_part, counters, mm);
+    volume_normalize_kernel<<<grid_for(n, 256), 256, 0, st>>>(original, predicted, mm, orig_norm, pred_norm, n);
+    static bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(mse_ssim_fast_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 LsFast<7>::SMEM_BYTES) != cudaSuccess)
+            return fail(B200SR_ECUDA, "mse_ssim_fast smem attribute failed");
+        configured = true;
+    }
+    LossArgs a;
+    std::memset(&a, 0, sizeof(a));
+    a.pred = pred_norm;
+    a.target = orig_norm;
+    a.H = H;
+    a.W = W;
+    a.K = 7;
+    for (int i = 0; i < LS_KMAX; ++i) a.win[i] = i < 7 ? 1.f / 7.f : 0.f;
+    a.cov_norm = 49.f / 48.f;
+    a.C1 = 0.01f * 0.01f;
+    a.C2 = 0.03f * 0.03f;
+    a.partials = ws + 2048;
+    a.counter = counters + 1;
+    a.out = out5;
+    a.per_slice = per_slice;
+    a.blocks_per_image = grid_m / S;
+    a.nimages = S;
+    mse_ssim_fast_kernel<7><<<grid_m, 256, LsFast<7>::SMEM_BYTES, st>>>(a);
+    return check_launch("volume_metrics kernels");
+}
+
 // ---- DeepCNN residual baseline -------------------------------------------------------------
 int b200sr_bn_bwd_masked(const void* dy, const void* z, const void* mask_src, int C, const float* scale,
                          const float* shift, const float* mean, const float* invstd, float* sums, int replicas,
@@ -1442,6 +1487,9 @@ int run_mse_ssim(const float* pred, const float* target, float* grad, double* su
     a.inv_n_ssim = 1.0 / (static_cast<double>(B) * (H - K + 1) * static_cast<double>(W - K + 1));
     a.w_mse = w_mse;
     a.w_ssim = w_ssim;
+    a.per_slice = nullptr;
+    a.blocks_per_image = 0;
+    a.nimages = B;
     const int grid = B * ((H + LS_T - 1) / LS_T) * ((W + LS_T - 1) / LS_T);
     if (partials != nullptr) B2_CHECK_ARG(counter != nullptr && out != nullptr && ws_doubles >= 2LL * grid);
     if ((K == 11 || K == 7) && getenv("B200SR_SSIM_GENERIC") == nullptr) {

@@ -43,9 +43,64 @@ struct LossArgs {
     float* out;
     double inv_n_mse, inv_n_ssim;
     float w_mse, w_ssim;
+    // evaluation-metrics mode (per_slice != NULL; reference compute_metrics, src/VolumeVisualization.py:237-269): partial
+    // slots hold {sum sq err, sum SSIM, sum abs err}; the last block turns them into per-slice {SSIM, PSNR} and
+    // out = {ssim_mean, ssim_std, psnr_mean, psnr_std, mae}. blocks_per_image = tiles of one slice (consecutive blocks).
+    float* per_slice;       // [B][2]
+    int blocks_per_image;
+    int nimages;
 };
 
-__device__ __forceinline__ void loss_finish(const LossArgs& a, const float (&s_red)[2][8], int tid) {
+__device__ __forceinline__ void metrics_finish(const LossArgs& a, const float (&s_red)[3][8], int tid) {
+    if (tid < 3) {
+        double acc = 0.0;
+        for (int w = 0; w < 8; ++w) acc += s_red[tid][w];
+        a.partials[static_cast<size_t>(blockIdx.x) * 4 + tid] = acc;
+    }
+    if (!last_block_ticket(a.counter, gridDim.x)) return;
+    // one thread per slice: its tiles' partials in tile order (fixed order -> reproducible)
+    __shared__ double s_abs[256];
+    double abs_acc = 0.0;
+    for (int img = tid; img < a.nimages; img += 256) {
+        double sq = 0.0, ss = 0.0, ab = 0.0;
+        const double* p = a.partials + static_cast<size_t>(img) * a.blocks_per_image * 4;
+        for (int b = 0; b < a.blocks_per_image; ++b) {
+            sq += __ldcg(p + 4 * b);
+            ss += __ldcg(p + 4 * b + 1);
+            ab += __ldcg(p + 4 * b + 2);
+        }
+        const double pix = static_cast<double>(a.H) * a.W;
+        a.per_slice[2 * img] = static_cast<float>(ss / (static_cast<double>(a.H - a.K + 1) * (a.W - a.K + 1)));
+        a.per_slice[2 * img + 1] = static_cast<float>(10.0 * log10(1.0 / (sq / pix)));  // PSNR, data_range 1.0
+        abs_acc += ab;
+    }
+    s_abs[tid] = abs_acc;
+    __threadfence_block();
+    __syncthreads();
+    if (tid == 0) {
+        double mae = 0.0;
+        for (int l = 0; l < 256; ++l) mae += s_abs[l];
+        double m[2] = {0.0, 0.0}, v[2] = {0.0, 0.0};
+        for (int i = 0; i < a.nimages; ++i) {
+            m[0] += a.per_slice[2 * i];
+            m[1] += a.per_slice[2 * i + 1];
+        }
+        m[0] /= a.nimages;
+        m[1] /= a.nimages;
+        for (int i = 0; i < a.nimages; ++i) {
+            v[0] += (a.per_slice[2 * i] - m[0]) * (a.per_slice[2 * i] - m[0]);
+            v[1] += (a.per_slice[2 * i + 1] - m[1]) * (a.per_slice[2 * i + 1] - m[1]);
+        }
+        a.out[0] = static_cast<float>(m[0]);
+        a.out[1] = static_cast<float>(sqrt(v[0] / a.nimages));  // np.std: population standard deviation
+        a.out[2] = static_cast<float>(m[1]);
+        a.out[3] = static_cast<float>(sqrt(v[1] / a.nimages));
+        a.out[4] = static_cast<float>(mae / (static_cast<double>(a.nimages) * a.H * a.W));
+    }
+}
+
+__device__ __forceinline__ void loss_finish(const LossArgs& a, const float (&s_red)[3][8], int tid) {
+    if (a.per_slice != nullptr) return metrics_finish(a, s_red, tid);
     if (a.partials == nullptr) {
         if (tid < 2) {
             double acc = 0.0;
@@ -92,7 +147,7 @@ __global__ void __launch_bounds__(256) mse_ssim_kernel(const LossArgs a) {
     float* s_h = s_y + LS_IT * LS_IT;           // 5 x [IT][MT]; later reused as 3 x [MT][T]
     float* s_g = s_h + 5 * LS_IT * LS_MT;       // 3 x [MT][MT]
     __shared__ float s_win[LS_KMAX];
-    __shared__ float s_red[2][8];
+    __shared__ float s_red[3][8];
 
     const int tid = threadIdx.x;
     const int tiles_w = (a.W + LS_T - 1) / LS_T;
@@ -197,7 +252,7 @@ __global__ void __launch_bounds__(256) mse_ssim_kernel(const LossArgs a) {
     __syncthreads();
 
     // vertical pass + combine with the MSE term
-    float mse_part = 0.f;
+    float mse_part = 0.f, abs_part = 0.f;
     for (int i = tid; i < LS_T * LS_T; i += 256) {
         const int r = i / LS_T, j = i % LS_T;
         const int qh = qh0 + r, qw = qw0 + j;
@@ -213,6 +268,7 @@ __global__ void __launch_bounds__(256) mse_ssim_kernel(const LossArgs a) {
         const float x = s_x[(r + R) * LS_IT + j + R], y = s_y[(r + R) * LS_IT + j + R];
         const float d = x - y;
         mse_part = fmaf(d, d, mse_part);
+        abs_part += fabsf(d);
         if (a.grad != nullptr)
             a.grad[(static_cast<size_t>(img) * a.H + qh) * a.W + qw] =
                 a.g_mse * d + a.g_ssim * (v0 + 2.f * x * v1 + y * v2);
@@ -223,10 +279,12 @@ __global__ void __launch_bounds__(256) mse_ssim_kernel(const LossArgs a) {
     for (int o = 16; o >= 1; o >>= 1) {
         mse_part += __shfl_xor_sync(0xffffffffu, mse_part, o);
         ssim_part += __shfl_xor_sync(0xffffffffu, ssim_part, o);
+        abs_part += __shfl_xor_sync(0xffffffffu, abs_part, o);
     }
     if ((tid & 31) == 0) {
         s_red[0][tid >> 5] = mse_part;
         s_red[1][tid >> 5] = ssim_part;
+        s_red[2][tid >> 5] = abs_part;
     }
     __syncthreads();
     loss_finish(a, s_red, tid);
@@ -261,7 +319,7 @@ __global__ void __launch_bounds__(256, 2) mse_ssim_fast_kernel(const LossArgs a)
     float* s_h = s_y + IT * PX;       // 5 x [IT][PM]; later reused as 3 x [MT][PT]
     float* s_g = s_h + 5 * IT * PM;   // 3 x [MT][PM]
     float* s_hg = s_h;
-    __shared__ float s_red[2][8];
+    __shared__ float s_red[3][8];
 
     const int tid = threadIdx.x;
     const int tiles_w = (a.W + LS_T - 1) / LS_T;
@@ -399,7 +457,7 @@ __global__ void __launch_bounds__(256, 2) mse_ssim_fast_kernel(const LossArgs a)
     __syncthreads();
 
     // ---- pass V2: along columns, strips of 8 rows, then combine with the MSE term ----
-    float mse_part = 0.f;
+    float mse_part = 0.f, abs_part = 0.f;
     {
         constexpr int SV = 8, NS = LS_T / SV;
         for (int item = tid; item < LS_T * NS; item += 256) {
@@ -426,6 +484,7 @@ __global__ void __launch_bounds__(256, 2) mse_ssim_fast_kernel(const LossArgs a)
                 const float x = s_x[(r + R) * PX + j + R], y = s_y[(r + R) * PX + j + R];
                 const float d = x - y;
                 mse_part = fmaf(d, d, mse_part);
+                abs_part += fabsf(d);
                 if (a.grad != nullptr)
                     a.grad[(static_cast<size_t>(img) * a.H + qh) * a.W + qw] =
                         a.g_mse * d + a.g_ssim * (v3[0][o] + 2.f * x * v3[1][o] + y * v3[2][o]);
@@ -437,13 +496,91 @@ __global__ void __launch_bounds__(256, 2) mse_ssim_fast_kernel(const LossArgs a)
     for (int o = 16; o >= 1; o >>= 1) {
         mse_part += __shfl_xor_sync(0xffffffffu, mse_part, o);
         ssim_part += __shfl_xor_sync(0xffffffffu, ssim_part, o);
+        abs_part += __shfl_xor_sync(0xffffffffu, abs_part, o);
     }
     if ((tid & 31) == 0) {
         s_red[0][tid >> 5] = mse_part;
         s_red[1][tid >> 5] = ssim_part;
+        s_red[2][tid >> 5] = abs_part;
     }
     __syncthreads();
     loss_finish(a, s_red, tid);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Evaluation metrics on the device (reference compute_metrics, src/VolumeVisualization.py:237-269): min / max of the
+// original volume, min-max normalisation by the ORIGINAL range with the prediction clipped to [0,1]; the per-slice
+// SSIM (7x7 uniform window, sample covariance = skimage defaults) / PSNR / MAE come from the loss kernel above in its
+// metrics mode.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) volume_minmax_kernel(const float* __restrict__ x, long long n,
+                                                            float* __restrict__ partial, unsigned* __restrict__ counter,
+                                                            float* __restrict__ out2) {
+    float lo = INFINITY, hi = -INFINITY;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const float v = __ldg(x + i);
+        lo = fminf(lo, v);
+        hi = fmaxf(hi, v);
+    }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+        lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+        hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    __shared__ float s_lo[8], s_hi[8];
+    if ((threadIdx.x & 31) == 0) {
+        s_lo[threadIdx.x >> 5] = lo;
+        s_hi[threadIdx.x >> 5] = hi;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w) {
+            lo = fminf(lo, s_lo[w]);
+            hi = fmaxf(hi, s_hi[w]);
+        }
+        partial[2 * blockIdx.x] = lo;
+        partial[2 * blockIdx.x + 1] = hi;
+    }
+    if (!last_block_ticket(counter, gridDim.x)) return;
+    lo = INFINITY;
+    hi = -INFINITY;
+    for (unsigned b = threadIdx.x; b < gridDim.x; b += 256) {
+        lo = fminf(lo, __ldcg(partial + 2 * b));
+        hi = fmaxf(hi, __ldcg(partial + 2 * b + 1));
+    }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+        lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+        hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        s_lo[threadIdx.x >> 5] = lo;
+        s_hi[threadIdx.x >> 5] = hi;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w) {
+            lo = fminf(lo, s_lo[w]);
+            hi = fmaxf(hi, s_hi[w]);
+        }
+        out2[0] = lo;
+        out2[1] = hi;
+    }
+}
+
+__global__ void __launch_bounds__(256) volume_normalize_kernel(const float* __restrict__ orig,
+                                                               const float* __restrict__ pred,
+                                                               const float* __restrict__ mm,
+                                                               float* __restrict__ orig_norm,
+                                                               float* __restrict__ pred_norm, long long n) {
+    const float lo = mm[0];
+    const float range = mm[1] - lo + 1e-8f;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        orig_norm[i] = (orig[i] - lo) / range;
+        pred_norm[i] = fminf(fmaxf((pred[i] - lo) / range, 0.f), 1.f);
+    }
 }
 
 }  // namespace b200sr

@@ -99,3 +99,26 @@ def test_ssim_properties():
         assert torch.allclose(m, torch.ones_like(m), atol=1e-12)  # SSIM(x,x) = 1
         b = torch.rand(2, 1, 40, 48, generator=g, dtype=torch.float64)
         assert torch.allclose(ssim_oracle.ssim_map(a, b, mode), ssim_oracle.ssim_map(b, a, mode))  # symmetric
+
+
+def test_metrics_oracle_follows_the_reference_definition():
+    """oracle/metrics_oracle.py restates compute_metrics (VolumeVisualization.py:237-269): normalisation by the ORIGINAL
+    range, clipped prediction, per-slice SSIM (pinned restatement above) / PSNR, MAE, population std."""
+    import numpy as np
+    from oracle import metrics_oracle, ssim_oracle
+    rng = np.random.default_rng(0)
+    o = rng.standard_normal((4, 64, 48)).astype(np.float32)
+    p = (o + 0.1 * rng.standard_normal(o.shape)).astype(np.float32)
+    p[0] += 10.0   # far outside the original's range -> clipped to 1
+    r = metrics_oracle.compute_metrics(o, p)
+    lo, rng_ = o.min(), o.max() - o.min() + 1e-8
+    on, pn = (o - lo) / rng_, np.clip((p - lo) / rng_, 0, 1)
+    assert np.array_equal(r["orig_norm"], on) and np.array_equal(r["pred_norm"], pn)
+    assert r["pred_norm"][0].max() == 1.0 and on.min() == 0.0
+    assert abs(r["mae"] - np.abs(on - pn).mean()) < 1e-12
+    s = [ssim_oracle.ssim_skimage_restatement(on[i], pn[i]) for i in range(4)]
+    q = [10 * np.log10(1.0 / np.mean((on[i].astype(np.float64) - pn[i]) ** 2)) for i in range(4)]
+    assert abs(r["ssim_mean"] - np.mean(s)) < 1e-12 and abs(r["ssim_std"] - np.std(s)) < 1e-12
+    assert abs(r["psnr_mean"] - np.mean(q)) < 1e-9 and abs(r["psnr_std"] - np.std(q)) < 1e-9
+    same = metrics_oracle.compute_metrics(o[1:], o[1:])
+    assert abs(same["ssim_mean"] - 1.0) < 1e-12 and same["mae"] == 0.0
