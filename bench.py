@@ -445,6 +445,26 @@ def run_b200sr(args):
             gc.collect()
             torch.cuda.empty_cache()
 
+    # ---- N > 1: BASELINE configs[4] ("batch-sharded 8 GPUs"): Fast-DDPM denoiser training (gradient all-reduce over NCCL)
+    # and T=10 sampling (batch sharded, no collective), every rank B samples; timed like the headline (barrier, max) -------
+    if world > 1 and not args.no_variants:
+        try:
+            fm = b200sr.FastDDPM(T=10, device=dev)
+            ftr = b200sr.FastDDPMTrainer(fm, device=dev, model_save_dir="/tmp/b200sr_bench", verbose=False)
+            fgen = b200sr.SyntheticTripletGenerator(B, H, W, device=dev, seed=1, rank=rank)
+            fx, fy = fgen.next()
+            f_ms = timed(lambda i: ftr.train_step(fx, fy), 10, 3) / 10
+            fm.eval()
+            s_ms = timed(lambda i: fm.sample(fx, dev), 6, 4) / 6
+            variants = {"fastddpm_train": {"ms_per_step": f_ms, "triplets_per_s": world * B / f_ms * 1e3,
+                                           "parallelism": f"dp{world}", "per_gpu_batch": B},
+                        "fastddpm_sample_T10": {"ms_per_batch": s_ms, "slices_per_s": world * B / s_ms * 1e3,
+                                                "denoiser_evals_per_s": 10 * world * B / s_ms * 1e3,
+                                                "parallelism": f"batch-sharded x{world}, no collective"}}
+            del fm, ftr
+        except Exception as exc:
+            variants = {"fastddpm": {"error": f"{type(exc).__name__}: {exc}"[:300]}}
+
     # ---- stock PyTorch (cuDNN) on the same GPU, same run (rank 0, N=1 only) ---------------------------------------
     gpu_lib = None
     if rank == 0 and world == 1 and not args.no_gpu_baseline:

@@ -57,6 +57,32 @@ int b200sr_conv3x3_fwd(const void* x, int x_pix_stride, int x_c_off, int Cin, co
                        const float* col_scale, const float* col_shift, int relu, float* stats,
                        int stats_replicas, void* stream);
 
+/* Train-mode nn.Conv2d + nn.BatchNorm2d statistics + finalize in ONE launch (unet_model.py:27-28,30-31): the conv
+ * as above with deterministic statistic slots (stats_replicas >= number of SMs), and b200sr_bn_finalize executed by the
+ * last CTA of every 64..256-channel column block to finish (ticket counter per column block; slots summed in slot order).
+ * Writes scale / shift / save_mean / save_invstd, updates running_mean / running_var / num_batches_tracked (all nullable
+ * together). HOST struct, DEVICE pointers. counters: >= Cout/64 uint32, zero-initialised once, reset by the kernel.
+ * Needs H % 16 == 0 and W % 8 == 0 (persistent kernel). */
+typedef struct b200sr_bn_train {
+    const float* gamma;
+    const float* beta;
+    const float* conv_bias; /* nullable: re-added to running_mean only (BatchNorm cancels it in the output) */
+    float* scale;
+    float* shift;
+    float* save_mean;
+    float* save_invstd;
+    float* running_mean;
+    float* running_var;
+    int64_t* num_batches_tracked;
+    uint32_t* counters;
+    double count; /* B*H*W */
+    float eps;
+    float momentum;
+} b200sr_bn_train;
+int b200sr_conv3x3_fwd_bn(const void* x, int x_pix_stride, int x_c_off, int Cin, const void* w_packed, int Cout, int B,
+                          int H, int W, void* out, int out_pix_stride, int out_c_off, float* stats, int stats_replicas,
+                          const b200sr_bn_train* bn, void* stream);
+
 /* Same kernel; dy: (B,H,W,Cout) slot, w_packed: [Cin][9*Cout] (PACK_CONV_DGRAD), dx: (B,H,W,Cin) slot.
  * stats (optional) receives per-channel sums of dx (used for the ConvTranspose2d bias gradient). */
 int b200sr_conv3x3_dgrad(const void* dy, int dy_pix_stride, int dy_c_off, int Cout, const void* w_packed,

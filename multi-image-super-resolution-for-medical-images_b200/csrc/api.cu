@@ -321,7 +321,7 @@ int dispatch_conv3(int block_n, const CUtensorMap& ma, const CUtensorMap& mb, co
 int run_conv3(int mode, const void* a, int a_stride, int a_coff, int Ca, const void* w_packed, int n_total, int B, int H, int W,
               void* out, int out_stride, int out_coff, const float* col_scale, const float* col_shift, int relu,
               float* stats, int stats_replicas, int cout_t, cudaStream_t st, const void* mask = nullptr,
-              int mask_stride = 0, int mask_coff = 0, int split_stride = 0) {
+              int mask_stride = 0, int mask_coff = 0, int split_stride = 0, const b200sr_bn_train* bn = nullptr) {
     B2_CHECK_ARG(a != nullptr && w_packed != nullptr && out != nullptr);
     // split_stride > 0: fp32-accuracy eval epilogue ([hi | lo | hi] output parts, conv3x3.cuh), modes 0 and 1 only
     B2_CHECK_ARG(split_stride == 0 || ((mode == 0 || mode == 1) && mask == nullptr && stats == nullptr &&
@@ -392,6 +392,7 @@ int run_conv3(int mode, const void* a, int a_stride, int a_coff, int Ca, const v
     args.mask_pix_stride = mask_stride;
     args.mask_c_off = mask_coff;
     args.split_stride = split_stride;
+    args.bn_scale = nullptr;
     {
         const int nh = block_n / (block_n < 128 ? block_n : 128);
         const int slots = taps * args.cin_chunks * nh;
@@ -416,6 +417,26 @@ int run_conv3(int mode, const void* a, int a_stride, int a_coff, int Ca, const v
     if (grid > args.num_tiles) grid = args.num_tiles;
     // deterministic statistics when the caller provides one slot per CTA of a column block (see Conv3Args::stats_slots)
     args.stats_slots = (stats != nullptr && stats_replicas >= grid / args.n_tiles) ? 1 : 0;
+    if (bn != nullptr) {
+        // fused train-mode BatchNorm finalize in the last CTA of every column block (needs the deterministic slots)
+        B2_CHECK_ARG(mode == 0 && mask == nullptr && split_stride == 0 && args.stats_slots == 1);
+        B2_CHECK_ARG(bn->gamma && bn->beta && bn->scale && bn->shift && bn->save_mean && bn->save_invstd && bn->counters);
+        B2_CHECK_ARG((bn->running_mean == nullptr) == (bn->running_var == nullptr) && bn->count > 1.0);
+        args.bn_gamma = bn->gamma;
+        args.bn_beta = bn->beta;
+        args.bn_conv_bias = bn->conv_bias;
+        args.bn_scale = bn->scale;
+        args.bn_shift = bn->shift;
+        args.bn_mean = bn->save_mean;
+        args.bn_invstd = bn->save_invstd;
+        args.bn_rmean = bn->running_mean;
+        args.bn_rvar = bn->running_var;
+        args.bn_nbt = reinterpret_cast<long long*>(bn->num_batches_tracked);
+        args.bn_counters = bn->counters;
+        args.bn_count = static_cast<float>(bn->count);
+        args.bn_eps = bn->eps;
+        args.bn_momentum = bn->momentum;
+    }
     if (split_stride > 0)
         return mode == 0 ? dispatch_conv3<0, true>(block_n, ma, mb, mo, args, grid, st)
                          : dispatch_conv3<1, true>(block_n, ma, mb, mo, args, grid, st);
@@ -624,6 +645,14 @@ int b200sr_conv3x3_fwd(const void* x, int x_pix_stride, int x_c_off, int Cin, co
                      out_c_off, col_scale, col_shift, relu, stats, stats_replicas, static_cast<cudaStream_t>(stream));
 }
 
+int b200sr_conv3x3_fwd_bn(const void* x, int x_pix_stride, int x_c_off, int Cin, const void* w_packed, int Cout, int B,
+                          int H, int W, void* out, int out_pix_stride, int out_c_off, float* stats, int stats_replicas,
+                          const b200sr_bn_train* bn, void* stream) {
+    B2_CHECK_ARG(bn != nullptr && stats != nullptr && H % C3_TILE_H == 0 && W % C3_TILE_W == 0);
+    return run_conv3(0, x, x_pix_stride, x_c_off, Cin, w_packed, Cout, B, H, W, out, out_pix_stride, out_c_off, nullptr,
+                     nullptr, 0, stats, stats_replicas, Cout, static_cast<cudaStream_t>(stream), nullptr, 0, 0, 0, bn);
+}
+
 int b200sr_conv3x3_dgrad(const void* dy, int dy_pix_stride, int dy_c_off, int Cout, const void* w_packed, int Cin,
                          int B, int H, int W, void* dx, int dx_pix_stride, int dx_c_off, float* stats,
                          int stats_replicas, void* stream) {
@@ -810,20 +839,25 @@ namespace {
 int launch_reduce_unpack(float* ws, int splits, long long split_stride, int T, int outer_total, int inner_total,
                          int inner_dst, int inner_off, float* dst, cudaStream_t st) {
     B2_CHECK_ARG(outer_total % PK_TILE == 0 && inner_total % PK_TILE == 0 && (T == 9 || T == 4 || T == 1));
-    if (splits > 1) {
-        // stage 2a: fold the split-K slices into slice 0 (element-parallel; part-lanes when there are many slices)
+    int tiles = (outer_total / PK_TILE) * (inner_total / PK_TILE);
+    int nsplits_tile = splits;
+    if (splits > 1 && tiles < 128) {
+        // few tiles (small layers, many split-K slices): stage 2a folds the slices into slice 0 with element- and
+        // slice-lane parallelism; with >= 128 tiles the layout kernel below sums the slices itself (one launch less, and
+        // slice 0 is not written and re-read)
         B2_CHECK_ARG(split_stride % 4 == 0);
         const long long n4 = split_stride / 4;
         const int lanes = splits >= 32 ? 8 : (splits >= 16 ? 4 : (splits >= 8 ? 2 : 1));
         const long long blocks = (n4 + 256 / lanes - 1) / (256 / lanes);
         reduce_splits_inplace_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(reinterpret_cast<float4*>(ws), splits,
                                                                                    n4, n4, lanes);
+        nsplits_tile = 1;
     }
-    // stage 2b: kernel layout [t][inner][outer] -> PyTorch parameter layout
-    int tiles = (outer_total / PK_TILE) * (inner_total / PK_TILE);
+    // stage 2b: kernel layout [t][inner][outer] -> PyTorch parameter layout (summing the slices in order when there
+    // still are several)
     if (tiles > num_sms() * 8) tiles = num_sms() * 8;
-    wgrad_reduce_unpack_kernel<<<tiles, 256, 0, st>>>(ws, 1, split_stride, T, outer_total, inner_total, inner_dst,
-                                                      inner_off, dst);
+    wgrad_reduce_unpack_kernel<<<tiles, 256, 0, st>>>(ws, nsplits_tile, split_stride, T, outer_total, inner_total,
+                                                      inner_dst, inner_off, dst);
     return check_launch("wgrad_reduce_unpack_kernel");
 }
 }  // namespace

@@ -50,7 +50,74 @@ struct Conv3Args {
     int mask_c_off;
     // SPLIT epilogue (fp32-accuracy eval mode, see below): channel distance between the [hi | lo | hi] parts of the output
     int split_stride;
+    // Fused train-mode BatchNorm finalize (slot-mode statistics only): the last CTA of a column block to finish (ticket
+    // counter per column block) sums that block's statistic slots in slot order and writes scale / shift / mean / invstd
+    // and the running statistics — b200sr_bn_finalize without its launch. bn_scale == nullptr: off.
+    const float* bn_gamma;
+    const float* bn_beta;
+    const float* bn_conv_bias;  // nullable
+    float* bn_scale;
+    float* bn_shift;
+    float* bn_mean;
+    float* bn_invstd;
+    float* bn_rmean;            // nullable (track_running_stats off)
+    float* bn_rvar;
+    long long* bn_nbt;          // nullable
+    unsigned* bn_counters;      // [n_tiles], zero-initialised once, self-resetting
+    float bn_count, bn_eps, bn_momentum;
 };
+
+// Fixed-order finalize of BLOCK_N channels from `used` statistic slots by all 256 threads of the CTA that drew the last
+// ticket. Layout: BLOCK_N/2 float4 column tasks (sum | sum of squares) x 512/BLOCK_N slot lanes; double accumulation like
+// bn_finalize_kernel. `scratch` >= 8 KB of shared memory.
+template <int BLOCK_N>
+__device__ __forceinline__ void c3_bn_finalize(const Conv3Args& args, int n0, int used, uint8_t* scratch) {
+    constexpr int TASKS = BLOCK_N / 2;     // float4 columns: [0, BLOCK_N/4) = sums, [BLOCK_N/4, BLOCK_N/2) = squares
+    constexpr int LANES = 256 / TASKS;     // 8 / 4 / 2
+    const int tid = threadIdx.x;
+    const int task = tid % TASKS, lane = tid / TASKS;
+    const int which = task / (BLOCK_N / 4), c4 = task % (BLOCK_N / 4);
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    const float* base = args.stats + static_cast<size_t>(which) * args.n_total + n0 + 4 * c4;
+#pragma unroll 4
+    for (int sl = lane; sl < used; sl += LANES) {
+        const float4 v = __ldcg(reinterpret_cast<const float4*>(base + static_cast<size_t>(sl) * 2 * args.n_total));
+        acc[0] += v.x;
+        acc[1] += v.y;
+        acc[2] += v.z;
+        acc[3] += v.w;
+    }
+    double* s_acc = reinterpret_cast<double*>(scratch);  // [LANES][2][BLOCK_N]
+#pragma unroll
+    for (int k = 0; k < 4; ++k) s_acc[(lane * 2 + which) * BLOCK_N + 4 * c4 + k] = acc[k];
+    __syncthreads();
+    if (tid < BLOCK_N) {
+        double s = 0.0, q = 0.0;
+#pragma unroll
+        for (int l = 0; l < LANES; ++l) {
+            s += s_acc[(l * 2 + 0) * BLOCK_N + tid];
+            q += s_acc[(l * 2 + 1) * BLOCK_N + tid];
+        }
+        const int c = n0 + tid;
+        const double count = static_cast<double>(args.bn_count);
+        const double mean = s / count;
+        double var = q / count - mean * mean;
+        if (var < 0.0) var = 0.0;
+        const float invstd = 1.0f / sqrtf(static_cast<float>(var) + args.bn_eps);
+        const float sc = args.bn_gamma[c] * invstd;
+        args.bn_scale[c] = sc;
+        args.bn_shift[c] = args.bn_beta[c] - static_cast<float>(mean) * sc;
+        args.bn_mean[c] = static_cast<float>(mean);
+        args.bn_invstd[c] = invstd;
+        if (args.bn_rmean != nullptr) {
+            const float b = args.bn_conv_bias ? args.bn_conv_bias[c] : 0.f;
+            const float unbiased = static_cast<float>(var * (count / (count - 1.0)));
+            args.bn_rmean[c] = (1.f - args.bn_momentum) * args.bn_rmean[c] + args.bn_momentum * (static_cast<float>(mean) + b);
+            args.bn_rvar[c] = (1.f - args.bn_momentum) * args.bn_rvar[c] + args.bn_momentum * unbiased;
+        }
+        if (c == 0 && args.bn_nbt != nullptr) *args.bn_nbt += 1;
+    }
+}
 
 #ifndef C3_HAS_MASK
 #define C3_HAS_MASK 1  // A/B switch for the fused ReLU-mask epilogue (build with -DC3_HAS_MASK=0 to compare)
@@ -493,6 +560,7 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_kernel(const __grid_con
                     for (int s2 = mine + used; s2 < args.stats_replicas; s2 += used)
                         args.stats[(static_cast<size_t>(s2) * 2 + which) * args.n_total + n0_last + col] = 0.f;
                 }
+                __threadfence();  // this CTA's slot is visible device-wide before its ticket (fused finalize) is drawn
             } else {
                 float* dst = args.stats + static_cast<size_t>(blockIdx.x % args.stats_replicas) * 2 * args.n_total + n0_last;
 #pragma unroll
@@ -509,6 +577,22 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_kernel(const __grid_con
     if (warp == 2) {
         tc_fence_after();
         tmem_dealloc(tmem_base, 2 * BLOCK_N);
+    }
+    if (MODE == 0 && !SPLIT && args.bn_scale != nullptr && blockIdx.x < args.num_tiles) {
+        // fused BatchNorm finalize: one ticket per CTA of this column block; the last one sums the slots in slot order
+        __shared__ int s_bn_last;
+        const int n_tile = static_cast<int>(blockIdx.x) % args.n_tiles;
+        const int used = static_cast<int>(gridDim.x) / args.n_tiles;
+        if (threadIdx.x == 0) {
+            const unsigned t = atomicAdd(args.bn_counters + n_tile, 1u);
+            s_bn_last = (t == static_cast<unsigned>(used) - 1u) ? 1 : 0;
+            if (s_bn_last) args.bn_counters[n_tile] = 0u;
+        }
+        __syncthreads();
+        if (s_bn_last) {
+            __threadfence();
+            c3_bn_finalize<BLOCK_N>(args, n_tile * BLOCK_N, used, out_stage);
+        }
     }
 }
 

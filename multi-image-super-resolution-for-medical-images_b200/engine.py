@@ -13,6 +13,8 @@ HBM layout (all activations NHWC bf16, resident for the whole step):
 """
 from __future__ import annotations
 
+import ctypes
+
 import numpy as np
 import torch
 
@@ -32,6 +34,25 @@ _PACK_JOB_DTYPE = np.dtype([("src", "<u8"), ("dst", "<u8"), ("kind", "<i4"), ("c
                             ("pad", "<i4"), ("count", "<i8")])
 _FOLD_JOB_DTYPE = np.dtype([("gamma", "<u8"), ("beta", "<u8"), ("rmean", "<u8"), ("rvar", "<u8"), ("cbias", "<u8"),
                             ("scale", "<u8"), ("shift", "<u8"), ("C", "<i4"), ("pad", "<i4")])
+
+
+class _Nvtx:
+    """NVTX ranges around every layer of the forward / backward pass (B200SR_NVTX=1): shows up in nsys / ncu --nvtx as
+    fwd/<layer>, bwd/<block>, so a profile maps kernels to reference layers. Off by default (two host calls per range)."""
+
+    enabled = __import__("os").environ.get("B200SR_NVTX") is not None
+
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if _Nvtx.enabled:
+            torch.cuda.nvtx.range_push(self.name)
+
+    def __exit__(self, *exc):
+        if _Nvtx.enabled:
+            torch.cuda.nvtx.range_pop()
+        return False
 
 
 def _align(n: int, a: int = 64) -> int:
@@ -226,6 +247,7 @@ class UNetEngine:
         bn_ws_floats = max(int(call("b200sr_bn_bwd_ws_floats", cs.cout)) for cs in self.convs)
         self.red_ws = torch.empty(max(bn_ws_floats, 4 * sms * 72), dtype=torch.float32, device=device)
         self.red_counters = torch.zeros(64, dtype=torch.int32, device=device)
+        self.bn_fwd_counters = torch.zeros(16 * len(self.convs), dtype=torch.int32, device=device)  # fused finalize tickets
         self.wg_ws = torch.empty(WGRAD_WS_FLOATS, dtype=torch.float32, device=device)
 
         fold = np.zeros(len(self.convs), dtype=_FOLD_JOB_DTYPE)
@@ -532,24 +554,39 @@ class UNetEngine:
 
     def _conv_bn_train(self, plan, cs, src, s_stride, s_off, h, w, act, a_stride, a_off, pooled, x_input=None):
         """conv -> batch statistics -> finalize -> BN-apply+ReLU(+pool)."""
+        with _Nvtx("fwd/" + cs.name):
+            self._conv_bn_train_impl(plan, cs, src, s_stride, s_off, h, w, act, a_stride, a_off, pooled, x_input)
+
+    def _conv_bn_train_impl(self, plan, cs, src, s_stride, s_off, h, w, act, a_stride, a_off, pooled, x_input=None):
         B = plan["B"]
         st = _lib.current_stream_ptr()
         z = plan["z:" + cs.name]
         stats = self.bn_stats.data_ptr() + 4 * self.bn_st_off[cs.name]
         slots = self.bn_slots[cs.name]  # one statistic slot per CTA: stored, never accumulated -> no zeroing, bit-reproducible
-        if x_input is not None:
-            call("b200sr_conv1_fwd", ptr(x_input), ptr(cs.conv.weight), None, None, 0, ptr(z), stats, slots, B, h, w, st)
-        else:
-            call("b200sr_conv3x3_fwd", ptr(src), s_stride, s_off, cs.cin, self._wp(self.wp_fwd, cs.name), cs.cout,
-                 B, h, w, ptr(z), cs.cout, 0, None, None, 0, stats, slots, st)
         bn = cs.bn
         track = bn.track_running_stats and bn.running_mean is not None
-        # (b200sr_bn_train_apply fuses these two launches, but its per-thread finalize prologue costs more HBM
-        # bandwidth-time than the extra tiny launch: 1.10 ms vs 0.95 ms per step over the 18 layers, measured)
-        call("b200sr_bn_finalize", stats, slots, cs.cout, float(B * h * w), ptr(bn.weight), ptr(bn.bias),
-             ptr(cs.conv.bias), BN_EPS, BN_MOMENTUM, self._bn(cs, "scale"), self._bn(cs, "shift"),
-             self._bn(cs, "mean"), self._bn(cs, "invstd"), ptr(bn.running_mean) if track else None,
-             ptr(bn.running_var) if track else None, ptr(bn.num_batches_tracked) if track else None, st)
+        if x_input is None and h % 16 == 0 and w % 8 == 0:
+            # conv + statistics + BatchNorm finalize in ONE launch: the last CTA of every column block finalizes it
+            desc = plan.get("bn:" + cs.name)
+            if desc is None:
+                li = self.convs.index(cs)
+                desc = plan["bn:" + cs.name] = _lib.BnTrain(
+                    ptr(bn.weight), ptr(bn.bias), ptr(cs.conv.bias), self._bn(cs, "scale"), self._bn(cs, "shift"),
+                    self._bn(cs, "mean"), self._bn(cs, "invstd"), ptr(bn.running_mean) if track else None,
+                    ptr(bn.running_var) if track else None, ptr(bn.num_batches_tracked) if track else None,
+                    self.bn_fwd_counters.data_ptr() + 4 * 16 * li, float(B * h * w), BN_EPS, BN_MOMENTUM)
+            call("b200sr_conv3x3_fwd_bn", ptr(src), s_stride, s_off, cs.cin, self._wp(self.wp_fwd, cs.name), cs.cout,
+                 B, h, w, ptr(z), cs.cout, 0, stats, slots, ctypes.byref(desc), st)
+        else:
+            if x_input is not None:
+                call("b200sr_conv1_fwd", ptr(x_input), ptr(cs.conv.weight), None, None, 0, ptr(z), stats, slots, B, h, w, st)
+            else:
+                call("b200sr_conv3x3_fwd", ptr(src), s_stride, s_off, cs.cin, self._wp(self.wp_fwd, cs.name), cs.cout,
+                     B, h, w, ptr(z), cs.cout, 0, None, None, 0, stats, slots, st)
+            call("b200sr_bn_finalize", stats, slots, cs.cout, float(B * h * w), ptr(bn.weight), ptr(bn.bias),
+                 ptr(cs.conv.bias), BN_EPS, BN_MOMENTUM, self._bn(cs, "scale"), self._bn(cs, "shift"),
+                 self._bn(cs, "mean"), self._bn(cs, "invstd"), ptr(bn.running_mean) if track else None,
+                 ptr(bn.running_var) if track else None, ptr(bn.num_batches_tracked) if track else None, st)
         call("b200sr_bnrelu_apply", ptr(z), cs.cout, self._bn(cs, "scale"), self._bn(cs, "shift"), ptr(act), a_stride,
              a_off, ptr(pooled), B, h, w, st)
 
@@ -711,6 +748,10 @@ class UNetEngine:
         dy = s0  # gradient w.r.t. the current block's output activation (dense)
 
         def block_bwd(name, lvl, in_buf, in_stride, in_c, dx_dst, dx_stride, dx_stats, dy_ptr, x_input=None):
+            with _Nvtx("bwd/" + name):
+                return block_bwd_impl(name, lvl, in_buf, in_stride, in_c, dx_dst, dx_stride, dx_stats, dy_ptr, x_input)
+
+        def block_bwd_impl(name, lvl, in_buf, in_stride, in_c, dx_dst, dx_stride, dx_stats, dy_ptr, x_input=None):
             """Backward through a UNetBlock: dy (dense, cout ch) -> dx into dx_dst (in_c channels)."""
             c1, c2 = self.blocks[name]
             h, w, c = H >> lvl, W >> lvl, c2.cout

@@ -610,6 +610,43 @@ def conv3x3_fwd_slots(B=6, H=64, W=64, Cin=64, Cout=128, seed=71):
             "bitwise": float((runs[0][1] - runs[1][1]).abs().max())}
 
 
+def conv3x3_fwd_bn_fused(B=6, H=64, W=64, Cin=64, Cout=128, seed=72):
+    """conv + statistics + BatchNorm finalize in one launch (last CTA per column block) against F.conv2d + F.batch_norm."""
+    _setup()
+    x = bf(rnd(B, Cin, H, W, seed=seed))
+    w = bf(rnd(Cout, Cin, 3, 3, seed=seed + 1, scale=(9 * Cin) ** -0.5))
+    gamma, beta = 1 + 0.1 * rnd(Cout, seed=seed + 2), 0.1 * rnd(Cout, seed=seed + 3)
+    cbias = 0.1 * rnd(Cout, seed=seed + 4)
+    wp = pack(w, 0, Cout, Cin)
+    xb = nhwc(x)
+    counters = torch.zeros(16, dtype=torch.int32, device=DEV)
+    runs = []
+    for _ in range(2):
+        ob = torch.zeros(B, H, W, Cout, dtype=torch.bfloat16, device=DEV)
+        stats = _garbage(SLOTS, 2, Cout)
+        ws = _garbage(4, Cout)
+        rm, rv = 0.2 * rnd(Cout, seed=seed + 5), 1 + 0.1 * rnd(Cout, seed=seed + 6).abs()
+        nbt = torch.full((), 3, dtype=torch.int64, device=DEV)
+        desc = _lib.BnTrain(ptr(gamma), ptr(beta), ptr(cbias), ptr(ws[0]), ptr(ws[1]), ptr(ws[2]), ptr(ws[3]), ptr(rm),
+                            ptr(rv), ptr(nbt), ptr(counters), float(B * H * W), 1e-5, 0.1)
+        call("b200sr_conv3x3_fwd_bn", ptr(xb), Cin, 0, Cin, ptr(wp), Cout, B, H, W, ptr(ob), Cout, 0, ptr(stats), SLOTS,
+             ctypes.byref(desc), st())
+        torch.cuda.synchronize()
+        runs.append((ob, ws, rm, rv, nbt))
+    ob, ws, rm, rv, nbt = runs[0]
+    z = nchw(ob)   # statistics are those of the stored (bf16) conv output
+    mean, var = z.double().mean(dim=(0, 2, 3)), z.double().var(dim=(0, 2, 3), unbiased=False)
+    invstd = 1.0 / torch.sqrt(var + 1e-5)
+    n = B * H * W
+    rm_ref = 0.8 * 0 + (0.9 * (0.2 * rnd(Cout, seed=seed + 5)).double() + 0.1 * (mean + cbias.double()))
+    rv_ref = 0.9 * (1 + 0.1 * rnd(Cout, seed=seed + 6).abs()).double() + 0.1 * var * n / (n - 1)
+    return {"z": rel(z, F.conv2d(x, w, padding=1)), "scale": rel(ws[0], gamma.double() * invstd),
+            "shift": rel(ws[1], beta.double() - mean * gamma.double() * invstd), "mean": rel(ws[2], mean),
+            "invstd": rel(ws[3], invstd), "running_mean": rel(rm, rm_ref), "running_var": rel(rv, rv_ref),
+            "nbt_exact": abs(int(nbt) - 4), "counters_reset": float(counters.abs().max()),
+            "bitwise": float(sum((a - b).abs().max() for a, b in zip(runs[0][1:4], runs[1][1:4])))}
+
+
 def conv3x3_wgrad_det(B=2, H=16, W=32, Cin=64, Cout=128, seed=3, cin_total=None, cin_off=0):
     _setup()
     x = bf(rnd(B, Cin, H, W, seed=seed))
@@ -969,6 +1006,15 @@ CHECKS = {
                                      {"out": BF16, "stats_sum": 1e-4, "stats_sq": 1e-4, "bitwise": 0.0}),
     "det_conv3x3_stats_generic_kernel": (conv3x3_fwd_slots, dict(Cin=64, Cout=128, B=2, H=8, W=16),
                                          {"out": BF16, "stats_sum": 1e-4, "stats_sq": 1e-4, "bitwise": 0.0}),
+    "fused_conv_bn_finalize_n128": (conv3x3_fwd_bn_fused, {}, {"z": BF16, "scale": 1e-5, "shift": 1e-4, "mean": 1e-4,
+                                    "invstd": 1e-5, "running_mean": 1e-5, "running_var": 1e-5, "nbt_exact": 0,
+                                    "counters_reset": 0.0, "bitwise": 0.0}),
+    "fused_conv_bn_finalize_n64": (conv3x3_fwd_bn_fused, dict(Cin=128, Cout=64, B=4, H=128, W=64),
+                                   {"z": BF16, "scale": 1e-5, "shift": 1e-4, "invstd": 1e-5, "running_var": 1e-5,
+                                    "counters_reset": 0.0, "bitwise": 0.0}),
+    "fused_conv_bn_finalize_n1024": (conv3x3_fwd_bn_fused, dict(Cin=512, Cout=1024, B=8, H=16, W=16),
+                                     {"z": BF16, "scale": 1e-5, "shift": 1e-4, "invstd": 1e-5, "running_mean": 1e-5,
+                                      "counters_reset": 0.0, "bitwise": 0.0}),
     "det_conv3x3_wgrad_modeA": (conv3x3_wgrad_det, dict(Cin=256, Cout=256, B=3, H=16, W=32), {"dw": BF16, "bitwise": 0.0}),
     "det_conv3x3_wgrad_modeB": (conv3x3_wgrad_det, dict(Cin=64, Cout=64, B=4, H=64, W=64), {"dw": BF16, "bitwise": 0.0}),
     "det_conv3x3_wgrad_n64": (conv3x3_wgrad_det, dict(Cin=128, Cout=64, B=2, H=32, W=64), {"dw": BF16, "bitwise": 0.0}),

@@ -70,7 +70,9 @@ def _worker(rank, world, port, ngpu, q):
     # a second full step through the public API (UNetTrainer.train_step) keeps the ranks in lock-step
     l2 = float(tr.train_step(x[lo:hi].to(dev), y[lo:hi].to(dev)))
     w2 = torch.cat([p.detach().flatten() for p in model.parameters()]).cpu()
-    q.put((rank, float(loss), grads if rank == 0 else None, weights if rank == 0 else None, launched, w2, l2,
+    # numpy payloads: torch tensors on a multiprocessing queue are passed by file descriptor and need the sender alive
+    q.put((rank, float(loss), {k: v.numpy() for k, v in grads.items()} if rank == 0 else None,
+           {k: v.numpy() for k, v in weights.items()} if rank == 0 else None, launched, w2.numpy(), l2,
            float(summed.abs().sum())))
     dist.barrier()
     dist.destroy_process_group()
@@ -111,7 +113,8 @@ def test_two_rank_gradients_match_oracle_per_shard_average():
 
     for r in range(world):
         assert abs(results[r][1] - o_losses[r]) / abs(o_losses[r]) < 1e-3, (r, results[r][1], o_losses[r])
-    grads, weights = results[0][2], results[0][3]
+    grads = {k: torch.from_numpy(v) for k, v in results[0][2].items()}
+    weights = {k: torch.from_numpy(v) for k, v in results[0][3].items()}
     worst = {}
     for n, g in grads.items():
         if n.endswith("conv.0.bias") or n.endswith("conv.3.bias"):
@@ -131,5 +134,5 @@ def test_two_rank_gradients_match_oracle_per_shard_average():
     # the reducer saw one range per block group and launched several buckets before the final flush
     assert len(results[0][4]) >= 3, results[0][4]
     # both ranks hold bit-identical weights after two steps
-    assert torch.equal(results[0][5], results[1][5])
+    assert (results[0][5] == results[1][5]).all()
     assert results[0][7] > 0
