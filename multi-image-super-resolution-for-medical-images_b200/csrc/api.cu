@@ -839,25 +839,23 @@ namespace {
 int launch_reduce_unpack(float* ws, int splits, long long split_stride, int T, int outer_total, int inner_total,
                          int inner_dst, int inner_off, float* dst, cudaStream_t st) {
     B2_CHECK_ARG(outer_total % PK_TILE == 0 && inner_total % PK_TILE == 0 && (T == 9 || T == 4 || T == 1));
-    int tiles = (outer_total / PK_TILE) * (inner_total / PK_TILE);
-    int nsplits_tile = splits;
-    if (splits > 1 && tiles < 128) {
-        // few tiles (small layers, many split-K slices): stage 2a folds the slices into slice 0 with element- and
-        // slice-lane parallelism; with >= 128 tiles the layout kernel below sums the slices itself (one launch less, and
-        // slice 0 is not written and re-read)
+    if (splits > 1) {
+        // stage 2a: fold the split-K slices into slice 0 (element-parallel; slice lanes when there are many slices).
+        // Measured (profiles/r2_ab_stage2.txt): letting the layout kernel below sum the slices itself for layers with
+        // >= 128 tiles saves a launch but costs 0.25 ms per step — its strided 4-byte reads of several slices are slower
+        // than this coalesced float4 pass.
         B2_CHECK_ARG(split_stride % 4 == 0);
         const long long n4 = split_stride / 4;
         const int lanes = splits >= 32 ? 8 : (splits >= 16 ? 4 : (splits >= 8 ? 2 : 1));
         const long long blocks = (n4 + 256 / lanes - 1) / (256 / lanes);
         reduce_splits_inplace_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(reinterpret_cast<float4*>(ws), splits,
                                                                                    n4, n4, lanes);
-        nsplits_tile = 1;
     }
-    // stage 2b: kernel layout [t][inner][outer] -> PyTorch parameter layout (summing the slices in order when there
-    // still are several)
+    // stage 2b: kernel layout [t][inner][outer] -> PyTorch parameter layout
+    int tiles = (outer_total / PK_TILE) * (inner_total / PK_TILE);
     if (tiles > num_sms() * 8) tiles = num_sms() * 8;
-    wgrad_reduce_unpack_kernel<<<tiles, 256, 0, st>>>(ws, nsplits_tile, split_stride, T, outer_total, inner_total,
-                                                      inner_dst, inner_off, dst);
+    wgrad_reduce_unpack_kernel<<<tiles, 256, 0, st>>>(ws, 1, split_stride, T, outer_total, inner_total, inner_dst,
+                                                      inner_off, dst);
     return check_launch("wgrad_reduce_unpack_kernel");
 }
 }  // namespace

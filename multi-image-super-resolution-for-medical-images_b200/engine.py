@@ -121,6 +121,7 @@ class UNetEngine:
         self.wgrad_late = os.environ.get("B200SR_WGRAD_LATE") is not None
         self.timing_skip_pack = os.environ.get("B200SR_TIMING_SKIP_PACK") is not None  # timing experiment only
         self.eval_graphs = os.environ.get("B200SR_NO_EVAL_GRAPH") is None
+        self.fused_bn_finalize = os.environ.get("B200SR_NO_FUSED_BN") is None  # A/B switch: separate b200sr_bn_finalize launches
         self._eval_graph_cache, self._eval_graph_calls = {}, {}
         self._hp = None
 
@@ -565,7 +566,7 @@ class UNetEngine:
         slots = self.bn_slots[cs.name]  # one statistic slot per CTA: stored, never accumulated -> no zeroing, bit-reproducible
         bn = cs.bn
         track = bn.track_running_stats and bn.running_mean is not None
-        if x_input is None and h % 16 == 0 and w % 8 == 0:
+        if x_input is None and h % 16 == 0 and w % 8 == 0 and self.fused_bn_finalize:
             # conv + statistics + BatchNorm finalize in ONE launch: the last CTA of every column block finalizes it
             desc = plan.get("bn:" + cs.name)
             if desc is None:
