@@ -299,7 +299,7 @@ int launch_conv3_t(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorM
         if (e != cudaSuccess) return fail(B200SR_ECUDA, std::string("conv3x3 smem attribute: ") + cudaGetErrorString(e));
         configured = true;
     }
-    conv3x3_kernel<BLOCK_N, MODE, SPLIT><<<grid, C3_THREADS, smem, st>>>(ma, mb, mo, args);
+    conv3x3_kernel<BLOCK_N, MODE, SPLIT><<<grid, c3_threads<BLOCK_N, MODE, SPLIT>(), smem, st>>>(ma, mb, mo, args);
     return check_launch("conv3x3_kernel");
 }
 

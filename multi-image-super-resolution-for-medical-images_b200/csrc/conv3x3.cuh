@@ -156,14 +156,28 @@ struct C3Cfg {
 // ordinary main loop over K' = 3*Cin accumulates a_hi*w_hi + a_lo*w_hi + a_hi*w_lo in fp32 (the dropped lo*lo term is
 // 2^-18 relative). Only the epilogue differs: the fp32 result (after the fp32 affine / ReLU) is split again and the
 // three parts are stored at channel offsets 0, split_stride, 2*split_stride of the output slot.
+// ConvTranspose modes (1, 2) have K = Cin only (one tap per box), so a tile's main loop is short and its epilogue — 64 KB
+// of bf16 output per 128 x 256 tile — is the critical path. They run TWO epilogue teams of four warps (warps 4-7 and
+// 8-11, each covering the 128 TMEM lanes): team t converts and stores the 64-column groups g with g % 2 == t through its
+// own staging buffer and its own TMA-store issuer thread, so two groups are in flight per CTA.
+template <int BLOCK_N, int MODE_T, bool SPLIT>
+__host__ __device__ constexpr int c3_teams() {
+    return ((MODE_T == 1 || MODE_T == 2) && BLOCK_N >= 128 && !SPLIT) ? 2 : 1;
+}
+template <int BLOCK_N, int MODE_T, bool SPLIT>
+__host__ __device__ constexpr int c3_threads() {
+    return 128 + 128 * c3_teams<BLOCK_N, MODE_T, SPLIT>();
+}
+
 template <int BLOCK_N, int MODE_T, bool SPLIT = false>
-__global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_kernel(const __grid_constant__ CUtensorMap map_a,
+__global__ void __launch_bounds__((c3_threads<BLOCK_N, MODE_T, SPLIT>()), 1) conv3x3_kernel(const __grid_constant__ CUtensorMap map_a,
                                                                 const __grid_constant__ CUtensorMap map_b,
                                                                 const __grid_constant__ CUtensorMap map_out,
                                                                 const Conv3Args args) {
     using Cfg = C3Cfg<BLOCK_N, SPLIT>;
     static_assert(!SPLIT || MODE_T == 0 || MODE_T == 1, "SPLIT epilogue exists for conv3x3 forward and ConvT forward");
     constexpr int SB = Cfg::SB, NH = Cfg::NH, BN_SLOT = Cfg::BN_SLOT;
+    constexpr int TEAMS = c3_teams<BLOCK_N, MODE_T, SPLIT>();
     const int SA = args.sa;
     // MODE 4 = MODE 0 (3x3 conv / dgrad) + the ReLU-mask epilogue: a separate instantiation, so the kernels of the UNet
     // hot path carry none of its registers or branches (measured: +2 % per step when it was a runtime branch of MODE 0)
@@ -207,7 +221,7 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_kernel(const __grid_con
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(&acc_full[s], 1);
-            mbar_init(&acc_empty[s], 128);
+            mbar_init(&acc_empty[s], 128 * TEAMS);
         }
         fence_barrier_init();
     }
@@ -215,7 +229,7 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_kernel(const __grid_con
         tmem_alloc(tmem_ptr_smem, 2 * BLOCK_N);
         tmem_relinquish();
     }
-    if (warp >= 4 && blockIdx.x < args.num_tiles) {
+    if (warp >= 4 && warp < 8 && blockIdx.x < args.num_tiles) {
         // the tile schedule keeps a CTA on one column block, so its affine vectors can be staged once
         const int n0 = (static_cast<int>(blockIdx.x) % args.n_tiles) * BLOCK_N;
         for (int i = threadIdx.x - 128; i < BLOCK_N; i += 128) {
@@ -341,10 +355,12 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_kernel(const __grid_con
     } else if (warp >= 4) {
         // ===================== epilogue =====================
         const int q = warp & 3;
+        const int team = (warp - 4) >> 2;  // 0, or 1 for the second epilogue team of the ConvTranspose modes
+        const int bar_a = 1 + 2 * team, bar_b = 2 + 2 * team;  // named barriers of this team
         const int row = q * 32 + lane;  // pixel inside the tile: row = h_local * 8 + w_local
         const bool do_stats = args.stats != nullptr;
         const bool affine = args.col_scale != nullptr || args.col_shift != nullptr;
-        const bool issuer = threadIdx.x == 128;  // issues the TMA stores
+        const bool issuer = threadIdx.x == 128 + 128 * team;  // issues this team's TMA stores
         float st_sum[BLOCK_N / 32], st_sq[BLOCK_N / 32];
 #pragma unroll
         for (int i = 0; i < BLOCK_N / 32; ++i) st_sum[i] = st_sq[i] = 0.f;
@@ -434,11 +450,12 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_kernel(const __grid_con
                     }
                     continue;
                 }
-                uint8_t* stage = out_stage + sbuf * C3_OUT_STAGE;
-                if (Cfg::NBUF == 1) {
-                    // single staging buffer: the previous store must have finished reading it before it is rewritten
+                if (TEAMS == 2 && (grp & 1) != team) continue;  // the other team's group
+                uint8_t* stage = out_stage + (TEAMS == 2 ? team : sbuf) * C3_OUT_STAGE;
+                if (Cfg::NBUF == 1 || TEAMS == 2) {
+                    // single staging buffer (per team): the previous store must have finished reading it before it is rewritten
                     if (issuer) tma_store_wait_read<0>();
-                    named_bar_sync(2, 128);
+                    named_bar_sync(bar_b, 128);
                 }
 #pragma unroll
                 for (int half = 0; half < 2; ++half) {
@@ -512,8 +529,8 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_kernel(const __grid_con
                 // make the generic-proxy writes visible to the TMA engine, make sure the OTHER buffer's previous
                 // store has finished reading shared memory (it is the next one to be overwritten), then store
                 fence_proxy_async_smem();
-                if (Cfg::NBUF == 2 && issuer) tma_store_wait_read<0>();
-                named_bar_sync(1, 128);
+                if (Cfg::NBUF == 2 && TEAMS == 1 && issuer) tma_store_wait_read<0>();
+                named_bar_sync(bar_a, 128);
                 if (issuer) {
                     const int col0 = n0 + grp * 64;
                     if (MODE == 1) {
@@ -525,7 +542,7 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_kernel(const __grid_con
                     }
                     tma_store_commit();
                 }
-                if (Cfg::NBUF == 2) sbuf ^= 1;
+                if (Cfg::NBUF == 2 && TEAMS == 1) sbuf ^= 1;
             }
             // all TMEM reads of this thread have completed (tmem_ld_wait above): hand the accumulator back
             tc_fence_before();

@@ -695,10 +695,11 @@ def conv1x1_wgrad_det(B=2, H=16, W=32, Cin=64, Cout=128, seed=44):
     dz = bf(rnd(B, Cout, H, W, seed=seed + 1))
     ref = torch.nn.grad.conv2d_weight(x, (Cout, Cin, 1, 1), dz)
     outs = []
+    xb, dzb = nhwc(x), nhwc(dz)
     for _ in range(2):
         dw = _garbage(Cout, Cin, 1, 1)
         ws = _garbage(WS_FLOATS)
-        call("b200sr_conv1x1_wgrad_det", ptr(nhwc(x)), Cin, 0, Cin, ptr(nhwc(dz)), Cout, 0, Cout, B, H, W, ptr(dw),
+        call("b200sr_conv1x1_wgrad_det", ptr(xb), Cin, 0, Cin, ptr(dzb), Cout, 0, Cout, B, H, W, ptr(dw),
              ptr(ws), WS_FLOATS, st())
         torch.cuda.synchronize()
         outs.append(dw)
@@ -719,7 +720,8 @@ def conv1_det(B=3, H=64, W=48, seed=7):
         call("b200sr_conv1_fwd", ptr(x), ptr(w), None, None, 0, ptr(ob), ptr(stats), 2 * SLOTS, B, H, W, st())
         dw = _garbage(64, 2, 3, 3)
         ws = _garbage(WS_FLOATS)
-        call("b200sr_conv1_wgrad_det", ptr(x), ptr(nhwc(dz)), ptr(dw), B, H, W, ptr(ws), WS_FLOATS, st())
+        dzb = nhwc(dz)
+        call("b200sr_conv1_wgrad_det", ptr(x), ptr(dzb), ptr(dw), B, H, W, ptr(ws), WS_FLOATS, st())
         torch.cuda.synchronize()
         runs.append((ob, stats, dw))
     out = nchw(runs[0][0])

@@ -225,7 +225,8 @@ def test_maxpool_level(ctx, lvl):
     pb = torch.zeros(B, H // 2, W // 2, C, dtype=torch.bfloat16, device="cuda")
     call("b200sr_maxpool2x2_fwd", ptr(ab), C, 0, C, ptr(pb), B, H, W, st)
     dyb = torch.zeros(B, H, W, C, dtype=torch.bfloat16, device="cuda")
-    call("b200sr_maxpool2x2_bwd", ptr(ab), C, 0, ptr(nhwc(dpool)), ptr(nhwc(dskip)), C, 0, C, ptr(dyb), B, H, W, st)
+    dpb, dsb = nhwc(dpool), nhwc(dskip)   # named: a temporary would be freed (and its memory reused) before the launch
+    call("b200sr_maxpool2x2_bwd", ptr(ab), C, 0, ptr(dpb), ptr(dsb), C, 0, C, ptr(dyb), B, H, W, st)
     torch.cuda.synchronize()
     assert torch.equal(nchw(pb), pooled_ref.detach())
     assert float((nchw(dyb) - dy_ref).abs().max()) == 0.0
