@@ -288,18 +288,36 @@ int num_sms() {
     return n;
 }
 
-template <int BLOCK_N, int MODE, bool SPLIT = false>
+template <int BLOCK_N, int MODE, bool SPLIT = false, bool PAIR = false>
 int launch_conv3_t(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mo, const Conv3Args& args, int grid,
                    cudaStream_t st) {
     constexpr int smem = C3Cfg<BLOCK_N, SPLIT>::SMEM_BYTES;
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(conv3x3_kernel<BLOCK_N, MODE, SPLIT>,
+        cudaError_t e = cudaFuncSetAttribute(conv3x3_kernel<BLOCK_N, MODE, SPLIT, PAIR>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return fail(B200SR_ECUDA, std::string("conv3x3 smem attribute: ") + cudaGetErrorString(e));
         configured = true;
     }
-    conv3x3_kernel<BLOCK_N, MODE, SPLIT><<<grid, c3_threads<BLOCK_N, MODE, SPLIT>(), smem, st>>>(ma, mb, mo, args);
+    if (PAIR) {
+        // clusters of two CTAs (one TPC): tcgen05.mma.cta_group::2
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid);
+        cfg.blockDim = dim3(c3_threads<BLOCK_N, MODE, SPLIT>());
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        cudaLaunchAttribute attr;
+        attr.id = cudaLaunchAttributeClusterDimension;
+        attr.val.clusterDim.x = 2;
+        attr.val.clusterDim.y = 1;
+        attr.val.clusterDim.z = 1;
+        cfg.attrs = &attr;
+        cfg.numAttrs = 1;
+        cudaError_t e = cudaLaunchKernelEx(&cfg, conv3x3_kernel<BLOCK_N, MODE, SPLIT, PAIR>, ma, mb, mo, args);
+        if (e != cudaSuccess) return fail(B200SR_ECUDA, std::string("conv3x3 pair launch: ") + cudaGetErrorString(e));
+        return check_launch("conv3x3_kernel (cta_group::2)");
+    }
+    conv3x3_kernel<BLOCK_N, MODE, SPLIT, PAIR><<<grid, c3_threads<BLOCK_N, MODE, SPLIT>(), smem, st>>>(ma, mb, mo, args);
     return check_launch("conv3x3_kernel");
 }
 
@@ -357,7 +375,16 @@ int run_conv3(int mode, const void* a, int a_stride, int a_coff, int Ca, const v
         rc = make_gather_map(&ma, a, a_stride, a_coff, Ca, B, H, W, C3_TILE_W, C3_TILE_H);
     if (rc) return rc;
     const int taps = mode == 0 ? 9 : (mode == 2 ? 4 : 1);
-    rc = make_weight_map(&mb, w_packed, taps * Ca, n_total, block_n < 128 ? block_n : 128);
+    // CTA pairs (tcgen05.mma.cta_group::2, M = 256) for the N = 64 conv3x3 layers whose weights stay resident in shared
+    // memory (K <= 1152): each CTA of a pair stages half of the weight rows
+    const long long m_tiles_all = static_cast<long long>(B) * (H / C3_TILE_H) * (W / C3_TILE_W);
+    // OPT-IN (B200SR_PAIR=1): measured slower than the single-CTA kernel on this part (enc1.3 forward 299 vs 184 us, dec1.0
+    // 355 vs 336 us, step +0.3 ms; profiles/r2_cta_pair_experiment.txt) — kept as a tested, documented negative result
+    const bool pair_enabled = getenv("B200SR_PAIR") != nullptr;
+    const bool pair = pair_enabled && mode == 0 && block_n == 64 && n_total == 64 && mask == nullptr && split_stride == 0 &&
+                      taps * (Ca / 64) <= C3Cfg<64>::SB && m_tiles_all % 2 == 0 && num_sms() % 2 == 0 &&
+                      getenv("B200SR_NO_BRESIDENT") == nullptr;
+    rc = make_weight_map(&mb, w_packed, taps * Ca, n_total, pair ? 32 : (block_n < 128 ? block_n : 128));
     if (rc) return rc;
     // output tile store: 128 pixels x 64 channels per TMA store; mode 1 scatters through the sub-pixel view
     CUtensorMap mo;
@@ -440,6 +467,8 @@ int run_conv3(int mode, const void* a, int a_stride, int a_coff, int Ca, const v
     if (split_stride > 0)
         return mode == 0 ? dispatch_conv3<0, true>(block_n, ma, mb, mo, args, grid, st)
                          : dispatch_conv3<1, true>(block_n, ma, mb, mo, args, grid, st);
+    if (pair && args.b_resident && grid % 2 == 0) return launch_conv3_t<64, 0, false, true>(ma, mb, mo, args, grid, st);
+    if (pair) return fail(B200SR_EINVAL, "conv3x3: pair mode chosen for a shape it does not cover");
     if (mode == 0 && mask != nullptr) return dispatch_conv3<4>(block_n, ma, mb, mo, args, grid, st);
     if (mode == 0) return dispatch_conv3<0>(block_n, ma, mb, mo, args, grid, st);
     if (mode == 1) return dispatch_conv3<1>(block_n, ma, mb, mo, args, grid, st);

@@ -169,13 +169,25 @@ __host__ __device__ constexpr int c3_threads() {
     return 128 + 128 * c3_teams<BLOCK_N, MODE_T, SPLIT>();
 }
 
-template <int BLOCK_N, int MODE_T, bool SPLIT = false>
+//
+// PAIR (BLOCK_N = 64, MODE 0, resident weights): the kernel runs as clusters of two CTAs (one TPC) issuing
+// tcgen05.mma.cta_group::2 with M = 256: CTA r of a pair owns pixel tile (blockIdx.x + k*gridDim.x) — the pair's two tiles
+// are neighbours — stages its own haloed activation boxes and HALF (32) of the 64 weight rows; the leader (rank 0) issues
+// every MMA, each CTA's accumulator rows land in its own TMEM and are drained by its own epilogue warps. An N = 64 MMA
+// reads 6 KB of shared memory per 32 tensor-core cycles in one CTA (192 B/clk against the 128 B/clk an SM delivers); as a
+// pair each SM reads 5 KB. Barriers: TMA bytes of both CTAs are credited to the leader's "full" barriers, MMA completion is
+// multicast to both CTAs' "empty" / "accumulator full" barriers, the peer's epilogue arrives remotely on the leader's
+// "accumulator empty" barrier.
+template <int BLOCK_N, int MODE_T, bool SPLIT = false, bool PAIR = false>
 __global__ void __launch_bounds__((c3_threads<BLOCK_N, MODE_T, SPLIT>()), 1) conv3x3_kernel(const __grid_constant__ CUtensorMap map_a,
                                                                 const __grid_constant__ CUtensorMap map_b,
                                                                 const __grid_constant__ CUtensorMap map_out,
                                                                 const Conv3Args args) {
     using Cfg = C3Cfg<BLOCK_N, SPLIT>;
     static_assert(!SPLIT || MODE_T == 0 || MODE_T == 1, "SPLIT epilogue exists for conv3x3 forward and ConvT forward");
+    static_assert(!PAIR || (BLOCK_N == 64 && MODE_T == 0 && !SPLIT), "CTA pairs exist for the N = 64 conv3x3 kernel");
+    const uint32_t pair_rank = PAIR ? cluster_ctarank() : 0u;
+    const bool leader = pair_rank == 0;
     constexpr int SB = Cfg::SB, NH = Cfg::NH, BN_SLOT = Cfg::BN_SLOT;
     constexpr int TEAMS = c3_teams<BLOCK_N, MODE_T, SPLIT>();
     const int SA = args.sa;
@@ -221,13 +233,18 @@ __global__ void __launch_bounds__((c3_threads<BLOCK_N, MODE_T, SPLIT>()), 1) con
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(&acc_full[s], 1);
-            mbar_init(&acc_empty[s], 128 * TEAMS);
+            mbar_init(&acc_empty[s], PAIR ? 256 : 128 * TEAMS);  // pair: both CTAs' epilogue threads arrive on the leader's
         }
         fence_barrier_init();
     }
     if (warp == 2) {
-        tmem_alloc(tmem_ptr_smem, 2 * BLOCK_N);
-        tmem_relinquish();
+        if (PAIR) {
+            tmem_alloc_2sm(tmem_ptr_smem, 2 * BLOCK_N);
+            tmem_relinquish_2sm();
+        } else {
+            tmem_alloc(tmem_ptr_smem, 2 * BLOCK_N);
+            tmem_relinquish();
+        }
     }
     if (warp >= 4 && warp < 8 && blockIdx.x < args.num_tiles) {
         // the tile schedule keeps a CTA on one column block, so its affine vectors can be staged once
@@ -239,7 +256,10 @@ __global__ void __launch_bounds__((c3_threads<BLOCK_N, MODE_T, SPLIT>()), 1) con
         }
     }
     tc_fence_before();
-    __syncthreads();
+    if (PAIR)
+        cluster_sync_all();  // both CTAs' barriers are initialised and their TMEM allocated before anything crosses over
+    else
+        __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
 
@@ -261,6 +281,11 @@ __global__ void __launch_bounds__((c3_threads<BLOCK_N, MODE_T, SPLIT>()), 1) con
                 for (int c = 0; c < chunks; ++c) {
                     for (int dw = 0; dw < NG; ++dw) {
                         mbar_wait(&a_empty[sa], pa ^ 1);
+                        if (PAIR) {
+                            // both CTAs load their own box; the bytes of both are credited to the leader's barrier
+                            if (leader) mbar_arrive_expect_tx(&a_full[sa], 2 * A_BYTES);
+                            tma_load_4d_2sm(&map_a, &a_full[sa], ring_a + sa * C3_A_SLOT, c * 64, w0 + dw - 1, h0 - 1, img);
+                        } else {
                         mbar_arrive_expect_tx(&a_full[sa], A_BYTES);
                         if (MODE == 0)
                             tma_load_4d(&map_a, &a_full[sa], ring_a + sa * C3_A_SLOT, c * 64, w0 + dw - 1, h0 - 1, img);
@@ -269,6 +294,7 @@ __global__ void __launch_bounds__((c3_threads<BLOCK_N, MODE_T, SPLIT>()), 1) con
                         else
                             tma_load_5d(&map_a, &a_full[sa], ring_a + sa * C3_A_SLOT, c * 64, dw & 1, w0, dw >> 1,
                                         img * args.H + h0);
+                        }
                         if (++sa == SA) {
                             sa = 0;
                             pa ^= 1;
@@ -277,6 +303,16 @@ __global__ void __launch_bounds__((c3_threads<BLOCK_N, MODE_T, SPLIT>()), 1) con
                             const int kcol = (MODE == 0 ? (dh * 3 + dw) : dw) * args.C + c * 64;
 #pragma unroll
                             for (int nh = 0; nh < NH; ++nh) {
+                                if (PAIR) {
+                                    // resident weights (host guarantees it): each CTA keeps 32 of the 64 rows
+                                    if (tile == static_cast<int>(blockIdx.x)) {
+                                        if (leader) mbar_arrive_expect_tx(&b_full[sb], Cfg::B_SLOT);  // 2 x 4 KB
+                                        tma_load_2d_2sm(&map_b, &b_full[sb], ring_b + sb * Cfg::B_SLOT, kcol,
+                                                        n0 + static_cast<int>(pair_rank) * (BN_SLOT / 2));
+                                        ++sb;
+                                    }
+                                    continue;
+                                }
                                 if (args.b_resident) {
                                     // slot = position in the (fixed) per-tile consumption order; loaded once
                                     if (tile == static_cast<int>(blockIdx.x)) {
@@ -302,8 +338,8 @@ __global__ void __launch_bounds__((c3_threads<BLOCK_N, MODE_T, SPLIT>()), 1) con
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        if (elect_one()) {
-            constexpr uint32_t idesc = umma_idesc_bf16(128, BN_SLOT, 0, 0);
+        if ((!PAIR || leader) && elect_one()) {
+            constexpr uint32_t idesc = umma_idesc_bf16(PAIR ? 256 : 128, BN_SLOT, 0, 0);
             int sa = 0, sb = 0, as = 0;
             uint32_t pa = 0, pb = 0, pacc = 0;
             for (int tile = blockIdx.x; tile < args.num_tiles; tile += gridDim.x) {
@@ -325,8 +361,12 @@ __global__ void __launch_bounds__((c3_threads<BLOCK_N, MODE_T, SPLIT>()), 1) con
                                 const uint64_t db = umma_smem_desc_sw128(smem_u32(ring_b + sb * Cfg::B_SLOT), 0, 1024);
                                 const uint32_t first = (c | dw | dh) == 0 ? 0u : 1u;
 #pragma unroll
-                                for (int k = 0; k < 4; ++k)
-                                    umma_bf16(d_base + nh * BN_SLOT, da + 2 * k, db + 2 * k, idesc, first | k);
+                                for (int k = 0; k < 4; ++k) {
+                                    if (PAIR)
+                                        umma_bf16_2sm(d_base + nh * BN_SLOT, da + 2 * k, db + 2 * k, idesc, first | k);
+                                    else
+                                        umma_bf16(d_base + nh * BN_SLOT, da + 2 * k, db + 2 * k, idesc, first | k);
+                                }
                                 if (args.b_resident) {
                                     ++sb;
                                 } else {
@@ -338,14 +378,20 @@ __global__ void __launch_bounds__((c3_threads<BLOCK_N, MODE_T, SPLIT>()), 1) con
                                 }
                             }
                         }
-                        umma_commit(&a_empty[sa]);
+                        if (PAIR)
+                            umma_commit_2sm(&a_empty[sa]);  // frees the slot in both CTAs
+                        else
+                            umma_commit(&a_empty[sa]);
                         if (++sa == SA) {
                             sa = 0;
                             pa ^= 1;
                         }
                     }
                 }
-                umma_commit(&acc_full[as]);
+                if (PAIR)
+                    umma_commit_2sm(&acc_full[as]);  // both CTAs' epilogues
+                else
+                    umma_commit(&acc_full[as]);
                 if (++as == 2) {
                     as = 0;
                     pacc ^= 1;
@@ -546,7 +592,10 @@ __global__ void __launch_bounds__((c3_threads<BLOCK_N, MODE_T, SPLIT>()), 1) con
             }
             // all TMEM reads of this thread have completed (tmem_ld_wait above): hand the accumulator back
             tc_fence_before();
-            mbar_arrive(&acc_empty[as]);
+            if (PAIR && !leader)
+                mbar_arrive_cluster(&acc_empty[as], 0);  // the leader's MMA thread waits for both CTAs' epilogues
+            else
+                mbar_arrive(&acc_empty[as]);
             if (++as == 2) {
                 as = 0;
                 pacc ^= 1;
@@ -590,10 +639,16 @@ __global__ void __launch_bounds__((c3_threads<BLOCK_N, MODE_T, SPLIT>()), 1) con
     }
 
     tc_fence_before();
-    __syncthreads();
+    if (PAIR)
+        cluster_sync_all();  // neither CTA's TMEM / barriers go away while the other may still touch them
+    else
+        __syncthreads();
     if (warp == 2) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, 2 * BLOCK_N);
+        if (PAIR)
+            tmem_dealloc_2sm(tmem_base, 2 * BLOCK_N);
+        else
+            tmem_dealloc(tmem_base, 2 * BLOCK_N);
     }
     if (MODE == 0 && !SPLIT && args.bn_scale != nullptr && blockIdx.x < args.num_tiles) {
         // fused BatchNorm finalize: one ticket per CTA of this column block; the last one sums the slots in slot order

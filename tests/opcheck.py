@@ -647,6 +647,20 @@ def conv3x3_fwd_bn_fused(B=6, H=64, W=64, Cin=64, Cout=128, seed=72):
             "bitwise": float(sum((a - b).abs().max() for a, b in zip(runs[0][1:4], runs[1][1:4])))}
 
 
+def conv3x3_fwd_cta_pair(**kw):
+    """The opt-in cta_group::2 (two-SM MMA, M = 256) variant of the N = 64 conv kernel: same parity and bit-reproducibility
+    checks as the default kernel, and bit-identical to it."""
+    import os
+    base = conv3x3_fwd_slots(**kw)
+    os.environ["B200SR_PAIR"] = "1"
+    try:
+        res = conv3x3_fwd_slots(**kw)
+    finally:
+        del os.environ["B200SR_PAIR"]
+    res["same_as_single_cta"] = abs(res["stats_sq"] - base["stats_sq"]) + abs(res["out"] - base["out"])
+    return res
+
+
 def conv3x3_wgrad_det(B=2, H=16, W=32, Cin=64, Cout=128, seed=3, cin_total=None, cin_off=0):
     _setup()
     x = bf(rnd(B, Cin, H, W, seed=seed))
@@ -1017,6 +1031,10 @@ CHECKS = {
     "fused_conv_bn_finalize_n1024": (conv3x3_fwd_bn_fused, dict(Cin=512, Cout=1024, B=8, H=16, W=16),
                                      {"z": BF16, "scale": 1e-5, "shift": 1e-4, "invstd": 1e-5, "running_mean": 1e-5,
                                       "counters_reset": 0.0, "bitwise": 0.0}),
+    "cta_pair_conv3x3_n64": (conv3x3_fwd_cta_pair, dict(Cin=128, Cout=64, B=4, H=128, W=64),
+                             {"out": BF16, "stats_sum": 1e-4, "stats_sq": 1e-4, "bitwise": 0.0, "same_as_single_cta": 0.0}),
+    "cta_pair_conv3x3_n64_small": (conv3x3_fwd_cta_pair, dict(Cin=64, Cout=64, B=1, H=16, W=16),
+                                   {"out": BF16, "stats_sum": 1e-4, "stats_sq": 1e-4, "bitwise": 0.0}),
     "det_conv3x3_wgrad_modeA": (conv3x3_wgrad_det, dict(Cin=256, Cout=256, B=3, H=16, W=32), {"dw": BF16, "bitwise": 0.0}),
     "det_conv3x3_wgrad_modeB": (conv3x3_wgrad_det, dict(Cin=64, Cout=64, B=4, H=64, W=64), {"dw": BF16, "bitwise": 0.0}),
     "det_conv3x3_wgrad_n64": (conv3x3_wgrad_det, dict(Cin=128, Cout=64, B=2, H=32, W=64), {"dw": BF16, "bitwise": 0.0}),
