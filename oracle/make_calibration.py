@@ -93,6 +93,58 @@ def train_entry(ref_loader, sd, case, loss_name):
             "post_adam_weights": adam_w, "adam_update_cos": adam_cos}
 
 
+def generic_entry(make_model, sd, inputs, loss_of):
+    """fp32 vs bf16-autocast run of an unmodified reference module: outputs, loss, every gradient."""
+    def run(autocast):
+        m = make_model()
+        m.load_state_dict(sd)
+        m.train()
+        if autocast:
+            with torch.autocast("cpu", dtype=torch.bfloat16):
+                outs = m(*inputs)
+        else:
+            outs = m(*inputs)
+        outs = outs if isinstance(outs, (tuple, list)) else (outs,)
+        outs = [o.float() for o in outs]
+        loss = loss_of(outs)
+        loss.backward()
+        return float(loss), [o.detach() for o in outs], {k: p.grad.detach().float().clone() for k, p in m.named_parameters()}
+
+    l32, o32, g32 = run(False)
+    l16, o16, g16 = run(True)
+    grads = {k: [rel(g16[k], g32[k]), cos(g16[k], g32[k])] for k in g32 if g32[k].norm() > 1e-7}
+    # eval mode after ONE train-mode forward (the running statistics the GPU eval tests use)
+    m = make_model()
+    m.load_state_dict(sd)
+    m.train()
+    with torch.no_grad():
+        m(*inputs)
+        m.eval()
+        e32 = m(*inputs)
+        with torch.autocast("cpu", dtype=torch.bfloat16):
+            e16 = m(*inputs)
+    e32 = e32 if isinstance(e32, (tuple, list)) else (e32,)
+    e16 = e16 if isinstance(e16, (tuple, list)) else (e16,)
+    return {"loss_fp32": l32, "loss": abs(l16 - l32) / abs(l32), "out": [rel(a, b) for a, b in zip(o16, o32)], "grads": grads,
+            "eval_out": [rel(a.float(), b) for a, b in zip(e16, e32)]}
+
+
+def progressive_entry(ref_loader):
+    sd = cases.seeded_state_dict(ref_loader.ProgressiveUNet, seed=3)
+    c = cases.PROGRESSIVE_CASE
+    sl = cases.seeded_slices(c["B"], c["H"], c["W"], c["seed"])
+    w = unet_oracle.PROGRESSIVE_LOSS_WEIGHTS
+    loss_of = lambda outs: sum(wi * torch.nn.functional.mse_loss(o, sl[:, k:k + 1]) for wi, o, k in zip(w, outs, (1, 2, 3)))
+    return generic_entry(ref_loader.ProgressiveUNet, sd, (sl,), loss_of)
+
+
+def deepcnn_entry(ref_loader):
+    sd = cases.seeded_state_dict(ref_loader.DeepCNN, seed=5)
+    c = cases.DEEPCNN_CASE
+    x, y = cases.seeded_batch(c["B"], c["H"], c["W"], c["seed"])
+    return generic_entry(ref_loader.DeepCNN, sd, (x,), lambda outs: torch.nn.functional.mse_loss(outs[0], y))
+
+
 def eval_entry(ref_loader, sd, case):
     # non-trivial running statistics: the ones one train step on the small case produces (as tests/e2echeck.py does)
     c = cases.TRAIN_CASE
@@ -119,6 +171,9 @@ def main():
     print("train_small")
     cal["train_small_mse"] = train_entry(ref_loader, sd, cases.TRAIN_CASE, "mse")
     cal["train_small_combined"] = train_entry(ref_loader, sd, cases.TRAIN_CASE, "combined")
+    print("progressive_small / deepcnn_small")
+    cal["progressive_small"] = progressive_entry(ref_loader)
+    cal["deepcnn_small"] = deepcnn_entry(ref_loader)
     print("eval_b8")
     cal["eval_b8"] = eval_entry(ref_loader, sd, BIG_EVAL)
     if "--skip-b32" not in sys.argv:
@@ -129,6 +184,10 @@ def main():
     with open(OUT, "w") as f:
         json.dump(cal, f, indent=1, sort_keys=True)
     print("wrote", OUT)
+    for k in ("progressive_small", "deepcnn_small"):
+        v = cal[k]
+        worst = max(v["grads"].items(), key=lambda kv: kv[1][0])
+        print(f"{k}: out {v['out']} loss {v['loss']:.2e} worst grad {worst[0]} rel {worst[1][0]:.2e} cos {worst[1][1]:.4f}")
     for k, v in cal.items():
         if k.startswith("train"):
             worst = max(v["grads"].items(), key=lambda kv: kv[1][0])

@@ -1,8 +1,11 @@
 """GPU parity of the DeepCNN residual baseline against the CPU oracle / golden fixtures.
 
-Tolerances: every kernel holds rel-L2 1e-2 per op (test_gpu_ops.py). End to end on this random-init case the REFERENCE
-under torch.autocast(bfloat16) deviates from its own fp32 run by 3.8e-2 on the output, 4.1e-3 on the loss and
-0.1-0.45 rel-L2 on gradients (cosine 0.90-0.99), so the gates are: output 6e-2, loss 1e-2, gradient cosines."""
+Tolerances: every kernel holds rel-L2 1e-2 per op (test_gpu_ops.py). End to end on this random-init case the unmodified
+REFERENCE under torch.autocast(bfloat16) deviates from its own fp32 run by 3.8e-2 on the output, 4.1e-3 on the LOSS (the
+un-normalised kaiming(fan_out) init puts the output at ~1e3, so the 1e-3 loss bar is below what any bf16 execution of this
+case holds) and up to 0.53 rel-L2 / cosine 0.877 on gradients (tests/golden/bf16_calibration.json `deepcnn_small`,
+oracle/make_calibration.py). Gates: max(north-star bound, 1.5 x that reference deviation) per quantity and per tensor."""
+import json
 import os
 
 import numpy as np
@@ -14,6 +17,8 @@ from oracle import cases, unet_oracle
 
 pytestmark = pytest.mark.gpu
 GOLD = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "deepcnn_golden.npz"))
+with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "bf16_calibration.json")) as _f:
+    CAL = json.load(_f)["deepcnn_small"]
 
 
 def rel(a, b):
@@ -44,16 +49,18 @@ def test_train_forward_backward_matches_oracle():
     loss, dout = crit.value_and_grad(out, y.cuda())
     eng.backward(dout)
     torch.cuda.synchronize()
-    assert rel(out.cpu(), o_out) < 6e-2
-    assert abs(float(loss) - float(o_loss)) / float(o_loss) < 1e-2
+    assert abs(float(o_loss) - CAL["loss_fp32"]) / CAL["loss_fp32"] < 1e-5   # same case as the calibration run
+    assert rel(out.cpu(), o_out) <= max(1e-2, 1.5 * CAL["out"][0]), (rel(out.cpu(), o_out), CAL["out"])
+    assert abs(float(loss) - float(o_loss)) / float(o_loss) <= max(1e-3, 1.5 * CAL["loss"]), CAL["loss"]
     for (name, _), g in zip(m.named_parameters(), eng.grad_views):
         ref = o_grads[name]
-        if ref.norm() < 1e-9:
+        if ref.norm() < 1e-7:
             continue
-        cs = cos(g.cpu(), ref)
-        assert cs > 0.5, (name, cs)
-        if name.startswith(("output_conv", "layer4.1.bn2", "layer4.1.conv2")):
-            assert cs > 0.95, (name, cs)
+        r, cs = rel(g.cpu(), ref), cos(g.cpu(), ref)
+        r_cal, c_cal = CAL["grads"][name]
+        shallow = name.startswith(("output_conv", "layer4.1.bn2", "layer4.1.conv2"))
+        assert r <= max(1e-2, 1.5 * r_cal), (name, r, r_cal)
+        assert cs >= min(0.99 if shallow else 0.9, 1.0 - 1.5 * (1.0 - c_cal)), (name, cs, c_cal)
     msd = m.state_dict()
     assert max(rel(msd[k].cpu(), v) for k, v in o_stats.items()) < 1e-2
 
@@ -67,7 +74,8 @@ def test_eval_forward_matches_golden():
     m = _model(sd).eval()
     with torch.no_grad():
         out = m(x.cuda())
-    assert rel(out.cpu(), torch.from_numpy(GOLD["eval_out"])) < 6e-2
+    r = rel(out.cpu(), torch.from_numpy(GOLD["eval_out"]))
+    assert r <= max(1e-2, 1.5 * CAL["eval_out"][0]), (r, CAL["eval_out"])   # north-star bf16 bound (reference bf16: 4.1e-3)
 
 
 def test_trainer_learns(tmp_path):

@@ -1,5 +1,8 @@
-"""GPU parity of the Progressive UNet chain against the CPU oracle / golden fixtures. Tolerances as in
-test_gpu_unet.py: loss 1e-3 relative, forward 2.5e-2 (bf16 end to end), gradients by cosine."""
+"""GPU parity of the Progressive UNet chain against the CPU oracle / golden fixtures. Gates as in
+test_gpu_parity_big.py: loss 1e-3 relative; outputs and every gradient gated PER TENSOR by the unmodified reference's own
+bf16-autocast deviation on this case (tests/golden/bf16_calibration.json `progressive_small`, oracle/make_calibration.py):
+rel-L2 <= max(1e-2, 1.5 x reference), cosine >= 0.9 (0.99 for the heads / dec1) unless the reference itself is below."""
+import json
 import os
 
 import numpy as np
@@ -11,6 +14,8 @@ from oracle import cases, unet_oracle
 
 pytestmark = pytest.mark.gpu
 GOLD = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "progressive_golden.npz"))
+with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "bf16_calibration.json")) as _f:
+    CAL = json.load(_f)["progressive_small"]
 
 
 def rel(a, b):
@@ -38,7 +43,7 @@ def test_eval_forward_matches_golden():
     with torch.no_grad():
         outs = m(sl.cuda())
     for o, k in zip(outs, ("eval_p1", "eval_p2", "eval_p3")):
-        assert rel(o.cpu(), torch.from_numpy(GOLD[k])) < 2.5e-2, k
+        assert rel(o.cpu(), torch.from_numpy(GOLD[k])) < 1e-2, k   # eval mode: the north-star bf16 bound
 
 
 def test_train_step_matches_oracle():
@@ -56,18 +61,18 @@ def test_train_step_matches_oracle():
     loss.backward()
     torch.cuda.synchronize()
     assert abs(float(loss) - float(o_loss)) / float(o_loss) < 1e-3
-    for got, ref in zip((p1, p2, p3), o_out):
-        assert rel(got.detach().cpu(), ref) < 2.5e-2
+    assert abs(float(o_loss) - CAL["loss_fp32"]) / CAL["loss_fp32"] < 1e-5   # same case as the calibration run
+    for got, ref, r_cal in zip((p1, p2, p3), o_out, CAL["out"]):
+        assert rel(got.detach().cpu(), ref) <= max(1e-2, 1.5 * r_cal), (rel(got.detach().cpu(), ref), r_cal)
     for name, p in m.named_parameters():
         ref = o_grads[name]
         if ref.norm() < 1e-7:
             continue
-        cs = cos(p.grad.cpu(), ref)
-        assert cs > 0.5, (name, cs)
-        if name.startswith(("unet2.final", "unet3.final", "unet2.dec1", "unet3.dec1")):
-            assert cs > 0.95, (name, cs)
-    # stage 1 receives gradient through BOTH second-stage networks: its head gradient must match closely
-    assert cos(m.unet1.final.weight.grad.cpu(), o_grads["unet1.final.weight"]) > 0.95
+        r, cs = rel(p.grad.cpu(), ref), cos(p.grad.cpu(), ref)
+        r_cal, c_cal = CAL["grads"][name]
+        shallow = name.split(".", 1)[1].startswith(("final", "dec1"))
+        assert r <= max(1e-2, 1.5 * r_cal), (name, r, r_cal)
+        assert cs >= min(0.99 if shallow else 0.9, 1.0 - 1.5 * (1.0 - c_cal)), (name, cs, c_cal)
 
 
 def test_trainer_matches_autograd_and_learns(tmp_path):
