@@ -368,6 +368,13 @@ int64_t b200sr_bn_bwd_ws_floats(int C);
 int b200sr_bn_bwd_reduce_det(const void* dy, int dy_pix_stride, int dy_c_off, const void* z, int C, const float* scale,
                              const float* shift, const float* mean, const float* invstd, float* sums, float* ws,
                              int64_t ws_floats, uint32_t* counters, const void* mask_src, int64_t npix, void* stream);
+/* b200sr_maxpool2x2_bwd (unet_model.py:52-61 backward + skip-connection add) fused with b200sr_bn_bwd_reduce_det of the
+ * BatchNorm+ReLU the gradient flows into (the encoder block's conv.4/conv.5): dy (B,H,W,C) dense is written AND reduced
+ * against z in the same pass; sums[2][C] as b200sr_bn_bwd_reduce_det writes them. C % 64 == 0. */
+int b200sr_maxpool2x2_bwd_bnred(const void* act, int act_pix_stride, int act_c_off, const void* dpool, const void* dskip,
+                                int dskip_pix_stride, int dskip_c_off, int C, void* dy, const void* z, const float* scale,
+                                const float* shift, const float* mean, const float* invstd, float* sums, float* ws,
+                                int64_t ws_floats, uint32_t* counters, int B, int H, int W, void* stream);
 /* 1x1 head backward with dw (64) / db (1) WRITTEN; ws: 72 floats per CTA (up to 4 CTAs per SM); counter: 1 uint32. */
 int b200sr_head_bwd_det(const float* dout, const void* act, const float* w, void* dact, float* dw, float* db,
                         int64_t npix, float* ws, int64_t ws_floats, uint32_t* counter, void* stream);

@@ -94,6 +94,8 @@ _SIGNATURES = {
     "b200sr_sum_slots": [_P, c_int, c_int64, c_int, _P, _P],
     "b200sr_bn_bwd_ws_floats": [c_int],
     "b200sr_bn_bwd_reduce_det": [_P, c_int, c_int, _P, c_int, _P, _P, _P, _P, _P, _P, c_int64, _P, _P, c_int64, _P],
+    "b200sr_maxpool2x2_bwd_bnred": [_P, c_int, c_int, _P, _P, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, _P, c_int64,
+                                    _P, c_int, c_int, c_int, _P],
     "b200sr_head_bwd_det": [_P, _P, _P, _P, _P, _P, c_int64, _P, c_int64, _P, _P],
     "b200sr_mse_ssim_det": [_P, _P, _P, _P, c_int, c_int, c_int, _P, c_int, c_float, c_float, c_float, c_float, c_float,
                             _P, c_int64, _P, _P],
@@ -177,6 +179,8 @@ def _cost(name, a):
         return 2.0 * a[8] * a[9] * a[10] * a[3] * a[7] * 4, 0.0
     if name == "b200sr_conv1x1_wgrad_det":
         return 2.0 * a[8] * a[9] * a[10] * a[3] * a[7], 0.0
+    if name == "b200sr_maxpool2x2_bwd_bnred":
+        return 0.0, a[18] * a[19] * a[20] * a[7] * 2.0 * 4.25   # act, dskip, z read + dy written + dpool/4
     if name == "b200sr_bn_bwd_reduce_det":
         return 0.0, a[14] * a[4] * 2.0 * 2
     if name == "b200sr_head_bwd_det":

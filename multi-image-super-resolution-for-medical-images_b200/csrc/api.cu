@@ -570,7 +570,8 @@ int launch_wgrad3_t(const CUtensorMap& mx, const CUtensorMap& mz, WG3Args& args,
     int best = 1;
     double best_score = -1.0;
     // up to two waves' worth of splits: a single-job layer (Cin = Cout = 64) must still be able to fill every SM
-    const int split_cap = 2 * sms > 64 ? 2 * sms : 64;
+    static const int cap_env = getenv("B200SR_WGRAD_SPLIT_CAP") ? atoi(getenv("B200SR_WGRAD_SPLIT_CAP")) : 0;
+    const int split_cap = cap_env > 0 ? cap_env : (2 * sms > 64 ? 2 * sms : 64);
     int max_splits = args.total_chunks < split_cap ? args.total_chunks : split_cap;
     if (ws_max_splits > 0 && max_splits > ws_max_splits) max_splits = ws_max_splits;  // partial workspace capacity
     for (int s = 1; s <= max_splits; ++s) {
@@ -1100,6 +1101,30 @@ int b200sr_volume_metrics(const float* original, const float* predicted, int S, 
     a.nimages = S;
     mse_ssim_fast_kernel<7><<<grid_m, 256, LsFast<7>::SMEM_BYTES, st>>>(a);
     return check_launch("volume_metrics kernels");
+}
+
+/* MaxPool2d(2,2) backward + skip add (b200sr_maxpool2x2_bwd) fused with pass 1 of the BatchNorm+ReLU backward of the layer
+ * the gradient flows into (b200sr_bn_bwd_reduce_det on the dy it writes): saves the re-read of dy and one launch. */
+int b200sr_maxpool2x2_bwd_bnred(const void* act, int act_pix_stride, int act_c_off, const void* dpool, const void* dskip,
+                                int dskip_pix_stride, int dskip_c_off, int C, void* dy, const void* z, const float* scale,
+                                const float* shift, const float* mean, const float* invstd, float* sums, float* ws,
+                                int64_t ws_floats, uint32_t* counters, int B, int H, int W, void* stream) {
+    B2_CHECK_ARG(act && dpool && dskip && dy && z && scale && shift && mean && invstd && sums && ws && counters);
+    B2_CHECK_ARG(C % 64 == 0 && act_pix_stride % 8 == 0 && act_c_off % 8 == 0 && dskip_pix_stride % 8 == 0 &&
+                 dskip_c_off % 8 == 0 && H % 2 == 0 && W % 2 == 0 && B > 0);
+    B2_CHECK_ARG(aligned16(act) && aligned16(dpool) && aligned16(dskip) && aligned16(dy) && aligned16(z) && aligned16(ws));
+    const int groups = C / 64;
+    const long long nquads = static_cast<long long>(B) * (H / 2) * (W / 2);
+    long long slices = (num_sms() * 2) / groups;
+    if (slices > (nquads + 31) / 32) slices = (nquads + 31) / 32;
+    if (slices > ws_floats / (128LL * groups)) slices = ws_floats / (128LL * groups);
+    B2_CHECK_ARG(slices >= 1);
+    dim3 grid(static_cast<unsigned>(slices), static_cast<unsigned>(groups));
+    maxpool2x2_bwd_bnred_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16*>(act), act_pix_stride, act_c_off, static_cast<const __nv_bfloat16*>(dpool),
+        static_cast<const __nv_bfloat16*>(dskip), dskip_pix_stride, dskip_c_off, C, static_cast<__nv_bfloat16*>(dy),
+        static_cast<const __nv_bfloat16*>(z), scale, shift, mean, invstd, sums, ws, counters, H, W, nquads);
+    return check_launch("maxpool2x2_bwd_bnred_kernel");
 }
 
 // ---- DeepCNN residual baseline -------------------------------------------------------------

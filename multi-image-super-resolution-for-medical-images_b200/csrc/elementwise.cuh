@@ -868,6 +868,55 @@ __global__ void __launch_bounds__(256, 3) bn_bwd_reduce_fast_kernel(const __nv_b
     }
 }
 
+// Block- and grid-level finish shared by the deterministic BatchNorm-backward reductions: thread (tx = tid & 7, ty = tid >> 3)
+// holds partial sums of channels blockIdx.y*64 + tx*8 .. +7 over its pixels. Pixel lanes are combined in lane order, the
+// block's 128 sums go to its own slot, and the last block of the channel group (ticket) adds the slots in slice order.
+__device__ __forceinline__ void bn_red_block_finish(const float (&s1)[8], const float (&s2)[8], float* __restrict__ sums,
+                                                    float* __restrict__ ws, unsigned* __restrict__ counters,
+                                                    const float* __restrict__ invstd, int C) {
+    const int slices = gridDim.x, slice = blockIdx.x, group = blockIdx.y;
+    const int tx = threadIdx.x & 7, ty = threadIdx.x >> 3;
+    __shared__ float red[2][32][65];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        red[0][ty][tx * 8 + k] = s1[k];
+        red[1][ty][tx * 8 + k] = s2[k];
+    }
+    __syncthreads();
+    float* slot = ws + (static_cast<size_t>(group) * slices + slice) * 128;
+    if (threadIdx.x < 128) {
+        const int which = threadIdx.x >> 6, ch = threadIdx.x & 63;
+        float acc = 0.f;
+#pragma unroll 8
+        for (int r = 0; r < 32; ++r) acc += red[which][r][ch];
+        slot[threadIdx.x] = acc;
+    }
+    if (!last_block_ticket(counters + group, static_cast<unsigned>(slices))) return;
+    // last block of this channel group: 32 float4 columns x 8 slice-lanes, lanes combined in lane order
+    __shared__ float4 s_t[8][32];
+    const int col4 = threadIdx.x & 31, sl = threadIdx.x >> 5;
+    const float4* base = reinterpret_cast<const float4*>(ws + static_cast<size_t>(group) * slices * 128) + col4;
+    float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 8
+    for (int r = sl; r < slices; r += 8) {
+        const float4 v = __ldcg(base + static_cast<size_t>(r) * 32);
+        a4.x += v.x;
+        a4.y += v.y;
+        a4.z += v.z;
+        a4.w += v.w;
+    }
+    s_t[sl][col4] = a4;
+    __syncthreads();
+    if (threadIdx.x < 128) {
+        const int which = threadIdx.x >> 6, ch = threadIdx.x & 63;
+        float acc = 0.f;
+#pragma unroll
+        for (int l = 0; l < 8; ++l) acc += reinterpret_cast<const float*>(&s_t[l][0])[threadIdx.x];
+        if (which == 1) acc *= invstd[group * 64 + ch];
+        sums[static_cast<size_t>(which) * C + group * 64 + ch] = acc;
+    }
+}
+
 // Deterministic BatchNorm+ReLU backward reduction (pass 1). grid = (slices, C/64): a block owns 64 channels (8 threads
 // x 8 channels per pixel) and every `slices`-th group of 32 pixels; its 128 partial sums go to its own slot of `ws`; the
 // last block of a channel group (ticket counter per group) sums that group's slots in slice order and writes the final
@@ -918,48 +967,77 @@ __global__ void __launch_bounds__(256, 3) bn_bwd_reduce_det_kernel(
             }
         }
     }
-    // in-block: pixel lanes combined in lane order
-    __shared__ float red[2][32][65];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        red[0][ty][tx * 8 + k] = s1[k];
-        red[1][ty][tx * 8 + k] = s2[k];
-    }
-    __syncthreads();
-    float* slot = ws + (static_cast<size_t>(group) * slices + slice) * 128;
-    if (threadIdx.x < 128) {
-        const int which = threadIdx.x >> 6, ch = threadIdx.x & 63;
-        float acc = 0.f;
-#pragma unroll 8
-        for (int r = 0; r < 32; ++r) acc += red[which][r][ch];
-        slot[threadIdx.x] = acc;
-    }
-    if (!last_block_ticket(counters + group, static_cast<unsigned>(slices))) return;
-    // last block of this channel group: 32 float4 columns x 8 slice-lanes, lanes combined in lane order
-    __shared__ float4 s_t[8][32];
-    const int col4 = threadIdx.x & 31, sl = threadIdx.x >> 5;
-    const float4* base = reinterpret_cast<const float4*>(ws + static_cast<size_t>(group) * slices * 128) + col4;
-    float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 8
-    for (int r = sl; r < slices; r += 8) {
-        const float4 v = __ldcg(base + static_cast<size_t>(r) * 32);
-        a4.x += v.x;
-        a4.y += v.y;
-        a4.z += v.z;
-        a4.w += v.w;
-    }
-    s_t[sl][col4] = a4;
-    __syncthreads();
-    if (threadIdx.x < 128) {
-        const int which = threadIdx.x >> 6, ch = threadIdx.x & 63;
-        float acc = 0.f;
-#pragma unroll
-        for (int l = 0; l < 8; ++l) acc += reinterpret_cast<const float*>(&s_t[l][0])[threadIdx.x];
-        if (which == 1) acc *= invstd[group * 64 + ch];
-        sums[static_cast<size_t>(which) * C + group * 64 + ch] = acc;
-    }
+    bn_red_block_finish(s1, s2, sums, ws, counters, invstd, C);
 }
 
+// MaxPool2d(2,2) backward + skip-gradient add (maxpool2x2_bwd_kernel) that ALSO produces the BatchNorm+ReLU backward
+// reduction of the layer the gradient flows into (encoder conv.3 -> BN -> ReLU -> {skip, pool}): the dY it writes is the very
+// tensor bn_bwd_reduce_det would read back, so the separate reduction pass (and its re-read of dY) disappears; the sums are
+// taken from the values as stored (bf16), exactly like the two-kernel path. grid = (slices, C/64); a block owns 64
+// channels and every slices-th group of 32 2x2 quads.
+__global__ void __launch_bounds__(256, 2) maxpool2x2_bwd_bnred_kernel(
+    const __nv_bfloat16* __restrict__ act, int act_stride, int act_coff, const __nv_bfloat16* __restrict__ dpool,
+    const __nv_bfloat16* __restrict__ dskip, int dskip_stride, int dskip_coff, int C, __nv_bfloat16* __restrict__ dy,
+    const __nv_bfloat16* __restrict__ z, const float* __restrict__ scale, const float* __restrict__ shift,
+    const float* __restrict__ mean, const float* __restrict__ invstd, float* __restrict__ sums, float* __restrict__ ws,
+    unsigned* __restrict__ counters, int H, int W, long long nquads) {
+    const int slices = gridDim.x, slice = blockIdx.x, group = blockIdx.y;
+    const int tx = threadIdx.x & 7, ty = threadIdx.x >> 3;
+    const int c = group * 64 + tx * 8;
+    const int W2 = W >> 1, H2 = H >> 1;
+    const F8 sc = ld_f32x8(scale + c), sh = ld_f32x8(shift + c), mu = ld_f32x8(mean + c);
+    float s1[8], s2[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s1[k] = s2[k] = 0.f;
+    for (long long q = static_cast<long long>(slice) * 32 + ty; q < nquads; q += static_cast<long long>(slices) * 32) {
+        const int w2 = static_cast<int>(q % W2);
+        long long r = q / W2;
+        const int h2 = static_cast<int>(r % H2);
+        const long long img = r / H2;
+        const long long p00 = (img * H + 2 * h2) * W + 2 * w2;
+        const long long pix[4] = {p00, p00 + 1, p00 + W, p00 + W + 1};
+        uint4 ua[4], ud[4], uz[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            ua[j] = ld_stream(act + pix[j] * act_stride + act_coff + c);
+            ud[j] = ld_stream(dskip + pix[j] * dskip_stride + dskip_coff + c);
+            uz[j] = ld_stream(z + pix[j] * C + c);
+        }
+        const F8 g = unpack8(ld_stream(dpool + ((img * H2 + h2) * W2 + w2) * C + c));
+        F8 a[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) a[j] = unpack8(ua[j]);
+        int arg[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            int best = 0;
+            float bv = a[0].v[k];
+#pragma unroll
+            for (int j = 1; j < 4; ++j)
+                if (a[j].v[k] > bv) {
+                    bv = a[j].v[k];
+                    best = j;
+                }
+            arg[k] = best;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            F8 o = unpack8(ud[j]);
+            const F8 zf = unpack8(uz[j]);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) o.v[k] += (arg[k] == j) ? g.v[k] : 0.f;
+            st_bf16x8(dy + pix[j] * C + c, o);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const float gv = bf16_round(o.v[k]);  // the reduction sees dY as stored
+                const float gm = fmaf(zf.v[k], sc.v[k], sh.v[k]) > 0.f ? gv : 0.f;
+                s1[k] += gm;
+                s2[k] = fmaf(gm, zf.v[k] - mu.v[k], s2[k]);
+            }
+        }
+    }
+    bn_red_block_finish(s1, s2, sums, ws, counters, invstd, C);
+}
 
 __global__ void __launch_bounds__(256, 3) bn_bwd_apply_fast_kernel(const __nv_bfloat16* __restrict__ dy, int dy_stride,
                                                                 int dy_coff, const __nv_bfloat16* __restrict__ z, int C,

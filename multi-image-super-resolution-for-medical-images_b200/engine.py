@@ -122,6 +122,7 @@ class UNetEngine:
         self.timing_skip_pack = os.environ.get("B200SR_TIMING_SKIP_PACK") is not None  # timing experiment only
         self.eval_graphs = os.environ.get("B200SR_NO_EVAL_GRAPH") is None
         self.fused_bn_finalize = os.environ.get("B200SR_NO_FUSED_BN") is None  # A/B switch: separate b200sr_bn_finalize launches
+        self.fused_pool_bnred = os.environ.get("B200SR_NO_FUSED_POOL_BNRED") is None  # A/B switch: separate reduction pass
         self._eval_graph_cache, self._eval_graph_calls = {}, {}
         self._hp = None
 
@@ -645,16 +646,18 @@ class UNetEngine:
     # ------------------------------------------------------------------------------------------------
     # backward
     # ------------------------------------------------------------------------------------------------
-    def _bn_bwd(self, plan, cs, dy, dy_stride, dy_off, h, w, dz):
-        """BatchNorm+ReLU backward of one layer: dy -> dz (dense), dgamma/dbeta into the flat gradient."""
+    def _bn_bwd(self, plan, cs, dy, dy_stride, dy_off, h, w, dz, sums_ready=False):
+        """BatchNorm+ReLU backward of one layer: dy -> dz (dense), dgamma/dbeta into the flat gradient. sums_ready: pass 1
+        (the reduction) was already done by the kernel that produced dy (fused max-pool backward)."""
         B = plan["B"]
         st = _lib.current_stream_ptr()
         z = plan["z:" + cs.name]
         sums = self.bn_sums.data_ptr() + 4 * self.bn_sum_off[cs.name]
         npix = B * h * w
         sc, sh, mu, iv = (self._bn(cs, k) for k in ("scale", "shift", "mean", "invstd"))
-        call("b200sr_bn_bwd_reduce_det", dy, dy_stride, dy_off, ptr(z), cs.cout, sc, sh, mu, iv, sums, ptr(self.red_ws),
-             self.red_ws.numel(), ptr(self.red_counters), None, npix, st)
+        if not sums_ready:
+            call("b200sr_bn_bwd_reduce_det", dy, dy_stride, dy_off, ptr(z), cs.cout, sc, sh, mu, iv, sums, ptr(self.red_ws),
+                 self.red_ws.numel(), ptr(self.red_counters), None, npix, st)
         g = self.flat_g.data_ptr()
         call("b200sr_bn_bwd_apply_fused", dy, dy_stride, dy_off, ptr(z), cs.cout, sc, sh, mu, iv, sums, 1,
              float(npix), g + 4 * self.off_of[id(cs.bn.weight)], g + 4 * self.off_of[id(cs.bn.bias)], dz, npix, st)
@@ -748,11 +751,14 @@ class UNetEngine:
              B * H * W, ptr(self.red_ws), self.red_ws.numel(), ptr(self.red_counters) + 4 * 63, st)
         dy = s0  # gradient w.r.t. the current block's output activation (dense)
 
-        def block_bwd(name, lvl, in_buf, in_stride, in_c, dx_dst, dx_stride, dx_stats, dy_ptr, x_input=None):
+        def block_bwd(name, lvl, in_buf, in_stride, in_c, dx_dst, dx_stride, dx_stats, dy_ptr, x_input=None,
+                      sums_ready=False):
             with _Nvtx("bwd/" + name):
-                return block_bwd_impl(name, lvl, in_buf, in_stride, in_c, dx_dst, dx_stride, dx_stats, dy_ptr, x_input)
+                return block_bwd_impl(name, lvl, in_buf, in_stride, in_c, dx_dst, dx_stride, dx_stats, dy_ptr, x_input,
+                                      sums_ready)
 
-        def block_bwd_impl(name, lvl, in_buf, in_stride, in_c, dx_dst, dx_stride, dx_stats, dy_ptr, x_input=None):
+        def block_bwd_impl(name, lvl, in_buf, in_stride, in_c, dx_dst, dx_stride, dx_stats, dy_ptr, x_input=None,
+                           sums_ready=False):
             """Backward through a UNetBlock: dy (dense, cout ch) -> dx into dx_dst (in_c channels)."""
             c1, c2 = self.blocks[name]
             h, w, c = H >> lvl, W >> lvl, c2.cout
@@ -762,7 +768,7 @@ class UNetEngine:
             # Stream choreography: the persistent dgrad and wgrad kernels each want every SM (one CTA per SM, > 200 KB of
             # shared memory); launched together they serialise. `late` (experiment, off) orders the wgrad behind the dgrad.
             late = self.wgrad_late
-            self._bn_bwd(plan, c2, dy_ptr, c, 0, h, w, dz2)
+            self._bn_bwd(plan, c2, dy_ptr, c, 0, h, w, dz2, sums_ready=sums_ready)
             if not late:
                 side_after_main()
                 wgrad3(ptr(a1), c, c, dz2, c, h, w, c2.conv.weight)
@@ -828,12 +834,22 @@ class UNetEngine:
             h, w, c = H >> lvl, W >> lvl, ch[lvl]
             cat, dcat = plan[f"cat{lvl}"], plan[f"dcat{lvl}"]
             dy = [p for p in (s0, s1, s2) if p != dpool][0]
-            call("b200sr_maxpool2x2_bwd", ptr(cat), 2 * c, c, dpool, ptr(dcat), 2 * c, c, c, dy, B, h, w, st)
+            fused = self.fused_pool_bnred
+            if fused:
+                # max-pool backward + skip add + pass 1 of the BatchNorm backward of this block's conv.3 in one launch
+                c2 = self.blocks[name][1]
+                call("b200sr_maxpool2x2_bwd_bnred", ptr(cat), 2 * c, c, dpool, ptr(dcat), 2 * c, c, c, dy,
+                     ptr(plan["z:" + c2.name]), self._bn(c2, "scale"), self._bn(c2, "shift"), self._bn(c2, "mean"),
+                     self._bn(c2, "invstd"), self.bn_sums.data_ptr() + 4 * self.bn_sum_off[c2.name], ptr(self.red_ws),
+                     self.red_ws.numel(), ptr(self.red_counters), B, h, w, st)
+            else:
+                call("b200sr_maxpool2x2_bwd", ptr(cat), 2 * c, c, dpool, ptr(dcat), 2 * c, c, c, dy, B, h, w, st)
             if lvl == 0:
-                block_bwd(name, lvl, None, 0, 2, None, 0, None, dy, x_input=x)
+                block_bwd(name, lvl, None, 0, 2, None, 0, None, dy, x_input=x, sums_ready=fused)
             else:
                 nxt = [p for p in (s0, s1, s2) if p != dy][0]
-                block_bwd(name, lvl, plan[f"pool{lvl - 1}"], ch[lvl - 1], ch[lvl - 1], nxt, ch[lvl - 1], None, dy)
+                block_bwd(name, lvl, plan[f"pool{lvl - 1}"], ch[lvl - 1], ch[lvl - 1], nxt, ch[lvl - 1], None, dy,
+                          sums_ready=fused)
                 dpool = nxt
             hi = report(self.blocks[name][0].conv.weight, hi)
         if overlap:

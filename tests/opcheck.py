@@ -661,6 +661,43 @@ def conv3x3_fwd_cta_pair(**kw):
     return res
 
 
+def maxpool_bwd_bnred(B=3, H=64, W=48, C=128, seed=93):
+    """fused max-pool backward + skip add + BatchNorm-backward reduction == the two separate kernels (dy bit for bit,
+    sums to fp32 round-off), and bit-reproducible."""
+    _setup()
+    z = bf(rnd(B, C, H, W, seed=seed) * 1.5 + 0.3)
+    gamma, beta = 1 + 0.1 * rnd(C, seed=seed + 1), 0.1 * rnd(C, seed=seed + 2)
+    mean = z.mean(dim=(0, 2, 3))
+    invstd = torch.rsqrt(z.var(dim=(0, 2, 3), unbiased=False) + 1e-5)
+    scale, shift = (gamma * invstd).contiguous(), (beta - mean * gamma * invstd).contiguous()
+    act = bf(torch.relu(z * scale[None, :, None, None] + shift[None, :, None, None]))
+    dpool = bf(rnd(B, C, H // 2, W // 2, seed=seed + 3))
+    dskip = bf(rnd(B, C, H, W, seed=seed + 4))
+    catb = slot_buffer(B, H, W, C, 2 * C, C, nhwc(act))
+    dcatb = slot_buffer(B, H, W, C, 2 * C, C, nhwc(dskip))
+    dpb, zb = nhwc(dpool), nhwc(z)
+    N = B * H * W
+    nws = int(call("b200sr_bn_bwd_ws_floats", C))
+    counters = torch.zeros(64, dtype=torch.int32, device=DEV)
+    # reference: the two separate kernels
+    dy_ref = torch.zeros(B, H, W, C, dtype=torch.bfloat16, device=DEV)
+    call("b200sr_maxpool2x2_bwd", ptr(catb), 2 * C, C, ptr(dpb), ptr(dcatb), 2 * C, C, C, ptr(dy_ref), B, H, W, st())
+    sums_ref, ws = _garbage(2, C), _garbage(nws)
+    call("b200sr_bn_bwd_reduce_det", ptr(dy_ref), C, 0, ptr(zb), C, ptr(scale), ptr(shift), ptr(mean), ptr(invstd),
+         ptr(sums_ref), ptr(ws), nws, ptr(counters), None, N, st())
+    runs = []
+    for _ in range(2):
+        dy = torch.zeros(B, H, W, C, dtype=torch.bfloat16, device=DEV)
+        sums, ws2 = _garbage(2, C), _garbage(nws)
+        call("b200sr_maxpool2x2_bwd_bnred", ptr(catb), 2 * C, C, ptr(dpb), ptr(dcatb), 2 * C, C, C, ptr(dy), ptr(zb),
+             ptr(scale), ptr(shift), ptr(mean), ptr(invstd), ptr(sums), ptr(ws2), nws, ptr(counters), B, H, W, st())
+        torch.cuda.synchronize()
+        runs.append((dy, sums))
+    return {"dy_exact": float((runs[0][0].float() - dy_ref.float()).abs().max()), "sums": rel(runs[0][1], sums_ref),
+            "counters_reset": float(counters.abs().max()),
+            "bitwise": float((runs[0][0].float() - runs[1][0].float()).abs().max() + (runs[0][1] - runs[1][1]).abs().max())}
+
+
 def conv3x3_wgrad_det(B=2, H=16, W=32, Cin=64, Cout=128, seed=3, cin_total=None, cin_off=0):
     _setup()
     x = bf(rnd(B, Cin, H, W, seed=seed))
@@ -1035,6 +1072,11 @@ CHECKS = {
                              {"out": BF16, "stats_sum": 1e-4, "stats_sq": 1e-4, "bitwise": 0.0, "same_as_single_cta": 0.0}),
     "cta_pair_conv3x3_n64_small": (conv3x3_fwd_cta_pair, dict(Cin=64, Cout=64, B=1, H=16, W=16),
                                    {"out": BF16, "stats_sum": 1e-4, "stats_sq": 1e-4, "bitwise": 0.0}),
+    "fused_maxpool_bwd_bnred": (maxpool_bwd_bnred, {}, {"dy_exact": 0.0, "sums": 1e-5, "counters_reset": 0.0, "bitwise": 0.0}),
+    "fused_maxpool_bwd_bnred_c64": (maxpool_bwd_bnred, dict(C=64, B=4, H=128, W=128),
+                                    {"dy_exact": 0.0, "sums": 1e-5, "counters_reset": 0.0, "bitwise": 0.0}),
+    "fused_maxpool_bwd_bnred_c512": (maxpool_bwd_bnred, dict(C=512, B=4, H=32, W=32),
+                                     {"dy_exact": 0.0, "sums": 1e-5, "counters_reset": 0.0, "bitwise": 0.0}),
     "det_conv3x3_wgrad_modeA": (conv3x3_wgrad_det, dict(Cin=256, Cout=256, B=3, H=16, W=32), {"dw": BF16, "bitwise": 0.0}),
     "det_conv3x3_wgrad_modeB": (conv3x3_wgrad_det, dict(Cin=64, Cout=64, B=4, H=64, W=64), {"dw": BF16, "bitwise": 0.0}),
     "det_conv3x3_wgrad_n64": (conv3x3_wgrad_det, dict(Cin=128, Cout=64, B=2, H=32, W=64), {"dw": BF16, "bitwise": 0.0}),
