@@ -53,6 +53,38 @@ def load_peaks():
             "source": "fallback (B200_PROFILING.md)"}
 
 
+def ncu_traffic_per_launch():
+    """Mean DRAM bytes (read + write) per tensor-core launch of one B=32 train step, parsed from the committed ncu
+    summary of the same launch population (tools/ncu_step.py under ncu --set full; tools/ncu_summary.py)."""
+    path = os.path.join(ROOT, "profiles", "r2_gemm_ncu_summary.txt")
+    if not os.path.exists(path):
+        return None, "profiles/r2_gemm_ncu_summary.txt missing"
+    tot, n = 0.0, 0
+    with open(path) as f:
+        for line in f:
+            if line.startswith("#") or "dram_rd_MB=" not in line:
+                continue
+            try:
+                rd = float(line.split("dram_rd_MB=")[1].split()[0])
+                wr = float(line.split("dram_wr_MB=")[1].split()[0])
+            except (IndexError, ValueError):
+                continue
+            tot += (rd + wr) * 1e6
+            n += 1
+    if n == 0:
+        return None, "no launches parsed from profiles/r2_gemm_ncu_summary.txt"
+    return tot / n, f"profiles/r2_gemm_ncu_summary.txt: {n} tensor-core launches of one train step (ncu --set full, cold cache)"
+
+
+def bench_config(world, B):
+    """The workload both arms are quoted on (the reference arm times a bounded sample of it, see cpu_baseline.sample)."""
+    return {"workload": "unet_train_combined_mse_ssim_b32_256x256 (BASELINE configs[2] hot path: UNet fwd+bwd, "
+                        "MSE+0.005*(1-SSIM), Adam; the same step with the VGG16 perceptual term is reported as "
+                        "'full_combined_loss', the other BASELINE configs under 'variants')",
+            "global_batch": world * B, "per_gpu_batch": B, "parallelism": f"dp{world}",
+            "l2": "per-step working set (activations + gradients, several GB) >> 126 MB L2; ring of 4 distinct input batches"}
+
+
 class ClockSampler:
     QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -119,7 +151,8 @@ def cpu_train_sample(batch, steps, warmup, threads=None):
             times.append(time.perf_counter() - t0)
     total = sum(times)
     return {"value": batch * steps / total, "ms_per_step": 1e3 * total / steps, "cores": threads,
-            "sample": f"{steps} train steps (MSE+0.005*(1-SSIM), Adam) at batch {batch}, 256x256 fp32, "
+            "sample": f"bounded sample of the workload: {steps} train steps (UNet fwd+bwd, MSE+0.005*(1-SSIM), Adam) at "
+                      f"batch {batch} instead of 32 (throughput in triplets/s is batch-size normalised), 256x256 fp32, "
                       f"torch {torch.__version__} CPU, {warmup} warm-up"}
 
 
@@ -235,8 +268,7 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "unet_train_combined_mse_ssim_b32_256x256 (configs[2] hot path; CPU sample at "
-                                   f"batch {batch} per step)", "global_batch": batch},
+            "config": bench_config(max(int(os.environ.get("WORLD_SIZE", "1")), 1), args.batch),
             "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
                              "sample": r["sample"]},
             "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -360,6 +392,30 @@ def run_b200sr(args):
         inf32_big_value = world * B * 10 / (inf32_big_ms / 1e3)
         model.set_eval_precision("bf16")
 
+    # ---- fused MSE+SSIM loss kernel at a batch large enough to leave the launch-latency regime (SURVEY hard-part 7) ---
+    ssim_big = None
+    if rank == 0:
+        try:
+            pb, tb = torch.randn(512, 1, H, W, device=dev), torch.randn(512, 1, H, W, device=dev)
+            crit = trainer.criterion
+            for _ in range(3):
+                crit.value_and_grad(pb, tb)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(10):
+                crit.value_and_grad(pb, tb)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / 10
+            gbs = 512 * 786432 / (ms / 1e3) / 1e9
+            ssim_big = {"batch": 512, "ms": ms, "gbs_algorithmic": gbs, "frac_of_hbm": gbs / peaks["hbm_gbs"],
+                        "note": "786,432 B/triplet (pred + target read, gradient written); instruction-issue bound: >= 220 "
+                                "FMA/pixel for 12 B/pixel caps an fp32 CUDA-core implementation at 0.30 of HBM (DESIGN.md §3)"}
+            del pb, tb
+        except Exception as exc:
+            ssim_big = {"error": f"{type(exc).__name__}: {exc}"[:200]}
+
     # ---- the same step with the full BASELINE configs[2] loss (MSE + 0.01*VGG16 perceptual + 0.005*(1-SSIM)) -------------
     full_loss = None
     try:
@@ -404,13 +460,13 @@ def run_b200sr(args):
         all_ms = sum(v["ms"] for v in agg.values())
         achieved = g_flop / (g_ms / 1e3) / 1e12
         peak = peaks["bf16_tflops_sustained"] or peaks["bf16_tflops"]
-        roofline = {"bound": "tensor", "kernel": "igemm_kernel + wgrad_kernel (tcgen05 implicit GEMM: conv3x3 "
+        traffic, traffic_src = ncu_traffic_per_launch()
+        roofline = {"bound": "tensor", "kernel": "conv3x3_kernel + wgrad3x3_kernel + wgrad_kernel (tcgen05 implicit GEMM: conv3x3 "
                     "fwd/dgrad/wgrad, ConvT fwd/dgrad/wgrad)", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                     "frac": achieved / peak,
-                    # DRAM bytes per tensor-core launch (dram__bytes_read+write, ncu --set full): mean over the 48
-                    # conv3x3/wgrad3x3 launches of profiles/r1_final_gemm_ncu_summary.txt (mid-network layers, 101.8 MB)
-                    # and profiles/r1c_gemm_ncu_summary.txt (256^2/128^2 layers of the backward pass, 330.7 MB)
-                    "traffic": 216.3e6,
+                    # DRAM bytes per tensor-core launch: dram__bytes_read.sum + dram__bytes_write.sum of every tensor-core
+                    # launch of ONE train step of this very workload (ncu --set full, committed summary), mean per launch
+                    "traffic": traffic, "traffic_source": traffic_src,
                     "peak_source": peaks["source"] + " sustained bf16 (kernels timed inside a long step); burst "
                                    f"{peaks['bf16_tflops']}",
                     "note": "per-kernel times from 3 instrumented eager steps (CUDA graph and wgrad side stream off)",
@@ -491,16 +547,12 @@ def run_b200sr(args):
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-                "config": {"workload": "unet_train_combined_mse_ssim_b32_256x256 (BASELINE configs[2] hot path: "
-                                       "UNet fwd+bwd, MSE+0.005*(1-SSIM), Adam; the same step with the VGG16 perceptual term and the "
-                                       "other BASELINE configs are timed under 'variants')",
-                           "global_batch": world * B, "per_gpu_batch": B, "parallelism": f"dp{world}",
-                           "l2": "per-step working set (activations + gradients, several GB) >> 126 MB L2; ring of 4 "
-                                 "distinct input batches"},
+                "config": bench_config(world, B),
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                         "ms_per_step": e2e_ms / args.steps},
                 "gpu_launches": launches_timed, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
-                "full_combined_loss": full_loss, "gpu_library_baseline": gpu_lib, "variants": variants,
+                "full_combined_loss": full_loss, "gpu_library_baseline": gpu_lib, "ssim_kernel_b512": ssim_big,
+                "variants": variants,
                 "inference": {"value": inf_value, "unit": UNIT, "batch_per_gpu": 8, "ms_per_batch": inf_ms / 20,
                               "workload": "BASELINE configs[0]: UNet eval forward (B=8,2,256,256)->(B,1,256,256), "
                                           "fp32 in/out, bf16 tensor-core compute",

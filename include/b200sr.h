@@ -89,6 +89,14 @@ int b200sr_conv3x3_dgrad(const void* dy, int dy_pix_stride, int dy_c_off, int Co
                          int Cin, int B, int H, int W, void* dx, int dx_pix_stride, int dx_c_off, float* stats,
                          int stats_replicas, void* stream);
 
+/* Data gradient that also leaves the per-channel SUMS of its first `ncols` output channels in deterministic per-CTA slots
+ * colsum_slots[slots][2][Cin] (row 0; finish with b200sr_sum_slots): the ConvTranspose2d bias gradient is the column sum
+ * of the upsampled half of the decoder concat gradient (unet_model.py:101-113 backward). Cheaper than the full statistics
+ * of b200sr_conv3x3_dgrad (no squares, no work for the skip half). slots >= number of SMs; ncols % 32 == 0. */
+int b200sr_conv3x3_dgrad_colsum(const void* dy, int dy_pix_stride, int dy_c_off, int Cout, const void* w_packed, int Cin,
+                                int B, int H, int W, void* dx, int dx_pix_stride, int dx_c_off, float* colsum_slots,
+                                int slots, int ncols, void* stream);
+
 /* Data gradient fused with the ReLU backward of the layer it flows into (Conv+ReLU stacks without BatchNorm: the
  * DoubleConv of ModelLoader.py:521-533, the VGG features of the perceptual loss): dx = dgrad(dy) * [act > 0], act the
  * (B,H,W,Cin) activation slot of that layer. stats (optional) receives the per-channel sums of the stored dx, i.e. that

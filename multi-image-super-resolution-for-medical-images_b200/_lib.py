@@ -27,6 +27,8 @@ _SIGNATURES = {
     "b200sr_conv3x3_fwd_bn": [_P, c_int, c_int, c_int, _P, c_int, c_int, c_int, c_int, _P, c_int, c_int, _P, c_int, _P, _P],
     "b200sr_conv3x3_dgrad": [_P, c_int, c_int, c_int, _P, c_int, c_int, c_int, c_int, _P, c_int, c_int, _P, c_int,
                              _P],
+    "b200sr_conv3x3_dgrad_colsum": [_P, c_int, c_int, c_int, _P, c_int, c_int, c_int, c_int, _P, c_int, c_int, _P, c_int,
+                                    c_int, _P],
     "b200sr_conv3x3_dgrad_relu": [_P, c_int, c_int, c_int, _P, c_int, c_int, c_int, c_int, _P, c_int, c_int, _P, c_int,
                                   c_int, _P, c_int, _P],
     "b200sr_convT2x2_fwd": [_P, c_int, c_int, c_int, _P, c_int, _P, c_int, c_int, c_int, _P, c_int, c_int, _P],
@@ -160,14 +162,14 @@ _KERNELS_PER_CALL = {"b200sr_conv3x3_wgrad_det": 3, "b200sr_convT2x2_wgrad_det":
                      "b200sr_bn_bwd_ws_floats": 0, "b200sr_version": 0, "b200sr_device_ok": 0}
 GEMM_OPS = ("b200sr_conv3x3_fwd", "b200sr_conv3x3_dgrad", "b200sr_conv3x3_dgrad_relu", "b200sr_conv3x3_wgrad", "b200sr_convT2x2_fwd",
             "b200sr_convT2x2_dgrad", "b200sr_convT2x2_wgrad", "b200sr_conv1x1", "b200sr_conv1x1_wgrad",
-            "b200sr_conv3x3_wgrad_det", "b200sr_convT2x2_wgrad_det", "b200sr_conv1x1_wgrad_det", "b200sr_conv3x3_fwd_bn", "b200sr_conv3x3_fwd_split", "b200sr_convT2x2_fwd_split")
+            "b200sr_conv3x3_wgrad_det", "b200sr_convT2x2_wgrad_det", "b200sr_conv1x1_wgrad_det", "b200sr_conv3x3_fwd_bn", "b200sr_conv3x3_dgrad_colsum", "b200sr_conv3x3_fwd_split", "b200sr_convT2x2_fwd_split")
 _profile = None  # list of (name, start_event, end_event, flop, bytes) while profiling is enabled
 
 
 def _cost(name, a):
     """Algorithmic (flop, bytes) of one call, from its argument list (see include/b200sr.h for the order)."""
     if name in ("b200sr_conv3x3_fwd", "b200sr_conv3x3_dgrad", "b200sr_conv3x3_dgrad_relu", "b200sr_conv3x3_fwd_split",
-                "b200sr_conv3x3_fwd_bn"):
+                "b200sr_conv3x3_fwd_bn", "b200sr_conv3x3_dgrad_colsum"):
         return 2.0 * a[6] * a[7] * a[8] * a[3] * a[5] * 9, 0.0   # (split: issued flops, 3x the algorithmic ones)
     if name in ("b200sr_convT2x2_dgrad",):
         return 2.0 * a[6] * a[7] * a[8] * a[3] * a[5] * 4, 0.0

@@ -339,7 +339,8 @@ int dispatch_conv3(int block_n, const CUtensorMap& ma, const CUtensorMap& mb, co
 int run_conv3(int mode, const void* a, int a_stride, int a_coff, int Ca, const void* w_packed, int n_total, int B, int H, int W,
               void* out, int out_stride, int out_coff, const float* col_scale, const float* col_shift, int relu,
               float* stats, int stats_replicas, int cout_t, cudaStream_t st, const void* mask = nullptr,
-              int mask_stride = 0, int mask_coff = 0, int split_stride = 0, const b200sr_bn_train* bn = nullptr) {
+              int mask_stride = 0, int mask_coff = 0, int split_stride = 0, const b200sr_bn_train* bn = nullptr,
+              int stats_sum_cols = 0) {
     B2_CHECK_ARG(a != nullptr && w_packed != nullptr && out != nullptr);
     // split_stride > 0: fp32-accuracy eval epilogue ([hi | lo | hi] output parts, conv3x3.cuh), modes 0 and 1 only
     B2_CHECK_ARG(split_stride == 0 || ((mode == 0 || mode == 1) && mask == nullptr && stats == nullptr &&
@@ -419,6 +420,7 @@ int run_conv3(int mode, const void* a, int a_stride, int a_coff, int Ca, const v
     args.mask_pix_stride = mask_stride;
     args.mask_c_off = mask_coff;
     args.split_stride = split_stride;
+    args.stats_sum_cols = stats_sum_cols;
     args.bn_scale = nullptr;
     {
         const int nh = block_n / (block_n < 128 ? block_n : 128);
@@ -570,8 +572,9 @@ int launch_wgrad3_t(const CUtensorMap& mx, const CUtensorMap& mz, WG3Args& args,
     int best = 1;
     double best_score = -1.0;
     // up to two waves' worth of splits: a single-job layer (Cin = Cout = 64) must still be able to fill every SM
-    static const int cap_env = getenv("B200SR_WGRAD_SPLIT_CAP") ? atoi(getenv("B200SR_WGRAD_SPLIT_CAP")) : 0;
-    const int split_cap = cap_env > 0 ? cap_env : (2 * sms > 64 ? 2 * sms : 64);
+    // (capping the splits at one wave of CTAs — half the partial traffic of the second stage — was measured: no effect on
+    // the step within +-0.05 ms, profiles/r2_ab_stage2.txt)
+    const int split_cap = 2 * sms > 64 ? 2 * sms : 64;
     int max_splits = args.total_chunks < split_cap ? args.total_chunks : split_cap;
     if (ws_max_splits > 0 && max_splits > ws_max_splits) max_splits = ws_max_splits;  // partial workspace capacity
     for (int s = 1; s <= max_splits; ++s) {
@@ -691,6 +694,15 @@ int b200sr_conv3x3_dgrad(const void* dy, int dy_pix_stride, int dy_c_off, int Co
                          nullptr, nullptr, 0, stats, stats_replicas, Cin, static_cast<cudaStream_t>(stream));
     return run_igemm(0, dy, dy_pix_stride, dy_c_off, Cout, 9, w_packed, Cin, B, H, W, 0, Cin, dx, dx_pix_stride,
                      dx_c_off, nullptr, nullptr, 0, stats, stats_replicas, static_cast<cudaStream_t>(stream));
+}
+
+int b200sr_conv3x3_dgrad_colsum(const void* dy, int dy_pix_stride, int dy_c_off, int Cout, const void* w_packed, int Cin,
+                                int B, int H, int W, void* dx, int dx_pix_stride, int dx_c_off, float* colsum_slots,
+                                int slots, int ncols, void* stream) {
+    B2_CHECK_ARG(colsum_slots != nullptr && slots > 0 && ncols > 0 && ncols <= Cin && ncols % 32 == 0);
+    B2_CHECK_ARG(H % C3_TILE_H == 0 && W % C3_TILE_W == 0);
+    return run_conv3(0, dy, dy_pix_stride, dy_c_off, Cout, w_packed, Cin, B, H, W, dx, dx_pix_stride, dx_c_off, nullptr,
+                     nullptr, 0, colsum_slots, slots, Cin, static_cast<cudaStream_t>(stream), nullptr, 0, 0, 0, nullptr, ncols);
 }
 
 int b200sr_conv3x3_dgrad_relu(const void* dy, int dy_pix_stride, int dy_c_off, int Cout, const void* w_packed, int Cin,

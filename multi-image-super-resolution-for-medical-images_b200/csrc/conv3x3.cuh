@@ -33,6 +33,8 @@ struct Conv3Args {
     int out_c_off;
     int stats_replicas;
     int cout_t;        // MODE 1: channels per (i,j) sub-pixel (n_total = 4 * cout_t); modulus of the affine vectors
+    int stats_sum_cols;  // > 0: only the column SUMS of the first stats_sum_cols output columns are needed (ConvTranspose2d
+                         // bias gradient from a dgrad): no squares, no work for the other columns
     int stats_slots;   // > 0: deterministic statistics — CTA (blockIdx.x / n_tiles) STORES its partial sums into its own
                        // slot of stats[stats_replicas][2][n_total] (no atomics, no pre-zeroing; unused slots are zeroed
                        // here); 0: legacy mode, partial sums are atomically ADDED into slot blockIdx.x % stats_replicas
@@ -75,21 +77,23 @@ __device__ __forceinline__ void c3_bn_finalize(const Conv3Args& args, int n0, in
     constexpr int TASKS = BLOCK_N / 2;     // float4 columns: [0, BLOCK_N/4) = sums, [BLOCK_N/4, BLOCK_N/2) = squares
     constexpr int LANES = 256 / TASKS;     // 8 / 4 / 2
     const int tid = threadIdx.x;
-    const int task = tid % TASKS, lane = tid / TASKS;
-    const int which = task / (BLOCK_N / 4), c4 = task % (BLOCK_N / 4);
-    double acc[4] = {0.0, 0.0, 0.0, 0.0};
-    const float* base = args.stats + static_cast<size_t>(which) * args.n_total + n0 + 4 * c4;
-#pragma unroll 4
-    for (int sl = lane; sl < used; sl += LANES) {
-        const float4 v = __ldcg(reinterpret_cast<const float4*>(base + static_cast<size_t>(sl) * 2 * args.n_total));
-        acc[0] += v.x;
-        acc[1] += v.y;
-        acc[2] += v.z;
-        acc[3] += v.w;
-    }
     double* s_acc = reinterpret_cast<double*>(scratch);  // [LANES][2][BLOCK_N]
+    if (tid < 256) {  // (the CTA may have 384 threads: two epilogue teams)
+        const int task = tid % TASKS, lane = tid / TASKS;
+        const int which = task / (BLOCK_N / 4), c4 = task % (BLOCK_N / 4);
+        double acc[4] = {0.0, 0.0, 0.0, 0.0};
+        const float* base = args.stats + static_cast<size_t>(which) * args.n_total + n0 + 4 * c4;
+#pragma unroll 4
+        for (int sl = lane; sl < used; sl += LANES) {
+            const float4 v = __ldcg(reinterpret_cast<const float4*>(base + static_cast<size_t>(sl) * 2 * args.n_total));
+            acc[0] += v.x;
+            acc[1] += v.y;
+            acc[2] += v.z;
+            acc[3] += v.w;
+        }
 #pragma unroll
-    for (int k = 0; k < 4; ++k) s_acc[(lane * 2 + which) * BLOCK_N + 4 * c4 + k] = acc[k];
+        for (int k = 0; k < 4; ++k) s_acc[(lane * 2 + which) * BLOCK_N + 4 * c4 + k] = acc[k];
+    }
     __syncthreads();
     if (tid < BLOCK_N) {
         double s = 0.0, q = 0.0;
@@ -160,9 +164,12 @@ struct C3Cfg {
 // of bf16 output per 128 x 256 tile — is the critical path. They run TWO epilogue teams of four warps (warps 4-7 and
 // 8-11, each covering the 128 TMEM lanes): team t converts and stores the 64-column groups g with g % 2 == t through its
 // own staging buffer and its own TMA-store issuer thread, so two groups are in flight per CTA.
+// The conv3x3 forward / dgrad (MODE 0) with BLOCK_N >= 128 runs two teams as well: with the BatchNorm statistics (a
+// 32 x 32 transposing shuffle reduction per 32 columns and statistic) the epilogue of one warp per scheduler is longer than
+// the main loop of the small-K layers (K = 576: 36 MMAs per tile).
 template <int BLOCK_N, int MODE_T, bool SPLIT>
 __host__ __device__ constexpr int c3_teams() {
-    return ((MODE_T == 1 || MODE_T == 2) && BLOCK_N >= 128 && !SPLIT) ? 2 : 1;
+    return ((MODE_T == 0 || MODE_T == 1 || MODE_T == 2) && BLOCK_N >= 128 && !SPLIT) ? 2 : 1;
 }
 template <int BLOCK_N, int MODE_T, bool SPLIT>
 __host__ __device__ constexpr int c3_threads() {
@@ -556,7 +563,7 @@ __global__ void __launch_bounds__((c3_threads<BLOCK_N, MODE_T, SPLIT>()), 1) con
                         *reinterpret_cast<uint4*>(stage + row_off + ((j ^ row_xor) << 4)) =
                             make_uint4(packed[4 * i], packed[4 * i + 1], packed[4 * i + 2], packed[4 * i + 3]);
                     }
-                    if (do_stats) {
+                    if (do_stats && (args.stats_sum_cols == 0 || n0 + chunk * 32 < args.stats_sum_cols)) {
                         // statistics of the tensor as stored (bf16-rounded), like BatchNorm reading the conv output
                         float s1[32], s2[32];
 #pragma unroll
@@ -569,7 +576,7 @@ __global__ void __launch_bounds__((c3_threads<BLOCK_N, MODE_T, SPLIT>()), 1) con
                             s2[2 * i + 1] = b * b;
                         }
                         st_sum[chunk] += warp_transpose_reduce32(s1, lane);
-                        st_sq[chunk] += warp_transpose_reduce32(s2, lane);
+                        if (args.stats_sum_cols == 0) st_sq[chunk] += warp_transpose_reduce32(s2, lane);
                     }
                 }
                 // make the generic-proxy writes visible to the TMA engine, make sure the OTHER buffer's previous
@@ -609,19 +616,21 @@ __global__ void __launch_bounds__((c3_threads<BLOCK_N, MODE_T, SPLIT>()), 1) con
                 // CTA owns are zeroed by the CTA that owns slot (s mod used), so bn_finalize can sum all of them in order
                 const int used = static_cast<int>(gridDim.x) / args.n_tiles;
                 const int mine = static_cast<int>(blockIdx.x) / args.n_tiles;
-                float* s_red = reinterpret_cast<float*>(out_stage);  // staging tile is dead (stores drained above)
-                named_bar_sync(1, 128);
+                float* s_red = reinterpret_cast<float*>(out_stage);  // staging tiles are dead (stores drained above)
+                constexpr int EW = 4 * TEAMS;  // epilogue warps; each holds the sums of ITS pixel rows x ITS column groups
+                const int ew = warp - 4;
+                named_bar_sync(5, 128 * TEAMS);
 #pragma unroll
                 for (int chunk = 0; chunk < BLOCK_N / 32; ++chunk) {
-                    s_red[(q * 2 + 0) * BLOCK_N + chunk * 32 + lane] = st_sum[chunk];
-                    s_red[(q * 2 + 1) * BLOCK_N + chunk * 32 + lane] = st_sq[chunk];
+                    s_red[(ew * 2 + 0) * BLOCK_N + chunk * 32 + lane] = st_sum[chunk];
+                    s_red[(ew * 2 + 1) * BLOCK_N + chunk * 32 + lane] = st_sq[chunk];
                 }
-                named_bar_sync(1, 128);
-                for (int i = threadIdx.x - 128; i < 2 * BLOCK_N; i += 128) {
+                named_bar_sync(5, 128 * TEAMS);
+                for (int i = threadIdx.x - 128; i < 2 * BLOCK_N; i += 128 * TEAMS) {
                     const int which = i / BLOCK_N, col = i - which * BLOCK_N;
                     float acc = 0.f;
 #pragma unroll
-                    for (int w4 = 0; w4 < 4; ++w4) acc += s_red[(w4 * 2 + which) * BLOCK_N + col];
+                    for (int w8 = 0; w8 < EW; ++w8) acc += s_red[(w8 * 2 + which) * BLOCK_N + col];
                     args.stats[(static_cast<size_t>(mine) * 2 + which) * args.n_total + n0_last + col] = acc;
                     for (int s2 = mine + used; s2 < args.stats_replicas; s2 += used)
                         args.stats[(static_cast<size_t>(s2) * 2 + which) * args.n_total + n0_last + col] = 0.f;

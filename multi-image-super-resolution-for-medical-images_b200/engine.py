@@ -123,6 +123,7 @@ class UNetEngine:
         self.eval_graphs = os.environ.get("B200SR_NO_EVAL_GRAPH") is None
         self.fused_bn_finalize = os.environ.get("B200SR_NO_FUSED_BN") is None  # A/B switch: separate b200sr_bn_finalize launches
         self.fused_pool_bnred = os.environ.get("B200SR_NO_FUSED_POOL_BNRED") is None  # A/B switch: separate reduction pass
+        self._ab_full_stats = os.environ.get("B200SR_DGRAD_FULL_STATS") is not None  # A/B switch: sums + squares of all columns
         self._eval_graph_cache, self._eval_graph_calls = {}, {}
         self._hp = None
 
@@ -788,8 +789,14 @@ class UNetEngine:
             if not late:
                 side_after_main()
                 wgrad3(ptr(in_buf), in_stride, in_c, dz1, c, h, w, c1.conv.weight)
-            call("b200sr_conv3x3_dgrad", dz1, c, 0, c, self._wp(self.wp_dgrad, c1.name), in_c, B, h, w, dx_dst,
-                 dx_stride, 0, dx_stats, n_slots if dx_stats else 0, st)
+            if dx_stats and not self._ab_full_stats:
+                # decoder conv.0: the gradient of the concat buffer; the column sums of its upsampled half (first in_c/2
+                # channels) are the ConvTranspose2d bias gradient
+                call("b200sr_conv3x3_dgrad_colsum", dz1, c, 0, c, self._wp(self.wp_dgrad, c1.name), in_c, B, h, w, dx_dst,
+                     dx_stride, 0, dx_stats, n_slots, in_c // 2, st)
+            else:
+                call("b200sr_conv3x3_dgrad", dz1, c, 0, c, self._wp(self.wp_dgrad, c1.name), in_c, B, h, w, dx_dst,
+                     dx_stride, 0, dx_stats, n_slots if dx_stats else 0, st)
             if late:
                 side_after_main()
                 wgrad3(ptr(in_buf), in_stride, in_c, dz1, c, h, w, c1.conv.weight)
