@@ -341,6 +341,7 @@ def run_b200sr(args):
     clocks = sampler.stop() if rank == 0 else None
     ms_per_step = total_ms / args.steps
     value = world * B * args.steps / (total_ms / 1e3)
+    grad_buffer_registered = bool(getattr(model._get_engine(), "flat_g_registered", False))
     launches_timed = launches_total * args.steps // (args.steps + args.warmup)
 
     # ---- e2e: the public API from pinned HOST buffers: DevicePrefetcher (H2D of batch i+1 overlaps step i) feeding
@@ -551,6 +552,9 @@ def run_b200sr(args):
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                         "ms_per_step": e2e_ms / args.steps},
                 "gpu_launches": launches_timed, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+                "ddp": {"world": world, "collective": "NCCL all-reduce(sum) of the flat fp32 gradient buffer, one range per "
+                        "UNet block, overlapped with backward" if world > 1 else None,
+                        "nccl_user_buffer_registration": grad_buffer_registered},
                 "full_combined_loss": full_loss, "gpu_library_baseline": gpu_lib, "ssim_kernel_b512": ssim_big,
                 "variants": variants,
                 "inference": {"value": inf_value, "unit": UNIT, "batch_per_gpu": 8, "ms_per_batch": inf_ms / 20,

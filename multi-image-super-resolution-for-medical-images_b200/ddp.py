@@ -28,6 +28,29 @@ def broadcast_module_state(module, src: int = 0) -> None:
             dist.broadcast(t.data, src=src)
 
 
+def alloc_comm_buffer(numel: int, device):
+    """A zeroed flat fp32 buffer allocated by NCCL's own allocator (ncclMemAlloc) and registered with the communicator
+    (user-buffer registration): all-reduces on (ranges of) it can then run zero-copy, with in-switch reduction (NVLS) on
+    NVSwitch systems, instead of staging through NCCL's internal buffers — fewer SMs and less HBM traffic taken from the
+    backward pass they overlap. Returns None when not distributed / not NCCL / not supported by this torch build
+    (B200SR_NO_NCCL_REG=1 switches it off); the caller then falls back to an ordinary allocation."""
+    import os
+    if not is_distributed() or os.environ.get("B200SR_NO_NCCL_REG") is not None:
+        return None
+    try:
+        if dist.get_backend() != "nccl":
+            return None
+        backend = dist.group.WORLD._get_backend(torch.device(device))
+        pool = torch.cuda.MemPool(backend.mem_allocator)
+        with torch.cuda.use_mem_pool(pool):
+            buf = torch.zeros(numel, dtype=torch.float32, device=device)
+        backend.register_mem_pool(pool)
+        buf._b200sr_pool = pool  # keep the pool (and its registration) alive as long as the buffer
+        return buf
+    except Exception:  # older torch / NCCL, or a backend without a memory allocator
+        return None
+
+
 def shard_batch(n_total: int, rank: int, world_size: int):
     """Contiguous [lo, hi) slice of a global batch owned by `rank` (inference shards with no collective)."""
     per = (n_total + world_size - 1) // world_size

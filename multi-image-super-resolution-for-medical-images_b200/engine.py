@@ -169,7 +169,11 @@ class UNetEngine:
             total += _align(p.numel())
         self.p_off, self.p_total = offs, total
         self.flat_p = torch.zeros(total, dtype=torch.float32, device=device)
-        self.flat_g = torch.zeros(total, dtype=torch.float32, device=device)
+        from .ddp import alloc_comm_buffer
+        self.flat_g = alloc_comm_buffer(total, device)  # NCCL-registered when data-parallel (zero-copy / NVLS all-reduce)
+        self.flat_g_registered = self.flat_g is not None
+        if self.flat_g is None:
+            self.flat_g = torch.zeros(total, dtype=torch.float32, device=device)
         # (flat_g is zeroed ONCE: every real gradient is WRITTEN by a deterministic kernel each step; the conv biases in front
         # of a BatchNorm have an exactly-zero gradient and are never touched)
         self.grad_views = []
