@@ -72,6 +72,7 @@ EncodeTiledFn get_encode_fn() {
 struct MapKey {
     const void* ptr;
     uint32_t rank;
+    uint32_t promo;
     uint64_t dims[5];
     uint64_t strides[4];
     uint32_t box[5];
@@ -93,12 +94,18 @@ std::mutex g_map_mutex;
 std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_map_cache;
 
 // bf16 tiled map with the 128-byte swizzle; out-of-bounds elements read as zero.
+// narrow: the box covers only part of each pixel's bytes (a channel slot of a wider buffer): promote L2 requests to 128 B
+// instead of 256 B — with 256 B every read of the upsampled HALF of a decoder concat gradient (256 B per pixel at level 0)
+// dragged the skip half through DRAM as well (ncu: ConvT dgrad / wgrad at level 0 read 2x their algorithmic bytes)
 int make_map(CUtensorMap* out, const void* ptr, uint32_t rank, const uint64_t* dims, const uint64_t* strides_bytes,
-             const uint32_t* box) {
+             const uint32_t* box, bool narrow = false) {
     MapKey key;
     std::memset(&key, 0, sizeof(key));
     key.ptr = ptr;
     key.rank = rank;
+    static const bool force_256 = std::getenv("B200SR_L2_PROMO_256") != nullptr;  // A/B switch
+    if (force_256) narrow = false;
+    key.promo = narrow ? 1u : 0u;
     for (uint32_t i = 0; i < rank; ++i) {
         key.dims[i] = dims[i];
         key.box[i] = box[i];
@@ -126,7 +133,8 @@ int make_map(CUtensorMap* out, const void* ptr, uint32_t rank, const uint64_t* d
     }
     CUtensorMap m;
     CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(ptr), gdims, gstrides, gbox, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                     narrow ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(B200SR_ECUDA, "cuTensorMapEncodeTiled failed, CUresult=" + std::to_string(r));
     {
@@ -147,7 +155,7 @@ int make_act_map(CUtensorMap* out, const void* base, int pix_stride, int c_off, 
     const uint64_t s = static_cast<uint64_t>(pix_stride) * 2;
     const uint64_t strides[3] = {s, s * W, s * W * H};
     const uint32_t box[4] = {64, static_cast<uint32_t>(box_w), static_cast<uint32_t>(box_h), 1};
-    return make_map(out, p, 4, dims, strides, box);
+    return make_map(out, p, 4, dims, strides, box, C < pix_stride);
 }
 
 // (B,2H,2W,C) channel slot viewed as the 5-D tensor (c, j, w, i, b*H + h): sub-pixel (i,j) gather
@@ -159,7 +167,7 @@ int make_gather_map(CUtensorMap* out, const void* base, int pix_stride, int c_of
     const uint64_t s = static_cast<uint64_t>(pix_stride) * 2;
     const uint64_t strides[4] = {s, 2 * s, 2 * static_cast<uint64_t>(W) * s, 4 * static_cast<uint64_t>(W) * s};
     const uint32_t box[5] = {64, 1, static_cast<uint32_t>(box_w), 1, static_cast<uint32_t>(box_h)};
-    return make_map(out, p, 5, dims, strides, box);
+    return make_map(out, p, 5, dims, strides, box, true);  // every other pixel, and possibly half of its channels
 }
 
 // (B,H,W,C) channel slot viewed as the 5-D tensor (c within a 64-channel chunk, w, h, chunk, b): one box can
@@ -173,7 +181,7 @@ int make_chunk_map(CUtensorMap* out, const void* base, int pix_stride, int c_off
     const uint64_t strides[4] = {s, s * W, 128, s * W * H};
     const uint32_t box[5] = {64, static_cast<uint32_t>(box_w), static_cast<uint32_t>(box_h),
                              static_cast<uint32_t>(box_chunks), 1};
-    return make_map(out, p, 5, dims, strides, box);
+    return make_map(out, p, 5, dims, strides, box, C < pix_stride);
 }
 
 int make_weight_map(CUtensorMap* out, const void* w, int K_total, int N_total, int block_n) {
