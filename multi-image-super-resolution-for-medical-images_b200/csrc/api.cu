@@ -904,8 +904,15 @@ int launch_reduce_unpack(float* ws, int splits, long long split_stride, int T, i
     // stage 2b: kernel layout [t][inner][outer] -> PyTorch parameter layout
     int tiles = (outer_total / PK_TILE) * (inner_total / PK_TILE);
     if (tiles > num_sms() * 8) tiles = num_sms() * 8;
-    wgrad_reduce_unpack_kernel<<<tiles, 256, 0, st>>>(ws, 1, split_stride, T, outer_total, inner_total, inner_dst,
-                                                      inner_off, dst);
+    if (T == 9)
+        wgrad_reduce_unpack_kernel<9><<<tiles, 256, 0, st>>>(ws, 1, split_stride, outer_total, inner_total, inner_dst,
+                                                             inner_off, dst);
+    else if (T == 4)
+        wgrad_reduce_unpack_kernel<4><<<tiles, 256, 0, st>>>(ws, 1, split_stride, outer_total, inner_total, inner_dst,
+                                                             inner_off, dst);
+    else
+        wgrad_reduce_unpack_kernel<1><<<tiles, 256, 0, st>>>(ws, 1, split_stride, outer_total, inner_total, inner_dst,
+                                                             inner_off, dst);
     return check_launch("wgrad_reduce_unpack_kernel");
 }
 }  // namespace

@@ -331,44 +331,48 @@ __global__ void __launch_bounds__(256) reduce_splits_inplace_kernel(float4* __re
 // the PyTorch parameter layout dst[outer][inner_off + inner][t] (row length inner_dst) — the fixed-order replacement of
 // red.global.add + unpack. T = 9 (Conv2d 3x3: outer = Cout, inner = Cin), 4 (ConvTranspose2d: outer = Cin, inner = Cout)
 // or 1 (Conv2d 1x1). One 32 x 32 x T tile per block iteration; reads and writes are coalesced runs.
+template <int T>
 __global__ void __launch_bounds__(256) wgrad_reduce_unpack_kernel(const float* __restrict__ parts, int nsplits,
-                                                                  long long split_stride, int T, int outer_total,
+                                                                  long long split_stride, int outer_total,
                                                                   int inner_total, int inner_dst, int inner_off,
                                                                   float* __restrict__ dst) {
-    __shared__ float tile[PK_TILE][PK_TILE * 9 + 1];
+    // T is a template parameter so that the 4 * T loads of a thread are issued back to back: with a run-time T the
+    // per-element predicate kept every load behind the add of the previous one (one DRAM round trip each, 20 us per launch)
+    __shared__ float tile[PK_TILE][PK_TILE * T + 1];
+    constexpr int ROW = PK_TILE * T;
+    constexpr int PER_THREAD = (PK_TILE * ROW) / 256;  // 4 * T
     const int tiles_in = inner_total / PK_TILE;
     const int num_tiles = (outer_total / PK_TILE) * tiles_in;
-    const int row = PK_TILE * T;
     const int tid = threadIdx.x;
-    const int per_thread = (PK_TILE * row) / 256;  // 4 * T
     for (int tl = blockIdx.x; tl < num_tiles; tl += gridDim.x) {
         const int o0 = (tl / tiles_in) * PK_TILE, i0 = (tl % tiles_in) * PK_TILE;
-        float acc[36];
+        float acc[PER_THREAD];
 #pragma unroll
-        for (int j = 0; j < 36; ++j) acc[j] = 0.f;
+        for (int j = 0; j < PER_THREAD; ++j) acc[j] = 0.f;
         for (int sp = 0; sp < nsplits; ++sp) {
             const float* src = parts + static_cast<long long>(sp) * split_stride;
+            float v[PER_THREAD];
 #pragma unroll
-            for (int j = 0; j < 36; ++j) {
-                if (j < per_thread) {
-                    const int idx = tid + 256 * j;
-                    const int o = idx % PK_TILE, i = (idx / PK_TILE) % PK_TILE, t = idx / (PK_TILE * PK_TILE);
-                    acc[j] += __ldcs(src + (static_cast<long long>(t) * inner_total + i0 + i) * outer_total + o0 + o);
-                }
-            }
-        }
-        __syncthreads();
-#pragma unroll
-        for (int j = 0; j < 36; ++j) {
-            if (j < per_thread) {
+            for (int j = 0; j < PER_THREAD; ++j) {
                 const int idx = tid + 256 * j;
                 const int o = idx % PK_TILE, i = (idx / PK_TILE) % PK_TILE, t = idx / (PK_TILE * PK_TILE);
-                tile[o][i * T + t] = acc[j];
+                v[j] = __ldcs(src + (static_cast<long long>(t) * inner_total + i0 + i) * outer_total + o0 + o);
             }
+#pragma unroll
+            for (int j = 0; j < PER_THREAD; ++j) acc[j] += v[j];
         }
         __syncthreads();
-        for (int idx = tid; idx < PK_TILE * row; idx += 256) {
-            const int o = idx / row, r = idx - o * row;
+#pragma unroll
+        for (int j = 0; j < PER_THREAD; ++j) {
+            const int idx = tid + 256 * j;
+            const int o = idx % PK_TILE, i = (idx / PK_TILE) % PK_TILE, t = idx / (PK_TILE * PK_TILE);
+            tile[o][i * T + t] = acc[j];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < PER_THREAD; ++j) {
+            const int idx = tid + 256 * j;
+            const int o = idx / ROW, r = idx - o * ROW;
             dst[(static_cast<long long>(o0 + o) * inner_dst + inner_off + i0) * T + r] = tile[o][r];
         }
     }
@@ -1562,9 +1566,17 @@ __global__ void __launch_bounds__(256) adam_flat_kernel(float* __restrict__ p, c
     // corrections of step t = completed + 1 itself and the last block to finish publishes t — the host never has to
     // hand over per-step scalars, so an unsynchronised host running several steps ahead cannot skew them
     if (step_dev != nullptr) {
-        const double t = static_cast<double>(step_dev[0] + 1);
-        bias_corr1 = static_cast<float>(1.0 - pow(static_cast<double>(beta1), t));
-        bias_corr2_sqrt = static_cast<float>(sqrt(1.0 - pow(static_cast<double>(beta2), t)));
+        // one thread per block evaluates the two double-precision pow()s (every thread doing so made the kernel FP64-bound:
+        // 138 us for 7.76 M parameters against a 30 us HBM floor)
+        __shared__ float s_corr[2];
+        if (threadIdx.x == 0) {
+            const double t = static_cast<double>(step_dev[0] + 1);
+            s_corr[0] = static_cast<float>(1.0 - pow(static_cast<double>(beta1), t));
+            s_corr[1] = static_cast<float>(sqrt(1.0 - pow(static_cast<double>(beta2), t)));
+        }
+        __syncthreads();
+        bias_corr1 = s_corr[0];
+        bias_corr2_sqrt = s_corr[1];
     }
     for (long long i = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) * 4; i < n;
          i += static_cast<long long>(gridDim.x) * blockDim.x * 4) {
