@@ -353,7 +353,18 @@ int run_conv3(int mode, const void* a, int a_stride, int a_coff, int Ca, const v
     // split_stride > 0: fp32-accuracy eval epilogue ([hi | lo | hi] output parts, conv3x3.cuh), modes 0 and 1 only
     B2_CHECK_ARG(split_stride == 0 || ((mode == 0 || mode == 1) && mask == nullptr && stats == nullptr &&
                                        split_stride % 8 == 0 && split_stride >= (mode == 1 ? cout_t : n_total)));
-    B2_CHECK_ARG(B > 0 && H > 0 && W > 0 && H % C3_TILE_H == 0 && W % C3_TILE_W == 0);
+    B2_CHECK_ARG(B > 0 && H > 0 && W > 0);
+    // Any H, W: edge tiles of a shape that is not a multiple of the 16 x 8 pixel tile reach past the image — TMA zero-fills
+    // those loads (the same zeros as the convolution's padding) and clips the stores, the epilogue masks the statistics.
+    // The ConvTranspose modes (no halo) see the batch as ONE image of B*H rows: their sub-pixel views fold (b, h) into one
+    // TMA dimension, so a ragged H must not leave a partial tile between two images.
+    const bool ragged = H % C3_TILE_H != 0 || W % C3_TILE_W != 0;
+    if (ragged && mode != 0) {
+        B2_CHECK_ARG(static_cast<long long>(B) * H < (1ll << 30));
+        H *= B;
+        B = 1;
+    }
+    const int tiles_w = (W + C3_TILE_W - 1) / C3_TILE_W, tiles_h = (H + C3_TILE_H - 1) / C3_TILE_H;
     B2_CHECK_ARG(mask == nullptr || (mode == 0 && mask_stride % 8 == 0 && mask_coff % 8 == 0 && aligned16(mask)));
     if (mode == 1) B2_CHECK_ARG(cout_t % 32 == 0 && n_total == 4 * cout_t);
     B2_CHECK_ARG(Ca % 64 == 0 && n_total % 64 == 0);
@@ -363,7 +374,7 @@ int run_conv3(int mode, const void* a, int a_stride, int a_coff, int Ca, const v
     int block_n = n_total % 256 == 0 ? 256 : (n_total % 128 == 0 ? 128 : 64);
     if (block_n == 256) {
         // wave quantisation on the persistent grid: 128-wide tiles cost ~4 % more per column but halve the tail
-        const long long m_tiles = static_cast<long long>(B) * (H / C3_TILE_H) * (W / C3_TILE_W);
+        const long long m_tiles = static_cast<long long>(B) * tiles_h * tiles_w;
         const int sms = num_sms();
         const long long t256 = m_tiles * (n_total / 256), t128 = m_tiles * (n_total / 128);
         const double c256 = static_cast<double>((t256 + sms - 1) / sms) * 256.0;
@@ -386,11 +397,11 @@ int run_conv3(int mode, const void* a, int a_stride, int a_coff, int Ca, const v
     const int taps = mode == 0 ? 9 : (mode == 2 ? 4 : 1);
     // CTA pairs (tcgen05.mma.cta_group::2, M = 256) for the N = 64 conv3x3 layers whose weights stay resident in shared
     // memory (K <= 1152): each CTA of a pair stages half of the weight rows
-    const long long m_tiles_all = static_cast<long long>(B) * (H / C3_TILE_H) * (W / C3_TILE_W);
+    const long long m_tiles_all = static_cast<long long>(B) * tiles_h * tiles_w;
     // OPT-IN (B200SR_PAIR=1): measured slower than the single-CTA kernel on this part (enc1.3 forward 299 vs 184 us, dec1.0
     // 355 vs 336 us, step +0.3 ms; profiles/r2_cta_pair_experiment.txt) — kept as a tested, documented negative result
     const bool pair_enabled = getenv("B200SR_PAIR") != nullptr;
-    const bool pair = pair_enabled && mode == 0 && block_n == 64 && n_total == 64 && mask == nullptr && split_stride == 0 &&
+    const bool pair = pair_enabled && !ragged && mode == 0 && block_n == 64 && n_total == 64 && mask == nullptr && split_stride == 0 &&
                       taps * (Ca / 64) <= C3Cfg<64>::SB && m_tiles_all % 2 == 0 && num_sms() % 2 == 0 &&
                       getenv("B200SR_NO_BRESIDENT") == nullptr;
     rc = make_weight_map(&mb, w_packed, taps * Ca, n_total, pair ? 32 : (block_n < 128 ? block_n : 128));
@@ -406,8 +417,9 @@ int run_conv3(int mode, const void* a, int a_stride, int a_coff, int Ca, const v
     Conv3Args args;
     args.H = H;
     args.W = W;
-    args.tiles_w = W / C3_TILE_W;
-    args.tiles_hw = (H / C3_TILE_H) * (W / C3_TILE_W);
+    args.tiles_w = tiles_w;
+    args.tiles_hw = tiles_h * tiles_w;
+    args.ragged = ragged ? 1 : 0;
     args.n_tiles = n_total / block_n;
     const long long tiles = static_cast<long long>(B) * args.tiles_hw * args.n_tiles;
     B2_CHECK_ARG(tiles < (1ll << 31));
@@ -523,7 +535,9 @@ int run_wgrad(int t_mode, const void* t, int t_stride, int t_coff, int Ct, int n
               int p_coff, int Cp, int B, int H, int W, float* G, cudaStream_t st, long long ws_floats = 0,
               int* splits_out = nullptr) {
     B2_CHECK_ARG(t != nullptr && p != nullptr && G != nullptr);
-    B2_CHECK_ARG(B > 0 && H > 0 && W > 0 && H % 2 == 0 && W % 16 == 0);
+    // any H, W: K chunks (2 x 16 pixels) that reach past the image load zeros for P through TMA (h and b are separate
+    // dimensions of its map), so they add nothing to the sum
+    B2_CHECK_ARG(B > 0 && H > 0 && W > 0);
     B2_CHECK_ARG(Ct % 64 == 0 && Cp % 64 == 0);
     B2_CHECK_ARG(t_stride % 8 == 0 && t_coff % 8 == 0 && p_stride % 8 == 0 && p_coff % 8 == 0);
     B2_CHECK_ARG(aligned16(t) && aligned16(p) && aligned16(G));
@@ -539,8 +553,8 @@ int run_wgrad(int t_mode, const void* t, int t_stride, int t_coff, int Ct, int n
     WGradArgs args;
     args.H = H;
     args.W = W;
-    args.chunks_w = W / 16;
-    args.chunks_hw = (H / 2) * (W / 16);
+    args.chunks_w = (W + 15) / 16;
+    args.chunks_hw = ((H + 1) / 2) * args.chunks_w;
     args.total_chunks = B * args.chunks_hw;
     args.chunks_per_cta = args.total_chunks;
     args.t_mode = t_mode;
@@ -612,7 +626,6 @@ int launch_wgrad3_t(const CUtensorMap& mx, const CUtensorMap& mz, WG3Args& args,
 // returns -1 when the shape is not covered (caller falls back to the first-generation kernel)
 int run_wgrad3(const void* x, int x_stride, int x_coff, int Cin, const void* dz, int dz_stride, int dz_coff, int Cout,
                int B, int H, int W, float* G, cudaStream_t st, long long ws_floats = 0, int* splits_out = nullptr) {
-    if (H % 4 != 0 || W % 16 != 0) return -1;
     const bool mode_b = Cin == 64;
     if (!mode_b && Cin % 128 != 0) return -1;
     if (Cout % 64 != 0) return -1;
@@ -625,8 +638,9 @@ int run_wgrad3(const void* x, int x_stride, int x_coff, int Cin, const void* dz,
     WG3Args args;
     args.H = H;
     args.W = W;
-    args.chunks_w = W / 16;
-    args.chunks_hw = (H / 4) * (W / 16);
+    // any H, W: K chunks (4 x 16 pixels) past the image edge are zero-filled by TMA for both operands
+    args.chunks_w = (W + 15) / 16;
+    args.chunks_hw = ((H + 3) / 4) * args.chunks_w;
     args.total_chunks = B * args.chunks_hw;
     args.chunks_per_cta = args.total_chunks;
     args.mode_b = mode_b ? 1 : 0;
@@ -675,11 +689,23 @@ int b200sr_device_ok(void) {
     return B200SR_OK;
 }
 
+namespace {
+// exact 16 x 8 pixel tiles -> persistent kernel; shapes the first-generation kernel tiles exactly (8 x 16) stay on it (no
+// padded tile rows at the bottleneck of H % 256 != 0 inputs); everything else -> persistent kernel with ragged edge tiles
+// (the first-generation kernel's deterministic statistics need one slot per tile: with fewer slots it is not used either)
+bool use_conv3(int B, int H, int W, const float* stats = nullptr, int stats_replicas = 0) {
+    const bool ig_exact = H % IG_TILE_H == 0 && W % IG_TILE_W == 0;
+    if (getenv("B200SR_CONV_V1") != nullptr && ig_exact) return false;
+    if (H % C3_TILE_H == 0 && W % C3_TILE_W == 0) return true;
+    if (!ig_exact) return true;
+    return stats != nullptr && stats_replicas < static_cast<long long>(B) * (H / IG_TILE_H) * (W / IG_TILE_W);
+}
+}  // namespace
+
 int b200sr_conv3x3_fwd(const void* x, int x_pix_stride, int x_c_off, int Cin, const void* w_packed, int Cout, int B,
                        int H, int W, void* out, int out_pix_stride, int out_c_off, const float* col_scale,
                        const float* col_shift, int relu, float* stats, int stats_replicas, void* stream) {
-    // persistent kernel needs 16x8 pixel tiles; other shapes (H % 8 == 0, W % 16 == 0) use the generic kernel
-    if (getenv("B200SR_CONV_V1") == nullptr && H % C3_TILE_H == 0 && W % C3_TILE_W == 0)
+    if (use_conv3(B, H, W, stats, stats_replicas))
         return run_conv3(0, x, x_pix_stride, x_c_off, Cin, w_packed, Cout, B, H, W, out, out_pix_stride, out_c_off,
                          col_scale, col_shift, relu, stats, stats_replicas, Cout, static_cast<cudaStream_t>(stream));
     return run_igemm(0, x, x_pix_stride, x_c_off, Cin, 9, w_packed, Cout, B, H, W, 0, Cout, out, out_pix_stride,
@@ -689,7 +715,7 @@ int b200sr_conv3x3_fwd(const void* x, int x_pix_stride, int x_c_off, int Cin, co
 int b200sr_conv3x3_fwd_bn(const void* x, int x_pix_stride, int x_c_off, int Cin, const void* w_packed, int Cout, int B,
                           int H, int W, void* out, int out_pix_stride, int out_c_off, float* stats, int stats_replicas,
                           const b200sr_bn_train* bn, void* stream) {
-    B2_CHECK_ARG(bn != nullptr && stats != nullptr && H % C3_TILE_H == 0 && W % C3_TILE_W == 0);
+    B2_CHECK_ARG(bn != nullptr && stats != nullptr);
     return run_conv3(0, x, x_pix_stride, x_c_off, Cin, w_packed, Cout, B, H, W, out, out_pix_stride, out_c_off, nullptr,
                      nullptr, 0, stats, stats_replicas, Cout, static_cast<cudaStream_t>(stream), nullptr, 0, 0, 0, bn);
 }
@@ -697,7 +723,7 @@ int b200sr_conv3x3_fwd_bn(const void* x, int x_pix_stride, int x_c_off, int Cin,
 int b200sr_conv3x3_dgrad(const void* dy, int dy_pix_stride, int dy_c_off, int Cout, const void* w_packed, int Cin,
                          int B, int H, int W, void* dx, int dx_pix_stride, int dx_c_off, float* stats,
                          int stats_replicas, void* stream) {
-    if (getenv("B200SR_CONV_V1") == nullptr && H % C3_TILE_H == 0 && W % C3_TILE_W == 0)
+    if (use_conv3(B, H, W, stats, stats_replicas))
         return run_conv3(0, dy, dy_pix_stride, dy_c_off, Cout, w_packed, Cin, B, H, W, dx, dx_pix_stride, dx_c_off,
                          nullptr, nullptr, 0, stats, stats_replicas, Cin, static_cast<cudaStream_t>(stream));
     return run_igemm(0, dy, dy_pix_stride, dy_c_off, Cout, 9, w_packed, Cin, B, H, W, 0, Cin, dx, dx_pix_stride,
@@ -708,7 +734,6 @@ int b200sr_conv3x3_dgrad_colsum(const void* dy, int dy_pix_stride, int dy_c_off,
                                 int B, int H, int W, void* dx, int dx_pix_stride, int dx_c_off, float* colsum_slots,
                                 int slots, int ncols, void* stream) {
     B2_CHECK_ARG(colsum_slots != nullptr && slots > 0 && ncols > 0 && ncols <= Cin && ncols % 32 == 0);
-    B2_CHECK_ARG(H % C3_TILE_H == 0 && W % C3_TILE_W == 0);
     return run_conv3(0, dy, dy_pix_stride, dy_c_off, Cout, w_packed, Cin, B, H, W, dx, dx_pix_stride, dx_c_off, nullptr,
                      nullptr, 0, colsum_slots, slots, Cin, static_cast<cudaStream_t>(stream), nullptr, 0, 0, 0, nullptr, ncols);
 }
@@ -716,7 +741,7 @@ int b200sr_conv3x3_dgrad_colsum(const void* dy, int dy_pix_stride, int dy_c_off,
 int b200sr_conv3x3_dgrad_relu(const void* dy, int dy_pix_stride, int dy_c_off, int Cout, const void* w_packed, int Cin,
                               int B, int H, int W, void* dx, int dx_pix_stride, int dx_c_off, const void* act,
                               int act_pix_stride, int act_c_off, float* stats, int stats_replicas, void* stream) {
-    B2_CHECK_ARG(act != nullptr && H % C3_TILE_H == 0 && W % C3_TILE_W == 0);
+    B2_CHECK_ARG(act != nullptr);
     return run_conv3(0, dy, dy_pix_stride, dy_c_off, Cout, w_packed, Cin, B, H, W, dx, dx_pix_stride, dx_c_off, nullptr,
                      nullptr, 0, stats, stats_replicas, Cin, static_cast<cudaStream_t>(stream), act, act_pix_stride,
                      act_c_off);
@@ -725,7 +750,7 @@ int b200sr_conv3x3_dgrad_relu(const void* dy, int dy_pix_stride, int dy_c_off, i
 int b200sr_convT2x2_fwd(const void* x, int x_pix_stride, int x_c_off, int Cin, const void* w_packed, int Cout,
                         const float* bias, int B, int H, int W, void* out, int out_pix_stride, int out_c_off,
                         void* stream) {
-    if (getenv("B200SR_CONV_V1") == nullptr && H % C3_TILE_H == 0 && W % C3_TILE_W == 0)
+    if (use_conv3(B, H, W))
         return run_conv3(1, x, x_pix_stride, x_c_off, Cin, w_packed, 4 * Cout, B, H, W, out, out_pix_stride, out_c_off,
                          nullptr, bias, 0, nullptr, 0, Cout, static_cast<cudaStream_t>(stream));
     return run_igemm(0, x, x_pix_stride, x_c_off, Cin, 1, w_packed, 4 * Cout, B, H, W, 1, Cout, out, out_pix_stride,
@@ -734,7 +759,7 @@ int b200sr_convT2x2_fwd(const void* x, int x_pix_stride, int x_c_off, int Cin, c
 
 int b200sr_convT2x2_dgrad(const void* dup, int dup_pix_stride, int dup_c_off, int Cout, const void* w_packed, int Cin,
                           int B, int H, int W, void* dx, int dx_pix_stride, int dx_c_off, void* stream) {
-    if (getenv("B200SR_CONV_V1") == nullptr && H % C3_TILE_H == 0 && W % C3_TILE_W == 0)
+    if (use_conv3(B, H, W))
         return run_conv3(2, dup, dup_pix_stride, dup_c_off, Cout, w_packed, Cin, B, H, W, dx, dx_pix_stride, dx_c_off,
                          nullptr, nullptr, 0, nullptr, 0, Cin, static_cast<cudaStream_t>(stream));
     return run_igemm(1, dup, dup_pix_stride, dup_c_off, Cout, 4, w_packed, Cin, B, H, W, 0, Cin, dx, dx_pix_stride,
@@ -830,12 +855,18 @@ int b200sr_bn_finalize(const float* stats, int replicas, int C, double count, co
 int b200sr_bnrelu_apply(const void* z, int C, const float* scale, const float* shift, void* act, int act_pix_stride,
                         int act_c_off, void* pooled, int B, int H, int W, void* stream) {
     B2_CHECK_ARG(z && scale && shift && act);
-    B2_CHECK_ARG(C % 8 == 0 && act_pix_stride % 8 == 0 && act_c_off % 8 == 0 && H % 2 == 0 && W % 2 == 0);
+    B2_CHECK_ARG(C % 8 == 0 && act_pix_stride % 8 == 0 && act_c_off % 8 == 0 && B > 0 && H > 0 && W > 0);
+    B2_CHECK_ARG(pooled == nullptr || (H % 2 == 0 && W % 2 == 0));  // MaxPool2d(2,2) of an even-sized level
     B2_CHECK_ARG(aligned16(z) && aligned16(act) && (pooled == nullptr || aligned16(pooled)));
-    const long long total = static_cast<long long>(B) * (H / 2) * (W / 2) * (C / 8);
-    bnrelu_apply_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        static_cast<const __nv_bfloat16*>(z), C, scale, shift, static_cast<__nv_bfloat16*>(act), act_pix_stride,
-        act_c_off, static_cast<__nv_bfloat16*>(pooled), H, W, total);
+    const long long total = static_cast<long long>(B) * ((H + 1) / 2) * ((W + 1) / 2) * (C / 8);
+    if (H % 2 == 0 && W % 2 == 0)
+        bnrelu_apply_kernel<false><<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+            static_cast<const __nv_bfloat16*>(z), C, scale, shift, static_cast<__nv_bfloat16*>(act), act_pix_stride,
+            act_c_off, static_cast<__nv_bfloat16*>(pooled), H, W, total);
+    else
+        bnrelu_apply_kernel<true><<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+            static_cast<const __nv_bfloat16*>(z), C, scale, shift, static_cast<__nv_bfloat16*>(act), act_pix_stride,
+            act_c_off, static_cast<__nv_bfloat16*>(pooled), H, W, total);
     return check_launch("bnrelu_apply_kernel");
 }
 
@@ -1044,7 +1075,7 @@ int b200sr_adam_step_auto(float* p, const float* g, float* m, float* v, int64_t 
 int b200sr_conv3x3_fwd_split(const void* x, int x_pix_stride, int x_c_off, int Cin3, const void* w_packed, int Cout,
                              int B, int H, int W, void* out, int out_pix_stride, int out_c_off, int part_stride,
                              const float* col_scale, const float* col_shift, int relu, void* stream) {
-    B2_CHECK_ARG(Cin3 % 192 == 0 && part_stride >= Cout && H % C3_TILE_H == 0 && W % C3_TILE_W == 0);
+    B2_CHECK_ARG(Cin3 % 192 == 0 && part_stride >= Cout);
     return run_conv3(0, x, x_pix_stride, x_c_off, Cin3, w_packed, Cout, B, H, W, out, out_pix_stride, out_c_off,
                      col_scale, col_shift, relu, nullptr, 0, Cout, static_cast<cudaStream_t>(stream), nullptr, 0, 0,
                      part_stride);
@@ -1053,7 +1084,7 @@ int b200sr_conv3x3_fwd_split(const void* x, int x_pix_stride, int x_c_off, int C
 int b200sr_convT2x2_fwd_split(const void* x, int x_pix_stride, int x_c_off, int Cin3, const void* w_packed, int Cout,
                               const float* bias, int B, int H, int W, void* out, int out_pix_stride, int out_c_off,
                               int part_stride, void* stream) {
-    B2_CHECK_ARG(Cin3 % 192 == 0 && part_stride >= Cout && H % C3_TILE_H == 0 && W % C3_TILE_W == 0);
+    B2_CHECK_ARG(Cin3 % 192 == 0 && part_stride >= Cout);
     return run_conv3(1, x, x_pix_stride, x_c_off, Cin3, w_packed, 4 * Cout, B, H, W, out, out_pix_stride, out_c_off,
                      nullptr, bias, 0, nullptr, 0, Cout, static_cast<cudaStream_t>(stream), nullptr, 0, 0, part_stride);
 }

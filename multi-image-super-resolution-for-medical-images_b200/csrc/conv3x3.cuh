@@ -21,8 +21,11 @@ namespace b200sr {
 
 struct Conv3Args {
     int H, W;
-    int tiles_w;       // W / 8
-    int tiles_hw;      // (H / 16) * (W / 8)
+    int tiles_w;       // ceil(W / 8)
+    int tiles_hw;      // ceil(H / 16) * ceil(W / 8)
+    int ragged;        // H % 16 != 0 or W % 8 != 0: edge tiles reach past the image. TMA zero-fills their loads and clips
+                       // their stores; the epilogue only has to keep the out-of-image pixels out of the statistics (and
+                       // out of the ReLU-mask reads)
     int n_tiles;       // N / BLOCK_N
     int num_tiles;     // B * tiles_hw * n_tiles
     int cin_chunks;    // C / 64
@@ -434,6 +437,7 @@ __global__ void __launch_bounds__((c3_threads<BLOCK_N, MODE_T, SPLIT>()), 1) con
             const int w0 = (t_in % args.tiles_w) * C3_TILE_W;
             const int n0 = n_tile * BLOCK_N;
             n0_last = n0;
+            const bool valid = !args.ragged || (h0 + (row >> 3) < args.H && w0 + (row & 7) < args.W);
             mbar_wait(&acc_full[as], pacc);
             tc_fence_after();
             const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BLOCK_N;
@@ -520,7 +524,7 @@ __global__ void __launch_bounds__((c3_threads<BLOCK_N, MODE_T, SPLIT>()), 1) con
                         const uint4* mp = reinterpret_cast<const uint4*>(args.mask + pix * args.mask_pix_stride +
                                                                          args.mask_c_off + n0 + chunk * 32);
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) mraw[i] = __ldg(mp + i);
+                        for (int i = 0; i < 4; ++i) mraw[i] = valid ? __ldg(mp + i) : make_uint4(0u, 0u, 0u, 0u);
                     }
                     uint32_t raw[32];
                     tmem_ld32(t_addr + chunk * 32, raw);
@@ -556,7 +560,7 @@ __global__ void __launch_bounds__((c3_threads<BLOCK_N, MODE_T, SPLIT>()), 1) con
                     }
                     uint32_t packed[16];
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) packed[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+                    for (int i = 0; i < 16; ++i) packed[i] = valid ? pack_bf16x2(v[2 * i], v[2 * i + 1]) : 0u;
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         const uint32_t j = static_cast<uint32_t>(half * 4 + i);

@@ -527,14 +527,15 @@ __global__ void bn_fold_eval_kernel(const FoldJob* __restrict__ jobs, float eps)
 // (possibly concat-slot) destination and, for encoder blocks, the pooled tensor in the same pass.
 // One thread = 8 channels of a 2x2 pixel quad.
 // ------------------------------------------------------------------------------------------------
+template <bool EDGE>  // EDGE: H or W odd (never with pooling) — the last 2x2 group of a row / column is partial
 __global__ void __launch_bounds__(256) bnrelu_apply_kernel(const __nv_bfloat16* __restrict__ z, int C,
                                                            const float* __restrict__ scale,
                                                            const float* __restrict__ shift,
                                                            __nv_bfloat16* __restrict__ act, int act_stride,
                                                            int act_coff, __nv_bfloat16* __restrict__ pooled, int H,
-                                                           int W, long long total /* B*(H/2)*(W/2)*(C/8) */) {
+                                                           int W, long long total /* B*ceil(H/2)*ceil(W/2)*(C/8) */) {
     const int c8n = C >> 3;
-    const int W2 = W >> 1, H2 = H >> 1;
+    const int W2 = (W + 1) >> 1, H2 = (H + 1) >> 1;  // odd sizes (no pooling then): the last group is partial
     for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
          idx += static_cast<long long>(gridDim.x) * blockDim.x) {
         const int c = static_cast<int>(idx % c8n) * 8;
@@ -547,11 +548,16 @@ __global__ void __launch_bounds__(256) bnrelu_apply_kernel(const __nv_bfloat16* 
         F8 mx;
 #pragma unroll
         for (int k = 0; k < 8; ++k) mx.v[k] = 0.f;  // post-ReLU values are >= 0
+        // no branch between the four loads (they must issue back to back): a pixel past an odd edge re-reads the last row /
+        // column instead and is simply not stored
 #pragma unroll
         for (int dy = 0; dy < 2; ++dy)
 #pragma unroll
             for (int dx = 0; dx < 2; ++dx) {
-                const size_t pix = (static_cast<size_t>(img) * H + 2 * h2 + dy) * W + 2 * w2 + dx;
+                const int hh = 2 * h2 + dy, ww = 2 * w2 + dx;
+                const bool inside = !EDGE || (hh < H && ww < W);
+                const size_t pix = EDGE ? (static_cast<size_t>(img) * H + min(hh, H - 1)) * W + min(ww, W - 1)
+                                        : (static_cast<size_t>(img) * H + hh) * W + ww;
                 F8 v = ld_bf16x8(z + pix * C + c);
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
@@ -559,7 +565,7 @@ __global__ void __launch_bounds__(256) bnrelu_apply_kernel(const __nv_bfloat16* 
                     // pool over the values as stored (bf16), like MaxPool2d reading the activation tensor
                     mx.v[k] = fmaxf(mx.v[k], bf16_round(v.v[k]));
                 }
-                st_bf16x8(act + pix * act_stride + act_coff + c, v);
+                if (inside) st_bf16x8(act + pix * act_stride + act_coff + c, v);
             }
         if (pooled != nullptr) st_bf16x8(pooled + ((static_cast<size_t>(img) * H2 + h2) * W2 + w2) * C + c, mx);
     }

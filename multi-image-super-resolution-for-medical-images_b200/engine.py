@@ -328,14 +328,10 @@ class UNetEngine:
         plan = self._plans.get(key)
         if plan is not None:
             return plan
-        if H % 128 != 0 or W % 256 != 0:
-            # deepest level (H/16, W/16) must still tile into 8x16 pixel GEMM tiles
-            raise _lib.B200SRError(f"b200sr UNet needs H % 128 == 0 and W % 256 == 0 (got {H}x{W})")
-        if (H >> 4) % 16 != 0 and B * ((H >> 4) // 8) * ((W >> 4) // 16) > self.n_sms:
-            # the bottleneck then runs on the generic one-tile-per-CTA kernel, whose deterministic statistics need one
-            # slot per tile
-            raise _lib.B200SRError(f"b200sr UNet: batch {B} at {H}x{W} exceeds the statistic slots of the bottleneck "
-                                   f"layer ({self.n_sms}); use H % 256 == 0 or a smaller batch")
+        if H % 16 != 0 or W % 16 != 0 or H <= 0 or W <= 0:
+            # four 2x2 poolings, like the reference (src/unet_model.py:56-75: any multiple of 16). Levels whose size is not a
+            # multiple of the GEMM pixel tile run the same kernels with ragged edge tiles (csrc/conv3x3.cuh).
+            raise _lib.B200SRError(f"b200sr UNet needs H % 16 == 0 and W % 16 == 0 (got {H}x{W})")
         dev, bf = self.device, torch.bfloat16
         ch = self.chans
         plan = {"B": B, "H": H, "W": W}
@@ -459,8 +455,8 @@ class UNetEngine:
         plan = self._plans.get(key)
         ch = self.chans
         if plan is None:
-            if H % 256 != 0 or W % 128 != 0:
-                raise _lib.B200SRError(f"b200sr UNet fp32 eval mode needs H % 256 == 0 and W % 128 == 0 (got {H}x{W})")
+            if H % 16 != 0 or W % 16 != 0:
+                raise _lib.B200SRError(f"b200sr UNet needs H % 16 == 0 and W % 16 == 0 (got {H}x{W})")
             bf, dev = torch.bfloat16, self.device
             plan = {}
             for lvl in range(5):
@@ -572,7 +568,8 @@ class UNetEngine:
         slots = self.bn_slots[cs.name]  # one statistic slot per CTA: stored, never accumulated -> no zeroing, bit-reproducible
         bn = cs.bn
         track = bn.track_running_stats and bn.running_mean is not None
-        if x_input is None and h % 16 == 0 and w % 8 == 0 and self.fused_bn_finalize:
+        # (shapes that tile exactly into the first-generation kernel's 8 x 16 tiles but not into 16 x 8 stay unfused)
+        if x_input is None and ((h % 16 == 0 and w % 8 == 0) or h % 8 != 0 or w % 16 != 0) and self.fused_bn_finalize:
             # conv + statistics + BatchNorm finalize in ONE launch: the last CTA of every column block finalizes it
             desc = plan.get("bn:" + cs.name)
             if desc is None:

@@ -1,4 +1,4 @@
-"""Teacher-forced per-layer parity at the REAL layer shapes of BASELINE configs[0] (B=8, 256x256).
+"""Teacher-forced per-layer parity at the REAL layer shapes of BASELINE configs[0] (B=8, 256x256) and at ragged shapes.
 
 The CPU oracle (pinned bit-for-bit to the reference, oracle/make_golden.py) runs one train-mode forward/backward and
 hands out, for each of the 18 Conv3x3+BN+ReLU layers and the 4 ConvTranspose2d layers, its own layer input, raw conv
@@ -23,8 +23,14 @@ SLOTS = 148
 WS_FLOATS = 24 * 1024 * 1024
 
 
-@pytest.fixture(scope="module")
-def ctx():
+# (B, H, W): the benchmarked layer shapes, plus two inputs whose levels do NOT tile into the 16 x 8 pixel GEMM tile — the
+# reference takes any multiple of 16 (src/unet_model.py:56-75). 80x48 -> 40x24 -> 20x12 -> 10x6 -> 5x3 (every level ragged,
+# odd sizes, images narrower than a tile); 144x208 -> 72x104 -> 36x52 -> 18x26 -> 9x13 (exact at level 0, ragged below).
+SHAPES = [(8, 256, 256), (3, 80, 48), (2, 144, 208)]
+
+
+@pytest.fixture(scope="module", params=SHAPES, ids=lambda s: "b%d_%dx%d" % s)
+def ctx(request):
     import b200sr
     from b200sr import _lib
     from b200sr.engine import _PACK_JOB_DTYPE, _jobs_to_device
@@ -33,7 +39,7 @@ def ctx():
     torch.backends.cuda.matmul.allow_tf32 = False
     torch.set_num_threads(max(torch.get_num_threads(), 1))
     sd = cases.seeded_state_dict(b200sr.UNet)
-    x, y = cases.seeded_batch(8, 256, 256, 4321)
+    x, y = cases.seeded_batch(*request.param, 4321)
     loss_fn = lambda p, t: ssim_oracle.combined_loss(p, t, 1.0, 0.005, "gaussian")
     loss, out, taps, grads = unet_oracle.layer_taps(sd, x, y, loss_fn)
 
@@ -242,7 +248,8 @@ def test_head_and_loss(ctx):
     B, C, H, W = act.shape
     w, b = ctx.sd["final_conv.weight"].cuda(), ctx.sd["final_conv.bias"].cuda()
     out = torch.zeros(B, 1, H, W, device="cuda")
-    call("b200sr_head_fwd", ptr(nhwc(act)), ptr(w), ptr(b), ptr(out), B * H * W, st)
+    actb = nhwc(act)
+    call("b200sr_head_fwd", ptr(actb), ptr(w), ptr(b), ptr(out), B * H * W, st)
     out_ref = F.conv2d(act, ctx.sd["final_conv.weight"], ctx.sd["final_conv.bias"])
     assert rel(out.cpu(), out_ref) <= TOL
     p = out_ref.clone().requires_grad_(True)

@@ -1,0 +1,110 @@
+"""Whole-network parity at input sizes that do not tile into the GEMM pixel tiles.
+
+The reference UNet takes any H, W that survive four 2x2 poolings, i.e. any multiple of 16 (src/unet_model.py:56-75).
+The tcgen05 kernels tile pixels 16 x 8 (conv) and 4 x 16 / 2 x 16 (weight gradients); sizes that are not a multiple run
+the same kernels with ragged edge tiles (TMA zero fill / clipping, masked statistics). The per-layer 1e-2 bound at such
+shapes is in test_gpu_layers.py; here the network as a whole:
+  * fp32 evaluation mode against the oracle: rel-L2 <= 1e-4 (tight: no bf16 noise to hide an edge bug behind),
+  * bf16 evaluation: rel-L2 <= 1e-2 (north-star bound),
+  * one train step: loss within 1e-3, forward output / gradients of the shallow layers within the bf16 noise floor of a
+    random-init network (see test_gpu_unet.py for why deep-layer gradients cannot be gated at 1e-2 end to end),
+    BN-cancelled bias gradients exactly 0, bit-identical repetition.
+"""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+SHAPES = [(2, 80, 48), (1, 16, 16), (3, 48, 112), (2, 240, 240), (1, 16, 400)]
+
+
+def rel(a, b):
+    a, b = a.double(), b.double()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def cos(a, b):
+    a, b = a.double().flatten(), b.double().flatten()
+    return float((a @ b) / (a.norm() * b.norm()).clamp_min(1e-30))
+
+
+def _trained_stats_sd(B, H, W):
+    """Seeded weights with non-trivial running statistics (one oracle train-mode pass at this very shape)."""
+    import b200sr
+    from oracle import cases, unet_oracle
+    sd = cases.seeded_state_dict(b200sr.UNet)
+    x, y = cases.seeded_batch(max(B, 2), H, W, 77)
+    _, _, _, new_stats = unet_oracle.loss_and_grads(sd, x, y)
+    sd.update(new_stats)
+    return sd
+
+
+@pytest.mark.parametrize("shape", SHAPES, ids=lambda s: "b%d_%dx%d" % s)
+def test_eval_any_multiple_of_16(shape):
+    import b200sr
+    from oracle import cases, unet_oracle
+    B, H, W = shape
+    sd = _trained_stats_sd(B, H, W)
+    x, _ = cases.seeded_batch(B, H, W, 4321)
+    ref = unet_oracle.unet_forward(sd, x, training=False)
+    m = b200sr.UNet()
+    m.load_state_dict(sd)
+    m = m.cuda().eval()
+    with torch.no_grad():
+        out_bf16 = m(x.cuda())
+        m.set_eval_precision("fp32")
+        out_fp32 = m(x.cuda())
+    torch.cuda.synchronize()
+    assert out_bf16.shape == ref.shape
+    assert rel(out_fp32.cpu(), ref) <= 1e-4, (shape, rel(out_fp32.cpu(), ref))
+    assert rel(out_bf16.cpu(), ref) <= 1e-2, (shape, rel(out_bf16.cpu(), ref))
+
+
+@pytest.mark.parametrize("shape", [(2, 80, 48), (3, 48, 112), (2, 240, 240)], ids=lambda s: "b%d_%dx%d" % s)
+def test_train_step_any_multiple_of_16(shape):
+    import b200sr
+    from oracle import cases, ssim_oracle, unet_oracle
+    B, H, W = shape
+    sd = cases.seeded_state_dict(b200sr.UNet)
+    x, y = cases.seeded_batch(B, H, W, 1234)
+    loss_fn = lambda p, t: ssim_oracle.combined_loss(p, t, 1.0, 0.005, "gaussian")
+    o_loss, o_out, o_grads, o_stats = unet_oracle.loss_and_grads(sd, x, y, loss_fn)
+    crit = b200sr.CombinedLoss(1.0, 0.005, "gaussian")
+
+    def run():
+        m = b200sr.UNet()
+        m.load_state_dict(sd)
+        m = m.cuda().train()
+        eng = m._get_engine()
+        out = eng.forward_train(x.cuda())
+        lval, dout = crit.value_and_grad(out, y.cuda())
+        eng.backward(dout)
+        torch.cuda.synchronize()
+        return m, out.clone(), float(lval), [g.detach().clone() for g in eng.grad_views]
+
+    m, out, lval, grads = run()
+    assert abs(lval - float(o_loss)) / abs(float(o_loss)) < 1e-3, (lval, float(o_loss))
+    assert rel(out.cpu(), o_out) < 3e-2, rel(out.cpu(), o_out)
+    msd = m.state_dict()
+    assert max(rel(msd[k].cpu(), v) for k, v in o_stats.items()) < 1e-2
+    names = unet_oracle.param_names(sd)
+    for n, g in zip(names, grads):
+        if n.endswith("conv.0.bias") or n.endswith("conv.3.bias"):
+            assert float(g.abs().max()) == 0.0, n           # BatchNorm cancels these
+        elif n.startswith(("final_conv", "dec1")):
+            assert cos(g.cpu(), o_grads[n]) > 0.98, (n, cos(g.cpu(), o_grads[n]), rel(g.cpu(), o_grads[n]))
+        else:
+            assert cos(g.cpu(), o_grads[n]) > 0.5, (n, cos(g.cpu(), o_grads[n]))   # wiring check; tight gates: test_gpu_layers
+    # deterministic: a second, independent run gives the same bits
+    _, out2, lval2, grads2 = run()
+    assert torch.equal(out, out2) and lval == lval2
+    for n, a, b in zip(names, grads, grads2):
+        assert torch.equal(a, b), n
+
+
+def test_rejects_sizes_the_reference_rejects():
+    import b200sr
+    m = b200sr.UNet().cuda().eval()
+    with pytest.raises(Exception):
+        with torch.no_grad():
+            m(torch.zeros(1, 2, 40, 64, device="cuda"))   # 40 is not a multiple of 16: the reference's concat fails too
