@@ -51,7 +51,9 @@ int b200sr_device_ok(void);
  *   - stats_replicas >= number of SMs (148): DETERMINISTIC slot mode — every CTA stores its partial sums into its own
  *     slot, the unused slots are zeroed by the kernel, nothing has to be pre-zeroed and no atomics touch the data;
  *   - fewer replicas: legacy mode, partial sums are atomically ADDED into slot (CTA % stats_replicas) of a buffer the
- *     caller zeroed. The same rule holds for every entry point that takes (stats, stats_replicas). */
+ *     caller zeroed. The same rule holds for every entry point that takes (stats, stats_replicas).
+ * Any B, H, W > 0: the kernel tiles pixels 16 x 8; edge tiles of other sizes reach past the image (TMA zero fill, clipped
+ * stores, out-of-image pixels masked out of the statistics). The same holds for every tensor-core entry point below. */
 int b200sr_conv3x3_fwd(const void* x, int x_pix_stride, int x_c_off, int Cin, const void* w_packed, int Cout,
                        int B, int H, int W, void* out, int out_pix_stride, int out_c_off,
                        const float* col_scale, const float* col_shift, int relu, float* stats,
@@ -61,8 +63,7 @@ int b200sr_conv3x3_fwd(const void* x, int x_pix_stride, int x_c_off, int Cin, co
  * as above with deterministic statistic slots (stats_replicas >= number of SMs), and b200sr_bn_finalize executed by the
  * last CTA of every 64..256-channel column block to finish (ticket counter per column block; slots summed in slot order).
  * Writes scale / shift / save_mean / save_invstd, updates running_mean / running_var / num_batches_tracked (all nullable
- * together). HOST struct, DEVICE pointers. counters: >= Cout/64 uint32, zero-initialised once, reset by the kernel.
- * Needs H % 16 == 0 and W % 8 == 0 (persistent kernel). */
+ * together). HOST struct, DEVICE pointers. counters: >= Cout/64 uint32, zero-initialised once, reset by the kernel. */
 typedef struct b200sr_bn_train {
     const float* gamma;
     const float* beta;
@@ -100,7 +101,7 @@ int b200sr_conv3x3_dgrad_colsum(const void* dy, int dy_pix_stride, int dy_c_off,
 /* Data gradient fused with the ReLU backward of the layer it flows into (Conv+ReLU stacks without BatchNorm: the
  * DoubleConv of ModelLoader.py:521-533, the VGG features of the perceptual loss): dx = dgrad(dy) * [act > 0], act the
  * (B,H,W,Cin) activation slot of that layer. stats (optional) receives the per-channel sums of the stored dx, i.e. that
- * layer's bias gradient. Needs H % 16 == 0 and W % 8 == 0 (persistent kernel only). */
+ * layer's bias gradient. */
 int b200sr_conv3x3_dgrad_relu(const void* dy, int dy_pix_stride, int dy_c_off, int Cout, const void* w_packed, int Cin,
                               int B, int H, int W, void* dx, int dx_pix_stride, int dx_c_off, const void* act,
                               int act_pix_stride, int act_c_off, float* stats, int stats_replicas, void* stream);

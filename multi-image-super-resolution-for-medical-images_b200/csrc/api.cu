@@ -12,7 +12,6 @@
 #include "deepcnn.cuh"
 #include "fastddpm.cuh"
 #include "firstconv.cuh"
-#include "igemm.cuh"
 #include "loss.cuh"
 #include "wgrad.cuh"
 #include "wgrad3x3.cuh"
@@ -198,89 +197,6 @@ int grid_for(long long total, int block, int max_blocks = 148 * 16) {
     if (g < 1) g = 1;
     if (g > max_blocks) g = max_blocks;
     return static_cast<int>(g);
-}
-
-// ---------------------------------------------------------------------------------------------
-// igemm launch
-// ---------------------------------------------------------------------------------------------
-template <int BLOCK_N, int STAGES>
-int launch_igemm_t(const CUtensorMap& ma, const CUtensorMap& mb, const IGemmArgs& args, int grid, cudaStream_t st) {
-    constexpr int smem = ig_smem_bytes<BLOCK_N, STAGES>();
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(igemm_kernel<BLOCK_N, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             smem);
-        if (e != cudaSuccess) return fail(B200SR_ECUDA, std::string("igemm smem attribute: ") + cudaGetErrorString(e));
-        configured = true;
-    }
-    igemm_kernel<BLOCK_N, STAGES><<<grid, IG_THREADS, smem, st>>>(ma, mb, args);
-    return check_launch("igemm_kernel");
-}
-
-int pick_block_n(int n_total) {
-    const char* env = getenv("B200SR_BLOCK_N");
-    if (env != nullptr) {
-        const int v = atoi(env);
-        if ((v == 64 || v == 128 || v == 256) && n_total % v == 0) return v;
-    }
-    if (n_total % 128 == 0) return 128;
-    return 64;
-}
-
-// a_mode 0: A is (B,H,W,Ca) slot with num_taps in {1,9}; a_mode 1: A is the (B,2H,2W,Ca) slot gathered per (i,j).
-int run_igemm(int a_mode, const void* a, int a_stride, int a_coff, int Ca, int num_taps, const void* w_packed,
-              int n_total, int B, int H, int W, int epi_mode, int cout_t, void* out, int out_stride, int out_coff,
-              const float* col_scale, const float* col_shift, int relu, float* stats, int stats_replicas,
-              cudaStream_t st) {
-    B2_CHECK_ARG(a != nullptr && w_packed != nullptr && out != nullptr);
-    B2_CHECK_ARG(B > 0 && H > 0 && W > 0 && H % IG_TILE_H == 0 && W % IG_TILE_W == 0);
-    B2_CHECK_ARG(Ca % 64 == 0 && n_total % 64 == 0);
-    B2_CHECK_ARG(a_stride % 8 == 0 && a_coff % 8 == 0 && out_stride % 8 == 0 && out_coff % 8 == 0);
-    B2_CHECK_ARG(aligned16(a) && aligned16(w_packed) && aligned16(out));
-    B2_CHECK_ARG(stats == nullptr || stats_replicas > 0);
-    if (epi_mode == 1) B2_CHECK_ARG(cout_t % 32 == 0 && n_total == 4 * cout_t);
-    const int block_n = pick_block_n(n_total);
-    CUtensorMap ma, mb;
-    int rc;
-    if (a_mode == 0)
-        rc = make_act_map(&ma, a, a_stride, a_coff, Ca, B, H, W, IG_TILE_W, IG_TILE_H);
-    else
-        rc = make_gather_map(&ma, a, a_stride, a_coff, Ca, B, H, W, IG_TILE_W, IG_TILE_H);
-    if (rc) return rc;
-    rc = make_weight_map(&mb, w_packed, num_taps * Ca, n_total, block_n);
-    if (rc) return rc;
-
-    IGemmArgs args;
-    args.H = H;
-    args.W = W;
-    args.tiles_w = W / IG_TILE_W;
-    args.tiles_hw = (H / IG_TILE_H) * (W / IG_TILE_W);
-    args.a_mode = a_mode;
-    args.num_taps = num_taps;
-    args.kc_per_tap = Ca / 64;
-    args.n_total = n_total;
-    args.n_tiles = n_total / block_n;
-    args.epi_mode = epi_mode;
-    args.cout_t = cout_t;
-    args.relu = relu;
-    args.out_pix_stride = out_stride;
-    args.out_c_off = out_coff;
-    args.stats_replicas = stats_replicas > 0 ? stats_replicas : 1;
-    args.out = static_cast<__nv_bfloat16*>(out);
-    args.col_scale = col_scale;
-    args.col_shift = col_shift;
-    args.stats = stats;
-    const long long grid = static_cast<long long>(B) * args.tiles_hw * args.n_tiles;
-    B2_CHECK_ARG(grid < (1ll << 31));
-    args.stats_slots = (stats != nullptr && stats_replicas >= static_cast<long long>(B) * args.tiles_hw) ? 1 : 0;
-    switch (block_n) {
-        case 64:
-            return launch_igemm_t<64, 4>(ma, mb, args, static_cast<int>(grid), st);
-        case 128:
-            return launch_igemm_t<128, 3>(ma, mb, args, static_cast<int>(grid), st);
-        default:
-            return launch_igemm_t<256, 4>(ma, mb, args, static_cast<int>(grid), st);
-    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -689,27 +605,11 @@ int b200sr_device_ok(void) {
     return B200SR_OK;
 }
 
-namespace {
-// exact 16 x 8 pixel tiles -> persistent kernel; shapes the first-generation kernel tiles exactly (8 x 16) stay on it (no
-// padded tile rows at the bottleneck of H % 256 != 0 inputs); everything else -> persistent kernel with ragged edge tiles
-// (the first-generation kernel's deterministic statistics need one slot per tile: with fewer slots it is not used either)
-bool use_conv3(int B, int H, int W, const float* stats = nullptr, int stats_replicas = 0) {
-    const bool ig_exact = H % IG_TILE_H == 0 && W % IG_TILE_W == 0;
-    if (getenv("B200SR_CONV_V1") != nullptr && ig_exact) return false;
-    if (H % C3_TILE_H == 0 && W % C3_TILE_W == 0) return true;
-    if (!ig_exact) return true;
-    return stats != nullptr && stats_replicas < static_cast<long long>(B) * (H / IG_TILE_H) * (W / IG_TILE_W);
-}
-}  // namespace
-
 int b200sr_conv3x3_fwd(const void* x, int x_pix_stride, int x_c_off, int Cin, const void* w_packed, int Cout, int B,
                        int H, int W, void* out, int out_pix_stride, int out_c_off, const float* col_scale,
                        const float* col_shift, int relu, float* stats, int stats_replicas, void* stream) {
-    if (use_conv3(B, H, W, stats, stats_replicas))
-        return run_conv3(0, x, x_pix_stride, x_c_off, Cin, w_packed, Cout, B, H, W, out, out_pix_stride, out_c_off,
-                         col_scale, col_shift, relu, stats, stats_replicas, Cout, static_cast<cudaStream_t>(stream));
-    return run_igemm(0, x, x_pix_stride, x_c_off, Cin, 9, w_packed, Cout, B, H, W, 0, Cout, out, out_pix_stride,
-                     out_c_off, col_scale, col_shift, relu, stats, stats_replicas, static_cast<cudaStream_t>(stream));
+    return run_conv3(0, x, x_pix_stride, x_c_off, Cin, w_packed, Cout, B, H, W, out, out_pix_stride, out_c_off,
+                     col_scale, col_shift, relu, stats, stats_replicas, Cout, static_cast<cudaStream_t>(stream));
 }
 
 int b200sr_conv3x3_fwd_bn(const void* x, int x_pix_stride, int x_c_off, int Cin, const void* w_packed, int Cout, int B,
@@ -723,11 +623,8 @@ int b200sr_conv3x3_fwd_bn(const void* x, int x_pix_stride, int x_c_off, int Cin,
 int b200sr_conv3x3_dgrad(const void* dy, int dy_pix_stride, int dy_c_off, int Cout, const void* w_packed, int Cin,
                          int B, int H, int W, void* dx, int dx_pix_stride, int dx_c_off, float* stats,
                          int stats_replicas, void* stream) {
-    if (use_conv3(B, H, W, stats, stats_replicas))
-        return run_conv3(0, dy, dy_pix_stride, dy_c_off, Cout, w_packed, Cin, B, H, W, dx, dx_pix_stride, dx_c_off,
-                         nullptr, nullptr, 0, stats, stats_replicas, Cin, static_cast<cudaStream_t>(stream));
-    return run_igemm(0, dy, dy_pix_stride, dy_c_off, Cout, 9, w_packed, Cin, B, H, W, 0, Cin, dx, dx_pix_stride,
-                     dx_c_off, nullptr, nullptr, 0, stats, stats_replicas, static_cast<cudaStream_t>(stream));
+    return run_conv3(0, dy, dy_pix_stride, dy_c_off, Cout, w_packed, Cin, B, H, W, dx, dx_pix_stride, dx_c_off,
+                     nullptr, nullptr, 0, stats, stats_replicas, Cin, static_cast<cudaStream_t>(stream));
 }
 
 int b200sr_conv3x3_dgrad_colsum(const void* dy, int dy_pix_stride, int dy_c_off, int Cout, const void* w_packed, int Cin,
@@ -750,20 +647,14 @@ int b200sr_conv3x3_dgrad_relu(const void* dy, int dy_pix_stride, int dy_c_off, i
 int b200sr_convT2x2_fwd(const void* x, int x_pix_stride, int x_c_off, int Cin, const void* w_packed, int Cout,
                         const float* bias, int B, int H, int W, void* out, int out_pix_stride, int out_c_off,
                         void* stream) {
-    if (use_conv3(B, H, W))
-        return run_conv3(1, x, x_pix_stride, x_c_off, Cin, w_packed, 4 * Cout, B, H, W, out, out_pix_stride, out_c_off,
-                         nullptr, bias, 0, nullptr, 0, Cout, static_cast<cudaStream_t>(stream));
-    return run_igemm(0, x, x_pix_stride, x_c_off, Cin, 1, w_packed, 4 * Cout, B, H, W, 1, Cout, out, out_pix_stride,
-                     out_c_off, nullptr, bias, 0, nullptr, 0, static_cast<cudaStream_t>(stream));
+    return run_conv3(1, x, x_pix_stride, x_c_off, Cin, w_packed, 4 * Cout, B, H, W, out, out_pix_stride, out_c_off,
+                     nullptr, bias, 0, nullptr, 0, Cout, static_cast<cudaStream_t>(stream));
 }
 
 int b200sr_convT2x2_dgrad(const void* dup, int dup_pix_stride, int dup_c_off, int Cout, const void* w_packed, int Cin,
                           int B, int H, int W, void* dx, int dx_pix_stride, int dx_c_off, void* stream) {
-    if (use_conv3(B, H, W))
-        return run_conv3(2, dup, dup_pix_stride, dup_c_off, Cout, w_packed, Cin, B, H, W, dx, dx_pix_stride, dx_c_off,
-                         nullptr, nullptr, 0, nullptr, 0, Cin, static_cast<cudaStream_t>(stream));
-    return run_igemm(1, dup, dup_pix_stride, dup_c_off, Cout, 4, w_packed, Cin, B, H, W, 0, Cin, dx, dx_pix_stride,
-                     dx_c_off, nullptr, nullptr, 0, nullptr, 0, static_cast<cudaStream_t>(stream));
+    return run_conv3(2, dup, dup_pix_stride, dup_c_off, Cout, w_packed, Cin, B, H, W, dx, dx_pix_stride, dx_c_off,
+                     nullptr, nullptr, 0, nullptr, 0, Cin, static_cast<cudaStream_t>(stream));
 }
 
 int b200sr_conv3x3_wgrad(const void* x, int x_pix_stride, int x_c_off, int Cin, const void* dz, int dz_pix_stride,
@@ -1285,11 +1176,8 @@ int b200sr_headw_bwd(const float* dout, const void* act, int C, const float* w, 
 /* Conv2d 1x1 forward / dgrad: D[pixel, n] = sum_c A[pixel, c] * Wp[n, c] (Wp: PACK_CONV1X1_FWD / _DGRAD) */
 int b200sr_conv1x1(const void* a, int a_pix_stride, int a_c_off, int Ca, const void* w_packed, int N, int B, int H,
                    int W, void* out, int out_pix_stride, int out_c_off, float* stats, int stats_replicas, void* stream) {
-    if (H % C3_TILE_H == 0 && W % C3_TILE_W == 0)
-        return run_conv3(3, a, a_pix_stride, a_c_off, Ca, w_packed, N, B, H, W, out, out_pix_stride, out_c_off, nullptr,
-                         nullptr, 0, stats, stats_replicas, N, static_cast<cudaStream_t>(stream));
-    return run_igemm(0, a, a_pix_stride, a_c_off, Ca, 1, w_packed, N, B, H, W, 0, N, out, out_pix_stride, out_c_off,
-                     nullptr, nullptr, 0, stats, stats_replicas, static_cast<cudaStream_t>(stream));
+    return run_conv3(3, a, a_pix_stride, a_c_off, Ca, w_packed, N, B, H, W, out, out_pix_stride, out_c_off, nullptr,
+                     nullptr, 0, stats, stats_replicas, N, static_cast<cudaStream_t>(stream));
 }
 
 int b200sr_conv1x1_wgrad(const void* x, int x_pix_stride, int x_c_off, int Cin, const void* dz, int dz_pix_stride,

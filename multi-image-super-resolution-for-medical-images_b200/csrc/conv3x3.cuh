@@ -3,7 +3,10 @@
 //
 //   D[pixel, n] = sum_{dh,dw,c} A[pixel + (dh-1, dw-1), c] * Wp[n, (dh*3+dw)*C + c]
 //
-// What differs from the generic one-tile-per-CTA kernel (igemm.cuh):
+// Design (this kernel replaced a first-generation one-tile-per-CTA kernel, retired in round 2):
+//   * any H, W: edge tiles of a shape that is not a multiple of the 16 x 8 pixel tile reach past the image — TMA zero-fills
+//     those loads (the same zeros as the padding), clips the stores, and the epilogue keeps the out-of-image pixels out of
+//     the BatchNorm statistics (Conv3Args::ragged).
 //   * persistent CTAs (one per SM) walk a static tile schedule; the accumulator is double-buffered in TMEM so the
 //     epilogue of tile i overlaps the main loop of tile i+1; barrier set-up / TMEM allocation happen once per CTA.
 //   * an output tile is 16 rows x 8 columns of pixels. For a fixed horizontal tap dw, ONE haloed TMA box

@@ -568,8 +568,7 @@ class UNetEngine:
         slots = self.bn_slots[cs.name]  # one statistic slot per CTA: stored, never accumulated -> no zeroing, bit-reproducible
         bn = cs.bn
         track = bn.track_running_stats and bn.running_mean is not None
-        # (shapes that tile exactly into the first-generation kernel's 8 x 16 tiles but not into 16 x 8 stay unfused)
-        if x_input is None and ((h % 16 == 0 and w % 8 == 0) or h % 8 != 0 or w % 16 != 0) and self.fused_bn_finalize:
+        if x_input is None and self.fused_bn_finalize:
             # conv + statistics + BatchNorm finalize in ONE launch: the last CTA of every column block finalizes it
             desc = plan.get("bn:" + cs.name)
             if desc is None:

@@ -283,10 +283,9 @@ class FastDDPMEngine:
         plan = self._plans.get(key)
         if plan is not None:
             return plan
-        if H % 64 != 0 or W % 64 != 0:
-            # the deepest level (H/4, W/4) must tile into the 16x8-pixel tiles of the persistent conv kernel and the
-            # first layer into 16x16 tiles
-            raise _lib.B200SRError(f"b200sr UNet2D needs H % 64 == 0 and W % 64 == 0 (got {H}x{W})")
+        if H % 16 != 0 or W % 16 != 0:
+            # the first layer works on 16x16-pixel tiles; the deeper levels may be ragged (csrc/conv3x3.cuh)
+            raise _lib.B200SRError(f"b200sr UNet2D needs H % 16 == 0 and W % 16 == 0 (got {H}x{W})")
         dev, bf, f32 = self.device, torch.bfloat16, torch.float32
         H1, W1, H2, W2 = H // 2, W // 2, H // 4, W // 4
 

@@ -111,8 +111,8 @@ class PerceptualLoss(nn.Module):
         b = self._bufs.get(key)
         if b is not None:
             return b
-        if H % 64 != 0 or W % 64 != 0:
-            raise _lib.B200SRError(f"PerceptualLoss needs H % 64 == 0 and W % 64 == 0 (got {H}x{W})")
+        if H % 16 != 0 or W % 16 != 0:
+            raise _lib.B200SRError(f"PerceptualLoss needs H % 16 == 0 and W % 16 == 0 (got {H}x{W})")
         bf = torch.bfloat16
         N = 2 * B
         shapes = {1: (H, W, 64), 2: (H, W, 64), 3: (H // 2, W // 2, 128), 4: (H // 2, W // 2, 128),

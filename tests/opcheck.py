@@ -1048,6 +1048,7 @@ CHECKS = {
     # (measured 8e-4); the input gradient is ReLU-mask sensitive like the UNet's own deep gradients (measured
     # rel-L2 8.6e-2, cosine 0.996 vs the fp64 oracle)
     "perceptual_vgg": (perceptual, {}, {"loss": 1e-2, "grad": 0.15, "grad_cos_defect": 1e-2}),
+    "perceptual_vgg_ragged_48x80": (perceptual, dict(B=2, H=48, W=80), {"loss": 1e-2, "grad": 0.15, "grad_cos_defect": 1e-2}),
     "adam": (adam, {}, {"delta": 1e-3,  # fp32 rounding of p (~1) against a 1e-4 update
               "m": 1e-5, "v": 1e-4}),
     "layout_casts": (layout_casts, {}, {"fwd_exact": 0.0, "back_exact": 0.0}),
@@ -1105,6 +1106,37 @@ CHECKS = {
     "fp32_convT_split": (convT_fwd_split, {}, {"out": 1e-4, "hi_copies_equal": 0.0, "slot_untouched": 0.0}),
     "fp32_convT_split_big": (convT_fwd_split, dict(Cin=1024, Cout=512, B=2, H=16, W=16), {"out": 1e-4}),
     "fp32_small_ops": (split_small_ops, {}, {"conv1": 1e-5, "maxpool_exact": 0.0, "head": 1e-5}),
+    # ragged shapes: H, W that are not multiples of the 16 x 8 / 4 x 16 / 2 x 16 pixel tiles (edge tiles reach past the image:
+    # TMA zero fill + clipped stores, out-of-image pixels masked out of the statistics; the ConvTranspose modes fold the batch
+    # into one image of B*H rows). The levels of a 80x48 / 240x240 input look like this.
+    "ragged_conv3x3_fwd_10x6": (conv3x3_fwd, dict(B=3, H=10, W=6), {"out": BF16, "stats_sum": 1e-3, "stats_sq": 1e-3}),
+    "ragged_conv3x3_fwd_5x3_deep": (conv3x3_fwd, dict(B=3, H=5, W=3, Cin=512, Cout=1024),
+                                    {"out": BF16, "stats_sum": 1e-3, "stats_sq": 1e-3}),
+    "ragged_conv3x3_fwd_30x30_slot": (conv3x3_fwd, dict(B=2, H=30, W=30, Cin=128, Cout=64, slot=True, affine=True),
+                                      {"out": BF16, "slot_untouched": 0.0}),
+    "ragged_conv3x3_stats_slots_60x60": (conv3x3_fwd_slots, dict(B=3, H=60, W=60, Cin=64, Cout=128),
+                                         {"out": BF16, "stats_sum": 1e-4, "stats_sq": 1e-4, "bitwise": 0.0}),
+    "ragged_fused_conv_bn_finalize_15x15": (conv3x3_fwd_bn_fused, dict(B=4, H=15, W=15, Cin=128, Cout=256),
+                                            {"z": BF16, "scale": 1e-5, "shift": 1e-4, "mean": 1e-4, "invstd": 1e-5,
+                                             "running_mean": 1e-5, "running_var": 1e-5, "counters_reset": 0.0, "bitwise": 0.0}),
+    "ragged_conv3x3_dgrad_20x12": (conv3x3_dgrad, dict(B=3, H=20, W=12), {"dx": BF16, "colsum": 1e-3}),
+    "ragged_conv3x3_dgrad_relu_9x13": (conv3x3_dgrad_relu, dict(B=2, H=9, W=13),
+                                       {"dx": BF16, "colsum": 1e-3, "masked_nonzero": 0.0}),
+    "ragged_conv3x3_wgrad_modeA_15x15": (conv3x3_wgrad_det, dict(Cin=256, Cout=256, B=3, H=15, W=15),
+                                         {"dw": BF16, "bitwise": 0.0}),
+    "ragged_conv3x3_wgrad_modeB_30x26": (conv3x3_wgrad_det, dict(Cin=64, Cout=64, B=2, H=30, W=26),
+                                         {"dw": BF16, "bitwise": 0.0}),
+    "ragged_conv3x3_wgrad_generic_5x3": (conv3x3_wgrad_det, dict(Cin=320, Cout=256, B=3, H=5, W=3),
+                                         {"dw": BF16, "bitwise": 0.0}),
+    "ragged_convT_fwd_5x3": (convT_fwd, dict(B=3, H=5, W=3), {"out": BF16, "slot_untouched": 0.0}),
+    "ragged_convT_fwd_15x15_big": (convT_fwd, dict(Cin=1024, Cout=512, B=2, H=15, W=15), {"out": BF16}),
+    "ragged_convT_dgrad_5x3": (convT_dgrad, dict(B=3, H=5, W=3), {"dx": BF16}),
+    "ragged_convT_dgrad_30x30": (convT_dgrad, dict(B=2, H=30, W=30), {"dx": BF16}),
+    "ragged_convT_wgrad_5x3": (convT_wgrad_det, dict(B=3, H=5, W=3), {"dw": BF16, "bitwise": 0.0}),
+    "ragged_convT_wgrad_15x15": (convT_wgrad_det, dict(Cin=512, Cout=256, B=2, H=15, W=15), {"dw": BF16, "bitwise": 0.0}),
+    "ragged_fp32_conv3x3_split_10x6": (conv3x3_fwd_split, dict(B=3, H=10, W=6), {"out": 1e-4, "hi_copies_equal": 0.0}),
+    "ragged_fp32_convT_split_5x3": (convT_fwd_split, dict(B=3, H=5, W=3),
+                                    {"out": 1e-4, "hi_copies_equal": 0.0, "slot_untouched": 0.0}),
 }
 
 

@@ -108,3 +108,29 @@ def test_rejects_sizes_the_reference_rejects():
     with pytest.raises(Exception):
         with torch.no_grad():
             m(torch.zeros(1, 2, 40, 64, device="cuda"))   # 40 is not a multiple of 16: the reference's concat fails too
+
+
+def test_fastddpm_train_step_at_a_ragged_size():
+    """Fast-DDPM UNet2D (two poolings) at 48x80: levels 24x40 and 12x20 do not tile into 16x8 pixels."""
+    import b200sr
+    from oracle import cases, fastddpm_oracle
+    case = dict(B=2, H=48, W=80, seed=9753, noise_seed=77, t=(3, 8), init_seed=11)
+    sd = cases.fastddpm_state_dict(b200sr.FastDDPM, case)
+    cond, target, t, noise = cases.fastddpm_inputs(case)
+    o_loss, o_eps, o_grads = fastddpm_oracle.loss_and_grads(sd, cond, target, t, noise)
+    m = b200sr.FastDDPM(T=10, device="cpu")
+    m.load_state_dict(sd)
+    m = m.cuda()
+    m.scheduler.to("cuda")
+    m.train()
+    eng = m.unet._get_engine()
+    loss, dout = m.loss_and_grad(cond.cuda(), target.cuda(), t.cuda(), noise=noise.cuda())
+    eps = eng.forward(target.cuda(), cond.cuda(), t.cuda(), noise=noise.cuda(), coef=m._coef(t.cuda(), target.cuda().device),
+                      keep=True)
+    eng.backward(dout)
+    torch.cuda.synchronize()
+    assert rel(eps.cpu(), o_eps) < 1e-2
+    assert abs(float(loss) - float(o_loss)) / float(o_loss) < 1e-3
+    for (name, _), g in zip(m.unet.named_parameters(), eng.grad_views):
+        ref = o_grads["unet." + name]
+        assert cos(g.cpu(), ref) > 0.999 and rel(g.cpu(), ref) < 3e-2, (name, rel(g.cpu(), ref), cos(g.cpu(), ref))
