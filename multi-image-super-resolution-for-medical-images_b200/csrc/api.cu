@@ -811,11 +811,14 @@ namespace {
 int launch_reduce_unpack(float* ws, int splits, long long split_stride, int T, int outer_total, int inner_total,
                          int inner_dst, int inner_off, float* dst, cudaStream_t st) {
     B2_CHECK_ARG(outer_total % PK_TILE == 0 && inner_total % PK_TILE == 0 && (T == 9 || T == 4 || T == 1));
-    if (splits > 1) {
-        // stage 2a: fold the split-K slices into slice 0 (element-parallel; slice lanes when there are many slices).
-        // Measured (profiles/r2_ab_stage2.txt): letting the layout kernel below sum the slices itself for layers with
-        // >= 128 tiles saves a launch but costs 0.25 ms per step — its strided 4-byte reads of several slices are slower
-        // than this coalesced float4 pass.
+    int tiles = (outer_total / PK_TILE) * (inner_total / PK_TILE);
+    // Layers with at least one tile per SM and few split-K slices: the layout kernel sums the slices itself (fixed slice
+    // order), one launch instead of two. (Round-2 A/B had this at +0.25 ms — that was the run-time-T kernel whose loads
+    // were serialised, see wgrad_reduce_unpack_kernel.) B200SR_UNPACK_TWO_STAGE=1 restores the two-stage form.
+    static const bool two_stage = getenv("B200SR_UNPACK_TWO_STAGE") != nullptr;
+    const bool direct = !two_stage && splits > 1 && splits <= 4 && tiles >= num_sms();
+    if (splits > 1 && !direct) {
+        // stage 2a: fold the split-K slices into slice 0 (element-parallel; slice lanes when there are many slices)
         B2_CHECK_ARG(split_stride % 4 == 0);
         const long long n4 = split_stride / 4;
         const int lanes = splits >= 32 ? 8 : (splits >= 16 ? 4 : (splits >= 8 ? 2 : 1));
@@ -824,16 +827,16 @@ int launch_reduce_unpack(float* ws, int splits, long long split_stride, int T, i
                                                                                    n4, n4, lanes);
     }
     // stage 2b: kernel layout [t][inner][outer] -> PyTorch parameter layout
-    int tiles = (outer_total / PK_TILE) * (inner_total / PK_TILE);
+    const int ns = direct ? splits : 1;
     if (tiles > num_sms() * 8) tiles = num_sms() * 8;
     if (T == 9)
-        wgrad_reduce_unpack_kernel<9><<<tiles, 256, 0, st>>>(ws, 1, split_stride, outer_total, inner_total, inner_dst,
+        wgrad_reduce_unpack_kernel<9><<<tiles, 256, 0, st>>>(ws, ns, split_stride, outer_total, inner_total, inner_dst,
                                                              inner_off, dst);
     else if (T == 4)
-        wgrad_reduce_unpack_kernel<4><<<tiles, 256, 0, st>>>(ws, 1, split_stride, outer_total, inner_total, inner_dst,
+        wgrad_reduce_unpack_kernel<4><<<tiles, 256, 0, st>>>(ws, ns, split_stride, outer_total, inner_total, inner_dst,
                                                              inner_off, dst);
     else
-        wgrad_reduce_unpack_kernel<1><<<tiles, 256, 0, st>>>(ws, 1, split_stride, outer_total, inner_total, inner_dst,
+        wgrad_reduce_unpack_kernel<1><<<tiles, 256, 0, st>>>(ws, ns, split_stride, outer_total, inner_total, inner_dst,
                                                              inner_off, dst);
     return check_launch("wgrad_reduce_unpack_kernel");
 }
