@@ -223,25 +223,33 @@ int launch_conv3_t(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorM
         if (e != cudaSuccess) return fail(B200SR_ECUDA, std::string("conv3x3 smem attribute: ") + cudaGetErrorString(e));
         configured = true;
     }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(c3_threads<BLOCK_N, MODE, SPLIT>());
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attrs[2];
+    int na = 0;
     if (PAIR) {
         // clusters of two CTAs (one TPC): tcgen05.mma.cta_group::2
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(grid);
-        cfg.blockDim = dim3(c3_threads<BLOCK_N, MODE, SPLIT>());
-        cfg.dynamicSmemBytes = smem;
-        cfg.stream = st;
-        cudaLaunchAttribute attr;
-        attr.id = cudaLaunchAttributeClusterDimension;
-        attr.val.clusterDim.x = 2;
-        attr.val.clusterDim.y = 1;
-        attr.val.clusterDim.z = 1;
-        cfg.attrs = &attr;
-        cfg.numAttrs = 1;
-        cudaError_t e = cudaLaunchKernelEx(&cfg, conv3x3_kernel<BLOCK_N, MODE, SPLIT, PAIR>, ma, mb, mo, args);
-        if (e != cudaSuccess) return fail(B200SR_ECUDA, std::string("conv3x3 pair launch: ") + cudaGetErrorString(e));
-        return check_launch("conv3x3_kernel (cta_group::2)");
+        attrs[na].id = cudaLaunchAttributeClusterDimension;
+        attrs[na].val.clusterDim.x = 2;
+        attrs[na].val.clusterDim.y = 1;
+        attrs[na].val.clusterDim.z = 1;
+        ++na;
     }
-    conv3x3_kernel<BLOCK_N, MODE, SPLIT, PAIR><<<grid, c3_threads<BLOCK_N, MODE, SPLIT>(), smem, st>>>(ma, mb, mo, args);
+    // programmatic dependent launch: the CTAs may be scheduled while the previous kernel of the stream drains; the kernel
+    // does its set-up (mbarriers, TMEM, descriptor prefetch) and then waits for that kernel (griddep_wait, conv3x3.cuh)
+    static const bool pdl = getenv("B200SR_NO_PDL") == nullptr;
+    if (pdl) {
+        attrs[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attrs[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
+    cfg.attrs = attrs;
+    cfg.numAttrs = na;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, conv3x3_kernel<BLOCK_N, MODE, SPLIT, PAIR>, ma, mb, mo, args);
+    if (e != cudaSuccess) return fail(B200SR_ECUDA, std::string("conv3x3 launch: ") + cudaGetErrorString(e));
     return check_launch("conv3x3_kernel");
 }
 

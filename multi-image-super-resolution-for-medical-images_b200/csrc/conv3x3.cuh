@@ -89,7 +89,7 @@ __device__ __forceinline__ void c3_bn_finalize(const Conv3Args& args, int n0, in
         const int which = task / (BLOCK_N / 4), c4 = task % (BLOCK_N / 4);
         double acc[4] = {0.0, 0.0, 0.0, 0.0};
         const float* base = args.stats + static_cast<size_t>(which) * args.n_total + n0 + 4 * c4;
-#pragma unroll 4
+#pragma unroll 8  // this CTA is the last of its column block: every round trip here is on the critical path
         for (int sl = lane; sl < used; sl += LANES) {
             const float4 v = __ldcg(reinterpret_cast<const float4*>(base + static_cast<size_t>(sl) * 2 * args.n_total));
             acc[0] += v.x;
@@ -259,6 +259,10 @@ __global__ void __launch_bounds__((c3_threads<BLOCK_N, MODE_T, SPLIT>()), 1) con
             tmem_relinquish();
         }
     }
+    // PDL: everything above ran while the previous kernel of the stream was still draining; from here on its results are
+    // needed. The trigger comes AFTER the wait so that "this grid has started" implies "its predecessors have completed".
+    griddep_wait();
+    griddep_launch_dependents();
     if (warp >= 4 && warp < 8 && blockIdx.x < args.num_tiles) {
         // the tile schedule keeps a CTA on one column block, so its affine vectors can be staged once
         const int n0 = (static_cast<int>(blockIdx.x) % args.n_tiles) * BLOCK_N;

@@ -465,7 +465,7 @@ __global__ void __launch_bounds__(256) bn_finalize_kernel(const float* __restric
     const int c = blockIdx.x * 32 + col;
     double s = 0.0, q = 0.0;
     if (c < C) {
-#pragma unroll 4
+#pragma unroll 8
         for (int r = sl; r < replicas; r += 8) {
             s += stats[(static_cast<size_t>(r) * 2) * C + c];
             q += stats[(static_cast<size_t>(r) * 2 + 1) * C + c];
@@ -534,6 +534,7 @@ __global__ void __launch_bounds__(256) bnrelu_apply_kernel(const __nv_bfloat16* 
                                                            __nv_bfloat16* __restrict__ act, int act_stride,
                                                            int act_coff, __nv_bfloat16* __restrict__ pooled, int H,
                                                            int W, long long total /* B*ceil(H/2)*ceil(W/2)*(C/8) */) {
+    griddep_launch_dependents();  // PDL: a conv kernel launched next may start its set-up while this grid drains
     const int c8n = C >> 3;
     const int W2 = (W + 1) >> 1, H2 = (H + 1) >> 1;  // odd sizes (no pooling then): the last group is partial
     for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
@@ -689,6 +690,7 @@ __global__ void __launch_bounds__(256) maxpool2x2_bwd_kernel(const __nv_bfloat16
                                                              int dskip_stride, int dskip_coff, int C,
                                                              __nv_bfloat16* __restrict__ dy, int H, int W,
                                                              long long total) {
+    griddep_launch_dependents();  // PDL: a conv kernel launched next may start its set-up while this grid drains
     const int c8n = C >> 3;
     const int W2 = W >> 1, H2 = H >> 1;
     for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
@@ -991,6 +993,7 @@ __global__ void __launch_bounds__(256, 2) maxpool2x2_bwd_bnred_kernel(
     const __nv_bfloat16* __restrict__ z, const float* __restrict__ scale, const float* __restrict__ shift,
     const float* __restrict__ mean, const float* __restrict__ invstd, float* __restrict__ sums, float* __restrict__ ws,
     unsigned* __restrict__ counters, int H, int W, long long nquads) {
+    griddep_launch_dependents();  // PDL: a conv kernel launched next may start its set-up while this grid drains
     const int slices = gridDim.x, slice = blockIdx.x, group = blockIdx.y;
     const int tx = threadIdx.x & 7, ty = threadIdx.x >> 3;
     const int c = group * 64 + tx * 8;
@@ -1110,6 +1113,7 @@ __global__ void __launch_bounds__(256, 3) bn_bwd_apply_fused_kernel(
     const float* __restrict__ invstd, const float* __restrict__ sums, int replicas, float count,
     float* __restrict__ dgamma, float* __restrict__ dbeta, __nv_bfloat16* __restrict__ dz, long long npix,
     const __nv_bfloat16* __restrict__ mask_src) {
+    griddep_launch_dependents();  // PDL: a conv kernel launched next may start its set-up while this grid drains
     const int CV = C >> 3;
     const int PB = 256 / CV;
     const int cv = threadIdx.x % CV, pl = threadIdx.x / CV;
@@ -1497,6 +1501,7 @@ __global__ void __launch_bounds__(256) maxpool2x2_split_kernel(const __nv_bfloat
                                                                int in_coff, int in_part, int C,
                                                                __nv_bfloat16* __restrict__ out, int H, int W,
                                                                long long total) {
+    griddep_launch_dependents();  // PDL: a conv kernel launched next may start its set-up while this grid drains
     const int c8n = C >> 3;
     const int W2 = W >> 1, H2 = H >> 1;
     for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;

@@ -90,6 +90,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // ---------------------------------------------------------------------------------------------
 // TMA
 // ---------------------------------------------------------------------------------------------
+// Programmatic dependent launch (PDL). A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start
+// while its predecessor in the stream is still draining: everything before griddep_wait() (barrier init, TMEM allocation,
+// descriptor prefetch) overlaps the predecessor's tail; griddep_wait() returns once the predecessor grid has completed and
+// its writes are visible. Without the launch attribute both instructions are no-ops.
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// lets the NEXT kernel in the stream (if launched with the attribute) be scheduled as soon as every CTA of this grid has
+// executed this instruction or exited
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
 }
