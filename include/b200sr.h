@@ -37,6 +37,10 @@ enum {
 
 int b200sr_version(void);
 const char* b200sr_last_error(void);
+
+/* Launch accounting: number of kernels the last b200sr_*_wgrad_det call of this thread enqueued (split-K kernel, the slice
+ * fold when it was needed, the layout kernel): 2 or 3. Used by bench.py's gpu_launches claim. */
+int b200sr_last_wgrad_launches(void);
 /* 0 when a compute-capability 10.x device is current, B200SR_ENODEV otherwise. */
 int b200sr_device_ok(void);
 

@@ -21,6 +21,7 @@ _P = c_void_p
 _SIGNATURES = {
     "b200sr_version": [],
     "b200sr_last_error": [],
+    "b200sr_last_wgrad_launches": [],
     "b200sr_device_ok": [],
     "b200sr_conv3x3_fwd": [_P, c_int, c_int, c_int, _P, c_int, c_int, c_int, c_int, _P, c_int, c_int, _P, _P, c_int,
                            _P, c_int, _P],
@@ -114,7 +115,7 @@ _SIGNATURES = {
     "b200sr_nhwc_bf16_to_nchw_f32": [_P, c_int, c_int, _P, c_int, c_int, c_int, c_int, _P],
 }
 _RESTYPES = {"b200sr_last_error": c_char_p, "b200sr_bn_bwd_ws_floats": c_int64}
-_PLAIN_VALUE = ("b200sr_version", "b200sr_last_error", "b200sr_bn_bwd_ws_floats")  # return a value, not a status code
+_PLAIN_VALUE = ("b200sr_version", "b200sr_last_error", "b200sr_bn_bwd_ws_floats", "b200sr_last_wgrad_launches")  # return a value, not a status code
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 
@@ -157,9 +158,9 @@ def last_error() -> str:
 # ---- launch accounting and optional per-call CUDA-event timing (used by bench.py for the roofline) ------------
 LAUNCH_COUNTER = {"n": 0}
 # entry points that enqueue more than one kernel (split-K gradient + its fixed-order reduction, multi-kernel helpers)
-_KERNELS_PER_CALL = {"b200sr_conv3x3_wgrad_det": 3, "b200sr_convT2x2_wgrad_det": 3, "b200sr_conv1x1_wgrad_det": 3,
-                     "b200sr_conv1_wgrad_det": 2, "b200sr_bn_bwd_masked": 2, "b200sr_grad_clip": 2, "b200sr_volume_metrics": 3, "b200sr_fd_time_bwd": 5,
-                     "b200sr_bn_bwd_ws_floats": 0, "b200sr_version": 0, "b200sr_device_ok": 0}
+_WGRAD_DET = ("b200sr_conv3x3_wgrad_det", "b200sr_convT2x2_wgrad_det", "b200sr_conv1x1_wgrad_det")  # 2 or 3: asked per call
+_KERNELS_PER_CALL = {"b200sr_conv1_wgrad_det": 2, "b200sr_bn_bwd_masked": 2, "b200sr_grad_clip": 2, "b200sr_volume_metrics": 3, "b200sr_fd_time_bwd": 5,
+                     "b200sr_bn_bwd_ws_floats": 0, "b200sr_version": 0, "b200sr_device_ok": 0, "b200sr_last_wgrad_launches": 0}
 GEMM_OPS = ("b200sr_conv3x3_fwd", "b200sr_conv3x3_dgrad", "b200sr_conv3x3_dgrad_relu", "b200sr_conv3x3_wgrad", "b200sr_convT2x2_fwd",
             "b200sr_convT2x2_dgrad", "b200sr_convT2x2_wgrad", "b200sr_conv1x1", "b200sr_conv1x1_wgrad",
             "b200sr_conv3x3_wgrad_det", "b200sr_convT2x2_wgrad_det", "b200sr_conv1x1_wgrad_det", "b200sr_conv3x3_fwd_bn", "b200sr_conv3x3_dgrad_colsum", "b200sr_conv3x3_fwd_split", "b200sr_convT2x2_fwd_split")
@@ -266,7 +267,10 @@ def call(name: str, *args):
         _profile.append((name, e0, e1) + _cost(name, args))
     else:
         rc = fn(*args)
-    LAUNCH_COUNTER["n"] += _KERNELS_PER_CALL.get(name, 1)
+    if name in _WGRAD_DET:
+        LAUNCH_COUNTER["n"] += load().b200sr_last_wgrad_launches() if rc == 0 else 0
+    else:
+        LAUNCH_COUNTER["n"] += _KERNELS_PER_CALL.get(name, 1)
     if name in _PLAIN_VALUE:
         return rc
     if rc != 0:

@@ -42,6 +42,9 @@ int bn_blocks_per_sm() {
     return v;
 }
 
+// kernels enqueued by the last *_wgrad_det call of this thread (split-K kernel + 0/1 slice fold + layout kernel)
+thread_local int g_last_wgrad_launches = 0;
+
 int check_launch(const char* what) {
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(B200SR_ECUDA, std::string(what) + ": " + cudaGetErrorString(e));
@@ -598,6 +601,8 @@ int b200sr_version(void) { return 100; }
 
 const char* b200sr_last_error(void) { return g_last_error.c_str(); }
 
+int b200sr_last_wgrad_launches(void) { return g_last_wgrad_launches; }
+
 int b200sr_device_ok(void) {
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) {
@@ -834,6 +839,7 @@ int launch_reduce_unpack(float* ws, int splits, long long split_stride, int T, i
         reduce_splits_inplace_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(reinterpret_cast<float4*>(ws), splits,
                                                                                    n4, n4, lanes);
     }
+    g_last_wgrad_launches = 2 + ((splits > 1 && !direct) ? 1 : 0);
     // stage 2b: kernel layout [t][inner][outer] -> PyTorch parameter layout
     const int ns = direct ? splits : 1;
     if (tiles > num_sms() * 8) tiles = num_sms() * 8;
