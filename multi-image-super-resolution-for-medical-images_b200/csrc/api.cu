@@ -429,14 +429,14 @@ int run_conv3(int mode, const void* a, int a_stride, int a_coff, int Ca, const v
 // wgrad launch
 // ---------------------------------------------------------------------------------------------
 // max_splits > 0: deterministic mode (partials of split s at args.out + s * args.split_stride), at most max_splits splits
-template <int N_TILE, int STAGES>
+template <int N_TILE, int STAGES, int KPIX = 32>
 int launch_wgrad_t(const CUtensorMap& mt, const CUtensorMap& mp, WGradArgs& args, cudaStream_t st, int max_splits = 0,
                    int* splits_out = nullptr) {
-    constexpr int smem = wg_smem_bytes<N_TILE, STAGES>();
+    constexpr int smem = wg_smem_bytes<N_TILE, STAGES, KPIX>();
     static bool configured = false;
     if (!configured) {
         cudaError_t e =
-            cudaFuncSetAttribute(wgrad_kernel<N_TILE, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            cudaFuncSetAttribute(wgrad_kernel<N_TILE, STAGES, KPIX>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return fail(B200SR_ECUDA, std::string("wgrad smem attribute: ") + cudaGetErrorString(e));
         configured = true;
     }
@@ -446,14 +446,15 @@ int launch_wgrad_t(const CUtensorMap& mt, const CUtensorMap& mp, WGradArgs& args
     const int groups = groups_x * groups_y;
     int target = 296;  // two waves of 148 SMs
     if (const char* env = getenv("B200SR_WGRAD_CTAS")) target = atoi(env) > 0 ? atoi(env) : target;
-    int splits = groups >= target ? 1 : (target + groups - 1) / groups;
+    // whole waves: never more CTAs than the target (upconv4: 32 groups x 10 splits = 320 CTAs was a third, mostly empty wave)
+    int splits = groups >= target ? 1 : target / groups;
     if (splits > args.total_chunks) splits = args.total_chunks;
     if (max_splits > 0 && splits > max_splits) splits = max_splits;
     args.chunks_per_cta = (args.total_chunks + splits - 1) / splits;
     splits = (args.total_chunks + args.chunks_per_cta - 1) / args.chunks_per_cta;
     if (splits_out != nullptr) *splits_out = splits;
     dim3 grid(groups_x, groups_y, splits);
-    wgrad_kernel<N_TILE, STAGES><<<grid, WG_THREADS, smem, st>>>(mt, mp, args);
+    wgrad_kernel<N_TILE, STAGES, KPIX><<<grid, WG_THREADS, smem, st>>>(mt, mp, args);
     return check_launch("wgrad_kernel");
 }
 
@@ -468,20 +469,23 @@ int run_wgrad(int t_mode, const void* t, int t_stride, int t_coff, int Ct, int n
     B2_CHECK_ARG(Ct % 64 == 0 && Cp % 64 == 0);
     B2_CHECK_ARG(t_stride % 8 == 0 && t_coff % 8 == 0 && p_stride % 8 == 0 && p_coff % 8 == 0);
     B2_CHECK_ARG(aligned16(t) && aligned16(p) && aligned16(G));
+    // pixel rows per pipeline stage: 4 for the N_TILE = 256 variant (64-pixel stages), 2 otherwise
+    static const bool k64 = getenv("B200SR_WGRAD_K32") == nullptr;
+    const int rows = (Cp % 256 == 0 && k64) ? 4 : 2;
     CUtensorMap mt, mp;
     int rc;
     if (t_mode == 0)
-        rc = make_act_map(&mt, t, t_stride, t_coff, Ct, B, H, W, 16, 2);
+        rc = make_act_map(&mt, t, t_stride, t_coff, Ct, B, H, W, 16, rows);
     else
-        rc = make_gather_map(&mt, t, t_stride, t_coff, Ct, B, H, W, 16, 2);
+        rc = make_gather_map(&mt, t, t_stride, t_coff, Ct, B, H, W, 16, rows);
     if (rc) return rc;
-    rc = make_act_map(&mp, p, p_stride, p_coff, Cp, B, H, W, 16, 2);
+    rc = make_act_map(&mp, p, p_stride, p_coff, Cp, B, H, W, 16, rows);
     if (rc) return rc;
     WGradArgs args;
     args.H = H;
     args.W = W;
     args.chunks_w = (W + 15) / 16;
-    args.chunks_hw = ((H + 1) / 2) * args.chunks_w;
+    args.chunks_hw = ((H + rows - 1) / rows) * args.chunks_w;
     args.total_chunks = B * args.chunks_hw;
     args.chunks_per_cta = args.total_chunks;
     args.t_mode = t_mode;
@@ -497,6 +501,7 @@ int run_wgrad(int t_mode, const void* t, int t_stride, int t_coff, int Ct, int n
         max_splits = static_cast<int>(ws_floats / args.split_stride < 4096 ? ws_floats / args.split_stride : 4096);
         B2_CHECK_ARG(max_splits >= 1);
     }
+    if (Cp % 256 == 0 && rows == 4) return launch_wgrad_t<256, 3, 64>(mt, mp, args, st, max_splits, splits_out);
     if (Cp % 256 == 0) return launch_wgrad_t<256, 6>(mt, mp, args, st, max_splits, splits_out);
     if (Cp % 128 == 0) return launch_wgrad_t<128, 5>(mt, mp, args, st, max_splits, splits_out);
     return launch_wgrad_t<64, 3>(mt, mp, args, st, max_splits, splits_out);

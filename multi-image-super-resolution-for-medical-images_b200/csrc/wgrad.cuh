@@ -22,8 +22,8 @@ namespace b200sr {
 
 struct WGradArgs {
     int H, W;            // spatial size of the pixel space (per image) the reduction runs over
-    int chunks_w;        // W / 16
-    int chunks_hw;       // (H / 2) * (W / 16)
+    int chunks_w;        // ceil(W / 16)
+    int chunks_hw;       // ceil(H / rows) * chunks_w, rows = KPIX / 16 pixel rows per pipeline stage
     int total_chunks;    // B * chunks_hw
     int chunks_per_cta;  // split-K slice length
     int t_mode;          // 0: 4-D taps on T (3x3: 9 taps, 1x1: 1 tap), 1: 5-D gather (4 taps)
@@ -36,30 +36,35 @@ struct WGradArgs {
 };
 
 constexpr int WG_THREADS = 256;
-constexpr int WG_KPIX = 32;          // pixels per pipeline stage (2 rows x 16 cols)
-constexpr int WG_ATOM_BYTES = 4096;  // 32 pixels x 64 ch x 2 B
-
+// KPIX = pixels per pipeline stage: 32 (2 rows x 16 cols) or 64 (4 rows x 16 cols; the N_TILE = 256 variant, whose stage then
+// carries 8 MMAs of 128 x 256 x 16 per barrier round trip instead of 4). One atom = KPIX pixels x 64 ch x 2 B.
+template <int KPIX>
+__host__ __device__ constexpr int wg_atom_bytes() {
+    return KPIX * 128;
+}
 template <int N_TILE>
 __host__ __device__ constexpr int wg_atoms_per_cta() {
     return 2 * (512 / N_TILE);
 }
-template <int N_TILE>
+template <int N_TILE, int KPIX>
 __host__ __device__ constexpr int wg_stage_bytes() {
-    return (wg_atoms_per_cta<N_TILE>() + N_TILE / 64) * WG_ATOM_BYTES;
+    return (wg_atoms_per_cta<N_TILE>() + N_TILE / 64) * wg_atom_bytes<KPIX>();
 }
-template <int N_TILE, int STAGES>
+template <int N_TILE, int STAGES, int KPIX>
 __host__ __device__ constexpr int wg_smem_bytes() {
-    return STAGES * wg_stage_bytes<N_TILE>() + 256 + 1024;
+    return STAGES * wg_stage_bytes<N_TILE, KPIX>() + 256 + 1024;
 }
 
-template <int N_TILE, int STAGES>
+template <int N_TILE, int STAGES, int KPIX>
 __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const __grid_constant__ CUtensorMap map_t,
                                                               const __grid_constant__ CUtensorMap map_p,
                                                               const WGradArgs args) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     constexpr int AT = wg_atoms_per_cta<N_TILE>();
-    constexpr int STAGE_BYTES = wg_stage_bytes<N_TILE>();
+    constexpr int STAGE_BYTES = wg_stage_bytes<N_TILE, KPIX>();
+    constexpr int WG_ATOM_BYTES = wg_atom_bytes<KPIX>();
+    constexpr int ROWS = KPIX / 16;
     constexpr int NB = N_TILE / 64;
     uint8_t* ring = smem;
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
@@ -109,7 +114,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const __grid_const
                 const int chunk = chunk_begin + it;
                 const int img = chunk / args.chunks_hw;
                 const int r = chunk - img * args.chunks_hw;
-                const int h0 = (r / args.chunks_w) * 2;
+                const int h0 = (r / args.chunks_w) * ROWS;
                 const int w0 = (r % args.chunks_w) * 16;
                 mbar_wait(&empty_bar[stage], phase ^ 1);
                 uint8_t* st = ring + stage * STAGE_BYTES;
@@ -153,7 +158,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const __grid_const
                 for (int mt = 0; mt < m_tiles; ++mt) {
                     const uint64_t da = umma_smem_desc_sw128(st + 2 * mt * WG_ATOM_BYTES, WG_ATOM_BYTES, 1024);
 #pragma unroll
-                    for (int k = 0; k < WG_KPIX / 16; ++k) {
+                    for (int k = 0; k < KPIX / 16; ++k) {
                         // 16 pixels = 16 rows of 128 B = 2048 B (>>4 = 128)
                         umma_bf16(tmem_base + mt * N_TILE, da + 128 * k, db + 128 * k, idesc, (it | k) != 0);
                     }
