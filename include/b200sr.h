@@ -391,6 +391,12 @@ int b200sr_maxpool2x2_bwd_bnred(const void* act, int act_pix_stride, int act_c_o
 /* 1x1 head backward with dw (64) / db (1) WRITTEN; ws: 72 floats per CTA (up to 4 CTAs per SM); counter: 1 uint32. */
 int b200sr_head_bwd_det(const float* dout, const void* act, const float* w, void* dact, float* dw, float* db,
                         int64_t npix, float* ws, int64_t ws_floats, uint32_t* counter, void* stream);
+/* b200sr_head_bwd_det fused with b200sr_bn_bwd_reduce_det of the BatchNorm+ReLU feeding the head (dec1.conv.4/.5,
+ * unet_model.py:76-80): dact (npix x 64) is written AND reduced against z in the same pass; sums[2][64] as
+ * b200sr_bn_bwd_reduce_det writes them. ws: 200 floats per CTA; counters: 2 uint32, zero-initialised once. */
+int b200sr_head_bwd_bnred(const float* dout, const void* act, const float* w, void* dact, float* dw, float* db,
+                          const void* z, const float* scale, const float* shift, const float* mean, const float* invstd,
+                          float* sums, int64_t npix, float* ws, int64_t ws_floats, uint32_t* counters, void* stream);
 /* Fused MSE + SSIM loss: out3 = {loss, mse, mean SSIM} (DEVICE f32) WRITTEN by the last CTA; ws: 2 doubles per CTA
  * (B * ceil(H/32) * ceil(W/32) CTAs); counter: 1 uint32. Nothing is left for the host to combine. */
 int b200sr_mse_ssim_det(const float* pred, const float* target, float* grad, float* out3, int B, int H, int W,

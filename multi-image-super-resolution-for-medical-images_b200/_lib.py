@@ -100,6 +100,7 @@ _SIGNATURES = {
     "b200sr_maxpool2x2_bwd_bnred": [_P, c_int, c_int, _P, _P, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, _P, c_int64,
                                     _P, c_int, c_int, c_int, _P],
     "b200sr_head_bwd_det": [_P, _P, _P, _P, _P, _P, c_int64, _P, c_int64, _P, _P],
+    "b200sr_head_bwd_bnred": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, _P, c_int64, _P, _P],
     "b200sr_mse_ssim_det": [_P, _P, _P, _P, c_int, c_int, c_int, _P, c_int, c_float, c_float, c_float, c_float, c_float,
                             _P, c_int64, _P, _P],
     "b200sr_adam_step_auto": [_P, _P, _P, _P, c_int64, c_float, c_float, c_float, c_float, _P, c_float, _P],
@@ -188,6 +189,8 @@ def _cost(name, a):
         return 0.0, a[14] * a[4] * 2.0 * 2
     if name == "b200sr_head_bwd_det":
         return 0.0, a[6] * (4.0 + 128 + 128)
+    if name == "b200sr_head_bwd_bnred":
+        return 0.0, a[12] * (4.0 + 128 + 128 + 128)   # dout, act and z read, dact written
     if name == "b200sr_mse_ssim_det":
         return 0.0, a[4] * a[5] * a[6] * 4.0 * (3 if a[2] else 2)
     if name == "b200sr_adam_step_auto":

@@ -975,6 +975,21 @@ int b200sr_head_bwd_det(const float* dout, const void* act, const float* w, void
     return check_launch("head_bwd_det_kernel");
 }
 
+int b200sr_head_bwd_bnred(const float* dout, const void* act, const float* w, void* dact, float* dw, float* db,
+                          const void* z, const float* scale, const float* shift, const float* mean, const float* invstd,
+                          float* sums, int64_t npix, float* ws, int64_t ws_floats, uint32_t* counters, void* stream) {
+    B2_CHECK_ARG(dout && act && w && dact && dw && db && z && scale && shift && mean && invstd && sums && ws && counters);
+    B2_CHECK_ARG(npix > 0 && aligned16(act) && aligned16(dact) && aligned16(w) && aligned16(z) && aligned16(ws));
+    long long slices = num_sms() * 3;
+    if (slices > (npix + 31) / 32) slices = (npix + 31) / 32;
+    if (slices > ws_floats / 200) slices = ws_floats / 200;  // 72 (head) + 128 (BatchNorm) floats per block
+    B2_CHECK_ARG(slices >= 1);  // (72 floats = 288 B per head slot: the BatchNorm slot area behind them stays 16-byte aligned)
+    head_bwd_bnred_kernel<<<dim3(static_cast<unsigned>(slices), 1), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        dout, static_cast<const __nv_bfloat16*>(act), w, static_cast<__nv_bfloat16*>(dact), dw, db,
+        static_cast<const __nv_bfloat16*>(z), scale, shift, mean, invstd, sums, ws, counters, npix);
+    return check_launch("head_bwd_bnred_kernel");
+}
+
 int b200sr_adam_step_auto(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
                           float eps, int32_t* step_dev, float grad_scale, void* stream) {
     B2_CHECK_ARG(p && g && m && v && n > 0 && step_dev);

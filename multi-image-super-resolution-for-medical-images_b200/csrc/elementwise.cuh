@@ -1439,6 +1439,95 @@ __global__ void __launch_bounds__(256) head_bwd_det_kernel(const float* __restri
 }
 
 
+// head_bwd_det_kernel that ALSO produces the BatchNorm+ReLU backward reduction (pass 1) of the layer feeding the head
+// (dec1.conv.3 -> BN -> ReLU -> final 1x1 conv, unet_model.py:76-80,113-117): the dact it writes is the tensor
+// bn_bwd_reduce_det would read back, so that pass (and its 2 B/element re-read of dact) disappears. Sums are taken from the
+// values as stored (bf16), like the two-kernel path. grid = (slices, 1), 64 channels: thread (tx = tid & 7, ty = tid >> 3)
+// owns channels 8 tx .. 8 tx + 7 of every slices-th group of 32 pixels. ws: [slices][72] head partials, then [slices][128]
+// BatchNorm partials; counters: [0] BatchNorm ticket (one channel group), [1] head ticket.
+__global__ void __launch_bounds__(256, 3) head_bwd_bnred_kernel(
+    const float* __restrict__ dout, const __nv_bfloat16* __restrict__ act, const float* __restrict__ w,
+    __nv_bfloat16* __restrict__ dact, float* __restrict__ dw, float* __restrict__ db, const __nv_bfloat16* __restrict__ z,
+    const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ mean,
+    const float* __restrict__ invstd, float* __restrict__ sums, float* __restrict__ ws, unsigned* __restrict__ counters,
+    long long npix) {
+    griddep_launch_dependents();
+    const int slices = gridDim.x, slice = blockIdx.x;
+    const int tx = threadIdx.x & 7, ty = threadIdx.x >> 3;
+    const int c = tx * 8;
+    const F8 wv = ld_f32x8(w + c), sc = ld_f32x8(scale + c), sh = ld_f32x8(shift + c), mu = ld_f32x8(mean + c);
+    float accw[8], s1[8], s2[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) accw[k] = s1[k] = s2[k] = 0.f;
+    float accb = 0.f;
+    constexpr int U = 2;
+    const long long step = static_cast<long long>(slices) * 32;
+    for (long long p0 = static_cast<long long>(slice) * 32 + ty; p0 < npix; p0 += step * U) {
+        float g[U];
+        uint4 ua[U], uz[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const long long p = p0 + u * step;
+            if (p < npix) {
+                g[u] = dout[p];
+                ua[u] = ld_stream(act + p * 64 + c);
+                uz[u] = ld_stream(z + p * 64 + c);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const long long p = p0 + u * step;
+            if (p < npix) {
+                const F8 a = unpack8(ua[u]), zf = unpack8(uz[u]);
+                F8 o;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    o.v[k] = bf16_round(g[u] * wv.v[k]);  // the gradient as stored
+                    accw[k] = fmaf(g[u], a.v[k], accw[k]);
+                    const float gm = fmaf(zf.v[k], sc.v[k], sh.v[k]) > 0.f ? o.v[k] : 0.f;
+                    s1[k] += gm;
+                    s2[k] = fmaf(gm, zf.v[k] - mu.v[k], s2[k]);
+                }
+                st_bf16x8(dact + p * 64 + c, o);
+                if (tx == 0) accb += g[u];
+            }
+        }
+    }
+    // ---- head partials: pixel lanes combined in lane order, slot per block, last block adds the slots in block order ----
+    {
+        __shared__ float s_h[32][66];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s_h[ty][c + k] = accw[k];
+        if (tx == 0) s_h[ty][64] = accb;
+        __syncthreads();
+        float* slot = ws + static_cast<size_t>(slice) * 72;
+        if (threadIdx.x < 65) {
+            float acc = 0.f;
+#pragma unroll 8
+            for (int r = 0; r < 32; ++r) acc += s_h[r][threadIdx.x];
+            slot[threadIdx.x] = acc;
+        }
+        if (last_block_ticket(counters + 1, static_cast<unsigned>(slices))) {
+            __shared__ float s_t[3][66];
+            const int o = threadIdx.x % 65, sl = threadIdx.x / 65;
+            if (sl < 3) {
+                float acc = 0.f;
+#pragma unroll 16
+                for (int r = sl; r < slices; r += 3) acc += __ldcg(ws + static_cast<size_t>(r) * 72 + o);
+                s_t[sl][o] = acc;
+            }
+            __syncthreads();
+            if (threadIdx.x < 65) {
+                const float t = s_t[0][threadIdx.x] + s_t[1][threadIdx.x] + s_t[2][threadIdx.x];
+                if (threadIdx.x < 64) dw[threadIdx.x] = t;
+                else *db = t;
+            }
+        }
+    }
+    // ---- BatchNorm backward sums (blockIdx.y == 0: one 64-channel group) ----
+    bn_red_block_finish(s1, s2, sums, ws + static_cast<size_t>(slices) * 72, counters, invstd, 64);
+}
+
 // ------------------------------------------------------------------------------------------------
 // fp32-accuracy eval mode: the bandwidth kernels around the SPLIT tensor-core convolutions (conv3x3.cuh). Activations
 // are (B,H,W,3C) bf16 [hi | lo | hi] with hi + lo the fp32 value to 2^-17 relative.

@@ -123,6 +123,9 @@ class UNetEngine:
         self.eval_graphs = os.environ.get("B200SR_NO_EVAL_GRAPH") is None
         self.fused_bn_finalize = os.environ.get("B200SR_NO_FUSED_BN") is None  # A/B switch: separate b200sr_bn_finalize launches
         self.fused_pool_bnred = os.environ.get("B200SR_NO_FUSED_POOL_BNRED") is None  # A/B switch: separate reduction pass
+        # opt-in: head backward fused with the BatchNorm-backward reduction of dec1.conv.3 — measured SLOWER than the two
+        # kernels (12.78 vs 12.67 ms per step, same box), kept as a tested alternative
+        self.fused_head_bnred = os.environ.get("B200SR_FUSED_HEAD_BNRED") is not None
         self._ab_full_stats = os.environ.get("B200SR_DGRAD_FULL_STATS") is not None  # A/B switch: sums + squares of all columns
         self._eval_graph_cache, self._eval_graph_calls = {}, {}
         self._hp = None
@@ -252,7 +255,7 @@ class UNetEngine:
         # workspaces of the deterministic reductions. Main-stream ops (BatchNorm backward, head) and side-stream ops
         # (weight gradients) never share one; ticket counters are zeroed once and reset by the kernels themselves.
         bn_ws_floats = max(int(call("b200sr_bn_bwd_ws_floats", cs.cout)) for cs in self.convs)
-        self.red_ws = torch.empty(max(bn_ws_floats, 4 * sms * 72), dtype=torch.float32, device=device)
+        self.red_ws = torch.empty(max(bn_ws_floats, 4 * sms * 72, 3 * sms * 200), dtype=torch.float32, device=device)
         self.red_counters = torch.zeros(64, dtype=torch.int32, device=device)
         self.bn_fwd_counters = torch.zeros(16 * len(self.convs), dtype=torch.int32, device=device)  # fused finalize tickets
         self.wg_ws = torch.empty(WGRAD_WS_FLOATS, dtype=torch.float32, device=device)
@@ -748,8 +751,17 @@ class UNetEngine:
 
         # head
         a_last = plan["dec_a2_0"]
-        call("b200sr_head_bwd_det", ptr(dout), ptr(a_last), ptr(fc.weight), s0, self._g(fc.weight), self._g(fc.bias),
-             B * H * W, ptr(self.red_ws), self.red_ws.numel(), ptr(self.red_counters) + 4 * 63, st)
+        head_sums_ready = self.fused_head_bnred
+        if head_sums_ready:
+            # 1x1 head backward + pass 1 of the BatchNorm backward of dec1.conv.3 (whose gradient it writes) in one kernel
+            cs = self.blocks["dec1"][1]
+            call("b200sr_head_bwd_bnred", ptr(dout), ptr(a_last), ptr(fc.weight), s0, self._g(fc.weight), self._g(fc.bias),
+                 ptr(plan["z:" + cs.name]), self._bn(cs, "scale"), self._bn(cs, "shift"), self._bn(cs, "mean"),
+                 self._bn(cs, "invstd"), self.bn_sums.data_ptr() + 4 * self.bn_sum_off[cs.name], B * H * W,
+                 ptr(self.red_ws), self.red_ws.numel(), ptr(self.red_counters) + 4 * 60, st)
+        else:
+            call("b200sr_head_bwd_det", ptr(dout), ptr(a_last), ptr(fc.weight), s0, self._g(fc.weight), self._g(fc.bias),
+                 B * H * W, ptr(self.red_ws), self.red_ws.numel(), ptr(self.red_counters) + 4 * 63, st)
         dy = s0  # gradient w.r.t. the current block's output activation (dense)
 
         def block_bwd(name, lvl, in_buf, in_stride, in_c, dx_dst, dx_stride, dx_stats, dy_ptr, x_input=None,
@@ -810,7 +822,8 @@ class UNetEngine:
             h, w, c = H >> lvl, W >> lvl, ch[lvl]
             dcat = plan[f"dcat{lvl}"]
             up_stats = self.up_stats.data_ptr() + 4 * self.up_st_off[k]
-            block_bwd(f"dec{k}", lvl, plan[f"cat{lvl}"], 2 * c, 2 * c, ptr(dcat), 2 * c, up_stats, dy)
+            block_bwd(f"dec{k}", lvl, plan[f"cat{lvl}"], 2 * c, 2 * c, ptr(dcat), 2 * c, up_stats, dy,
+                      sums_ready=(k == 1 and head_sums_ready))
             # ConvTranspose bias gradient = column sums of the upsampled half of dcat: per-CTA slots [sum | sumsq][2c]
             # from the dgrad epilogue, added in slot order
             call("b200sr_sum_slots", up_stats, n_slots, 2 * 2 * c, c, self._g(us.mod.bias), st)

@@ -837,6 +837,47 @@ def head_det(B=2, H=64, W=96, seed=11):
             "db": rel(runs[0][1][64:], b.grad), "bitwise": float((runs[0][1] - runs[1][1]).abs().max())}
 
 
+def head_bnred(B=2, H=64, W=96, seed=15):
+    """fused 1x1-head backward + BatchNorm-backward reduction of the layer feeding the head == the two separate kernels
+    (dact bit for bit, dw / db / sums to fp32 round-off) and bit-reproducible."""
+    _setup()
+    C = 64
+    z = bf(rnd(B, C, H, W, seed=seed) * 1.5 + 0.3)
+    gamma, beta = 1 + 0.1 * rnd(C, seed=seed + 1), 0.1 * rnd(C, seed=seed + 2)
+    mean = z.mean(dim=(0, 2, 3))
+    invstd = torch.rsqrt(z.var(dim=(0, 2, 3), unbiased=False) + 1e-5)
+    scale, shift = (gamma * invstd).contiguous(), (beta - mean * gamma * invstd).contiguous()
+    act = bf(torch.relu(z * scale[None, :, None, None] + shift[None, :, None, None]))
+    w = rnd(1, 64, 1, 1, seed=seed + 3, scale=0.125)
+    dout = rnd(B, 1, H, W, seed=seed + 4)
+    ab, zb = nhwc(act), nhwc(z)
+    N = B * H * W
+    nws = int(call("b200sr_bn_bwd_ws_floats", C))
+    counters = torch.zeros(64, dtype=torch.int32, device=DEV)
+    # reference: the two separate kernels
+    dact_ref = torch.zeros(B, H, W, 64, dtype=torch.bfloat16, device=DEV)
+    dwb_ref, ws = _garbage(65), _garbage(4 * SLOTS * 72)
+    call("b200sr_head_bwd_det", ptr(dout), ptr(ab), ptr(w), ptr(dact_ref), ptr(dwb_ref), ptr(dwb_ref) + 4 * 64, N,
+         ptr(ws), ws.numel(), ptr(counters) + 4 * 63, st())
+    sums_ref, ws1 = _garbage(2, C), _garbage(nws)
+    call("b200sr_bn_bwd_reduce_det", ptr(dact_ref), C, 0, ptr(zb), C, ptr(scale), ptr(shift), ptr(mean), ptr(invstd),
+         ptr(sums_ref), ptr(ws1), nws, ptr(counters), None, N, st())
+    runs = []
+    for _ in range(2):
+        dact = torch.zeros(B, H, W, 64, dtype=torch.bfloat16, device=DEV)
+        dwb, sums, ws2 = _garbage(65), _garbage(2, C), _garbage(3 * SLOTS * 200)
+        call("b200sr_head_bwd_bnred", ptr(dout), ptr(ab), ptr(w), ptr(dact), ptr(dwb), ptr(dwb) + 4 * 64, ptr(zb),
+             ptr(scale), ptr(shift), ptr(mean), ptr(invstd), ptr(sums), N, ptr(ws2), ws2.numel(), ptr(counters) + 4 * 60,
+             st())
+        torch.cuda.synchronize()
+        runs.append((dact, dwb, sums))
+    return {"dact_exact": float((runs[0][0].float() - dact_ref.float()).abs().max()),
+            "dw": rel(runs[0][1][:64], dwb_ref[:64]), "db": rel(runs[0][1][64:], dwb_ref[64:]),
+            "sums": rel(runs[0][2], sums_ref), "counters_reset": float(counters.abs().max()),
+            "bitwise": float((runs[0][0].float() - runs[1][0].float()).abs().max() + (runs[0][1] - runs[1][1]).abs().max()
+                             + (runs[0][2] - runs[1][2]).abs().max())}
+
+
 def mse_ssim_det(B=3, H=96, W=80, seed=12):
     """the loss module runs on the deterministic kernel: value, components and gradient identical over two calls."""
     _setup()
@@ -1094,6 +1135,12 @@ CHECKS = {
     "det_bn_bwd_c64_large": (bn_bwd_det, dict(C=64, B=4, H=128, W=96),
                              {"dz": BF16, "dgamma": 1e-3, "dbeta": 1e-3, "counters_reset": 0.0, "bitwise": 0.0}),
     "det_head": (head_det, {}, {"dact": BF16, "dw": 1e-4, "db": 1e-4, "bitwise": 0.0}),
+    "fused_head_bwd_bnred": (head_bnred, {}, {"dact_exact": 0.0, "dw": 1e-5, "db": 1e-5, "sums": 1e-5, "counters_reset": 0.0,
+                                              "bitwise": 0.0}),
+    "fused_head_bwd_bnred_large": (head_bnred, dict(B=4, H=256, W=256), {"dact_exact": 0.0, "dw": 1e-5, "db": 1e-5,
+                                                                        "sums": 1e-5, "counters_reset": 0.0, "bitwise": 0.0}),
+    "fused_head_bwd_bnred_ragged": (head_bnred, dict(B=3, H=5, W=3), {"dact_exact": 0.0, "dw": 1e-5, "db": 1e-5,
+                                                                      "sums": 1e-5, "counters_reset": 0.0, "bitwise": 0.0}),
     "det_mse_ssim": (mse_ssim_det, {}, {"bitwise": 0.0, "mse_component": 1e-5, "loss_consistent": 1e-6}),
     "det_adam_auto": (adam_auto, {}, {"delta": 1e-3, "m": 1e-5, "v": 1e-4, "step_count": 0}),
     "det_sum_slots": (sum_slots, {}, {"sum": 1e-6}),
