@@ -980,7 +980,7 @@ int b200sr_head_bwd_bnred(const float* dout, const void* act, const float* w, vo
                           float* sums, int64_t npix, float* ws, int64_t ws_floats, uint32_t* counters, void* stream) {
     B2_CHECK_ARG(dout && act && w && dact && dw && db && z && scale && shift && mean && invstd && sums && ws && counters);
     B2_CHECK_ARG(npix > 0 && aligned16(act) && aligned16(dact) && aligned16(w) && aligned16(z) && aligned16(ws));
-    long long slices = num_sms() * 3;
+    long long slices = num_sms() * 2;
     if (slices > (npix + 31) / 32) slices = (npix + 31) / 32;
     if (slices > ws_floats / 200) slices = ws_floats / 200;  // 72 (head) + 128 (BatchNorm) floats per block
     B2_CHECK_ARG(slices >= 1);  // (72 floats = 288 B per head slot: the BatchNorm slot area behind them stays 16-byte aligned)

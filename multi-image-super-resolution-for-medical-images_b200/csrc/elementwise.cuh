@@ -1445,7 +1445,7 @@ __global__ void __launch_bounds__(256) head_bwd_det_kernel(const float* __restri
 // values as stored (bf16), like the two-kernel path. grid = (slices, 1), 64 channels: thread (tx = tid & 7, ty = tid >> 3)
 // owns channels 8 tx .. 8 tx + 7 of every slices-th group of 32 pixels. ws: [slices][72] head partials, then [slices][128]
 // BatchNorm partials; counters: [0] BatchNorm ticket (one channel group), [1] head ticket.
-__global__ void __launch_bounds__(256, 3) head_bwd_bnred_kernel(
+__global__ void __launch_bounds__(256, 2) head_bwd_bnred_kernel(
     const float* __restrict__ dout, const __nv_bfloat16* __restrict__ act, const float* __restrict__ w,
     __nv_bfloat16* __restrict__ dact, float* __restrict__ dw, float* __restrict__ db, const __nv_bfloat16* __restrict__ z,
     const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ mean,
@@ -1460,7 +1460,7 @@ __global__ void __launch_bounds__(256, 3) head_bwd_bnred_kernel(
 #pragma unroll
     for (int k = 0; k < 8; ++k) accw[k] = s1[k] = s2[k] = 0.f;
     float accb = 0.f;
-    constexpr int U = 2;
+    constexpr int U = 4;  // four pixels in flight per thread (two spilled registers at three blocks per SM)
     const long long step = static_cast<long long>(slices) * 32;
     for (long long p0 = static_cast<long long>(slice) * 32 + ty; p0 < npix; p0 += step * U) {
         float g[U];

@@ -123,9 +123,9 @@ class UNetEngine:
         self.eval_graphs = os.environ.get("B200SR_NO_EVAL_GRAPH") is None
         self.fused_bn_finalize = os.environ.get("B200SR_NO_FUSED_BN") is None  # A/B switch: separate b200sr_bn_finalize launches
         self.fused_pool_bnred = os.environ.get("B200SR_NO_FUSED_POOL_BNRED") is None  # A/B switch: separate reduction pass
-        # opt-in: head backward fused with the BatchNorm-backward reduction of dec1.conv.3 — measured SLOWER than the two
-        # kernels (12.78 vs 12.67 ms per step, same box), kept as a tested alternative
-        self.fused_head_bnred = os.environ.get("B200SR_FUSED_HEAD_BNRED") is not None
+        # head backward fused with the BatchNorm-backward reduction of dec1.conv.3 (-0.1 ms per step once the kernel ran
+        # without register spills); A/B switch: B200SR_NO_FUSED_HEAD_BNRED=1 -> the two separate kernels
+        self.fused_head_bnred = os.environ.get("B200SR_NO_FUSED_HEAD_BNRED") is None
         self._ab_full_stats = os.environ.get("B200SR_DGRAD_FULL_STATS") is not None  # A/B switch: sums + squares of all columns
         self._eval_graph_cache, self._eval_graph_calls = {}, {}
         self._hp = None
